@@ -1,0 +1,147 @@
+"""Readers for the typing database files, producing the same containers the reference builds in
+genotyping_locus (reference hisatgenotype_modules/hisatgenotype_typing_core.py:2417-2485).
+
+Each reader takes the *text* of a file so that tests can feed fixtures without touching disk;
+`load_database(prefix)` reads the files of `<ix_dir>/<base>`.
+
+  read_locus        <- hisatgenotype_typing_common.py:279-309   (.locus, 7 columns, non-genome form)
+  read_variants     <- hisatgenotype_typing_common.py:339-368   (.snp)
+  read_links        <- hisatgenotype_typing_common.py:388-403   (.link)
+  read_backbone     <- hisatgenotype_typing_common.py:313-334   (_backbone.fa)
+  build_genes       <- hisatgenotype_typing_core.py:2199-2237, 2462-2485
+"""
+from __future__ import annotations
+
+import os
+
+
+def read_locus(text):
+    refGenes, refGene_loci = {}, {}
+    for line in text.strip("\n").split("\n"):
+        if not line.strip():
+            continue
+        name, chrom, left, right, _, exon_str, _strand = line.split()
+        gene = name.split("*")[0]
+        assert gene not in refGenes
+        refGenes[gene] = name
+        exons, primary = [], []
+        for ex in exon_str.split(","):
+            is_primary = ex.endswith("p")
+            if is_primary:
+                ex = ex[:-1]
+            a, b = ex.split("-")
+            exons.append([int(a), int(b)])
+            if is_primary:
+                primary.append([int(a), int(b)])
+        refGene_loci[gene] = [name, chrom, int(left), int(right), exons, primary]
+    return refGenes, refGene_loci
+
+
+def read_variants(text):
+    Vars, Var_list = {}, {}
+    for line in text.strip("\n").split("\n"):
+        if not line:
+            continue
+        var_id, var_type, name, pos, data = line.split("\t")
+        gene = name.split("*")[0]
+        Vars.setdefault(gene, {})
+        Var_list.setdefault(gene, [])
+        assert var_id not in Vars[gene]
+        Vars[gene][var_id] = [var_type, int(pos), data]
+        Var_list[gene].append([int(pos), var_id])
+    for gene in Var_list:
+        Var_list[gene].sort(key=lambda x: x[0])  # stable: file order inside one position
+    return Vars, Var_list
+
+
+def read_links(text):
+    links = {}
+    for line in text.strip("\n").split("\n"):
+        if not line:
+            continue
+        cols = line.replace(" ", "\t").split("\t")
+        assert cols[0] not in links
+        links[cols[0]] = cols[1:]
+    return links
+
+
+def read_backbone(text):
+    Genes = {}
+    for chunk in text.strip("\n").split(">")[1:]:
+        nl = chunk.find("\n")
+        name = chunk[:nl]
+        gene = name.split("*")[0]
+        Genes.setdefault(gene, {})
+        if name in Genes[gene]:
+            raise SystemExit("Error: Nonunique sequence name: %s" % name)
+        Genes[gene][name] = chunk[nl:].replace("\n", "")
+    return Genes
+
+
+def build_genes(Genes, Vars, Var_list, Links, allele_names):
+    """Allele sequences = backbone + linked variants; then alleles identical to the backbone."""
+    for gene in Genes:
+        assert len(Genes[gene]) == 1
+        bb_name, bb = list(Genes[gene].items())[0]
+        gene_vars = Vars.get(gene, {})
+        allele_vars = {}
+        for _, var_id in Var_list.get(gene, []):
+            for allele in Links.get(var_id, []):
+                allele_vars.setdefault(allele, []).append(var_id)
+        for allele, ids in allele_vars.items():
+            out, prev = [], 0
+            for var_id in ids:
+                t, pos, data = gene_vars[var_id]
+                assert prev <= pos
+                if pos > prev:
+                    out.append(bb[prev:pos])
+                if t == "single":
+                    out.append(data)
+                    prev = pos + 1
+                elif t == "deletion":
+                    prev = pos + int(data)
+                else:
+                    assert t == "insertion"
+                    out.append(data)
+                    prev = pos
+            if prev < len(bb):
+                out.append(bb[prev:])
+            Genes[gene][allele] = "".join(out)
+        if len(Genes[gene]) <= 1:
+            Genes[gene]["%s*GRCh38" % gene] = bb
+    # alleles only listed in .allele are identical to the backbone (core:2462-2467).  The reference
+    # iterates a Python set here, so their relative order is unpinned; sorted order is used.
+    for allele in sorted(allele_names):
+        gene = allele.split("*")[0]
+        assert gene in Genes
+        if allele not in Genes[gene]:
+            Genes[gene][allele] = Genes[gene]["%s*BACKBONE" % gene]
+    Gene_names = {g: list(d.keys()) for g, d in Genes.items()}
+    Gene_lengths = {g: {a: len(s) for a, s in d.items()} for g, d in Genes.items()}
+    return Gene_names, Gene_lengths
+
+
+def load_database_text(db):
+    """db: {'.locus': text, '.snp': text, '.link': text, '_backbone.fa': text, '.allele': text, '.partial': text}"""
+    refGenes, refGene_loci = read_locus(db[".locus"])
+    Vars, Var_list = read_variants(db[".snp"])
+    Links = read_links(db[".link"])
+    Genes = read_backbone(db["_backbone.fa"])
+    alleles = [l.strip() for l in db[".allele"].split("\n") if l.strip()]
+    partial = set(l.strip() for l in db.get(".partial", "").split("\n") if l.strip())
+    for gene in refGene_loci:
+        if gene not in Vars:
+            Vars[gene], Var_list[gene] = {}, []
+    Gene_names, Gene_lengths = build_genes(Genes, Vars, Var_list, Links, alleles)
+    return dict(refGenes=refGenes, refGene_loci=refGene_loci, Vars=Vars, Var_list=Var_list, Links=Links,
+                Genes=Genes, Gene_names=Gene_names, Gene_lengths=Gene_lengths, partial_alleles=partial)
+
+
+def load_database(prefix):
+    db = {}
+    for ext in ["_backbone.fa", ".locus", ".snp", ".link", ".allele", ".partial"]:
+        path = prefix + ext
+        if not os.path.exists(path):
+            raise SystemExit("Error: index files missing (%s)" % path)
+        db[ext] = open(path).read()
+    return load_database_text(db)
