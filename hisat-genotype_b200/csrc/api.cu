@@ -1,0 +1,65 @@
+// Context, error plumbing and small helpers of libhgt.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+static thread_local char g_err[1024] = "";
+
+void hgt_set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *hgt_last_error(void) { return g_err; }
+extern "C" int hgt_abi_version(void) { return 1; }
+extern "C" int hgt_row_pitch(int n_alleles) {
+    int w = (n_alleles + 63) / 64;
+    if (w < 2) w = 2;
+    return (w + 1) & ~1;
+}
+
+extern "C" int hgt_init(int device, hgt_ctx **out) {
+    if (!out) {
+        hgt_set_error("hgt_init: out is null");
+        return HGT_ERR_ARG;
+    }
+    *out = nullptr;
+    int n = 0;
+    HGT_CUDA(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) {
+        hgt_set_error("hgt_init: device %d out of range (%d visible)", device, n);
+        return HGT_ERR_ARG;
+    }
+    HGT_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    HGT_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        hgt_set_error("hgt_init: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                      prop.major, prop.minor);
+        return HGT_ERR_UNSUPPORTED;
+    }
+    hgt_ctx *c = new hgt_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        hgt_set_error("cudaStreamCreate: %s", cudaGetErrorString(e));
+        delete c;
+        return HGT_ERR_CUDA;
+    }
+    *out = c;
+    return HGT_OK;
+}
+
+extern "C" void hgt_free(hgt_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+extern "C" int64_t hgt_launch_count(const hgt_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int hgt_sm_count(const hgt_ctx *ctx) { return ctx ? ctx->sm_count : 0; }

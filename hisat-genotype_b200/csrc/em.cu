@@ -1,0 +1,728 @@
+// Stage (b): EM abundance with SQUAREM acceleration, whole loop inside one kernel launch.
+//
+// Replaces single_abundance() of the reference
+//   (hisatgenotype_modules/hisatgenotype_typing_common.py:1282-1410; matrix form in SURVEY.md appendix A.9).
+//
+// Data layout in HBM: class x allele membership as a row-major bit matrix bits[C][wp] (uint64 words, wp even
+// so a row slab is a multiple of 16 bytes and moves with one cp.async.bulk / TMA bulk copy), class counts
+// cnt[C] (double), optional allele lengths len[A].  Probability vectors are A doubles and live in a small
+// global workspace that stays L2-resident; the vector a pass reads is staged in shared memory.
+//
+// One next_prob() evaluation = one sweep over the bit matrix.  A CTA owns a contiguous range of class rows and
+// walks it in slabs that are bulk-copied into shared memory; while a slab is resident BOTH halves of the E/M
+// step run on it:
+//   phase 1 (warp per class row)   s_k = sum_{a in S_k} p[a],  w_k = n_k / s_k
+//   phase 2 (thread per allele)    acc[a] += w_k for every row of the slab that has bit a set
+// so the matrix is read from HBM/L2 once per next_prob() (algorithmic bytes 3*C*(wp*8+8)+6*A*8 per loop
+// iteration).  If a CTA's rows fit its slab buffer they are loaded once and stay in shared
+// memory for every iteration (small loci: zero HBM traffic inside the loop).
+//
+// Two launch shapes share the code: batched (grid = problems, one CTA each) and cooperative (grid = one CTA
+// per SM on ONE problem; partial accumulators are reduced through global memory in a fixed order with two
+// grid syncs per sweep, so results are bit-reproducible run to run).  All sums use a fixed association.
+#include <cooperative_groups.h>
+#include <math.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int EM_THREADS = 1024;
+constexpr int EM_WARPS = EM_THREADS / 32;
+constexpr int MODE_INIT = 0, MODE_NEXT = 1, MODE_FIRSTK = 2;
+constexpr int32_t FK_NONE = 0x7fffffff;
+
+struct EmArgs {
+    const uint64_t *bits;
+    const double *cnt;
+    const double *len;
+    int C, A, wp, remove_low, fixed_iters;
+    int slab_rows;  // rows per slab buffer
+    double *prob;
+    uint8_t *in_result;
+    int32_t *first_class;
+    int32_t *iters_status;  // [3]: iters, status, sweeps
+    // workspace
+    double *vec;     // 4 x [Apad]
+    uint8_t *live;   // 4 x [Apad]
+    double *part_acc;   // [G][Apad]   (cooperative only)
+    int32_t *part_aux;  // [G][Apad]   hit flag or first-class index
+    double *red_acc;    // [Apad]
+    int32_t *red_aux;   // [Apad]
+};
+
+struct Smem {
+    uint64_t *mbar;
+    double *red;
+    double *p;
+    double *w;
+    uint8_t *valid;
+    uint64_t *slab;
+};
+
+__device__ __forceinline__ double block_sum(double v, double *red) {
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double x = red[lane];  // EM_WARPS == 32
+        x = warp_sum(x);
+        if (lane == 0) red[32] = x;
+    }
+    __syncthreads();
+    double r = red[32];
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ double block_max(double v, double *red) {
+    v = warp_max(v);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        double x = red[lane];
+        x = warp_max(x);
+        if (lane == 0) red[32] = x;
+    }
+    __syncthreads();
+    double r = red[32];
+    __syncthreads();
+    return r;
+}
+__device__ __forceinline__ int block_or(int v) { return __syncthreads_or(v); }
+
+// One sweep over this CTA's class rows.  mode INIT: initial mass (common:1299-1309); NEXT: next_prob
+// (common:1311-1336); FIRSTK: only the dict insertion order of next_prob's output.
+template <int NA, bool COOP>
+__device__ void em_sweep(const EmArgs &a, const Smem &sm, int mode, const double *pin, const uint8_t *livein,
+                         double *pout, uint8_t *liveout, int32_t *fkout, int row_lo, int row_hi, bool resident,
+                         bool &loaded, uint32_t &parity, int *status) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int A = a.A, wp = a.wp;
+    const int Apad = wp * 64;
+    // stage the input vector (0 for alleles that are not keys of the input dict)
+    if (mode != MODE_INIT) {
+        for (int i = tid; i < Apad; i += EM_THREADS) sm.p[i] = (i < A && livein[i]) ? pin[i] : 0.0;
+    }
+    double acc[NA];
+    int32_t fk[NA];
+    uint32_t hit = 0;
+#pragma unroll
+    for (int i = 0; i < NA; i++) {
+        acc[i] = 0.0;
+        fk[i] = FK_NONE;
+    }
+    __syncthreads();
+    const uint32_t *slab32 = reinterpret_cast<const uint32_t *>(sm.slab);
+    for (int r0 = row_lo; r0 < row_hi; r0 += a.slab_rows) {
+        const int nr = min(a.slab_rows, row_hi - r0);
+        if (!(resident && loaded)) {
+            if (tid == 0) {
+                const uint32_t bytes = (uint32_t)nr * (uint32_t)wp * 8u;
+                mbar_expect_tx(sm.mbar, bytes);
+                bulk_g2s(sm.slab, a.bits + (size_t)r0 * wp, bytes, sm.mbar);
+            }
+            mbar_wait(sm.mbar, parity);
+            parity ^= 1u;
+            loaded = true;
+        }
+        // ---- phase 1: warp per row ---------------------------------------------------------------------
+        for (int r = warp; r < nr; r += EM_WARPS) {
+            const uint64_t *row = sm.slab + (size_t)r * wp;
+            double s = 0.0;
+            if (mode == MODE_INIT) {
+                int pc = 0;
+                for (int j = lane; j < wp; j += 32) pc += __popcll(row[j]);
+                for (int o = 16; o > 0; o >>= 1) pc += __shfl_xor_sync(0xffffffffu, pc, o);
+                s = (double)pc;
+            } else {
+                for (int j = 0; j < wp; j++) {
+                    const uint64_t word = row[j];  // same address in all lanes: broadcast
+                    if (word == 0) continue;
+                    if ((word >> lane) & 1ull) s += sm.p[j * 64 + lane];
+                    if ((word >> (lane + 32)) & 1ull) s += sm.p[j * 64 + 32 + lane];
+                }
+                s = warp_sum(s);
+            }
+            if (lane == 0) {
+                const bool ok = s > 0.0;
+                sm.valid[r] = ok ? 1 : 0;
+                sm.w[r] = ok ? a.cnt[r0 + r] / s : 0.0;
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: thread per allele column -----------------------------------------------------------
+        if (mode == MODE_FIRSTK) {
+            for (int r = 0; r < nr; r++) {
+                if (!sm.valid[r]) continue;
+#pragma unroll
+                for (int i = 0; i < NA; i++) {
+                    const int al = tid + i * EM_THREADS;
+                    if (al < A && fk[i] == FK_NONE) {
+                        const uint32_t w32 = slab32[(size_t)r * wp * 2 + (al >> 5)];
+                        if ((w32 >> (al & 31)) & 1u) fk[i] = r0 + r;
+                    }
+                }
+            }
+        } else {
+            for (int r = 0; r < nr; r++) {
+                if (!sm.valid[r]) continue;
+                const double w = sm.w[r];
+#pragma unroll
+                for (int i = 0; i < NA; i++) {
+                    const int al = tid + i * EM_THREADS;
+                    if (al < Apad) {
+                        const uint32_t w32 = slab32[(size_t)r * wp * 2 + (al >> 5)];
+                        if ((w32 >> (al & 31)) & 1u) {
+                            acc[i] += w;
+                            hit |= 1u << i;
+                        }
+                    }
+                }
+            }
+        }
+        __syncthreads();
+    }
+    // ---- cross-CTA reduction (cooperative launch only) ------------------------------------------------------
+    if (COOP) {
+        cg::grid_group grid = cg::this_grid();
+        const int G = gridDim.x, g = blockIdx.x;
+#pragma unroll
+        for (int i = 0; i < NA; i++) {
+            const int al = tid + i * EM_THREADS;
+            if (al < A) {
+                a.part_acc[(size_t)g * Apad + al] = acc[i];
+                a.part_aux[(size_t)g * Apad + al] = (mode == MODE_FIRSTK) ? fk[i] : (int32_t)((hit >> i) & 1u);
+            }
+        }
+        grid.sync();
+        const int Ag = (A + G - 1) / G;
+        const int a_lo = g * Ag, a_hi = min(A, a_lo + Ag);
+        for (int al = a_lo + warp; al < a_hi; al += EM_WARPS) {
+            double s = 0.0;
+            int32_t x = (mode == MODE_FIRSTK) ? FK_NONE : 0;
+            for (int gg = lane; gg < G; gg += 32) {
+                s += a.part_acc[(size_t)gg * Apad + al];
+                const int32_t y = a.part_aux[(size_t)gg * Apad + al];
+                x = (mode == MODE_FIRSTK) ? min(x, y) : (x | y);
+            }
+            s = warp_sum(s);
+            for (int o = 16; o > 0; o >>= 1) {
+                const int32_t y = __shfl_xor_sync(0xffffffffu, x, o);
+                x = (mode == MODE_FIRSTK) ? min(x, y) : (x | y);
+            }
+            if (lane == 0) {
+                a.red_acc[al] = s;
+                a.red_aux[al] = x;
+            }
+        }
+        grid.sync();
+        hit = 0;
+#pragma unroll
+        for (int i = 0; i < NA; i++) {
+            const int al = tid + i * EM_THREADS;
+            if (al < A) {
+                acc[i] = a.red_acc[al];
+                const int32_t x = a.red_aux[al];
+                if (mode == MODE_FIRSTK) fk[i] = x;
+                else if (x) hit |= 1u << i;
+            }
+        }
+    }
+    if (mode == MODE_FIRSTK) {
+#pragma unroll
+        for (int i = 0; i < NA; i++) {
+            const int al = tid + i * EM_THREADS;
+            if (al < A) fkout[al] = livein[al] ? fk[i] : FK_NONE;
+        }
+        __syncthreads();
+        return;
+    }
+    // ---- q = p * acc, keys = live & hit, normalize (common:1285-1297) ----------------------------------------
+    double part = 0.0;
+    int nkeys = 0;
+#pragma unroll
+    for (int i = 0; i < NA; i++) {
+        const int al = tid + i * EM_THREADS;
+        bool key = false;
+        double q = 0.0;
+        if (al < A) {
+            key = ((hit >> i) & 1u) && (mode == MODE_INIT || livein[al]);
+            if (key) {
+                q = (mode == MODE_INIT) ? acc[i] : sm.p[al] * acc[i];
+                if (a.len) q = q / a.len[al];
+                part += q;
+                nkeys = 1;
+            }
+        }
+        acc[i] = q;
+        hit = key ? (hit | (1u << i)) : (hit & ~(1u << i));
+    }
+    const double total = block_sum(part, sm.red);
+    const int any = block_or(nkeys);
+    if (any && !(total > 0.0) && !(total < 0.0)) {
+        if (tid == 0) *status = HGT_ERR_ZERODIV;
+    }
+#pragma unroll
+    for (int i = 0; i < NA; i++) {
+        const int al = tid + i * EM_THREADS;
+        if (al < A) {
+            const bool key = (hit >> i) & 1u;
+            pout[al] = key ? acc[i] / total : 0.0;
+            liveout[al] = key ? 1 : 0;
+        }
+    }
+    __syncthreads();
+}
+
+// select_alleles (common:1338-1346): keep p >= max/10
+__device__ void em_prune(const EmArgs &a, const Smem &sm, double *p, uint8_t *live) {
+    double mx = -1.0;
+    for (int al = threadIdx.x; al < a.A; al += EM_THREADS)
+        if (live[al]) mx = fmax(mx, p[al]);
+    mx = block_max(mx, sm.red);
+    if (mx < 0.0) return;
+    const double thr = mx / 10.0;
+    for (int al = threadIdx.x; al < a.A; al += EM_THREADS) {
+        if (live[al] && !(p[al] >= thr)) {
+            live[al] = 0;
+            p[al] = 0.0;
+        }
+    }
+    __syncthreads();
+}
+
+template <int NA, bool COOP>
+__global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restrict__ args_arr) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const EmArgs a = COOP ? args_arr[0] : args_arr[blockIdx.x];
+    const int tid = threadIdx.x;
+    const int Apad = a.wp * 64;
+    Smem sm;
+    sm.mbar = reinterpret_cast<uint64_t *>(smem_raw);
+    sm.red = reinterpret_cast<double *>(smem_raw + 16);
+    sm.p = sm.red + 40;
+    sm.w = sm.p + Apad;
+    sm.slab = reinterpret_cast<uint64_t *>(sm.w + a.slab_rows);  // offset stays a multiple of 16 (slab_rows even)
+    sm.valid = reinterpret_cast<uint8_t *>(sm.slab + (size_t)a.slab_rows * a.wp);
+    if (tid == 0) {
+        mbar_init(sm.mbar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    int row_lo = 0, row_hi = a.C;
+    if (COOP) {
+        const int G = gridDim.x;
+        const int per = (a.C + G - 1) / G;
+        row_lo = min(a.C, (int)blockIdx.x * per);
+        row_hi = min(a.C, row_lo + per);
+    }
+    const bool resident = (row_hi - row_lo) <= a.slab_rows;
+    bool loaded = false;
+    uint32_t parity = 0;
+    __shared__ int s_status;
+    if (tid == 0) s_status = HGT_OK;
+    __syncthreads();
+    double *v0 = a.vec, *v1 = a.vec + Apad, *v2 = a.vec + 2 * (size_t)Apad, *v3 = a.vec + 3 * (size_t)Apad;
+    uint8_t *l0 = a.live, *l1 = a.live + Apad, *l2 = a.live + 2 * (size_t)Apad;
+    // In cooperative mode every CTA computes the same vectors and writes identical values to the shared
+    // workspace; reads of those values are ordered by the sweep's grid syncs / __syncthreads.
+    em_sweep<NA, COOP>(a, sm, MODE_INIT, nullptr, nullptr, v0, l0, nullptr, row_lo, row_hi, resident, loaded,
+                       parity, &s_status);
+    double diff = 1.0;
+    int iter = 0, sweeps = 0;
+    const double *last_in = v0;
+    const uint8_t *last_live = l0;
+    bool have_last = false;
+    while (a.fixed_iters > 0 ? iter < a.fixed_iters : (diff > 0.0001 && iter < 1000)) {
+        if (s_status != HGT_OK) break;
+        em_sweep<NA, COOP>(a, sm, MODE_NEXT, v0, l0, v1, l1, nullptr, row_lo, row_hi, resident, loaded, parity,
+                           &s_status);
+        em_sweep<NA, COOP>(a, sm, MODE_NEXT, v1, l1, v2, l2, nullptr, row_lo, row_hi, resident, loaded, parity,
+                           &s_status);
+        sweeps += 2;
+        // SQUAREM extrapolation (common:1361-1383)
+        double ssr = 0.0, ssv = 0.0;
+        int keyerr = 0;
+        for (int al = tid; al < a.A; al += EM_THREADS) {
+            if (l0[al]) {
+                if (!l1[al] || !l2[al]) keyerr = 1;
+                const double r = v1[al] - v0[al];
+                const double v = v2[al] - v1[al] - r;
+                ssr += r * r;
+                ssv += v * v;
+            }
+        }
+        ssr = block_sum(ssr, sm.red);
+        ssv = block_sum(ssv, sm.red);
+        if (block_or(keyerr)) {
+            if (tid == 0) s_status = HGT_ERR_KEY;
+            __syncthreads();
+            break;
+        }
+        if (ssv > 0.0) {
+            // extrapolated vector goes to a 4th buffer: slower CTAs may still be reading v2 (cooperative mode)
+            const double g = -sqrt(ssr / ssv);
+            for (int al = tid; al < a.A; al += EM_THREADS) {
+                double x = 0.0;
+                if (l0[al]) {
+                    const double r = v1[al] - v0[al];
+                    const double v = v2[al] - v1[al] - r;
+                    x = v0[al] - 2 * g * r + g * g * v;
+                    x = x > 0.0 ? x : 0.0;
+                }
+                v3[al] = x;
+            }
+            __syncthreads();
+            em_sweep<NA, COOP>(a, sm, MODE_NEXT, v3, l2, v1, l1, nullptr, row_lo, row_hi, resident, loaded,
+                               parity, &s_status);
+            sweeps += 1;
+            last_in = v3;
+            last_live = l2;
+        } else {
+            last_in = v0;
+            last_live = l0;
+        }
+        have_last = true;
+        // prob_diff (common:1272-1279)
+        double d = 0.0;
+        for (int al = tid; al < a.A; al += EM_THREADS)
+            if (l0[al]) d += l1[al] ? fabs(v0[al] - v1[al]) : v0[al];
+        diff = block_sum(d, sm.red);
+        // (cooperative mode) v0 becomes the next sweep's target; that sweep only writes after its own grid
+        // syncs, which every CTA reaches after the reads above, so no extra sync is needed here
+        // Gene_prob = Gene_prob_next
+        {
+            double *tv = v0; v0 = v1; v1 = tv;
+            uint8_t *tl = l0; l0 = l1; l1 = tl;
+        }
+        if (iter >= 10 && a.remove_low) {
+            em_prune(a, sm, v0, l0);
+        }
+        iter++;
+    }
+    if (s_status == HGT_OK) {
+        if (a.remove_low) em_prune(a, sm, v0, l0);
+        // final normalize (common:1404-1407)
+        double part = 0.0;
+        int nk = 0;
+        for (int al = tid; al < a.A; al += EM_THREADS)
+            if (l0[al]) {
+                part += a.len ? v0[al] / a.len[al] : v0[al];
+                nk = 1;
+            }
+        const double total = block_sum(part, sm.red);
+        if (block_or(nk) && !(total > 0.0) && !(total < 0.0)) {
+            if (tid == 0) s_status = HGT_ERR_ZERODIV;
+            __syncthreads();
+        }
+        const bool writer = !COOP || blockIdx.x == 0;
+        if (writer) {
+            for (int al = tid; al < a.A; al += EM_THREADS) {
+                const bool key = l0[al];
+                a.prob[al] = key ? (a.len ? v0[al] / a.len[al] / total : v0[al] / total) : 0.0;
+                a.in_result[al] = key ? 1 : 0;
+            }
+        }
+        // dict insertion order of the final Gene_prob = order in which the last next_prob() call met the
+        // alleles (common:1324-1331); needed for the stable sort's tie-break (common:1409)
+        if (have_last) {
+            em_sweep<NA, COOP>(a, sm, MODE_FIRSTK, last_in, last_live, nullptr, nullptr, a.first_class, row_lo,
+                               row_hi, resident, loaded, parity, &s_status);
+        } else if (writer) {
+            for (int al = tid; al < a.A; al += EM_THREADS) a.first_class[al] = FK_NONE;
+        }
+    }
+    if (tid == 0 && (!COOP || blockIdx.x == 0)) {
+        a.iters_status[0] = iter;
+        a.iters_status[1] = s_status;
+        a.iters_status[2] = sweeps;
+    }
+}
+
+struct EmPlan {
+    int na;
+    int slab_rows;
+    size_t smem;
+};
+
+int em_plan(const hgt_ctx *ctx, int rows_per_cta, int A, int wp, EmPlan *plan) {
+    const int Apad = wp * 64;
+    if (A > 16 * EM_THREADS) {
+        hgt_set_error("EM kernel supports at most %d alleles per problem (got %d)", 16 * EM_THREADS, A);
+        return HGT_ERR_UNSUPPORTED;
+    }
+    int na = 1;
+    while (na * EM_THREADS < Apad) na *= 2;
+    const size_t fixed = 16 + 40 * 8 + (size_t)Apad * 8;
+    const size_t budget = ctx->smem_optin > 1024 ? ctx->smem_optin - 1024 : 0;
+    if (fixed + 2 * ((size_t)wp * 8 + 9) > budget) {
+        hgt_set_error("EM kernel: %d alleles do not fit shared memory", A);
+        return HGT_ERR_UNSUPPORTED;
+    }
+    size_t rows = (budget - fixed) / ((size_t)wp * 8 + 9);
+    rows &= ~(size_t)1;
+    int want = rows_per_cta < 2 ? 2 : ((rows_per_cta + 1) & ~1);
+    if ((size_t)want < rows) rows = want;
+    plan->na = na;
+    plan->slab_rows = (int)rows;
+    plan->smem = fixed + rows * ((size_t)wp * 8 + 8) + rows + 16;
+    return HGT_OK;
+}
+
+template <bool COOP>
+int em_launch(hgt_ctx *ctx, cudaStream_t st, const EmArgs *d_args, int grid, int na, size_t smem) {
+    void (*kern)(const EmArgs *) = nullptr;
+    switch (na) {
+        case 1: kern = em_kernel<1, COOP>; break;
+        case 2: kern = em_kernel<2, COOP>; break;
+        case 4: kern = em_kernel<4, COOP>; break;
+        case 8: kern = em_kernel<8, COOP>; break;
+        default: kern = em_kernel<16, COOP>; break;
+    }
+    HGT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (COOP) {
+        void *params[] = {(void *)&d_args};
+        HGT_CUDA(cudaLaunchCooperativeKernel((void *)kern, dim3(grid), dim3(EM_THREADS), params, smem, st));
+    } else {
+        kern<<<grid, EM_THREADS, smem, st>>>(d_args);
+        HGT_CUDA(cudaGetLastError());
+    }
+    ctx->launches++;
+    return HGT_OK;
+}
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// workspace carve-up (device pointers) for one problem
+struct EmWs {
+    EmArgs *d_args;
+    double *vec;
+    uint8_t *live;
+    double *part_acc;
+    int32_t *part_aux;
+    double *red_acc;
+    int32_t *red_aux;
+};
+size_t em_ws_bytes(int sm_count, int A) {
+    const size_t Apad = (size_t)hgt_row_pitch(A) * 64;
+    size_t b = 256;                                   // args
+    b += align_up(4 * Apad * 8, 256);                 // vec
+    b += align_up(4 * Apad, 256);                     // live
+    b += align_up((size_t)sm_count * Apad * 8, 256);  // part_acc
+    b += align_up((size_t)sm_count * Apad * 4, 256);  // part_aux
+    b += align_up(Apad * 8, 256) + align_up(Apad * 4, 256);
+    return b;
+}
+EmWs em_ws_carve(void *ws, int sm_count, int A) {
+    const size_t Apad = (size_t)hgt_row_pitch(A) * 64;
+    unsigned char *p = static_cast<unsigned char *>(ws);
+    EmWs w;
+    w.d_args = reinterpret_cast<EmArgs *>(p); p += 256;
+    w.vec = reinterpret_cast<double *>(p); p += align_up(4 * Apad * 8, 256);
+    w.live = p; p += align_up(4 * Apad, 256);
+    w.part_acc = reinterpret_cast<double *>(p); p += align_up((size_t)sm_count * Apad * 8, 256);
+    w.part_aux = reinterpret_cast<int32_t *>(p); p += align_up((size_t)sm_count * Apad * 4, 256);
+    w.red_acc = reinterpret_cast<double *>(p); p += align_up(Apad * 8, 256);
+    w.red_aux = reinterpret_cast<int32_t *>(p);
+    return w;
+}
+
+}  // namespace
+
+extern "C" size_t hgt_em_workspace_bytes(const hgt_ctx *ctx, int32_t n_classes, int32_t n_alleles) {
+    (void)n_classes;
+    return em_ws_bytes(ctx ? ctx->sm_count : 148, n_alleles);
+}
+
+extern "C" int hgt_em_dev(hgt_ctx *ctx, void *stream, const uint64_t *class_bits, const double *class_count,
+                          int32_t n_classes, int32_t n_alleles, int32_t wp, const double *allele_len,
+                          int32_t remove_low, int32_t fixed_iters, int32_t n_ctas, double *prob,
+                          uint8_t *in_result, int32_t *first_class, int32_t *iters_status, void *workspace) {
+    if (!ctx || !class_bits || !class_count || !prob || !in_result || !first_class || !iters_status || !workspace) {
+        hgt_set_error("hgt_em_dev: null argument");
+        return HGT_ERR_ARG;
+    }
+    if (wp != hgt_row_pitch(n_alleles) || n_classes < 1 || n_alleles < 1) {
+        hgt_set_error("hgt_em_dev: need n_classes >= 1, n_alleles >= 1 and wp == hgt_row_pitch(n_alleles)");
+        return HGT_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int G = n_ctas;
+    if (G <= 0) {
+        // one CTA until the matrix stops fitting comfortably in a single SM's shared memory
+        const size_t bytes = (size_t)n_classes * wp * 8;
+        G = bytes <= 160 * 1024 ? 1 : ctx->sm_count;
+    }
+    if (G > ctx->sm_count) G = ctx->sm_count;
+    if (G > n_classes) G = n_classes;
+    if (G < 1) G = 1;
+    const int rows_per_cta = (n_classes + G - 1) / G;
+    EmPlan plan;
+    HGT_CHECK(em_plan(ctx, rows_per_cta, n_alleles, wp, &plan));
+    EmWs w = em_ws_carve(workspace, ctx->sm_count, n_alleles);
+    EmArgs a;
+    a.bits = class_bits; a.cnt = class_count; a.len = allele_len;
+    a.C = n_classes; a.A = n_alleles; a.wp = wp; a.remove_low = remove_low; a.fixed_iters = fixed_iters;
+    a.slab_rows = plan.slab_rows;
+    a.prob = prob; a.in_result = in_result; a.first_class = first_class; a.iters_status = iters_status;
+    a.vec = w.vec; a.live = w.live; a.part_acc = w.part_acc; a.part_aux = w.part_aux;
+    a.red_acc = w.red_acc; a.red_aux = w.red_aux;
+    HGT_CUDA(cudaMemcpyAsync(w.d_args, &a, sizeof(a), cudaMemcpyHostToDevice, st));
+    if (G == 1) return em_launch<false>(ctx, st, w.d_args, 1, plan.na, plan.smem);
+    return em_launch<true>(ctx, st, w.d_args, G, plan.na, plan.smem);
+}
+
+extern "C" int hgt_em(hgt_ctx *ctx, const uint64_t *class_bits, const int64_t *class_count, int32_t n_classes,
+                      int32_t n_alleles, int32_t wp, const double *allele_len, int32_t remove_low, double *prob,
+                      uint8_t *in_result, int32_t *first_class, int32_t *iters) {
+    if (!ctx) {
+        hgt_set_error("hgt_em: null context");
+        return HGT_ERR_ARG;
+    }
+    HGT_CUDA(cudaSetDevice(ctx->device));
+    if (n_classes == 0) {  // empty Gene_cmpt: the reference loop runs once on empty dicts and returns []
+        for (int i = 0; i < n_alleles; i++) { prob[i] = 0.0; in_result[i] = 0; first_class[i] = FK_NONE; }
+        if (iters) *iters = 1;
+        return HGT_OK;
+    }
+    cudaStream_t st = ctx->stream;
+    const size_t nb = (size_t)n_classes * wp * 8;
+    const size_t wsb = em_ws_bytes(ctx->sm_count, n_alleles);
+    unsigned char *d = nullptr;
+    const size_t o_bits = 0, o_cnt = align_up(nb, 256), o_len = o_cnt + align_up((size_t)n_classes * 8, 256),
+                 o_prob = o_len + align_up((size_t)n_alleles * 8, 256),
+                 o_in = o_prob + align_up((size_t)n_alleles * 8, 256), o_fk = o_in + align_up(n_alleles, 256),
+                 o_is = o_fk + align_up((size_t)n_alleles * 4, 256), o_ws = o_is + 256, total = o_ws + wsb;
+    HGT_CUDA(cudaMalloc(&d, total));
+    std::vector<double> cnt(n_classes);
+    for (int i = 0; i < n_classes; i++) cnt[i] = (double)class_count[i];
+    int rc = HGT_OK;
+    int32_t is[3] = {0, 0, 0};
+    do {
+#define TRY(call)                                                                                 \
+    {                                                                                             \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            hgt_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            rc = HGT_ERR_CUDA;                                                                    \
+            break;                                                                                \
+        }                                                                                         \
+    }
+        TRY(cudaMemcpyAsync(d + o_bits, class_bits, nb, cudaMemcpyHostToDevice, st));
+        TRY(cudaMemcpyAsync(d + o_cnt, cnt.data(), (size_t)n_classes * 8, cudaMemcpyHostToDevice, st));
+        if (allele_len) TRY(cudaMemcpyAsync(d + o_len, allele_len, (size_t)n_alleles * 8, cudaMemcpyHostToDevice, st));
+        rc = hgt_em_dev(ctx, st, reinterpret_cast<uint64_t *>(d + o_bits), reinterpret_cast<double *>(d + o_cnt),
+                        n_classes, n_alleles, wp, allele_len ? reinterpret_cast<double *>(d + o_len) : nullptr,
+                        remove_low, 0, 0, reinterpret_cast<double *>(d + o_prob), d + o_in,
+                        reinterpret_cast<int32_t *>(d + o_fk), reinterpret_cast<int32_t *>(d + o_is), d + o_ws);
+        if (rc != HGT_OK) break;
+        TRY(cudaMemcpyAsync(prob, d + o_prob, (size_t)n_alleles * 8, cudaMemcpyDeviceToHost, st));
+        TRY(cudaMemcpyAsync(in_result, d + o_in, (size_t)n_alleles, cudaMemcpyDeviceToHost, st));
+        TRY(cudaMemcpyAsync(first_class, d + o_fk, (size_t)n_alleles * 4, cudaMemcpyDeviceToHost, st));
+        TRY(cudaMemcpyAsync(is, d + o_is, sizeof(is), cudaMemcpyDeviceToHost, st));
+        TRY(cudaStreamSynchronize(st));
+#undef TRY
+    } while (0);
+    cudaFree(d);
+    if (rc != HGT_OK) return rc;
+    if (iters) *iters = is[0];
+    if (is[1] == HGT_ERR_KEY) hgt_set_error("KeyError: allele vanished from next_prob output during SQUAREM step");
+    if (is[1] == HGT_ERR_ZERODIV) hgt_set_error("ZeroDivisionError: float division by zero in normalize");
+    return is[1];
+}
+
+extern "C" int hgt_em_batch(hgt_ctx *ctx, int32_t n_problems, const uint64_t *class_bits, const int64_t *class_count,
+                            const int64_t *class_off, const int64_t *allele_off, int32_t wp, const double *allele_len,
+                            const uint8_t *remove_low, double *prob, uint8_t *in_result, int32_t *first_class,
+                            int32_t *iters, int32_t *status) {
+    if (!ctx || n_problems < 0 || !class_off || !allele_off) {
+        hgt_set_error("hgt_em_batch: bad argument");
+        return HGT_ERR_ARG;
+    }
+    if (n_problems == 0) return HGT_OK;
+    HGT_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = ctx->stream;
+    const int64_t Ctot = class_off[n_problems], Atot = allele_off[n_problems];
+    const size_t Apad = (size_t)wp * 64;
+    std::vector<EmArgs> args(n_problems);
+    std::vector<double> cnt((size_t)Ctot);
+    for (int64_t i = 0; i < Ctot; i++) cnt[i] = (double)class_count[i];
+    // device arena
+    const size_t o_bits = 0, o_cnt = align_up((size_t)Ctot * wp * 8, 256), o_len = o_cnt + align_up((size_t)Ctot * 8, 256),
+                 o_prob = o_len + align_up((size_t)Atot * 8, 256), o_in = o_prob + align_up((size_t)Atot * 8, 256),
+                 o_fk = o_in + align_up((size_t)Atot, 256), o_is = o_fk + align_up((size_t)Atot * 4, 256),
+                 o_args = o_is + align_up((size_t)n_problems * 12, 256),
+                 o_vec = o_args + align_up((size_t)n_problems * sizeof(EmArgs), 256),
+                 o_live = o_vec + (size_t)n_problems * 4 * Apad * 8, total = o_live + (size_t)n_problems * 4 * Apad;
+    unsigned char *d = nullptr;
+    HGT_CUDA(cudaMalloc(&d, total));
+    int rc = HGT_OK;
+    int na = 1;
+    size_t smem = 0;
+    std::vector<int32_t> is((size_t)n_problems * 3, 0);
+    for (int i = 0; i < n_problems && rc == HGT_OK; i++) {
+        const int C = (int)(class_off[i + 1] - class_off[i]), A = (int)(allele_off[i + 1] - allele_off[i]);
+        if (A < 1 || hgt_row_pitch(A) > wp) {
+            hgt_set_error("hgt_em_batch: problem %d has %d alleles, pitch %d too small", i, A, wp);
+            rc = HGT_ERR_ARG;
+            break;
+        }
+        EmPlan plan;
+        rc = em_plan(ctx, C < 1 ? 1 : C, (int)Apad, wp, &plan);
+        if (rc != HGT_OK) break;
+        // a batched problem must be resident-or-streamed by ONE CTA; both work, plan.slab_rows caps the buffer
+        na = plan.na;
+        if (plan.smem > smem) smem = plan.smem;
+        EmArgs &a = args[i];
+        a.bits = reinterpret_cast<uint64_t *>(d + o_bits) + (size_t)class_off[i] * wp;
+        a.cnt = reinterpret_cast<double *>(d + o_cnt) + class_off[i];
+        a.len = allele_len ? reinterpret_cast<double *>(d + o_len) + allele_off[i] : nullptr;
+        a.C = C; a.A = A; a.wp = wp; a.remove_low = remove_low ? remove_low[i] : 0; a.fixed_iters = 0;
+        a.slab_rows = plan.slab_rows;
+        a.prob = reinterpret_cast<double *>(d + o_prob) + allele_off[i];
+        a.in_result = d + o_in + allele_off[i];
+        a.first_class = reinterpret_cast<int32_t *>(d + o_fk) + allele_off[i];
+        a.iters_status = reinterpret_cast<int32_t *>(d + o_is) + (size_t)i * 3;
+        a.vec = reinterpret_cast<double *>(d + o_vec) + (size_t)i * 4 * Apad;
+        a.live = d + o_live + (size_t)i * 4 * Apad;
+        a.part_acc = nullptr; a.part_aux = nullptr; a.red_acc = nullptr; a.red_aux = nullptr;
+    }
+    do {
+        if (rc != HGT_OK) break;
+#define TRY(call)                                                                                 \
+    {                                                                                             \
+        cudaError_t e_ = (call);                                                                  \
+        if (e_ != cudaSuccess) {                                                                  \
+            hgt_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            rc = HGT_ERR_CUDA;                                                                    \
+            break;                                                                                \
+        }                                                                                         \
+    }
+        TRY(cudaMemcpyAsync(d + o_bits, class_bits, (size_t)Ctot * wp * 8, cudaMemcpyHostToDevice, st));
+        TRY(cudaMemcpyAsync(d + o_cnt, cnt.data(), (size_t)Ctot * 8, cudaMemcpyHostToDevice, st));
+        if (allele_len) TRY(cudaMemcpyAsync(d + o_len, allele_len, (size_t)Atot * 8, cudaMemcpyHostToDevice, st));
+        TRY(cudaMemcpyAsync(d + o_args, args.data(), (size_t)n_problems * sizeof(EmArgs), cudaMemcpyHostToDevice, st));
+        TRY(cudaMemsetAsync(d + o_is, 0, (size_t)n_problems * 12, st));
+        rc = em_launch<false>(ctx, st, reinterpret_cast<EmArgs *>(d + o_args), n_problems, na, smem);
+        if (rc != HGT_OK) break;
+        TRY(cudaMemcpyAsync(prob, d + o_prob, (size_t)Atot * 8, cudaMemcpyDeviceToHost, st));
+        TRY(cudaMemcpyAsync(in_result, d + o_in, (size_t)Atot, cudaMemcpyDeviceToHost, st));
+        TRY(cudaMemcpyAsync(first_class, d + o_fk, (size_t)Atot * 4, cudaMemcpyDeviceToHost, st));
+        TRY(cudaMemcpyAsync(is.data(), d + o_is, (size_t)n_problems * 12, cudaMemcpyDeviceToHost, st));
+        TRY(cudaStreamSynchronize(st));
+#undef TRY
+    } while (0);
+    cudaFree(d);
+    if (rc != HGT_OK) return rc;
+    for (int i = 0; i < n_problems; i++) {
+        if (iters) iters[i] = is[(size_t)i * 3];
+        if (status) status[i] = is[(size_t)i * 3 + 1];
+    }
+    return HGT_OK;
+}

@@ -1,0 +1,131 @@
+"""GPU parity: EM kernel (csrc/em.cu) through the C ABI vs the oracle and the reference goldens."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN_NAMES, load_golden
+
+pytestmark = pytest.mark.gpu
+
+REL = 1e-6  # tolerance stated by BASELINE.json north_star for EM abundances
+
+
+def _check(res, ref):
+    assert [a for a, _ in res] == [a for a, _ in ref]
+    for (_, p), (_, q) in zip(res, ref):
+        assert p == pytest.approx(q, rel=REL, abs=1e-12)
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_em_matches_reference_goldens(name):
+    from hisatgenotype_b200.typing_common import single_abundance
+    g = load_golden(name)
+    assert g["em_calls"]
+    for call in g["em_calls"]:
+        res = single_abundance(dict((k, c) for k, c in call["cmpt"]), call["remove_low"], call["lengths"])
+        _check(res, call["result"])
+
+
+def random_problem(rng, A, C, groups, dense_frac=0.05):
+    """Class table shaped like Gene_cmpt: classes are subsets of one allele group (+ a few dense ones)."""
+    names = ["A*%03d:%03d" % (i // 40 + 1, i % 40 + 1) for i in range(A)]
+    gsize = max(1, A // groups)
+    cmpt = {}
+    truth = rng.choice(A, size=2, replace=False)
+    while len(cmpt) < C:
+        if rng.random() < dense_frac:
+            mem = np.nonzero(rng.random(A) < 0.5)[0]
+        else:
+            t = truth[rng.integers(0, 2)] if rng.random() < 0.7 else rng.integers(0, A)
+            g0 = (t // gsize) * gsize
+            pool = np.arange(g0, min(A, g0 + gsize))
+            mem = pool[rng.random(pool.size) < rng.uniform(0.05, 0.9)]
+            mem = np.union1d(mem, [t])
+        if mem.size == 0:
+            continue
+        key = "-".join(sorted(names[i] for i in mem))
+        cmpt[key] = cmpt.get(key, 0) + int(rng.integers(1, 40))
+    lengths = {n: int(3000 + rng.integers(0, 600)) for n in names}
+    return cmpt, lengths
+
+
+@pytest.mark.parametrize("A,C,groups,remove_low,use_len", [
+    (50, 20, 5, False, False),
+    (700, 84, 12, True, False),      # exon-table sized (C=84, A=702)
+    (800, 300, 20, True, True),
+    (2000, 500, 40, False, True),
+    (4000, 1500, 60, True, True),
+    (8000, 2000, 60, True, True),    # BASELINE.md "EM large"
+    (8192, 6000, 64, True, False),   # multi-CTA cooperative path, streaming slabs
+])
+def test_em_matches_c_oracle(A, C, groups, remove_low, use_len):
+    import em_oracle
+    from hisatgenotype_b200.typing_common import single_abundance
+    rng = np.random.default_rng(A * 31 + C)
+    cmpt, lengths = random_problem(rng, A, C, groups)
+    ln = lengths if use_len else {}
+    ref, _ = em_oracle.single_abundance(cmpt, remove_low, ln)
+    res = single_abundance(cmpt, remove_low, ln)
+    _check(res, ref)
+
+
+def test_em_iteration_count_and_first_class():
+    import em_oracle
+    from hisatgenotype_b200 import _lib
+    from hisatgenotype_b200.typing_common import _index_alleles, em_arrays
+    rng = np.random.default_rng(5)
+    cmpt, _ = random_problem(rng, 600, 150, 10)
+    keys = list(cmpt)
+    names, index = _index_alleles(keys)
+    bits = _lib.pack_bits([[index[a] for a in k.split("-")] for k in keys], len(names))
+    prob, inres, fk, iters = em_arrays(bits, [cmpt[k] for k in keys], len(names), None, False)
+    ref, ref_iters = em_oracle.single_abundance(cmpt, False, {})
+    assert iters == ref_iters
+    assert int(inres.sum()) == len(ref)
+    assert abs(prob.sum() - 1.0) < 1e-9
+
+
+def test_em_empty_and_single_class():
+    from hisatgenotype_b200.typing_common import single_abundance
+    assert single_abundance({}) == []
+    res = single_abundance({"A*01:01-A*01:02": 7})
+    assert [a for a, _ in res] == ["A*01:01", "A*01:02"]
+    assert res[0][1] == pytest.approx(0.5) and res[1][1] == pytest.approx(0.5)
+
+
+def test_em_batch_matches_single():
+    from hisatgenotype_b200 import _lib
+    from hisatgenotype_b200.typing_common import _index_alleles, em_arrays
+    rng = np.random.default_rng(11)
+    probs = []
+    for i in range(9):
+        cmpt, lengths = random_problem(rng, 200 + 50 * i, 40 + 10 * i, 6)
+        keys = list(cmpt)
+        names, index = _index_alleles(keys)
+        probs.append((cmpt, keys, names, index, lengths))
+    Amax = max(len(p[2]) for p in probs)
+    wp = _lib.row_pitch(Amax)
+    bits = np.concatenate(
+        [_lib.pack_bits([[p[3][a] for a in k.split("-")] for k in p[1]], len(p[2]), wp) for p in probs])
+    cnt = np.concatenate([np.asarray([p[0][k] for k in p[1]], np.int64) for p in probs])
+    coff = np.cumsum([0] + [len(p[1]) for p in probs]).astype(np.int64)
+    aoff = np.cumsum([0] + [len(p[2]) for p in probs]).astype(np.int64)
+    ln = np.concatenate([np.asarray([p[4][n] for n in p[2]], np.float64) for p in probs])
+    rl = np.asarray([i % 2 for i in range(len(probs))], np.uint8)
+    At = int(aoff[-1])
+    prob = np.zeros(At)
+    inres = np.zeros(At, np.uint8)
+    fk = np.zeros(At, np.int32)
+    iters = np.zeros(len(probs), np.int32)
+    status = np.zeros(len(probs), np.int32)
+    _lib.check(_lib.lib().hgt_em_batch(_lib.ctx(), len(probs), _lib.ptr(bits), _lib.ptr(cnt), _lib.ptr(coff),
+                                       _lib.ptr(aoff), wp, _lib.ptr(ln), _lib.ptr(rl), _lib.ptr(prob),
+                                       _lib.ptr(inres), _lib.ptr(fk), _lib.ptr(iters), _lib.ptr(status)))
+    assert (status == 0).all()
+    for i, p in enumerate(probs):
+        b1 = _lib.pack_bits([[p[3][a] for a in k.split("-")] for k in p[1]], len(p[2]))
+        pr, ir, f, it = em_arrays(b1, [p[0][k] for k in p[1]], len(p[2]), [p[4][n] for n in p[2]], bool(rl[i]))
+        s = slice(int(aoff[i]), int(aoff[i + 1]))
+        assert it == iters[i]
+        np.testing.assert_array_equal(ir, inres[s])
+        np.testing.assert_allclose(pr, prob[s], rtol=1e-12, atol=0)
+        np.testing.assert_array_equal(f, fk[s])

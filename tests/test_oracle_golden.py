@@ -97,3 +97,12 @@ def test_em_python_restatement(name):
         assert [a for a, _ in res] == [a for a, _ in call["result"]]
         for (a, p), (b, q) in zip(res, call["result"]):
             assert p == pytest.approx(q, rel=1e-12, abs=1e-300)
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_em_c_restatement_bit_exact(name):
+    import em_oracle
+    g = load_golden(name)
+    for call in g["em_calls"]:
+        res, _ = em_oracle.single_abundance(call["cmpt"], call["remove_low"], call["lengths"])
+        assert res == [[a, p] for a, p in call["result"]]
