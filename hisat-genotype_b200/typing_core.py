@@ -1,0 +1,192 @@
+"""Host-side mirror of the reference's hisatgenotype_typing_core API for the typing hot path.
+
+  type_locus()   stage (a) for one (sample, locus): alignment lines in, Gene_cmpt / Gene_counts out — the
+                 per-read loop of typing() (reference hisatgenotype_typing_core.py:598-1596) on the GPU.
+  locus_abundance()   the EM driver of typing() (core:1679-1789) on device-resident tables.
+  typing() / genotyping_locus()   drop-in entry points with the reference's signatures and .report format
+                 (core:249-286, 2278-2309); see report.py.
+There is no CPU fallback: everything below needs libhgt.so and a B200.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from .locus import LocusTables, Params, lib
+from .typing_common import rank_result
+
+TABLE_GENE, TABLE_EXON, TABLE_PRIMARY = 0, 1, 2
+
+
+def make_params(num_editdist=2, error_correction=True, allow_discordant=False, simulation=False, base_locus=0,
+                n_threads=0):
+    return Params(int(num_editdist), 1 if error_correction else 0, 1 if allow_discordant else 0,
+                  1 if simulation else 0, int(base_locus), int(n_threads))
+
+
+def _sam_bytes(sam):
+    if isinstance(sam, bytes):
+        return sam
+    if isinstance(sam, str):
+        return sam.encode()
+    return ("\n".join(sam) + "\n").encode()
+
+
+class TypingRun:
+    """Result of stage (a) for one (sample, locus); tables stay on the device until asked for."""
+
+    def __init__(self, tables: LocusTables, sam, params: Params):
+        self.tables = tables
+        self.handle = ctypes.c_void_p()
+        buf = _sam_bytes(sam)
+        rc = lib().hgt_typing_run(_lib.ctx(tables.device), tables.handle, buf, len(buf), ctypes.byref(params),
+                                  ctypes.byref(self.handle))
+        if rc == _lib.HGT_ERR_AMBIGUITY:
+            raise SystemExit("Error: %s" % _lib.last_error())
+        if rc == _lib.HGT_ERR_PARSE:
+            raise AssertionError(_lib.last_error())
+        _lib.check(rc)
+        nr, npairs = ctypes.c_int64(0), ctypes.c_int64(0)
+        ncls = (ctypes.c_int32 * 3)()
+        _lib.check(lib().hgt_typing_summary(self.handle, ctypes.byref(nr), ctypes.byref(npairs), ctypes.byref(ncls)))
+        self.num_reads, self.num_pairs = nr.value, npairs.value
+        self.n_classes = [ncls[0], ncls[1], ncls[2]]
+        self._cache = {}
+
+    def close(self):
+        if self.handle is not None and self.handle.value:
+            lib().hgt_typing_free(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def table_arrays(self, table):
+        """(class_bits[C][wp], class_count[C], class_first[C], allele_count[A], allele_first[A])"""
+        if table not in self._cache:
+            t = self.tables
+            C = self.n_classes[table]
+            bits = np.zeros((max(C, 1), t.wp), np.uint64)
+            cnt = np.zeros(max(C, 1), np.int64)
+            first = np.zeros(max(C, 1), np.int64)
+            acount = np.zeros(t.A, np.int64)
+            afirst = np.zeros(t.A, np.int64)
+            _lib.check(lib().hgt_typing_table(self.handle, table, _lib.ptr(bits), _lib.ptr(cnt), _lib.ptr(first),
+                                              _lib.ptr(acount), _lib.ptr(afirst)))
+            self._cache[table] = (bits[:C], cnt[:C], first[:C], acount, afirst)
+        return self._cache[table]
+
+    def gene_cmpt(self, table=TABLE_GENE):
+        """Gene_cmpt of the table as an insertion-ordered dict (core:1229-1234)."""
+        bits, cnt, _, _, _ = self.table_arrays(table)
+        return {self.tables.key_of(bits[k]): int(cnt[k]) for k in range(len(cnt))}
+
+    def gene_counts(self, table=TABLE_GENE):
+        """Gene_counts in dict order: alleles enter at the first pair that counts them, in Gene_names order
+        within one pair (core:1179-1190)."""
+        _, _, _, acount, afirst = self.table_arrays(table)
+        t = self.tables
+        idx = np.nonzero(acount > 0)[0]
+        order = sorted(idx.tolist(), key=lambda a: (int(afirst[a]), int(t.gn_rank[a])))
+        return [[t.names[a], int(acount[a])] for a in order]
+
+    def pileup(self):
+        t = self.tables
+        counts = np.zeros((len(t.ref_seq), 6), np.uint32)
+        mask = np.zeros(len(t.ref_seq), np.uint8)
+        _lib.check(lib().hgt_typing_pileup(self.handle, _lib.ptr(counts), _lib.ptr(mask)))
+        return counts, mask
+
+    def abundance(self, table, keep_alleles=None, lengths=None, remove_low=False):
+        """single_abundance on a device-resident table; keep_alleles projects the classes first (core:1753-1766)."""
+        t = self.tables
+        keep = t.mask_of(keep_alleles) if keep_alleles is not None else None
+        ln = None
+        if lengths:
+            ln = np.asarray([lengths[n] for n in t.names], np.float64)
+        prob = np.zeros(t.A, np.float64)
+        inres = np.zeros(t.A, np.uint8)
+        fk = np.zeros(t.A, np.int32)
+        iters = ctypes.c_int32(0)
+        rc = lib().hgt_typing_em(_lib.ctx(t.device), self.handle, table, _lib.ptr(keep), _lib.ptr(ln),
+                                 1 if remove_low else 0, _lib.ptr(prob), _lib.ptr(inres), _lib.ptr(fk),
+                                 ctypes.byref(iters))
+        if rc == _lib.HGT_ERR_KEY:
+            raise KeyError(_lib.last_error())
+        if rc == _lib.HGT_ERR_ZERODIV:
+            raise ZeroDivisionError("float division by zero")
+        _lib.check(rc)
+        return rank_result(t.names, prob, inres, fk)
+
+
+def type_locus(tables, sam, num_editdist=2, error_correction=True, allow_discordant=False, simulation=False,
+               base_locus=0):
+    return TypingRun(tables, sam, make_params(num_editdist, error_correction, allow_discordant, simulation,
+                                              base_locus))
+
+
+def locus_abundance(run: TypingRun, remove_low_abundance_alleles=True):
+    """Gene_prob for one locus: the EM driver of typing() (core:1679-1789)."""
+    t = run.tables
+    if t.is_hla:
+        exon_prob = run.abundance(TABLE_EXON, None, None, remove_low_abundance_alleles)
+        gene_prob = exon_prob
+        exon_alleles, exon_prob_sum = set(), 0.0
+        for i, (allele, prob) in enumerate(exon_prob):
+            if i >= 10 and prob < 0.03:
+                break
+            group = t.allele_rep_groups[allele]
+            if len(group) <= 1:
+                continue
+            exon_prob_sum += prob
+            exon_alleles |= set(group)
+        if len(exon_alleles) > 0:
+            full = run.abundance(TABLE_GENE, exon_alleles, t.gene_lengths, True)
+            combined = {}
+            for allele, prob in exon_prob:
+                if allele not in exon_alleles:
+                    combined[allele] = prob
+            for allele, prob in full:
+                combined[allele] = prob * exon_prob_sum
+            gene_prob = sorted(([a, p] for a, p in combined.items()), key=lambda x: x[1], reverse=True)
+        return gene_prob
+    if run.n_classes[TABLE_GENE] <= 1:
+        if run.n_classes[TABLE_GENE] == 1:
+            # the reference evaluates Gene_cmpt.keys()[0] here, a TypeError on Python 3 (core:1787)
+            raise TypeError("'dict_keys' object is not subscriptable")
+        return []
+    return run.abundance(TABLE_GENE, None, None, False)
+
+
+class HostWalk:
+    """Host half of stage (a) with a caller-supplied pileup (no GPU): used by the CPU-side tests."""
+
+    def __init__(self, tables: LocusTables, sam, params: Params, counts, nt_mask):
+        buf = _sam_bytes(sam)
+        counts = np.ascontiguousarray(counts, np.uint32)
+        nt_mask = np.ascontiguousarray(nt_mask, np.uint8)
+        h = ctypes.c_void_p()
+        rc = lib().hgt_host_walk(tables.handle, buf, len(buf), ctypes.byref(params), _lib.ptr(counts),
+                                 _lib.ptr(nt_mask), ctypes.byref(h))
+        _lib.check(rc)
+        nr, npairs = ctypes.c_int64(0), ctypes.c_int64(0)
+        nh, nrows = (ctypes.c_int64 * 3)(), (ctypes.c_int64 * 3)()
+        _lib.check(lib().hgt_walk_summary(h, ctypes.byref(nr), ctypes.byref(npairs), ctypes.byref(nh),
+                                          ctypes.byref(nrows)))
+        self.num_reads, self.num_pairs = nr.value, npairs.value
+        self.tables_out = []
+        for tb in range(3):
+            job_off = np.zeros(self.num_pairs + 1, np.int64)
+            hl = np.zeros(max(nh[tb], 1), np.int32)
+            hr = np.zeros(max(nh[tb], 1), np.int32)
+            ro = np.zeros(nh[tb] + 1, np.int64)
+            rows = np.zeros(max(nrows[tb], 1), np.int32)
+            _lib.check(lib().hgt_walk_table(h, tb, _lib.ptr(job_off), _lib.ptr(hl), _lib.ptr(hr), _lib.ptr(ro),
+                                            _lib.ptr(rows)))
+            self.tables_out.append((job_off, hl[:nh[tb]], hr[:nh[tb]], ro, rows[:nrows[tb]]))
+        lib().hgt_walk_free(h)

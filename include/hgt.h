@@ -83,6 +83,86 @@ int hgt_em_dev(hgt_ctx *ctx, void *stream, const uint64_t *class_bits, const dou
                int32_t fixed_iters, int32_t n_ctas, double *prob, uint8_t *in_result, int32_t *first_class,
                int32_t *iters_status /* [2]: iters, status */, void *workspace);
 
+/* ---- stage (a): per-read allele compatibility -----------------------------------------------------------
+ * Replaces the per-read loop of typing() for index_type == "graph"
+ *   reference hisatgenotype_modules/hisatgenotype_typing_core.py:598-1596 (add_count :626-677, add_stat
+ *   :1171-1236, get_exon_haplotypes :718-792, error_correct :119-243) together with
+ *   hisatgenotype_typing_common.py get_mpileup :1059-1184 and identify_ambigious_diffs :1663-1955.
+ *
+ * A locus is described once (hgt_locus_desc mirrors the per-locus state typing() derives at core:385-596);
+ * hgt_typing_run consumes the alignment lines of one (sample, locus) exactly as the reference reads them from
+ * `samtools view <aln> <backbone> | sort -k1,1 -s` (core:436-468) and leaves Gene_cmpt / Gene_counts for the
+ * three tables on the device.  Table ids: 0 = Gene (all alleles), 1 = exon (allele_rep_set),
+ * 2 = primary exon (primary_exon_allele_rep_set); tables 1 and 2 exist only when is_hla != 0 (core:1274-1291). */
+typedef struct {
+    int32_t n_alleles;           /* alleles of the locus, backbone excluded, sorted-name order */
+    int32_t n_vars;              /* variants in Var_list order (sorted by position, file order inside one) */
+    int32_t ref_len;
+    const char *ref_seq;         /* backbone sequence */
+    const int32_t *var_pos;      /* [n_vars] 0-based backbone position */
+    const int32_t *var_len;      /* [n_vars] deletion length / inserted length / 1 for single */
+    const uint8_t *var_type;     /* [n_vars] 0 single, 1 deletion, 2 insertion */
+    const char *var_base;        /* [n_vars] alternative base of a single, else 0 */
+    const uint8_t *var_flags;    /* [n_vars] bit0: id is a key of Links, bit1: id starts with "hv" */
+    const char *var_ids;         /* n_vars NUL-terminated id strings, concatenated */
+    const int64_t *link_off;     /* [n_vars+1] CSR offsets into link_allele */
+    const int32_t *link_allele;  /* allele indices linked to each variant (Links[var_id]) */
+    int32_t n_exons;
+    const int32_t *exons;        /* [2*n_exons] left,right inclusive (ref_exons) */
+    int32_t n_primary_exons;
+    const int32_t *primary_exons;
+    const uint64_t *exon_rep_mask;     /* [wp] allele_rep_set, NULL when is_hla == 0 */
+    const uint64_t *primary_rep_mask;  /* [wp] primary_exon_allele_rep_set */
+    const int32_t *gene_names_rank;    /* [n_alleles] position of the allele in Gene_names[gene] (dict order of the
+                                          per-read count tables, core:1338-1347) */
+    int32_t is_hla;              /* base_fname == "hla" */
+    const char *alts_text;       /* get_alternatives() tables: lines "L\tkey\talt,alt,...\n" / "R\t..." */
+} hgt_locus_desc;
+
+typedef struct {
+    int32_t num_editdist;      /* --num-editdist (args.py:294-299), default 2 */
+    int32_t error_correction;  /* default on */
+    int32_t allow_discordant;  /* --discordant */
+    int32_t simulation;        /* read ids are cut at the first '|' (core:808-809) */
+    int32_t base_locus;        /* 0 unless typing inside a genotype genome (core:437-441) */
+    int32_t n_threads;         /* host threads for record intake; <= 0 = library default */
+} hgt_params;
+
+/* ctx may be NULL: the locus then only carries the host tables (used by hgt_host_walk). */
+int hgt_locus_create(hgt_ctx *ctx, const hgt_locus_desc *desc, hgt_locus **out);
+void hgt_locus_free(hgt_locus *locus);
+
+int hgt_typing_run(hgt_ctx *ctx, hgt_locus *locus, const char *sam_text, size_t n_bytes, const hgt_params *params,
+                   hgt_typing **out);
+void hgt_typing_free(hgt_typing *t);
+/* num_reads / num_pairs (core:1168, 1240, 1546) and number of classes per table */
+int hgt_typing_summary(const hgt_typing *t, int64_t *num_reads, int64_t *num_pairs, int32_t n_classes[3]);
+/* Gene_cmpt of one table in dict (first-seen) order: class_bits [n_classes][wp], class_count, class_first
+ * (pair index that created the key); Gene_counts as allele_count[n_alleles] plus allele_first[n_alleles]
+ * (pair index that inserted the allele; ties follow gene_names_rank).  Any output pointer may be NULL. */
+int hgt_typing_table(const hgt_typing *t, int32_t table, uint64_t *class_bits, int64_t *class_count,
+                     int64_t *class_first, int64_t *allele_count, int64_t *allele_first);
+/* pileup of the locus: counts [ref_len][6] for A,C,G,T,other,D and the nt_set mask (bit i = "ACGT"[i]) */
+int hgt_typing_pileup(const hgt_typing *t, uint32_t *counts, uint8_t *nt_mask);
+/* EM directly on a device-resident table.  keep_mask (nullable, [wp]) projects every class onto a subset of
+ * alleles first, merging classes that become equal and dropping empty ones (core:1753-1766). */
+int hgt_typing_em(hgt_ctx *ctx, const hgt_typing *t, int32_t table, const uint64_t *keep_mask,
+                  const double *allele_len, int32_t remove_low, double *prob, uint8_t *in_result,
+                  int32_t *first_class, int32_t *iters);
+
+/* Host-only half of stage (a) with a caller-supplied pileup (no GPU needed): intake, filters, walk, error
+ * correction, ambiguity expansion, exon clipping.  Output is the job list the GPU consumes, flattened:
+ * for table tb: jobs tb_job_off[n_pairs+1] -> haplotypes (left, right, row_off[..+1] -> rows).  Buffers are
+ * owned by the returned handle. */
+typedef struct hgt_walk hgt_walk;
+int hgt_host_walk(hgt_locus *locus, const char *sam_text, size_t n_bytes, const hgt_params *params,
+                  const uint32_t *counts, const uint8_t *nt_mask, hgt_walk **out);
+int hgt_walk_summary(const hgt_walk *w, int64_t *num_reads, int64_t *num_pairs, int64_t n_haps[3],
+                     int64_t n_rows[3]);
+int hgt_walk_table(const hgt_walk *w, int32_t table, int64_t *job_off, int32_t *hap_left, int32_t *hap_right,
+                   int64_t *row_off, int32_t *rows);
+void hgt_walk_free(hgt_walk *w);
+
 #ifdef __cplusplus
 }
 #endif

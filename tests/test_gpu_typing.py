@@ -1,0 +1,100 @@
+"""GPU parity of stage (a) (csrc/typing.cu + walk.hpp) through the C ABI: alignment lines in, Gene_cmpt /
+Gene_counts / pileup out, bit-exact against the vectors captured from the unmodified reference; plus the EM
+driver (core:1679-1789) on the device-resident tables."""
+import numpy as np
+import pytest
+
+import hgt_oracle as O
+from conftest import GOLDEN_NAMES, load_golden
+from helpers import golden_db, oracle_locus, pileup_arrays, product_locus
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_tables_bit_exact_vs_reference(name):
+    from hisatgenotype_b200 import typing_core as TC
+    g = load_golden(name)
+    p = g["params"]
+    db = golden_db(g)
+    em_i = 0
+    for cap, mp in zip(g["loci"], g["mpileup"]):
+        t = product_locus(g, db, cap["gene"], cap["Gene_names"])
+        run = TC.type_locus(t, cap["sam"], p["num_editdist"], p["error_correction"], p["discordant"], p["simulation"])
+        assert run.num_reads == cap["num_reads"]
+        assert run.num_pairs == cap["num_pairs"]
+        # pileup (common:1059-1134)
+        counts, mask = run.pileup()
+        code = {"A": 0, "C": 1, "G": 2, "T": 3, "D": 5}
+        ref_counts = np.zeros_like(counts)
+        for i, d in enumerate(mp["counts"]):
+            for nt, k in d.items():
+                ref_counts[i, code.get(nt, 4)] += k
+        np.testing.assert_array_equal(counts, ref_counts)
+        ref_mask = [sum(1 << "ACGT".index(c) for c in s) for s in mp["nt_set"]]
+        np.testing.assert_array_equal(mask, np.asarray(ref_mask, np.uint8))
+        # the three tables, dict order included
+        assert list(map(list, run.gene_cmpt(TC.TABLE_GENE).items())) == cap["Gene_cmpt"]
+        assert run.gene_counts(TC.TABLE_GENE) == cap["Gene_counts"]
+        if p["base"] == "hla":
+            assert list(map(list, run.gene_cmpt(TC.TABLE_EXON).items())) == cap["Gene_exons_cmpt"]
+            assert run.gene_counts(TC.TABLE_EXON) == cap["Gene_exons_counts"]
+            assert list(map(list, run.gene_cmpt(TC.TABLE_PRIMARY).items())) == cap["Gene_primary_exons_cmpt"]
+            assert run.gene_counts(TC.TABLE_PRIMARY) == cap["Gene_primary_exons_counts"]
+        # EM driver: same sequence of single_abundance calls with the same results
+        calls = []
+        orig = run.abundance
+
+        def spy(table, keep=None, lengths=None, remove_low=False):
+            res = orig(table, keep, lengths, remove_low)
+            calls.append(res)
+            return res
+
+        run.abundance = spy
+        TC.locus_abundance(run, p["remove_low"])
+        for res in calls:
+            ref = g["em_calls"][em_i]["result"]
+            em_i += 1
+            assert [a for a, _ in res] == [a for a, _ in ref]
+            for (_, x), (_, y) in zip(res, ref):
+                assert x == pytest.approx(y, rel=1e-6, abs=1e-12)
+        run.close()
+        t.close()
+    assert em_i == len(g["em_calls"])
+
+
+def _synthetic_case(seed, A=300, L=2500, n_reads=4000):
+    """Bigger-than-golden case: database + reads from hisatgenotype_b200.synth, SAM synthesised from the true
+    alignment; oracle on the same lines."""
+    from hisatgenotype_b200 import synth
+    loc = synth.make_locus("A", seed, L=L, n_alleles=A, n_groups=12, core_vars=60, pool_private=300, del_frac=0.1)
+    rng = np.random.default_rng(seed)
+    names = sorted(n for n in loc.alleles if loc.alleles[n])
+    truth = [names[i] for i in rng.choice(len(names), 2, replace=False)]
+    sam = synth.simulate_sam(loc, truth, n_pairs=n_reads // 2, rng=rng, err_rate=0.004)
+    return loc, truth, sam
+
+
+@pytest.mark.parametrize("seed", [3, 4])
+def test_tables_bit_exact_vs_oracle_synthetic(seed):
+    from hisatgenotype_b200 import synth
+    from hisatgenotype_b200 import typing_core as TC
+    if not hasattr(synth, "simulate_sam"):
+        pytest.skip("synthetic SAM generator not built yet")
+    loc, truth, sam = _synthetic_case(seed)
+    cont = synth.reference_containers([loc], "hla")
+    gene = "A"
+    args = ("hla", gene, cont["refGenes"][gene], cont["Genes"][gene][cont["refGenes"][gene]], cont["Vars"][gene],
+            cont["Var_list"][gene], cont["Links"], cont["Gene_names"][gene], cont["Gene_lengths"][gene],
+            cont["refGene_loci"][gene][4], cont["refGene_loci"][gene][5])
+    ol = O.OracleLocus(*args)
+    from hisatgenotype_b200.locus import LocusTables
+    t = LocusTables(*args)
+    ref = O.type_locus(ol, sam, simulation=False)
+    run = TC.type_locus(t, sam)
+    assert run.num_reads == ref["num_reads"] and run.num_pairs == ref["num_pairs"]
+    for tb, key in ((TC.TABLE_GENE, "gene"), (TC.TABLE_EXON, "exon"), (TC.TABLE_PRIMARY, "primary")):
+        assert list(map(list, run.gene_cmpt(tb).items())) == ref["tables"][key].cmpt_items(ol)
+        assert run.gene_counts(tb) == ref["tables"][key].count_items(ol)
+    run.close()
+    t.close()
