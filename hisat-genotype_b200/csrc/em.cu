@@ -42,6 +42,9 @@ struct EmArgs {
     const double *len;
     int C, A, wp, remove_low, fixed_iters;
     int slab_rows;  // rows per slab buffer
+    const unsigned long long *cnt_u64;  // class counts as integers (device-resident tables); overrides cnt
+    const int32_t *C_ptr;               // number of classes read on the device at launch; overrides C
+    const int32_t *class_first;         // tie-break key of each class (first pair index); default = class index
     double *prob;
     uint8_t *in_result;
     int32_t *first_class;
@@ -152,7 +155,7 @@ __device__ void em_sweep(const EmArgs &a, const Smem &sm, int mode, const double
             if (lane == 0) {
                 const bool ok = s > 0.0;
                 sm.valid[r] = ok ? 1 : 0;
-                sm.w[r] = ok ? a.cnt[r0 + r] / s : 0.0;
+                sm.w[r] = ok ? (a.cnt_u64 ? (double)a.cnt_u64[r0 + r] : a.cnt[r0 + r]) / s : 0.0;
             }
         }
         __syncthreads();
@@ -160,12 +163,13 @@ __device__ void em_sweep(const EmArgs &a, const Smem &sm, int mode, const double
         if (mode == MODE_FIRSTK) {
             for (int r = 0; r < nr; r++) {
                 if (!sm.valid[r]) continue;
+                const int32_t key = a.class_first ? a.class_first[r0 + r] : r0 + r;
 #pragma unroll
                 for (int i = 0; i < NA; i++) {
                     const int al = tid + i * EM_THREADS;
-                    if (al < A && fk[i] == FK_NONE) {
+                    if (al < A) {
                         const uint32_t w32 = slab32[(size_t)r * wp * 2 + (al >> 5)];
-                        if ((w32 >> (al & 31)) & 1u) fk[i] = r0 + r;
+                        if ((w32 >> (al & 31)) & 1u) fk[i] = min(fk[i], key);
                     }
                 }
             }
@@ -300,7 +304,8 @@ __device__ void em_prune(const EmArgs &a, const Smem &sm, double *p, uint8_t *li
 template <int NA, bool COOP>
 __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restrict__ args_arr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const EmArgs a = COOP ? args_arr[0] : args_arr[blockIdx.x];
+    EmArgs a = COOP ? args_arr[0] : args_arr[blockIdx.x];
+    if (a.C_ptr) a.C = min(*a.C_ptr, a.C);
     const int tid = threadIdx.x;
     const int Apad = a.wp * 64;
     Smem sm;
@@ -570,6 +575,7 @@ extern "C" int hgt_em_dev(hgt_ctx *ctx, void *stream, const uint64_t *class_bits
     a.bits = class_bits; a.cnt = class_count; a.len = allele_len;
     a.C = n_classes; a.A = n_alleles; a.wp = wp; a.remove_low = remove_low; a.fixed_iters = fixed_iters;
     a.slab_rows = plan.slab_rows;
+    a.cnt_u64 = nullptr; a.C_ptr = nullptr; a.class_first = nullptr;
     a.prob = prob; a.in_result = in_result; a.first_class = first_class; a.iters_status = iters_status;
     a.vec = w.vec; a.live = w.live; a.part_acc = w.part_acc; a.part_aux = w.part_aux;
     a.red_acc = w.red_acc; a.red_aux = w.red_aux;
@@ -685,6 +691,7 @@ extern "C" int hgt_em_batch(hgt_ctx *ctx, int32_t n_problems, const uint64_t *cl
         a.len = allele_len ? reinterpret_cast<double *>(d + o_len) + allele_off[i] : nullptr;
         a.C = C; a.A = A; a.wp = wp; a.remove_low = remove_low ? remove_low[i] : 0; a.fixed_iters = 0;
         a.slab_rows = plan.slab_rows;
+        a.cnt_u64 = nullptr; a.C_ptr = nullptr; a.class_first = nullptr;
         a.prob = reinterpret_cast<double *>(d + o_prob) + allele_off[i];
         a.in_result = d + o_in + allele_off[i];
         a.first_class = reinterpret_cast<int32_t *>(d + o_fk) + allele_off[i];
@@ -725,4 +732,45 @@ extern "C" int hgt_em_batch(hgt_ctx *ctx, int32_t n_problems, const uint64_t *cl
         if (status) status[i] = is[(size_t)i * 3 + 1];
     }
     return HGT_OK;
+}
+
+// ---- internal: batched EM on device-resident class tables (used by typing.cu) ----------------------------------
+#include "em_internal.h"
+
+size_t hgt_em_batch_ws_bytes(int n_problems, int wp) {
+    const size_t Apad = (size_t)wp * 64;
+    return align_up((size_t)n_problems * sizeof(EmArgs), 256) + (size_t)n_problems * 4 * Apad * 8 +
+           (size_t)n_problems * 4 * Apad;
+}
+
+int hgt_em_batch_dev(hgt_ctx *ctx, cudaStream_t st, int n_problems, const EmDevProblem *pr, int wp, void *ws) {
+    if (n_problems <= 0) return HGT_OK;
+    const size_t Apad = (size_t)wp * 64;
+    std::vector<EmArgs> args(n_problems);
+    unsigned char *d = static_cast<unsigned char *>(ws);
+    EmArgs *d_args = reinterpret_cast<EmArgs *>(d);
+    double *vec = reinterpret_cast<double *>(d + align_up((size_t)n_problems * sizeof(EmArgs), 256));
+    uint8_t *live = reinterpret_cast<uint8_t *>(vec + (size_t)n_problems * 4 * Apad);
+    int na = 1;
+    size_t smem = 0;
+    for (int i = 0; i < n_problems; i++) {
+        EmPlan plan;
+        HGT_CHECK(em_plan(ctx, pr[i].C_max < 1 ? 1 : pr[i].C_max, (int)Apad, wp, &plan));
+        na = plan.na;
+        if (plan.smem > smem) smem = plan.smem;
+        EmArgs &a = args[i];
+        a.bits = pr[i].bits; a.cnt = nullptr; a.len = pr[i].len;
+        a.C = pr[i].C_max; a.A = pr[i].A; a.wp = wp; a.remove_low = pr[i].remove_low; a.fixed_iters = 0;
+        a.slab_rows = plan.slab_rows;
+        a.cnt_u64 = pr[i].cnt; a.C_ptr = pr[i].C_ptr; a.class_first = pr[i].class_first;
+        a.prob = pr[i].prob; a.in_result = pr[i].in_result; a.first_class = pr[i].first_class;
+        a.iters_status = pr[i].iters_status;
+        a.vec = vec + (size_t)i * 4 * Apad;
+        a.live = live + (size_t)i * 4 * Apad;
+        a.part_acc = nullptr; a.part_aux = nullptr; a.red_acc = nullptr; a.red_aux = nullptr;
+    }
+    // the argument block must outlive the async copy: stage it in pinned memory owned by the context
+    HGT_CUDA(cudaMemcpyAsync(d_args, args.data(), (size_t)n_problems * sizeof(EmArgs), cudaMemcpyHostToDevice, st));
+    HGT_CUDA(cudaStreamSynchronize(st));
+    return em_launch<false>(ctx, st, d_args, n_problems, na, smem);
 }

@@ -18,7 +18,9 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
 #include <numeric>
+#include <thread>
 #include <string>
 #include <string_view>
 #include <unordered_map>
@@ -26,6 +28,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "em_internal.h"
 #include "walk.hpp"
 
 using namespace hgt;
@@ -40,6 +43,9 @@ struct hgt_locus {
     std::vector<uint64_t> mask;  // [3][wp]
     std::vector<int32_t> gn_rank;
     std::vector<int32_t> delr_right, delr_row;
+    std::vector<int64_t> group_off;      // [A+1] members of the exon group represented by allele a (allele_rep_groups)
+    std::vector<int32_t> group_member;
+    std::vector<double> allele_len;      // [A] Gene_lengths
     hgt_ctx *ctx = nullptr;
     int32_t *d_var_pos = nullptr, *d_delr_right = nullptr, *d_delr_row = nullptr, *d_gn_rank = nullptr;
     uint64_t *d_st = nullptr, *d_mask = nullptr;
@@ -223,6 +229,13 @@ extern "C" int hgt_locus_create(hgt_ctx *ctx, const hgt_locus_desc *d, hgt_locus
         l->delr_row.push_back(r);
     }
     l->n_delr = (int)order.size();
+    l->group_off.assign(l->A + 1, 0);
+    if (d->group_off && d->group_member) {
+        l->group_off.assign(d->group_off, d->group_off + l->A + 1);
+        l->group_member.assign(d->group_member, d->group_member + d->group_off[l->A]);
+    }
+    l->allele_len.assign(l->A, 1.0);
+    if (d->allele_len) l->allele_len.assign(d->allele_len, d->allele_len + l->A);
     if (!ctx) {
         *out = l;
         return HGT_OK;
@@ -518,13 +531,15 @@ constexpr int WARPS_PER_CTA = 8;
 // ---- pileup (common:1100-1121): warp per record, lanes over the bases of each CIGAR op -------------------
 __global__ void pileup_kernel(const int32_t *__restrict__ pos, const int64_t *__restrict__ cig_off,
                               const uint32_t *__restrict__ cig, const int64_t *__restrict__ seq_off,
-                              const char *__restrict__ seq, int64_t n_rec, int L, uint32_t *__restrict__ counts) {
+                              const char *__restrict__ seq, const int32_t *__restrict__ rec_unit, int64_t n_rec, int L,
+                              uint32_t *__restrict__ counts_all) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t r = warp0; r < n_rec; r += nwarps) {
         int gpos = pos[r];
         int64_t rpos = seq_off[r];
+        uint32_t *counts = counts_all + (size_t)rec_unit[r] * L * 6;
         for (int64_t c = cig_off[r]; c < cig_off[r + 1]; c++) {
             const uint32_t x = cig[c];
             const int len = (int)(x >> 4), op = (int)(x & 15u);
@@ -547,21 +562,6 @@ __global__ void pileup_kernel(const int32_t *__restrict__ pos, const int64_t *__
     }
 }
 
-// representative bases (common:1124-1134): depth >= 20 and (count >= depth*0.2 or count >= 7)
-__global__ void ntset_kernel(const uint32_t *__restrict__ counts, int L, uint8_t *__restrict__ mask) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= L) return;
-    const uint32_t *c = counts + (size_t)i * 6;
-    const uint32_t depth = c[0] + c[1] + c[2] + c[3] + c[4] + c[5];
-    uint8_t m = 0;
-    if (depth >= 20) {
-        const double thr = (double)depth * 0.2;  // same IEEE product as Python's num_nt * 0.2
-        for (int k = 0; k < 4; k++)
-            if ((double)c[k] >= thr || c[k] >= 7) m |= (uint8_t)(1u << k);
-    }
-    mask[i] = m;
-}
-
 __device__ __forceinline__ int lower_bound_dev(const int32_t *a, int n, int key) {
     int lo = 0, hi = n;
     while (lo < hi) {
@@ -576,7 +576,8 @@ __device__ __forceinline__ int lower_bound_dev(const int32_t *a, int n, int key)
 // warp per haplotype; lane l owns words l, l+32, ... of the row (WPL words per lane).
 template <int WPL>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-    compat_kernel(LocusDev loc, int table, const int32_t *__restrict__ hap_left, const int32_t *__restrict__ hap_right,
+    compat_kernel(LocusDev loc, const int32_t *__restrict__ hap_table, const int32_t *__restrict__ hap_left,
+                  const int32_t *__restrict__ hap_right,
                   const int64_t *__restrict__ row_off, const int32_t *__restrict__ rows, int64_t n_haps,
                   uint64_t *__restrict__ out) {
     extern __shared__ __align__(16) int32_t s_pos[];  // var_pos staged once per CTA (persistent grid)
@@ -585,12 +586,12 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
     const int lane = threadIdx.x & 31;
     const int wp = loc.wp;
     const size_t lvl = (size_t)max(loc.V, 1) * wp;
-    const uint64_t *mask = loc.mask + (size_t)table * wp;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t h = warp0; h < n_haps; h += nwarps) {
         const int left = hap_left[h], right = hap_right[h];
         const int64_t r0 = row_off[h], r1 = row_off[h + 1];
+        const uint64_t *mask = loc.mask + (size_t)hap_table[h] * wp;
         uint64_t acc[WPL], neg[WPL];
 #pragma unroll
         for (int i = 0; i < WPL; i++) {
@@ -658,16 +659,18 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 }
 
 // ---- per-pair class (add_stat, core:1171-1236) + de-duplication --------------------------------------------
+// Classes of every (unit, table) are de-duplicated through one open-addressing hash table per locus batch; the
+// rows of table `ut` are allocated contiguously inside a region reserved for it (its number of pairs bounds the
+// number of classes), so the EM kernel can stream them without a gather.
 struct ClassPool {
     unsigned long long *keys;  // open-addressing table, 0 = empty
-    int32_t *slot_class;       // class id once its row is written, -1 before
+    int32_t *slot_class;       // absolute class row once its bits are written, -1 before
     uint32_t cap_mask;
-    uint64_t *bits;            // [max_classes][wp]
-    unsigned long long *count;
-    int32_t *first;            // first pair index
-    int32_t *table;            // table id of the class
-    int32_t *n_classes;
-    int32_t max_classes;
+    uint64_t *bits;            // [rows][wp]
+    unsigned long long *count; // [rows]
+    int32_t *first;            // [rows] first pair index
+    const int64_t *ut_base;    // [n_ut] first row of each (unit, table) region
+    int32_t *ut_ncls;          // [n_ut] classes created so far
 };
 
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {
@@ -675,18 +678,89 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
     return x;
 }
 
-// warp per job; a job = (pair, table) with a list of haplotype bitsets; P bit-planes count up to 2^P-1
+// Insert bitset `best` (WPL words per lane) into table `ut`; adds `add` to its count and lowers its first index.
+template <int WPL>
+__device__ __forceinline__ void pool_insert(const ClassPool &pool, int wp, int ut, const uint64_t (&best)[WPL],
+                                            unsigned long long add, int first, int lane) {
+    uint64_t hsh = 0;
+#pragma unroll
+    for (int i = 0; i < WPL; i++) {
+        const int j = lane + 32 * i;
+        if (j < wp) hsh += mix64(best[i] + 0x9e3779b97f4a7c15ULL * (uint64_t)(j + 1));
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) hsh += __shfl_xor_sync(0xffffffffu, hsh, o);
+    const unsigned long long key = mix64(hsh + 0x632be59bd9b4e019ULL * (uint64_t)(ut + 1)) | 1ull;
+    uint32_t slot = (uint32_t)(key >> 20) & pool.cap_mask;
+    const int64_t base = pool.ut_base[ut], limit = pool.ut_base[ut + 1];
+    int64_t cid = -1;
+    while (true) {
+        unsigned long long prev = 0;
+        if (lane == 0) prev = atomicCAS(&pool.keys[slot], 0ull, key);
+        prev = __shfl_sync(0xffffffffu, prev, 0);
+        if (prev == 0ull) {  // we own the slot: publish a new class row
+            int c = 0;
+            if (lane == 0) c = atomicAdd(&pool.ut_ncls[ut], 1);
+            c = __shfl_sync(0xffffffffu, c, 0);
+            cid = base + c;
+            if (cid < limit) {
+#pragma unroll
+                for (int i = 0; i < WPL; i++) {
+                    const int j = lane + 32 * i;
+                    if (j < wp) pool.bits[(size_t)cid * wp + j] = best[i];
+                }
+                __threadfence();
+                __syncwarp();
+                if (lane == 0) atomicExch(&pool.slot_class[slot], (int32_t)cid);
+            }
+            break;
+        }
+        if (prev == key) {
+            int c = -1;
+            if (lane == 0) {
+                while ((c = *((volatile int32_t *)&pool.slot_class[slot])) < 0) {
+                }
+                __threadfence();
+            }
+            c = __shfl_sync(0xffffffffu, c, 0);
+            // the slot holds a published (fully written) row; it is ours iff it lies in our table's region and
+            // carries the same bits
+            bool same = c >= base && c < limit;
+            if (same) {
+#pragma unroll
+                for (int i = 0; i < WPL; i++) {
+                    const int j = lane + 32 * i;
+                    if (j < wp) same &= (__ldcg(&pool.bits[(size_t)c * wp + j]) == best[i]);
+                }
+            }
+            if (__all_sync(0xffffffffu, same)) {
+                cid = c;
+                break;
+            }
+        }
+        slot = (slot + 1) & pool.cap_mask;
+    }
+    if (lane == 0 && cid < limit) {
+        atomicAdd(&pool.count[cid], add);
+        atomicMin(&pool.first[cid], first);
+    }
+}
+
+// warp per job; a job = (unit, table, pair) with a list of haplotype bitsets; P bit-planes count up to 2^P-1
 template <int WPL, int P>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
-    class_kernel(int wp, const uint64_t *__restrict__ mask, int table, const int64_t *__restrict__ job_off,
+    class_kernel(int wp, const uint64_t *__restrict__ masks, const int64_t *__restrict__ job_off,
+                 const int32_t *__restrict__ job_ut, const int32_t *__restrict__ job_pair,
                  const int32_t *__restrict__ job_list, int64_t n_jobs, const uint64_t *__restrict__ hapbits,
                  ClassPool pool) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t q = warp0; q < n_jobs; q += nwarps) {
-        const int pair = job_list ? job_list[q] : (int)q;
-        const int64_t h0 = job_off[pair], h1 = job_off[pair + 1];
+        const int job = job_list[q];
+        const int64_t h0 = job_off[job], h1 = job_off[job + 1];
+        const int ut = job_ut[job];
+        const uint64_t *mask = masks + (size_t)(ut % 3) * wp;
         uint64_t plane[P][WPL], best[WPL];
 #pragma unroll
         for (int p = 0; p < P; p++)
@@ -720,106 +794,90 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
                 for (int i = 0; i < WPL; i++) best[i] &= plane[p][i];
             }
         }
-        // hash of the class bitset
-        uint64_t hsh = 0;
+        pool_insert<WPL>(pool, wp, ut, best, 1ull, job_pair[job], lane);
+    }
+}
+
+// Projection of the Gene table onto a kept allele set (core:1753-1766): every class of table src_ut is ANDed with
+// the unit's keep mask and inserted (count added, first index lowered) into table dst_ut; empty results vanish.
+template <int WPL>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+    project_kernel(int wp, int n_units, const int32_t *__restrict__ unit_list, const uint64_t *__restrict__ keep,
+                   ClassPool pool) {
+    const int lane = threadIdx.x & 31;
+    const int warp = threadIdx.x >> 5;
+    for (int ui = blockIdx.y; ui < n_units; ui += gridDim.y) {
+        const int u = unit_list[ui];
+        const int src = u * 4 + 0, dst = u * 4 + 3;
+        const int n = min(__ldcg(&pool.ut_ncls[src]), (int)(pool.ut_base[src + 1] - pool.ut_base[src]));
+        const int64_t base = pool.ut_base[src];
+        for (int k = blockIdx.x * WARPS_PER_CTA + warp; k < n; k += gridDim.x * WARPS_PER_CTA) {
+            uint64_t row[WPL];
+            uint64_t any = 0;
 #pragma unroll
-        for (int i = 0; i < WPL; i++) {
-            const int j = lane + 32 * i;
-            if (j < wp) hsh += mix64(best[i] + 0x9e3779b97f4a7c15ULL * (uint64_t)(j + 1));
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) hsh += __shfl_xor_sync(0xffffffffu, hsh, o);
-        const unsigned long long key = mix64(hsh + 0x632be59bd9b4e019ULL * (uint64_t)(table + 1)) | 1ull;
-        uint32_t slot = (uint32_t)(key >> 20) & pool.cap_mask;
-        int cid = -1;
-        while (true) {
-            unsigned long long prev = 0;
-            if (lane == 0) prev = atomicCAS(&pool.keys[slot], 0ull, key);
-            prev = __shfl_sync(0xffffffffu, prev, 0);
-            if (prev == 0ull) {  // we own the slot: publish a new class
-                int c = 0;
-                if (lane == 0) c = atomicAdd(pool.n_classes, 1);
-                c = __shfl_sync(0xffffffffu, c, 0);
-                if (c < pool.max_classes) {
-#pragma unroll
-                    for (int i = 0; i < WPL; i++) {
-                        const int j = lane + 32 * i;
-                        if (j < wp) pool.bits[(size_t)c * wp + j] = best[i];
-                    }
-                    if (lane == 0) pool.table[c] = table;
-                    __threadfence();
-                    __syncwarp();
-                    if (lane == 0) atomicExch(&pool.slot_class[slot], c);
-                }
-                cid = c;
-                break;
+            for (int i = 0; i < WPL; i++) {
+                const int j = lane + 32 * i;
+                row[i] = j < wp ? (pool.bits[(size_t)(base + k) * wp + j] & keep[(size_t)ui * wp + j]) : 0ull;
+                any |= row[i];
             }
-            if (prev == key) {
-                int c = -1;
-                if (lane == 0) {
-                    while ((c = *((volatile int32_t *)&pool.slot_class[slot])) < 0) {
-                    }
-                    __threadfence();
-                }
-                c = __shfl_sync(0xffffffffu, c, 0);
-                bool same = __ldcg(&pool.table[c]) == table;
-#pragma unroll
-                for (int i = 0; i < WPL; i++) {
-                    const int j = lane + 32 * i;
-                    if (j < wp) same &= (__ldcg(&pool.bits[(size_t)c * wp + j]) == best[i]);
-                }
-                if (__all_sync(0xffffffffu, same)) {
-                    cid = c;
-                    break;
-                }
-            }
-            slot = (slot + 1) & pool.cap_mask;
-        }
-        if (lane == 0 && cid < pool.max_classes) {
-            atomicAdd(&pool.count[cid], 1ull);
-            atomicMin(&pool.first[cid], pair);
+            if (!__any_sync(0xffffffffu, any != 0ull)) continue;
+            pool_insert<WPL>(pool, wp, dst, row, pool.count[base + k], pool.first[base + k], lane);
         }
     }
 }
 
-// Gene_counts (core:1187-1190): counts[a] = sum of class counts over classes holding a; first[a] = first pair
-__global__ void table_counts_kernel(int A, int wp, const int32_t *__restrict__ cls_idx, int n_cls,
-                                    const uint64_t *__restrict__ bits, const unsigned long long *__restrict__ count,
-                                    const int32_t *__restrict__ first, long long *__restrict__ a_count,
-                                    long long *__restrict__ a_first) {
+// Gene_counts (core:1187-1190) of table (unit, 0): counts[a] = sum of class counts over classes holding a;
+// first[a] = first pair whose class holds a.  grid.y = unit.
+__global__ void table_counts_kernel(int A, int wp, int table, ClassPool pool, long long *__restrict__ a_count,
+                                    int32_t *__restrict__ a_first) {
+    const int u = blockIdx.y;
+    const int ut = u * 4 + table;
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
     if (a >= A) return;
-    long long c = 0, f = 0x7fffffffffffffffLL;
-    for (int k = 0; k < n_cls; k++) {
-        const int id = cls_idx[k];
-        const uint64_t w = bits[(size_t)id * wp + (a >> 6)];
+    const int64_t base = pool.ut_base[ut];
+    const int n = min(pool.ut_ncls[ut], (int)(pool.ut_base[ut + 1] - base));
+    long long c = 0;
+    int32_t f = 0x7fffffff;
+    for (int k = 0; k < n; k++) {
+        const uint64_t w = pool.bits[(size_t)(base + k) * wp + (a >> 6)];
         if ((w >> (a & 63)) & 1ull) {
-            c += (long long)count[id];
-            f = min(f, (long long)first[id]);
+            c += (long long)pool.count[base + k];
+            f = min(f, pool.first[base + k]);
         }
     }
-    a_count[a] = c;
-    a_first[a] = c ? f : -1;
+    a_count[(size_t)u * A + a] = c;
+    a_first[(size_t)u * A + a] = c ? f : -1;
 }
 
-__global__ void gather_rows_kernel(int wp, const int32_t *__restrict__ idx, int n, const uint64_t *__restrict__ src,
-                                   uint64_t *__restrict__ dst) {
-    const size_t total = (size_t)n * wp;
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
-        const int r = (int)(i / wp), j = (int)(i % wp);
-        dst[i] = src[(size_t)idx[r] * wp + j];
+// pileup-derived per-position flags the host walk needs: nt_set mask and the hla deletion-artefact flag
+// (core:1064-1077: del_count * 6 < nt_count)
+__global__ void pileup_flags_kernel(const uint32_t *__restrict__ counts, int64_t n_pos, uint8_t *__restrict__ mask,
+                                    uint8_t *__restrict__ del_artefact) {
+    const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (i >= n_pos) return;
+    const uint32_t *c = counts + (size_t)i * 6;
+    const uint32_t depth = c[0] + c[1] + c[2] + c[3] + c[4] + c[5];
+    uint8_t m = 0;
+    if (depth >= 20) {
+        const double thr = (double)depth * 0.2;  // same IEEE product as Python's num_nt * 0.2
+        for (int k = 0; k < 4; k++)
+            if ((double)c[k] >= thr || c[k] >= 7) m |= (uint8_t)(1u << k);
     }
+    mask[i] = m;
+    const uint64_t dels = c[5], nts = (uint64_t)c[0] + c[1] + c[2] + c[3] + c[4];
+    del_artefact[i] = dels * 6 < nts ? 1 : 0;
 }
 
 }  // namespace
 
 // ================================================================================================================
-// Device arena helper
+// Device buffers
 // ================================================================================================================
 struct DevBuf {
     void *p = nullptr;
     size_t bytes = 0;
     int alloc(size_t n) {
+        release();
         bytes = n;
         if (n == 0) n = 16;
         cudaError_t e = cudaMalloc(&p, n);
@@ -833,6 +891,7 @@ struct DevBuf {
     void release() {
         if (p) cudaFree(p);
         p = nullptr;
+        bytes = 0;
     }
     template <class T>
     T *as() const { return static_cast<T *>(p); }
@@ -845,90 +904,741 @@ static int upload(DevBuf *b, const std::vector<T> &v, cudaStream_t st) {
     return HGT_OK;
 }
 
+static int wpl_of(int wp) {
+    const int w = (wp + 31) / 32;
+    return w <= 1 ? 1 : w <= 2 ? 2 : w <= 4 ? 4 : 8;
+}
+
 // ================================================================================================================
-// Typing result
+// Batch of (sample, locus) units
+// ================================================================================================================
+struct UnitHost {
+    int locus = 0;
+    const char *sam = nullptr;
+    size_t n_bytes = 0;
+    Intake in;
+    HostOut ho;
+    int rc = HGT_OK;
+    std::string err;
+    int local = 0;  // index inside its locus batch
+    std::vector<uint8_t> nt_mask, del_flag;
+    std::vector<uint32_t> counts;  // kept only when requested (single-unit API / tests)
+};
+
+struct LocusBatch {
+    hgt_locus *loc = nullptr;
+    std::vector<int> units;  // global unit ids
+    // jobs of all units and tables of this locus
+    std::vector<int64_t> job_off{0};
+    std::vector<int32_t> job_ut, job_pair, job_small, job_big;
+    std::vector<int32_t> hap_left, hap_right, hap_table;
+    std::vector<int64_t> row_off{0};
+    std::vector<int32_t> rows;
+    std::vector<int64_t> ut_base;  // [n_units*4 + 1]
+    int64_t n_rows_pool = 0;
+    // device
+    DevBuf d_job_off, d_job_ut, d_job_pair, d_job_list, d_hl, d_hr, d_ht, d_ro, d_rows, d_hapbits;
+    DevBuf d_keys, d_slot, d_bits, d_count, d_first, d_ut_base, d_ut_ncls;
+    DevBuf d_prob, d_inres, d_fk, d_is, d_emws, d_len;      // EM over exon (hla) / gene (other) tables
+    DevBuf d_prob2, d_inres2, d_fk2, d_is2, d_emws2, d_keep, d_ulist;  // second-level EM (hla)
+    DevBuf d_acount, d_afirst;
+    uint32_t cap = 0;
+    std::vector<int32_t> ut_ncls;  // host copy after finish
+    std::vector<double> prob, prob2;
+    std::vector<uint8_t> inres, inres2;
+    std::vector<int32_t> fk, fk2, is, is2;
+    std::vector<uint8_t> has2;  // unit ran the second-level EM
+    void release() {
+        DevBuf *all[] = {&d_job_off, &d_job_ut, &d_job_pair, &d_job_list, &d_hl, &d_hr, &d_ht, &d_ro, &d_rows, &d_hapbits,
+                         &d_keys, &d_slot, &d_bits, &d_count, &d_first, &d_ut_base, &d_ut_ncls, &d_prob, &d_inres, &d_fk,
+                         &d_is, &d_emws, &d_len, &d_prob2, &d_inres2, &d_fk2, &d_is2, &d_emws2, &d_keep, &d_ulist,
+                         &d_acount, &d_afirst};
+        for (DevBuf *b : all) b->release();
+    }
+    ClassPool pool() const {
+        ClassPool p;
+        p.keys = d_keys.as<unsigned long long>(); p.slot_class = d_slot.as<int32_t>(); p.cap_mask = cap - 1;
+        p.bits = d_bits.as<uint64_t>(); p.count = d_count.as<unsigned long long>(); p.first = d_first.as<int32_t>();
+        p.ut_base = d_ut_base.as<int64_t>(); p.ut_ncls = d_ut_ncls.as<int32_t>();
+        return p;
+    }
+};
+
+struct hgt_batch {
+    hgt_ctx *ctx = nullptr;
+    hgt_params params;
+    std::vector<hgt_locus *> loci;
+    std::vector<UnitHost> units;
+    std::vector<LocusBatch> lb;
+    bool keep_counts = false;
+    bool prepared = false, executed = false, finished = false;
+    int remove_low = 1;
+    std::vector<double> allele_len_host;  // unused placeholder
+    ~hgt_batch() {
+        if (ctx) cudaSetDevice(ctx->device);
+        for (LocusBatch &b : lb) b.release();
+    }
+};
+
+static void set_unit_error(UnitHost &u, int rc) {
+    u.rc = rc;
+    u.err = hgt_last_error();
+}
+
+// Parallel-for over units on host threads (intake and walk are independent per unit).
+template <class F>
+static void parallel_units(int n_threads, size_t n, F f) {
+    if (n_threads <= 1 || n <= 1) {
+        for (size_t i = 0; i < n; i++) f(i);
+        return;
+    }
+    std::atomic<size_t> next{0};
+    std::vector<std::thread> th;
+    const int nt = (int)std::min<size_t>(n_threads, n);
+    for (int t = 0; t < nt; t++)
+        th.emplace_back([&]() {
+            while (true) {
+                const size_t i = next.fetch_add(1);
+                if (i >= n) break;
+                f(i);
+            }
+        });
+    for (auto &x : th) x.join();
+}
+
+static int batch_threads(const hgt_params &p) {
+    if (p.n_threads > 0) return p.n_threads;
+    const unsigned hc = std::thread::hardware_concurrency();
+    return hc ? (int)hc : 1;
+}
+
+// ---- stage 1: intake + pileup (GPU) + walk (host threads) + job upload -----------------------------------------
+static int batch_prepare(hgt_batch *b) {
+    hgt_ctx *ctx = b->ctx;
+    cudaStream_t st = ctx->stream;
+    const int nthreads = batch_threads(b->params);
+    const size_t nu = b->units.size();
+    b->lb.assign(b->loci.size(), LocusBatch());
+    for (size_t l = 0; l < b->loci.size(); l++) b->lb[l].loc = b->loci[l];
+    for (size_t u = 0; u < nu; u++) {
+        LocusBatch &lb = b->lb[b->units[u].locus];
+        b->units[u].local = (int)lb.units.size();
+        lb.units.push_back((int)u);
+    }
+    // intake (parallel)
+    parallel_units(nthreads, nu, [&](size_t u) {
+        UnitHost &U = b->units[u];
+        const int rc = intake(U.sam, U.n_bytes, b->params, &U.in);
+        if (rc != HGT_OK) set_unit_error(U, rc);
+    });
+    for (UnitHost &U : b->units)
+        if (U.rc != HGT_OK) {
+            hgt_set_error("%s", U.err.c_str());
+            return U.rc;
+        }
+    // pileup per locus batch: one launch over the records of all its units
+    for (LocusBatch &lb : b->lb) {
+        if (lb.units.empty()) continue;
+        const int L = lb.loc->L;
+        const size_t n_units = lb.units.size();
+        std::vector<PileupIn> pis(n_units);
+        std::vector<int> rcs(n_units, HGT_OK);
+        std::vector<std::string> errs(n_units);
+        parallel_units(nthreads, n_units, [&](size_t i) {
+            rcs[i] = build_pileup_input(b->units[lb.units[i]].in, b->params, &pis[i]);
+            if (rcs[i] != HGT_OK) errs[i] = hgt_last_error();
+        });
+        for (size_t i = 0; i < n_units; i++)
+            if (rcs[i] != HGT_OK) {
+                hgt_set_error("%s", errs[i].c_str());
+                return rcs[i];
+            }
+        PileupIn all;
+        std::vector<int32_t> rec_unit;
+        for (size_t i = 0; i < n_units; i++) {
+            const PileupIn &p = pis[i];
+            const int64_t c0 = (int64_t)all.cig.size(), s0 = (int64_t)all.seq.size();
+            all.pos.insert(all.pos.end(), p.pos.begin(), p.pos.end());
+            for (size_t k = 1; k < p.cig_off.size(); k++) all.cig_off.push_back(c0 + p.cig_off[k]);
+            for (size_t k = 1; k < p.seq_off.size(); k++) all.seq_off.push_back(s0 + p.seq_off[k]);
+            all.cig.insert(all.cig.end(), p.cig.begin(), p.cig.end());
+            all.seq.insert(all.seq.end(), p.seq.begin(), p.seq.end());
+            rec_unit.insert(rec_unit.end(), p.pos.size(), (int32_t)i);
+        }
+        DevBuf d_pos, d_co, d_c, d_so, d_s, d_ru, d_cnt, d_m, d_f;
+        int rc = HGT_OK;
+        std::vector<uint8_t> mask(n_units * (size_t)L), flag(n_units * (size_t)L);
+        std::vector<uint32_t> counts;
+        do {
+            if ((rc = upload(&d_pos, all.pos, st)) != HGT_OK) break;
+            if ((rc = upload(&d_co, all.cig_off, st)) != HGT_OK) break;
+            if ((rc = upload(&d_c, all.cig, st)) != HGT_OK) break;
+            if ((rc = upload(&d_so, all.seq_off, st)) != HGT_OK) break;
+            if ((rc = upload(&d_s, all.seq, st)) != HGT_OK) break;
+            if ((rc = upload(&d_ru, rec_unit, st)) != HGT_OK) break;
+            if ((rc = d_cnt.alloc(n_units * (size_t)L * 24)) != HGT_OK) break;
+            if ((rc = d_m.alloc(n_units * (size_t)L)) != HGT_OK) break;
+            if ((rc = d_f.alloc(n_units * (size_t)L)) != HGT_OK) break;
+            cudaError_t e = cudaMemsetAsync(d_cnt.p, 0, n_units * (size_t)L * 24, st);
+            const int64_t n = (int64_t)all.pos.size();
+            if (e == cudaSuccess && n > 0) {
+                const int ctas = (int)std::min<int64_t>((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 8);
+                pileup_kernel<<<ctas, WARPS_PER_CTA * 32, 0, st>>>(d_pos.as<int32_t>(), d_co.as<int64_t>(), d_c.as<uint32_t>(),
+                                                                    d_so.as<int64_t>(), d_s.as<char>(), d_ru.as<int32_t>(), n, L,
+                                                                    d_cnt.as<uint32_t>());
+                ctx->launches++;
+            }
+            const int64_t npos = (int64_t)n_units * L;
+            pileup_flags_kernel<<<(unsigned)((npos + 255) / 256), 256, 0, st>>>(d_cnt.as<uint32_t>(), npos, d_m.as<uint8_t>(),
+                                                                               d_f.as<uint8_t>());
+            ctx->launches++;
+            if (e == cudaSuccess) e = cudaGetLastError();
+            if (e == cudaSuccess) e = cudaMemcpyAsync(mask.data(), d_m.p, mask.size(), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(flag.data(), d_f.p, flag.size(), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess && b->keep_counts) {
+                counts.resize(n_units * (size_t)L * 6);
+                e = cudaMemcpyAsync(counts.data(), d_cnt.p, counts.size() * 4, cudaMemcpyDeviceToHost, st);
+            }
+            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            if (e != cudaSuccess) {
+                hgt_set_error("pileup: %s", cudaGetErrorString(e));
+                rc = HGT_ERR_CUDA;
+            }
+        } while (0);
+        d_pos.release(); d_co.release(); d_c.release(); d_so.release(); d_s.release(); d_ru.release();
+        d_cnt.release(); d_m.release(); d_f.release();
+        if (rc != HGT_OK) return rc;
+        for (size_t i = 0; i < n_units; i++) {
+            UnitHost &U = b->units[lb.units[i]];
+            U.nt_mask.assign(mask.begin() + i * (size_t)L, mask.begin() + (i + 1) * (size_t)L);
+            U.del_flag.assign(flag.begin() + i * (size_t)L, flag.begin() + (i + 1) * (size_t)L);
+            if (b->keep_counts) U.counts.assign(counts.begin() + i * (size_t)L * 6, counts.begin() + (i + 1) * (size_t)L * 6);
+        }
+    }
+    // walk (parallel over units)
+    parallel_units(nthreads, nu, [&](size_t u) {
+        UnitHost &U = b->units[u];
+        const hgt_locus *loc = b->loci[U.locus];
+        PileupView pu;
+        pu.nt_mask = U.nt_mask.data(); pu.del_artefact = U.del_flag.data(); pu.L = loc->L;
+        const int rc = host_walk(loc, U.in, b->params, pu, &U.ho);
+        if (rc != HGT_OK) set_unit_error(U, rc);
+        U.in.recs.clear();
+        U.in.recs.shrink_to_fit();
+    });
+    for (UnitHost &U : b->units)
+        if (U.rc != HGT_OK) {
+            hgt_set_error("%s", U.err.c_str());
+            return U.rc;
+        }
+    // concatenate jobs per locus and upload
+    for (LocusBatch &lb : b->lb) {
+        if (lb.units.empty()) continue;
+        const hgt_locus *loc = lb.loc;
+        const int wp = loc->wp;
+        const int n_tables = loc->is_hla ? 3 : 1;
+        const size_t n_units = lb.units.size();
+        lb.ut_base.assign(n_units * 4 + 1, 0);
+        for (size_t i = 0; i < n_units; i++) {
+            const UnitHost &U = b->units[lb.units[i]];
+            for (int tb = 0; tb < 4; tb++) {
+                const bool active = tb < n_tables || (tb == 3 && loc->is_hla);
+                lb.ut_base[i * 4 + tb + 1] = lb.ut_base[i * 4 + tb] + (active ? U.ho.num_pairs : 0);
+            }
+            for (int tb = 0; tb < n_tables; tb++) {
+                const TableJobs &J = U.ho.tb[tb];
+                const int64_t h0 = (int64_t)lb.hap_left.size(), r0 = (int64_t)lb.rows.size();
+                lb.hap_left.insert(lb.hap_left.end(), J.hap_left.begin(), J.hap_left.end());
+                lb.hap_right.insert(lb.hap_right.end(), J.hap_right.begin(), J.hap_right.end());
+                lb.hap_table.insert(lb.hap_table.end(), J.hap_left.size(), tb);
+                for (size_t k = 1; k < J.row_off.size(); k++) lb.row_off.push_back(r0 + J.row_off[k]);
+                lb.rows.insert(lb.rows.end(), J.rows.begin(), J.rows.end());
+                for (int64_t p = 0; p < U.ho.num_pairs; p++) {
+                    const int64_t k = J.job_off[p + 1] - J.job_off[p];
+                    if (k > 255) {
+                        hgt_set_error("a read pair expands to %lld haplotypes (limit 255)", (long long)k);
+                        return HGT_ERR_UNSUPPORTED;
+                    }
+                    const int32_t job = (int32_t)lb.job_ut.size();
+                    (k <= 7 ? lb.job_small : lb.job_big).push_back(job);
+                    lb.job_ut.push_back((int32_t)(i * 4 + tb));
+                    lb.job_pair.push_back((int32_t)p);
+                    lb.job_off.push_back(h0 + J.job_off[p + 1]);
+                }
+            }
+        }
+        lb.n_rows_pool = lb.ut_base.back();
+        const int64_t n_jobs = (int64_t)lb.job_ut.size();
+        const int64_t H = (int64_t)lb.hap_left.size();
+        lb.cap = 64;
+        while ((int64_t)lb.cap < 2 * std::max<int64_t>(lb.n_rows_pool, 1)) lb.cap <<= 1;
+        std::vector<int32_t> jl(lb.job_small);
+        jl.insert(jl.end(), lb.job_big.begin(), lb.job_big.end());
+        HGT_CHECK(upload(&lb.d_job_off, lb.job_off, st));
+        HGT_CHECK(upload(&lb.d_job_ut, lb.job_ut, st));
+        HGT_CHECK(upload(&lb.d_job_pair, lb.job_pair, st));
+        HGT_CHECK(upload(&lb.d_job_list, jl, st));
+        HGT_CHECK(upload(&lb.d_hl, lb.hap_left, st));
+        HGT_CHECK(upload(&lb.d_hr, lb.hap_right, st));
+        HGT_CHECK(upload(&lb.d_ht, lb.hap_table, st));
+        HGT_CHECK(upload(&lb.d_ro, lb.row_off, st));
+        HGT_CHECK(upload(&lb.d_rows, lb.rows, st));
+        HGT_CHECK(upload(&lb.d_ut_base, lb.ut_base, st));
+        HGT_CHECK(lb.d_hapbits.alloc((size_t)std::max<int64_t>(H, 1) * wp * 8));
+        HGT_CHECK(lb.d_keys.alloc((size_t)lb.cap * 8));
+        HGT_CHECK(lb.d_slot.alloc((size_t)lb.cap * 4));
+        const size_t pr = (size_t)std::max<int64_t>(lb.n_rows_pool, 1);
+        HGT_CHECK(lb.d_bits.alloc(pr * wp * 8));
+        HGT_CHECK(lb.d_count.alloc(pr * 8));
+        HGT_CHECK(lb.d_first.alloc(pr * 4));
+        HGT_CHECK(lb.d_ut_ncls.alloc(n_units * 4 * 4));
+        // EM buffers
+        const size_t A = (size_t)loc->A;
+        HGT_CHECK(lb.d_prob.alloc(n_units * A * 8));
+        HGT_CHECK(lb.d_inres.alloc(n_units * A));
+        HGT_CHECK(lb.d_fk.alloc(n_units * A * 4));
+        HGT_CHECK(lb.d_is.alloc(n_units * 12));
+        HGT_CHECK(lb.d_emws.alloc(hgt_em_batch_ws_bytes((int)n_units, wp)));
+        HGT_CHECK(lb.d_acount.alloc(n_units * A * 8));
+        HGT_CHECK(lb.d_afirst.alloc(n_units * A * 4));
+        (void)n_jobs;
+    }
+    HGT_CUDA(cudaStreamSynchronize(st));
+    b->prepared = true;
+    return HGT_OK;
+}
+
+// ---- stage 2: GPU only, no host synchronisation -----------------------------------------------------------------
+template <int WPL>
+static void launch_stage_a(hgt_ctx *ctx, cudaStream_t st, LocusBatch &lb) {
+    const hgt_locus *loc = lb.loc;
+    const LocusDev ld = locus_dev(loc);
+    const int wp = loc->wp;
+    const int64_t H = (int64_t)lb.hap_left.size();
+    if (H > 0) {
+        const size_t smem = (size_t)std::max(ld.V, 1) * 4;
+        cudaFuncSetAttribute(compat_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        const int ctas = (int)std::min<int64_t>((H + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 4);
+        compat_kernel<WPL><<<ctas, WARPS_PER_CTA * 32, smem, st>>>(ld, lb.d_ht.as<int32_t>(), lb.d_hl.as<int32_t>(),
+                                                                   lb.d_hr.as<int32_t>(), lb.d_ro.as<int64_t>(),
+                                                                   lb.d_rows.as<int32_t>(), H, lb.d_hapbits.as<uint64_t>());
+        ctx->launches++;
+    }
+    const ClassPool pool = lb.pool();
+    const int64_t ns = (int64_t)lb.job_small.size(), nb = (int64_t)lb.job_big.size();
+    if (ns > 0) {
+        const int ctas = (int)std::min<int64_t>((ns + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 8);
+        class_kernel<WPL, 3><<<ctas, WARPS_PER_CTA * 32, 0, st>>>(wp, loc->d_mask, lb.d_job_off.as<int64_t>(),
+                                                                  lb.d_job_ut.as<int32_t>(), lb.d_job_pair.as<int32_t>(),
+                                                                  lb.d_job_list.as<int32_t>(), ns, lb.d_hapbits.as<uint64_t>(), pool);
+        ctx->launches++;
+    }
+    if (nb > 0) {
+        const int ctas = (int)std::min<int64_t>((nb + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 8);
+        class_kernel<WPL, 8><<<ctas, WARPS_PER_CTA * 32, 0, st>>>(wp, loc->d_mask, lb.d_job_off.as<int64_t>(),
+                                                                  lb.d_job_ut.as<int32_t>(), lb.d_job_pair.as<int32_t>(),
+                                                                  lb.d_job_list.as<int32_t>() + ns, nb, lb.d_hapbits.as<uint64_t>(), pool);
+        ctx->launches++;
+    }
+}
+
+static int em_on_table(hgt_ctx *ctx, cudaStream_t st, LocusBatch &lb, int table, const std::vector<int> &local_units,
+                       const double *d_len, int remove_low, DevBuf &prob, DevBuf &inres, DevBuf &fk, DevBuf &is, DevBuf &ws) {
+    const hgt_locus *loc = lb.loc;
+    const size_t A = (size_t)loc->A;
+    std::vector<EmDevProblem> pr(local_units.size());
+    for (size_t k = 0; k < local_units.size(); k++) {
+        const int i = local_units[k];
+        const int ut = i * 4 + table;
+        EmDevProblem &p = pr[k];
+        p.bits = lb.d_bits.as<uint64_t>() + (size_t)lb.ut_base[ut] * loc->wp;
+        p.cnt = lb.d_count.as<unsigned long long>() + lb.ut_base[ut];
+        p.class_first = lb.d_first.as<int32_t>() + lb.ut_base[ut];
+        p.C_ptr = lb.d_ut_ncls.as<int32_t>() + ut;
+        p.C_max = (int)(lb.ut_base[ut + 1] - lb.ut_base[ut]);
+        p.A = loc->A;
+        p.len = d_len;
+        p.remove_low = remove_low;
+        p.prob = prob.as<double>() + (size_t)i * A;
+        p.in_result = inres.as<uint8_t>() + (size_t)i * A;
+        p.first_class = fk.as<int32_t>() + (size_t)i * A;
+        p.iters_status = is.as<int32_t>() + (size_t)i * 3;
+    }
+    return hgt_em_batch_dev(ctx, st, (int)pr.size(), pr.data(), loc->wp, ws.p);
+}
+
+static int batch_execute(hgt_batch *b, cudaStream_t st) {
+    hgt_ctx *ctx = b->ctx;
+    for (LocusBatch &lb : b->lb) {
+        if (lb.units.empty()) continue;
+        const hgt_locus *loc = lb.loc;
+        const size_t n_units = lb.units.size();
+        const size_t pr = (size_t)std::max<int64_t>(lb.n_rows_pool, 1);
+        HGT_CUDA(cudaMemsetAsync(lb.d_keys.p, 0, (size_t)lb.cap * 8, st));
+        HGT_CUDA(cudaMemsetAsync(lb.d_slot.p, 0xff, (size_t)lb.cap * 4, st));
+        HGT_CUDA(cudaMemsetAsync(lb.d_count.p, 0, pr * 8, st));
+        HGT_CUDA(cudaMemsetAsync(lb.d_first.p, 0x7f, pr * 4, st));
+        HGT_CUDA(cudaMemsetAsync(lb.d_ut_ncls.p, 0, n_units * 16, st));
+        HGT_CUDA(cudaMemsetAsync(lb.d_is.p, 0, n_units * 12, st));
+        switch (wpl_of(loc->wp)) {
+            case 1: launch_stage_a<1>(ctx, st, lb); break;
+            case 2: launch_stage_a<2>(ctx, st, lb); break;
+            case 4: launch_stage_a<4>(ctx, st, lb); break;
+            default: launch_stage_a<8>(ctx, st, lb); break;
+        }
+        HGT_CUDA(cudaGetLastError());
+        // Gene_counts of the Gene table
+        {
+            dim3 grid((loc->A + 127) / 128, (unsigned)n_units);
+            table_counts_kernel<<<grid, 128, 0, st>>>(loc->A, loc->wp, 0, lb.pool(), lb.d_acount.as<long long>(),
+                                                      lb.d_afirst.as<int32_t>());
+            ctx->launches++;
+            HGT_CUDA(cudaGetLastError());
+        }
+        // first-level EM: exon table on the hla path (core:1732-1737), Gene table otherwise (core:1789)
+        std::vector<int> all(n_units);
+        std::iota(all.begin(), all.end(), 0);
+        HGT_CHECK(em_on_table(ctx, st, lb, loc->is_hla ? 1 : 0, all, nullptr, loc->is_hla ? b->remove_low : 0, lb.d_prob,
+                              lb.d_inres, lb.d_fk, lb.d_is, lb.d_emws));
+    }
+    b->executed = true;
+    return HGT_OK;
+}
+
+// ---- stage 3: results back; on the hla path the second-level EM over full-length alleles (core:1739-1782) -------
+static int batch_finish(hgt_batch *b, cudaStream_t st) {
+    hgt_ctx *ctx = b->ctx;
+    for (LocusBatch &lb : b->lb) {
+        if (lb.units.empty()) continue;
+        const hgt_locus *loc = lb.loc;
+        const size_t n_units = lb.units.size(), A = (size_t)loc->A;
+        const int wp = loc->wp;
+        lb.ut_ncls.resize(n_units * 4);
+        lb.prob.resize(n_units * A); lb.inres.resize(n_units * A); lb.fk.resize(n_units * A); lb.is.resize(n_units * 3);
+        HGT_CUDA(cudaMemcpyAsync(lb.ut_ncls.data(), lb.d_ut_ncls.p, n_units * 16, cudaMemcpyDeviceToHost, st));
+        HGT_CUDA(cudaMemcpyAsync(lb.prob.data(), lb.d_prob.p, n_units * A * 8, cudaMemcpyDeviceToHost, st));
+        HGT_CUDA(cudaMemcpyAsync(lb.inres.data(), lb.d_inres.p, n_units * A, cudaMemcpyDeviceToHost, st));
+        HGT_CUDA(cudaMemcpyAsync(lb.fk.data(), lb.d_fk.p, n_units * A * 4, cudaMemcpyDeviceToHost, st));
+        HGT_CUDA(cudaMemcpyAsync(lb.is.data(), lb.d_is.p, n_units * 12, cudaMemcpyDeviceToHost, st));
+    }
+    HGT_CUDA(cudaStreamSynchronize(st));
+    for (LocusBatch &lb : b->lb) {
+        if (lb.units.empty() || !lb.loc->is_hla) continue;
+        const hgt_locus *loc = lb.loc;
+        const size_t n_units = lb.units.size(), A = (size_t)loc->A;
+        const int wp = loc->wp;
+        // choose exon_alleles per unit (core:1739-1749) from the ranked exon EM result
+        std::vector<int32_t> ulist;
+        std::vector<uint64_t> keep;
+        lb.has2.assign(n_units, 0);
+        std::vector<int> order;
+        for (size_t i = 0; i < n_units; i++) {
+            if (lb.is[i * 3 + 1] != HGT_OK) continue;
+            const double *p = &lb.prob[i * A];
+            const uint8_t *in = &lb.inres[i * A];
+            const int32_t *fk = &lb.fk[i * A];
+            order.clear();
+            for (int a = 0; a < (int)A; a++)
+                if (in[a]) order.push_back(a);
+            std::sort(order.begin(), order.end(), [&](int x, int y) {
+                if (p[x] != p[y]) return p[x] > p[y];
+                if (fk[x] != fk[y]) return fk[x] < fk[y];
+                return x < y;
+            });
+            std::vector<uint64_t> m(wp, 0);
+            bool any = false;
+            for (size_t r = 0; r < order.size(); r++) {
+                const int a = order[r];
+                if (r >= 10 && p[a] < 0.03) break;
+                if (loc->group_off[a + 1] - loc->group_off[a] <= 1) continue;
+                any = true;
+                for (int64_t g = loc->group_off[a]; g < loc->group_off[a + 1]; g++) {
+                    const int mem = loc->group_member[g];
+                    m[mem >> 6] |= 1ull << (mem & 63);
+                }
+            }
+            if (!any) continue;
+            lb.has2[i] = 1;
+            ulist.push_back((int32_t)i);
+            keep.insert(keep.end(), m.begin(), m.end());
+        }
+        if (ulist.empty()) continue;
+        HGT_CHECK(upload(&lb.d_ulist, ulist, st));
+        HGT_CHECK(upload(&lb.d_keep, keep, st));
+        if (!lb.d_len.p) {
+            HGT_CHECK(upload(&lb.d_len, loc->allele_len, st));
+        }
+        {
+            dim3 grid(8, (unsigned)std::min<size_t>(ulist.size(), 16384));
+            const ClassPool pool = lb.pool();
+            switch (wpl_of(wp)) {
+                case 1: project_kernel<1><<<grid, WARPS_PER_CTA * 32, 0, st>>>(wp, (int)ulist.size(), lb.d_ulist.as<int32_t>(), lb.d_keep.as<uint64_t>(), pool); break;
+                case 2: project_kernel<2><<<grid, WARPS_PER_CTA * 32, 0, st>>>(wp, (int)ulist.size(), lb.d_ulist.as<int32_t>(), lb.d_keep.as<uint64_t>(), pool); break;
+                case 4: project_kernel<4><<<grid, WARPS_PER_CTA * 32, 0, st>>>(wp, (int)ulist.size(), lb.d_ulist.as<int32_t>(), lb.d_keep.as<uint64_t>(), pool); break;
+                default: project_kernel<8><<<grid, WARPS_PER_CTA * 32, 0, st>>>(wp, (int)ulist.size(), lb.d_ulist.as<int32_t>(), lb.d_keep.as<uint64_t>(), pool); break;
+            }
+            ctx->launches++;
+            HGT_CUDA(cudaGetLastError());
+        }
+        HGT_CHECK(lb.d_prob2.alloc(n_units * A * 8));
+        HGT_CHECK(lb.d_inres2.alloc(n_units * A));
+        HGT_CHECK(lb.d_fk2.alloc(n_units * A * 4));
+        HGT_CHECK(lb.d_is2.alloc(n_units * 12));
+        HGT_CUDA(cudaMemsetAsync(lb.d_is2.p, 0, n_units * 12, st));
+        HGT_CHECK(lb.d_emws2.alloc(hgt_em_batch_ws_bytes((int)ulist.size(), wp)));
+        std::vector<int> lu(ulist.begin(), ulist.end());
+        HGT_CHECK(em_on_table(ctx, st, lb, 3, lu, lb.d_len.as<double>(), 1, lb.d_prob2, lb.d_inres2, lb.d_fk2, lb.d_is2,
+                              lb.d_emws2));
+        lb.prob2.resize(n_units * A); lb.inres2.resize(n_units * A); lb.fk2.resize(n_units * A); lb.is2.resize(n_units * 3);
+        HGT_CUDA(cudaMemcpyAsync(lb.prob2.data(), lb.d_prob2.p, n_units * A * 8, cudaMemcpyDeviceToHost, st));
+        HGT_CUDA(cudaMemcpyAsync(lb.inres2.data(), lb.d_inres2.p, n_units * A, cudaMemcpyDeviceToHost, st));
+        HGT_CUDA(cudaMemcpyAsync(lb.fk2.data(), lb.d_fk2.p, n_units * A * 4, cudaMemcpyDeviceToHost, st));
+        HGT_CUDA(cudaMemcpyAsync(lb.is2.data(), lb.d_is2.p, n_units * 12, cudaMemcpyDeviceToHost, st));
+        HGT_CUDA(cudaMemcpyAsync(lb.ut_ncls.data(), lb.d_ut_ncls.p, n_units * 16, cudaMemcpyDeviceToHost, st));
+    }
+    HGT_CUDA(cudaStreamSynchronize(st));
+    b->finished = true;
+    return HGT_OK;
+}
+
+// ================================================================================================================
+// C ABI: batches
+// ================================================================================================================
+extern "C" int hgt_batch_create(hgt_ctx *ctx, int32_t n_loci, hgt_locus *const *loci, const hgt_params *params,
+                                int32_t remove_low, hgt_batch **out) {
+    if (!ctx || !loci || n_loci < 1 || !params || !out) {
+        hgt_set_error("hgt_batch_create: bad argument");
+        return HGT_ERR_ARG;
+    }
+    for (int i = 0; i < n_loci; i++) {
+        if (!loci[i] || !loci[i]->ctx) {
+            hgt_set_error("hgt_batch_create: locus %d has no device tables", i);
+            return HGT_ERR_ARG;
+        }
+        if (loci[i]->wp > 256) {
+            hgt_set_error("typing kernels support at most 16384 alleles per locus (got %d)", loci[i]->A);
+            return HGT_ERR_UNSUPPORTED;
+        }
+    }
+    hgt_batch *b = new hgt_batch();
+    b->ctx = ctx;
+    b->params = *params;
+    b->remove_low = remove_low;
+    b->loci.assign(loci, loci + n_loci);
+    *out = b;
+    return HGT_OK;
+}
+
+extern "C" void hgt_batch_free(hgt_batch *b) { delete b; }
+
+extern "C" int64_t hgt_batch_add_unit(hgt_batch *b, int32_t locus_index, const char *sam_text, size_t n_bytes) {
+    if (!b || locus_index < 0 || locus_index >= (int)b->loci.size() || (!sam_text && n_bytes) || b->prepared) {
+        hgt_set_error("hgt_batch_add_unit: bad argument");
+        return HGT_ERR_ARG;
+    }
+    UnitHost u;
+    u.locus = locus_index;
+    u.sam = sam_text;
+    u.n_bytes = n_bytes;
+    b->units.push_back(std::move(u));
+    return (int64_t)b->units.size() - 1;
+}
+
+extern "C" int hgt_batch_prepare(hgt_batch *b) {
+    if (!b || b->prepared) {
+        hgt_set_error("hgt_batch_prepare: bad state");
+        return HGT_ERR_ARG;
+    }
+    HGT_CUDA(cudaSetDevice(b->ctx->device));
+    return batch_prepare(b);
+}
+
+extern "C" int hgt_batch_execute(hgt_batch *b, void *stream) {
+    if (!b || !b->prepared) {
+        hgt_set_error("hgt_batch_execute: batch is not prepared");
+        return HGT_ERR_ARG;
+    }
+    HGT_CUDA(cudaSetDevice(b->ctx->device));
+    return batch_execute(b, stream ? static_cast<cudaStream_t>(stream) : b->ctx->stream);
+}
+
+extern "C" int hgt_batch_finish(hgt_batch *b, void *stream) {
+    if (!b || !b->executed) {
+        hgt_set_error("hgt_batch_finish: batch was not executed");
+        return HGT_ERR_ARG;
+    }
+    HGT_CUDA(cudaSetDevice(b->ctx->device));
+    return batch_finish(b, stream ? static_cast<cudaStream_t>(stream) : b->ctx->stream);
+}
+
+extern "C" int hgt_batch_run(hgt_batch *b) {
+    HGT_CHECK(hgt_batch_prepare(b));
+    HGT_CHECK(hgt_batch_execute(b, nullptr));
+    return hgt_batch_finish(b, nullptr);
+}
+
+extern "C" int hgt_batch_totals(const hgt_batch *b, int64_t *n_units, int64_t *num_reads, int64_t *num_pairs,
+                                int64_t *n_haplotypes, int64_t *n_rows, int64_t *algorithmic_bytes) {
+    if (!b) return HGT_ERR_ARG;
+    int64_t r = 0, p = 0, h = 0, rows = 0, bytes = 0;
+    for (const UnitHost &u : b->units) {
+        r += u.ho.num_reads;
+        p += u.ho.num_pairs;
+    }
+    for (const LocusBatch &lb : b->lb) {
+        if (lb.units.empty()) continue;
+        h += (int64_t)lb.hap_left.size();
+        rows += (int64_t)lb.rows.size();
+        const int n_tables = lb.loc->is_hla ? 3 : 1;
+        // per pair S_rec + T * wp * 8, S_rec = packed haplotype records actually read
+        bytes += (int64_t)lb.hap_left.size() * 12 + (int64_t)lb.rows.size() * 4 + (int64_t)lb.job_ut.size() * 16;
+        for (int u : lb.units) bytes += b->units[u].ho.num_pairs * (int64_t)n_tables * lb.loc->wp * 8;
+    }
+    if (n_units) *n_units = (int64_t)b->units.size();
+    if (num_reads) *num_reads = r;
+    if (num_pairs) *num_pairs = p;
+    if (n_haplotypes) *n_haplotypes = h;
+    if (n_rows) *n_rows = rows;
+    if (algorithmic_bytes) *algorithmic_bytes = bytes;
+    return HGT_OK;
+}
+
+static int unit_check(const hgt_batch *b, int64_t unit, bool need_finish) {
+    if (!b || unit < 0 || unit >= (int64_t)b->units.size() || (need_finish && !b->finished)) {
+        hgt_set_error("batch accessor: bad unit index or batch not finished");
+        return HGT_ERR_ARG;
+    }
+    return HGT_OK;
+}
+
+extern "C" int hgt_batch_unit_summary(const hgt_batch *b, int64_t unit, int64_t *num_reads, int64_t *num_pairs,
+                                      int32_t n_classes[4], int32_t em_iters[2], int32_t em_status[2]) {
+    HGT_CHECK(unit_check(b, unit, false));
+    const UnitHost &U = b->units[unit];
+    if (num_reads) *num_reads = U.ho.num_reads;
+    if (num_pairs) *num_pairs = U.ho.num_pairs;
+    if (b->finished) {
+        const LocusBatch &lb = b->lb[U.locus];
+        for (int t = 0; t < 4; t++) {
+            const int64_t room = lb.ut_base[(size_t)U.local * 4 + t + 1] - lb.ut_base[(size_t)U.local * 4 + t];
+            if (n_classes) n_classes[t] = (int32_t)std::min<int64_t>(lb.ut_ncls[(size_t)U.local * 4 + t], room);
+        }
+        if (em_iters) {
+            em_iters[0] = lb.is[(size_t)U.local * 3];
+            em_iters[1] = (!lb.has2.empty() && lb.has2[U.local]) ? lb.is2[(size_t)U.local * 3] : 0;
+        }
+        if (em_status) {
+            em_status[0] = lb.is[(size_t)U.local * 3 + 1];
+            em_status[1] = (!lb.has2.empty() && lb.has2[U.local]) ? lb.is2[(size_t)U.local * 3 + 1] : 0;
+        }
+    }
+    return HGT_OK;
+}
+
+extern "C" int hgt_batch_unit_table(hgt_batch *b, int64_t unit, int32_t table, uint64_t *class_bits, int64_t *class_count,
+                                    int64_t *class_first, int64_t *allele_count, int64_t *allele_first) {
+    HGT_CHECK(unit_check(b, unit, true));
+    if (table < 0 || table > 3) {
+        hgt_set_error("hgt_batch_unit_table: table must be 0..3");
+        return HGT_ERR_ARG;
+    }
+    const UnitHost &U = b->units[unit];
+    LocusBatch &lb = b->lb[U.locus];
+    const hgt_locus *loc = lb.loc;
+    HGT_CUDA(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    const int ut = U.local * 4 + table;
+    const int64_t base = lb.ut_base[ut];
+    const int n = (int)std::min<int64_t>(lb.ut_ncls[ut], lb.ut_base[ut + 1] - base);
+    const int wp = loc->wp, A = loc->A;
+    std::vector<uint64_t> bits((size_t)std::max(n, 1) * wp);
+    std::vector<unsigned long long> cnt(std::max(n, 1));
+    std::vector<int32_t> first(std::max(n, 1));
+    if (n > 0) {
+        HGT_CUDA(cudaMemcpyAsync(bits.data(), lb.d_bits.as<uint64_t>() + (size_t)base * wp, (size_t)n * wp * 8,
+                                 cudaMemcpyDeviceToHost, st));
+        HGT_CUDA(cudaMemcpyAsync(cnt.data(), lb.d_count.as<unsigned long long>() + base, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+        HGT_CUDA(cudaMemcpyAsync(first.data(), lb.d_first.as<int32_t>() + base, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    }
+    std::vector<long long> ac;
+    std::vector<int32_t> af;
+    if ((allele_count || allele_first) && table == 0) {
+        ac.resize(A);
+        af.resize(A);
+        HGT_CUDA(cudaMemcpyAsync(ac.data(), lb.d_acount.as<long long>() + (size_t)U.local * A, (size_t)A * 8, cudaMemcpyDeviceToHost, st));
+        HGT_CUDA(cudaMemcpyAsync(af.data(), lb.d_afirst.as<int32_t>() + (size_t)U.local * A, (size_t)A * 4, cudaMemcpyDeviceToHost, st));
+    }
+    HGT_CUDA(cudaStreamSynchronize(st));
+    // dict order = first-seen order (each pair creates at most one class per table, so `first` is a strict key)
+    std::vector<int> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::sort(order.begin(), order.end(), [&](int x, int y) { return first[x] < first[y]; });
+    for (int k = 0; k < n; k++) {
+        const int c = order[k];
+        if (class_bits) memcpy(class_bits + (size_t)k * wp, &bits[(size_t)c * wp], (size_t)wp * 8);
+        if (class_count) class_count[k] = (int64_t)cnt[c];
+        if (class_first) class_first[k] = first[c];
+    }
+    if (allele_count || allele_first) {
+        if (table == 0) {
+            for (int a = 0; a < A; a++) {
+                if (allele_count) allele_count[a] = ac[a];
+                if (allele_first) allele_first[a] = af[a];
+            }
+        } else {  // other tables: derive from the class rows just read
+            for (int a = 0; a < A; a++) {
+                int64_t c = 0, f = -1;
+                for (int k = 0; k < n; k++)
+                    if ((bits[(size_t)k * wp + (a >> 6)] >> (a & 63)) & 1ull) {
+                        c += (int64_t)cnt[k];
+                        if (f < 0 || first[k] < f) f = first[k];
+                    }
+                if (allele_count) allele_count[a] = c;
+                if (allele_first) allele_first[a] = f;
+            }
+        }
+    }
+    return HGT_OK;
+}
+
+extern "C" int hgt_batch_unit_em(const hgt_batch *b, int64_t unit, int32_t level, double *prob, uint8_t *in_result,
+                                 int32_t *first_class, int32_t *iters, int32_t *status) {
+    HGT_CHECK(unit_check(b, unit, true));
+    const UnitHost &U = b->units[unit];
+    const LocusBatch &lb = b->lb[U.locus];
+    const size_t A = (size_t)lb.loc->A, o = (size_t)U.local * A;
+    if (level == 0) {
+        if (prob) memcpy(prob, &lb.prob[o], A * 8);
+        if (in_result) memcpy(in_result, &lb.inres[o], A);
+        if (first_class) memcpy(first_class, &lb.fk[o], A * 4);
+        if (iters) *iters = lb.is[(size_t)U.local * 3];
+        if (status) *status = lb.is[(size_t)U.local * 3 + 1];
+        return HGT_OK;
+    }
+    if (lb.has2.empty() || !lb.has2[U.local]) {
+        if (status) *status = 1;  // not run: no exon group with more than one member was selected (core:1752)
+        if (iters) *iters = 0;
+        return HGT_OK;
+    }
+    if (prob) memcpy(prob, &lb.prob2[o], A * 8);
+    if (in_result) memcpy(in_result, &lb.inres2[o], A);
+    if (first_class) memcpy(first_class, &lb.fk2[o], A * 4);
+    if (iters) *iters = lb.is2[(size_t)U.local * 3];
+    if (status) *status = lb.is2[(size_t)U.local * 3 + 1];
+    return HGT_OK;
+}
+
+// ================================================================================================================
+// C ABI: single (sample, locus) — a batch of one unit
 // ================================================================================================================
 struct hgt_typing {
-    hgt_ctx *ctx = nullptr;
-    const hgt_locus *locus = nullptr;
-    int64_t num_reads = 0, num_pairs = 0;
-    int32_t n_classes[3] = {0, 0, 0};
-    std::vector<int32_t> cls_idx[3];  // class ids of each table in first-seen order
-    std::vector<int64_t> cls_count[3], cls_first[3];
-    std::vector<uint32_t> pile_counts;
-    std::vector<uint8_t> pile_mask;
-    DevBuf d_bits, d_count, d_first, d_table;  // class pool
-    int32_t total_classes = 0;
+    hgt_batch *batch = nullptr;
 };
 
 extern "C" void hgt_typing_free(hgt_typing *t) {
     if (!t) return;
-    if (t->ctx) cudaSetDevice(t->ctx->device);
-    t->d_bits.release(); t->d_count.release(); t->d_first.release(); t->d_table.release();
+    delete t->batch;
     delete t;
-}
-
-static int run_pileup(hgt_ctx *ctx, const hgt_locus *loc, const PileupIn &pi, std::vector<uint32_t> *counts,
-                      std::vector<uint8_t> *mask) {
-    cudaStream_t st = ctx->stream;
-    const int L = loc->L;
-    counts->assign((size_t)L * 6, 0);
-    mask->assign(L, 0);
-    DevBuf d_pos, d_co, d_c, d_so, d_s, d_cnt, d_m;
-    int rc = HGT_OK;
-    do {
-        if ((rc = upload(&d_pos, pi.pos, st)) != HGT_OK) break;
-        if ((rc = upload(&d_co, pi.cig_off, st)) != HGT_OK) break;
-        if ((rc = upload(&d_c, pi.cig, st)) != HGT_OK) break;
-        if ((rc = upload(&d_so, pi.seq_off, st)) != HGT_OK) break;
-        if ((rc = upload(&d_s, pi.seq, st)) != HGT_OK) break;
-        if ((rc = d_cnt.alloc((size_t)L * 6 * 4)) != HGT_OK) break;
-        if ((rc = d_m.alloc(L)) != HGT_OK) break;
-        cudaError_t e = cudaMemsetAsync(d_cnt.p, 0, (size_t)L * 6 * 4, st);
-        const int64_t n = (int64_t)pi.pos.size();
-        if (e == cudaSuccess && n > 0) {
-            const int ctas = (int)std::min<int64_t>((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 8);
-            pileup_kernel<<<ctas, WARPS_PER_CTA * 32, 0, st>>>(d_pos.as<int32_t>(), d_co.as<int64_t>(), d_c.as<uint32_t>(),
-                                                                d_so.as<int64_t>(), d_s.as<char>(), n, L, d_cnt.as<uint32_t>());
-            ctx->launches++;
-        }
-        ntset_kernel<<<(L + 255) / 256, 256, 0, st>>>(d_cnt.as<uint32_t>(), L, d_m.as<uint8_t>());
-        ctx->launches++;
-        if (e == cudaSuccess) e = cudaGetLastError();
-        if (e == cudaSuccess) e = cudaMemcpyAsync(counts->data(), d_cnt.p, (size_t)L * 6 * 4, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(mask->data(), d_m.p, L, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) {
-            hgt_set_error("pileup: %s", cudaGetErrorString(e));
-            rc = HGT_ERR_CUDA;
-        }
-    } while (0);
-    d_pos.release(); d_co.release(); d_c.release(); d_so.release(); d_s.release(); d_cnt.release(); d_m.release();
-    return rc;
-}
-
-template <int WPL>
-static void launch_compat(hgt_ctx *ctx, cudaStream_t st, const LocusDev &ld, int table, const int32_t *hl,
-                          const int32_t *hr, const int64_t *ro, const int32_t *rows, int64_t n, uint64_t *out) {
-    const size_t smem = (size_t)std::max(ld.V, 1) * 4;
-    cudaFuncSetAttribute(compat_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    const int ctas = (int)std::min<int64_t>((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 4);
-    compat_kernel<WPL><<<ctas, WARPS_PER_CTA * 32, smem, st>>>(ld, table, hl, hr, ro, rows, n, out);
-    ctx->launches++;
-}
-
-template <int WPL, int P>
-static void launch_class(hgt_ctx *ctx, cudaStream_t st, int wp, const uint64_t *mask, int table, const int64_t *job_off,
-                         const int32_t *job_list, int64_t n, const uint64_t *hapbits, const ClassPool &pool) {
-    if (n <= 0) return;
-    const int ctas = (int)std::min<int64_t>((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 8);
-    class_kernel<WPL, P><<<ctas, WARPS_PER_CTA * 32, 0, st>>>(wp, mask, table, job_off, job_list, n, hapbits, pool);
-    ctx->launches++;
-}
-
-static int wpl_of(int wp) {
-    const int w = (wp + 31) / 32;
-    return w <= 1 ? 1 : w <= 2 ? 2 : w <= 4 ? 4 : 8;
 }
 
 extern "C" int hgt_typing_run(hgt_ctx *ctx, hgt_locus *loc, const char *sam, size_t n_bytes, const hgt_params *params,
@@ -938,196 +1648,38 @@ extern "C" int hgt_typing_run(hgt_ctx *ctx, hgt_locus *loc, const char *sam, siz
         return HGT_ERR_ARG;
     }
     *out = nullptr;
-    if (!loc->ctx) {
-        hgt_set_error("hgt_typing_run: locus was created without a context");
-        return HGT_ERR_ARG;
+    hgt_batch *b = nullptr;
+    hgt_locus *loci[1] = {loc};
+    HGT_CHECK(hgt_batch_create(ctx, 1, loci, params, 1, &b));
+    b->keep_counts = true;
+    int rc = (int)hgt_batch_add_unit(b, 0, sam, n_bytes);
+    if (rc >= 0) rc = hgt_batch_prepare(b);
+    if (rc == HGT_OK) rc = hgt_batch_execute(b, nullptr);
+    if (rc == HGT_OK) rc = hgt_batch_finish(b, nullptr);
+    if (rc != HGT_OK) {
+        delete b;
+        return rc;
     }
-    if (loc->wp > 256) {
-        hgt_set_error("typing kernels support at most 16384 alleles per locus (got %d)", loc->A);
-        return HGT_ERR_UNSUPPORTED;
-    }
-    HGT_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    Intake in;
-    HGT_CHECK(intake(sam, n_bytes, *params, &in));
-    PileupIn pi;
-    HGT_CHECK(build_pileup_input(in, *params, &pi));
     hgt_typing *t = new hgt_typing();
-    t->ctx = ctx;
-    t->locus = loc;
-    int rc = run_pileup(ctx, loc, pi, &t->pile_counts, &t->pile_mask);
-    HostOut ho;
-    if (rc == HGT_OK) {
-        PileupView pu;
-        pu.counts = t->pile_counts.data(); pu.nt_mask = t->pile_mask.data(); pu.L = loc->L;
-        rc = host_walk(loc, in, *params, pu, &ho);
-    }
-    if (rc != HGT_OK) {
-        hgt_typing_free(t);
-        return rc;
-    }
-    t->num_reads = ho.num_reads;
-    t->num_pairs = ho.num_pairs;
-    const int n_tables = loc->is_hla ? 3 : 1;
-    const int wp = loc->wp;
-    const int64_t n_pairs = ho.num_pairs;
-    const int64_t max_classes = std::max<int64_t>(1, n_pairs * n_tables);
-    uint32_t cap = 64;
-    while ((int64_t)cap < 2 * max_classes) cap <<= 1;
-    DevBuf d_keys, d_slot, d_ncls;
-    DevBuf d_hl[3], d_hr[3], d_ro[3], d_rows[3], d_jo[3], d_hb[3], d_jl[3];
-    std::vector<int32_t> cls_table;
-    do {
-        if (n_pairs == 0) break;
-        if ((rc = d_keys.alloc((size_t)cap * 8)) != HGT_OK) break;
-        if ((rc = d_slot.alloc((size_t)cap * 4)) != HGT_OK) break;
-        if ((rc = d_ncls.alloc(4)) != HGT_OK) break;
-        if ((rc = t->d_bits.alloc((size_t)max_classes * wp * 8)) != HGT_OK) break;
-        if ((rc = t->d_count.alloc((size_t)max_classes * 8)) != HGT_OK) break;
-        if ((rc = t->d_first.alloc((size_t)max_classes * 4)) != HGT_OK) break;
-        if ((rc = t->d_table.alloc((size_t)max_classes * 4)) != HGT_OK) break;
-        cudaError_t e = cudaMemsetAsync(d_keys.p, 0, (size_t)cap * 8, st);
-        if (e == cudaSuccess) e = cudaMemsetAsync(d_slot.p, 0xff, (size_t)cap * 4, st);
-        if (e == cudaSuccess) e = cudaMemsetAsync(d_ncls.p, 0, 4, st);
-        if (e == cudaSuccess) e = cudaMemsetAsync(t->d_count.p, 0, (size_t)max_classes * 8, st);
-        if (e == cudaSuccess) e = cudaMemsetAsync(t->d_first.p, 0x7f, (size_t)max_classes * 4, st);
-        if (e != cudaSuccess) {
-            hgt_set_error("typing: %s", cudaGetErrorString(e));
-            rc = HGT_ERR_CUDA;
-            break;
-        }
-        ClassPool pool;
-        pool.keys = d_keys.as<unsigned long long>(); pool.slot_class = d_slot.as<int32_t>(); pool.cap_mask = cap - 1;
-        pool.bits = t->d_bits.as<uint64_t>(); pool.count = t->d_count.as<unsigned long long>();
-        pool.first = t->d_first.as<int32_t>(); pool.table = t->d_table.as<int32_t>();
-        pool.n_classes = d_ncls.as<int32_t>(); pool.max_classes = (int32_t)max_classes;
-        const LocusDev ld = locus_dev(loc);
-        const int wpl = wpl_of(wp);
-        for (int tb = 0; tb < n_tables && rc == HGT_OK; tb++) {
-            const TableJobs &J = ho.tb[tb];
-            const int64_t H = (int64_t)J.hap_left.size();
-            // jobs with more than 7 haplotypes need the wide counter
-            std::vector<int32_t> small, big;
-            for (int64_t p = 0; p < n_pairs; p++) {
-                const int64_t k = J.job_off[p + 1] - J.job_off[p];
-                if (k > 255) {
-                    hgt_set_error("a read pair expands to %lld haplotypes (limit 255)", (long long)k);
-                    rc = HGT_ERR_UNSUPPORTED;
-                    break;
-                }
-                (k <= 7 ? small : big).push_back((int32_t)p);
-            }
-            if (rc != HGT_OK) break;
-            if ((rc = upload(&d_hl[tb], J.hap_left, st)) != HGT_OK) break;
-            if ((rc = upload(&d_hr[tb], J.hap_right, st)) != HGT_OK) break;
-            if ((rc = upload(&d_ro[tb], J.row_off, st)) != HGT_OK) break;
-            if ((rc = upload(&d_rows[tb], J.rows, st)) != HGT_OK) break;
-            if ((rc = upload(&d_jo[tb], J.job_off, st)) != HGT_OK) break;
-            if ((rc = d_hb[tb].alloc((size_t)std::max<int64_t>(H, 1) * wp * 8)) != HGT_OK) break;
-            std::vector<int32_t> jl(small);
-            jl.insert(jl.end(), big.begin(), big.end());
-            if ((rc = upload(&d_jl[tb], jl, st)) != HGT_OK) break;
-            const uint64_t *mask = loc->d_mask + (size_t)tb * wp;
-#define DISPATCH(W)                                                                                                  \
-    {                                                                                                                \
-        if (H > 0)                                                                                                   \
-            launch_compat<W>(ctx, st, ld, tb, d_hl[tb].as<int32_t>(), d_hr[tb].as<int32_t>(), d_ro[tb].as<int64_t>(), \
-                             d_rows[tb].as<int32_t>(), H, d_hb[tb].as<uint64_t>());                                  \
-        launch_class<W, 3>(ctx, st, wp, mask, tb, d_jo[tb].as<int64_t>(), d_jl[tb].as<int32_t>(),                    \
-                           (int64_t)small.size(), d_hb[tb].as<uint64_t>(), pool);                                    \
-        launch_class<W, 8>(ctx, st, wp, mask, tb, d_jo[tb].as<int64_t>(), d_jl[tb].as<int32_t>() + small.size(),     \
-                           (int64_t)big.size(), d_hb[tb].as<uint64_t>(), pool);                                      \
-    }
-            switch (wpl) {
-                case 1: DISPATCH(1); break;
-                case 2: DISPATCH(2); break;
-                case 4: DISPATCH(4); break;
-                default: DISPATCH(8); break;
-            }
-#undef DISPATCH
-            e = cudaGetLastError();
-            if (e != cudaSuccess) {
-                hgt_set_error("typing kernels: %s", cudaGetErrorString(e));
-                rc = HGT_ERR_CUDA;
-            }
-        }
-        if (rc != HGT_OK) break;
-        int32_t ncls = 0;
-        e = cudaMemcpyAsync(&ncls, d_ncls.p, 4, cudaMemcpyDeviceToHost, st);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-        if (e != cudaSuccess) {
-            hgt_set_error("typing: %s", cudaGetErrorString(e));
-            rc = HGT_ERR_CUDA;
-            break;
-        }
-        t->total_classes = ncls;
-        std::vector<unsigned long long> cnt(ncls);
-        std::vector<int32_t> first(ncls);
-        cls_table.resize(ncls);
-        if (ncls > 0) {
-            e = cudaMemcpyAsync(cnt.data(), t->d_count.p, (size_t)ncls * 8, cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(first.data(), t->d_first.p, (size_t)ncls * 4, cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(cls_table.data(), t->d_table.p, (size_t)ncls * 4, cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-            if (e != cudaSuccess) {
-                hgt_set_error("typing: %s", cudaGetErrorString(e));
-                rc = HGT_ERR_CUDA;
-                break;
-            }
-        }
-        for (int c = 0; c < ncls; c++) t->cls_idx[cls_table[c]].push_back(c);
-        for (int tb = 0; tb < 3; tb++) {
-            std::vector<int32_t> &ix = t->cls_idx[tb];
-            std::sort(ix.begin(), ix.end(), [&](int a, int b) { return first[a] < first[b]; });
-            t->n_classes[tb] = (int32_t)ix.size();
-            for (int c : ix) {
-                t->cls_count[tb].push_back((int64_t)cnt[c]);
-                t->cls_first[tb].push_back(first[c]);
-            }
-        }
-    } while (0);
-    d_keys.release(); d_slot.release(); d_ncls.release();
-    for (int tb = 0; tb < 3; tb++) {
-        d_hl[tb].release(); d_hr[tb].release(); d_ro[tb].release(); d_rows[tb].release(); d_jo[tb].release();
-        d_hb[tb].release(); d_jl[tb].release();
-    }
-    if (rc != HGT_OK) {
-        hgt_typing_free(t);
-        return rc;
-    }
+    t->batch = b;
     *out = t;
     return HGT_OK;
 }
 
 extern "C" int hgt_typing_summary(const hgt_typing *t, int64_t *num_reads, int64_t *num_pairs, int32_t n_classes[3]) {
     if (!t) return HGT_ERR_ARG;
-    if (num_reads) *num_reads = t->num_reads;
-    if (num_pairs) *num_pairs = t->num_pairs;
+    int32_t nc[4] = {0, 0, 0, 0};
+    HGT_CHECK(hgt_batch_unit_summary(t->batch, 0, num_reads, num_pairs, nc, nullptr, nullptr));
     if (n_classes)
-        for (int i = 0; i < 3; i++) n_classes[i] = t->n_classes[i];
+        for (int i = 0; i < 3; i++) n_classes[i] = nc[i];
     return HGT_OK;
 }
 
 extern "C" int hgt_typing_pileup(const hgt_typing *t, uint32_t *counts, uint8_t *nt_mask) {
     if (!t) return HGT_ERR_ARG;
-    if (counts) memcpy(counts, t->pile_counts.data(), t->pile_counts.size() * 4);
-    if (nt_mask) memcpy(nt_mask, t->pile_mask.data(), t->pile_mask.size());
-    return HGT_OK;
-}
-
-// class rows of one table, first-seen order, gathered into a contiguous device buffer
-static int gather_table(const hgt_typing *t, int table, DevBuf *d_idx, DevBuf *d_rows) {
-    hgt_ctx *ctx = t->ctx;
-    cudaStream_t st = ctx->stream;
-    const int n = t->n_classes[table], wp = t->locus->wp;
-    HGT_CHECK(upload(d_idx, t->cls_idx[table], st));
-    HGT_CHECK(d_rows->alloc((size_t)std::max(n, 1) * wp * 8));
-    if (n > 0) {
-        gather_rows_kernel<<<std::min(ctx->sm_count * 4, (n * wp + 255) / 256), 256, 0, st>>>(
-            wp, d_idx->as<int32_t>(), n, t->d_bits.as<uint64_t>(), d_rows->as<uint64_t>());
-        ctx->launches++;
-        HGT_CUDA(cudaGetLastError());
-    }
+    const UnitHost &U = t->batch->units[0];
+    if (counts) memcpy(counts, U.counts.data(), U.counts.size() * 4);
+    if (nt_mask) memcpy(nt_mask, U.nt_mask.data(), U.nt_mask.size());
     return HGT_OK;
 }
 
@@ -1137,38 +1689,7 @@ extern "C" int hgt_typing_table(const hgt_typing *t, int32_t table, uint64_t *cl
         hgt_set_error("hgt_typing_table: bad argument");
         return HGT_ERR_ARG;
     }
-    hgt_ctx *ctx = t->ctx;
-    HGT_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    const int n = t->n_classes[table], wp = t->locus->wp, A = t->locus->A;
-    if (class_count) memcpy(class_count, t->cls_count[table].data(), (size_t)n * 8);
-    if (class_first) memcpy(class_first, t->cls_first[table].data(), (size_t)n * 8);
-    DevBuf d_idx, d_rows, d_ac, d_af;
-    int rc = HGT_OK;
-    do {
-        if (class_bits && n > 0) {
-            if ((rc = gather_table(t, table, &d_idx, &d_rows)) != HGT_OK) break;
-            cudaError_t e = cudaMemcpyAsync(class_bits, d_rows.p, (size_t)n * wp * 8, cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-            if (e != cudaSuccess) { hgt_set_error("table readback: %s", cudaGetErrorString(e)); rc = HGT_ERR_CUDA; break; }
-        }
-        if (allele_count || allele_first) {
-            if (!d_idx.p && (rc = upload(&d_idx, t->cls_idx[table], st)) != HGT_OK) break;
-            if ((rc = d_ac.alloc((size_t)A * 8)) != HGT_OK) break;
-            if ((rc = d_af.alloc((size_t)A * 8)) != HGT_OK) break;
-            table_counts_kernel<<<(A + 127) / 128, 128, 0, st>>>(A, wp, d_idx.as<int32_t>(), n, t->d_bits.as<uint64_t>(),
-                                                                 t->d_count.as<unsigned long long>(), t->d_first.as<int32_t>(),
-                                                                 d_ac.as<long long>(), d_af.as<long long>());
-            ctx->launches++;
-            cudaError_t e = cudaGetLastError();
-            if (e == cudaSuccess && allele_count) e = cudaMemcpyAsync(allele_count, d_ac.p, (size_t)A * 8, cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess && allele_first) e = cudaMemcpyAsync(allele_first, d_af.p, (size_t)A * 8, cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-            if (e != cudaSuccess) { hgt_set_error("table counts: %s", cudaGetErrorString(e)); rc = HGT_ERR_CUDA; break; }
-        }
-    } while (0);
-    d_idx.release(); d_rows.release(); d_ac.release(); d_af.release();
-    return rc;
+    return hgt_batch_unit_table(t->batch, 0, table, class_bits, class_count, class_first, allele_count, allele_first);
 }
 
 extern "C" int hgt_typing_em(hgt_ctx *ctx, const hgt_typing *t, int32_t table, const uint64_t *keep_mask,
@@ -1178,10 +1699,14 @@ extern "C" int hgt_typing_em(hgt_ctx *ctx, const hgt_typing *t, int32_t table, c
         hgt_set_error("hgt_typing_em: bad argument");
         return HGT_ERR_ARG;
     }
-    const int n = t->n_classes[table], wp = t->locus->wp, A = t->locus->A;
+    const hgt_locus *loc = t->batch->loci[0];
+    const int wp = loc->wp, A = loc->A;
+    int32_t nc[4] = {0, 0, 0, 0};
+    HGT_CHECK(hgt_batch_unit_summary(t->batch, 0, nullptr, nullptr, nc, nullptr, nullptr));
+    const int n = nc[table];
     std::vector<uint64_t> bits((size_t)std::max(n, 1) * wp);
     std::vector<int64_t> cnt(std::max(n, 1));
-    HGT_CHECK(hgt_typing_table(t, table, bits.data(), cnt.data(), nullptr, nullptr, nullptr));
+    HGT_CHECK(hgt_batch_unit_table(t->batch, 0, table, bits.data(), cnt.data(), nullptr, nullptr, nullptr));
     int m = n;
     if (keep_mask) {
         // project classes onto the kept alleles, merge equal keys in first-seen order (core:1753-1766)
@@ -1230,7 +1755,13 @@ extern "C" int hgt_host_walk(hgt_locus *loc, const char *sam, size_t n_bytes, co
     HGT_CHECK(intake(sam, n_bytes, *params, &in));
     hgt_walk *w = new hgt_walk();
     PileupView pu;
-    pu.counts = counts; pu.nt_mask = nt_mask; pu.L = loc->L;
+    std::vector<uint8_t> flag(loc->L);
+    for (int i = 0; i < loc->L; i++) {
+        const uint32_t *c = counts + (size_t)i * 6;
+        const uint64_t dels = c[5], nts = (uint64_t)c[0] + c[1] + c[2] + c[3] + c[4];
+        flag[i] = dels * 6 < nts ? 1 : 0;
+    }
+    pu.nt_mask = nt_mask; pu.del_artefact = flag.data(); pu.L = loc->L;
     int rc = host_walk(loc, in, *params, pu, &w->ho);
     if (rc != HGT_OK) {
         delete w;

@@ -191,12 +191,12 @@ inline bool parse_cigar(const char *s, int n, std::vector<CigarOp> *out) {
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Pileup view handed to the walk: per position counts[6] (A,C,G,T,other,D) and the nt_set bit mask (bit i =
-// "ACGT"[i]); produced on the GPU (typing.cu pileup kernels), semantics of common:1059-1134.
+// Pileup view handed to the walk: per position the nt_set bit mask (bit i = "ACGT"[i]) and the deletion-artefact
+// flag; produced on the GPU (typing.cu pileup kernels), semantics of common:1059-1134.
 // ------------------------------------------------------------------------------------------------------------
 struct PileupView {
-    const uint32_t *counts = nullptr;  // [L][6]
-    const uint8_t *nt_mask = nullptr;  // [L]
+    const uint8_t *nt_mask = nullptr;       // [L] nt_set as a bit mask
+    const uint8_t *del_artefact = nullptr;  // [L] 1 where del_count * 6 < nt_count (core:1064-1077)
     int32_t L = 0;
 };
 inline int nt_code(char c) {
@@ -411,11 +411,8 @@ inline bool walk_record(const LocusHost &L, const Record &r, const PileupView &p
                     }
             }
             w->cmp.push_back({C_DELETION, right_pos, length, vid});
-            if (right_pos < pu.L) {  // artificial-deletion rule, hla only (core:1064-1077)
-                const uint32_t *c = pu.counts + (size_t)right_pos * 6;
-                const uint64_t dels = c[5], nts = (uint64_t)c[0] + c[1] + c[2] + c[3] + c[4];
-                if (L.is_hla && dels * 6 < nts) w->misaligned = true;
-            }
+            // artificial-deletion rule, hla only (core:1064-1077)
+            if (right_pos < pu.L && L.is_hla && pu.del_artefact[right_pos]) w->misaligned = true;
         } else if (op == 'S') {
             if (ci == 0) zs_pos += length;
             else if (ci + 1 != cig.size()) return fail("soft clip in the middle of a CIGAR");

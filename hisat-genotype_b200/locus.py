@@ -31,6 +31,7 @@ class LocusDesc(ctypes.Structure):
         ("n_primary_exons", ctypes.c_int32), ("primary_exons", ctypes.c_void_p),
         ("exon_rep_mask", ctypes.c_void_p), ("primary_rep_mask", ctypes.c_void_p),
         ("gene_names_rank", ctypes.c_void_p), ("is_hla", ctypes.c_int32), ("alts_text", ctypes.c_char_p),
+        ("group_off", ctypes.c_void_p), ("group_member", ctypes.c_void_p), ("allele_len", ctypes.c_void_p),
     ]
 
 
@@ -61,6 +62,26 @@ def _bind(L):
     L.hgt_typing_pileup.argtypes = [vp, vp, vp]
     L.hgt_typing_em.restype = ctypes.c_int
     L.hgt_typing_em.argtypes = [vp, vp, i32, vp, vp, i32, vp, vp, vp, P(i32)]
+    L.hgt_batch_create.restype = ctypes.c_int
+    L.hgt_batch_create.argtypes = [vp, i32, P(vp), P(Params), i32, P(vp)]
+    L.hgt_batch_free.restype = None
+    L.hgt_batch_free.argtypes = [vp]
+    L.hgt_batch_add_unit.restype = i64
+    L.hgt_batch_add_unit.argtypes = [vp, i32, vp, ctypes.c_size_t]
+    for fn in ("hgt_batch_prepare", "hgt_batch_run"):
+        getattr(L, fn).restype = ctypes.c_int
+        getattr(L, fn).argtypes = [vp]
+    for fn in ("hgt_batch_execute", "hgt_batch_finish"):
+        getattr(L, fn).restype = ctypes.c_int
+        getattr(L, fn).argtypes = [vp, vp]
+    L.hgt_batch_totals.restype = ctypes.c_int
+    L.hgt_batch_totals.argtypes = [vp] + [P(i64)] * 6
+    L.hgt_batch_unit_summary.restype = ctypes.c_int
+    L.hgt_batch_unit_summary.argtypes = [vp, i64, P(i64), P(i64), P(i32 * 4), P(i32 * 2), P(i32 * 2)]
+    L.hgt_batch_unit_table.restype = ctypes.c_int
+    L.hgt_batch_unit_table.argtypes = [vp, i64, i32, vp, vp, vp, vp, vp]
+    L.hgt_batch_unit_em.restype = ctypes.c_int
+    L.hgt_batch_unit_em.argtypes = [vp, i64, i32, vp, vp, vp, P(i32), P(i32)]
     L.hgt_host_walk.restype = ctypes.c_int
     L.hgt_host_walk.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, P(Params), vp, vp, P(vp)]
     L.hgt_walk_summary.restype = ctypes.c_int
@@ -304,6 +325,19 @@ class LocusTables:
         d.gene_names_rank = _lib.ptr(gn_rank)
         d.is_hla = 1 if self.is_hla else 0
         d.alts_text = k["alts"]
+        # exon groups (allele_rep_groups) as CSR over representative alleles, and allele lengths
+        group_off = np.zeros(self.A + 1, np.int64)
+        members = []
+        for a, name in enumerate(self.names):
+            grp = self.allele_rep_groups.get(name)
+            if grp:
+                members.extend(self.index[m] for m in grp if m in self.index)
+            group_off[a + 1] = len(members)
+        k["group_off"] = group_off
+        k["group_member"] = np.asarray(members if members else [0], np.int32)
+        k["allele_len"] = np.asarray([float(gene_lengths.get(n, len(ref_seq))) for n in self.names], np.float64)
+        d.group_off, d.group_member = _lib.ptr(k["group_off"]), _lib.ptr(k["group_member"])
+        d.allele_len = _lib.ptr(k["allele_len"])
         self._desc = d
         self.handle = ctypes.c_void_p()
         self.device = device

@@ -251,3 +251,152 @@ def write_database(loci, base, ix_dir, id_prefix="hv", partial_names=()):
     for fh in f.values():
         fh.close()
     return full
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# In-memory reference containers and synthetic alignment records (bench / large parity cases)
+# ----------------------------------------------------------------------------------------------------------------
+def reference_containers(loci, base="hla", id_prefix="hv"):
+    """The containers genotyping_locus() builds from the database files (core:2417-2485), straight from Locus
+    objects: refGenes, refGene_loci, Vars, Var_list, Links, Gene_names, Gene_lengths, Genes (backbone only)."""
+    refGenes, refGene_loci, Vars, Var_list, Links, Genes, Gene_names, Gene_lengths = {}, {}, {}, {}, {}, {}, {}, {}
+    num = 0
+    for loc in loci:
+        g = loc.gene
+        L = len(loc.backbone)
+        refGenes[g] = loc.backbone_name
+        refGene_loci[g] = [loc.backbone_name, loc.chrom, 0, L - 1, [[l, r] for l, r, _ in loc.exons],
+                           [[l, r] for l, r, p in loc.exons if p]]
+        loc.var_ids = ["%s%d" % (id_prefix, num + i) for i in range(len(loc.variants))]
+        num += len(loc.variants)
+        Vars[g] = {loc.var_ids[i]: [t, pos, data] for i, (t, pos, data) in enumerate(loc.variants)}
+        Var_list[g] = [[pos, loc.var_ids[i]] for i, (t, pos, data) in enumerate(loc.variants)]
+        links = [[] for _ in loc.variants]
+        lengths = {loc.backbone_name: L}
+        for name in sorted(loc.alleles):
+            n = L
+            for vi in loc.alleles[name]:
+                links[vi].append(name)
+                t, pos, data = loc.variants[vi]
+                if t == "deletion":
+                    n -= int(data)
+                elif t == "insertion":
+                    n += len(data)
+            lengths[name] = n
+        for vi, names in enumerate(links):
+            Links[loc.var_ids[vi]] = names
+        # Gene_names order: backbone, alleles in order of first appearance along Var_list/Links, then alleles
+        # identical to the backbone (core:2199-2237, 2462-2467)
+        order, seen = [loc.backbone_name], {loc.backbone_name}
+        for vi in range(len(loc.variants)):
+            for name in links[vi]:
+                if name not in seen:
+                    seen.add(name)
+                    order.append(name)
+        for name in sorted(loc.alleles):
+            if name not in seen:
+                seen.add(name)
+                order.append(name)
+        Gene_names[g] = order
+        Gene_lengths[g] = lengths
+        Genes[g] = {loc.backbone_name: loc.backbone}
+    return dict(refGenes=refGenes, refGene_loci=refGene_loci, Vars=Vars, Var_list=Var_list, Links=Links, Genes=Genes,
+                Gene_names=Gene_names, Gene_lengths=Gene_lengths)
+
+
+_sim = None
+
+
+def _simlib():
+    global _sim
+    if _sim is None:
+        import ctypes
+        import subprocess
+        tools = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools")
+        so = os.path.join(tools, "libhgtsim.so")
+        if not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(os.path.join(tools, "simgen.cpp")):
+            subprocess.check_call(["make", "-s", "-C", tools])
+        L = ctypes.CDLL(so)
+        L.hgtsim_locus_create.restype = ctypes.c_void_p
+        L.hgtsim_locus_create.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_int] + \
+            [ctypes.c_void_p] * 3 + [ctypes.c_char_p, ctypes.c_char_p]
+        L.hgtsim_add_allele.restype = ctypes.c_int
+        L.hgtsim_add_allele.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_char_p]
+        L.hgtsim_locus_free.argtypes = [ctypes.c_void_p]
+        L.hgtsim_generate.restype = ctypes.c_longlong
+        L.hgtsim_generate.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int,
+                                      ctypes.c_int, ctypes.c_double, ctypes.c_uint64, ctypes.c_int, ctypes.c_longlong,
+                                      ctypes.c_char_p, ctypes.c_char_p, ctypes.c_longlong]
+        _sim = L
+    return _sim
+
+
+class ReadSimulator:
+    """Draws reads from alleles of one Locus and formats them as HISAT2-style alignment lines (tools/simgen.cpp)."""
+
+    def __init__(self, loc):
+        import ctypes
+        self.loc = loc
+        if not loc.var_ids:
+            loc.var_ids = ["hv%d" % i for i in range(len(loc.variants))]
+        n = len(loc.variants)
+        tcode = {"single": 0, "deletion": 1, "insertion": 2}
+        self._pos = np.asarray([v[1] for v in loc.variants] or [0], np.int32)
+        self._len = np.asarray([int(v[2]) if v[0] == "deletion" else (len(v[2]) if v[0] == "insertion" else 1)
+                                for v in loc.variants] or [1], np.int32)
+        self._type = np.asarray([tcode[v[0]] for v in loc.variants] or [0], np.uint8)
+        self._base = bytes((ord(v[2][0]) if v[0] == "single" else 0) for v in loc.variants) + b"\0"
+        ids = b"".join(i.encode() + b"\0" for i in loc.var_ids) + b"\0"
+        L = _simlib()
+        self.h = L.hgtsim_locus_create(loc.backbone.encode(), len(loc.backbone), loc.backbone_name.encode(), n,
+                                       self._pos.ctypes.data_as(ctypes.c_void_p),
+                                       self._len.ctypes.data_as(ctypes.c_void_p),
+                                       self._type.ctypes.data_as(ctypes.c_void_p), self._base, ids)
+        self.slots = {}
+
+    def slot(self, allele):
+        import ctypes
+        if allele not in self.slots:
+            vs = np.asarray(self.loc.alleles[allele] or [0], np.int32)
+            s = _simlib().hgtsim_add_allele(self.h, len(self.loc.alleles[allele]),
+                                            vs.ctypes.data_as(ctypes.c_void_p), self._base)
+            if s < 0:
+                raise ValueError("allele %s carries an insertion; the simulator handles SNPs and deletions" % allele)
+            self.slots[allele] = s
+        return self.slots[allele]
+
+    def generate(self, alleles, n_pairs, seed, err_rate=0.0, read_len=100, frag_len=350, paired=True, id_start=0,
+                 prefix="r"):
+        """bytes of SAM text: n_pairs pairs (2 lines each) or n_pairs single reads, name-sorted."""
+        import ctypes
+        slots = np.asarray([self.slot(a) for a in alleles], np.int32)
+        cap = int(n_pairs) * (2 if paired else 1) * (330 + 2 * read_len) + 4096
+        while True:
+            buf = ctypes.create_string_buffer(cap)
+            n = _simlib().hgtsim_generate(self.h, len(slots), slots.ctypes.data_as(ctypes.c_void_p), int(n_pairs),
+                                          read_len, frag_len, float(err_rate), int(seed), 1 if paired else 0,
+                                          int(id_start), prefix.encode(), buf, cap)
+            if n >= 0:
+                return buf.raw[:n]
+            cap = -n + 4096
+
+    def close(self):
+        if self.h:
+            _simlib().hgtsim_locus_free(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def simulate_sam(loc, alleles, n_pairs, rng=None, err_rate=0.0, seed=None, **kw):
+    """Convenience wrapper: list of alignment lines for reads drawn from `alleles`."""
+    sim = ReadSimulator(loc)
+    if seed is None:
+        seed = int(rng.integers(1, 2 ** 31)) if rng is not None else 1
+    text = sim.generate(alleles, n_pairs, seed, err_rate, **kw)
+    sim.close()
+    return text.decode().splitlines()

@@ -163,6 +163,150 @@ def locus_abundance(run: TypingRun, remove_low_abundance_alleles=True):
     return run.abundance(TABLE_GENE, None, None, False)
 
 
+class Batch:
+    """Many (sample, locus) units through the GPU together (hgt_batch_* in include/hgt.h)."""
+
+    def __init__(self, loci, params=None, remove_low_abundance_alleles=True, device=None):
+        self.loci = list(loci)
+        self.params = params or make_params()
+        self.device = device
+        arr = (ctypes.c_void_p * len(self.loci))(*[t.handle for t in self.loci])
+        self.handle = ctypes.c_void_p()
+        _lib.check(lib().hgt_batch_create(_lib.ctx(device), len(self.loci), arr, ctypes.byref(self.params),
+                                          1 if remove_low_abundance_alleles else 0, ctypes.byref(self.handle)))
+        self._texts = []
+        self.unit_locus = []
+
+    def add_unit(self, locus_index, sam):
+        buf = _sam_bytes(sam)
+        self._texts.append(buf)  # must outlive prepare()
+        u = lib().hgt_batch_add_unit(self.handle, locus_index, ctypes.cast(ctypes.c_char_p(buf), ctypes.c_void_p),
+                                     len(buf))
+        if u < 0:
+            _lib.check(int(u))
+        self.unit_locus.append(locus_index)
+        return int(u)
+
+    def _call(self, rc):
+        if rc == _lib.HGT_ERR_AMBIGUITY:
+            raise SystemExit("Error: %s" % _lib.last_error())
+        if rc == _lib.HGT_ERR_PARSE:
+            raise AssertionError(_lib.last_error())
+        _lib.check(rc)
+
+    def prepare(self):
+        self._call(lib().hgt_batch_prepare(self.handle))
+        self._texts = []
+
+    def execute(self, stream=None):
+        self._call(lib().hgt_batch_execute(self.handle, stream))
+
+    def finish(self, stream=None):
+        self._call(lib().hgt_batch_finish(self.handle, stream))
+
+    def run(self):
+        self.prepare()
+        self.execute()
+        self.finish()
+
+    def totals(self):
+        v = [ctypes.c_int64(0) for _ in range(6)]
+        _lib.check(lib().hgt_batch_totals(self.handle, *[ctypes.byref(x) for x in v]))
+        keys = ("n_units", "num_reads", "num_pairs", "n_haplotypes", "n_rows", "algorithmic_bytes")
+        return dict(zip(keys, (x.value for x in v)))
+
+    def unit_summary(self, u):
+        nr, npairs = ctypes.c_int64(0), ctypes.c_int64(0)
+        nc, it, stt = (ctypes.c_int32 * 4)(), (ctypes.c_int32 * 2)(), (ctypes.c_int32 * 2)()
+        _lib.check(lib().hgt_batch_unit_summary(self.handle, u, ctypes.byref(nr), ctypes.byref(npairs),
+                                                ctypes.byref(nc), ctypes.byref(it), ctypes.byref(stt)))
+        return dict(num_reads=nr.value, num_pairs=npairs.value, n_classes=list(nc), em_iters=list(it),
+                    em_status=list(stt))
+
+    def unit_table(self, u, table):
+        t = self.loci[self.unit_locus[u]]
+        C = self.unit_summary(u)["n_classes"][table]
+        bits = np.zeros((max(C, 1), t.wp), np.uint64)
+        cnt = np.zeros(max(C, 1), np.int64)
+        first = np.zeros(max(C, 1), np.int64)
+        acount = np.zeros(t.A, np.int64)
+        afirst = np.zeros(t.A, np.int64)
+        _lib.check(lib().hgt_batch_unit_table(self.handle, u, table, _lib.ptr(bits), _lib.ptr(cnt), _lib.ptr(first),
+                                              _lib.ptr(acount), _lib.ptr(afirst)))
+        return bits[:C], cnt[:C], first[:C], acount, afirst
+
+    def unit_gene_cmpt(self, u, table=TABLE_GENE):
+        t = self.loci[self.unit_locus[u]]
+        bits, cnt, _, _, _ = self.unit_table(u, table)
+        return {t.key_of(bits[k]): int(cnt[k]) for k in range(len(cnt))}
+
+    def unit_gene_counts(self, u, table=TABLE_GENE):
+        t = self.loci[self.unit_locus[u]]
+        _, _, _, acount, afirst = self.unit_table(u, table)
+        idx = np.nonzero(acount > 0)[0]
+        order = sorted(idx.tolist(), key=lambda a: (int(afirst[a]), int(t.gn_rank[a])))
+        return [[t.names[a], int(acount[a])] for a in order]
+
+    def unit_em(self, u, level):
+        """Ranked [[allele, prob]] of the first- (level 0) or second-level (1) EM; None if level 1 did not run."""
+        t = self.loci[self.unit_locus[u]]
+        prob = np.zeros(t.A, np.float64)
+        inres = np.zeros(t.A, np.uint8)
+        fk = np.zeros(t.A, np.int32)
+        it, stt = ctypes.c_int32(0), ctypes.c_int32(0)
+        _lib.check(lib().hgt_batch_unit_em(self.handle, u, level, _lib.ptr(prob), _lib.ptr(inres), _lib.ptr(fk),
+                                           ctypes.byref(it), ctypes.byref(stt)))
+        if stt.value == 1:
+            return None
+        if stt.value == _lib.HGT_ERR_KEY:
+            raise KeyError("allele vanished from next_prob output during SQUAREM step")
+        if stt.value == _lib.HGT_ERR_ZERODIV:
+            raise ZeroDivisionError("float division by zero")
+        return rank_result(t.names, prob, inres, fk)
+
+    def unit_abundance(self, u):
+        """Gene_prob of the unit: the combination rule of core:1771-1782 (hla) or the plain EM (core:1789)."""
+        t = self.loci[self.unit_locus[u]]
+        first = self.unit_em(u, 0)
+        if not t.is_hla:
+            nc = self.unit_summary(u)["n_classes"][TABLE_GENE]
+            if nc <= 1:
+                if nc == 1:
+                    raise TypeError("'dict_keys' object is not subscriptable")  # core:1787 on Python 3
+                return []
+            return first
+        second = self.unit_em(u, 1)
+        if second is None:
+            return first
+        exon_alleles, exon_prob_sum = set(), 0.0
+        for i, (allele, prob) in enumerate(first):
+            if i >= 10 and prob < 0.03:
+                break
+            group = t.allele_rep_groups[allele]
+            if len(group) <= 1:
+                continue
+            exon_prob_sum += prob
+            exon_alleles |= set(group)
+        combined = {}
+        for allele, prob in first:
+            if allele not in exon_alleles:
+                combined[allele] = prob
+        for allele, prob in second:
+            combined[allele] = prob * exon_prob_sum
+        return sorted(([a, p] for a, p in combined.items()), key=lambda x: x[1], reverse=True)
+
+    def close(self):
+        if self.handle is not None and self.handle.value:
+            lib().hgt_batch_free(self.handle)
+            self.handle = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 class HostWalk:
     """Host half of stage (a) with a caller-supplied pileup (no GPU): used by the CPU-side tests."""
 

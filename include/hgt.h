@@ -117,6 +117,10 @@ typedef struct {
                                           per-read count tables, core:1338-1347) */
     int32_t is_hla;              /* base_fname == "hla" */
     const char *alts_text;       /* get_alternatives() tables: lines "L\tkey\talt,alt,...\n" / "R\t..." */
+    const int64_t *group_off;    /* [n_alleles+1] CSR: members of allele_rep_groups[a] (empty unless a is a
+                                    representative), used by the two-level EM driver (core:1739-1749); may be NULL */
+    const int32_t *group_member;
+    const double *allele_len;    /* [n_alleles] Gene_lengths[gene][allele] (core:2480-2485); may be NULL */
 } hgt_locus_desc;
 
 typedef struct {
@@ -149,6 +153,36 @@ int hgt_typing_pileup(const hgt_typing *t, uint32_t *counts, uint8_t *nt_mask);
 int hgt_typing_em(hgt_ctx *ctx, const hgt_typing *t, int32_t table, const uint64_t *keep_mask,
                   const double *allele_len, int32_t remove_low, double *prob, uint8_t *in_result,
                   int32_t *first_class, int32_t *iters);
+
+/* ---- batches of (sample, locus) units ----------------------------------------------------------------------
+ * The production shape of the path: the reference types one (sample, locus) at a time inside Pool workers
+ * (hisatgenotype:613-665, core:370); here any number of units over any number of loci go through the GPU
+ * together.  prepare = text intake, pileup (GPU), walk (host threads), upload of the packed haplotype jobs;
+ * execute = GPU only, no host synchronisation: haplotype->allele-set, per-pair class, class de-duplication,
+ * Gene_counts and the first-level EM (exon table on the hla path, Gene table otherwise) for every unit;
+ * finish = results back and, on the hla path, projection + second-level EM (core:1739-1782).
+ * execute and finish may be repeated on a prepared batch (bench).  Table 3 = the projected Gene table the
+ * second-level EM ran on.  sam_text buffers must stay valid until prepare returns. */
+typedef struct hgt_batch hgt_batch;
+int hgt_batch_create(hgt_ctx *ctx, int32_t n_loci, hgt_locus *const *loci, const hgt_params *params,
+                     int32_t remove_low_abundance_alleles, hgt_batch **out);
+void hgt_batch_free(hgt_batch *b);
+int64_t hgt_batch_add_unit(hgt_batch *b, int32_t locus_index, const char *sam_text, size_t n_bytes);
+int hgt_batch_prepare(hgt_batch *b);
+int hgt_batch_execute(hgt_batch *b, void *stream);
+int hgt_batch_finish(hgt_batch *b, void *stream);
+int hgt_batch_run(hgt_batch *b); /* prepare + execute + finish */
+/* totals over the batch; algorithmic_bytes = SURVEY.md 8d figure for stage (a): packed records read plus one
+ * allele-set row per pair and table */
+int hgt_batch_totals(const hgt_batch *b, int64_t *n_units, int64_t *num_reads, int64_t *num_pairs,
+                     int64_t *n_haplotypes, int64_t *n_rows, int64_t *algorithmic_bytes);
+int hgt_batch_unit_summary(const hgt_batch *b, int64_t unit, int64_t *num_reads, int64_t *num_pairs,
+                           int32_t n_classes[4], int32_t em_iters[2], int32_t em_status[2]);
+int hgt_batch_unit_table(hgt_batch *b, int64_t unit, int32_t table, uint64_t *class_bits, int64_t *class_count,
+                         int64_t *class_first, int64_t *allele_count, int64_t *allele_first);
+/* level 0: first-level EM; level 1: second-level EM (status 1 = not run for this unit, core:1752) */
+int hgt_batch_unit_em(const hgt_batch *b, int64_t unit, int32_t level, double *prob, uint8_t *in_result,
+                      int32_t *first_class, int32_t *iters, int32_t *status);
 
 /* Host-only half of stage (a) with a caller-supplied pileup (no GPU needed): intake, filters, walk, error
  * correction, ambiguity expansion, exon clipping.  Output is the job list the GPU consumes, flattened:

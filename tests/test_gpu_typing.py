@@ -98,3 +98,52 @@ def test_tables_bit_exact_vs_oracle_synthetic(seed):
         assert run.gene_counts(tb) == ref["tables"][key].count_items(ol)
     run.close()
     t.close()
+
+
+@pytest.mark.parametrize("name", ["hla_pair_err", "cyp_pair", "hla_indel"])
+def test_batch_matches_reference(name):
+    """All locus runs of a scenario as ONE batch (several loci, several units per locus): tables, counts and the
+    two-level EM result must equal the per-run goldens."""
+    from hisatgenotype_b200 import typing_core as TC
+    g = load_golden(name)
+    p = g["params"]
+    db = golden_db(g)
+    genes = []
+    for cap in g["loci"]:
+        if cap["gene"] not in genes:
+            genes.append(cap["gene"])
+    names = {cap["gene"]: cap["Gene_names"] for cap in g["loci"]}
+    loci = [product_locus(g, db, gene, names[gene]) for gene in genes]
+    batch = TC.Batch(loci, TC.make_params(p["num_editdist"], p["error_correction"], p["discordant"], p["simulation"]),
+                     p["remove_low"])
+    for cap in g["loci"]:
+        batch.add_unit(genes.index(cap["gene"]), cap["sam"])
+    batch.run()
+    em_i = 0
+    for u, cap in enumerate(g["loci"]):
+        s = batch.unit_summary(u)
+        assert s["num_reads"] == cap["num_reads"] and s["num_pairs"] == cap["num_pairs"]
+        assert list(map(list, batch.unit_gene_cmpt(u, TC.TABLE_GENE).items())) == cap["Gene_cmpt"]
+        assert batch.unit_gene_counts(u, TC.TABLE_GENE) == cap["Gene_counts"]
+        if p["base"] == "hla":
+            assert list(map(list, batch.unit_gene_cmpt(u, TC.TABLE_EXON).items())) == cap["Gene_exons_cmpt"]
+            assert batch.unit_gene_counts(u, TC.TABLE_EXON) == cap["Gene_exons_counts"]
+        for level in (0, 1):
+            res = batch.unit_em(u, level)
+            if res is None:
+                continue
+            ref = g["em_calls"][em_i]["result"]
+            em_i += 1
+            assert [a for a, _ in res] == [a for a, _ in ref]
+            for (_, x), (_, y) in zip(res, ref):
+                assert x == pytest.approx(y, rel=1e-6, abs=1e-12)
+        assert len(batch.unit_abundance(u)) > 0
+    assert em_i == len(g["em_calls"])
+    # repeat execute+finish on the prepared batch: identical tables (pools are reset)
+    batch.execute()
+    batch.finish()
+    for u, cap in enumerate(g["loci"]):
+        assert list(map(list, batch.unit_gene_cmpt(u, TC.TABLE_GENE).items())) == cap["Gene_cmpt"]
+    batch.close()
+    for t in loci:
+        t.close()
