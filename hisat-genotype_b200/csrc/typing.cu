@@ -760,7 +760,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
         const int job = job_list[q];
         const int64_t h0 = job_off[job], h1 = job_off[job + 1];
         const int ut = job_ut[job];
-        const uint64_t *mask = masks + (size_t)(ut % 3) * wp;
+        const uint64_t *mask = masks + (size_t)(ut & 3) * wp;
         uint64_t plane[P][WPL], best[WPL];
 #pragma unroll
         for (int p = 0; p < P; p++)
