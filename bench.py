@@ -1,0 +1,400 @@
+#!/usr/bin/env python3
+"""Benchmark of the typing hot path (stage a: per-read allele compatibility -> Gene_cmpt/Gene_counts, stage b: EM).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--samples S] [--impl reference]
+
+Workload = BASELINE.json configs[1]: HLA-A/B/C/DQA1/DQB1/DRB1, paired-end 2x100 bp, 30x, synthetic database of the
+named shape and reads drawn from a random diploid genotype per sample with 0.5 % sequencing
+errors; alignment records are synthesised HISAT2-style from the true placement (tools/simgen.cpp).  One step =
+one batch of S samples x 6 loci through the whole path.  Prints ONE JSON line (see DESIGN.md "Measurement").
+
+  value  reads typed/s with the packed alignments already resident in HBM (execute+finish of a prepared batch)
+  e2e    the same through the public batch call with HOST alignment text: intake, pileup, walk, H2D, kernels, D2H
+  roofline      stage (a) kernels against the measured HBM copy bandwidth (MEASURED_PEAKS.json)
+  cpu_baseline  the oracle port (oracle/hgt_oracle.py, oracle/em_oracle.c) on one host core, bounded sample
+--impl reference: the oracle port on all host cores (multiprocessing over units, like hisatgenotype:613-665).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LOCI = [  # gene, backbone length, alleles, allele groups  
+    ("A", 3500, 7000, 60), ("B", 3500, 8000, 64), ("C", 3500, 7000, 60),
+    ("DQA1", 6000, 400, 10), ("DQB1", 7000, 2000, 30), ("DRB1", 11000, 3000, 40),
+]
+READ_LEN, FRAG_LEN, COVERAGE, ERR = 100, 350, 30, 0.005
+DB_SEED = 7
+
+
+def build_database(scale=1.0):
+    import _hgt_path
+    _hgt_path.load()
+    from hisatgenotype_b200 import synth
+    loci = []
+    for i, (gene, L, A, G) in enumerate(LOCI):
+        A = max(40, int(A * scale))
+        G = max(4, int(G * min(1.0, scale * 2)))
+        loci.append(synth.make_locus(gene, DB_SEED + i, L=L, n_alleles=A, n_groups=G, core_vars=80,
+                                     pool_private=max(100, int(1600 * min(1.0, A / 7000.0 + 0.2))), del_frac=0.06))
+    cont = synth.reference_containers(loci, "hla")
+    return loci, cont
+
+
+def locus_args(cont, gene):
+    return ("hla", gene, cont["refGenes"][gene], cont["Genes"][gene][cont["refGenes"][gene]], cont["Vars"][gene],
+            cont["Var_list"][gene], cont["Links"], cont["Gene_names"][gene], cont["Gene_lengths"][gene],
+            cont["refGene_loci"][gene][4], cont["refGene_loci"][gene][5])
+
+
+def simulate_units(loci, sims, n_samples, sample0):
+    """[(locus index, alignment text bytes)] for samples sample0 .. sample0+n_samples-1 (seeded per sample)."""
+    import numpy as np
+    units = []
+    for s in range(sample0, sample0 + n_samples):
+        rng = np.random.default_rng(1000 + s)
+        for li, loc in enumerate(loci):
+            names = sims[li]["names"]
+            truth = [names[i] for i in rng.choice(len(names), 2, replace=False)]
+            n_pairs = int(round(COVERAGE * len(loc.backbone) / (2.0 * READ_LEN)))
+            text = sims[li]["sim"].generate(truth, n_pairs, seed=s * 64 + li + 1, err_rate=ERR, read_len=READ_LEN,
+                                            frag_len=FRAG_LEN, paired=True, prefix="s%05d_" % s)
+            units.append((li, text))
+    return units
+
+
+class ClockSampler:
+    def __init__(self, device):
+        self.rows, self.stop = [], threading.Event()
+        self.device = device
+        self.proc = None
+
+    def __enter__(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, universal_newlines=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for n, v in zip(names, r[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# oracle-port legs (CPU)
+# ------------------------------------------------------------------------------------------------------------
+_ORACLE = {}
+
+
+def _oracle_unit(job):
+    li, text = job
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import em_oracle
+    import hgt_oracle as O
+    ol = _ORACLE["loci"][li]
+    t0 = time.perf_counter()
+    res = O.type_locus(ol, text.decode().splitlines())
+    ta = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    iters = 0
+    cm = res["tables"]["exon"].cmpt_items(ol)
+    if cm:
+        _, it = em_oracle.single_abundance(cm, True, None)
+        iters += it
+    tb = time.perf_counter() - t0
+    return res["num_reads"], ta, iters, tb
+
+
+def build_oracle_loci(cont, loci):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import hgt_oracle as O
+    _ORACLE["loci"] = [O.OracleLocus(*locus_args(cont, loc.gene)) for loc in loci]
+
+
+def cpu_baseline(units):
+    """Oracle port on ONE core over a bounded sample of the same workload."""
+    reads = ta = iters = tb = 0
+    for job in units:
+        r, a, i, b = _oracle_unit(job)
+        reads += r
+        ta += a
+        iters += i
+        tb += b
+    return {"value": reads / ta if ta > 0 else None, "unit": "reads/s", "cores": 1, "kind": "port",
+            "sample": "%d (sample, locus) units = %d reads of the same workload, oracle/hgt_oracle.py stage (a); "
+                      "EM via oracle/em_oracle.c" % (len(units), reads),
+            "em_iters_per_sec": iters / tb if tb > 0 else None, "seconds": ta + tb}
+
+
+def run_reference_arm(args):
+    """--impl reference: the CPU implementation of the path (oracle port of the reference's Python) on all cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    scale = args.scale
+    loci, cont = build_database(scale)
+    from hisatgenotype_b200 import synth
+    sims = [{"sim": synth.ReadSimulator(l), "names": sorted(n for n in l.alleles if l.alleles[n])} for l in loci]
+    build_oracle_loci(cont, loci)
+    cores = os.cpu_count() or 1
+    n_samples = max(1, args.ref_samples)
+    ctx = mp.get_context("fork")
+    times, reads_step = [], 0
+    with ctx.Pool(cores) as pool:
+        for step in range(args.warmup + args.steps):
+            units = simulate_units(loci, sims, n_samples, 100000 + step * n_samples)
+            t0 = time.perf_counter()
+            out = pool.map(_oracle_unit, units, chunksize=1)
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                times.append(dt)
+                reads_step = sum(o[0] for o in out)
+    ms = 1000.0 * sum(times) / len(times)
+    value = reads_step / (ms / 1000.0)
+    line = {
+        "impl": "reference", "metric": "reads typed/sec", "value": value, "unit": "reads/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u64 bitsets + f64 EM", "data": "synthetic",
+        "config": workload_config(args, n_samples),
+        "cpu_baseline": {"value": value, "unit": "reads/s", "cores": cores, "kind": "port",
+                         "sample": "%d samples x 6 loci per step (%d reads), oracle port, multiprocessing over units"
+                                   % (n_samples, reads_step)},
+        "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, n_samples):
+    return {"workload": "BASELINE configs[1]: HLA-A/B/C/DQA1/DQB1/DRB1 paired-end 2x100 30x, synthetic database "
+                        "(A=7000/8000/7000/400/2000/3000 alleles, scale %.3g), batch of %d samples x 6 loci per step"
+                        % (args.scale, n_samples),
+            "samples_per_step": n_samples, "loci": [g for g, _, _, _ in LOCI], "coverage": COVERAGE,
+            "read_len": READ_LEN, "error_rate": ERR, "db_seed": DB_SEED,
+            "l2": "inputs per step exceed L2 and a 512 MiB buffer is rewritten between timed steps"}
+
+
+# ------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--samples", type=int, default=32, help="samples per step and GPU")
+    ap.add_argument("--scale", type=float, default=1.0, help="shrink the database (tests only)")
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--ref-samples", type=int, default=4)
+    ap.add_argument("--cpu-baseline-units", type=int, default=6)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    import numpy as np
+    import torch
+    import _hgt_path
+    _hgt_path.load()
+    from hisatgenotype_b200 import _lib, synth
+    from hisatgenotype_b200 import typing_core as TC
+    from hisatgenotype_b200.locus import LocusTables
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    os.environ["HGT_DEVICE"] = str(local)
+    ctx = _lib.ctx(local)
+    L = _lib.lib()
+
+    loci, cont = build_database(args.scale)
+    tables = [LocusTables(*locus_args(cont, l.gene), device=local) for l in loci]
+    sims = [{"sim": synth.ReadSimulator(l), "names": sorted(n for n in l.alleles if l.alleles[n])} for l in loci]
+    S = args.samples
+    units = simulate_units(loci, sims, S, rank * S)  # loci/sample sharding: no communication
+    params = TC.make_params()
+    stream = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    # ---- value: alignments already packed and resident in HBM -----------------------------------------------------
+    batch = TC.Batch(tables, params, True, device=local)
+    for li, text in units:
+        batch.add_unit(li, text)
+    batch.prepare()
+    tot = batch.totals()
+    L.hgt_profile_enable(ctx, 1)
+    for _ in range(args.warmup):
+        batch.execute(stream)
+        batch.finish(stream)
+    L.hgt_profile_reset(ctx)
+    launches0 = L.hgt_launch_count(ctx)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    with ClockSampler(local) as clocks:
+        for k in range(args.steps):
+            flush.zero_()
+            ev[k][0].record()
+            batch.execute(stream)
+            batch.finish(stream)
+            ev[k][1].record()
+        barrier()
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    dev_ms = float(sum(step_ms))
+    launches = L.hgt_launch_count(ctx) - launches0
+    stage_ms = (ctypes_array(8, "d"))
+    stage_n = (ctypes_array(8, "q"))
+    import ctypes
+    h2d, d2h = ctypes.c_int64(0), ctypes.c_int64(0)
+    L.hgt_profile_read(ctx, stage_ms, stage_n, ctypes.byref(h2d), ctypes.byref(d2h))
+    stage = {n: stage_ms[i] / args.steps for i, n in enumerate(
+        ["pileup", "compat", "class", "counts", "em1", "project", "em2"])}
+    # EM bookkeeping
+    em_iters = em_bytes = 0
+    for u in range(len(units)):
+        s = batch.unit_summary(u)
+        t = tables[batch.unit_locus[u]]
+        for lvl, tb in ((0, 1), (1, 3)):
+            it, C = s["em_iters"][lvl], s["n_classes"][tb]
+            em_iters += it
+            em_bytes += it * (3 * C * (t.wp * 8 + 8) + 6 * t.A * 8)
+    t_vec = torch.tensor([dev_ms, float(tot["num_reads"]), float(em_iters)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = t_vec.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = t_vec.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms_all, reads_all, iters_all = float(mx[0]), float(sm[1]), float(sm[2])
+    else:
+        dev_ms_all, reads_all, iters_all = dev_ms, float(tot["num_reads"]), float(em_iters)
+    ms_per_step = dev_ms_all / args.steps
+    value = reads_all / (ms_per_step / 1000.0)
+
+    # ---- e2e: host alignment text in, ranked alleles out ---------------------------------------------------------
+    L.hgt_profile_reset(ctx)
+    e2e_ms = []
+    n_e2e = max(2, min(args.steps, 3))
+    for k in range(1 + n_e2e):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if k == 1:
+            L.hgt_profile_reset(ctx)
+        a.record()
+        bt = TC.Batch(tables, params, True, device=local)
+        for li, text in units:
+            bt.add_unit(li, text)
+        bt.prepare()
+        bt.execute(stream)
+        bt.finish(stream)
+        calls = [bt.unit_abundance(u)[:2] for u in range(len(units))]
+        b.record()
+        torch.cuda.synchronize()
+        if k >= 1:
+            e2e_ms.append(a.elapsed_time(b))
+        bt.close()
+    L.hgt_profile_read(ctx, stage_ms, stage_n, ctypes.byref(h2d), ctypes.byref(d2h))
+    e2e_vec = torch.tensor([sum(e2e_ms) / len(e2e_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_vec, op=dist.ReduceOp.MAX)
+    e2e_value = reads_all / (float(e2e_vec[0]) / 1000.0)
+
+    if rank == 0:
+        peak, peak_src = measured_peak()
+        a_ms = stage["compat"] + stage["class"]
+        a_bytes = float(tot["algorithmic_bytes"])
+        achieved = a_bytes / (a_ms / 1000.0) / 1e9 if a_ms > 0 else None
+        em_ms = stage["em1"] + stage["em2"]
+        line = {
+            "metric": "reads typed/sec", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u64 bitsets + f64 EM", "data": "synthetic",
+            "config": workload_config(args, S),
+            "reads_per_step": reads_all, "pairs_per_step_rank0": tot["num_pairs"],
+            "em_iters_per_sec": iters_all / (ms_per_step / 1000.0) if ms_per_step else None,
+            "em_iters_per_step": iters_all,
+            "em_iters_per_sec_kernel_time": em_iters / (em_ms / 1000.0) if em_ms > 0 else None,
+            "stage_ms_per_step_rank0": stage,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak if achieved else None, "traffic": None,
+                         "kernel": "stage (a): compat_kernel + class_kernel", "peak_source": peak_src,
+                         "algorithmic_bytes_per_step": a_bytes, "kernel_ms_per_step": a_ms},
+            "roofline_em": {"bound": "hbm", "achieved": em_bytes / (em_ms / 1000.0) / 1e9 if em_ms > 0 else None,
+                            "peak": peak, "unit": "GB/s", "algorithmic_bytes_per_step": float(em_bytes),
+                            "kernel_ms_per_step": em_ms, "kernel": "em_kernel (batched, one CTA per unit)"},
+            "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d.value / n_e2e,
+                    "d2h_bytes_per_step": d2h.value / n_e2e, "ms_per_step": float(e2e_vec[0]),
+                    "input": "host alignment text, %d bytes per step on rank 0" % sum(len(t) for _, t in units)},
+            "gpu_launches": int(launches),
+            "clocks": clocks.summary(),
+            "example_call": calls[0],
+        }
+        if not args.no_cpu_baseline:
+            build_oracle_loci(cont, loci)
+            line["cpu_baseline"] = cpu_baseline(units[:args.cpu_baseline_units])
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+def ctypes_array(n, code):
+    import ctypes
+    return ((ctypes.c_double if code == "d" else ctypes.c_int64) * n)()
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -59,6 +59,12 @@ def lib():
         L.hgt_em_dev.restype = c_int
         L.hgt_em_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p, c_i32, c_i32,
                                  c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+        L.hgt_profile_enable.restype = None
+        L.hgt_profile_enable.argtypes = [c_void_p, c_int]
+        L.hgt_profile_reset.restype = None
+        L.hgt_profile_reset.argtypes = [c_void_p]
+        L.hgt_profile_read.restype = None
+        L.hgt_profile_read.argtypes = [c_void_p, c_void_p, c_void_p, P(c_i64), P(c_i64)]
         _lib = L
     return _lib
 

@@ -63,3 +63,25 @@ extern "C" void hgt_free(hgt_ctx *ctx) {
 
 extern "C" int64_t hgt_launch_count(const hgt_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int hgt_sm_count(const hgt_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
+
+extern "C" void hgt_profile_enable(hgt_ctx *ctx, int on) {
+    if (ctx) ctx->profile = on;
+}
+extern "C" void hgt_profile_reset(hgt_ctx *ctx) {
+    if (!ctx) return;
+    ctx->h2d_bytes = ctx->d2h_bytes = 0;
+    for (int i = 0; i < 8; i++) {
+        ctx->stage_ms[i] = 0;
+        ctx->stage_launches[i] = 0;
+    }
+}
+extern "C" void hgt_profile_read(const hgt_ctx *ctx, double *stage_ms, int64_t *stage_launches, int64_t *h2d_bytes,
+                                 int64_t *d2h_bytes) {
+    if (!ctx) return;
+    for (int i = 0; i < 8; i++) {
+        if (stage_ms) stage_ms[i] = ctx->stage_ms[i];
+        if (stage_launches) stage_launches[i] = ctx->stage_launches[i];
+    }
+    if (h2d_bytes) *h2d_bytes = ctx->h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = ctx->d2h_bytes;
+}

@@ -13,6 +13,11 @@ struct hgt_ctx {
     size_t smem_optin = 0;
     int64_t launches = 0;
     cudaStream_t stream = nullptr;  // stream used by the host-pointer entry points
+    // accounting read by bench.py through hgt_profile_read()
+    int64_t h2d_bytes = 0, d2h_bytes = 0;
+    int profile = 0;
+    double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // pileup, compat, class, counts, em1, project, em2, -
+    int64_t stage_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
 void hgt_set_error(const char *fmt, ...);

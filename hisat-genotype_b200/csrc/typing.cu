@@ -897,12 +897,53 @@ struct DevBuf {
     T *as() const { return static_cast<T *>(p); }
 };
 
+static thread_local hgt_ctx *g_acct = nullptr;  // context whose byte counters the copies below feed
+
 template <class T>
 static int upload(DevBuf *b, const std::vector<T> &v, cudaStream_t st) {
     HGT_CHECK(b->alloc(v.size() * sizeof(T)));
+    if (g_acct) g_acct->h2d_bytes += (int64_t)(v.size() * sizeof(T));
     if (!v.empty()) HGT_CUDA(cudaMemcpyAsync(b->p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
     return HGT_OK;
 }
+
+static inline cudaError_t d2h(void *dst, const void *src, size_t n, cudaStream_t st) {
+    if (g_acct) g_acct->d2h_bytes += (int64_t)n;
+    return cudaMemcpyAsync(dst, src, n, cudaMemcpyDeviceToHost, st);
+}
+
+struct StageTimer {  // CUDA-event bracket of one GPU stage, accumulated into ctx->stage_ms at resolve()
+    struct Span { int stage; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    hgt_ctx *ctx = nullptr;
+    cudaStream_t st = nullptr;
+    cudaEvent_t open_ev = nullptr;
+    int open_stage = -1;
+    void begin(hgt_ctx *c, cudaStream_t s, int stage) {
+        if (!c->profile) return;
+        ctx = c; st = s; open_stage = stage;
+        cudaEventCreate(&open_ev);
+        cudaEventRecord(open_ev, st);
+    }
+    void end(int n_launches) {
+        if (open_stage < 0) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, st);
+        spans.push_back({open_stage, open_ev, e});
+        ctx->stage_launches[open_stage] += n_launches;
+        open_stage = -1;
+    }
+    void resolve() {  // call after the stream has been synchronised
+        for (Span &s : spans) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) ctx->stage_ms[s.stage] += ms;
+            cudaEventDestroy(s.a);
+            cudaEventDestroy(s.b);
+        }
+        spans.clear();
+    }
+};
 
 static int wpl_of(int wp) {
     const int w = (wp + 31) / 32;
@@ -972,6 +1013,7 @@ struct hgt_batch {
     std::vector<LocusBatch> lb;
     bool keep_counts = false;
     bool prepared = false, executed = false, finished = false;
+    StageTimer timer;
     int remove_low = 1;
     std::vector<double> allele_len_host;  // unused placeholder
     ~hgt_batch() {
@@ -1081,6 +1123,7 @@ static int batch_prepare(hgt_batch *b) {
             if ((rc = d_f.alloc(n_units * (size_t)L)) != HGT_OK) break;
             cudaError_t e = cudaMemsetAsync(d_cnt.p, 0, n_units * (size_t)L * 24, st);
             const int64_t n = (int64_t)all.pos.size();
+            b->timer.begin(ctx, st, 0);
             if (e == cudaSuccess && n > 0) {
                 const int ctas = (int)std::min<int64_t>((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 8);
                 pileup_kernel<<<ctas, WARPS_PER_CTA * 32, 0, st>>>(d_pos.as<int32_t>(), d_co.as<int64_t>(), d_c.as<uint32_t>(),
@@ -1092,14 +1135,16 @@ static int batch_prepare(hgt_batch *b) {
             pileup_flags_kernel<<<(unsigned)((npos + 255) / 256), 256, 0, st>>>(d_cnt.as<uint32_t>(), npos, d_m.as<uint8_t>(),
                                                                                d_f.as<uint8_t>());
             ctx->launches++;
+            b->timer.end(n > 0 ? 2 : 1);
             if (e == cudaSuccess) e = cudaGetLastError();
-            if (e == cudaSuccess) e = cudaMemcpyAsync(mask.data(), d_m.p, mask.size(), cudaMemcpyDeviceToHost, st);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(flag.data(), d_f.p, flag.size(), cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = d2h(mask.data(), d_m.p, mask.size(), st);
+            if (e == cudaSuccess) e = d2h(flag.data(), d_f.p, flag.size(), st);
             if (e == cudaSuccess && b->keep_counts) {
                 counts.resize(n_units * (size_t)L * 6);
-                e = cudaMemcpyAsync(counts.data(), d_cnt.p, counts.size() * 4, cudaMemcpyDeviceToHost, st);
+                e = d2h(counts.data(), d_cnt.p, counts.size() * 4, st);
             }
             if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+            b->timer.resolve();
             if (e != cudaSuccess) {
                 hgt_set_error("pileup: %s", cudaGetErrorString(e));
                 rc = HGT_ERR_CUDA;
@@ -1210,11 +1255,13 @@ static int batch_prepare(hgt_batch *b) {
 
 // ---- stage 2: GPU only, no host synchronisation -----------------------------------------------------------------
 template <int WPL>
-static void launch_stage_a(hgt_ctx *ctx, cudaStream_t st, LocusBatch &lb) {
+static void launch_stage_a(hgt_batch *b, cudaStream_t st, LocusBatch &lb) {
+    hgt_ctx *ctx = b->ctx;
     const hgt_locus *loc = lb.loc;
     const LocusDev ld = locus_dev(loc);
     const int wp = loc->wp;
     const int64_t H = (int64_t)lb.hap_left.size();
+    b->timer.begin(ctx, st, 1);
     if (H > 0) {
         const size_t smem = (size_t)std::max(ld.V, 1) * 4;
         cudaFuncSetAttribute(compat_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1224,8 +1271,10 @@ static void launch_stage_a(hgt_ctx *ctx, cudaStream_t st, LocusBatch &lb) {
                                                                    lb.d_rows.as<int32_t>(), H, lb.d_hapbits.as<uint64_t>());
         ctx->launches++;
     }
+    b->timer.end(H > 0 ? 1 : 0);
     const ClassPool pool = lb.pool();
     const int64_t ns = (int64_t)lb.job_small.size(), nb = (int64_t)lb.job_big.size();
+    b->timer.begin(ctx, st, 2);
     if (ns > 0) {
         const int ctas = (int)std::min<int64_t>((ns + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 8);
         class_kernel<WPL, 3><<<ctas, WARPS_PER_CTA * 32, 0, st>>>(wp, loc->d_mask, lb.d_job_off.as<int64_t>(),
@@ -1240,6 +1289,7 @@ static void launch_stage_a(hgt_ctx *ctx, cudaStream_t st, LocusBatch &lb) {
                                                                   lb.d_job_list.as<int32_t>() + ns, nb, lb.d_hapbits.as<uint64_t>(), pool);
         ctx->launches++;
     }
+    b->timer.end((ns > 0) + (nb > 0));
 }
 
 static int em_on_table(hgt_ctx *ctx, cudaStream_t st, LocusBatch &lb, int table, const std::vector<int> &local_units,
@@ -1281,25 +1331,29 @@ static int batch_execute(hgt_batch *b, cudaStream_t st) {
         HGT_CUDA(cudaMemsetAsync(lb.d_ut_ncls.p, 0, n_units * 16, st));
         HGT_CUDA(cudaMemsetAsync(lb.d_is.p, 0, n_units * 12, st));
         switch (wpl_of(loc->wp)) {
-            case 1: launch_stage_a<1>(ctx, st, lb); break;
-            case 2: launch_stage_a<2>(ctx, st, lb); break;
-            case 4: launch_stage_a<4>(ctx, st, lb); break;
-            default: launch_stage_a<8>(ctx, st, lb); break;
+            case 1: launch_stage_a<1>(b, st, lb); break;
+            case 2: launch_stage_a<2>(b, st, lb); break;
+            case 4: launch_stage_a<4>(b, st, lb); break;
+            default: launch_stage_a<8>(b, st, lb); break;
         }
         HGT_CUDA(cudaGetLastError());
         // Gene_counts of the Gene table
         {
+            b->timer.begin(ctx, st, 3);
             dim3 grid((loc->A + 127) / 128, (unsigned)n_units);
             table_counts_kernel<<<grid, 128, 0, st>>>(loc->A, loc->wp, 0, lb.pool(), lb.d_acount.as<long long>(),
                                                       lb.d_afirst.as<int32_t>());
             ctx->launches++;
+            b->timer.end(1);
             HGT_CUDA(cudaGetLastError());
         }
         // first-level EM: exon table on the hla path (core:1732-1737), Gene table otherwise (core:1789)
         std::vector<int> all(n_units);
         std::iota(all.begin(), all.end(), 0);
+        b->timer.begin(ctx, st, 4);
         HGT_CHECK(em_on_table(ctx, st, lb, loc->is_hla ? 1 : 0, all, nullptr, loc->is_hla ? b->remove_low : 0, lb.d_prob,
                               lb.d_inres, lb.d_fk, lb.d_is, lb.d_emws));
+        b->timer.end(1);
     }
     b->executed = true;
     return HGT_OK;
@@ -1315,13 +1369,14 @@ static int batch_finish(hgt_batch *b, cudaStream_t st) {
         const int wp = loc->wp;
         lb.ut_ncls.resize(n_units * 4);
         lb.prob.resize(n_units * A); lb.inres.resize(n_units * A); lb.fk.resize(n_units * A); lb.is.resize(n_units * 3);
-        HGT_CUDA(cudaMemcpyAsync(lb.ut_ncls.data(), lb.d_ut_ncls.p, n_units * 16, cudaMemcpyDeviceToHost, st));
-        HGT_CUDA(cudaMemcpyAsync(lb.prob.data(), lb.d_prob.p, n_units * A * 8, cudaMemcpyDeviceToHost, st));
-        HGT_CUDA(cudaMemcpyAsync(lb.inres.data(), lb.d_inres.p, n_units * A, cudaMemcpyDeviceToHost, st));
-        HGT_CUDA(cudaMemcpyAsync(lb.fk.data(), lb.d_fk.p, n_units * A * 4, cudaMemcpyDeviceToHost, st));
-        HGT_CUDA(cudaMemcpyAsync(lb.is.data(), lb.d_is.p, n_units * 12, cudaMemcpyDeviceToHost, st));
+        HGT_CUDA(d2h(lb.ut_ncls.data(), lb.d_ut_ncls.p, n_units * 16, st));
+        HGT_CUDA(d2h(lb.prob.data(), lb.d_prob.p, n_units * A * 8, st));
+        HGT_CUDA(d2h(lb.inres.data(), lb.d_inres.p, n_units * A, st));
+        HGT_CUDA(d2h(lb.fk.data(), lb.d_fk.p, n_units * A * 4, st));
+        HGT_CUDA(d2h(lb.is.data(), lb.d_is.p, n_units * 12, st));
     }
     HGT_CUDA(cudaStreamSynchronize(st));
+    b->timer.resolve();
     for (LocusBatch &lb : b->lb) {
         if (lb.units.empty() || !lb.loc->is_hla) continue;
         const hgt_locus *loc = lb.loc;
@@ -1369,6 +1424,7 @@ static int batch_finish(hgt_batch *b, cudaStream_t st) {
             HGT_CHECK(upload(&lb.d_len, loc->allele_len, st));
         }
         {
+            b->timer.begin(ctx, st, 5);
             dim3 grid(8, (unsigned)std::min<size_t>(ulist.size(), 16384));
             const ClassPool pool = lb.pool();
             switch (wpl_of(wp)) {
@@ -1378,6 +1434,7 @@ static int batch_finish(hgt_batch *b, cudaStream_t st) {
                 default: project_kernel<8><<<grid, WARPS_PER_CTA * 32, 0, st>>>(wp, (int)ulist.size(), lb.d_ulist.as<int32_t>(), lb.d_keep.as<uint64_t>(), pool); break;
             }
             ctx->launches++;
+            b->timer.end(1);
             HGT_CUDA(cudaGetLastError());
         }
         HGT_CHECK(lb.d_prob2.alloc(n_units * A * 8));
@@ -1387,16 +1444,19 @@ static int batch_finish(hgt_batch *b, cudaStream_t st) {
         HGT_CUDA(cudaMemsetAsync(lb.d_is2.p, 0, n_units * 12, st));
         HGT_CHECK(lb.d_emws2.alloc(hgt_em_batch_ws_bytes((int)ulist.size(), wp)));
         std::vector<int> lu(ulist.begin(), ulist.end());
+        b->timer.begin(ctx, st, 6);
         HGT_CHECK(em_on_table(ctx, st, lb, 3, lu, lb.d_len.as<double>(), 1, lb.d_prob2, lb.d_inres2, lb.d_fk2, lb.d_is2,
                               lb.d_emws2));
+        b->timer.end(1);
         lb.prob2.resize(n_units * A); lb.inres2.resize(n_units * A); lb.fk2.resize(n_units * A); lb.is2.resize(n_units * 3);
-        HGT_CUDA(cudaMemcpyAsync(lb.prob2.data(), lb.d_prob2.p, n_units * A * 8, cudaMemcpyDeviceToHost, st));
-        HGT_CUDA(cudaMemcpyAsync(lb.inres2.data(), lb.d_inres2.p, n_units * A, cudaMemcpyDeviceToHost, st));
-        HGT_CUDA(cudaMemcpyAsync(lb.fk2.data(), lb.d_fk2.p, n_units * A * 4, cudaMemcpyDeviceToHost, st));
-        HGT_CUDA(cudaMemcpyAsync(lb.is2.data(), lb.d_is2.p, n_units * 12, cudaMemcpyDeviceToHost, st));
-        HGT_CUDA(cudaMemcpyAsync(lb.ut_ncls.data(), lb.d_ut_ncls.p, n_units * 16, cudaMemcpyDeviceToHost, st));
+        HGT_CUDA(d2h(lb.prob2.data(), lb.d_prob2.p, n_units * A * 8, st));
+        HGT_CUDA(d2h(lb.inres2.data(), lb.d_inres2.p, n_units * A, st));
+        HGT_CUDA(d2h(lb.fk2.data(), lb.d_fk2.p, n_units * A * 4, st));
+        HGT_CUDA(d2h(lb.is2.data(), lb.d_is2.p, n_units * 12, st));
+        HGT_CUDA(d2h(lb.ut_ncls.data(), lb.d_ut_ncls.p, n_units * 16, st));
     }
     HGT_CUDA(cudaStreamSynchronize(st));
+    b->timer.resolve();
     b->finished = true;
     return HGT_OK;
 }
@@ -1450,6 +1510,7 @@ extern "C" int hgt_batch_prepare(hgt_batch *b) {
         return HGT_ERR_ARG;
     }
     HGT_CUDA(cudaSetDevice(b->ctx->device));
+    g_acct = b->ctx;
     return batch_prepare(b);
 }
 
@@ -1459,6 +1520,7 @@ extern "C" int hgt_batch_execute(hgt_batch *b, void *stream) {
         return HGT_ERR_ARG;
     }
     HGT_CUDA(cudaSetDevice(b->ctx->device));
+    g_acct = b->ctx;
     return batch_execute(b, stream ? static_cast<cudaStream_t>(stream) : b->ctx->stream);
 }
 
@@ -1468,6 +1530,7 @@ extern "C" int hgt_batch_finish(hgt_batch *b, void *stream) {
         return HGT_ERR_ARG;
     }
     HGT_CUDA(cudaSetDevice(b->ctx->device));
+    g_acct = b->ctx;
     return batch_finish(b, stream ? static_cast<cudaStream_t>(stream) : b->ctx->stream);
 }
 
@@ -1557,16 +1620,16 @@ extern "C" int hgt_batch_unit_table(hgt_batch *b, int64_t unit, int32_t table, u
     if (n > 0) {
         HGT_CUDA(cudaMemcpyAsync(bits.data(), lb.d_bits.as<uint64_t>() + (size_t)base * wp, (size_t)n * wp * 8,
                                  cudaMemcpyDeviceToHost, st));
-        HGT_CUDA(cudaMemcpyAsync(cnt.data(), lb.d_count.as<unsigned long long>() + base, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
-        HGT_CUDA(cudaMemcpyAsync(first.data(), lb.d_first.as<int32_t>() + base, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        HGT_CUDA(d2h(cnt.data(), lb.d_count.as<unsigned long long>() + base, (size_t)n * 8, st));
+        HGT_CUDA(d2h(first.data(), lb.d_first.as<int32_t>() + base, (size_t)n * 4, st));
     }
     std::vector<long long> ac;
     std::vector<int32_t> af;
     if ((allele_count || allele_first) && table == 0) {
         ac.resize(A);
         af.resize(A);
-        HGT_CUDA(cudaMemcpyAsync(ac.data(), lb.d_acount.as<long long>() + (size_t)U.local * A, (size_t)A * 8, cudaMemcpyDeviceToHost, st));
-        HGT_CUDA(cudaMemcpyAsync(af.data(), lb.d_afirst.as<int32_t>() + (size_t)U.local * A, (size_t)A * 4, cudaMemcpyDeviceToHost, st));
+        HGT_CUDA(d2h(ac.data(), lb.d_acount.as<long long>() + (size_t)U.local * A, (size_t)A * 8, st));
+        HGT_CUDA(d2h(af.data(), lb.d_afirst.as<int32_t>() + (size_t)U.local * A, (size_t)A * 4, st));
     }
     HGT_CUDA(cudaStreamSynchronize(st));
     // dict order = first-seen order (each pair creates at most one class per table, so `first` is a strict key)

@@ -52,6 +52,14 @@ void hgt_free(hgt_ctx *ctx);
 /* number of kernels this context has launched so far (bench.py reports it as gpu_launches) */
 int64_t hgt_launch_count(const hgt_ctx *ctx);
 int hgt_sm_count(const hgt_ctx *ctx);
+/* Measurement hooks for bench.py: with profiling on, batch execute/finish bracket each GPU stage with CUDA
+ * events on the launching stream.  stage_ms / stage_launches [8]: pileup, haplotype->allele-set (compat),
+ * per-pair class + de-duplication, Gene_counts, first-level EM, projection, second-level EM, unused.
+ * h2d/d2h_bytes count every host<->device copy the library issued since the last reset. */
+void hgt_profile_enable(hgt_ctx *ctx, int on);
+void hgt_profile_reset(hgt_ctx *ctx);
+void hgt_profile_read(const hgt_ctx *ctx, double *stage_ms, int64_t *stage_launches, int64_t *h2d_bytes,
+                      int64_t *d2h_bytes);
 
 /* ---- stage (b): EM abundance ----------------------------------------------------------------------------
  * Replaces single_abundance(Gene_cmpt, remove_low_abundance_allele, Gene_length)
