@@ -301,6 +301,178 @@ __device__ void em_prune(const EmArgs &a, const Smem &sm, double *p, uint8_t *li
     __syncthreads();
 }
 
+
+// ---- compact mode ------------------------------------------------------------------------------------------------
+// Once at most 64 alleles are still keys of Gene_prob (typically right after the first select_alleles() at
+// iteration 10, common:1390-1391) every class row collapses to ONE 64-bit word over those alleles.  The rest of
+// the loop then runs entirely out of shared memory: cm[C] (row masks), cnt[C], w[C] and 64-entry vectors.
+// Sums run in a fixed order (ascending allele / fixed lane stride + butterfly), so results are reproducible.
+struct Compact {
+    uint64_t *cm;   // [C] membership of the compact alleles in each class
+    double *cnt;    // [C]
+    double *w;      // [C] n_k / s_k, negative = class skipped (s_k <= 0)
+    int *lv;        // [64] allele id of compact slot j (ascending)
+    double *v;      // [4][64] p0, p1, p2, extrapolated
+    int *l;         // [3][64] key flags of p0, p1, p2
+    double *len;    // [64]
+    double *q;      // [64] scratch
+    int n;          // compact alleles
+};
+
+__device__ void compact_sweep(const EmArgs &a, const Compact &c, const double *pin, const int *lin, double *pout,
+                              int *lout, int *status) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int C = a.C;
+    for (int r = tid; r < C; r += EM_THREADS) {
+        uint64_t m = c.cm[r];
+        double s = 0.0;
+        while (m) {
+            const int j = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            if (lin[j]) s += pin[j];
+        }
+        c.w[r] = s > 0.0 ? c.cnt[r] / s : -1.0;
+    }
+    __syncthreads();
+    for (int j = warp; j < c.n; j += EM_WARPS) {
+        double acc = 0.0;
+        int hit = 0;
+        for (int r = lane; r < C; r += 32) {
+            const double w = c.w[r];
+            if (((c.cm[r] >> j) & 1ull) && w >= 0.0) {
+                acc += w;
+                hit = 1;
+            }
+        }
+        acc = warp_sum(acc);
+        hit = __any_sync(0xffffffffu, hit);
+        if (lane == 0) {
+            const int key = lin[j] && hit;
+            double q = key ? pin[j] * acc : 0.0;
+            if (a.len && key) q = q / c.len[j];
+            c.q[j] = q;
+            lout[j] = key;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double part = 0.0;
+        int any = 0;
+        for (int j = lane; j < c.n; j += 32)
+            if (lout[j]) {
+                part += c.q[j];
+                any = 1;
+            }
+        const double total = warp_sum(part);
+        any = __any_sync(0xffffffffu, any);
+        if (any && !(total > 0.0) && !(total < 0.0) && lane == 0) *status = HGT_ERR_ZERODIV;
+        for (int j = lane; j < c.n; j += 32) pout[j] = lout[j] ? c.q[j] / total : 0.0;
+    }
+    __syncthreads();
+}
+
+// Runs the remaining loop iterations in compact form.  On return slot 0 holds Gene_prob, `last` tells which
+// slot fed the last next_prob() (0 or 3) with key flags in l[last == 3 ? 2 : 0].
+__device__ void compact_loop(const EmArgs &a, Compact &c, double &diff, int &iter, int &sweeps, int &last,
+                             bool &have_last, int *status) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    double *v0 = c.v, *v1 = c.v + 64, *v2 = c.v + 128, *v3 = c.v + 192;
+    int *l0 = c.l, *l1 = c.l + 64, *l2 = c.l + 128;
+    __shared__ double s_diff;
+    __shared__ int s_flag;
+    while (a.fixed_iters > 0 ? iter < a.fixed_iters : (diff > 0.0001 && iter < 1000)) {
+        if (*status != HGT_OK) break;
+        compact_sweep(a, c, v0, l0, v1, l1, status);
+        compact_sweep(a, c, v1, l1, v2, l2, status);
+        sweeps += 2;
+        if (warp == 0) {
+            double ssr = 0.0, ssv = 0.0;
+            int keyerr = 0;
+            for (int j = lane; j < c.n; j += 32)
+                if (l0[j]) {
+                    if (!l1[j] || !l2[j]) keyerr = 1;
+                    const double r = v1[j] - v0[j];
+                    const double v = v2[j] - v1[j] - r;
+                    ssr += r * r;
+                    ssv += v * v;
+                }
+            ssr = warp_sum(ssr);
+            ssv = warp_sum(ssv);
+            keyerr = __any_sync(0xffffffffu, keyerr);
+            int flag = 0;
+            if (keyerr) flag = 2;
+            else if (ssv > 0.0) {
+                flag = 1;
+                const double g = -sqrt(ssr / ssv);
+                for (int j = lane; j < c.n; j += 32) {
+                    double x = 0.0;
+                    if (l0[j]) {
+                        const double r = v1[j] - v0[j];
+                        const double v = v2[j] - v1[j] - r;
+                        x = v0[j] - 2 * g * r + g * g * v;
+                        x = x > 0.0 ? x : 0.0;
+                    }
+                    v3[j] = x;
+                }
+            }
+            if (lane == 0) s_flag = flag;
+        }
+        __syncthreads();
+        const int flag = s_flag;
+        if (flag == 2) {
+            if (tid == 0) *status = HGT_ERR_KEY;
+            __syncthreads();
+            break;
+        }
+        if (flag == 1) {
+            compact_sweep(a, c, v3, l2, v1, l1, status);
+            sweeps += 1;
+            last = 3;
+        } else {
+            last = 0;
+        }
+        have_last = true;
+        if (warp == 0) {
+            double d = 0.0;
+            for (int j = lane; j < c.n; j += 32)
+                if (l0[j]) d += l1[j] ? fabs(v0[j] - v1[j]) : v0[j];
+            d = warp_sum(d);
+            if (lane == 0) s_diff = d;
+        }
+        __syncthreads();
+        diff = s_diff;
+        // Gene_prob = Gene_prob_next: slot 0 <- slot 1 (a copy keeps `last == 0` pointing at the old vector in slot 1)
+        if (tid < 64) {
+            const double t = v0[tid];
+            const int tl = l0[tid];
+            v0[tid] = v1[tid];
+            l0[tid] = l1[tid];
+            v1[tid] = t;
+            l1[tid] = tl;
+        }
+        __syncthreads();
+        if (last == 0) last = 1;  // the input of the last next_prob() now sits in slot 1
+        if (iter >= 10 && a.remove_low) {
+            if (warp == 0) {
+                double mx = -1.0;
+                for (int j = lane; j < c.n; j += 32)
+                    if (l0[j]) mx = fmax(mx, v0[j]);
+                mx = warp_max(mx);
+                if (mx >= 0.0) {
+                    const double thr = mx / 10.0;
+                    for (int j = lane; j < c.n; j += 32)
+                        if (l0[j] && !(v0[j] >= thr)) {
+                            l0[j] = 0;
+                            v0[j] = 0.0;
+                        }
+                }
+            }
+            __syncthreads();
+        }
+        iter++;
+    }
+}
+
 template <int NA, bool COOP>
 __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restrict__ args_arr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -344,8 +516,94 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
     const double *last_in = v0;
     const uint8_t *last_live = l0;
     bool have_last = false;
+    // bytes from sm.p to the end of the slab buffer can be re-used by the compact mode
+    const size_t compact_room = (size_t)Apad * 8 + (size_t)a.slab_rows * 8 + (size_t)a.slab_rows * a.wp * 8;
+    const bool compact_ok = !COOP && ((size_t)a.C * 24 + 64 * 64 <= compact_room);
     while (a.fixed_iters > 0 ? iter < a.fixed_iters : (diff > 0.0001 && iter < 1000)) {
         if (s_status != HGT_OK) break;
+        if (compact_ok && (iter == 0 || (iter > 10 && a.remove_low))) {
+            int cnt_live = 0;
+            for (int al = tid; al < a.A; al += EM_THREADS) cnt_live += l0[al] ? 1 : 0;
+            cnt_live = (int)block_sum((double)cnt_live, sm.red);
+            if (cnt_live > 0 && cnt_live <= 64) {
+                // ---- build the compact problem ---------------------------------------------------------------
+                Compact c;
+                unsigned char *base = reinterpret_cast<unsigned char *>(sm.p);
+                c.v = reinterpret_cast<double *>(base);
+                c.len = c.v + 256;
+                c.q = c.len + 64;
+                c.lv = reinterpret_cast<int *>(c.q + 64);
+                c.l = c.lv + 64;
+                c.cnt = reinterpret_cast<double *>(c.l + 192);
+                c.w = c.cnt + a.C;
+                c.cm = reinterpret_cast<uint64_t *>(c.w + a.C);
+                c.n = cnt_live;
+                __syncthreads();
+                if (tid < 32) {  // ordered list of key alleles
+                    int n = 0;
+                    for (int a0 = 0; a0 < a.A; a0 += 32) {
+                        const int al = a0 + tid;
+                        const bool k = al < a.A && l0[al];
+                        const unsigned m = __ballot_sync(0xffffffffu, k);
+                        if (k) c.lv[n + __popc(m & ((1u << tid) - 1u))] = al;
+                        n += __popc(m);
+                    }
+                }
+                __syncthreads();
+                if (tid < 64) {
+                    const bool k = tid < c.n;
+                    const int al = k ? c.lv[tid] : 0;
+                    c.v[tid] = k ? v0[al] : 0.0;
+                    c.v[64 + tid] = c.v[128 + tid] = c.v[192 + tid] = 0.0;
+                    c.l[tid] = k ? 1 : 0;
+                    c.l[64 + tid] = c.l[128 + tid] = 0;
+                    c.len[tid] = (k && a.len) ? a.len[al] : 1.0;
+                }
+                // row masks straight from global memory: warp per class row, lane per compact allele
+                {
+                    const int lane = tid & 31, warp = tid >> 5;
+                    const int a_lo = lane < c.n ? c.lv[lane] : -1, a_hi = lane + 32 < c.n ? c.lv[lane + 32] : -1;
+                    for (int r = warp; r < a.C; r += EM_WARPS) {
+                        const uint64_t *row = a.bits + (size_t)r * a.wp;
+                        const bool b_lo = a_lo >= 0 && ((row[a_lo >> 6] >> (a_lo & 63)) & 1ull);
+                        const bool b_hi = a_hi >= 0 && ((row[a_hi >> 6] >> (a_hi & 63)) & 1ull);
+                        const unsigned m_lo = __ballot_sync(0xffffffffu, b_lo), m_hi = __ballot_sync(0xffffffffu, b_hi);
+                        if (lane == 0) {
+                            c.cm[r] = (uint64_t)m_lo | ((uint64_t)m_hi << 32);
+                            c.cnt[r] = a.cnt_u64 ? (double)a.cnt_u64[r] : a.cnt[r];
+                        }
+                    }
+                }
+                __syncthreads();
+                int last = 0;
+                const int iter_before = iter;
+                compact_loop(a, c, diff, iter, sweeps, last, have_last, &s_status);
+                const bool ran = iter > iter_before;  // otherwise the dense last_in / last_live stay valid
+                // ---- back to the dense representation for the epilogue ----------------------------------------
+                for (int al = tid; al < a.A; al += EM_THREADS) {
+                    v0[al] = 0.0; l0[al] = 0;
+                    if (ran) { v3[al] = 0.0; l2[al] = 0; }
+                }
+                __syncthreads();
+                if (tid < c.n) {
+                    const int al = c.lv[tid];
+                    v0[al] = c.v[tid];
+                    l0[al] = (uint8_t)c.l[tid];
+                    if (ran) {
+                        const int slot = last;  // 1 or 3
+                        v3[al] = c.v[slot * 64 + tid];
+                        l2[al] = (uint8_t)(slot == 3 ? c.l[128 + tid] : c.l[64 + tid]);
+                    }
+                }
+                __syncthreads();
+                if (ran) {
+                    last_in = v3;
+                    last_live = l2;
+                }
+                loaded = false;  // the slab buffer was overwritten
+                break;
+            }
+        }
         em_sweep<NA, COOP>(a, sm, MODE_NEXT, v0, l0, v1, l1, nullptr, row_lo, row_hi, resident, loaded, parity,
                            &s_status);
         em_sweep<NA, COOP>(a, sm, MODE_NEXT, v1, l1, v2, l2, nullptr, row_lo, row_hi, resident, loaded, parity,
