@@ -23,6 +23,7 @@
 #include <cooperative_groups.h>
 #include <math.h>
 
+#include <algorithm>
 #include <vector>
 
 #include "common.cuh"
@@ -42,6 +43,8 @@ struct EmArgs {
     const double *len;
     int C, A, wp, remove_low, fixed_iters;
     int slab_rows;  // rows per slab buffer
+    int compact;     // host plan: keep an allele-compacted copy of ALL class rows in shared memory (batched launches)
+    int A_live_max;  // upper bound of the alleles that are members of any class (sizes the compact buffers)
     const unsigned long long *cnt_u64;  // class counts as integers (device-resident tables); overrides cnt
     const int32_t *C_ptr;               // number of classes read on the device at launch; overrides C
     const int32_t *class_first;         // tie-break key of each class (first pair index); default = class index
@@ -65,7 +68,14 @@ struct Smem {
     double *w;
     uint8_t *valid;
     uint64_t *slab;
+    // allele-compacted layout only (null otherwise)
+    const int32_t *lv;   // [A'] original allele index of compact column j (ascending)
+    double *cnt;         // [C] class counts as doubles
+    uint64_t *cm64;      // [C] row masks of the <= 64-allele mode
+    unsigned char *c64;  // 4 KB block for the small vectors of the <= 64-allele mode
 };
+
+__device__ __forceinline__ int orig_allele(const Smem &sm, int al) { return sm.lv ? sm.lv[al] : al; }
 
 __device__ __forceinline__ double block_sum(double v, double *red) {
     v = warp_sum(v);
@@ -144,18 +154,24 @@ __device__ void em_sweep(const EmArgs &a, const Smem &sm, int mode, const double
                 for (int o = 16; o > 0; o >>= 1) pc += __shfl_xor_sync(0xffffffffu, pc, o);
                 s = (double)pc;
             } else {
-                for (int j = 0; j < wp; j++) {
-                    const uint64_t word = row[j];  // same address in all lanes: broadcast
-                    if (word == 0) continue;
-                    if ((word >> lane) & 1ull) s += sm.p[j * 64 + lane];
-                    if ((word >> (lane + 32)) & 1ull) s += sm.p[j * 64 + 32 + lane];
+                // lane per 32-bit word, walking its set bits: cost follows the row's population, not its width
+                const uint32_t *row32 = reinterpret_cast<const uint32_t *>(row);
+                for (int j = lane; j < 2 * wp; j += 32) {
+                    uint32_t m = row32[j];
+                    const double *pj = sm.p + j * 32;
+                    while (m) {
+                        const int b = __ffs((int)m) - 1;
+                        m &= m - 1;
+                        s += pj[b];
+                    }
                 }
                 s = warp_sum(s);
             }
             if (lane == 0) {
                 const bool ok = s > 0.0;
                 sm.valid[r] = ok ? 1 : 0;
-                sm.w[r] = ok ? (a.cnt_u64 ? (double)a.cnt_u64[r0 + r] : a.cnt[r0 + r]) / s : 0.0;
+                const double n = sm.cnt ? sm.cnt[r0 + r] : (a.cnt_u64 ? (double)a.cnt_u64[r0 + r] : a.cnt[r0 + r]);
+                sm.w[r] = ok ? n / s : 0.0;
             }
         }
         __syncthreads();
@@ -181,7 +197,8 @@ __device__ void em_sweep(const EmArgs &a, const Smem &sm, int mode, const double
                 for (int i = 0; i < NA; i++) {
                     const int al = tid + i * EM_THREADS;
                     if (al < Apad) {
-                        const uint32_t w32 = slab32[(size_t)r * wp * 2 + (al >> 5)];
+                        const uint32_t w32 = slab32[(size_t)r * wp * 2 + (al >> 5)];  // one word per warp: broadcast
+                        if (w32 == 0u) continue;                                       // warp-uniform skip
                         if ((w32 >> (al & 31)) & 1u) {
                             acc[i] += w;
                             hit |= 1u << i;
@@ -242,7 +259,7 @@ __device__ void em_sweep(const EmArgs &a, const Smem &sm, int mode, const double
 #pragma unroll
         for (int i = 0; i < NA; i++) {
             const int al = tid + i * EM_THREADS;
-            if (al < A) fkout[al] = livein[al] ? fk[i] : FK_NONE;
+            if (al < A) fkout[orig_allele(sm, al)] = livein[al] ? fk[i] : FK_NONE;
         }
         __syncthreads();
         return;
@@ -259,7 +276,7 @@ __device__ void em_sweep(const EmArgs &a, const Smem &sm, int mode, const double
             key = ((hit >> i) & 1u) && (mode == MODE_INIT || livein[al]);
             if (key) {
                 q = (mode == MODE_INIT) ? acc[i] : sm.p[al] * acc[i];
-                if (a.len) q = q / a.len[al];
+                if (a.len) q = q / a.len[orig_allele(sm, al)];
                 part += q;
                 nkeys = 1;
             }
@@ -473,20 +490,136 @@ __device__ void compact_loop(const EmArgs &a, Compact &c, double &diff, int &ite
     }
 }
 
+// Builds the allele-compacted problem in shared memory: the alleles that are members of at least one class
+// (every other allele keeps probability 0 for the whole run, common:1299-1309) are renumbered 0..A'-1 in
+// ascending order and every class row is gathered into A' bits.  Returns A'.
+__device__ int em_compact_build(const EmArgs &a, Smem &sm, int32_t *lv, int C, int *s_int) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wp = a.wp;  // <= 256
+    uint64_t *lw = reinterpret_cast<uint64_t *>(sm.c64);           // [256] OR of all rows
+    int32_t *base = reinterpret_cast<int32_t *>(sm.c64 + 2048);    // [256] live alleles before word j
+    for (int j = tid; j < 256; j += EM_THREADS) lw[j] = 0ull;
+    __syncthreads();
+    {
+        uint64_t acc[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc[i] = 0ull;
+        for (int r = warp; r < C; r += EM_WARPS) {
+            const uint64_t *row = a.bits + (size_t)r * wp;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const int j = lane + 32 * i;
+                if (j < wp) acc[i] |= row[j];
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            if (acc[i]) atomicOr(reinterpret_cast<unsigned long long *>(&lw[lane + 32 * i]), (unsigned long long)acc[i]);
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int run = 0;
+        for (int j0 = 0; j0 < wp; j0 += 32) {
+            const int j = j0 + lane;
+            const int c = j < wp ? __popcll(lw[j]) : 0;
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            if (j < wp) base[j] = run + incl - c;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) *s_int = run;
+    }
+    __syncthreads();
+    const int An = *s_int;
+    if (An > a.A_live_max) return An;  // caller reports the broken bound
+    for (int j = tid; j < wp; j += EM_THREADS) {
+        uint64_t m = lw[j];
+        int n = base[j];
+        while (m) {
+            const int b = __ffsll((long long)m) - 1;
+            m &= m - 1;
+            lv[n++] = j * 64 + b;
+        }
+    }
+    __syncthreads();
+    const int wpc = max(2, ((An + 63) / 64 + 1) & ~1);
+    uint32_t *slab32 = reinterpret_cast<uint32_t *>(sm.slab);
+    for (int r = warp; r < C; r += EM_WARPS) {
+        const uint64_t *row = a.bits + (size_t)r * wp;
+        for (int c = 0; c < 2 * wpc; c++) {
+            const int k = c * 32 + lane;
+            bool bit = false;
+            if (k < An) {
+                const int al = lv[k];
+                bit = (row[al >> 6] >> (al & 63)) & 1ull;
+            }
+            const unsigned m = __ballot_sync(0xffffffffu, bit);
+            if (lane == 0) slab32[(size_t)r * wpc * 2 + c] = m;
+        }
+        if (lane == 0) sm.cnt[r] = a.cnt_u64 ? (double)a.cnt_u64[r] : a.cnt[r];
+    }
+    __syncthreads();
+    return An;
+}
+
 template <int NA, bool COOP>
 __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restrict__ args_arr) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     EmArgs a = COOP ? args_arr[0] : args_arr[blockIdx.x];
     if (a.C_ptr) a.C = min(*a.C_ptr, a.C);
     const int tid = threadIdx.x;
-    const int Apad = a.wp * 64;
+    const int A_orig = a.A;
+    __shared__ int s_status;
+    __shared__ int s_int;
+    if (tid == 0) s_status = HGT_OK;
     Smem sm;
     sm.mbar = reinterpret_cast<uint64_t *>(smem_raw);
     sm.red = reinterpret_cast<double *>(smem_raw + 16);
-    sm.p = sm.red + 40;
-    sm.w = sm.p + Apad;
-    sm.slab = reinterpret_cast<uint64_t *>(sm.w + a.slab_rows);  // offset stays a multiple of 16 (slab_rows even)
-    sm.valid = reinterpret_cast<uint8_t *>(sm.slab + (size_t)a.slab_rows * a.wp);
+    sm.lv = nullptr; sm.cnt = nullptr; sm.cm64 = nullptr; sm.c64 = nullptr;
+    bool compacted = false;
+    if (!COOP && a.compact) {
+        // ---- allele-compacted, fully shared-memory-resident problem ---------------------------------------------
+        const int wpc_max = max(2, ((a.A_live_max + 63) / 64 + 1) & ~1);
+        const size_t Apadc = (size_t)wpc_max * 64, Cpad = (size_t)a.slab_rows;
+        unsigned char *q = smem_raw + 16 + 40 * 8;
+        sm.c64 = q; q += 4096;
+        int32_t *lv = reinterpret_cast<int32_t *>(q); q += Apadc * 4;
+        sm.p = reinterpret_cast<double *>(q); q += Apadc * 8;
+        sm.w = reinterpret_cast<double *>(q); q += Cpad * 8;
+        sm.cnt = reinterpret_cast<double *>(q); q += Cpad * 8;
+        sm.cm64 = reinterpret_cast<uint64_t *>(q); q += Cpad * 8;
+        sm.slab = reinterpret_cast<uint64_t *>(q); q += Cpad * wpc_max * 8;
+        sm.valid = q;
+        for (int al = tid; al < A_orig; al += EM_THREADS) {
+            a.prob[al] = 0.0;
+            a.in_result[al] = 0;
+            a.first_class[al] = FK_NONE;
+        }
+        const int An = em_compact_build(a, sm, lv, a.C, &s_int);
+        if (An > a.A_live_max) {
+            if (tid == 0) {
+                a.iters_status[0] = 0;
+                a.iters_status[1] = HGT_ERR_ARG;
+                a.iters_status[2] = 0;
+            }
+            return;
+        }
+        sm.lv = lv;
+        a.A = An;
+        a.wp = max(2, ((An + 63) / 64 + 1) & ~1);
+        compacted = true;
+    } else {
+        const int Apad0 = a.wp * 64;
+        sm.p = sm.red + 40;
+        sm.w = sm.p + Apad0;
+        sm.slab = reinterpret_cast<uint64_t *>(sm.w + a.slab_rows);  // offset stays a multiple of 16 (slab_rows even)
+        sm.valid = reinterpret_cast<uint8_t *>(sm.slab + (size_t)a.slab_rows * a.wp);
+    }
+    const int Apad = a.wp * 64;
     if (tid == 0) {
         mbar_init(sm.mbar, 1);
         fence_barrier_init();
@@ -499,12 +632,9 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
         row_lo = min(a.C, (int)blockIdx.x * per);
         row_hi = min(a.C, row_lo + per);
     }
-    const bool resident = (row_hi - row_lo) <= a.slab_rows;
-    bool loaded = false;
+    const bool resident = compacted || (row_hi - row_lo) <= a.slab_rows;
+    bool loaded = compacted;
     uint32_t parity = 0;
-    __shared__ int s_status;
-    if (tid == 0) s_status = HGT_OK;
-    __syncthreads();
     double *v0 = a.vec, *v1 = a.vec + Apad, *v2 = a.vec + 2 * (size_t)Apad, *v3 = a.vec + 3 * (size_t)Apad;
     uint8_t *l0 = a.live, *l1 = a.live + Apad, *l2 = a.live + 2 * (size_t)Apad;
     // In cooperative mode every CTA computes the same vectors and writes identical values to the shared
@@ -517,8 +647,9 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
     const uint8_t *last_live = l0;
     bool have_last = false;
     // bytes from sm.p to the end of the slab buffer can be re-used by the compact mode
+    // (the allele-compacted layout has dedicated buffers for it instead, so its slab stays intact)
     const size_t compact_room = (size_t)Apad * 8 + (size_t)a.slab_rows * 8 + (size_t)a.slab_rows * a.wp * 8;
-    const bool compact_ok = !COOP && ((size_t)a.C * 24 + 64 * 64 <= compact_room);
+    const bool compact_ok = !COOP && (compacted || (size_t)a.C * 24 + 64 * 64 <= compact_room);
     while (a.fixed_iters > 0 ? iter < a.fixed_iters : (diff > 0.0001 && iter < 1000)) {
         if (s_status != HGT_OK) break;
         if (compact_ok && (iter == 0 || (iter > 10 && a.remove_low))) {
@@ -528,15 +659,21 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
             if (cnt_live > 0 && cnt_live <= 64) {
                 // ---- build the compact problem ---------------------------------------------------------------
                 Compact c;
-                unsigned char *base = reinterpret_cast<unsigned char *>(sm.p);
+                unsigned char *base = compacted ? sm.c64 : reinterpret_cast<unsigned char *>(sm.p);
                 c.v = reinterpret_cast<double *>(base);
                 c.len = c.v + 256;
                 c.q = c.len + 64;
                 c.lv = reinterpret_cast<int *>(c.q + 64);
                 c.l = c.lv + 64;
-                c.cnt = reinterpret_cast<double *>(c.l + 192);
-                c.w = c.cnt + a.C;
-                c.cm = reinterpret_cast<uint64_t *>(c.w + a.C);
+                if (compacted) {
+                    c.cnt = sm.cnt;
+                    c.w = sm.w;
+                    c.cm = sm.cm64;
+                } else {
+                    c.cnt = reinterpret_cast<double *>(c.l + 192);
+                    c.w = c.cnt + a.C;
+                    c.cm = reinterpret_cast<uint64_t *>(c.w + a.C);
+                }
                 c.n = cnt_live;
                 __syncthreads();
                 if (tid < 32) {  // ordered list of key alleles
@@ -557,20 +694,20 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
                     c.v[64 + tid] = c.v[128 + tid] = c.v[192 + tid] = 0.0;
                     c.l[tid] = k ? 1 : 0;
                     c.l[64 + tid] = c.l[128 + tid] = 0;
-                    c.len[tid] = (k && a.len) ? a.len[al] : 1.0;
+                    c.len[tid] = (k && a.len) ? a.len[orig_allele(sm, al)] : 1.0;
                 }
                 // row masks straight from global memory: warp per class row, lane per compact allele
                 {
                     const int lane = tid & 31, warp = tid >> 5;
                     const int a_lo = lane < c.n ? c.lv[lane] : -1, a_hi = lane + 32 < c.n ? c.lv[lane + 32] : -1;
                     for (int r = warp; r < a.C; r += EM_WARPS) {
-                        const uint64_t *row = a.bits + (size_t)r * a.wp;
+                        const uint64_t *row = (compacted ? sm.slab : a.bits) + (size_t)r * a.wp;
                         const bool b_lo = a_lo >= 0 && ((row[a_lo >> 6] >> (a_lo & 63)) & 1ull);
                         const bool b_hi = a_hi >= 0 && ((row[a_hi >> 6] >> (a_hi & 63)) & 1ull);
                         const unsigned m_lo = __ballot_sync(0xffffffffu, b_lo), m_hi = __ballot_sync(0xffffffffu, b_hi);
                         if (lane == 0) {
                             c.cm[r] = (uint64_t)m_lo | ((uint64_t)m_hi << 32);
-                            c.cnt[r] = a.cnt_u64 ? (double)a.cnt_u64[r] : a.cnt[r];
+                            if (!compacted) c.cnt[r] = a.cnt_u64 ? (double)a.cnt_u64[r] : a.cnt[r];
                         }
                     }
                 }
@@ -600,7 +737,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
                     last_in = v3;
                     last_live = l2;
                 }
-                loaded = false;  // the slab buffer was overwritten
+                if (!compacted) loaded = false;  // the slab buffer was overwritten
                 break;
             }
         }
@@ -676,7 +813,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
         int nk = 0;
         for (int al = tid; al < a.A; al += EM_THREADS)
             if (l0[al]) {
-                part += a.len ? v0[al] / a.len[al] : v0[al];
+                part += a.len ? v0[al] / a.len[orig_allele(sm, al)] : v0[al];
                 nk = 1;
             }
         const double total = block_sum(part, sm.red);
@@ -688,8 +825,9 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
         if (writer) {
             for (int al = tid; al < a.A; al += EM_THREADS) {
                 const bool key = l0[al];
-                a.prob[al] = key ? (a.len ? v0[al] / a.len[al] / total : v0[al] / total) : 0.0;
-                a.in_result[al] = key ? 1 : 0;
+                const int ao = orig_allele(sm, al);
+                a.prob[ao] = key ? (a.len ? v0[al] / a.len[ao] / total : v0[al] / total) : 0.0;
+                a.in_result[ao] = key ? 1 : 0;
             }
         }
         // dict insertion order of the final Gene_prob = order in which the last next_prob() call met the
@@ -698,7 +836,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
             em_sweep<NA, COOP>(a, sm, MODE_FIRSTK, last_in, last_live, nullptr, nullptr, a.first_class, row_lo,
                                row_hi, resident, loaded, parity, &s_status);
         } else if (writer) {
-            for (int al = tid; al < a.A; al += EM_THREADS) a.first_class[al] = FK_NONE;
+            for (int al = tid; al < A_orig; al += EM_THREADS) a.first_class[al] = FK_NONE;
         }
     }
     if (tid == 0 && (!COOP || blockIdx.x == 0)) {
@@ -757,6 +895,66 @@ int em_launch(hgt_ctx *ctx, cudaStream_t st, const EmArgs *d_args, int grid, int
         HGT_CUDA(cudaGetLastError());
     }
     ctx->launches++;
+    return HGT_OK;
+}
+
+// Plan of one batched problem (one CTA): the allele-compacted shared-memory-resident layout when it fits, else the
+// streaming layout of em_plan().
+struct EmShape {
+    int C, A, wp, A_live_max;
+};
+int em_plan_batched(const hgt_ctx *ctx, const EmShape &sh, EmArgs *a, int *na, size_t *smem) {
+    const size_t budget = ctx->smem_optin > 1024 ? ctx->smem_optin - 1024 : 0;
+    int alive = sh.A_live_max < sh.A ? sh.A_live_max : sh.A;
+    if (alive < 1) alive = 1;
+    const int wpc = hgt_row_pitch(alive);
+    const size_t Apadc = (size_t)wpc * 64;
+    const size_t Cpad = sh.C < 2 ? 2 : (size_t)((sh.C + 1) & ~1);
+    const size_t need = 16 + 40 * 8 + 4096 + Apadc * 12 + Cpad * ((size_t)wpc * 8 + 25) + 16;
+    if (sh.wp <= 256 && need <= budget && Apadc <= (size_t)16 * EM_THREADS) {
+        a->compact = 1;
+        a->A_live_max = alive;
+        a->slab_rows = (int)Cpad;
+        int n = 1;
+        while ((size_t)n * EM_THREADS < Apadc) n *= 2;
+        *na = n;
+        *smem = need;
+        return HGT_OK;
+    }
+    EmPlan plan;
+    HGT_CHECK(em_plan(ctx, sh.C < 1 ? 1 : sh.C, sh.A, sh.wp, &plan));
+    a->compact = 0;
+    a->A_live_max = sh.A;
+    a->slab_rows = plan.slab_rows;
+    *na = plan.na;
+    *smem = plan.smem;
+    return HGT_OK;
+}
+
+// Launches n planned problems (one CTA each): grouped by register variant, heaviest problems first inside a group.
+// h_args (host, pinned or otherwise alive until the stream has passed the copy) and d_args hold n EmArgs.
+int em_launch_batched(hgt_ctx *ctx, cudaStream_t st, int n, const EmArgs *planned, const int *na, const size_t *smem,
+                      EmArgs *h_args, EmArgs *d_args) {
+    std::vector<int> order(n);
+    for (int i = 0; i < n; i++) order[i] = i;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+        if (na[x] != na[y]) return na[x] > na[y];
+        if (planned[x].compact != planned[y].compact) return planned[x].compact < planned[y].compact;
+        return (double)planned[x].C * planned[x].A_live_max > (double)planned[y].C * planned[y].A_live_max;
+    });
+    for (int i = 0; i < n; i++) h_args[i] = planned[order[i]];
+    HGT_CUDA(cudaMemcpyAsync(d_args, h_args, (size_t)n * sizeof(EmArgs), cudaMemcpyHostToDevice, st));
+    int i0 = 0;
+    while (i0 < n) {
+        int i1 = i0;
+        size_t sm = 0;
+        while (i1 < n && na[order[i1]] == na[order[i0]]) {
+            if (smem[order[i1]] > sm) sm = smem[order[i1]];
+            i1++;
+        }
+        HGT_CHECK(em_launch<false>(ctx, st, d_args + i0, i1 - i0, na[order[i0]], sm));
+        i0 = i1;
+    }
     return HGT_OK;
 }
 
@@ -827,16 +1025,25 @@ extern "C" int hgt_em_dev(hgt_ctx *ctx, void *stream, const uint64_t *class_bits
     if (G < 1) G = 1;
     const int rows_per_cta = (n_classes + G - 1) / G;
     EmPlan plan;
-    HGT_CHECK(em_plan(ctx, rows_per_cta, n_alleles, wp, &plan));
     EmWs w = em_ws_carve(workspace, ctx->sm_count, n_alleles);
     EmArgs a;
     a.bits = class_bits; a.cnt = class_count; a.len = allele_len;
     a.C = n_classes; a.A = n_alleles; a.wp = wp; a.remove_low = remove_low; a.fixed_iters = fixed_iters;
-    a.slab_rows = plan.slab_rows;
     a.cnt_u64 = nullptr; a.C_ptr = nullptr; a.class_first = nullptr;
     a.prob = prob; a.in_result = in_result; a.first_class = first_class; a.iters_status = iters_status;
     a.vec = w.vec; a.live = w.live; a.part_acc = w.part_acc; a.part_aux = w.part_aux;
     a.red_acc = w.red_acc; a.red_aux = w.red_aux;
+    if (G == 1) {
+        const EmShape sh{n_classes, n_alleles, wp, n_alleles};
+        int na = 1;
+        size_t smem = 0;
+        HGT_CHECK(em_plan_batched(ctx, sh, &a, &na, &smem));
+        plan.na = na; plan.smem = smem; plan.slab_rows = a.slab_rows;
+    } else {
+        HGT_CHECK(em_plan(ctx, rows_per_cta, n_alleles, wp, &plan));
+        a.compact = 0; a.A_live_max = n_alleles;
+        a.slab_rows = plan.slab_rows;
+    }
     HGT_CUDA(cudaMemcpyAsync(w.d_args, &a, sizeof(a), cudaMemcpyHostToDevice, st));
     if (G == 1) return em_launch<false>(ctx, st, w.d_args, 1, plan.na, plan.smem);
     return em_launch<true>(ctx, st, w.d_args, G, plan.na, plan.smem);
@@ -927,8 +1134,9 @@ extern "C" int hgt_em_batch(hgt_ctx *ctx, int32_t n_problems, const uint64_t *cl
     unsigned char *d = nullptr;
     HGT_CUDA(cudaMalloc(&d, total));
     int rc = HGT_OK;
-    int na = 1;
-    size_t smem = 0;
+    std::vector<int> nas(n_problems, 1);
+    std::vector<size_t> smems(n_problems, 0);
+    std::vector<EmArgs> h_args(n_problems);
     std::vector<int32_t> is((size_t)n_problems * 3, 0);
     for (int i = 0; i < n_problems && rc == HGT_OK; i++) {
         const int C = (int)(class_off[i + 1] - class_off[i]), A = (int)(allele_off[i + 1] - allele_off[i]);
@@ -937,18 +1145,14 @@ extern "C" int hgt_em_batch(hgt_ctx *ctx, int32_t n_problems, const uint64_t *cl
             rc = HGT_ERR_ARG;
             break;
         }
-        EmPlan plan;
-        rc = em_plan(ctx, C < 1 ? 1 : C, (int)Apad, wp, &plan);
-        if (rc != HGT_OK) break;
-        // a batched problem must be resident-or-streamed by ONE CTA; both work, plan.slab_rows caps the buffer
-        na = plan.na;
-        if (plan.smem > smem) smem = plan.smem;
         EmArgs &a = args[i];
+        const EmShape sh{C, A, wp, A};
+        rc = em_plan_batched(ctx, sh, &a, &nas[i], &smems[i]);
+        if (rc != HGT_OK) break;
         a.bits = reinterpret_cast<uint64_t *>(d + o_bits) + (size_t)class_off[i] * wp;
         a.cnt = reinterpret_cast<double *>(d + o_cnt) + class_off[i];
         a.len = allele_len ? reinterpret_cast<double *>(d + o_len) + allele_off[i] : nullptr;
         a.C = C; a.A = A; a.wp = wp; a.remove_low = remove_low ? remove_low[i] : 0; a.fixed_iters = 0;
-        a.slab_rows = plan.slab_rows;
         a.cnt_u64 = nullptr; a.C_ptr = nullptr; a.class_first = nullptr;
         a.prob = reinterpret_cast<double *>(d + o_prob) + allele_off[i];
         a.in_result = d + o_in + allele_off[i];
@@ -972,9 +1176,9 @@ extern "C" int hgt_em_batch(hgt_ctx *ctx, int32_t n_problems, const uint64_t *cl
         TRY(cudaMemcpyAsync(d + o_bits, class_bits, (size_t)Ctot * wp * 8, cudaMemcpyHostToDevice, st));
         TRY(cudaMemcpyAsync(d + o_cnt, cnt.data(), (size_t)Ctot * 8, cudaMemcpyHostToDevice, st));
         if (allele_len) TRY(cudaMemcpyAsync(d + o_len, allele_len, (size_t)Atot * 8, cudaMemcpyHostToDevice, st));
-        TRY(cudaMemcpyAsync(d + o_args, args.data(), (size_t)n_problems * sizeof(EmArgs), cudaMemcpyHostToDevice, st));
         TRY(cudaMemsetAsync(d + o_is, 0, (size_t)n_problems * 12, st));
-        rc = em_launch<false>(ctx, st, reinterpret_cast<EmArgs *>(d + o_args), n_problems, na, smem);
+        rc = em_launch_batched(ctx, st, n_problems, args.data(), nas.data(), smems.data(), h_args.data(),
+                               reinterpret_cast<EmArgs *>(d + o_args));
         if (rc != HGT_OK) break;
         TRY(cudaMemcpyAsync(prob, d + o_prob, (size_t)Atot * 8, cudaMemcpyDeviceToHost, st));
         TRY(cudaMemcpyAsync(in_result, d + o_in, (size_t)Atot, cudaMemcpyDeviceToHost, st));
@@ -995,40 +1199,31 @@ extern "C" int hgt_em_batch(hgt_ctx *ctx, int32_t n_problems, const uint64_t *cl
 // ---- internal: batched EM on device-resident class tables (used by typing.cu) ----------------------------------
 #include "em_internal.h"
 
-size_t hgt_em_batch_ws_bytes(int n_problems, int wp) {
+size_t hgt_em_problem_ws_bytes(int wp) {
     const size_t Apad = (size_t)wp * 64;
-    return align_up((size_t)n_problems * sizeof(EmArgs), 256) + (size_t)n_problems * 4 * Apad * 8 +
-           (size_t)n_problems * 4 * Apad;
+    return align_up(4 * Apad * 8 + 4 * Apad, 256);
 }
+size_t hgt_em_args_bytes(int n_problems) { return align_up((size_t)n_problems * sizeof(EmArgs), 256); }
 
-int hgt_em_batch_dev(hgt_ctx *ctx, cudaStream_t st, int n_problems, const EmDevProblem *pr, int wp, void *ws) {
+int hgt_em_batch_dev(hgt_ctx *ctx, cudaStream_t st, int n_problems, const EmDevProblem *pr, void *h_args, void *d_args) {
     if (n_problems <= 0) return HGT_OK;
-    const size_t Apad = (size_t)wp * 64;
     std::vector<EmArgs> args(n_problems);
-    unsigned char *d = static_cast<unsigned char *>(ws);
-    EmArgs *d_args = reinterpret_cast<EmArgs *>(d);
-    double *vec = reinterpret_cast<double *>(d + align_up((size_t)n_problems * sizeof(EmArgs), 256));
-    uint8_t *live = reinterpret_cast<uint8_t *>(vec + (size_t)n_problems * 4 * Apad);
-    int na = 1;
-    size_t smem = 0;
+    std::vector<int> nas(n_problems, 1);
+    std::vector<size_t> smems(n_problems, 0);
     for (int i = 0; i < n_problems; i++) {
-        EmPlan plan;
-        HGT_CHECK(em_plan(ctx, pr[i].C_max < 1 ? 1 : pr[i].C_max, (int)Apad, wp, &plan));
-        na = plan.na;
-        if (plan.smem > smem) smem = plan.smem;
         EmArgs &a = args[i];
+        const size_t Apad = (size_t)pr[i].wp * 64;
+        const EmShape sh{pr[i].C_max < 1 ? 1 : pr[i].C_max, pr[i].A, pr[i].wp, pr[i].A_live_max};
+        HGT_CHECK(em_plan_batched(ctx, sh, &a, &nas[i], &smems[i]));
         a.bits = pr[i].bits; a.cnt = nullptr; a.len = pr[i].len;
-        a.C = pr[i].C_max; a.A = pr[i].A; a.wp = wp; a.remove_low = pr[i].remove_low; a.fixed_iters = 0;
-        a.slab_rows = plan.slab_rows;
+        a.C = pr[i].C_max; a.A = pr[i].A; a.wp = pr[i].wp; a.remove_low = pr[i].remove_low; a.fixed_iters = 0;
         a.cnt_u64 = pr[i].cnt; a.C_ptr = pr[i].C_ptr; a.class_first = pr[i].class_first;
         a.prob = pr[i].prob; a.in_result = pr[i].in_result; a.first_class = pr[i].first_class;
         a.iters_status = pr[i].iters_status;
-        a.vec = vec + (size_t)i * 4 * Apad;
-        a.live = live + (size_t)i * 4 * Apad;
+        a.vec = static_cast<double *>(pr[i].ws);
+        a.live = reinterpret_cast<uint8_t *>(a.vec + 4 * Apad);
         a.part_acc = nullptr; a.part_aux = nullptr; a.red_acc = nullptr; a.red_aux = nullptr;
     }
-    // the argument block must outlive the async copy: stage it in pinned memory owned by the context
-    HGT_CUDA(cudaMemcpyAsync(d_args, args.data(), (size_t)n_problems * sizeof(EmArgs), cudaMemcpyHostToDevice, st));
-    HGT_CUDA(cudaStreamSynchronize(st));
-    return em_launch<false>(ctx, st, d_args, n_problems, na, smem);
+    return em_launch_batched(ctx, st, n_problems, args.data(), nas.data(), smems.data(), static_cast<EmArgs *>(h_args),
+                             static_cast<EmArgs *>(d_args));
 }

@@ -9,15 +9,22 @@ struct EmDevProblem {
     const uint64_t *bits;            // [C_max][wp] class rows (contiguous region of a class pool)
     const unsigned long long *cnt;   // [C_max] class counts
     const int32_t *class_first;      // [C_max] first pair index of each class (tie-break key)
-    const int32_t *C_ptr;            // device counter: number of classes actually present
-    int C_max, A;
+    const int32_t *C_ptr;            // device counter: number of classes actually present (<= C_max)
+    int C_max, A, wp;
+    int A_live_max;                  // upper bound of alleles that can be members of a class (table / keep mask size)
     const double *len;               // [A] or null
     int remove_low;
     double *prob;                    // [A]
     uint8_t *in_result;              // [A]
     int32_t *first_class;            // [A]
     int32_t *iters_status;           // [3]
+    void *ws;                        // hgt_em_problem_ws_bytes(wp) bytes of device scratch
 };
 
-size_t hgt_em_batch_ws_bytes(int n_problems, int wp);
-int hgt_em_batch_dev(hgt_ctx *ctx, cudaStream_t st, int n_problems, const EmDevProblem *problems, int wp, void *ws);
+size_t hgt_em_problem_ws_bytes(int wp);
+size_t hgt_em_args_bytes(int n_problems);
+// One CTA per problem, all problems of all loci in as few launches as the register variants need.  h_args: host
+// staging (pinned) and d_args: device copy, hgt_em_args_bytes(n_problems) each; h_args must stay untouched until the
+// stream has passed this call.
+int hgt_em_batch_dev(hgt_ctx *ctx, cudaStream_t st, int n_problems, const EmDevProblem *problems, void *h_args,
+                     void *d_args);

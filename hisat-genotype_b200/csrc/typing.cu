@@ -897,6 +897,30 @@ struct DevBuf {
     T *as() const { return static_cast<T *>(p); }
 };
 
+struct PinBuf {  // page-locked host memory: asynchronous D2H targets and kernel-argument staging
+    void *p = nullptr;
+    size_t bytes = 0;
+    int alloc(size_t n) {
+        if (p && bytes >= n) return HGT_OK;
+        release();
+        cudaError_t e = cudaMallocHost(&p, n ? n : 16);
+        if (e != cudaSuccess) {
+            hgt_set_error("cudaMallocHost(%zu) -> %s", n, cudaGetErrorString(e));
+            p = nullptr;
+            return HGT_ERR_NOMEM;
+        }
+        bytes = n;
+        return HGT_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        bytes = 0;
+    }
+    template <class T>
+    T *as() const { return static_cast<T *>(p); }
+};
+
 static thread_local hgt_ctx *g_acct = nullptr;  // context whose byte counters the copies below feed
 
 template <class T>
@@ -981,20 +1005,26 @@ struct LocusBatch {
     DevBuf d_job_off, d_job_ut, d_job_pair, d_job_list, d_hl, d_hr, d_ht, d_ro, d_rows, d_hapbits;
     DevBuf d_keys, d_slot, d_bits, d_count, d_first, d_ut_base, d_ut_ncls;
     DevBuf d_prob, d_inres, d_fk, d_is, d_emws, d_len;      // EM over exon (hla) / gene (other) tables
-    DevBuf d_prob2, d_inres2, d_fk2, d_is2, d_emws2, d_keep, d_ulist;  // second-level EM (hla)
+    DevBuf d_prob2, d_inres2, d_fk2, d_is2, d_keep, d_ulist;  // second-level EM (hla)
     DevBuf d_acount, d_afirst;
     uint32_t cap = 0;
-    std::vector<int32_t> ut_ncls;  // host copy after finish
-    std::vector<double> prob, prob2;
-    std::vector<uint8_t> inres, inres2;
-    std::vector<int32_t> fk, fk2, is, is2;
+    int n_live[4] = {0, 0, 0, 0};  // alleles that can be members of a class of table t (popcount of its mask)
+    // results on the host (page-locked)
+    PinBuf h_ncls, h_prob, h_inres, h_fk, h_is, h_prob2, h_inres2, h_fk2, h_is2, h_keep, h_ulist;
+    int32_t *ut_ncls = nullptr;
+    double *prob = nullptr, *prob2 = nullptr;
+    uint8_t *inres = nullptr, *inres2 = nullptr;
+    int32_t *fk = nullptr, *fk2 = nullptr, *is = nullptr, *is2 = nullptr;
     std::vector<uint8_t> has2;  // unit ran the second-level EM
+    int n_level2 = 0;
     void release() {
         DevBuf *all[] = {&d_job_off, &d_job_ut, &d_job_pair, &d_job_list, &d_hl, &d_hr, &d_ht, &d_ro, &d_rows, &d_hapbits,
                          &d_keys, &d_slot, &d_bits, &d_count, &d_first, &d_ut_base, &d_ut_ncls, &d_prob, &d_inres, &d_fk,
-                         &d_is, &d_emws, &d_len, &d_prob2, &d_inres2, &d_fk2, &d_is2, &d_emws2, &d_keep, &d_ulist,
+                         &d_is, &d_emws, &d_len, &d_prob2, &d_inres2, &d_fk2, &d_is2, &d_keep, &d_ulist,
                          &d_acount, &d_afirst};
         for (DevBuf *b : all) b->release();
+        PinBuf *pins[] = {&h_ncls, &h_prob, &h_inres, &h_fk, &h_is, &h_prob2, &h_inres2, &h_fk2, &h_is2, &h_keep, &h_ulist};
+        for (PinBuf *b : pins) b->release();
     }
     ClassPool pool() const {
         ClassPool p;
@@ -1015,10 +1045,15 @@ struct hgt_batch {
     bool prepared = false, executed = false, finished = false;
     StageTimer timer;
     int remove_low = 1;
-    std::vector<double> allele_len_host;  // unused placeholder
+    PinBuf h_em_args[2];   // kernel-argument staging of the two EM levels
+    DevBuf d_em_args[2];
     ~hgt_batch() {
         if (ctx) cudaSetDevice(ctx->device);
         for (LocusBatch &b : lb) b.release();
+        for (int i = 0; i < 2; i++) {
+            h_em_args[i].release();
+            d_em_args[i].release();
+        }
     }
 };
 
@@ -1237,16 +1272,51 @@ static int batch_prepare(hgt_batch *b) {
         HGT_CHECK(lb.d_count.alloc(pr * 8));
         HGT_CHECK(lb.d_first.alloc(pr * 4));
         HGT_CHECK(lb.d_ut_ncls.alloc(n_units * 4 * 4));
-        // EM buffers
+        // EM buffers (both levels; nothing is allocated after prepare)
         const size_t A = (size_t)loc->A;
         HGT_CHECK(lb.d_prob.alloc(n_units * A * 8));
         HGT_CHECK(lb.d_inres.alloc(n_units * A));
         HGT_CHECK(lb.d_fk.alloc(n_units * A * 4));
         HGT_CHECK(lb.d_is.alloc(n_units * 12));
-        HGT_CHECK(lb.d_emws.alloc(hgt_em_batch_ws_bytes((int)n_units, wp)));
+        HGT_CHECK(lb.d_emws.alloc(n_units * hgt_em_problem_ws_bytes(wp)));
         HGT_CHECK(lb.d_acount.alloc(n_units * A * 8));
         HGT_CHECK(lb.d_afirst.alloc(n_units * A * 4));
+        HGT_CHECK(lb.h_ncls.alloc(n_units * 16));
+        HGT_CHECK(lb.h_prob.alloc(n_units * A * 8));
+        HGT_CHECK(lb.h_inres.alloc(n_units * A));
+        HGT_CHECK(lb.h_fk.alloc(n_units * A * 4));
+        HGT_CHECK(lb.h_is.alloc(n_units * 12));
+        lb.ut_ncls = lb.h_ncls.as<int32_t>(); lb.prob = lb.h_prob.as<double>(); lb.inres = lb.h_inres.as<uint8_t>();
+        lb.fk = lb.h_fk.as<int32_t>(); lb.is = lb.h_is.as<int32_t>();
+        memset(lb.ut_ncls, 0, n_units * 16);
+        for (int tb = 0; tb < 3; tb++) {
+            int n = 0;
+            for (int j = 0; j < wp; j++) n += __builtin_popcountll(loc->mask[(size_t)tb * wp + j]);
+            lb.n_live[tb] = n;
+        }
+        lb.n_live[3] = loc->A;
+        if (loc->is_hla) {
+            HGT_CHECK(lb.d_prob2.alloc(n_units * A * 8));
+            HGT_CHECK(lb.d_inres2.alloc(n_units * A));
+            HGT_CHECK(lb.d_fk2.alloc(n_units * A * 4));
+            HGT_CHECK(lb.d_is2.alloc(n_units * 12));
+            HGT_CHECK(lb.d_keep.alloc(n_units * (size_t)wp * 8));
+            HGT_CHECK(lb.d_ulist.alloc(n_units * 4));
+            HGT_CHECK(upload(&lb.d_len, loc->allele_len, st));
+            HGT_CHECK(lb.h_prob2.alloc(n_units * A * 8));
+            HGT_CHECK(lb.h_inres2.alloc(n_units * A));
+            HGT_CHECK(lb.h_fk2.alloc(n_units * A * 4));
+            HGT_CHECK(lb.h_is2.alloc(n_units * 12));
+            HGT_CHECK(lb.h_keep.alloc(n_units * (size_t)wp * 8));
+            HGT_CHECK(lb.h_ulist.alloc(n_units * 4));
+            lb.prob2 = lb.h_prob2.as<double>(); lb.inres2 = lb.h_inres2.as<uint8_t>();
+            lb.fk2 = lb.h_fk2.as<int32_t>(); lb.is2 = lb.h_is2.as<int32_t>();
+        }
         (void)n_jobs;
+    }
+    for (int i = 0; i < 2; i++) {
+        HGT_CHECK(b->h_em_args[i].alloc(hgt_em_args_bytes((int)nu)));
+        HGT_CHECK(b->d_em_args[i].alloc(hgt_em_args_bytes((int)nu)));
     }
     HGT_CUDA(cudaStreamSynchronize(st));
     b->prepared = true;
@@ -1292,29 +1362,34 @@ static void launch_stage_a(hgt_batch *b, cudaStream_t st, LocusBatch &lb) {
     b->timer.end((ns > 0) + (nb > 0));
 }
 
-static int em_on_table(hgt_ctx *ctx, cudaStream_t st, LocusBatch &lb, int table, const std::vector<int> &local_units,
-                       const double *d_len, int remove_low, DevBuf &prob, DevBuf &inres, DevBuf &fk, DevBuf &is, DevBuf &ws) {
+// EM problems of one locus batch on table `table` for the listed local units, appended to `out`.
+static void em_problems(LocusBatch &lb, int table, const std::vector<int> &local_units, const int *c_max,
+                        const int *a_live, const double *d_len, int remove_low, DevBuf &prob, DevBuf &inres, DevBuf &fk,
+                        DevBuf &is, std::vector<EmDevProblem> *out) {
     const hgt_locus *loc = lb.loc;
     const size_t A = (size_t)loc->A;
-    std::vector<EmDevProblem> pr(local_units.size());
+    const size_t wsb = hgt_em_problem_ws_bytes(loc->wp);
     for (size_t k = 0; k < local_units.size(); k++) {
         const int i = local_units[k];
         const int ut = i * 4 + table;
-        EmDevProblem &p = pr[k];
+        EmDevProblem p;
         p.bits = lb.d_bits.as<uint64_t>() + (size_t)lb.ut_base[ut] * loc->wp;
         p.cnt = lb.d_count.as<unsigned long long>() + lb.ut_base[ut];
         p.class_first = lb.d_first.as<int32_t>() + lb.ut_base[ut];
         p.C_ptr = lb.d_ut_ncls.as<int32_t>() + ut;
-        p.C_max = (int)(lb.ut_base[ut + 1] - lb.ut_base[ut]);
+        p.C_max = std::min<int>(c_max[k], (int)(lb.ut_base[ut + 1] - lb.ut_base[ut]));
         p.A = loc->A;
+        p.wp = loc->wp;
+        p.A_live_max = a_live[k];
         p.len = d_len;
         p.remove_low = remove_low;
         p.prob = prob.as<double>() + (size_t)i * A;
         p.in_result = inres.as<uint8_t>() + (size_t)i * A;
         p.first_class = fk.as<int32_t>() + (size_t)i * A;
         p.iters_status = is.as<int32_t>() + (size_t)i * 3;
+        p.ws = static_cast<unsigned char *>(lb.d_emws.p) + (size_t)i * wsb;
+        out->push_back(p);
     }
-    return hgt_em_batch_dev(ctx, st, (int)pr.size(), pr.data(), loc->wp, ws.p);
 }
 
 static int batch_execute(hgt_batch *b, cudaStream_t st) {
@@ -1347,14 +1422,30 @@ static int batch_execute(hgt_batch *b, cudaStream_t st) {
             b->timer.end(1);
             HGT_CUDA(cudaGetLastError());
         }
-        // first-level EM: exon table on the hla path (core:1732-1737), Gene table otherwise (core:1789)
-        std::vector<int> all(n_units);
-        std::iota(all.begin(), all.end(), 0);
-        b->timer.begin(ctx, st, 4);
-        HGT_CHECK(em_on_table(ctx, st, lb, loc->is_hla ? 1 : 0, all, nullptr, loc->is_hla ? b->remove_low : 0, lb.d_prob,
-                              lb.d_inres, lb.d_fk, lb.d_is, lb.d_emws));
-        b->timer.end(1);
+        HGT_CUDA(d2h(lb.ut_ncls, lb.d_ut_ncls.p, n_units * 16, st));
     }
+    // class counts of every (unit, table) are now known: the one host synchronisation of the GPU stage, it lets the
+    // EM launch size each problem's shared memory exactly
+    HGT_CUDA(cudaStreamSynchronize(st));
+    // first-level EM of every unit of every locus in one go: exon table on the hla path (core:1732-1737), Gene table
+    // otherwise (core:1789)
+    std::vector<EmDevProblem> probs;
+    std::vector<int> all, cmax, alive;
+    for (LocusBatch &lb : b->lb) {
+        if (lb.units.empty()) continue;
+        const hgt_locus *loc = lb.loc;
+        const size_t n_units = lb.units.size();
+        const int table = loc->is_hla ? 1 : 0;
+        all.resize(n_units); cmax.resize(n_units); alive.assign(n_units, lb.n_live[table]);
+        std::iota(all.begin(), all.end(), 0);
+        for (size_t i = 0; i < n_units; i++) cmax[i] = lb.ut_ncls[i * 4 + table];
+        em_problems(lb, table, all, cmax.data(), alive.data(), nullptr, loc->is_hla ? b->remove_low : 0, lb.d_prob, lb.d_inres,
+                    lb.d_fk, lb.d_is, &probs);
+    }
+    b->timer.begin(ctx, st, 4);
+    const int64_t l0 = ctx->launches;
+    HGT_CHECK(hgt_em_batch_dev(ctx, st, (int)probs.size(), probs.data(), b->h_em_args[0].p, b->d_em_args[0].p));
+    b->timer.end((int)(ctx->launches - l0));
     b->executed = true;
     return HGT_OK;
 }
@@ -1366,27 +1457,25 @@ static int batch_finish(hgt_batch *b, cudaStream_t st) {
         if (lb.units.empty()) continue;
         const hgt_locus *loc = lb.loc;
         const size_t n_units = lb.units.size(), A = (size_t)loc->A;
-        const int wp = loc->wp;
-        lb.ut_ncls.resize(n_units * 4);
-        lb.prob.resize(n_units * A); lb.inres.resize(n_units * A); lb.fk.resize(n_units * A); lb.is.resize(n_units * 3);
-        HGT_CUDA(d2h(lb.ut_ncls.data(), lb.d_ut_ncls.p, n_units * 16, st));
-        HGT_CUDA(d2h(lb.prob.data(), lb.d_prob.p, n_units * A * 8, st));
-        HGT_CUDA(d2h(lb.inres.data(), lb.d_inres.p, n_units * A, st));
-        HGT_CUDA(d2h(lb.fk.data(), lb.d_fk.p, n_units * A * 4, st));
-        HGT_CUDA(d2h(lb.is.data(), lb.d_is.p, n_units * 12, st));
+        HGT_CUDA(d2h(lb.prob, lb.d_prob.p, n_units * A * 8, st));
+        HGT_CUDA(d2h(lb.inres, lb.d_inres.p, n_units * A, st));
+        HGT_CUDA(d2h(lb.fk, lb.d_fk.p, n_units * A * 4, st));
+        HGT_CUDA(d2h(lb.is, lb.d_is.p, n_units * 12, st));
     }
     HGT_CUDA(cudaStreamSynchronize(st));
     b->timer.resolve();
+    std::vector<EmDevProblem> probs;
     for (LocusBatch &lb : b->lb) {
+        lb.n_level2 = 0;
         if (lb.units.empty() || !lb.loc->is_hla) continue;
         const hgt_locus *loc = lb.loc;
         const size_t n_units = lb.units.size(), A = (size_t)loc->A;
         const int wp = loc->wp;
         // choose exon_alleles per unit (core:1739-1749) from the ranked exon EM result
-        std::vector<int32_t> ulist;
-        std::vector<uint64_t> keep;
+        int32_t *ulist = lb.h_ulist.as<int32_t>();
+        uint64_t *keep = lb.h_keep.as<uint64_t>();
         lb.has2.assign(n_units, 0);
-        std::vector<int> order;
+        std::vector<int> order, lu, cmax, alive;
         for (size_t i = 0; i < n_units; i++) {
             if (lb.is[i * 3 + 1] != HGT_OK) continue;
             const double *p = &lb.prob[i * A];
@@ -1400,7 +1489,8 @@ static int batch_finish(hgt_batch *b, cudaStream_t st) {
                 if (fk[x] != fk[y]) return fk[x] < fk[y];
                 return x < y;
             });
-            std::vector<uint64_t> m(wp, 0);
+            uint64_t *m = keep + (size_t)lb.n_level2 * wp;
+            memset(m, 0, (size_t)wp * 8);
             bool any = false;
             for (size_t r = 0; r < order.size(); r++) {
                 const int a = order[r];
@@ -1414,49 +1504,53 @@ static int batch_finish(hgt_batch *b, cudaStream_t st) {
             }
             if (!any) continue;
             lb.has2[i] = 1;
-            ulist.push_back((int32_t)i);
-            keep.insert(keep.end(), m.begin(), m.end());
+            ulist[lb.n_level2++] = (int32_t)i;
+            lu.push_back((int)i);
+            cmax.push_back(lb.ut_ncls[i * 4 + 0]);  // a projection never has more classes than its source
+            int n = 0;
+            for (int j = 0; j < wp; j++) n += __builtin_popcountll(m[j]);
+            alive.push_back(n);
         }
-        if (ulist.empty()) continue;
-        HGT_CHECK(upload(&lb.d_ulist, ulist, st));
-        HGT_CHECK(upload(&lb.d_keep, keep, st));
-        if (!lb.d_len.p) {
-            HGT_CHECK(upload(&lb.d_len, loc->allele_len, st));
-        }
+        if (lb.n_level2 == 0) continue;
+        const size_t n2 = (size_t)lb.n_level2;
+        if (g_acct) g_acct->h2d_bytes += (int64_t)(n2 * 4 + n2 * wp * 8);
+        HGT_CUDA(cudaMemcpyAsync(lb.d_ulist.p, ulist, n2 * 4, cudaMemcpyHostToDevice, st));
+        HGT_CUDA(cudaMemcpyAsync(lb.d_keep.p, keep, n2 * wp * 8, cudaMemcpyHostToDevice, st));
         {
             b->timer.begin(ctx, st, 5);
-            dim3 grid(8, (unsigned)std::min<size_t>(ulist.size(), 16384));
+            dim3 grid(8, (unsigned)std::min<size_t>(n2, 16384));
             const ClassPool pool = lb.pool();
             switch (wpl_of(wp)) {
-                case 1: project_kernel<1><<<grid, WARPS_PER_CTA * 32, 0, st>>>(wp, (int)ulist.size(), lb.d_ulist.as<int32_t>(), lb.d_keep.as<uint64_t>(), pool); break;
-                case 2: project_kernel<2><<<grid, WARPS_PER_CTA * 32, 0, st>>>(wp, (int)ulist.size(), lb.d_ulist.as<int32_t>(), lb.d_keep.as<uint64_t>(), pool); break;
-                case 4: project_kernel<4><<<grid, WARPS_PER_CTA * 32, 0, st>>>(wp, (int)ulist.size(), lb.d_ulist.as<int32_t>(), lb.d_keep.as<uint64_t>(), pool); break;
-                default: project_kernel<8><<<grid, WARPS_PER_CTA * 32, 0, st>>>(wp, (int)ulist.size(), lb.d_ulist.as<int32_t>(), lb.d_keep.as<uint64_t>(), pool); break;
+                case 1: project_kernel<1><<<grid, WARPS_PER_CTA * 32, 0, st>>>(wp, (int)n2, lb.d_ulist.as<int32_t>(), lb.d_keep.as<uint64_t>(), pool); break;
+                case 2: project_kernel<2><<<grid, WARPS_PER_CTA * 32, 0, st>>>(wp, (int)n2, lb.d_ulist.as<int32_t>(), lb.d_keep.as<uint64_t>(), pool); break;
+                case 4: project_kernel<4><<<grid, WARPS_PER_CTA * 32, 0, st>>>(wp, (int)n2, lb.d_ulist.as<int32_t>(), lb.d_keep.as<uint64_t>(), pool); break;
+                default: project_kernel<8><<<grid, WARPS_PER_CTA * 32, 0, st>>>(wp, (int)n2, lb.d_ulist.as<int32_t>(), lb.d_keep.as<uint64_t>(), pool); break;
             }
             ctx->launches++;
             b->timer.end(1);
             HGT_CUDA(cudaGetLastError());
         }
-        HGT_CHECK(lb.d_prob2.alloc(n_units * A * 8));
-        HGT_CHECK(lb.d_inres2.alloc(n_units * A));
-        HGT_CHECK(lb.d_fk2.alloc(n_units * A * 4));
-        HGT_CHECK(lb.d_is2.alloc(n_units * 12));
         HGT_CUDA(cudaMemsetAsync(lb.d_is2.p, 0, n_units * 12, st));
-        HGT_CHECK(lb.d_emws2.alloc(hgt_em_batch_ws_bytes((int)ulist.size(), wp)));
-        std::vector<int> lu(ulist.begin(), ulist.end());
-        b->timer.begin(ctx, st, 6);
-        HGT_CHECK(em_on_table(ctx, st, lb, 3, lu, lb.d_len.as<double>(), 1, lb.d_prob2, lb.d_inres2, lb.d_fk2, lb.d_is2,
-                              lb.d_emws2));
-        b->timer.end(1);
-        lb.prob2.resize(n_units * A); lb.inres2.resize(n_units * A); lb.fk2.resize(n_units * A); lb.is2.resize(n_units * 3);
-        HGT_CUDA(d2h(lb.prob2.data(), lb.d_prob2.p, n_units * A * 8, st));
-        HGT_CUDA(d2h(lb.inres2.data(), lb.d_inres2.p, n_units * A, st));
-        HGT_CUDA(d2h(lb.fk2.data(), lb.d_fk2.p, n_units * A * 4, st));
-        HGT_CUDA(d2h(lb.is2.data(), lb.d_is2.p, n_units * 12, st));
-        HGT_CUDA(d2h(lb.ut_ncls.data(), lb.d_ut_ncls.p, n_units * 16, st));
+        em_problems(lb, 3, lu, cmax.data(), alive.data(), lb.d_len.as<double>(), 1, lb.d_prob2, lb.d_inres2, lb.d_fk2, lb.d_is2,
+                    &probs);
     }
-    HGT_CUDA(cudaStreamSynchronize(st));
-    b->timer.resolve();
+    if (!probs.empty()) {
+        b->timer.begin(ctx, st, 6);
+        const int64_t l0 = ctx->launches;
+        HGT_CHECK(hgt_em_batch_dev(ctx, st, (int)probs.size(), probs.data(), b->h_em_args[1].p, b->d_em_args[1].p));
+        b->timer.end((int)(ctx->launches - l0));
+        for (LocusBatch &lb : b->lb) {
+            if (lb.n_level2 == 0) continue;
+            const size_t n_units = lb.units.size(), A = (size_t)lb.loc->A;
+            HGT_CUDA(d2h(lb.prob2, lb.d_prob2.p, n_units * A * 8, st));
+            HGT_CUDA(d2h(lb.inres2, lb.d_inres2.p, n_units * A, st));
+            HGT_CUDA(d2h(lb.fk2, lb.d_fk2.p, n_units * A * 4, st));
+            HGT_CUDA(d2h(lb.is2, lb.d_is2.p, n_units * 12, st));
+            HGT_CUDA(d2h(lb.ut_ncls, lb.d_ut_ncls.p, n_units * 16, st));
+        }
+        HGT_CUDA(cudaStreamSynchronize(st));
+        b->timer.resolve();
+    }
     b->finished = true;
     return HGT_OK;
 }
