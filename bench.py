@@ -327,24 +327,39 @@ def main():
     L.hgt_profile_reset(ctx)
     e2e_ms = []
     n_e2e = max(2, min(args.steps, 3))
+    wall = {"add_units": 0.0, "prepare": 0.0, "execute": 0.0, "finish": 0.0, "results": 0.0}
     for k in range(1 + n_e2e):
         barrier()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         if k == 1:
             L.hgt_profile_reset(ctx)
+            wall = {n: 0.0 for n in wall}
         a.record()
+        t0 = time.perf_counter()
         bt = TC.Batch(tables, params, True, device=local)
         for li, text in units:
             bt.add_unit(li, text)
+        t1 = time.perf_counter()
         bt.prepare()
+        t2 = time.perf_counter()
         bt.execute(stream)
+        t3 = time.perf_counter()
         bt.finish(stream)
-        calls = [bt.unit_abundance(u)[:2] for u in range(len(units))]
+        t4 = time.perf_counter()
+        calls = bt.top_calls(2)
+        t5 = time.perf_counter()
         b.record()
         torch.cuda.synchronize()
+        for n, dt in zip(("add_units", "prepare", "execute", "finish", "results"), (t1 - t0, t2 - t1, t3 - t2, t4 - t3, t5 - t4)):
+            wall[n] += dt * 1000.0
         if k >= 1:
             e2e_ms.append(a.elapsed_time(b))
         bt.close()
+    host_ms = ctypes_array(8, "d")
+    L.hgt_profile_host(ctx, host_ms)
+    e2e_host = {n: host_ms[i] / n_e2e for i, n in enumerate(
+        ["intake", "pileup_pack", "pileup_gpu", "walk", "job_pack", "upload_alloc", "finish_host_and_em2"])}
+    e2e_wall = {n: v / n_e2e for n, v in wall.items()}
     L.hgt_profile_read(ctx, stage_ms, stage_n, ctypes.byref(h2d), ctypes.byref(d2h))
     e2e_vec = torch.tensor([sum(e2e_ms) / len(e2e_ms)], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -376,7 +391,8 @@ def main():
                             "kernel_ms_per_step": em_ms, "kernel": "em_kernel (batched, one CTA per unit)"},
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d.value / n_e2e,
                     "d2h_bytes_per_step": d2h.value / n_e2e, "ms_per_step": float(e2e_vec[0]),
-                    "input": "host alignment text, %d bytes per step on rank 0" % sum(len(t) for _, t in units)},
+                    "input": "host alignment text, %d bytes per step on rank 0" % sum(len(t) for _, t in units),
+                    "wall_ms_rank0": e2e_wall, "host_stage_ms_rank0": e2e_host, "host_threads": os.cpu_count()},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "example_call": calls[0],

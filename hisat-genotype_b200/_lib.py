@@ -65,6 +65,8 @@ def lib():
         L.hgt_profile_reset.argtypes = [c_void_p]
         L.hgt_profile_read.restype = None
         L.hgt_profile_read.argtypes = [c_void_p, c_void_p, c_void_p, P(c_i64), P(c_i64)]
+        L.hgt_profile_host.restype = None
+        L.hgt_profile_host.argtypes = [c_void_p, c_void_p]
         _lib = L
     return _lib
 

@@ -12,6 +12,44 @@ void hgt_set_error(const char *fmt, ...) {
     va_end(ap);
 }
 
+int MemPool::get(bool pinned, size_t n, void **out, size_t *cap) {
+    const size_t want = round_up(n);
+    std::multimap<size_t, void *> &fl = pinned ? free_pin : free_dev;
+    auto it = fl.lower_bound(want);
+    if (it != fl.end() && it->first <= want + want / 2) {
+        *out = it->second;
+        *cap = it->first;
+        (pinned ? held_pin : held_dev) -= it->first;
+        fl.erase(it);
+        return HGT_OK;
+    }
+    cudaError_t e = pinned ? cudaMallocHost(out, want) : cudaMalloc(out, want);
+    if (e != cudaSuccess) {  // give cached blocks back to the driver and retry once
+        cudaGetLastError();
+        drain();
+        e = pinned ? cudaMallocHost(out, want) : cudaMalloc(out, want);
+    }
+    if (e != cudaSuccess) {
+        hgt_set_error("%s(%zu) -> %s", pinned ? "cudaMallocHost" : "cudaMalloc", want, cudaGetErrorString(e));
+        *out = nullptr;
+        return HGT_ERR_NOMEM;
+    }
+    *cap = want;
+    return HGT_OK;
+}
+void MemPool::put(bool pinned, void *p, size_t cap) {
+    if (!p) return;
+    (pinned ? free_pin : free_dev).emplace(cap, p);
+    (pinned ? held_pin : held_dev) += cap;
+}
+void MemPool::drain() {
+    for (auto &kv : free_dev) cudaFree(kv.second);
+    for (auto &kv : free_pin) cudaFreeHost(kv.second);
+    free_dev.clear();
+    free_pin.clear();
+    held_dev = held_pin = 0;
+}
+
 extern "C" const char *hgt_last_error(void) { return g_err; }
 extern "C" int hgt_abi_version(void) { return 1; }
 extern "C" int hgt_row_pitch(int n_alleles) {
@@ -57,6 +95,7 @@ extern "C" int hgt_init(int device, hgt_ctx **out) {
 extern "C" void hgt_free(hgt_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
+    ctx->pool.drain();
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -73,6 +112,7 @@ extern "C" void hgt_profile_reset(hgt_ctx *ctx) {
     for (int i = 0; i < 8; i++) {
         ctx->stage_ms[i] = 0;
         ctx->stage_launches[i] = 0;
+        ctx->host_ms[i] = 0;
     }
 }
 extern "C" void hgt_profile_read(const hgt_ctx *ctx, double *stage_ms, int64_t *stage_launches, int64_t *h2d_bytes,
@@ -84,4 +124,8 @@ extern "C" void hgt_profile_read(const hgt_ctx *ctx, double *stage_ms, int64_t *
     }
     if (h2d_bytes) *h2d_bytes = ctx->h2d_bytes;
     if (d2h_bytes) *d2h_bytes = ctx->d2h_bytes;
+}
+extern "C" void hgt_profile_host(const hgt_ctx *ctx, double *host_ms) {
+    if (!ctx || !host_ms) return;
+    for (int i = 0; i < 8; i++) host_ms[i] = ctx->host_ms[i];
 }

@@ -3,9 +3,27 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <map>
 #include <string>
 
 #include "../../include/hgt.h"
+
+// Caching allocator of a context: device (cudaMalloc) and page-locked host (cudaMallocHost) blocks are kept on free
+// lists when released and handed out again to later batches, so the steady state of a typing service does no
+// driver allocation at all (cudaMalloc / cudaMallocHost / cudaFree cost 0.1-10 ms each and synchronise the device).
+struct MemPool {
+    std::multimap<size_t, void *> free_dev, free_pin;
+    size_t held_dev = 0, held_pin = 0;
+    static size_t round_up(size_t n) {
+        if (n < 4096) return 4096;
+        size_t g = 4096;
+        while (g * 16 < n) g <<= 1;  // granularity = 1/16 .. 1/8 of the size: <= 12.5 % slack
+        return (n + g - 1) / g * g;
+    }
+    int get(bool pinned, size_t n, void **out, size_t *cap);
+    void put(bool pinned, void *p, size_t cap);
+    void drain();
+};
 
 struct hgt_ctx {
     int device = 0;
@@ -14,13 +32,26 @@ struct hgt_ctx {
     int64_t launches = 0;
     cudaStream_t stream = nullptr;  // stream used by the host-pointer entry points
     // accounting read by bench.py through hgt_profile_read()
+    MemPool pool;
     int64_t h2d_bytes = 0, d2h_bytes = 0;
     int profile = 0;
     double stage_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // pileup, compat, class, counts, em1, project, em2, -
     int64_t stage_launches[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double host_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // intake, pileup prep, pileup GPU+wait, walk, pack, upload, finish host, -
 };
 
 void hgt_set_error(const char *fmt, ...);
+
+#include <chrono>
+struct HostTimer {  // wall-clock bracket of one host stage, accumulated into ctx->host_ms (bench.py reads it)
+    hgt_ctx *ctx;
+    int k;
+    std::chrono::steady_clock::time_point t0;
+    HostTimer(hgt_ctx *c, int stage) : ctx(c), k(stage), t0(std::chrono::steady_clock::now()) {}
+    ~HostTimer() {
+        if (ctx) ctx->host_ms[k] += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+};
 
 #define HGT_CUDA(call)                                                                          \
     do {                                                                                        \

@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <memory>
 #include <numeric>
 #include <thread>
 #include <string>
@@ -49,6 +50,7 @@ struct hgt_locus {
     hgt_ctx *ctx = nullptr;
     int32_t *d_var_pos = nullptr, *d_delr_right = nullptr, *d_delr_row = nullptr, *d_gn_rank = nullptr;
     uint64_t *d_st = nullptr, *d_mask = nullptr;
+    double *d_allele_len = nullptr;
 };
 
 struct LocusDev {
@@ -155,7 +157,7 @@ extern "C" void hgt_locus_free(hgt_locus *l) {
     if (l->ctx) {
         cudaSetDevice(l->ctx->device);
         cudaFree(l->d_var_pos); cudaFree(l->d_delr_right); cudaFree(l->d_delr_row); cudaFree(l->d_gn_rank);
-        cudaFree(l->d_st); cudaFree(l->d_mask);
+        cudaFree(l->d_st); cudaFree(l->d_mask); cudaFree(l->d_allele_len);
     }
     delete l;
 }
@@ -202,6 +204,7 @@ extern "C" int hgt_locus_create(hgt_ctx *ctx, const hgt_locus_desc *d, hgt_locus
         delete l;
         return rc;
     }
+    h.finalize();
     const int wp = l->wp;
     l->mask.assign((size_t)3 * wp, 0);
     for (int a = 0; a < l->A; a++) l->mask[a >> 6] |= 1ull << (a & 63);
@@ -271,6 +274,7 @@ extern "C" int hgt_locus_create(hgt_ctx *ctx, const hgt_locus_desc *d, hgt_locus
     LTRY(cudaMalloc(&l->d_gn_rank, sizeof(int32_t) * l->A));
     LTRY(cudaMalloc(&l->d_mask, sizeof(uint64_t) * 3 * wp));
     LTRY(cudaMalloc(&l->d_st, sizeof(uint64_t) * lvl_words * levels));
+    LTRY(cudaMalloc(&l->d_allele_len, sizeof(double) * l->A));
     cudaStream_t st = ctx->stream;
     if (V > 0) LTRY(cudaMemcpyAsync(l->d_var_pos, h.var_pos.data(), sizeof(int32_t) * V, cudaMemcpyHostToDevice, st));
     if (l->n_delr > 0) {
@@ -278,6 +282,7 @@ extern "C" int hgt_locus_create(hgt_ctx *ctx, const hgt_locus_desc *d, hgt_locus
         LTRY(cudaMemcpyAsync(l->d_delr_row, l->delr_row.data(), sizeof(int32_t) * l->n_delr, cudaMemcpyHostToDevice, st));
     }
     LTRY(cudaMemcpyAsync(l->d_gn_rank, l->gn_rank.data(), sizeof(int32_t) * l->A, cudaMemcpyHostToDevice, st));
+    LTRY(cudaMemcpyAsync(l->d_allele_len, l->allele_len.data(), sizeof(double) * l->A, cudaMemcpyHostToDevice, st));
     LTRY(cudaMemcpyAsync(l->d_mask, l->mask.data(), sizeof(uint64_t) * 3 * wp, cudaMemcpyHostToDevice, st));
     LTRY(cudaMemcpyAsync(l->d_st, lbits.data(), sizeof(uint64_t) * lvl_words, cudaMemcpyHostToDevice, st));
     if (e == cudaSuccess) {
@@ -324,13 +329,6 @@ struct HostOut {
     TableJobs tb[3];
 };
 
-struct PileupIn {  // records that take part in the pileup (weaker filters, common:1084-1098)
-    std::vector<int32_t> pos;
-    std::vector<int64_t> cig_off{0}, seq_off{0};
-    std::vector<uint32_t> cig;  // len << 4 | op (0 M, 1 I, 2 D, 3 S, 4 N)
-    std::vector<char> seq;
-};
-
 struct Intake {
     std::vector<Record> recs;
 };
@@ -367,29 +365,6 @@ static int op_code(char c) {
     }
 }
 
-static int build_pileup_input(const Intake &in, const hgt_params &pr, PileupIn *pi) {
-    std::vector<CigarOp> cig;
-    for (const Record &r : in.recs) {
-        if (r.flag & 0x4) continue;
-        if (r.pos < 0) continue;
-        if (!pr.allow_discordant && !(r.flag & 0x2)) continue;
-        if (!parse_cigar(r.cigar, r.cigar_len, &cig)) {
-            hgt_set_error("malformed CIGAR in read %.*s", r.qname_len, r.qname);
-            return HGT_ERR_PARSE;
-        }
-        pi->pos.push_back(r.pos);
-        for (const CigarOp &c : cig) {
-            const int oc = op_code(c.op);
-            if (oc < 0) continue;  // the reference's pileup ignores ops outside MIDNS (common:1107-1121)
-            pi->cig.push_back(((uint32_t)c.len << 4) | (uint32_t)oc);
-        }
-        pi->cig_off.push_back((int64_t)pi->cig.size());
-        pi->seq.insert(pi->seq.end(), r.seq, r.seq + r.seq_len);
-        pi->seq_off.push_back((int64_t)pi->seq.size());
-    }
-    return HGT_OK;
-}
-
 static int host_walk(const hgt_locus *loc, const Intake &in, const hgt_params &pr, const PileupView &pu, HostOut *out) {
     const LocusHost &L = loc->host;
     std::unordered_set<std::string_view> seen[3];
@@ -402,6 +377,7 @@ static int host_walk(const hgt_locus *loc, const Intake &in, const hgt_params &p
     WalkResult w;
     WalkError err;
     Ambig amb;
+    AmbigScratch amb_scratch;
     std::vector<Cmp> c2;
     std::string_view prev_id;
     bool have_prev = false;
@@ -497,7 +473,7 @@ static int host_walk(const hgt_locus *loc, const Intake &in, const hgt_params &p
             hgt_set_error("read %.*s has an empty alignment", r.qname_len, r.qname);
             return HGT_ERR_PARSE;
         }
-        if (!identify_ambiguous_diffs(L, c2, &amb, &err)) {
+        if (!identify_ambiguous_diffs(L, c2, &amb, &err, &amb_scratch)) {
             hgt_set_error("%s (read %.*s)", err.msg.c_str(), r.qname_len, r.qname);
             return err.code;
         }
@@ -531,7 +507,8 @@ constexpr int WARPS_PER_CTA = 8;
 // ---- pileup (common:1100-1121): warp per record, lanes over the bases of each CIGAR op -------------------
 __global__ void pileup_kernel(const int32_t *__restrict__ pos, const int64_t *__restrict__ cig_off,
                               const uint32_t *__restrict__ cig, const int64_t *__restrict__ seq_off,
-                              const char *__restrict__ seq, const int32_t *__restrict__ rec_unit, int64_t n_rec, int L,
+                              const char *__restrict__ seq, const int32_t *__restrict__ rec_unit, int64_t n_rec,
+                              const int64_t *__restrict__ unit_pos0, const int32_t *__restrict__ unit_L,
                               uint32_t *__restrict__ counts_all) {
     const int lane = threadIdx.x & 31;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
@@ -539,7 +516,9 @@ __global__ void pileup_kernel(const int32_t *__restrict__ pos, const int64_t *__
     for (int64_t r = warp0; r < n_rec; r += nwarps) {
         int gpos = pos[r];
         int64_t rpos = seq_off[r];
-        uint32_t *counts = counts_all + (size_t)rec_unit[r] * L * 6;
+        const int u = rec_unit[r];
+        const int L = unit_L[u];
+        uint32_t *counts = counts_all + (size_t)unit_pos0[u] * 6;
         for (int64_t c = cig_off[r]; c < cig_off[r + 1]; c++) {
             const uint32_t x = cig[c];
             const int len = (int)(x >> 4), op = (int)(x & 15u);
@@ -873,55 +852,41 @@ __global__ void pileup_flags_kernel(const uint32_t *__restrict__ counts, int64_t
 // ================================================================================================================
 // Device buffers
 // ================================================================================================================
-struct DevBuf {
-    void *p = nullptr;
-    size_t bytes = 0;
-    int alloc(size_t n) {
-        release();
-        bytes = n;
-        if (n == 0) n = 16;
-        cudaError_t e = cudaMalloc(&p, n);
-        if (e != cudaSuccess) {
-            hgt_set_error("cudaMalloc(%zu) -> %s", n, cudaGetErrorString(e));
-            p = nullptr;
-            return e == cudaErrorMemoryAllocation ? HGT_ERR_NOMEM : HGT_ERR_CUDA;
-        }
-        return HGT_OK;
-    }
-    void release() {
-        if (p) cudaFree(p);
-        p = nullptr;
-        bytes = 0;
-    }
-    template <class T>
-    T *as() const { return static_cast<T *>(p); }
-};
+static thread_local hgt_ctx *g_acct = nullptr;  // context of the running entry point: owns the pool and the byte counters
 
-struct PinBuf {  // page-locked host memory: asynchronous D2H targets and kernel-argument staging
+// Device / page-locked host buffers drawn from the context's caching allocator (MemPool, common.cuh).
+template <bool PINNED>
+struct PoolBuf {
     void *p = nullptr;
-    size_t bytes = 0;
+    size_t bytes = 0, cap = 0;
+    hgt_ctx *owner = nullptr;
     int alloc(size_t n) {
-        if (p && bytes >= n) return HGT_OK;
-        release();
-        cudaError_t e = cudaMallocHost(&p, n ? n : 16);
-        if (e != cudaSuccess) {
-            hgt_set_error("cudaMallocHost(%zu) -> %s", n, cudaGetErrorString(e));
-            p = nullptr;
-            return HGT_ERR_NOMEM;
+        if (p && cap >= n) {
+            bytes = n;
+            return HGT_OK;
         }
+        release();
+        owner = g_acct;
+        if (!owner) {
+            hgt_set_error("internal: buffer allocation outside an entry point");
+            return HGT_ERR_ARG;
+        }
+        HGT_CHECK(owner->pool.get(PINNED, n ? n : 16, &p, &cap));
         bytes = n;
         return HGT_OK;
     }
     void release() {
-        if (p) cudaFreeHost(p);
+        if (p && owner) owner->pool.put(PINNED, p, cap);
         p = nullptr;
-        bytes = 0;
+        bytes = cap = 0;
     }
     template <class T>
     T *as() const { return static_cast<T *>(p); }
 };
+using DevBuf = PoolBuf<false>;
+using PinBuf = PoolBuf<true>;
 
-static thread_local hgt_ctx *g_acct = nullptr;  // context whose byte counters the copies below feed
+  // context whose byte counters the copies below feed
 
 template <class T>
 static int upload(DevBuf *b, const std::vector<T> &v, cudaStream_t st) {
@@ -986,25 +951,37 @@ struct UnitHost {
     int rc = HGT_OK;
     std::string err;
     int local = 0;  // index inside its locus batch
-    std::vector<uint8_t> nt_mask, del_flag;
+    const uint8_t *nt_mask = nullptr, *del_flag = nullptr;  // [L] views into the batch's page-locked pileup result
     std::vector<uint32_t> counts;  // kept only when requested (single-unit API / tests)
+    // pileup packing (records that pass the weaker filters of common:1084-1098)
+    std::vector<uint32_t> pu_rec;   // indices into in.recs
+    std::vector<uint32_t> pu_cig;   // len << 4 | op
+    std::vector<uint32_t> pu_ncig;  // ops per record
+    int64_t pu_seq = 0;             // bases
+    int64_t pu_rec0 = 0, pu_cig0 = 0, pu_seq0 = 0, pos0 = 0;  // offsets inside the batch arenas
 };
 
 struct LocusBatch {
     hgt_locus *loc = nullptr;
     std::vector<int> units;  // global unit ids
-    // jobs of all units and tables of this locus
-    std::vector<int64_t> job_off{0};
-    std::vector<int32_t> job_ut, job_pair, job_small, job_big;
-    std::vector<int32_t> hap_left, hap_right, hap_table;
-    std::vector<int64_t> row_off{0};
-    std::vector<int32_t> rows;
+    // jobs of all units and tables of this locus: one arena, identical layout in page-locked host memory (filled by
+    // the host threads in parallel) and on the device (one copy): job_off | row_off | ut_base | job_ut | job_pair |
+    // job_list (<= 7 haplotypes first, then the rest) | hap_left | hap_right | hap_table | rows
+    struct JobArena {
+        size_t o_job_off = 0, o_row_off = 0, o_ut_base = 0, o_job_ut = 0, o_job_pair = 0, o_job_list = 0, o_hl = 0, o_hr = 0,
+               o_ht = 0, o_rows = 0, bytes = 0;
+    } ja;
+    int64_t n_jobs = 0, n_small = 0, n_big = 0, n_haps = 0, n_rows = 0;
     std::vector<int64_t> ut_base;  // [n_units*4 + 1]
     int64_t n_rows_pool = 0;
-    // device
-    DevBuf d_job_off, d_job_ut, d_job_pair, d_job_list, d_hl, d_hr, d_ht, d_ro, d_rows, d_hapbits;
-    DevBuf d_keys, d_slot, d_bits, d_count, d_first, d_ut_base, d_ut_ncls;
-    DevBuf d_prob, d_inres, d_fk, d_is, d_emws, d_len;      // EM over exon (hla) / gene (other) tables
+    PinBuf h_jobs;
+    DevBuf d_jobs, d_hapbits;
+    template <class T>
+    T *dj(size_t off) const { return reinterpret_cast<T *>(static_cast<unsigned char *>(d_jobs.p) + off); }
+    template <class T>
+    T *hj(size_t off) const { return reinterpret_cast<T *>(static_cast<unsigned char *>(h_jobs.p) + off); }
+    DevBuf d_keys, d_slot, d_bits, d_count, d_first, d_ut_ncls;
+    DevBuf d_prob, d_inres, d_fk, d_is, d_emws;      // EM over exon (hla) / gene (other) tables
     DevBuf d_prob2, d_inres2, d_fk2, d_is2, d_keep, d_ulist;  // second-level EM (hla)
     DevBuf d_acount, d_afirst;
     uint32_t cap = 0;
@@ -1016,21 +993,23 @@ struct LocusBatch {
     uint8_t *inres = nullptr, *inres2 = nullptr;
     int32_t *fk = nullptr, *fk2 = nullptr, *is = nullptr, *is2 = nullptr;
     std::vector<uint8_t> has2;  // unit ran the second-level EM
+    std::vector<int32_t> slot2;      // its slot in the keep-mask / unit list of the second level
+    std::vector<double> exon_prob_sum;  // core:1739-1749
     int n_level2 = 0;
     void release() {
-        DevBuf *all[] = {&d_job_off, &d_job_ut, &d_job_pair, &d_job_list, &d_hl, &d_hr, &d_ht, &d_ro, &d_rows, &d_hapbits,
-                         &d_keys, &d_slot, &d_bits, &d_count, &d_first, &d_ut_base, &d_ut_ncls, &d_prob, &d_inres, &d_fk,
-                         &d_is, &d_emws, &d_len, &d_prob2, &d_inres2, &d_fk2, &d_is2, &d_keep, &d_ulist,
+        DevBuf *all[] = {&d_jobs, &d_hapbits,
+                         &d_keys, &d_slot, &d_bits, &d_count, &d_first, &d_ut_ncls, &d_prob, &d_inres, &d_fk,
+                         &d_is, &d_emws, &d_prob2, &d_inres2, &d_fk2, &d_is2, &d_keep, &d_ulist,
                          &d_acount, &d_afirst};
         for (DevBuf *b : all) b->release();
-        PinBuf *pins[] = {&h_ncls, &h_prob, &h_inres, &h_fk, &h_is, &h_prob2, &h_inres2, &h_fk2, &h_is2, &h_keep, &h_ulist};
+        PinBuf *pins[] = {&h_jobs, &h_ncls, &h_prob, &h_inres, &h_fk, &h_is, &h_prob2, &h_inres2, &h_fk2, &h_is2, &h_keep, &h_ulist};
         for (PinBuf *b : pins) b->release();
     }
     ClassPool pool() const {
         ClassPool p;
         p.keys = d_keys.as<unsigned long long>(); p.slot_class = d_slot.as<int32_t>(); p.cap_mask = cap - 1;
         p.bits = d_bits.as<uint64_t>(); p.count = d_count.as<unsigned long long>(); p.first = d_first.as<int32_t>();
-        p.ut_base = d_ut_base.as<int64_t>(); p.ut_ncls = d_ut_ncls.as<int32_t>();
+        p.ut_base = dj<int64_t>(ja.o_ut_base); p.ut_ncls = d_ut_ncls.as<int32_t>();
         return p;
     }
 };
@@ -1045,11 +1024,17 @@ struct hgt_batch {
     bool prepared = false, executed = false, finished = false;
     StageTimer timer;
     int remove_low = 1;
+    PinBuf h_pileup, h_pumask;  // pileup input arena / nt_set + deletion-artefact flags of every unit
     PinBuf h_em_args[2];   // kernel-argument staging of the two EM levels
     DevBuf d_em_args[2];
     ~hgt_batch() {
-        if (ctx) cudaSetDevice(ctx->device);
+        if (ctx) {
+            cudaSetDevice(ctx->device);
+            cudaDeviceSynchronize();  // pooled blocks go back to the allocator: nothing may still be using them
+        }
         for (LocusBatch &b : lb) b.release();
+        h_pileup.release();
+        h_pumask.release();
         for (int i = 0; i < 2; i++) {
             h_em_args[i].release();
             d_em_args[i].release();
@@ -1090,6 +1075,8 @@ static int batch_threads(const hgt_params &p) {
 }
 
 // ---- stage 1: intake + pileup (GPU) + walk (host threads) + job upload -----------------------------------------
+static inline size_t a16(size_t x) { return (x + 15) & ~(size_t)15; }
+
 static int batch_prepare(hgt_batch *b) {
     hgt_ctx *ctx = b->ctx;
     cudaStream_t st = ctx->stream;
@@ -1102,223 +1089,319 @@ static int batch_prepare(hgt_batch *b) {
         b->units[u].local = (int)lb.units.size();
         lb.units.push_back((int)u);
     }
-    // intake (parallel)
-    parallel_units(nthreads, nu, [&](size_t u) {
-        UnitHost &U = b->units[u];
-        const int rc = intake(U.sam, U.n_bytes, b->params, &U.in);
-        if (rc != HGT_OK) set_unit_error(U, rc);
-    });
-    for (UnitHost &U : b->units)
-        if (U.rc != HGT_OK) {
-            hgt_set_error("%s", U.err.c_str());
-            return U.rc;
-        }
-    // pileup per locus batch: one launch over the records of all its units
-    for (LocusBatch &lb : b->lb) {
-        if (lb.units.empty()) continue;
-        const int L = lb.loc->L;
-        const size_t n_units = lb.units.size();
-        std::vector<PileupIn> pis(n_units);
-        std::vector<int> rcs(n_units, HGT_OK);
-        std::vector<std::string> errs(n_units);
-        parallel_units(nthreads, n_units, [&](size_t i) {
-            rcs[i] = build_pileup_input(b->units[lb.units[i]].in, b->params, &pis[i]);
-            if (rcs[i] != HGT_OK) errs[i] = hgt_last_error();
+    auto first_error = [&]() {
+        for (UnitHost &U : b->units)
+            if (U.rc != HGT_OK) {
+                hgt_set_error("%s", U.err.c_str());
+                return U.rc;
+            }
+        return (int)HGT_OK;
+    };
+    // ---- intake + pileup packing, pass 1 (parallel over units): parse the text, pick the pileup records, parse CIGARs
+    {
+        HostTimer ht(ctx, 0);
+        parallel_units(nthreads, nu, [&](size_t u) {
+            UnitHost &U = b->units[u];
+            int rc = intake(U.sam, U.n_bytes, b->params, &U.in);
+            if (rc != HGT_OK) {
+                set_unit_error(U, rc);
+                return;
+            }
+            std::vector<CigarOp> cig;
+            for (size_t k = 0; k < U.in.recs.size(); k++) {
+                const Record &r = U.in.recs[k];
+                if (r.flag & 0x4) continue;
+                if (r.pos < 0) continue;
+                if (!b->params.allow_discordant && !(r.flag & 0x2)) continue;
+                if (!parse_cigar(r.cigar, r.cigar_len, &cig)) {
+                    hgt_set_error("malformed CIGAR in read %.*s", r.qname_len, r.qname);
+                    set_unit_error(U, HGT_ERR_PARSE);
+                    return;
+                }
+                uint32_t n = 0;
+                for (const CigarOp &c : cig) {
+                    const int oc = op_code(c.op);
+                    if (oc < 0) continue;  // the reference's pileup ignores ops outside MIDNS (common:1107-1121)
+                    U.pu_cig.push_back(((uint32_t)c.len << 4) | (uint32_t)oc);
+                    n++;
+                }
+                U.pu_rec.push_back((uint32_t)k);
+                U.pu_ncig.push_back(n);
+                U.pu_seq += r.seq_len;
+            }
         });
-        for (size_t i = 0; i < n_units; i++)
-            if (rcs[i] != HGT_OK) {
-                hgt_set_error("%s", errs[i].c_str());
-                return rcs[i];
+    }
+    HGT_CHECK(first_error());
+    // ---- pileup: one arena for all units of all loci, one copy, one launch -----------------------------------------
+    int64_t R = 0, CG = 0, SQ = 0, POS = 0;
+    for (UnitHost &U : b->units) {
+        U.pu_rec0 = R; U.pu_cig0 = CG; U.pu_seq0 = SQ; U.pos0 = POS;
+        R += (int64_t)U.pu_rec.size(); CG += (int64_t)U.pu_cig.size(); SQ += U.pu_seq;
+        POS += b->loci[U.locus]->L;
+    }
+    const size_t o_pos = 0, o_ru = a16(o_pos + (size_t)R * 4), o_co = a16(o_ru + (size_t)R * 4),
+                 o_so = a16(o_co + (size_t)(R + 1) * 8), o_up = a16(o_so + (size_t)(R + 1) * 8),
+                 o_ul = a16(o_up + nu * 8), o_cg = a16(o_ul + nu * 4), o_sq = a16(o_cg + (size_t)CG * 4),
+                 pu_bytes = a16(o_sq + (size_t)SQ);
+    DevBuf d_pu, d_cnt, d_mf;
+    std::vector<uint32_t> counts_all;
+    {
+        HostTimer ht(ctx, 1);
+        HGT_CHECK(b->h_pileup.alloc(pu_bytes));
+        HGT_CHECK(b->h_pumask.alloc((size_t)POS * 2));
+        unsigned char *hp = static_cast<unsigned char *>(b->h_pileup.p);
+        int32_t *h_pos = reinterpret_cast<int32_t *>(hp + o_pos), *h_ru = reinterpret_cast<int32_t *>(hp + o_ru);
+        int64_t *h_co = reinterpret_cast<int64_t *>(hp + o_co), *h_so = reinterpret_cast<int64_t *>(hp + o_so);
+        int64_t *h_up = reinterpret_cast<int64_t *>(hp + o_up);
+        int32_t *h_ul = reinterpret_cast<int32_t *>(hp + o_ul);
+        uint32_t *h_cg = reinterpret_cast<uint32_t *>(hp + o_cg);
+        char *h_sq = reinterpret_cast<char *>(hp + o_sq);
+        h_co[R] = CG;
+        h_so[R] = SQ;
+        parallel_units(nthreads, nu, [&](size_t u) {
+            UnitHost &U = b->units[u];
+            h_up[u] = U.pos0;
+            h_ul[u] = b->loci[U.locus]->L;
+            int64_t c = U.pu_cig0, q = U.pu_seq0;
+            if (!U.pu_cig.empty()) memcpy(h_cg + c, U.pu_cig.data(), U.pu_cig.size() * 4);
+            for (size_t k = 0; k < U.pu_rec.size(); k++) {
+                const Record &r = U.in.recs[U.pu_rec[k]];
+                const int64_t i = U.pu_rec0 + (int64_t)k;
+                h_pos[i] = r.pos;
+                h_ru[i] = (int32_t)u;
+                h_co[i] = c;
+                h_so[i] = q;
+                memcpy(h_sq + q, r.seq, (size_t)r.seq_len);
+                c += U.pu_ncig[k];
+                q += r.seq_len;
             }
-        PileupIn all;
-        std::vector<int32_t> rec_unit;
-        for (size_t i = 0; i < n_units; i++) {
-            const PileupIn &p = pis[i];
-            const int64_t c0 = (int64_t)all.cig.size(), s0 = (int64_t)all.seq.size();
-            all.pos.insert(all.pos.end(), p.pos.begin(), p.pos.end());
-            for (size_t k = 1; k < p.cig_off.size(); k++) all.cig_off.push_back(c0 + p.cig_off[k]);
-            for (size_t k = 1; k < p.seq_off.size(); k++) all.seq_off.push_back(s0 + p.seq_off[k]);
-            all.cig.insert(all.cig.end(), p.cig.begin(), p.cig.end());
-            all.seq.insert(all.seq.end(), p.seq.begin(), p.seq.end());
-            rec_unit.insert(rec_unit.end(), p.pos.size(), (int32_t)i);
-        }
-        DevBuf d_pos, d_co, d_c, d_so, d_s, d_ru, d_cnt, d_m, d_f;
-        int rc = HGT_OK;
-        std::vector<uint8_t> mask(n_units * (size_t)L), flag(n_units * (size_t)L);
-        std::vector<uint32_t> counts;
-        do {
-            if ((rc = upload(&d_pos, all.pos, st)) != HGT_OK) break;
-            if ((rc = upload(&d_co, all.cig_off, st)) != HGT_OK) break;
-            if ((rc = upload(&d_c, all.cig, st)) != HGT_OK) break;
-            if ((rc = upload(&d_so, all.seq_off, st)) != HGT_OK) break;
-            if ((rc = upload(&d_s, all.seq, st)) != HGT_OK) break;
-            if ((rc = upload(&d_ru, rec_unit, st)) != HGT_OK) break;
-            if ((rc = d_cnt.alloc(n_units * (size_t)L * 24)) != HGT_OK) break;
-            if ((rc = d_m.alloc(n_units * (size_t)L)) != HGT_OK) break;
-            if ((rc = d_f.alloc(n_units * (size_t)L)) != HGT_OK) break;
-            cudaError_t e = cudaMemsetAsync(d_cnt.p, 0, n_units * (size_t)L * 24, st);
-            const int64_t n = (int64_t)all.pos.size();
-            b->timer.begin(ctx, st, 0);
-            if (e == cudaSuccess && n > 0) {
-                const int ctas = (int)std::min<int64_t>((n + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 8);
-                pileup_kernel<<<ctas, WARPS_PER_CTA * 32, 0, st>>>(d_pos.as<int32_t>(), d_co.as<int64_t>(), d_c.as<uint32_t>(),
-                                                                    d_so.as<int64_t>(), d_s.as<char>(), d_ru.as<int32_t>(), n, L,
-                                                                    d_cnt.as<uint32_t>());
-                ctx->launches++;
-            }
-            const int64_t npos = (int64_t)n_units * L;
-            pileup_flags_kernel<<<(unsigned)((npos + 255) / 256), 256, 0, st>>>(d_cnt.as<uint32_t>(), npos, d_m.as<uint8_t>(),
-                                                                               d_f.as<uint8_t>());
+            std::vector<uint32_t>().swap(U.pu_cig);
+            std::vector<uint32_t>().swap(U.pu_rec);
+            std::vector<uint32_t>().swap(U.pu_ncig);
+        });
+    }
+    {
+        HostTimer ht(ctx, 2);
+        HGT_CHECK(d_pu.alloc(pu_bytes));
+        HGT_CHECK(d_cnt.alloc((size_t)POS * 24));
+        HGT_CHECK(d_mf.alloc((size_t)POS * 2));
+        unsigned char *dp = static_cast<unsigned char *>(d_pu.p);
+        ctx->h2d_bytes += (int64_t)pu_bytes;
+        HGT_CUDA(cudaMemcpyAsync(d_pu.p, b->h_pileup.p, pu_bytes, cudaMemcpyHostToDevice, st));
+        HGT_CUDA(cudaMemsetAsync(d_cnt.p, 0, (size_t)POS * 24, st));
+        b->timer.begin(ctx, st, 0);
+        if (R > 0) {
+            const int ctas = (int)std::min<int64_t>((R + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 8);
+            pileup_kernel<<<ctas, WARPS_PER_CTA * 32, 0, st>>>(
+                reinterpret_cast<int32_t *>(dp + o_pos), reinterpret_cast<int64_t *>(dp + o_co),
+                reinterpret_cast<uint32_t *>(dp + o_cg), reinterpret_cast<int64_t *>(dp + o_so),
+                reinterpret_cast<char *>(dp + o_sq), reinterpret_cast<int32_t *>(dp + o_ru), R,
+                reinterpret_cast<int64_t *>(dp + o_up), reinterpret_cast<int32_t *>(dp + o_ul), d_cnt.as<uint32_t>());
             ctx->launches++;
-            b->timer.end(n > 0 ? 2 : 1);
-            if (e == cudaSuccess) e = cudaGetLastError();
-            if (e == cudaSuccess) e = d2h(mask.data(), d_m.p, mask.size(), st);
-            if (e == cudaSuccess) e = d2h(flag.data(), d_f.p, flag.size(), st);
-            if (e == cudaSuccess && b->keep_counts) {
-                counts.resize(n_units * (size_t)L * 6);
-                e = d2h(counts.data(), d_cnt.p, counts.size() * 4, st);
-            }
-            if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-            b->timer.resolve();
-            if (e != cudaSuccess) {
-                hgt_set_error("pileup: %s", cudaGetErrorString(e));
-                rc = HGT_ERR_CUDA;
-            }
-        } while (0);
-        d_pos.release(); d_co.release(); d_c.release(); d_so.release(); d_s.release(); d_ru.release();
-        d_cnt.release(); d_m.release(); d_f.release();
-        if (rc != HGT_OK) return rc;
-        for (size_t i = 0; i < n_units; i++) {
-            UnitHost &U = b->units[lb.units[i]];
-            U.nt_mask.assign(mask.begin() + i * (size_t)L, mask.begin() + (i + 1) * (size_t)L);
-            U.del_flag.assign(flag.begin() + i * (size_t)L, flag.begin() + (i + 1) * (size_t)L);
-            if (b->keep_counts) U.counts.assign(counts.begin() + i * (size_t)L * 6, counts.begin() + (i + 1) * (size_t)L * 6);
+        }
+        if (POS > 0) {
+            pileup_flags_kernel<<<(unsigned)((POS + 255) / 256), 256, 0, st>>>(d_cnt.as<uint32_t>(), POS, d_mf.as<uint8_t>(),
+                                                                               d_mf.as<uint8_t>() + POS);
+            ctx->launches++;
+        }
+        b->timer.end((R > 0) + (POS > 0));
+        HGT_CUDA(cudaGetLastError());
+        HGT_CUDA(d2h(b->h_pumask.p, d_mf.p, (size_t)POS * 2, st));
+        if (b->keep_counts) {
+            counts_all.resize((size_t)POS * 6);
+            HGT_CUDA(d2h(counts_all.data(), d_cnt.p, counts_all.size() * 4, st));
+        }
+        HGT_CUDA(cudaStreamSynchronize(st));
+        b->timer.resolve();
+        d_pu.release(); d_cnt.release(); d_mf.release();
+    }
+    for (UnitHost &U : b->units) {
+        U.nt_mask = b->h_pumask.as<uint8_t>() + U.pos0;
+        U.del_flag = b->h_pumask.as<uint8_t>() + POS + U.pos0;
+        if (b->keep_counts) {
+            const size_t L = (size_t)b->loci[U.locus]->L;
+            U.counts.assign(counts_all.begin() + (size_t)U.pos0 * 6, counts_all.begin() + ((size_t)U.pos0 + L) * 6);
         }
     }
-    // walk (parallel over units)
-    parallel_units(nthreads, nu, [&](size_t u) {
-        UnitHost &U = b->units[u];
-        const hgt_locus *loc = b->loci[U.locus];
-        PileupView pu;
-        pu.nt_mask = U.nt_mask.data(); pu.del_artefact = U.del_flag.data(); pu.L = loc->L;
-        const int rc = host_walk(loc, U.in, b->params, pu, &U.ho);
-        if (rc != HGT_OK) set_unit_error(U, rc);
-        U.in.recs.clear();
-        U.in.recs.shrink_to_fit();
-    });
-    for (UnitHost &U : b->units)
-        if (U.rc != HGT_OK) {
-            hgt_set_error("%s", U.err.c_str());
-            return U.rc;
-        }
-    // concatenate jobs per locus and upload
-    for (LocusBatch &lb : b->lb) {
-        if (lb.units.empty()) continue;
-        const hgt_locus *loc = lb.loc;
-        const int wp = loc->wp;
-        const int n_tables = loc->is_hla ? 3 : 1;
-        const size_t n_units = lb.units.size();
-        lb.ut_base.assign(n_units * 4 + 1, 0);
-        for (size_t i = 0; i < n_units; i++) {
-            const UnitHost &U = b->units[lb.units[i]];
-            for (int tb = 0; tb < 4; tb++) {
-                const bool active = tb < n_tables || (tb == 3 && loc->is_hla);
-                lb.ut_base[i * 4 + tb + 1] = lb.ut_base[i * 4 + tb] + (active ? U.ho.num_pairs : 0);
-            }
-            for (int tb = 0; tb < n_tables; tb++) {
-                const TableJobs &J = U.ho.tb[tb];
-                const int64_t h0 = (int64_t)lb.hap_left.size(), r0 = (int64_t)lb.rows.size();
-                lb.hap_left.insert(lb.hap_left.end(), J.hap_left.begin(), J.hap_left.end());
-                lb.hap_right.insert(lb.hap_right.end(), J.hap_right.begin(), J.hap_right.end());
-                lb.hap_table.insert(lb.hap_table.end(), J.hap_left.size(), tb);
-                for (size_t k = 1; k < J.row_off.size(); k++) lb.row_off.push_back(r0 + J.row_off[k]);
-                lb.rows.insert(lb.rows.end(), J.rows.begin(), J.rows.end());
-                for (int64_t p = 0; p < U.ho.num_pairs; p++) {
-                    const int64_t k = J.job_off[p + 1] - J.job_off[p];
-                    if (k > 255) {
-                        hgt_set_error("a read pair expands to %lld haplotypes (limit 255)", (long long)k);
-                        return HGT_ERR_UNSUPPORTED;
+    // ---- walk (parallel over units) ---------------------------------------------------------------------------------
+    {
+        HostTimer ht(ctx, 3);
+        parallel_units(nthreads, nu, [&](size_t u) {
+            UnitHost &U = b->units[u];
+            const hgt_locus *loc = b->loci[U.locus];
+            PileupView pu;
+            pu.nt_mask = U.nt_mask; pu.del_artefact = U.del_flag; pu.L = loc->L;
+            const int rc = host_walk(loc, U.in, b->params, pu, &U.ho);
+            if (rc != HGT_OK) set_unit_error(U, rc);
+            std::vector<Record>().swap(U.in.recs);
+        });
+    }
+    HGT_CHECK(first_error());
+    // ---- job arenas per locus: offsets (serial, tiny), then a parallel fill straight into page-locked memory --------
+    struct Fill { LocusBatch *lb; size_t i; int64_t h0[3], r0[3], j0[3], s0[3], b0[3]; };
+    std::vector<Fill> fills;
+    {
+        HostTimer ht(ctx, 4);
+        for (LocusBatch &lb : b->lb) {
+            if (lb.units.empty()) continue;
+            const hgt_locus *loc = lb.loc;
+            const int n_tables = loc->is_hla ? 3 : 1;
+            const size_t n_units = lb.units.size();
+            lb.ut_base.assign(n_units * 4 + 1, 0);
+            int64_t H = 0, RW = 0, J = 0, NS = 0, NB = 0;
+            const size_t f0 = fills.size();
+            for (size_t i = 0; i < n_units; i++) {
+                const UnitHost &U = b->units[lb.units[i]];
+                Fill f;
+                f.lb = &lb; f.i = i;
+                for (int tb = 0; tb < 4; tb++) {
+                    const bool active = tb < n_tables || (tb == 3 && loc->is_hla);
+                    lb.ut_base[i * 4 + tb + 1] = lb.ut_base[i * 4 + tb] + (active ? U.ho.num_pairs : 0);
+                }
+                for (int tb = 0; tb < 3; tb++) {
+                    f.h0[tb] = H; f.r0[tb] = RW; f.j0[tb] = J; f.s0[tb] = NS; f.b0[tb] = NB;
+                    if (tb >= n_tables) continue;
+                    const TableJobs &T = U.ho.tb[tb];
+                    int64_t small = 0;
+                    for (int64_t p = 0; p < U.ho.num_pairs; p++) {
+                        const int64_t k = T.job_off[p + 1] - T.job_off[p];
+                        if (k > 255) {
+                            hgt_set_error("a read pair expands to %lld haplotypes (limit 255)", (long long)k);
+                            return HGT_ERR_UNSUPPORTED;
+                        }
+                        small += k <= 7;
                     }
-                    const int32_t job = (int32_t)lb.job_ut.size();
-                    (k <= 7 ? lb.job_small : lb.job_big).push_back(job);
-                    lb.job_ut.push_back((int32_t)(i * 4 + tb));
-                    lb.job_pair.push_back((int32_t)p);
-                    lb.job_off.push_back(h0 + J.job_off[p + 1]);
+                    H += (int64_t)T.hap_left.size();
+                    RW += (int64_t)T.rows.size();
+                    J += U.ho.num_pairs;
+                    NS += small;
+                    NB += U.ho.num_pairs - small;
+                }
+                fills.push_back(f);
+            }
+            for (size_t k = f0; k < fills.size(); k++)
+                for (int tb = 0; tb < 3; tb++) fills[k].b0[tb] += NS;  // the > 7-haplotype jobs follow all small ones
+            lb.n_haps = H; lb.n_rows = RW; lb.n_jobs = J; lb.n_small = NS; lb.n_big = NB;
+            lb.n_rows_pool = lb.ut_base.back();
+            LocusBatch::JobArena &ja = lb.ja;
+            ja.o_job_off = 0;
+            ja.o_row_off = a16(ja.o_job_off + (size_t)(J + 1) * 8);
+            ja.o_ut_base = a16(ja.o_row_off + (size_t)(H + 1) * 8);
+            ja.o_job_ut = a16(ja.o_ut_base + (n_units * 4 + 1) * 8);
+            ja.o_job_pair = a16(ja.o_job_ut + (size_t)J * 4);
+            ja.o_job_list = a16(ja.o_job_pair + (size_t)J * 4);
+            ja.o_hl = a16(ja.o_job_list + (size_t)J * 4);
+            ja.o_hr = a16(ja.o_hl + (size_t)H * 4);
+            ja.o_ht = a16(ja.o_hr + (size_t)H * 4);
+            ja.o_rows = a16(ja.o_ht + (size_t)H * 4);
+            ja.bytes = a16(ja.o_rows + (size_t)RW * 4);
+            HGT_CHECK(lb.h_jobs.alloc(ja.bytes));
+            lb.hj<int64_t>(ja.o_job_off)[0] = 0;
+            lb.hj<int64_t>(ja.o_row_off)[0] = 0;
+            memcpy(lb.hj<int64_t>(ja.o_ut_base), lb.ut_base.data(), (n_units * 4 + 1) * 8);
+        }
+        parallel_units(nthreads, fills.size(), [&](size_t k) {
+            const Fill &f = fills[k];
+            LocusBatch &lb = *f.lb;
+            const LocusBatch::JobArena &ja = lb.ja;
+            const UnitHost &U = b->units[lb.units[f.i]];
+            const int n_tables = lb.loc->is_hla ? 3 : 1;
+            int64_t *job_off = lb.hj<int64_t>(ja.o_job_off), *row_off = lb.hj<int64_t>(ja.o_row_off);
+            int32_t *job_ut = lb.hj<int32_t>(ja.o_job_ut), *job_pair = lb.hj<int32_t>(ja.o_job_pair),
+                    *job_list = lb.hj<int32_t>(ja.o_job_list), *hl = lb.hj<int32_t>(ja.o_hl), *hr = lb.hj<int32_t>(ja.o_hr),
+                    *htb = lb.hj<int32_t>(ja.o_ht), *rows = lb.hj<int32_t>(ja.o_rows);
+            for (int tb = 0; tb < n_tables; tb++) {
+                const TableJobs &T = U.ho.tb[tb];
+                const int64_t h0 = f.h0[tb], r0 = f.r0[tb], j0 = f.j0[tb];
+                const size_t nh = T.hap_left.size();
+                if (nh) {
+                    memcpy(hl + h0, T.hap_left.data(), nh * 4);
+                    memcpy(hr + h0, T.hap_right.data(), nh * 4);
+                }
+                for (size_t h = 0; h < nh; h++) {
+                    htb[h0 + h] = tb;
+                    row_off[h0 + h + 1] = r0 + T.row_off[h + 1];
+                }
+                if (!T.rows.empty()) memcpy(rows + r0, T.rows.data(), T.rows.size() * 4);
+                int64_t s = f.s0[tb], g = f.b0[tb];
+                for (int64_t p = 0; p < U.ho.num_pairs; p++) {
+                    const int64_t job = j0 + p;
+                    job_ut[job] = (int32_t)(f.i * 4 + tb);
+                    job_pair[job] = (int32_t)p;
+                    job_off[job + 1] = h0 + T.job_off[p + 1];
+                    if (T.job_off[p + 1] - T.job_off[p] <= 7) job_list[s++] = (int32_t)job;
+                    else job_list[g++] = (int32_t)job;
                 }
             }
-        }
-        lb.n_rows_pool = lb.ut_base.back();
-        const int64_t n_jobs = (int64_t)lb.job_ut.size();
-        const int64_t H = (int64_t)lb.hap_left.size();
-        lb.cap = 64;
-        while ((int64_t)lb.cap < 2 * std::max<int64_t>(lb.n_rows_pool, 1)) lb.cap <<= 1;
-        std::vector<int32_t> jl(lb.job_small);
-        jl.insert(jl.end(), lb.job_big.begin(), lb.job_big.end());
-        HGT_CHECK(upload(&lb.d_job_off, lb.job_off, st));
-        HGT_CHECK(upload(&lb.d_job_ut, lb.job_ut, st));
-        HGT_CHECK(upload(&lb.d_job_pair, lb.job_pair, st));
-        HGT_CHECK(upload(&lb.d_job_list, jl, st));
-        HGT_CHECK(upload(&lb.d_hl, lb.hap_left, st));
-        HGT_CHECK(upload(&lb.d_hr, lb.hap_right, st));
-        HGT_CHECK(upload(&lb.d_ht, lb.hap_table, st));
-        HGT_CHECK(upload(&lb.d_ro, lb.row_off, st));
-        HGT_CHECK(upload(&lb.d_rows, lb.rows, st));
-        HGT_CHECK(upload(&lb.d_ut_base, lb.ut_base, st));
-        HGT_CHECK(lb.d_hapbits.alloc((size_t)std::max<int64_t>(H, 1) * wp * 8));
-        HGT_CHECK(lb.d_keys.alloc((size_t)lb.cap * 8));
-        HGT_CHECK(lb.d_slot.alloc((size_t)lb.cap * 4));
-        const size_t pr = (size_t)std::max<int64_t>(lb.n_rows_pool, 1);
-        HGT_CHECK(lb.d_bits.alloc(pr * wp * 8));
-        HGT_CHECK(lb.d_count.alloc(pr * 8));
-        HGT_CHECK(lb.d_first.alloc(pr * 4));
-        HGT_CHECK(lb.d_ut_ncls.alloc(n_units * 4 * 4));
-        // EM buffers (both levels; nothing is allocated after prepare)
-        const size_t A = (size_t)loc->A;
-        HGT_CHECK(lb.d_prob.alloc(n_units * A * 8));
-        HGT_CHECK(lb.d_inres.alloc(n_units * A));
-        HGT_CHECK(lb.d_fk.alloc(n_units * A * 4));
-        HGT_CHECK(lb.d_is.alloc(n_units * 12));
-        HGT_CHECK(lb.d_emws.alloc(n_units * hgt_em_problem_ws_bytes(wp)));
-        HGT_CHECK(lb.d_acount.alloc(n_units * A * 8));
-        HGT_CHECK(lb.d_afirst.alloc(n_units * A * 4));
-        HGT_CHECK(lb.h_ncls.alloc(n_units * 16));
-        HGT_CHECK(lb.h_prob.alloc(n_units * A * 8));
-        HGT_CHECK(lb.h_inres.alloc(n_units * A));
-        HGT_CHECK(lb.h_fk.alloc(n_units * A * 4));
-        HGT_CHECK(lb.h_is.alloc(n_units * 12));
-        lb.ut_ncls = lb.h_ncls.as<int32_t>(); lb.prob = lb.h_prob.as<double>(); lb.inres = lb.h_inres.as<uint8_t>();
-        lb.fk = lb.h_fk.as<int32_t>(); lb.is = lb.h_is.as<int32_t>();
-        memset(lb.ut_ncls, 0, n_units * 16);
-        for (int tb = 0; tb < 3; tb++) {
-            int n = 0;
-            for (int j = 0; j < wp; j++) n += __builtin_popcountll(loc->mask[(size_t)tb * wp + j]);
-            lb.n_live[tb] = n;
-        }
-        lb.n_live[3] = loc->A;
-        if (loc->is_hla) {
-            HGT_CHECK(lb.d_prob2.alloc(n_units * A * 8));
-            HGT_CHECK(lb.d_inres2.alloc(n_units * A));
-            HGT_CHECK(lb.d_fk2.alloc(n_units * A * 4));
-            HGT_CHECK(lb.d_is2.alloc(n_units * 12));
-            HGT_CHECK(lb.d_keep.alloc(n_units * (size_t)wp * 8));
-            HGT_CHECK(lb.d_ulist.alloc(n_units * 4));
-            HGT_CHECK(upload(&lb.d_len, loc->allele_len, st));
-            HGT_CHECK(lb.h_prob2.alloc(n_units * A * 8));
-            HGT_CHECK(lb.h_inres2.alloc(n_units * A));
-            HGT_CHECK(lb.h_fk2.alloc(n_units * A * 4));
-            HGT_CHECK(lb.h_is2.alloc(n_units * 12));
-            HGT_CHECK(lb.h_keep.alloc(n_units * (size_t)wp * 8));
-            HGT_CHECK(lb.h_ulist.alloc(n_units * 4));
-            lb.prob2 = lb.h_prob2.as<double>(); lb.inres2 = lb.h_inres2.as<uint8_t>();
-            lb.fk2 = lb.h_fk2.as<int32_t>(); lb.is2 = lb.h_is2.as<int32_t>();
-        }
-        (void)n_jobs;
+        });
     }
-    for (int i = 0; i < 2; i++) {
-        HGT_CHECK(b->h_em_args[i].alloc(hgt_em_args_bytes((int)nu)));
-        HGT_CHECK(b->d_em_args[i].alloc(hgt_em_args_bytes((int)nu)));
+    // ---- device buffers (from the context's pool) and the uploads ---------------------------------------------------
+    {
+        HostTimer ht(ctx, 5);
+        for (LocusBatch &lb : b->lb) {
+            if (lb.units.empty()) continue;
+            const hgt_locus *loc = lb.loc;
+            const int wp = loc->wp;
+            const size_t n_units = lb.units.size();
+            lb.cap = 64;
+            while ((int64_t)lb.cap < 2 * std::max<int64_t>(lb.n_rows_pool, 1)) lb.cap <<= 1;
+            HGT_CHECK(lb.d_jobs.alloc(lb.ja.bytes));
+            ctx->h2d_bytes += (int64_t)lb.ja.bytes;
+            HGT_CUDA(cudaMemcpyAsync(lb.d_jobs.p, lb.h_jobs.p, lb.ja.bytes, cudaMemcpyHostToDevice, st));
+            HGT_CHECK(lb.d_hapbits.alloc((size_t)std::max<int64_t>(lb.n_haps, 1) * wp * 8));
+            HGT_CHECK(lb.d_keys.alloc((size_t)lb.cap * 8));
+            HGT_CHECK(lb.d_slot.alloc((size_t)lb.cap * 4));
+            const size_t pr = (size_t)std::max<int64_t>(lb.n_rows_pool, 1);
+            HGT_CHECK(lb.d_bits.alloc(pr * wp * 8));
+            HGT_CHECK(lb.d_count.alloc(pr * 8));
+            HGT_CHECK(lb.d_first.alloc(pr * 4));
+            HGT_CHECK(lb.d_ut_ncls.alloc(n_units * 4 * 4));
+            // EM buffers (both levels; nothing is allocated after prepare)
+            const size_t A = (size_t)loc->A;
+            HGT_CHECK(lb.d_prob.alloc(n_units * A * 8));
+            HGT_CHECK(lb.d_inres.alloc(n_units * A));
+            HGT_CHECK(lb.d_fk.alloc(n_units * A * 4));
+            HGT_CHECK(lb.d_is.alloc(n_units * 12));
+            HGT_CHECK(lb.d_emws.alloc(n_units * hgt_em_problem_ws_bytes(wp)));
+            HGT_CHECK(lb.d_acount.alloc(n_units * A * 8));
+            HGT_CHECK(lb.d_afirst.alloc(n_units * A * 4));
+            HGT_CHECK(lb.h_ncls.alloc(n_units * 16));
+            HGT_CHECK(lb.h_prob.alloc(n_units * A * 8));
+            HGT_CHECK(lb.h_inres.alloc(n_units * A));
+            HGT_CHECK(lb.h_fk.alloc(n_units * A * 4));
+            HGT_CHECK(lb.h_is.alloc(n_units * 12));
+            lb.ut_ncls = lb.h_ncls.as<int32_t>(); lb.prob = lb.h_prob.as<double>(); lb.inres = lb.h_inres.as<uint8_t>();
+            lb.fk = lb.h_fk.as<int32_t>(); lb.is = lb.h_is.as<int32_t>();
+            memset(lb.ut_ncls, 0, n_units * 16);
+            for (int tb = 0; tb < 3; tb++) {
+                int n = 0;
+                for (int j = 0; j < wp; j++) n += __builtin_popcountll(loc->mask[(size_t)tb * wp + j]);
+                lb.n_live[tb] = n;
+            }
+            lb.n_live[3] = loc->A;
+            if (loc->is_hla) {
+                HGT_CHECK(lb.d_prob2.alloc(n_units * A * 8));
+                HGT_CHECK(lb.d_inres2.alloc(n_units * A));
+                HGT_CHECK(lb.d_fk2.alloc(n_units * A * 4));
+                HGT_CHECK(lb.d_is2.alloc(n_units * 12));
+                HGT_CHECK(lb.d_keep.alloc(n_units * (size_t)wp * 8));
+                HGT_CHECK(lb.d_ulist.alloc(n_units * 4));
+                HGT_CHECK(lb.h_prob2.alloc(n_units * A * 8));
+                HGT_CHECK(lb.h_inres2.alloc(n_units * A));
+                HGT_CHECK(lb.h_fk2.alloc(n_units * A * 4));
+                HGT_CHECK(lb.h_is2.alloc(n_units * 12));
+                HGT_CHECK(lb.h_keep.alloc(n_units * (size_t)wp * 8));
+                HGT_CHECK(lb.h_ulist.alloc(n_units * 4));
+                lb.prob2 = lb.h_prob2.as<double>(); lb.inres2 = lb.h_inres2.as<uint8_t>();
+                lb.fk2 = lb.h_fk2.as<int32_t>(); lb.is2 = lb.h_is2.as<int32_t>();
+            }
+        }
+        for (int i = 0; i < 2; i++) {
+            HGT_CHECK(b->h_em_args[i].alloc(hgt_em_args_bytes((int)nu)));
+            HGT_CHECK(b->d_em_args[i].alloc(hgt_em_args_bytes((int)nu)));
+        }
+        HGT_CUDA(cudaStreamSynchronize(st));
     }
-    HGT_CUDA(cudaStreamSynchronize(st));
     b->prepared = true;
     return HGT_OK;
 }
@@ -1330,33 +1413,33 @@ static void launch_stage_a(hgt_batch *b, cudaStream_t st, LocusBatch &lb) {
     const hgt_locus *loc = lb.loc;
     const LocusDev ld = locus_dev(loc);
     const int wp = loc->wp;
-    const int64_t H = (int64_t)lb.hap_left.size();
+    const int64_t H = lb.n_haps;
     b->timer.begin(ctx, st, 1);
     if (H > 0) {
         const size_t smem = (size_t)std::max(ld.V, 1) * 4;
         cudaFuncSetAttribute(compat_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int ctas = (int)std::min<int64_t>((H + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 4);
-        compat_kernel<WPL><<<ctas, WARPS_PER_CTA * 32, smem, st>>>(ld, lb.d_ht.as<int32_t>(), lb.d_hl.as<int32_t>(),
-                                                                   lb.d_hr.as<int32_t>(), lb.d_ro.as<int64_t>(),
-                                                                   lb.d_rows.as<int32_t>(), H, lb.d_hapbits.as<uint64_t>());
+        compat_kernel<WPL><<<ctas, WARPS_PER_CTA * 32, smem, st>>>(ld, lb.dj<int32_t>(lb.ja.o_ht), lb.dj<int32_t>(lb.ja.o_hl),
+                                                                   lb.dj<int32_t>(lb.ja.o_hr), lb.dj<int64_t>(lb.ja.o_row_off),
+                                                                   lb.dj<int32_t>(lb.ja.o_rows), H, lb.d_hapbits.as<uint64_t>());
         ctx->launches++;
     }
     b->timer.end(H > 0 ? 1 : 0);
     const ClassPool pool = lb.pool();
-    const int64_t ns = (int64_t)lb.job_small.size(), nb = (int64_t)lb.job_big.size();
+    const int64_t ns = lb.n_small, nb = lb.n_big;
     b->timer.begin(ctx, st, 2);
     if (ns > 0) {
         const int ctas = (int)std::min<int64_t>((ns + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 8);
-        class_kernel<WPL, 3><<<ctas, WARPS_PER_CTA * 32, 0, st>>>(wp, loc->d_mask, lb.d_job_off.as<int64_t>(),
-                                                                  lb.d_job_ut.as<int32_t>(), lb.d_job_pair.as<int32_t>(),
-                                                                  lb.d_job_list.as<int32_t>(), ns, lb.d_hapbits.as<uint64_t>(), pool);
+        class_kernel<WPL, 3><<<ctas, WARPS_PER_CTA * 32, 0, st>>>(wp, loc->d_mask, lb.dj<int64_t>(lb.ja.o_job_off),
+                                                                  lb.dj<int32_t>(lb.ja.o_job_ut), lb.dj<int32_t>(lb.ja.o_job_pair),
+                                                                  lb.dj<int32_t>(lb.ja.o_job_list), ns, lb.d_hapbits.as<uint64_t>(), pool);
         ctx->launches++;
     }
     if (nb > 0) {
         const int ctas = (int)std::min<int64_t>((nb + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 8);
-        class_kernel<WPL, 8><<<ctas, WARPS_PER_CTA * 32, 0, st>>>(wp, loc->d_mask, lb.d_job_off.as<int64_t>(),
-                                                                  lb.d_job_ut.as<int32_t>(), lb.d_job_pair.as<int32_t>(),
-                                                                  lb.d_job_list.as<int32_t>() + ns, nb, lb.d_hapbits.as<uint64_t>(), pool);
+        class_kernel<WPL, 8><<<ctas, WARPS_PER_CTA * 32, 0, st>>>(wp, loc->d_mask, lb.dj<int64_t>(lb.ja.o_job_off),
+                                                                  lb.dj<int32_t>(lb.ja.o_job_ut), lb.dj<int32_t>(lb.ja.o_job_pair),
+                                                                  lb.dj<int32_t>(lb.ja.o_job_list) + ns, nb, lb.d_hapbits.as<uint64_t>(), pool);
         ctx->launches++;
     }
     b->timer.end((ns > 0) + (nb > 0));
@@ -1464,6 +1547,7 @@ static int batch_finish(hgt_batch *b, cudaStream_t st) {
     }
     HGT_CUDA(cudaStreamSynchronize(st));
     b->timer.resolve();
+    HostTimer ht_finish(ctx, 6);
     std::vector<EmDevProblem> probs;
     for (LocusBatch &lb : b->lb) {
         lb.n_level2 = 0;
@@ -1475,6 +1559,8 @@ static int batch_finish(hgt_batch *b, cudaStream_t st) {
         int32_t *ulist = lb.h_ulist.as<int32_t>();
         uint64_t *keep = lb.h_keep.as<uint64_t>();
         lb.has2.assign(n_units, 0);
+        lb.slot2.assign(n_units, -1);
+        lb.exon_prob_sum.assign(n_units, 0.0);
         std::vector<int> order, lu, cmax, alive;
         for (size_t i = 0; i < n_units; i++) {
             if (lb.is[i * 3 + 1] != HGT_OK) continue;
@@ -1492,11 +1578,13 @@ static int batch_finish(hgt_batch *b, cudaStream_t st) {
             uint64_t *m = keep + (size_t)lb.n_level2 * wp;
             memset(m, 0, (size_t)wp * 8);
             bool any = false;
+            double psum = 0.0;
             for (size_t r = 0; r < order.size(); r++) {
                 const int a = order[r];
                 if (r >= 10 && p[a] < 0.03) break;
                 if (loc->group_off[a + 1] - loc->group_off[a] <= 1) continue;
                 any = true;
+                psum += p[a];
                 for (int64_t g = loc->group_off[a]; g < loc->group_off[a + 1]; g++) {
                     const int mem = loc->group_member[g];
                     m[mem >> 6] |= 1ull << (mem & 63);
@@ -1504,6 +1592,8 @@ static int batch_finish(hgt_batch *b, cudaStream_t st) {
             }
             if (!any) continue;
             lb.has2[i] = 1;
+            lb.slot2[i] = lb.n_level2;
+            lb.exon_prob_sum[i] = psum;
             ulist[lb.n_level2++] = (int32_t)i;
             lu.push_back((int)i);
             cmax.push_back(lb.ut_ncls[i * 4 + 0]);  // a projection never has more classes than its source
@@ -1531,7 +1621,7 @@ static int batch_finish(hgt_batch *b, cudaStream_t st) {
             HGT_CUDA(cudaGetLastError());
         }
         HGT_CUDA(cudaMemsetAsync(lb.d_is2.p, 0, n_units * 12, st));
-        em_problems(lb, 3, lu, cmax.data(), alive.data(), lb.d_len.as<double>(), 1, lb.d_prob2, lb.d_inres2, lb.d_fk2, lb.d_is2,
+        em_problems(lb, 3, lu, cmax.data(), alive.data(), loc->d_allele_len, 1, lb.d_prob2, lb.d_inres2, lb.d_fk2, lb.d_is2,
                     &probs);
     }
     if (!probs.empty()) {
@@ -1644,11 +1734,11 @@ extern "C" int hgt_batch_totals(const hgt_batch *b, int64_t *n_units, int64_t *n
     }
     for (const LocusBatch &lb : b->lb) {
         if (lb.units.empty()) continue;
-        h += (int64_t)lb.hap_left.size();
-        rows += (int64_t)lb.rows.size();
+        h += lb.n_haps;
+        rows += lb.n_rows;
         const int n_tables = lb.loc->is_hla ? 3 : 1;
         // per pair S_rec + T * wp * 8, S_rec = packed haplotype records actually read
-        bytes += (int64_t)lb.hap_left.size() * 12 + (int64_t)lb.rows.size() * 4 + (int64_t)lb.job_ut.size() * 16;
+        bytes += lb.n_haps * 12 + lb.n_rows * 4 + lb.n_jobs * 16;
         for (int u : lb.units) bytes += b->units[u].ho.num_pairs * (int64_t)n_tables * lb.loc->wp * 8;
     }
     if (n_units) *n_units = (int64_t)b->units.size();
@@ -1785,6 +1875,52 @@ extern "C" int hgt_batch_unit_em(const hgt_batch *b, int64_t unit, int32_t level
     return HGT_OK;
 }
 
+// Gene_prob of one unit, ranked: the combination rule of core:1771-1782 on the hla path (first-level entries
+// outside exon_alleles, then second-level entries scaled by exon_prob_sum, stable sort by probability), the plain
+// EM result otherwise.  Writes at most `cap` entries; *n_total receives the full length.
+extern "C" int hgt_batch_unit_abundance(const hgt_batch *b, int64_t unit, int32_t cap, int32_t *allele, double *prob,
+                                        int32_t *n_total) {
+    HGT_CHECK(unit_check(b, unit, true));
+    const UnitHost &U = b->units[unit];
+    const LocusBatch &lb = b->lb[U.locus];
+    const hgt_locus *loc = lb.loc;
+    const size_t A = (size_t)loc->A, o = (size_t)U.local * A;
+    const int st1 = lb.is[(size_t)U.local * 3 + 1];
+    if (st1 != HGT_OK) return st1;
+    struct Ent { int32_t a; double p; int32_t fk; };
+    auto ranked = [&](const double *p, const uint8_t *in, const int32_t *fk, std::vector<Ent> *out) {
+        out->clear();
+        for (int a = 0; a < (int)A; a++)
+            if (in[a]) out->push_back({a, p[a], fk[a]});
+        std::sort(out->begin(), out->end(), [](const Ent &x, const Ent &y) {
+            if (x.p != y.p) return x.p > y.p;
+            if (x.fk != y.fk) return x.fk < y.fk;
+            return x.a < y.a;
+        });
+    };
+    std::vector<Ent> first, second, comb;
+    ranked(lb.prob + o, lb.inres + o, lb.fk + o, &first);
+    const bool two = loc->is_hla && !lb.has2.empty() && lb.has2[U.local];
+    if (!two) {
+        comb.swap(first);
+    } else {
+        const int st2 = lb.is2[(size_t)U.local * 3 + 1];
+        if (st2 != HGT_OK) return st2;
+        ranked(lb.prob2 + o, lb.inres2 + o, lb.fk2 + o, &second);
+        const uint64_t *keep = lb.h_keep.as<uint64_t>() + (size_t)lb.slot2[U.local] * loc->wp;
+        for (const Ent &e : first)
+            if (!((keep[e.a >> 6] >> (e.a & 63)) & 1ull)) comb.push_back(e);
+        for (const Ent &e : second) comb.push_back({e.a, e.p * lb.exon_prob_sum[U.local], 0});
+        std::stable_sort(comb.begin(), comb.end(), [](const Ent &x, const Ent &y) { return x.p > y.p; });
+    }
+    if (n_total) *n_total = (int32_t)comb.size();
+    for (int32_t k = 0; k < cap && k < (int32_t)comb.size(); k++) {
+        if (allele) allele[k] = comb[k].a;
+        if (prob) prob[k] = comb[k].p;
+    }
+    return HGT_OK;
+}
+
 // ================================================================================================================
 // C ABI: single (sample, locus) — a batch of one unit
 // ================================================================================================================
@@ -1836,7 +1972,7 @@ extern "C" int hgt_typing_pileup(const hgt_typing *t, uint32_t *counts, uint8_t 
     if (!t) return HGT_ERR_ARG;
     const UnitHost &U = t->batch->units[0];
     if (counts) memcpy(counts, U.counts.data(), U.counts.size() * 4);
-    if (nt_mask) memcpy(nt_mask, U.nt_mask.data(), U.nt_mask.size());
+    if (nt_mask && U.nt_mask) memcpy(nt_mask, U.nt_mask, (size_t)t->batch->loci[U.locus]->L);
     return HGT_OK;
 }
 

@@ -42,6 +42,7 @@ struct AltEntry {
     int32_t anchor = 0;  // last token (left table) / first token (right table)
     std::string key;     // "529-hv8-hv22-606"
     std::vector<std::string> toks;
+    std::vector<int32_t> tok_rows;  // row of every token that is a variant id of the locus, else -1
     std::vector<AltHap> alts;
 };
 
@@ -53,6 +54,76 @@ struct LocusHost {
     std::vector<std::pair<int32_t, int32_t>> exons, primary_exons;
     std::vector<AltEntry> alts_left, alts_right;  // sorted by anchor
     bool is_hla = false;
+    // acceleration tables built by finalize(): anchors of Alts_left / Alts_right below each position, and whether
+    // every variant id is "<letters><digits>" with one common letter prefix (then the reference's substring test on
+    // '-'-joined ids, common:1734/1856, is a token comparison: all but the last id equal, the last one a prefix)
+    std::vector<int32_t> altl_below, altr_below;  // [ref+2] number of anchors < p
+    bool simple_ids = false;
+    std::string id_prefix;
+    std::vector<int32_t> row_by_num;  // simple ids: row of "<prefix><n>" or -1
+    void finalize() {
+        const int32_t n = (int32_t)ref.size();
+        auto below = [&](const std::vector<AltEntry> &v, std::vector<int32_t> *out) {
+            out->assign(n + 2, 0);
+            std::vector<int32_t> cnt(n + 2, 0);
+            for (const AltEntry &e : v) cnt[std::min(std::max(e.anchor, 0), n)]++;
+            int32_t run = 0;
+            for (int32_t p = 0; p <= n + 1; p++) {
+                (*out)[p] = run;
+                if (p <= n) run += cnt[p];
+            }
+        };
+        below(alts_left, &altl_below);
+        below(alts_right, &altr_below);
+        simple_ids = !vars.empty();
+        id_prefix.clear();
+        int64_t max_num = -1;
+        for (size_t i = 0; i < vars.size() && simple_ids; i++) {
+            const std::string &id = vars[i].id;
+            size_t k = 0;
+            while (k < id.size() && ((id[k] >= 'a' && id[k] <= 'z') || (id[k] >= 'A' && id[k] <= 'Z'))) k++;
+            if (k == 0 || k == id.size() || id.size() - k > 9) { simple_ids = false; break; }
+            for (size_t j = k; j < id.size(); j++)
+                if (id[j] < '0' || id[j] > '9') simple_ids = false;
+            if (id.size() > k + 1 && id[k] == '0') simple_ids = false;  // leading zeros would alias numbers
+            if (i == 0) id_prefix = id.substr(0, k);
+            else if (id.compare(0, k, id_prefix) != 0 || k != id_prefix.size()) simple_ids = false;
+            if (simple_ids) max_num = std::max<int64_t>(max_num, atoll(id.c_str() + k));
+        }
+        row_by_num.clear();
+        if (simple_ids && max_num <= 50000000) {
+            row_by_num.assign((size_t)max_num + 1, -1);
+            for (size_t i = 0; i < vars.size(); i++) row_by_num[atoll(vars[i].id.c_str() + id_prefix.size())] = (int32_t)i;
+        } else {
+            simple_ids = false;
+        }
+        for (std::vector<AltEntry> *tab : {&alts_left, &alts_right})
+            for (AltEntry &e : *tab) {
+                e.tok_rows.assign(e.toks.size(), -1);
+                for (size_t t = 0; t < e.toks.size(); t++) {
+                    auto f = row_of.find(e.toks[t]);
+                    if (f != row_of.end()) e.tok_rows[t] = f->second;
+                }
+            }
+    }
+    // row of a variant id given as characters (Zs tag), -3 when it is not a variant of this locus
+    int32_t row_of_chars(const char *p, size_t n) const {
+        if (simple_ids) {
+            const size_t k = id_prefix.size();
+            if (n <= k || n - k > 9 || memcmp(p, id_prefix.data(), k) != 0) return -3;
+            if (n > k + 1 && p[k] == '0') return -3;
+            int64_t v = 0;
+            for (size_t j = k; j < n; j++) {
+                if (p[j] < '0' || p[j] > '9') return -3;
+                v = v * 10 + (p[j] - '0');
+            }
+            if (v >= (int64_t)row_by_num.size()) return -3;
+            const int32_t r = row_by_num[(size_t)v];
+            return r < 0 ? -3 : r;
+        }
+        auto f = row_of.find(std::string(p, n));
+        return f == row_of.end() ? -3 : f->second;
+    }
     int32_t lower_bound(int32_t pos) const {
         return (int32_t)(std::lower_bound(var_pos.begin(), var_pos.end(), pos) - var_pos.begin());
     }
@@ -310,8 +381,7 @@ inline bool walk_record(const LocusHost &L, const Record &r, const PileupView &p
             ZsItem it;
             if (!parse_int(p, (int)(b1 - p), &it.off)) return fail("malformed Zs offset");
             it.kind = b1[1];
-            auto f = L.row_of.find(std::string(b2 + 1, q - b2 - 1));
-            it.row = f == L.row_of.end() ? -3 : f->second;
+            it.row = L.row_of_chars(b2 + 1, (size_t)(q - b2 - 1));
             zs.push_back(it);
             p = q + 1;
         }
@@ -457,7 +527,36 @@ inline int32_t alt_lower_bound(const std::vector<AltEntry> &v, int32_t pos) {
     return lo;
 }
 
-inline bool identify_ambiguous_diffs(const LocusHost &L, const std::vector<Cmp> &c2, Ambig *out, WalkError *err) {
+// Scratch that survives across reads (no per-read allocation in the common case).
+struct AmbigScratch {
+    std::vector<int32_t> all_ids, idn, nov, sl;
+};
+
+// Does the '-'-joined id string of `ids` occur inside the entry's key (common:1734, 1856)?
+inline bool key_contains_ids(const LocusHost &L, const AltEntry &a, const int32_t *ids, size_t m) {
+    if (L.simple_ids) {
+        const size_t T = a.tok_rows.size();
+        if (m > T) return false;
+        const std::string &last = L.vars[ids[m - 1]].id;
+        for (size_t t = 0; t + m <= T; t++) {
+            bool ok = true;
+            for (size_t k = 0; k + 1 < m && ok; k++) ok = a.tok_rows[t + k] == ids[k];
+            if (!ok) continue;
+            const std::string &kt = a.toks[t + m - 1];
+            if (kt.size() >= last.size() && memcmp(kt.data(), last.data(), last.size()) == 0) return true;
+        }
+        return false;
+    }
+    std::string joined;
+    for (size_t i = 0; i < m; i++) {
+        if (i) joined += '-';
+        joined += L.vars[ids[i]].id;
+    }
+    return a.key.find(joined) != std::string::npos;
+}
+
+inline bool identify_ambiguous_diffs(const LocusHost &L, const std::vector<Cmp> &c2, Ambig *out, WalkError *err,
+                                     AmbigScratch *sc) {
     const int32_t n = (int32_t)c2.size();
     out->cmp_left = 0;
     out->cmp_right = n - 1;
@@ -466,38 +565,45 @@ inline bool identify_ambiguous_diffs(const LocusHost &L, const std::vector<Cmp> 
     const int32_t left = c2[0].pos, right = c2[n - 1].pos + c2[n - 1].len - 1;
     const int32_t reflen = (int32_t)L.ref.size();
     auto id_is_hv = [&](const Cmp &e) { return e.var >= 0 && L.vars[e.var].is_hv; };
-    // ids / sequence length of a slice (get_haplotype_and_seq, common:1679-1700)
-    auto ids_and_len = [&](int32_t lo, int32_t hi, std::vector<int32_t> *ids, bool *has_novel, int32_t *seqlen) {
-        ids->clear();
-        *has_novel = false;
-        *seqlen = 0;
-        for (int32_t i = lo; i < hi; i++) {
+    // prefix sums over the entries: known ids, novel ids and sequence length of c2[0..i)
+    // (get_haplotype_and_seq, common:1679-1700)
+    bool prefix_ready = false;
+    auto build_prefix = [&]() {
+        if (prefix_ready) return;
+        prefix_ready = true;
+        sc->all_ids.clear();
+        sc->idn.assign(n + 1, 0);
+        sc->nov.assign(n + 1, 0);
+        sc->sl.assign(n + 1, 0);
+        for (int32_t i = 0; i < n; i++) {
             const Cmp &e = c2[i];
+            int32_t len = 0;
             if (e.type == C_MATCH) {
                 const int32_t a = std::min(std::max(e.pos, 0), reflen), b = std::min(std::max(e.pos + e.len, 0), reflen);
-                *seqlen += std::max(0, b - a);
+                len = std::max(0, b - a);
             } else if (e.type == C_MISMATCH) {
-                *seqlen += 1;
+                len = 1;
             }
+            int32_t novel = 0;
             if (e.type != C_MATCH && e.var != VAR_UNKNOWN) {
-                if (e.var >= 0) ids->push_back(e.var);
-                else *has_novel = true;
+                if (e.var >= 0) sc->all_ids.push_back(e.var);
+                else novel = 1;
             }
+            sc->idn[i + 1] = (int32_t)sc->all_ids.size();
+            sc->nov[i + 1] = sc->nov[i] + novel;
+            sc->sl[i + 1] = sc->sl[i] + len;
         }
-    };
-    auto join_ids = [&](const std::vector<int32_t> &ids) {
-        std::string s;
-        for (size_t i = 0; i < ids.size(); i++) {
-            if (i) s += '-';
-            s += L.vars[ids[i]].id;
-        }
-        return s;
     };
     auto hv_between = [&](int32_t lo, int32_t hi, std::vector<int32_t> *ids) {
         for (int32_t j = lo; j < hi; j++)
             if (c2[j].type != C_MATCH && id_is_hv(c2[j])) ids->push_back(c2[j].var);
     };
-    std::vector<int32_t> cur_ids;
+    // any anchor of the table inside [lo, hi]?  (conservative outside the backbone)
+    auto any_anchor = [&](const std::vector<int32_t> &below, int32_t lo, int32_t hi) {
+        if (lo < 0 || hi >= reflen) return true;
+        if (hi < lo) return false;
+        return below[hi + 1] - below[lo] > 0;
+    };
     // ---- left end ------------------------------------------------------------------------------------------
     bool found = false;
     if (!L.alts_left.empty()) {
@@ -508,6 +614,7 @@ inline bool identify_ambiguous_diffs(const LocusHost &L, const std::vector<Cmp> 
             }
             const int32_t cur_left = e.pos;
             const int32_t cur_right = (e.type == C_MATCH || e.type == C_DELETION) ? e.pos + e.len - 1 : e.pos;
+            if (!any_anchor(L.altl_below, cur_left, cur_right)) continue;
             const int32_t start = std::min(alt_lower_bound(L.alts_left, cur_right + 1) + 1, (int32_t)L.alts_left.size());
             bool candidates = false;
             for (int32_t j = start - 1; j >= 0; j--) {
@@ -518,29 +625,30 @@ inline bool identify_ambiguous_diffs(const LocusHost &L, const std::vector<Cmp> 
                 }
             }
             if (!candidates) continue;
-            bool has_novel;
-            int32_t cur_len;
-            ids_and_len(0, i + 1, &cur_ids, &has_novel, &cur_len);
-            const std::string joined = has_novel ? std::string() : join_ids(cur_ids);
-            const size_t n_ids = cur_ids.size() + (has_novel ? 1 : 0);  // novel ids count as ids that never match
+            build_prefix();
+            const bool has_novel = sc->nov[i + 1] > 0;
+            const int32_t cur_len = sc->sl[i + 1];
+            const int32_t *cur_ids = sc->all_ids.data();
+            const size_t n_cur = (size_t)sc->idn[i + 1];
+            const size_t n_ids = n_cur + (has_novel ? 1 : 0);  // novel ids count as ids that never match
             bool hit = false;
             for (int32_t j = start - 1; j >= 0; j--) {
                 const AltEntry &a = L.alts_left[j];
                 if (a.anchor < cur_left) break;
                 if (a.anchor > cur_right) continue;
                 if (n_ids > 0) {
-                    if (has_novel || a.key.find(joined) == std::string::npos) continue;
+                    if (has_novel || !key_contains_ids(L, a, cur_ids, n_cur)) continue;
                 }
                 const int32_t ntok = (int32_t)a.toks.size() - 1;  // key.split('-')[:-1]
-                if ((int32_t)cur_ids.size() + 1 == ntok) {
+                if ((int32_t)n_cur + 1 == ntok) {
                     if (left < atoi(a.toks[0].c_str())) continue;
                 } else {
-                    int32_t k = ntok - (int32_t)cur_ids.size() - 1;
+                    int32_t k = ntok - (int32_t)n_cur - 1;
                     if (k < 0) k += ntok;  // Python negative index
                     if (k < 0 || k >= ntok) { err->code = -6; err->msg = "alt haplotype index out of range"; return false; }
-                    auto f = L.row_of.find(a.toks[k]);
-                    if (f == L.row_of.end()) { err->code = -6; err->msg = "alt haplotype token is not a variant"; return false; }
-                    if (left <= L.vars[f->second].right()) continue;
+                    const int32_t row = a.tok_rows[k];
+                    if (row < 0) { err->code = -6; err->msg = "alt haplotype token is not a variant"; return false; }
+                    if (left <= L.vars[row].right()) continue;
                 }
                 hit = true;
                 for (const AltHap &alt : a.alts) {
@@ -575,7 +683,7 @@ inline bool identify_ambiguous_diffs(const LocusHost &L, const std::vector<Cmp> 
                     // cur_ht_str; a hit implies the slice holds no novel id (the substring test would fail)
                     AltSide s;
                     s.pos = left;
-                    s.ids = cur_ids;
+                    s.ids.assign(cur_ids, cur_ids + n_cur);
                     add_unique(out->left, std::move(s));
                 }
                 found = true;
@@ -593,30 +701,32 @@ inline bool identify_ambiguous_diffs(const LocusHost &L, const std::vector<Cmp> 
             }
             const int32_t cur_left = e.pos;
             const int32_t cur_right = (e.type == C_MATCH || e.type == C_DELETION) ? e.pos + e.len - 1 : e.pos;
+            if (!any_anchor(L.altr_below, cur_left, cur_right)) continue;
             const int32_t start = alt_lower_bound(L.alts_right, cur_left);
             if (start >= (int32_t)L.alts_right.size() || L.alts_right[start].anchor > cur_right) continue;
-            bool has_novel;
-            int32_t cur_len;
-            ids_and_len(i, n, &cur_ids, &has_novel, &cur_len);
-            const std::string joined = has_novel ? std::string() : join_ids(cur_ids);
-            const size_t n_ids = cur_ids.size() + (has_novel ? 1 : 0);
+            build_prefix();
+            const bool has_novel = sc->nov[n] - sc->nov[i] > 0;
+            const int32_t cur_len = sc->sl[n] - sc->sl[i];
+            const int32_t *cur_ids = sc->all_ids.data() + sc->idn[i];
+            const size_t n_cur = (size_t)(sc->idn[n] - sc->idn[i]);
+            const size_t n_ids = n_cur + (has_novel ? 1 : 0);
             bool hit = false;
             for (int32_t j = start; j < (int32_t)L.alts_right.size(); j++) {
                 const AltEntry &a = L.alts_right[j];
                 if (a.anchor > cur_right) break;
                 if (a.anchor < cur_left) continue;
                 if (n_ids > 0) {
-                    if (has_novel || a.key.find(joined) == std::string::npos) continue;
+                    if (has_novel || !key_contains_ids(L, a, cur_ids, n_cur)) continue;
                 }
                 const int32_t ntok = (int32_t)a.toks.size() - 1;  // key.split('-')[1:]
-                if ((int32_t)cur_ids.size() + 1 == ntok) {
+                if ((int32_t)n_cur + 1 == ntok) {
                     if (right > atoi(a.toks[ntok].c_str())) continue;
                 } else {
-                    const int32_t k = (int32_t)cur_ids.size();
+                    const int32_t k = (int32_t)n_cur;
                     if (k >= ntok) { err->code = -6; err->msg = "alt haplotype index out of range"; return false; }
-                    auto f = L.row_of.find(a.toks[1 + k]);
-                    if (f == L.row_of.end()) { err->code = -6; err->msg = "alt haplotype token is not a variant"; return false; }
-                    if (right >= L.vars[f->second].pos) continue;
+                    const int32_t row = a.tok_rows[1 + k];
+                    if (row < 0) { err->code = -6; err->msg = "alt haplotype token is not a variant"; return false; }
+                    if (right >= L.vars[row].pos) continue;
                 }
                 hit = true;
                 for (const AltHap &alt : a.alts) {
@@ -649,7 +759,7 @@ inline bool identify_ambiguous_diffs(const LocusHost &L, const std::vector<Cmp> 
                     out->cmp_right = i - 1;
                     AltSide s;
                     s.pos = right;
-                    s.ids = cur_ids;
+                    s.ids.assign(cur_ids, cur_ids + n_cur);
                     add_unique(out->right, std::move(s));
                 }
                 found = true;

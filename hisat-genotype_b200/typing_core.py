@@ -295,6 +295,31 @@ class Batch:
             combined[allele] = prob * exon_prob_sum
         return sorted(([a, p] for a, p in combined.items()), key=lambda x: x[1], reverse=True)
 
+    def unit_calls(self, u, max_n=None):
+        """Gene_prob of the unit ranked natively (same result as unit_abundance); max_n limits the list length."""
+        t = self.loci[self.unit_locus[u]]
+        if not t.is_hla:
+            nc = self.unit_summary(u)["n_classes"][TABLE_GENE]
+            if nc <= 1:
+                if nc == 1:
+                    raise TypeError("'dict_keys' object is not subscriptable")  # core:1787 on Python 3
+                return []
+        cap = t.A if max_n is None else int(max_n)
+        idx = np.zeros(max(cap, 1), np.int32)
+        prob = np.zeros(max(cap, 1), np.float64)
+        n = ctypes.c_int32(0)
+        rc = lib().hgt_batch_unit_abundance(self.handle, u, cap, _lib.ptr(idx), _lib.ptr(prob), ctypes.byref(n))
+        if rc == _lib.HGT_ERR_KEY:
+            raise KeyError("allele vanished from next_prob output during SQUAREM step")
+        if rc == _lib.HGT_ERR_ZERODIV:
+            raise ZeroDivisionError("float division by zero")
+        _lib.check(rc)
+        k = min(cap, n.value)
+        return [[t.names[int(idx[i])], float(prob[i])] for i in range(k)]
+
+    def top_calls(self, max_n=2):
+        return [self.unit_calls(u, max_n) for u in range(len(self.unit_locus))]
+
     def close(self):
         if self.handle is not None and self.handle.value:
             lib().hgt_batch_free(self.handle)

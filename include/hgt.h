@@ -60,6 +60,9 @@ void hgt_profile_enable(hgt_ctx *ctx, int on);
 void hgt_profile_reset(hgt_ctx *ctx);
 void hgt_profile_read(const hgt_ctx *ctx, double *stage_ms, int64_t *stage_launches, int64_t *h2d_bytes,
                       int64_t *d2h_bytes);
+/* wall-clock milliseconds the host stages of prepare/finish took since the last reset, host_ms[8]: record intake,
+ * pileup packing, pileup kernels + wait, walk, job packing, uploads + allocation, finish-side host work, unused */
+void hgt_profile_host(const hgt_ctx *ctx, double *host_ms);
 
 /* ---- stage (b): EM abundance ----------------------------------------------------------------------------
  * Replaces single_abundance(Gene_cmpt, remove_low_abundance_allele, Gene_length)
@@ -191,6 +194,12 @@ int hgt_batch_unit_table(hgt_batch *b, int64_t unit, int32_t table, uint64_t *cl
 /* level 0: first-level EM; level 1: second-level EM (status 1 = not run for this unit, core:1752) */
 int hgt_batch_unit_em(const hgt_batch *b, int64_t unit, int32_t level, double *prob, uint8_t *in_result,
                       int32_t *first_class, int32_t *iters, int32_t *status);
+
+/* Gene_prob of one unit as typing() ranks it (core:1771-1782 on the hla path, core:1789 otherwise): allele indices and
+ * probabilities in report order; at most cap entries are written, *n_total is the full length.  Returns the EM
+ * status of the unit (HGT_ERR_KEY / HGT_ERR_ZERODIV mirror the reference's exceptions). */
+int hgt_batch_unit_abundance(const hgt_batch *b, int64_t unit, int32_t cap, int32_t *allele, double *prob,
+                             int32_t *n_total);
 
 /* Host-only half of stage (a) with a caller-supplied pileup (no GPU needed): intake, filters, walk, error
  * correction, ambiguity expansion, exon clipping.  Output is the job list the GPU consumes, flattened:

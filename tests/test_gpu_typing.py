@@ -137,7 +137,10 @@ def test_batch_matches_reference(name):
             assert [a for a, _ in res] == [a for a, _ in ref]
             for (_, x), (_, y) in zip(res, ref):
                 assert x == pytest.approx(y, rel=1e-6, abs=1e-12)
-        assert len(batch.unit_abundance(u)) > 0
+        ab = batch.unit_abundance(u)
+        assert len(ab) > 0
+        assert batch.unit_calls(u) == ab  # native ranking == Python combination rule (core:1771-1782)
+        assert batch.unit_calls(u, 2) == ab[:2]
     assert em_i == len(g["em_calls"])
     # repeat execute+finish on the prepared batch: identical tables (pools are reset)
     batch.execute()
