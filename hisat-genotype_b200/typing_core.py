@@ -332,6 +332,134 @@ class Batch:
             pass
 
 
+def typing_from_alignments(base_fname, locus_tables, locus_list, alignments, simulation, num_editdist=2,
+                           error_correction=True, allow_discordant=False, remove_low_abundance_alleles=True,
+                           best_alleles=False, output_allele_counts=False, aligner="hisat2", index_type="graph",
+                           base_locus=0, device=None):
+    """The part of typing() between the alignment files and the report, for index_type == "graph"
+    (reference hisatgenotype_typing_core.py:336-343, 370-2142 minus assembly).
+
+    locus_tables  {gene: LocusTables}
+    locus_list    as typing() receives it: gene names, or in simulation mode the lists of truth alleles
+                  (gene = names[0].split('*')[0], core:380-383)
+    alignments    {gene: alignment lines in `samtools view <bam> <backbone> | sort -k1,1 -s` order (core:458-468)}
+    Returns (report body text starting at the aligner line, test_passed dict of the simulation mode)."""
+    from . import report
+    assert index_type == "graph", "the linear-index branch (core:1597-1648) stays on the reference path"
+    genes, truths = [], []
+    for entry in locus_list:
+        if simulation:
+            genes.append(entry[0].split("*")[0])
+            truths.append(list(entry))
+        else:
+            genes.append(entry)
+            truths.append([])
+    uniq = []
+    for g in genes:
+        if g not in uniq:
+            uniq.append(g)
+    batch = Batch([locus_tables[g] for g in uniq],
+                  make_params(num_editdist, error_correction, allow_discordant, simulation, base_locus),
+                  remove_low_abundance_alleles, device=device)
+    try:
+        for g in genes:
+            batch.add_unit(uniq.index(g), alignments[g])
+        batch.run()
+        text = [report.aligner_line(aligner, index_type)]
+        test_passed = {}
+        for u, g in enumerate(genes):
+            summ = batch.unit_summary(u)
+            if summ["num_reads"] <= 0:
+                continue
+            block, success = report.locus_block(summ["num_reads"], summ["num_pairs"], batch.unit_gene_counts(u, TABLE_GENE),
+                                                batch.unit_calls(u), simulation, truths[u], output_allele_counts,
+                                                best_alleles)
+            text.append(block)
+            for ok in success:
+                if ok:
+                    key = "%s %s" % (aligner, index_type)
+                    test_passed[key] = test_passed.get(key, 0) + 1
+    finally:
+        batch.close()
+    return "".join(text), test_passed
+
+
+def typing(simulation, full_path_base_fname, locus_list, genotype_genome, partial, partial_alleles, refGenes, Genes,
+           Gene_names, Gene_lengths, refGene_loci, Vars, Var_list, Links, aligners, num_editdist, assembly, output_base,
+           error_correction, keep_alignment, allow_discordant, type_primary_exons, remove_low_abundance_alleles,
+           display_alleles, fastq, read_fname, alignment_fname, num_frag_list, read_len, fragment_len, threads,
+           best_alleles, verbose, assembly_verbose, out_dir, dbversion, output_allele_counts, test_i=0):
+    """Drop-in for the reference's typing() (core:249-2171) on the contracted path: graph index, no assembly, not the
+    genotype-genome / CODIS branches.  Alignment itself stays on the reference path (its own align_reads + samtools);
+    everything between the alignment file and the report runs through libhgt on the GPU."""
+    import os
+    import subprocess
+    import sys
+
+    from . import report
+    if assembly or genotype_genome != "":
+        raise NotImplementedError("--assembly and genotype-genome typing stay on the reference path")
+    import hisatgenotype_typing_common as ref_common  # the reference module: alignment is not re-implemented
+    base_fname = full_path_base_fname.split("/")[-1]
+    if base_fname == "codis":
+        raise NotImplementedError("CODIS pair-distance logic stays on the reference path")
+    report_base = "%s/%s-%s." % (out_dir, output_base, base_fname)
+    if simulation:
+        core_fid = str(test_i + 1)
+        report_base += "test-"
+    else:
+        core_fid = "_".join(read_fname[0].split("/")[-1].split(".")[:-1])
+    report_base += core_fid
+    version_dir = "/".join(os.path.dirname(ref_common.__file__).split("/")[:-1])
+    hg_version = open(version_dir + "/VERSION").read()
+    h2_version = open(version_dir + "/hisat2/VERSION").read()
+    out = [report.header(h2_version, hg_version, dbversion, " ".join(sys.argv))]
+    test_passed = {}
+    tables = {}
+    for aligner, index_type in aligners:
+        if index_type != "graph":
+            raise NotImplementedError("linear-index typing stays on the reference path")
+        remove_alignment_file = False
+        aln = alignment_fname
+        if aln == "":
+            remove_alignment_file = True
+            aln = "%s_output.bam" % base_fname if simulation else "%s.bam" % core_fid
+            ref_common.align_reads(aligner, simulation, full_path_base_fname + "." + index_type, index_type, base_fname,
+                                   read_fname, fastq, threads, aln, verbose)
+        alignments = {}
+        for entry in locus_list:
+            gene = entry[0].split("*")[0] if simulation else entry
+            if gene in alignments:
+                continue
+            if gene not in tables:
+                ref_allele = refGenes[gene]
+                loc = refGene_loci[gene]
+                tables[gene] = LocusTables(base_fname, gene, ref_allele, Genes[gene][ref_allele], Vars[gene], Var_list[gene],
+                                           Links, Gene_names[gene], Gene_lengths[gene], loc[-2], loc[-1])
+            if not os.path.exists(aln + ".bai"):
+                os.system("samtools index %s" % aln)
+            view = subprocess.Popen(["samtools", "view", aln, refGenes[gene]], stdout=subprocess.PIPE,
+                                    stderr=subprocess.DEVNULL)
+            srt = subprocess.Popen(["sort", "-k", "1,1", "-s"], stdin=view.stdout, stdout=subprocess.PIPE,
+                                   stderr=subprocess.DEVNULL)
+            alignments[gene] = srt.communicate()[0]
+        body, passed = typing_from_alignments(base_fname, tables, locus_list, alignments, simulation, num_editdist,
+                                              error_correction, allow_discordant, remove_low_abundance_alleles,
+                                              best_alleles, output_allele_counts, aligner, index_type)
+        out.append(body)
+        for k, v in passed.items():
+            test_passed[k] = test_passed.get(k, 0) + v
+        if not keep_alignment and remove_alignment_file:
+            os.system("rm %s*" % aln)
+    text = "".join(out)
+    with open("%s.report" % report_base, "w") as f:
+        f.write(text)
+    if verbose or assembly_verbose or simulation:
+        sys.stderr.write(text)
+    if simulation:
+        return test_passed
+
+
 class HostWalk:
     """Host half of stage (a) with a caller-supplied pileup (no GPU): used by the CPU-side tests."""
 
