@@ -45,6 +45,8 @@ struct EmArgs {
     int slab_rows;  // rows per slab buffer
     int compact;     // host plan: keep an allele-compacted copy of ALL class rows in shared memory (batched launches)
     int A_live_max;  // upper bound of the alleles that are members of any class (sizes the compact buffers)
+    uint64_t *dense_ws;  // compact layout: global scratch for the gathered dense rows, slab_rows x pitch(A_live_max) words
+    uint64_t *mv_ws;     // compact layout: global scratch, 6 x wp words (bit-compress masks of every source word)
     const unsigned long long *cnt_u64;  // class counts as integers (device-resident tables); overrides cnt
     const int32_t *C_ptr;               // number of classes read on the device at launch; overrides C
     const int32_t *class_first;         // tie-break key of each class (first pair index); default = class index
@@ -73,6 +75,16 @@ struct Smem {
     double *cnt;         // [C] class counts as doubles
     uint64_t *cm64;      // [C] row masks of the <= 64-allele mode
     unsigned char *c64;  // 4 KB block for the small vectors of the <= 64-allele mode
+    // sparse form of the compacted matrix (null when the dense slab is used): the non-zero 32-bit words of every
+    // class row (row-major, for s_k) and of every 32-allele column (column-major, for acc[a]); rows/columns in
+    // ascending order, so all sums keep a fixed association
+    const int32_t *row_off;   // [C+1]
+    const int32_t *col_off;   // [2*wp+1]
+    const uint32_t *r_word;   // [nnzw]
+    const uint16_t *r_col;    // [nnzw] 32-bit word column of the entry
+    const uint32_t *c_word;   // [nnzw]
+    const uint16_t *c_row;    // [nnzw] class row of the entry
+    const uint64_t *dense_g;  // global copy of the compacted dense rows (pitch = wp words), kept for one-off gathers
 };
 
 __device__ __forceinline__ int orig_allele(const Smem &sm, int al) { return sm.lv ? sm.lv[al] : al; }
@@ -132,6 +144,64 @@ __device__ void em_sweep(const EmArgs &a, const Smem &sm, int mode, const double
     }
     __syncthreads();
     const uint32_t *slab32 = reinterpret_cast<const uint32_t *>(sm.slab);
+    if (sm.row_off) {
+        // ---- sparse resident form: cost follows the number of non-zero 32-bit words, not C x A -------------------
+        const int C = row_hi;
+        for (int r = warp; r < C; r += EM_WARPS) {
+            const int e0 = sm.row_off[r], e1 = sm.row_off[r + 1];
+            double s = 0.0;
+            if (mode == MODE_INIT) {
+                int pc = 0;
+                for (int e = e0 + lane; e < e1; e += 32) pc += __popc(sm.r_word[e]);
+                for (int o = 16; o > 0; o >>= 1) pc += __shfl_xor_sync(0xffffffffu, pc, o);
+                s = (double)pc;
+            } else {
+                double s1 = 0.0;
+                int e = e0;
+                for (; e + 1 < e1; e += 2) {  // whole warp per entry: word broadcast, lane = bit
+                    const uint32_t m0 = sm.r_word[e], m1 = sm.r_word[e + 1];
+                    const int c0 = sm.r_col[e], c1 = sm.r_col[e + 1];
+                    if ((m0 >> lane) & 1u) s += sm.p[c0 * 32 + lane];
+                    if ((m1 >> lane) & 1u) s1 += sm.p[c1 * 32 + lane];
+                }
+                if (e < e1) {
+                    const uint32_t m0 = sm.r_word[e];
+                    if ((m0 >> lane) & 1u) s += sm.p[(int)sm.r_col[e] * 32 + lane];
+                }
+                s = warp_sum(s + s1);
+            }
+            if (lane == 0) sm.w[r] = s > 0.0 ? sm.cnt[r] / s : -1.0;  // negative = class skipped (s_k <= 0)
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < NA; i++) {
+            const int c = warp + 32 * i;  // thread (warp, lane), slot i  <->  allele c*32 + lane = tid + i*EM_THREADS
+            if (c >= 2 * wp) continue;
+            const int e0 = sm.col_off[c], e1 = sm.col_off[c + 1];
+            if (mode == MODE_FIRSTK) {
+                for (int e = e0; e < e1; e++) {
+                    const int r = sm.c_row[e];
+                    if (sm.w[r] < 0.0) continue;
+                    if ((sm.c_word[e] >> lane) & 1u) fk[i] = min(fk[i], a.class_first ? a.class_first[r] : r);
+                }
+            } else {
+                double x = 0.0;
+                bool h = false;
+                for (int e = e0; e < e1; e++) {
+                    const double w = sm.w[(int)sm.c_row[e]];
+                    if (w < 0.0) continue;
+                    if ((sm.c_word[e] >> lane) & 1u) {
+                        x += w;
+                        h = true;
+                    }
+                }
+                acc[i] = x;
+                if (h) hit |= 1u << i;
+            }
+        }
+        __syncthreads();
+        row_lo = row_hi;  // nothing left for the slab loop
+    }
     for (int r0 = row_lo; r0 < row_hi; r0 += a.slab_rows) {
         const int nr = min(a.slab_rows, row_hi - r0);
         if (!(resident && loaded)) {
@@ -547,22 +617,153 @@ __device__ int em_compact_build(const EmArgs &a, Smem &sm, int32_t *lv, int C, i
     }
     __syncthreads();
     const int wpc = max(2, ((An + 63) / 64 + 1) & ~1);
-    uint32_t *slab32 = reinterpret_cast<uint32_t *>(sm.slab);
-    for (int r = warp; r < C; r += EM_WARPS) {
-        const uint64_t *row = a.bits + (size_t)r * wp;
-        for (int c = 0; c < 2 * wpc; c++) {
-            const int k = c * 32 + lane;
-            bool bit = false;
-            if (k < An) {
-                const int al = lv[k];
-                bit = (row[al >> 6] >> (al & 63)) & 1ull;
-            }
-            const unsigned m = __ballot_sync(0xffffffffu, bit);
-            if (lane == 0) slab32[(size_t)r * wpc * 2 + c] = m;
+    // ---- gather every class row to A' bits (dense, in global scratch) ------------------------------------------------
+    // bit-compress of a 64-bit word under the fixed mask live[j] (Hacker's Delight 7-4): the six move masks depend
+    // only on the mask, so they are computed once per source word and reused for all rows
+    for (int j = tid; j < wp; j += EM_THREADS) {
+        uint64_t m = lw[j], mk = ~m << 1;
+#pragma unroll
+        for (int i = 0; i < 6; i++) {
+            uint64_t mp = mk ^ (mk << 1);
+            mp ^= mp << 2; mp ^= mp << 4; mp ^= mp << 8; mp ^= mp << 16; mp ^= mp << 32;
+            const uint64_t mv = mp & m;
+            a.mv_ws[(size_t)j * 6 + i] = mv;
+            m = (m ^ mv) | (mv >> (1 << i));
+            mk &= ~mp;
         }
-        if (lane == 0) sm.cnt[r] = a.cnt_u64 ? (double)a.cnt_u64[r] : a.cnt[r];
+    }
+    uint64_t *dense = a.dense_ws;
+    for (int i = tid; i < C * wpc; i += EM_THREADS) dense[i] = 0ull;
+    __syncthreads();
+    for (int j = lane; j < wp; j += 32) {  // source word (slot-outer: its masks stay in registers)
+        const uint64_t m = lw[j];
+        if (m == 0ull) continue;
+        uint64_t mv[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) mv[i] = a.mv_ws[(size_t)j * 6 + i];
+        const int o = base[j], n = __popcll(m);
+        const int wi = o >> 6, sh = o & 63;
+        for (int r = warp; r < C; r += EM_WARPS) {
+            uint64_t x = a.bits[(size_t)r * wp + j] & m;
+            if (x == 0ull) continue;
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+                const uint64_t t = x & mv[i];
+                x = (x ^ t) | (t >> (1 << i));
+            }
+            atomicOr(reinterpret_cast<unsigned long long *>(&dense[(size_t)r * wpc + wi]), (unsigned long long)(x << sh));
+            if (sh + n > 64)
+                atomicOr(reinterpret_cast<unsigned long long *>(&dense[(size_t)r * wpc + wi + 1]),
+                         (unsigned long long)(x >> (64 - sh)));
+        }
+    }
+    for (int r = tid; r < C; r += EM_THREADS) sm.cnt[r] = a.cnt_u64 ? (double)a.cnt_u64[r] : a.cnt[r];
+    __threadfence();
+    __syncthreads();
+    sm.dense_g = dense;
+    // ---- sparse form: count the non-zero 32-bit words per row and per column ---------------------------------------------
+    const int wq = 2 * wpc, nb = (C + 31) / 32;
+    const uint32_t *dense32 = reinterpret_cast<const uint32_t *>(dense);
+    unsigned char *R = reinterpret_cast<unsigned char *>(sm.slab);
+    const size_t R_bytes = (size_t)a.slab_rows * (size_t)max(2, ((a.A_live_max + 63) / 64 + 1) & ~1) * 8;
+    int32_t *row_off = reinterpret_cast<int32_t *>(R);
+    int32_t *col_off = row_off + (C + 1);
+    uint32_t *nzbits = reinterpret_cast<uint32_t *>(col_off + (wq + 1));  // [wq][nb] rows with a non-zero word in column c
+    uint32_t *nzpre = nzbits + (size_t)wq * nb;                           // [wq][nb] such rows before block w
+    const size_t fixed = ((size_t)(C + 1) + (wq + 1) + 2 * (size_t)wq * nb) * 4;
+    if (fixed + 64 > R_bytes) {  // not even the index fits: dense slab
+        for (int i = tid; i < C * wpc; i += EM_THREADS) sm.slab[i] = __ldcg(&dense[i]);
+        __syncthreads();
+        return An;
+    }
+    for (int i = tid; i < wq * nb; i += EM_THREADS) nzbits[i] = 0u;
+    __syncthreads();
+    for (int r = warp; r < C; r += EM_WARPS) {
+        int n = 0;
+        for (int c0 = 0; c0 < wq; c0 += 32) {
+            const int c = c0 + lane;
+            const bool nz = c < wq && __ldcg(&dense32[(size_t)r * wq + c]) != 0u;
+            if (nz) atomicOr(&nzbits[(size_t)c * nb + (r >> 5)], 1u << (r & 31));
+            n += __popc(__ballot_sync(0xffffffffu, nz));
+        }
+        if (lane == 0) row_off[r + 1] = n;
     }
     __syncthreads();
+    if (warp == 0) {  // exclusive scans (fixed order)
+        int run = 0;
+        for (int r0 = 0; r0 < C; r0 += 32) {
+            const int r = r0 + lane;
+            const int c = r < C ? row_off[r + 1] : 0;
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            if (r < C) row_off[r + 1] = run + incl;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) row_off[0] = 0;
+    }
+    for (int c = tid; c < wq; c += EM_THREADS) {
+        int n = 0;
+        for (int w = 0; w < nb; w++) {
+            nzpre[(size_t)c * nb + w] = (uint32_t)n;
+            n += __popc(nzbits[(size_t)c * nb + w]);
+        }
+        col_off[c + 1] = n;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int run = 0;
+        for (int c0 = 0; c0 < wq; c0 += 32) {
+            const int c = c0 + lane;
+            const int v = c < wq ? col_off[c + 1] : 0;
+            int incl = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += y;
+            }
+            if (c < wq) col_off[c + 1] = run + incl;
+            run += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (lane == 0) col_off[0] = 0;
+    }
+    __syncthreads();
+    const int nnzw = row_off[C];
+    const size_t need = ((fixed + 15) & ~(size_t)15) + (size_t)nnzw * 12 + 16;
+    if (need > R_bytes || C > 65535) {  // too dense for the sparse form: dense slab (overwrites the index)
+        __syncthreads();
+        for (int i = tid; i < C * wpc; i += EM_THREADS) sm.slab[i] = __ldcg(&dense[i]);
+        __syncthreads();
+        return An;
+    }
+    uint32_t *r_word = reinterpret_cast<uint32_t *>(R + ((fixed + 15) & ~(size_t)15));
+    uint32_t *c_word = r_word + nnzw;
+    uint16_t *r_col = reinterpret_cast<uint16_t *>(c_word + nnzw);
+    uint16_t *c_row = r_col + nnzw;
+    for (int r = warp; r < C; r += EM_WARPS) {
+        int pos = row_off[r];
+        for (int c0 = 0; c0 < wq; c0 += 32) {
+            const int c = c0 + lane;
+            const uint32_t word = c < wq ? __ldcg(&dense32[(size_t)r * wq + c]) : 0u;
+            const unsigned nzm = __ballot_sync(0xffffffffu, word != 0u);
+            if (word != 0u) {
+                const int e = pos + __popc(nzm & ((1u << lane) - 1u));
+                r_word[e] = word;
+                r_col[e] = (uint16_t)c;
+                const int ce = col_off[c] + (int)nzpre[(size_t)c * nb + (r >> 5)] +
+                               __popc(nzbits[(size_t)c * nb + (r >> 5)] & ((1u << (r & 31)) - 1u));
+                c_word[ce] = word;
+                c_row[ce] = (uint16_t)r;
+            }
+            pos += __popc(nzm);
+        }
+    }
+    __syncthreads();
+    sm.row_off = row_off; sm.col_off = col_off;
+    sm.r_word = r_word; sm.r_col = r_col; sm.c_word = c_word; sm.c_row = c_row;
     return An;
 }
 
@@ -580,6 +781,8 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
     sm.mbar = reinterpret_cast<uint64_t *>(smem_raw);
     sm.red = reinterpret_cast<double *>(smem_raw + 16);
     sm.lv = nullptr; sm.cnt = nullptr; sm.cm64 = nullptr; sm.c64 = nullptr;
+    sm.row_off = nullptr; sm.col_off = nullptr; sm.r_word = nullptr; sm.c_word = nullptr; sm.r_col = nullptr;
+    sm.c_row = nullptr; sm.dense_g = nullptr;
     bool compacted = false;
     if (!COOP && a.compact) {
         // ---- allele-compacted, fully shared-memory-resident problem ---------------------------------------------
@@ -701,9 +904,9 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
                     const int lane = tid & 31, warp = tid >> 5;
                     const int a_lo = lane < c.n ? c.lv[lane] : -1, a_hi = lane + 32 < c.n ? c.lv[lane + 32] : -1;
                     for (int r = warp; r < a.C; r += EM_WARPS) {
-                        const uint64_t *row = (compacted ? sm.slab : a.bits) + (size_t)r * a.wp;
-                        const bool b_lo = a_lo >= 0 && ((row[a_lo >> 6] >> (a_lo & 63)) & 1ull);
-                        const bool b_hi = a_hi >= 0 && ((row[a_hi >> 6] >> (a_hi & 63)) & 1ull);
+                        const uint64_t *row = (compacted ? sm.dense_g : a.bits) + (size_t)r * a.wp;
+                        const bool b_lo = a_lo >= 0 && ((__ldcg(&row[a_lo >> 6]) >> (a_lo & 63)) & 1ull);
+                        const bool b_hi = a_hi >= 0 && ((__ldcg(&row[a_hi >> 6]) >> (a_hi & 63)) & 1ull);
                         const unsigned m_lo = __ballot_sync(0xffffffffu, b_lo), m_hi = __ballot_sync(0xffffffffu, b_hi);
                         if (lane == 0) {
                             c.cm[r] = (uint64_t)m_lo | ((uint64_t)m_hi << 32);
@@ -959,6 +1162,14 @@ int em_launch_batched(hgt_ctx *ctx, cudaStream_t st, int n, const EmArgs *planne
 }
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+// global scratch of one allele-compacted problem: the gathered dense rows (never larger than the shared-memory
+// budget they were planned into) + the bit-compress masks
+constexpr size_t EM_DENSE_SCRATCH = 232448;
+inline size_t em_compact_scratch_bytes(int wp) { return align_up(EM_DENSE_SCRATCH + (size_t)wp * 48, 256); }
+inline void em_set_scratch(EmArgs *a, void *scratch) {
+    a->dense_ws = static_cast<uint64_t *>(scratch);
+    a->mv_ws = reinterpret_cast<uint64_t *>(static_cast<unsigned char *>(scratch) + EM_DENSE_SCRATCH);
+}
 
 // workspace carve-up (device pointers) for one problem
 struct EmWs {
@@ -969,6 +1180,7 @@ struct EmWs {
     int32_t *part_aux;
     double *red_acc;
     int32_t *red_aux;
+    void *scratch;
 };
 size_t em_ws_bytes(int sm_count, int A) {
     const size_t Apad = (size_t)hgt_row_pitch(A) * 64;
@@ -978,6 +1190,7 @@ size_t em_ws_bytes(int sm_count, int A) {
     b += align_up((size_t)sm_count * Apad * 8, 256);  // part_acc
     b += align_up((size_t)sm_count * Apad * 4, 256);  // part_aux
     b += align_up(Apad * 8, 256) + align_up(Apad * 4, 256);
+    b += em_compact_scratch_bytes(hgt_row_pitch(A));
     return b;
 }
 EmWs em_ws_carve(void *ws, int sm_count, int A) {
@@ -990,7 +1203,8 @@ EmWs em_ws_carve(void *ws, int sm_count, int A) {
     w.part_acc = reinterpret_cast<double *>(p); p += align_up((size_t)sm_count * Apad * 8, 256);
     w.part_aux = reinterpret_cast<int32_t *>(p); p += align_up((size_t)sm_count * Apad * 4, 256);
     w.red_acc = reinterpret_cast<double *>(p); p += align_up(Apad * 8, 256);
-    w.red_aux = reinterpret_cast<int32_t *>(p);
+    w.red_aux = reinterpret_cast<int32_t *>(p); p += align_up(Apad * 4, 256);
+    w.scratch = p;
     return w;
 }
 
@@ -1033,6 +1247,7 @@ extern "C" int hgt_em_dev(hgt_ctx *ctx, void *stream, const uint64_t *class_bits
     a.prob = prob; a.in_result = in_result; a.first_class = first_class; a.iters_status = iters_status;
     a.vec = w.vec; a.live = w.live; a.part_acc = w.part_acc; a.part_aux = w.part_aux;
     a.red_acc = w.red_acc; a.red_aux = w.red_aux;
+    em_set_scratch(&a, w.scratch);
     if (G == 1) {
         const EmShape sh{n_classes, n_alleles, wp, n_alleles};
         int na = 1;
@@ -1130,7 +1345,9 @@ extern "C" int hgt_em_batch(hgt_ctx *ctx, int32_t n_problems, const uint64_t *cl
                  o_fk = o_in + align_up((size_t)Atot, 256), o_is = o_fk + align_up((size_t)Atot * 4, 256),
                  o_args = o_is + align_up((size_t)n_problems * 12, 256),
                  o_vec = o_args + align_up((size_t)n_problems * sizeof(EmArgs), 256),
-                 o_live = o_vec + (size_t)n_problems * 4 * Apad * 8, total = o_live + (size_t)n_problems * 4 * Apad;
+                 o_live = o_vec + (size_t)n_problems * 4 * Apad * 8,
+                 o_scr = align_up(o_live + (size_t)n_problems * 4 * Apad, 256),
+                 total = o_scr + (size_t)n_problems * em_compact_scratch_bytes(wp);
     unsigned char *d = nullptr;
     HGT_CUDA(cudaMalloc(&d, total));
     int rc = HGT_OK;
@@ -1160,6 +1377,7 @@ extern "C" int hgt_em_batch(hgt_ctx *ctx, int32_t n_problems, const uint64_t *cl
         a.iters_status = reinterpret_cast<int32_t *>(d + o_is) + (size_t)i * 3;
         a.vec = reinterpret_cast<double *>(d + o_vec) + (size_t)i * 4 * Apad;
         a.live = d + o_live + (size_t)i * 4 * Apad;
+        em_set_scratch(&a, d + o_scr + (size_t)i * em_compact_scratch_bytes(wp));
         a.part_acc = nullptr; a.part_aux = nullptr; a.red_acc = nullptr; a.red_aux = nullptr;
     }
     do {
@@ -1201,7 +1419,7 @@ extern "C" int hgt_em_batch(hgt_ctx *ctx, int32_t n_problems, const uint64_t *cl
 
 size_t hgt_em_problem_ws_bytes(int wp) {
     const size_t Apad = (size_t)wp * 64;
-    return align_up(4 * Apad * 8 + 4 * Apad, 256);
+    return align_up(4 * Apad * 8 + 4 * Apad, 256) + em_compact_scratch_bytes(wp);
 }
 size_t hgt_em_args_bytes(int n_problems) { return align_up((size_t)n_problems * sizeof(EmArgs), 256); }
 
@@ -1222,6 +1440,7 @@ int hgt_em_batch_dev(hgt_ctx *ctx, cudaStream_t st, int n_problems, const EmDevP
         a.iters_status = pr[i].iters_status;
         a.vec = static_cast<double *>(pr[i].ws);
         a.live = reinterpret_cast<uint8_t *>(a.vec + 4 * Apad);
+        em_set_scratch(&a, static_cast<unsigned char *>(pr[i].ws) + align_up(4 * Apad * 8 + 4 * Apad, 256));
         a.part_acc = nullptr; a.part_aux = nullptr; a.red_acc = nullptr; a.red_aux = nullptr;
     }
     return em_launch_batched(ctx, st, n_problems, args.data(), nas.data(), smems.data(), static_cast<EmArgs *>(h_args),
