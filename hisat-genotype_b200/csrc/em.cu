@@ -45,6 +45,7 @@ struct EmArgs {
     int slab_rows;  // rows per slab buffer
     int compact;     // host plan: keep an allele-compacted copy of ALL class rows in shared memory (batched launches)
     int A_live_max;  // upper bound of the alleles that are members of any class (sizes the compact buffers)
+    unsigned slab_bytes;  // compact layout: bytes of the slab region (>= slab_rows x pitch x 8; the sparse form may use more)
     uint64_t *dense_ws;  // compact layout: global scratch for the gathered dense rows, slab_rows x pitch(A_live_max) words
     uint64_t *mv_ws;     // compact layout: global scratch, 6 x wp words (bit-compress masks of every source word)
     const unsigned long long *cnt_u64;  // class counts as integers (device-resident tables); overrides cnt
@@ -665,7 +666,7 @@ __device__ int em_compact_build(const EmArgs &a, Smem &sm, int32_t *lv, int C, i
     const int wq = 2 * wpc, nb = (C + 31) / 32;
     const uint32_t *dense32 = reinterpret_cast<const uint32_t *>(dense);
     unsigned char *R = reinterpret_cast<unsigned char *>(sm.slab);
-    const size_t R_bytes = (size_t)a.slab_rows * (size_t)max(2, ((a.A_live_max + 63) / 64 + 1) & ~1) * 8;
+    const size_t R_bytes = a.slab_bytes;
     int32_t *row_off = reinterpret_cast<int32_t *>(R);
     int32_t *col_off = row_off + (C + 1);
     uint32_t *nzbits = reinterpret_cast<uint32_t *>(col_off + (wq + 1));  // [wq][nb] rows with a non-zero word in column c
@@ -795,7 +796,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
         sm.w = reinterpret_cast<double *>(q); q += Cpad * 8;
         sm.cnt = reinterpret_cast<double *>(q); q += Cpad * 8;
         sm.cm64 = reinterpret_cast<uint64_t *>(q); q += Cpad * 8;
-        sm.slab = reinterpret_cast<uint64_t *>(q); q += Cpad * wpc_max * 8;
+        sm.slab = reinterpret_cast<uint64_t *>(q); q += a.slab_bytes;
         sm.valid = q;
         for (int al = tid; al < A_orig; al += EM_THREADS) {
             a.prob[al] = 0.0;
@@ -1103,6 +1104,7 @@ int em_launch(hgt_ctx *ctx, cudaStream_t st, const EmArgs *d_args, int grid, int
 
 // Plan of one batched problem (one CTA): the allele-compacted shared-memory-resident layout when it fits, else the
 // streaming layout of em_plan().
+constexpr size_t EM_DENSE_SCRATCH = 232448;
 struct EmShape {
     int C, A, wp, A_live_max;
 };
@@ -1113,8 +1115,19 @@ int em_plan_batched(const hgt_ctx *ctx, const EmShape &sh, EmArgs *a, int *na, s
     const int wpc = hgt_row_pitch(alive);
     const size_t Apadc = (size_t)wpc * 64;
     const size_t Cpad = sh.C < 2 ? 2 : (size_t)((sh.C + 1) & ~1);
-    const size_t need = 16 + 40 * 8 + 4096 + Apadc * 12 + Cpad * ((size_t)wpc * 8 + 25) + 16;
-    if (sh.wp <= 256 && need <= budget && Apadc <= (size_t)16 * EM_THREADS) {
+    const size_t dense = Cpad * (size_t)wpc * 8;
+    const size_t other = 16 + 40 * 8 + 4096 + Apadc * 12 + Cpad * 25 + 16;
+    size_t need = other + dense;
+    if (sh.wp <= 256 && need <= budget && dense <= EM_DENSE_SCRATCH && Apadc <= (size_t)16 * EM_THREADS) {
+        // room for the sparse form (12 B per non-zero 32-bit word + index) up to full density, if the SM has it
+        const size_t nb = (Cpad + 31) / 32;
+        size_t want = 3 * dense + (Cpad + 1 + 2 * (size_t)wpc + 1 + 4 * (size_t)wpc * nb) * 4 + 64;
+        want = (want + 15) & ~(size_t)15;
+        size_t slab = dense;
+        if (other + want <= budget) slab = want;
+        else if (budget - other > dense) slab = (budget - other) & ~(size_t)15;
+        need = other + slab;
+        a->slab_bytes = (unsigned)slab;
         a->compact = 1;
         a->A_live_max = alive;
         a->slab_rows = (int)Cpad;
@@ -1127,6 +1140,7 @@ int em_plan_batched(const hgt_ctx *ctx, const EmShape &sh, EmArgs *a, int *na, s
     EmPlan plan;
     HGT_CHECK(em_plan(ctx, sh.C < 1 ? 1 : sh.C, sh.A, sh.wp, &plan));
     a->compact = 0;
+    a->slab_bytes = 0;
     a->A_live_max = sh.A;
     a->slab_rows = plan.slab_rows;
     *na = plan.na;
@@ -1141,30 +1155,26 @@ int em_launch_batched(hgt_ctx *ctx, cudaStream_t st, int n, const EmArgs *planne
     std::vector<int> order(n);
     for (int i = 0; i < n; i++) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
-        if (na[x] != na[y]) return na[x] > na[y];
         if (planned[x].compact != planned[y].compact) return planned[x].compact < planned[y].compact;
         return (double)planned[x].C * planned[x].A_live_max > (double)planned[y].C * planned[y].A_live_max;
     });
     for (int i = 0; i < n; i++) h_args[i] = planned[order[i]];
     HGT_CUDA(cudaMemcpyAsync(d_args, h_args, (size_t)n * sizeof(EmArgs), cudaMemcpyHostToDevice, st));
-    int i0 = 0;
-    while (i0 < n) {
-        int i1 = i0;
-        size_t sm = 0;
-        while (i1 < n && na[order[i1]] == na[order[i0]]) {
-            if (smem[order[i1]] > sm) sm = smem[order[i1]];
-            i1++;
-        }
-        HGT_CHECK(em_launch<false>(ctx, st, d_args + i0, i1 - i0, na[order[i0]], sm));
-        i0 = i1;
+    // one launch: the widest register variant serves every problem (narrower ones just skip slots), so all SMs
+    // stay busy instead of running the variants back to back
+    int na_max = 1;
+    size_t sm = 0;
+    for (int i = 0; i < n; i++) {
+        if (na[i] > na_max) na_max = na[i];
+        if (smem[i] > sm) sm = smem[i];
     }
+    HGT_CHECK(em_launch<false>(ctx, st, d_args, n, na_max, sm));
     return HGT_OK;
 }
 
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // global scratch of one allele-compacted problem: the gathered dense rows (never larger than the shared-memory
 // budget they were planned into) + the bit-compress masks
-constexpr size_t EM_DENSE_SCRATCH = 232448;
 inline size_t em_compact_scratch_bytes(int wp) { return align_up(EM_DENSE_SCRATCH + (size_t)wp * 48, 256); }
 inline void em_set_scratch(EmArgs *a, void *scratch) {
     a->dense_ws = static_cast<uint64_t *>(scratch);
@@ -1256,7 +1266,7 @@ extern "C" int hgt_em_dev(hgt_ctx *ctx, void *stream, const uint64_t *class_bits
         plan.na = na; plan.smem = smem; plan.slab_rows = a.slab_rows;
     } else {
         HGT_CHECK(em_plan(ctx, rows_per_cta, n_alleles, wp, &plan));
-        a.compact = 0; a.A_live_max = n_alleles;
+        a.compact = 0; a.A_live_max = n_alleles; a.slab_bytes = 0;
         a.slab_rows = plan.slab_rows;
     }
     HGT_CUDA(cudaMemcpyAsync(w.d_args, &a, sizeof(a), cudaMemcpyHostToDevice, st));
