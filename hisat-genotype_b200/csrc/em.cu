@@ -1433,26 +1433,66 @@ size_t hgt_em_problem_ws_bytes(int wp) {
 }
 size_t hgt_em_args_bytes(int n_problems) { return align_up((size_t)n_problems * sizeof(EmArgs), 256); }
 
+bool hgt_em_wants_coop(const hgt_ctx *ctx, int C, int A, int wp, int A_live_max) {
+    EmArgs a;
+    int na = 1;
+    size_t smem = 0;
+    const EmShape sh{C < 1 ? 1 : C, A, wp, A_live_max};
+    if (em_plan_batched(ctx, sh, &a, &na, &smem) != HGT_OK) return false;
+    return !a.compact && (size_t)C * wp * 8 > ((size_t)4 << 20);
+}
+size_t hgt_em_coop_ws_bytes(const hgt_ctx *ctx, int A) { return em_ws_bytes(ctx->sm_count, A); }
+
 int hgt_em_batch_dev(hgt_ctx *ctx, cudaStream_t st, int n_problems, const EmDevProblem *pr, void *h_args, void *d_args) {
     if (n_problems <= 0) return HGT_OK;
-    std::vector<EmArgs> args(n_problems);
-    std::vector<int> nas(n_problems, 1);
-    std::vector<size_t> smems(n_problems, 0);
+    std::vector<EmArgs> args, coop;
+    std::vector<int> nas, coop_na, coop_g;
+    std::vector<size_t> smems, coop_smem;
     for (int i = 0; i < n_problems; i++) {
-        EmArgs &a = args[i];
+        EmArgs a;
         const size_t Apad = (size_t)pr[i].wp * 64;
-        const EmShape sh{pr[i].C_max < 1 ? 1 : pr[i].C_max, pr[i].A, pr[i].wp, pr[i].A_live_max};
-        HGT_CHECK(em_plan_batched(ctx, sh, &a, &nas[i], &smems[i]));
         a.bits = pr[i].bits; a.cnt = nullptr; a.len = pr[i].len;
         a.C = pr[i].C_max; a.A = pr[i].A; a.wp = pr[i].wp; a.remove_low = pr[i].remove_low; a.fixed_iters = 0;
         a.cnt_u64 = pr[i].cnt; a.C_ptr = pr[i].C_ptr; a.class_first = pr[i].class_first;
         a.prob = pr[i].prob; a.in_result = pr[i].in_result; a.first_class = pr[i].first_class;
         a.iters_status = pr[i].iters_status;
+        a.part_acc = nullptr; a.part_aux = nullptr; a.red_acc = nullptr; a.red_aux = nullptr;
+        if (pr[i].coop_ws && pr[i].C_max > 1) {
+            // one problem on every SM (cooperative launch): the class matrix streams from HBM once per next_prob
+            int G = ctx->sm_count;
+            if (G > pr[i].C_max) G = pr[i].C_max;
+            EmPlan plan;
+            HGT_CHECK(em_plan(ctx, (pr[i].C_max + G - 1) / G, pr[i].A, pr[i].wp, &plan));
+            EmWs w = em_ws_carve(pr[i].coop_ws, ctx->sm_count, pr[i].A);
+            a.vec = w.vec; a.live = w.live; a.part_acc = w.part_acc; a.part_aux = w.part_aux;
+            a.red_acc = w.red_acc; a.red_aux = w.red_aux;
+            em_set_scratch(&a, w.scratch);
+            a.compact = 0; a.A_live_max = pr[i].A; a.slab_bytes = 0;
+            a.slab_rows = plan.slab_rows;
+            coop.push_back(a);
+            coop_na.push_back(plan.na);
+            coop_smem.push_back(plan.smem);
+            coop_g.push_back(G);
+            continue;
+        }
+        const EmShape sh{pr[i].C_max < 1 ? 1 : pr[i].C_max, pr[i].A, pr[i].wp, pr[i].A_live_max};
+        int na = 1;
+        size_t smem = 0;
+        HGT_CHECK(em_plan_batched(ctx, sh, &a, &na, &smem));
         a.vec = static_cast<double *>(pr[i].ws);
         a.live = reinterpret_cast<uint8_t *>(a.vec + 4 * Apad);
         em_set_scratch(&a, static_cast<unsigned char *>(pr[i].ws) + align_up(4 * Apad * 8 + 4 * Apad, 256));
-        a.part_acc = nullptr; a.part_aux = nullptr; a.red_acc = nullptr; a.red_aux = nullptr;
+        args.push_back(a);
+        nas.push_back(na);
+        smems.push_back(smem);
     }
-    return em_launch_batched(ctx, st, n_problems, args.data(), nas.data(), smems.data(), static_cast<EmArgs *>(h_args),
-                             static_cast<EmArgs *>(d_args));
+    EmArgs *h = static_cast<EmArgs *>(h_args), *d = static_cast<EmArgs *>(d_args);
+    const int nb = (int)args.size();
+    if (nb > 0) HGT_CHECK(em_launch_batched(ctx, st, nb, args.data(), nas.data(), smems.data(), h, d));
+    for (size_t k = 0; k < coop.size(); k++) {
+        h[nb + k] = coop[k];
+        HGT_CUDA(cudaMemcpyAsync(d + nb + k, h + nb + k, sizeof(EmArgs), cudaMemcpyHostToDevice, st));
+        HGT_CHECK(em_launch<true>(ctx, st, d + nb + k, coop_g[k], coop_na[k], coop_smem[k]));
+    }
+    return HGT_OK;
 }

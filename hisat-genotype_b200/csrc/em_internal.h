@@ -19,10 +19,15 @@ struct EmDevProblem {
     int32_t *first_class;            // [A]
     int32_t *iters_status;           // [3]
     void *ws;                        // hgt_em_problem_ws_bytes(wp) bytes of device scratch
+    void *coop_ws;                   // non-null: run this problem on all SMs (cooperative launch); needs
+                                     // hgt_em_coop_ws_bytes(ctx, A) bytes
 };
 
 size_t hgt_em_problem_ws_bytes(int wp);
 size_t hgt_em_args_bytes(int n_problems);
+// true when a problem of this shape is too large for one SM's shared memory and big enough to deserve the whole GPU
+bool hgt_em_wants_coop(const hgt_ctx *ctx, int C, int A, int wp, int A_live_max);
+size_t hgt_em_coop_ws_bytes(const hgt_ctx *ctx, int A);
 // One CTA per problem, all problems of all loci in as few launches as the register variants need.  h_args: host
 // staging (pinned) and d_args: device copy, hgt_em_args_bytes(n_problems) each; h_args must stay untouched until the
 // stream has passed this call.

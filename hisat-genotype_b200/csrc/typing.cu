@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <deque>
 #include <memory>
 #include <numeric>
 #include <thread>
@@ -352,6 +353,56 @@ static int intake(const char *sam, size_t n, const hgt_params &pr, Intake *in) {
         p = q + 1;
     }
     return HGT_OK;
+}
+
+// Read id of the record that starts at `line` (first whitespace-separated token; cut at '|' in simulation mode,
+// core:808-809); empty for blank and header lines.
+static std::string_view line_read_id(const char *line, const char *end, bool simulation) {
+    const char *a = line;
+    while (a < end && *a != '\n' && is_ws(*a)) a++;
+    if (a >= end || *a == '\n' || *a == '@') return std::string_view();
+    const char *q = a;
+    while (q < end && !is_ws(*q)) q++;
+    size_t n = (size_t)(q - a);
+    if (simulation) {
+        const void *bar = memchr(a, '|', n);
+        if (bar) n = (size_t)((const char *)bar - a);
+    }
+    return std::string_view(a, n);
+}
+
+// Cut [sam, sam+n) into pieces of about `target` bytes at line starts where the read id changes.
+static void split_text(const char *sam, size_t n, size_t target, bool simulation,
+                       std::vector<std::pair<const char *, size_t>> *out) {
+    const char *p = sam, *end = sam + n;
+    if (target < 256) target = 256;
+    while (p < end) {
+        if ((size_t)(end - p) <= target + target / 2) {
+            out->push_back({p, (size_t)(end - p)});
+            return;
+        }
+        const char *q = (const char *)memchr(p + target, '\n', (size_t)(end - (p + target)));
+        if (!q) {
+            out->push_back({p, (size_t)(end - p)});
+            return;
+        }
+        q++;  // first line of the next piece; move on while it continues the previous line's read
+        while (q < end) {
+            const char *prev = q - 1;  // the '\n' that ends the previous line
+            const char *ps = prev;
+            while (ps > p && ps[-1] != '\n') ps--;
+            const std::string_view a = line_read_id(ps, end, simulation), b2 = line_read_id(q, end, simulation);
+            if (a.empty() || b2.empty() || a != b2) break;
+            const char *nx = (const char *)memchr(q, '\n', (size_t)(end - q));
+            if (!nx) {
+                q = end;
+                break;
+            }
+            q = nx + 1;
+        }
+        out->push_back({p, (size_t)(q - p)});
+        p = q;
+    }
 }
 
 static int op_code(char c) {
@@ -942,23 +993,36 @@ static int wpl_of(int wp) {
 // ================================================================================================================
 // Batch of (sample, locus) units
 // ================================================================================================================
-struct UnitHost {
-    int locus = 0;
+// A unit is one (sample, locus).  Its alignment text is cut into tasks at read-id boundaries (the input is name
+// sorted, core:458-468, so mates, duplicate records of a read and therefore pairs never straddle a cut); host threads
+// take tasks, not units, so one deep unit (the oversized locus) uses every core and shallow units balance.
+struct TaskHost {
+    int unit = 0;
     const char *sam = nullptr;
     size_t n_bytes = 0;
     Intake in;
     HostOut ho;
     int rc = HGT_OK;
     std::string err;
-    int local = 0;  // index inside its locus batch
-    const uint8_t *nt_mask = nullptr, *del_flag = nullptr;  // [L] views into the batch's page-locked pileup result
-    std::vector<uint32_t> counts;  // kept only when requested (single-unit API / tests)
+    int64_t pair0 = 0;  // pairs of the unit before this task
     // pileup packing (records that pass the weaker filters of common:1084-1098)
     std::vector<uint32_t> pu_rec;   // indices into in.recs
     std::vector<uint32_t> pu_cig;   // len << 4 | op
     std::vector<uint32_t> pu_ncig;  // ops per record
     int64_t pu_seq = 0;             // bases
-    int64_t pu_rec0 = 0, pu_cig0 = 0, pu_seq0 = 0, pos0 = 0;  // offsets inside the batch arenas
+    int64_t pu_rec0 = 0, pu_cig0 = 0, pu_seq0 = 0;  // offsets inside the batch arena
+};
+
+struct UnitHost {
+    int locus = 0;
+    const char *sam = nullptr;
+    size_t n_bytes = 0;
+    int local = 0;  // index inside its locus batch
+    size_t task0 = 0, task1 = 0;
+    int64_t num_reads = 0, num_pairs = 0;
+    const uint8_t *nt_mask = nullptr, *del_flag = nullptr;  // [L] views into the batch's page-locked pileup result
+    std::vector<uint32_t> counts;  // kept only when requested (single-unit API / tests)
+    int64_t pos0 = 0;              // first position of the unit in the batch-wide pileup arrays
 };
 
 struct LocusBatch {
@@ -984,6 +1048,7 @@ struct LocusBatch {
     DevBuf d_prob, d_inres, d_fk, d_is, d_emws;      // EM over exon (hla) / gene (other) tables
     DevBuf d_prob2, d_inres2, d_fk2, d_is2, d_keep, d_ulist;  // second-level EM (hla)
     DevBuf d_acount, d_afirst;
+    std::deque<DevBuf> d_coopws;  // whole-GPU EM workspaces of oversized problems (allocated when class counts are known)
     uint32_t cap = 0;
     int n_live[4] = {0, 0, 0, 0};  // alleles that can be members of a class of table t (popcount of its mask)
     // results on the host (page-locked)
@@ -1002,6 +1067,8 @@ struct LocusBatch {
                          &d_is, &d_emws, &d_prob2, &d_inres2, &d_fk2, &d_is2, &d_keep, &d_ulist,
                          &d_acount, &d_afirst};
         for (DevBuf *b : all) b->release();
+        for (DevBuf &b : d_coopws) b.release();
+        d_coopws.clear();
         PinBuf *pins[] = {&h_jobs, &h_ncls, &h_prob, &h_inres, &h_fk, &h_is, &h_prob2, &h_inres2, &h_fk2, &h_is2, &h_keep, &h_ulist};
         for (PinBuf *b : pins) b->release();
     }
@@ -1019,8 +1086,11 @@ struct hgt_batch {
     hgt_params params;
     std::vector<hgt_locus *> loci;
     std::vector<UnitHost> units;
+    std::vector<TaskHost> tasks;
     std::vector<LocusBatch> lb;
     bool keep_counts = false;
+    int (*pileup_hook)(void *arg, void *dev_counts, size_t n_u32, void *stream) = nullptr;
+    void *pileup_hook_arg = nullptr;
     bool prepared = false, executed = false, finished = false;
     StageTimer timer;
     int remove_low = 1;
@@ -1042,9 +1112,9 @@ struct hgt_batch {
     }
 };
 
-static void set_unit_error(UnitHost &u, int rc) {
-    u.rc = rc;
-    u.err = hgt_last_error();
+static void set_task_error(TaskHost &t, int rc) {
+    t.rc = rc;
+    t.err = hgt_last_error();
 }
 
 // Parallel-for over units on host threads (intake and walk are independent per unit).
@@ -1089,54 +1159,82 @@ static int batch_prepare(hgt_batch *b) {
         b->units[u].local = (int)lb.units.size();
         lb.units.push_back((int)u);
     }
+    // tasks: every unit's text cut at read-id boundaries
+    b->tasks.clear();
+    {
+        const size_t target = b->params.chunk_bytes > 0 ? (size_t)b->params.chunk_bytes : (size_t)128 << 10;
+        std::vector<std::pair<const char *, size_t>> pieces;
+        for (size_t u = 0; u < nu; u++) {
+            UnitHost &U = b->units[u];
+            pieces.clear();
+            split_text(U.sam, U.n_bytes, target, b->params.simulation != 0, &pieces);
+            U.task0 = b->tasks.size();
+            for (auto &pc : pieces) {
+                b->tasks.emplace_back();
+                TaskHost &T = b->tasks.back();
+                T.unit = (int)u;
+                T.sam = pc.first;
+                T.n_bytes = pc.second;
+            }
+            U.task1 = b->tasks.size();
+        }
+    }
+    const size_t nt = b->tasks.size();
+    // heaviest tasks first (dynamic scheduling then ends with the small ones)
+    std::vector<uint32_t> sched(nt);
+    std::iota(sched.begin(), sched.end(), 0u);
+    std::stable_sort(sched.begin(), sched.end(), [&](uint32_t x, uint32_t y) { return b->tasks[x].n_bytes > b->tasks[y].n_bytes; });
     auto first_error = [&]() {
-        for (UnitHost &U : b->units)
-            if (U.rc != HGT_OK) {
-                hgt_set_error("%s", U.err.c_str());
-                return U.rc;
+        for (TaskHost &T : b->tasks)
+            if (T.rc != HGT_OK) {
+                hgt_set_error("%s", T.err.c_str());
+                return T.rc;
             }
         return (int)HGT_OK;
     };
-    // ---- intake + pileup packing, pass 1 (parallel over units): parse the text, pick the pileup records, parse CIGARs
+    // ---- intake + pileup packing, pass 1 (parallel over tasks): parse the text, pick the pileup records, parse CIGARs
     {
         HostTimer ht(ctx, 0);
-        parallel_units(nthreads, nu, [&](size_t u) {
-            UnitHost &U = b->units[u];
-            int rc = intake(U.sam, U.n_bytes, b->params, &U.in);
+        parallel_units(nthreads, nt, [&](size_t k) {
+            TaskHost &T = b->tasks[sched[k]];
+            int rc = intake(T.sam, T.n_bytes, b->params, &T.in);
             if (rc != HGT_OK) {
-                set_unit_error(U, rc);
+                set_task_error(T, rc);
                 return;
             }
             std::vector<CigarOp> cig;
-            for (size_t k = 0; k < U.in.recs.size(); k++) {
-                const Record &r = U.in.recs[k];
+            for (size_t i = 0; i < T.in.recs.size(); i++) {
+                const Record &r = T.in.recs[i];
                 if (r.flag & 0x4) continue;
                 if (r.pos < 0) continue;
                 if (!b->params.allow_discordant && !(r.flag & 0x2)) continue;
                 if (!parse_cigar(r.cigar, r.cigar_len, &cig)) {
                     hgt_set_error("malformed CIGAR in read %.*s", r.qname_len, r.qname);
-                    set_unit_error(U, HGT_ERR_PARSE);
+                    set_task_error(T, HGT_ERR_PARSE);
                     return;
                 }
                 uint32_t n = 0;
                 for (const CigarOp &c : cig) {
                     const int oc = op_code(c.op);
                     if (oc < 0) continue;  // the reference's pileup ignores ops outside MIDNS (common:1107-1121)
-                    U.pu_cig.push_back(((uint32_t)c.len << 4) | (uint32_t)oc);
+                    T.pu_cig.push_back(((uint32_t)c.len << 4) | (uint32_t)oc);
                     n++;
                 }
-                U.pu_rec.push_back((uint32_t)k);
-                U.pu_ncig.push_back(n);
-                U.pu_seq += r.seq_len;
+                T.pu_rec.push_back((uint32_t)i);
+                T.pu_ncig.push_back(n);
+                T.pu_seq += r.seq_len;
             }
         });
     }
     HGT_CHECK(first_error());
     // ---- pileup: one arena for all units of all loci, one copy, one launch -----------------------------------------
     int64_t R = 0, CG = 0, SQ = 0, POS = 0;
+    for (TaskHost &T : b->tasks) {
+        T.pu_rec0 = R; T.pu_cig0 = CG; T.pu_seq0 = SQ;
+        R += (int64_t)T.pu_rec.size(); CG += (int64_t)T.pu_cig.size(); SQ += T.pu_seq;
+    }
     for (UnitHost &U : b->units) {
-        U.pu_rec0 = R; U.pu_cig0 = CG; U.pu_seq0 = SQ; U.pos0 = POS;
-        R += (int64_t)U.pu_rec.size(); CG += (int64_t)U.pu_cig.size(); SQ += U.pu_seq;
+        U.pos0 = POS;
         POS += b->loci[U.locus]->L;
     }
     const size_t o_pos = 0, o_ru = a16(o_pos + (size_t)R * 4), o_co = a16(o_ru + (size_t)R * 4),
@@ -1158,26 +1256,28 @@ static int batch_prepare(hgt_batch *b) {
         char *h_sq = reinterpret_cast<char *>(hp + o_sq);
         h_co[R] = CG;
         h_so[R] = SQ;
-        parallel_units(nthreads, nu, [&](size_t u) {
-            UnitHost &U = b->units[u];
-            h_up[u] = U.pos0;
-            h_ul[u] = b->loci[U.locus]->L;
-            int64_t c = U.pu_cig0, q = U.pu_seq0;
-            if (!U.pu_cig.empty()) memcpy(h_cg + c, U.pu_cig.data(), U.pu_cig.size() * 4);
-            for (size_t k = 0; k < U.pu_rec.size(); k++) {
-                const Record &r = U.in.recs[U.pu_rec[k]];
-                const int64_t i = U.pu_rec0 + (int64_t)k;
-                h_pos[i] = r.pos;
-                h_ru[i] = (int32_t)u;
-                h_co[i] = c;
-                h_so[i] = q;
+        for (size_t u = 0; u < nu; u++) {
+            h_up[u] = b->units[u].pos0;
+            h_ul[u] = b->loci[b->units[u].locus]->L;
+        }
+        parallel_units(nthreads, nt, [&](size_t k) {
+            TaskHost &T = b->tasks[sched[k]];
+            int64_t c = T.pu_cig0, q = T.pu_seq0;
+            if (!T.pu_cig.empty()) memcpy(h_cg + c, T.pu_cig.data(), T.pu_cig.size() * 4);
+            for (size_t i = 0; i < T.pu_rec.size(); i++) {
+                const Record &r = T.in.recs[T.pu_rec[i]];
+                const int64_t at = T.pu_rec0 + (int64_t)i;
+                h_pos[at] = r.pos;
+                h_ru[at] = (int32_t)T.unit;
+                h_co[at] = c;
+                h_so[at] = q;
                 memcpy(h_sq + q, r.seq, (size_t)r.seq_len);
-                c += U.pu_ncig[k];
+                c += T.pu_ncig[i];
                 q += r.seq_len;
             }
-            std::vector<uint32_t>().swap(U.pu_cig);
-            std::vector<uint32_t>().swap(U.pu_rec);
-            std::vector<uint32_t>().swap(U.pu_ncig);
+            std::vector<uint32_t>().swap(T.pu_cig);
+            std::vector<uint32_t>().swap(T.pu_rec);
+            std::vector<uint32_t>().swap(T.pu_ncig);
         });
     }
     {
@@ -1198,6 +1298,14 @@ static int batch_prepare(hgt_batch *b) {
                 reinterpret_cast<char *>(dp + o_sq), reinterpret_cast<int32_t *>(dp + o_ru), R,
                 reinterpret_cast<int64_t *>(dp + o_up), reinterpret_cast<int32_t *>(dp + o_ul), d_cnt.as<uint32_t>());
             ctx->launches++;
+        }
+        if (b->pileup_hook) {  // read-sharded locus: the caller sums the raw counts over ranks
+            HGT_CUDA(cudaStreamSynchronize(st));
+            const int rc = b->pileup_hook(b->pileup_hook_arg, d_cnt.p, (size_t)POS * 6, st);
+            if (rc != 0) {
+                hgt_set_error("pileup hook failed with status %d", rc);
+                return HGT_ERR_ARG;
+            }
         }
         if (POS > 0) {
             pileup_flags_kernel<<<(unsigned)((POS + 255) / 256), 256, 0, st>>>(d_cnt.as<uint32_t>(), POS, d_mf.as<uint8_t>(),
@@ -1223,22 +1331,35 @@ static int batch_prepare(hgt_batch *b) {
             U.counts.assign(counts_all.begin() + (size_t)U.pos0 * 6, counts_all.begin() + ((size_t)U.pos0 + L) * 6);
         }
     }
-    // ---- walk (parallel over units) ---------------------------------------------------------------------------------
+    // ---- walk (parallel over tasks) ---------------------------------------------------------------------------------
     {
         HostTimer ht(ctx, 3);
-        parallel_units(nthreads, nu, [&](size_t u) {
-            UnitHost &U = b->units[u];
+        parallel_units(nthreads, nt, [&](size_t k) {
+            TaskHost &T = b->tasks[sched[k]];
+            const UnitHost &U = b->units[T.unit];
             const hgt_locus *loc = b->loci[U.locus];
             PileupView pu;
             pu.nt_mask = U.nt_mask; pu.del_artefact = U.del_flag; pu.L = loc->L;
-            const int rc = host_walk(loc, U.in, b->params, pu, &U.ho);
-            if (rc != HGT_OK) set_unit_error(U, rc);
-            std::vector<Record>().swap(U.in.recs);
+            const int rc = host_walk(loc, T.in, b->params, pu, &T.ho);
+            if (rc != HGT_OK) set_task_error(T, rc);
+            std::vector<Record>().swap(T.in.recs);
         });
     }
     HGT_CHECK(first_error());
+    for (UnitHost &U : b->units) {
+        U.num_reads = U.num_pairs = 0;
+        for (size_t t = U.task0; t < U.task1; t++) {
+            b->tasks[t].pair0 = U.num_pairs;
+            U.num_reads += b->tasks[t].ho.num_reads;
+            U.num_pairs += b->tasks[t].ho.num_pairs;
+        }
+        if (U.num_pairs > 0x7fffffff) {
+            hgt_set_error("a unit holds more than 2^31 read pairs");
+            return HGT_ERR_UNSUPPORTED;
+        }
+    }
     // ---- job arenas per locus: offsets (serial, tiny), then a parallel fill straight into page-locked memory --------
-    struct Fill { LocusBatch *lb; size_t i; int64_t h0[3], r0[3], j0[3], s0[3], b0[3]; };
+    struct Fill { LocusBatch *lb; size_t i; const TaskHost *task; int64_t h0[3], r0[3], j0[3], s0[3], b0[3]; };
     std::vector<Fill> fills;
     {
         HostTimer ht(ctx, 4);
@@ -1252,32 +1373,39 @@ static int batch_prepare(hgt_batch *b) {
             const size_t f0 = fills.size();
             for (size_t i = 0; i < n_units; i++) {
                 const UnitHost &U = b->units[lb.units[i]];
-                Fill f;
-                f.lb = &lb; f.i = i;
                 for (int tb = 0; tb < 4; tb++) {
                     const bool active = tb < n_tables || (tb == 3 && loc->is_hla);
-                    lb.ut_base[i * 4 + tb + 1] = lb.ut_base[i * 4 + tb] + (active ? U.ho.num_pairs : 0);
+                    lb.ut_base[i * 4 + tb + 1] = lb.ut_base[i * 4 + tb] + (active ? U.num_pairs : 0);
                 }
-                for (int tb = 0; tb < 3; tb++) {
-                    f.h0[tb] = H; f.r0[tb] = RW; f.j0[tb] = J; f.s0[tb] = NS; f.b0[tb] = NB;
-                    if (tb >= n_tables) continue;
-                    const TableJobs &T = U.ho.tb[tb];
-                    int64_t small = 0;
-                    for (int64_t p = 0; p < U.ho.num_pairs; p++) {
-                        const int64_t k = T.job_off[p + 1] - T.job_off[p];
-                        if (k > 255) {
-                            hgt_set_error("a read pair expands to %lld haplotypes (limit 255)", (long long)k);
-                            return HGT_ERR_UNSUPPORTED;
+                for (size_t t = U.task0; t < U.task1; t++) {
+                    const TaskHost &TK = b->tasks[t];
+                    Fill f;
+                    f.lb = &lb; f.i = i; f.task = &TK;
+                    for (int tb = 0; tb < 3; tb++) {
+                        f.h0[tb] = H; f.r0[tb] = RW; f.j0[tb] = J; f.s0[tb] = NS; f.b0[tb] = NB;
+                        if (tb >= n_tables) continue;
+                        const TableJobs &T = TK.ho.tb[tb];
+                        int64_t small = 0;
+                        for (int64_t p = 0; p < TK.ho.num_pairs; p++) {
+                            const int64_t k = T.job_off[p + 1] - T.job_off[p];
+                            if (k > 255) {
+                                hgt_set_error("a read pair expands to %lld haplotypes (limit 255)", (long long)k);
+                                return HGT_ERR_UNSUPPORTED;
+                            }
+                            small += k <= 7;
                         }
-                        small += k <= 7;
+                        H += (int64_t)T.hap_left.size();
+                        RW += (int64_t)T.rows.size();
+                        J += TK.ho.num_pairs;
+                        NS += small;
+                        NB += TK.ho.num_pairs - small;
                     }
-                    H += (int64_t)T.hap_left.size();
-                    RW += (int64_t)T.rows.size();
-                    J += U.ho.num_pairs;
-                    NS += small;
-                    NB += U.ho.num_pairs - small;
+                    fills.push_back(f);
                 }
-                fills.push_back(f);
+            }
+            if (J > 0x7fffffff || H > 0x7fffffff) {
+                hgt_set_error("more than 2^31 jobs or haplotypes in one locus batch: split the batch");
+                return HGT_ERR_UNSUPPORTED;
             }
             for (size_t k = f0; k < fills.size(); k++)
                 for (int tb = 0; tb < 3; tb++) fills[k].b0[tb] += NS;  // the > 7-haplotype jobs follow all small ones
@@ -1304,14 +1432,14 @@ static int batch_prepare(hgt_batch *b) {
             const Fill &f = fills[k];
             LocusBatch &lb = *f.lb;
             const LocusBatch::JobArena &ja = lb.ja;
-            const UnitHost &U = b->units[lb.units[f.i]];
+            const TaskHost &TK = *f.task;
             const int n_tables = lb.loc->is_hla ? 3 : 1;
             int64_t *job_off = lb.hj<int64_t>(ja.o_job_off), *row_off = lb.hj<int64_t>(ja.o_row_off);
             int32_t *job_ut = lb.hj<int32_t>(ja.o_job_ut), *job_pair = lb.hj<int32_t>(ja.o_job_pair),
                     *job_list = lb.hj<int32_t>(ja.o_job_list), *hl = lb.hj<int32_t>(ja.o_hl), *hr = lb.hj<int32_t>(ja.o_hr),
                     *htb = lb.hj<int32_t>(ja.o_ht), *rows = lb.hj<int32_t>(ja.o_rows);
             for (int tb = 0; tb < n_tables; tb++) {
-                const TableJobs &T = U.ho.tb[tb];
+                const TableJobs &T = TK.ho.tb[tb];
                 const int64_t h0 = f.h0[tb], r0 = f.r0[tb], j0 = f.j0[tb];
                 const size_t nh = T.hap_left.size();
                 if (nh) {
@@ -1324,10 +1452,10 @@ static int batch_prepare(hgt_batch *b) {
                 }
                 if (!T.rows.empty()) memcpy(rows + r0, T.rows.data(), T.rows.size() * 4);
                 int64_t s = f.s0[tb], g = f.b0[tb];
-                for (int64_t p = 0; p < U.ho.num_pairs; p++) {
+                for (int64_t p = 0; p < TK.ho.num_pairs; p++) {
                     const int64_t job = j0 + p;
                     job_ut[job] = (int32_t)(f.i * 4 + tb);
-                    job_pair[job] = (int32_t)p;
+                    job_pair[job] = (int32_t)(TK.pair0 + p);  // pair index inside the unit (first-seen order key)
                     job_off[job + 1] = h0 + T.job_off[p + 1];
                     if (T.job_off[p + 1] - T.job_off[p] <= 7) job_list[s++] = (int32_t)job;
                     else job_list[g++] = (int32_t)job;
@@ -1446,7 +1574,7 @@ static void launch_stage_a(hgt_batch *b, cudaStream_t st, LocusBatch &lb) {
 }
 
 // EM problems of one locus batch on table `table` for the listed local units, appended to `out`.
-static void em_problems(LocusBatch &lb, int table, const std::vector<int> &local_units, const int *c_max,
+static void em_problems(hgt_ctx *ctx, LocusBatch &lb, int table, const std::vector<int> &local_units, const int *c_max,
                         const int *a_live, const double *d_len, int remove_low, DevBuf &prob, DevBuf &inres, DevBuf &fk,
                         DevBuf &is, std::vector<EmDevProblem> *out) {
     const hgt_locus *loc = lb.loc;
@@ -1471,6 +1599,11 @@ static void em_problems(LocusBatch &lb, int table, const std::vector<int> &local
         p.first_class = fk.as<int32_t>() + (size_t)i * A;
         p.iters_status = is.as<int32_t>() + (size_t)i * 3;
         p.ws = static_cast<unsigned char *>(lb.d_emws.p) + (size_t)i * wsb;
+        p.coop_ws = nullptr;
+        if (hgt_em_wants_coop(ctx, p.C_max, p.A, p.wp, p.A_live_max)) {
+            lb.d_coopws.emplace_back();
+            if (lb.d_coopws.back().alloc(hgt_em_coop_ws_bytes(ctx, p.A)) == HGT_OK) p.coop_ws = lb.d_coopws.back().p;
+        }
         out->push_back(p);
     }
 }
@@ -1482,6 +1615,8 @@ static int batch_execute(hgt_batch *b, cudaStream_t st) {
         const hgt_locus *loc = lb.loc;
         const size_t n_units = lb.units.size();
         const size_t pr = (size_t)std::max<int64_t>(lb.n_rows_pool, 1);
+        for (DevBuf &x : lb.d_coopws) x.release();  // (a repeated execute: the previous finish has synchronised)
+        lb.d_coopws.clear();
         HGT_CUDA(cudaMemsetAsync(lb.d_keys.p, 0, (size_t)lb.cap * 8, st));
         HGT_CUDA(cudaMemsetAsync(lb.d_slot.p, 0xff, (size_t)lb.cap * 4, st));
         HGT_CUDA(cudaMemsetAsync(lb.d_count.p, 0, pr * 8, st));
@@ -1522,7 +1657,7 @@ static int batch_execute(hgt_batch *b, cudaStream_t st) {
         all.resize(n_units); cmax.resize(n_units); alive.assign(n_units, lb.n_live[table]);
         std::iota(all.begin(), all.end(), 0);
         for (size_t i = 0; i < n_units; i++) cmax[i] = lb.ut_ncls[i * 4 + table];
-        em_problems(lb, table, all, cmax.data(), alive.data(), nullptr, loc->is_hla ? b->remove_low : 0, lb.d_prob, lb.d_inres,
+        em_problems(ctx, lb, table, all, cmax.data(), alive.data(), nullptr, loc->is_hla ? b->remove_low : 0, lb.d_prob, lb.d_inres,
                     lb.d_fk, lb.d_is, &probs);
     }
     b->timer.begin(ctx, st, 4);
@@ -1621,7 +1756,7 @@ static int batch_finish(hgt_batch *b, cudaStream_t st) {
             HGT_CUDA(cudaGetLastError());
         }
         HGT_CUDA(cudaMemsetAsync(lb.d_is2.p, 0, n_units * 12, st));
-        em_problems(lb, 3, lu, cmax.data(), alive.data(), loc->d_allele_len, 1, lb.d_prob2, lb.d_inres2, lb.d_fk2, lb.d_is2,
+        em_problems(ctx, lb, 3, lu, cmax.data(), alive.data(), loc->d_allele_len, 1, lb.d_prob2, lb.d_inres2, lb.d_fk2, lb.d_is2,
                     &probs);
     }
     if (!probs.empty()) {
@@ -1674,6 +1809,16 @@ extern "C" int hgt_batch_create(hgt_ctx *ctx, int32_t n_loci, hgt_locus *const *
 }
 
 extern "C" void hgt_batch_free(hgt_batch *b) { delete b; }
+
+extern "C" int hgt_batch_set_pileup_hook(hgt_batch *b, hgt_pileup_hook fn, void *arg) {
+    if (!b || b->prepared) {
+        hgt_set_error("hgt_batch_set_pileup_hook: bad state");
+        return HGT_ERR_ARG;
+    }
+    b->pileup_hook = fn;
+    b->pileup_hook_arg = arg;
+    return HGT_OK;
+}
 
 extern "C" int64_t hgt_batch_add_unit(hgt_batch *b, int32_t locus_index, const char *sam_text, size_t n_bytes) {
     if (!b || locus_index < 0 || locus_index >= (int)b->loci.size() || (!sam_text && n_bytes) || b->prepared) {
@@ -1729,8 +1874,8 @@ extern "C" int hgt_batch_totals(const hgt_batch *b, int64_t *n_units, int64_t *n
     if (!b) return HGT_ERR_ARG;
     int64_t r = 0, p = 0, h = 0, rows = 0, bytes = 0;
     for (const UnitHost &u : b->units) {
-        r += u.ho.num_reads;
-        p += u.ho.num_pairs;
+        r += u.num_reads;
+        p += u.num_pairs;
     }
     for (const LocusBatch &lb : b->lb) {
         if (lb.units.empty()) continue;
@@ -1739,7 +1884,7 @@ extern "C" int hgt_batch_totals(const hgt_batch *b, int64_t *n_units, int64_t *n
         const int n_tables = lb.loc->is_hla ? 3 : 1;
         // per pair S_rec + T * wp * 8, S_rec = packed haplotype records actually read
         bytes += lb.n_haps * 12 + lb.n_rows * 4 + lb.n_jobs * 16;
-        for (int u : lb.units) bytes += b->units[u].ho.num_pairs * (int64_t)n_tables * lb.loc->wp * 8;
+        for (int u : lb.units) bytes += b->units[u].num_pairs * (int64_t)n_tables * lb.loc->wp * 8;
     }
     if (n_units) *n_units = (int64_t)b->units.size();
     if (num_reads) *num_reads = r;
@@ -1762,8 +1907,8 @@ extern "C" int hgt_batch_unit_summary(const hgt_batch *b, int64_t unit, int64_t 
                                       int32_t n_classes[4], int32_t em_iters[2], int32_t em_status[2]) {
     HGT_CHECK(unit_check(b, unit, false));
     const UnitHost &U = b->units[unit];
-    if (num_reads) *num_reads = U.ho.num_reads;
-    if (num_pairs) *num_pairs = U.ho.num_pairs;
+    if (num_reads) *num_reads = U.num_reads;
+    if (num_pairs) *num_pairs = U.num_pairs;
     if (b->finished) {
         const LocusBatch &lb = b->lb[U.locus];
         for (int t = 0; t < 4; t++) {
@@ -2044,8 +2189,6 @@ extern "C" int hgt_host_walk(hgt_locus *loc, const char *sam, size_t n_bytes, co
         return HGT_ERR_ARG;
     }
     *out = nullptr;
-    Intake in;
-    HGT_CHECK(intake(sam, n_bytes, *params, &in));
     hgt_walk *w = new hgt_walk();
     PileupView pu;
     std::vector<uint8_t> flag(loc->L);
@@ -2055,10 +2198,32 @@ extern "C" int hgt_host_walk(hgt_locus *loc, const char *sam, size_t n_bytes, co
         flag[i] = dels * 6 < nts ? 1 : 0;
     }
     pu.nt_mask = nt_mask; pu.del_artefact = flag.data(); pu.L = loc->L;
-    int rc = host_walk(loc, in, *params, pu, &w->ho);
-    if (rc != HGT_OK) {
-        delete w;
-        return rc;
+    // the same task decomposition as the batch path: pieces cut at read-id boundaries, walked independently, then
+    // concatenated in order
+    std::vector<std::pair<const char *, size_t>> pieces;
+    split_text(sam, n_bytes, params->chunk_bytes > 0 ? (size_t)params->chunk_bytes : (size_t)128 << 10,
+               params->simulation != 0, &pieces);
+    for (auto &pc : pieces) {
+        Intake in;
+        HostOut part;
+        int rc = intake(pc.first, pc.second, *params, &in);
+        if (rc == HGT_OK) rc = host_walk(loc, in, *params, pu, &part);
+        if (rc != HGT_OK) {
+            delete w;
+            return rc;
+        }
+        w->ho.num_reads += part.num_reads;
+        w->ho.num_pairs += part.num_pairs;
+        for (int t = 0; t < 3; t++) {
+            TableJobs &D = w->ho.tb[t];
+            const TableJobs &S = part.tb[t];
+            const int64_t h0 = (int64_t)D.hap_left.size(), r0 = (int64_t)D.rows.size();
+            for (size_t k = 1; k < S.job_off.size(); k++) D.job_off.push_back(h0 + S.job_off[k]);
+            D.hap_left.insert(D.hap_left.end(), S.hap_left.begin(), S.hap_left.end());
+            D.hap_right.insert(D.hap_right.end(), S.hap_right.begin(), S.hap_right.end());
+            for (size_t k = 1; k < S.row_off.size(); k++) D.row_off.push_back(r0 + S.row_off[k]);
+            D.rows.insert(D.rows.end(), S.rows.begin(), S.rows.end());
+        }
     }
     *out = w;
     return HGT_OK;

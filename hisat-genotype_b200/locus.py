@@ -38,7 +38,7 @@ class LocusDesc(ctypes.Structure):
 class Params(ctypes.Structure):
     _fields_ = [("num_editdist", ctypes.c_int32), ("error_correction", ctypes.c_int32),
                 ("allow_discordant", ctypes.c_int32), ("simulation", ctypes.c_int32),
-                ("base_locus", ctypes.c_int32), ("n_threads", ctypes.c_int32)]
+                ("base_locus", ctypes.c_int32), ("n_threads", ctypes.c_int32), ("chunk_bytes", ctypes.c_int32)]
 
 
 def _bind(L):

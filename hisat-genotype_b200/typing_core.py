@@ -21,9 +21,9 @@ TABLE_GENE, TABLE_EXON, TABLE_PRIMARY = 0, 1, 2
 
 
 def make_params(num_editdist=2, error_correction=True, allow_discordant=False, simulation=False, base_locus=0,
-                n_threads=0):
+                n_threads=0, chunk_bytes=0):
     return Params(int(num_editdist), 1 if error_correction else 0, 1 if allow_discordant else 0,
-                  1 if simulation else 0, int(base_locus), int(n_threads))
+                  1 if simulation else 0, int(base_locus), int(n_threads), int(chunk_bytes))
 
 
 def _sam_bytes(sam):

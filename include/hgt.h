@@ -140,7 +140,9 @@ typedef struct {
     int32_t allow_discordant;  /* --discordant */
     int32_t simulation;        /* read ids are cut at the first '|' (core:808-809) */
     int32_t base_locus;        /* 0 unless typing inside a genotype genome (core:437-441) */
-    int32_t n_threads;         /* host threads for record intake; <= 0 = library default */
+    int32_t n_threads;         /* host threads for record intake and walk; <= 0 = library default */
+    int32_t chunk_bytes;       /* alignment text of a unit is walked in tasks of about this size, cut where the read
+                                  id changes (input is name sorted); <= 0 = library default (128 KiB) */
 } hgt_params;
 
 /* ctx may be NULL: the locus then only carries the host tables (used by hgt_host_walk). */
@@ -179,6 +181,13 @@ int hgt_batch_create(hgt_ctx *ctx, int32_t n_loci, hgt_locus *const *loci, const
                      int32_t remove_low_abundance_alleles, hgt_batch **out);
 void hgt_batch_free(hgt_batch *b);
 int64_t hgt_batch_add_unit(hgt_batch *b, int32_t locus_index, const char *sam_text, size_t n_bytes);
+/* Read-sharded locus (several processes hold disjoint reads of the same (sample, locus)): error
+ * correction depends on the pileup of ALL reads (common:1124-1134), so prepare calls the hook once, after the raw
+ * base counts of this process are on the device and before nt_set is derived; the hook sums dev_counts
+ * (n_u32 uint32 values: every unit's [ref_len][6] histogram, units in add order) over the ranks in place, e.g. with
+ * ncclAllReduce, and returns 0.  `stream` is idle when the hook runs. */
+typedef int (*hgt_pileup_hook)(void *arg, void *dev_counts, size_t n_u32, void *stream);
+int hgt_batch_set_pileup_hook(hgt_batch *b, hgt_pileup_hook fn, void *arg);
 int hgt_batch_prepare(hgt_batch *b);
 int hgt_batch_execute(hgt_batch *b, void *stream);
 int hgt_batch_finish(hgt_batch *b, void *stream);

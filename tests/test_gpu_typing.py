@@ -100,8 +100,9 @@ def test_tables_bit_exact_vs_oracle_synthetic(seed):
     t.close()
 
 
+@pytest.mark.parametrize("chunk_bytes", [0, 4000])
 @pytest.mark.parametrize("name", ["hla_pair_err", "cyp_pair", "hla_indel"])
-def test_batch_matches_reference(name):
+def test_batch_matches_reference(name, chunk_bytes):
     """All locus runs of a scenario as ONE batch (several loci, several units per locus): tables, counts and the
     two-level EM result must equal the per-run goldens."""
     from hisatgenotype_b200 import typing_core as TC
@@ -114,8 +115,8 @@ def test_batch_matches_reference(name):
             genes.append(cap["gene"])
     names = {cap["gene"]: cap["Gene_names"] for cap in g["loci"]}
     loci = [product_locus(g, db, gene, names[gene]) for gene in genes]
-    batch = TC.Batch(loci, TC.make_params(p["num_editdist"], p["error_correction"], p["discordant"], p["simulation"]),
-                     p["remove_low"])
+    batch = TC.Batch(loci, TC.make_params(p["num_editdist"], p["error_correction"], p["discordant"], p["simulation"],
+                                          chunk_bytes=chunk_bytes), p["remove_low"])
     for cap in g["loci"]:
         batch.add_unit(genes.index(cap["gene"]), cap["sam"])
     batch.run()

@@ -21,8 +21,11 @@ def test_locus_tables_match_reference(name):
         t.close()
 
 
+@pytest.mark.parametrize("chunk_bytes", [0, 3000])
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
-def test_host_walk_tables(name):
+def test_host_walk_tables(name, chunk_bytes):
+    """chunk_bytes = 3000 cuts every unit into dozens of tasks at read-id boundaries (the decomposition the batch path
+    uses to spread one unit over all host threads); the result must not change."""
     from hisatgenotype_b200.typing_core import HostWalk, make_params
     g = load_golden(name)
     p = g["params"]
@@ -33,7 +36,7 @@ def test_host_walk_tables(name):
         c, m = pileup_arrays(counts, nt_sets)
         t = product_locus(g, db, cap["gene"], cap["Gene_names"], host_only=True)
         walk = HostWalk(t, cap["sam"], make_params(p["num_editdist"], p["error_correction"], p["discordant"],
-                                                   p["simulation"]), c, m)
+                                                   p["simulation"], chunk_bytes=chunk_bytes), c, m)
         assert walk.num_reads == cap["num_reads"]
         assert walk.num_pairs == cap["num_pairs"]
         res = tables_from_jobs(loc, walk, p["base"] == "hla")
