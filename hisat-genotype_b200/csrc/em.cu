@@ -22,6 +22,7 @@
 // grid syncs per sweep, so results are bit-reproducible run to run).  All sums use a fixed association.
 #include <cooperative_groups.h>
 #include <math.h>
+#include <string.h>
 
 #include <algorithm>
 #include <vector>
@@ -51,6 +52,7 @@ struct EmArgs {
     const unsigned long long *cnt_u64;  // class counts as integers (device-resident tables); overrides cnt
     const int32_t *C_ptr;               // number of classes read on the device at launch; overrides C
     const int32_t *class_first;         // tie-break key of each class (first pair index); default = class index
+    int32_t key_offset;                 // added to every class key (read-sharded locus: pairs of the lower ranks)
     double *prob;
     uint8_t *in_result;
     int32_t *first_class;
@@ -122,22 +124,21 @@ __device__ __forceinline__ double block_max(double v, double *red) {
 }
 __device__ __forceinline__ int block_or(int v) { return __syncthreads_or(v); }
 
-// One sweep over this CTA's class rows.  mode INIT: initial mass (common:1299-1309); NEXT: next_prob
-// (common:1311-1336); FIRSTK: only the dict insertion order of next_prob's output.
-template <int NA, bool COOP>
-__device__ void em_sweep(const EmArgs &a, const Smem &sm, int mode, const double *pin, const uint8_t *livein,
-                         double *pout, uint8_t *liveout, int32_t *fkout, int row_lo, int row_hi, bool resident,
-                         bool &loaded, uint32_t &parity, int *status) {
+// First half of a sweep: stage the input vector, then both halves of the E/M step over this CTA's rows.  Leaves the
+// per-allele sums in acc[] (thread tid, slot i <-> allele tid + i*EM_THREADS), the "met by a class with s_k > 0"
+// flags in `hit` and, in FIRSTK mode, the smallest class key in fk[].
+template <int NA>
+__device__ __forceinline__ void em_accumulate(const EmArgs &a, const Smem &sm, int mode, const double *pin,
+                                              const uint8_t *livein, int row_lo, int row_hi, bool resident, bool &loaded,
+                                              uint32_t &parity, double (&acc)[NA], int32_t (&fk)[NA], uint32_t &hit) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int A = a.A, wp = a.wp;
     const int Apad = wp * 64;
     // stage the input vector (0 for alleles that are not keys of the input dict)
     if (mode != MODE_INIT) {
-        for (int i = tid; i < Apad; i += EM_THREADS) sm.p[i] = (i < A && livein[i]) ? pin[i] : 0.0;
+        for (int i = tid; i < Apad; i += EM_THREADS) sm.p[i] = (i < A && (!livein || livein[i])) ? pin[i] : 0.0;
     }
-    double acc[NA];
-    int32_t fk[NA];
-    uint32_t hit = 0;
+    hit = 0;
 #pragma unroll
     for (int i = 0; i < NA; i++) {
         acc[i] = 0.0;
@@ -183,7 +184,7 @@ __device__ void em_sweep(const EmArgs &a, const Smem &sm, int mode, const double
                 for (int e = e0; e < e1; e++) {
                     const int r = sm.c_row[e];
                     if (sm.w[r] < 0.0) continue;
-                    if ((sm.c_word[e] >> lane) & 1u) fk[i] = min(fk[i], a.class_first ? a.class_first[r] : r);
+                    if ((sm.c_word[e] >> lane) & 1u) fk[i] = min(fk[i], (a.class_first ? a.class_first[r] : r) + a.key_offset);
                 }
             } else {
                 double x = 0.0;
@@ -250,7 +251,7 @@ __device__ void em_sweep(const EmArgs &a, const Smem &sm, int mode, const double
         if (mode == MODE_FIRSTK) {
             for (int r = 0; r < nr; r++) {
                 if (!sm.valid[r]) continue;
-                const int32_t key = a.class_first ? a.class_first[r0 + r] : r0 + r;
+                const int32_t key = (a.class_first ? a.class_first[r0 + r] : r0 + r) + a.key_offset;
 #pragma unroll
                 for (int i = 0; i < NA; i++) {
                     const int al = tid + i * EM_THREADS;
@@ -280,6 +281,21 @@ __device__ void em_sweep(const EmArgs &a, const Smem &sm, int mode, const double
         }
         __syncthreads();
     }
+}
+
+// One sweep over this CTA's class rows.  mode INIT: initial mass (common:1299-1309); NEXT: next_prob
+// (common:1311-1336); FIRSTK: only the dict insertion order of next_prob's output.
+template <int NA, bool COOP>
+__device__ void em_sweep(const EmArgs &a, const Smem &sm, int mode, const double *pin, const uint8_t *livein,
+                         double *pout, uint8_t *liveout, int32_t *fkout, int row_lo, int row_hi, bool resident,
+                         bool &loaded, uint32_t &parity, int *status) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int A = a.A, wp = a.wp;
+    const int Apad = wp * 64;
+    double acc[NA];
+    int32_t fk[NA];
+    uint32_t hit = 0;
+    em_accumulate<NA>(a, sm, mode, pin, livein, row_lo, row_hi, resident, loaded, parity, acc, fk, hit);
     // ---- cross-CTA reduction (cooperative launch only) ------------------------------------------------------
     if (COOP) {
         cg::grid_group grid = cg::this_grid();
@@ -1050,6 +1066,65 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
     }
 }
 
+// ---- partial sweeps for a read-sharded locus ---------------------------------------------------------
+// The class rows of one locus are spread over several GPUs; one next_prob() is then: every rank runs em_part_kernel +
+// em_part_reduce_kernel over ITS rows with the global probability vector, the per-allele sums are all-reduced (NCCL),
+// and every rank finishes the step identically (hisat-genotype_b200/em_dist.py).
+template <int NA>
+__global__ void __launch_bounds__(EM_THREADS, 1) em_part_kernel(EmArgs a, int mode, const double *__restrict__ pin) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int tid = threadIdx.x;
+    Smem sm;
+    sm.mbar = reinterpret_cast<uint64_t *>(smem_raw);
+    sm.red = reinterpret_cast<double *>(smem_raw + 16);
+    sm.lv = nullptr; sm.cnt = nullptr; sm.cm64 = nullptr; sm.c64 = nullptr;
+    sm.row_off = nullptr; sm.col_off = nullptr; sm.r_word = nullptr; sm.c_word = nullptr; sm.r_col = nullptr;
+    sm.c_row = nullptr; sm.dense_g = nullptr;
+    const int Apad = a.wp * 64;
+    sm.p = sm.red + 40;
+    sm.w = sm.p + Apad;
+    sm.slab = reinterpret_cast<uint64_t *>(sm.w + a.slab_rows);
+    sm.valid = reinterpret_cast<uint8_t *>(sm.slab + (size_t)a.slab_rows * a.wp);
+    if (tid == 0) {
+        mbar_init(sm.mbar, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    const int G = gridDim.x, g = blockIdx.x;
+    const int per = (a.C + G - 1) / G;
+    const int row_lo = min(a.C, g * per), row_hi = min(a.C, row_lo + per);
+    bool loaded = false;
+    uint32_t parity = 0;
+    double acc[NA];
+    int32_t fk[NA];
+    uint32_t hit = 0;
+    em_accumulate<NA>(a, sm, mode, pin, nullptr, row_lo, row_hi, false, loaded, parity, acc, fk, hit);
+#pragma unroll
+    for (int i = 0; i < NA; i++) {
+        const int al = tid + i * EM_THREADS;
+        if (al < a.A) {
+            a.part_acc[(size_t)g * Apad + al] = acc[i];
+            a.part_aux[(size_t)g * Apad + al] = (mode == MODE_FIRSTK) ? fk[i] : (int32_t)((hit >> i) & 1u);
+        }
+    }
+}
+
+__global__ void em_part_reduce_kernel(int G, int A, int Apad, int mode, const double *__restrict__ part_acc,
+                                      const int32_t *__restrict__ part_aux, double *__restrict__ acc_out,
+                                      int32_t *__restrict__ aux_out) {
+    const int al = blockIdx.x * blockDim.x + threadIdx.x;
+    if (al >= A) return;
+    double s = 0.0;
+    int32_t x = (mode == MODE_FIRSTK) ? FK_NONE : 0;
+    for (int g = 0; g < G; g++) {  // fixed order: reproducible
+        s += part_acc[(size_t)g * Apad + al];
+        const int32_t y = part_aux[(size_t)g * Apad + al];
+        x = (mode == MODE_FIRSTK) ? min(x, y) : (x | y);
+    }
+    acc_out[al] = s;
+    aux_out[al] = x;
+}
+
 struct EmPlan {
     int na;
     int slab_rows;
@@ -1253,7 +1328,7 @@ extern "C" int hgt_em_dev(hgt_ctx *ctx, void *stream, const uint64_t *class_bits
     EmArgs a;
     a.bits = class_bits; a.cnt = class_count; a.len = allele_len;
     a.C = n_classes; a.A = n_alleles; a.wp = wp; a.remove_low = remove_low; a.fixed_iters = fixed_iters;
-    a.cnt_u64 = nullptr; a.C_ptr = nullptr; a.class_first = nullptr;
+    a.cnt_u64 = nullptr; a.C_ptr = nullptr; a.class_first = nullptr; a.key_offset = 0;
     a.prob = prob; a.in_result = in_result; a.first_class = first_class; a.iters_status = iters_status;
     a.vec = w.vec; a.live = w.live; a.part_acc = w.part_acc; a.part_aux = w.part_aux;
     a.red_acc = w.red_acc; a.red_aux = w.red_aux;
@@ -1380,7 +1455,7 @@ extern "C" int hgt_em_batch(hgt_ctx *ctx, int32_t n_problems, const uint64_t *cl
         a.cnt = reinterpret_cast<double *>(d + o_cnt) + class_off[i];
         a.len = allele_len ? reinterpret_cast<double *>(d + o_len) + allele_off[i] : nullptr;
         a.C = C; a.A = A; a.wp = wp; a.remove_low = remove_low ? remove_low[i] : 0; a.fixed_iters = 0;
-        a.cnt_u64 = nullptr; a.C_ptr = nullptr; a.class_first = nullptr;
+        a.cnt_u64 = nullptr; a.C_ptr = nullptr; a.class_first = nullptr; a.key_offset = 0;
         a.prob = reinterpret_cast<double *>(d + o_prob) + allele_off[i];
         a.in_result = d + o_in + allele_off[i];
         a.first_class = reinterpret_cast<int32_t *>(d + o_fk) + allele_off[i];
@@ -1424,6 +1499,57 @@ extern "C" int hgt_em_batch(hgt_ctx *ctx, int32_t n_problems, const uint64_t *cl
     return HGT_OK;
 }
 
+extern "C" size_t hgt_em_partial_workspace_bytes(const hgt_ctx *ctx, int32_t n_alleles) {
+    const size_t Apad = (size_t)hgt_row_pitch(n_alleles) * 64;
+    const int G = ctx ? ctx->sm_count : 148;
+    return align_up((size_t)G * Apad * 8, 256) + align_up((size_t)G * Apad * 4, 256);
+}
+
+extern "C" int hgt_em_partial_dev(hgt_ctx *ctx, void *stream, const uint64_t *class_bits, const double *class_count_f64,
+                                  const uint64_t *class_count_u64, const int32_t *class_key, int32_t key_offset,
+                                  int32_t n_classes, int32_t n_alleles, int32_t wp, const double *p_in, int32_t mode,
+                                  double *acc_out, int32_t *aux_out, void *workspace) {
+    if (!ctx || !acc_out || !aux_out || !workspace || (!class_count_f64 && !class_count_u64 && n_classes > 0) ||
+        (mode != MODE_INIT && !p_in) || mode < 0 || mode > 2 || (n_classes > 0 && !class_bits)) {
+        hgt_set_error("hgt_em_partial_dev: bad argument");
+        return HGT_ERR_ARG;
+    }
+    if (wp != hgt_row_pitch(n_alleles) || n_alleles < 1 || n_classes < 0) {
+        hgt_set_error("hgt_em_partial_dev: need n_alleles >= 1 and wp == hgt_row_pitch(n_alleles)");
+        return HGT_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const size_t Apad = (size_t)wp * 64;
+    int G = ctx->sm_count;
+    if (G > n_classes) G = n_classes < 1 ? 1 : n_classes;
+    EmPlan plan;
+    HGT_CHECK(em_plan(ctx, (n_classes + G - 1) / G, n_alleles, wp, &plan));
+    EmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.bits = class_bits; a.cnt = class_count_f64; a.cnt_u64 = reinterpret_cast<const unsigned long long *>(class_count_u64);
+    a.class_first = class_key; a.key_offset = key_offset;
+    a.C = n_classes; a.A = n_alleles; a.wp = wp; a.slab_rows = plan.slab_rows;
+    unsigned char *w = static_cast<unsigned char *>(workspace);
+    a.part_acc = reinterpret_cast<double *>(w);
+    a.part_aux = reinterpret_cast<int32_t *>(w + align_up((size_t)ctx->sm_count * Apad * 8, 256));
+    void (*kern)(EmArgs, int, const double *) = nullptr;
+    switch (plan.na) {
+        case 1: kern = em_part_kernel<1>; break;
+        case 2: kern = em_part_kernel<2>; break;
+        case 4: kern = em_part_kernel<4>; break;
+        case 8: kern = em_part_kernel<8>; break;
+        default: kern = em_part_kernel<16>; break;
+    }
+    HGT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem));
+    kern<<<G, EM_THREADS, plan.smem, st>>>(a, mode, p_in);
+    HGT_CUDA(cudaGetLastError());
+    em_part_reduce_kernel<<<(n_alleles + 255) / 256, 256, 0, st>>>(G, n_alleles, (int)Apad, mode, a.part_acc, a.part_aux,
+                                                                   acc_out, aux_out);
+    HGT_CUDA(cudaGetLastError());
+    ctx->launches += 2;
+    return HGT_OK;
+}
+
 // ---- internal: batched EM on device-resident class tables (used by typing.cu) ----------------------------------
 #include "em_internal.h"
 
@@ -1453,7 +1579,7 @@ int hgt_em_batch_dev(hgt_ctx *ctx, cudaStream_t st, int n_problems, const EmDevP
         const size_t Apad = (size_t)pr[i].wp * 64;
         a.bits = pr[i].bits; a.cnt = nullptr; a.len = pr[i].len;
         a.C = pr[i].C_max; a.A = pr[i].A; a.wp = pr[i].wp; a.remove_low = pr[i].remove_low; a.fixed_iters = 0;
-        a.cnt_u64 = pr[i].cnt; a.C_ptr = pr[i].C_ptr; a.class_first = pr[i].class_first;
+        a.cnt_u64 = pr[i].cnt; a.C_ptr = pr[i].C_ptr; a.class_first = pr[i].class_first; a.key_offset = 0;
         a.prob = pr[i].prob; a.in_result = pr[i].in_result; a.first_class = pr[i].first_class;
         a.iters_status = pr[i].iters_status;
         a.part_acc = nullptr; a.part_aux = nullptr; a.red_acc = nullptr; a.red_aux = nullptr;

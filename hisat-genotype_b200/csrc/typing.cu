@@ -857,26 +857,32 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 }
 
 // Gene_counts (core:1187-1190) of table (unit, 0): counts[a] = sum of class counts over classes holding a;
-// first[a] = first pair whose class holds a.  grid.y = unit.
-__global__ void table_counts_kernel(int A, int wp, int table, ClassPool pool, long long *__restrict__ a_count,
+// first[a] = first pair whose class holds a.  grid = (allele tiles, units, class chunks): a CTA folds one chunk of
+// COUNT_CHUNK classes into the totals with integer atomics (order-independent, so still exact).
+constexpr int COUNT_CHUNK = 512;
+__global__ void table_counts_kernel(int A, int wp, int table, ClassPool pool, unsigned long long *__restrict__ a_count,
                                     int32_t *__restrict__ a_first) {
     const int u = blockIdx.y;
     const int ut = u * 4 + table;
     const int a = blockIdx.x * blockDim.x + threadIdx.x;
-    if (a >= A) return;
     const int64_t base = pool.ut_base[ut];
     const int n = min(pool.ut_ncls[ut], (int)(pool.ut_base[ut + 1] - base));
-    long long c = 0;
+    const int k0 = blockIdx.z * COUNT_CHUNK, k1 = min(n, k0 + COUNT_CHUNK);
+    if (a >= A || k0 >= k1) return;
+    unsigned long long c = 0;
     int32_t f = 0x7fffffff;
-    for (int k = 0; k < n; k++) {
+#pragma unroll 4
+    for (int k = k0; k < k1; k++) {
         const uint64_t w = pool.bits[(size_t)(base + k) * wp + (a >> 6)];
         if ((w >> (a & 63)) & 1ull) {
-            c += (long long)pool.count[base + k];
+            c += pool.count[base + k];
             f = min(f, pool.first[base + k]);
         }
     }
-    a_count[(size_t)u * A + a] = c;
-    a_first[(size_t)u * A + a] = c ? f : -1;
+    if (c) {
+        atomicAdd(&a_count[(size_t)u * A + a], c);
+        atomicMin(&a_first[(size_t)u * A + a], f);
+    }
 }
 
 // pileup-derived per-position flags the host walk needs: nt_set mask and the hla deletion-artefact flag
@@ -1089,6 +1095,7 @@ struct hgt_batch {
     std::vector<TaskHost> tasks;
     std::vector<LocusBatch> lb;
     bool keep_counts = false;
+    bool skip_em = false;
     int (*pileup_hook)(void *arg, void *dev_counts, size_t n_u32, void *stream) = nullptr;
     void *pileup_hook_arg = nullptr;
     bool prepared = false, executed = false, finished = false;
@@ -1633,8 +1640,13 @@ static int batch_execute(hgt_batch *b, cudaStream_t st) {
         // Gene_counts of the Gene table
         {
             b->timer.begin(ctx, st, 3);
-            dim3 grid((loc->A + 127) / 128, (unsigned)n_units);
-            table_counts_kernel<<<grid, 128, 0, st>>>(loc->A, loc->wp, 0, lb.pool(), lb.d_acount.as<long long>(),
+            int64_t max_pairs = 1;
+            for (int u : lb.units) max_pairs = std::max<int64_t>(max_pairs, b->units[u].num_pairs);
+            dim3 grid((loc->A + 127) / 128, (unsigned)n_units,
+                      (unsigned)std::min<int64_t>((max_pairs + COUNT_CHUNK - 1) / COUNT_CHUNK, 65535));
+            HGT_CUDA(cudaMemsetAsync(lb.d_acount.p, 0, n_units * (size_t)loc->A * 8, st));
+            HGT_CUDA(cudaMemsetAsync(lb.d_afirst.p, 0x7f, n_units * (size_t)loc->A * 4, st));
+            table_counts_kernel<<<grid, 128, 0, st>>>(loc->A, loc->wp, 0, lb.pool(), lb.d_acount.as<unsigned long long>(),
                                                       lb.d_afirst.as<int32_t>());
             ctx->launches++;
             b->timer.end(1);
@@ -1660,10 +1672,12 @@ static int batch_execute(hgt_batch *b, cudaStream_t st) {
         em_problems(ctx, lb, table, all, cmax.data(), alive.data(), nullptr, loc->is_hla ? b->remove_low : 0, lb.d_prob, lb.d_inres,
                     lb.d_fk, lb.d_is, &probs);
     }
-    b->timer.begin(ctx, st, 4);
-    const int64_t l0 = ctx->launches;
-    HGT_CHECK(hgt_em_batch_dev(ctx, st, (int)probs.size(), probs.data(), b->h_em_args[0].p, b->d_em_args[0].p));
-    b->timer.end((int)(ctx->launches - l0));
+    if (!b->skip_em) {
+        b->timer.begin(ctx, st, 4);
+        const int64_t l0 = ctx->launches;
+        HGT_CHECK(hgt_em_batch_dev(ctx, st, (int)probs.size(), probs.data(), b->h_em_args[0].p, b->d_em_args[0].p));
+        b->timer.end((int)(ctx->launches - l0));
+    }
     b->executed = true;
     return HGT_OK;
 }
@@ -1671,6 +1685,17 @@ static int batch_execute(hgt_batch *b, cudaStream_t st) {
 // ---- stage 3: results back; on the hla path the second-level EM over full-length alleles (core:1739-1782) -------
 static int batch_finish(hgt_batch *b, cudaStream_t st) {
     hgt_ctx *ctx = b->ctx;
+    if (b->skip_em) {
+        HGT_CUDA(cudaStreamSynchronize(st));
+        b->timer.resolve();
+        for (LocusBatch &lb : b->lb) {
+            if (lb.units.empty()) continue;
+            lb.has2.assign(lb.units.size(), 0);
+            for (size_t i = 0; i < lb.units.size() * 3; i++) lb.is[i] = i % 3 == 1 ? 1 : 0;  // status 1 = EM not run
+        }
+        b->finished = true;
+        return HGT_OK;
+    }
     for (LocusBatch &lb : b->lb) {
         if (lb.units.empty()) continue;
         const hgt_locus *loc = lb.loc;
@@ -1975,7 +2000,7 @@ extern "C" int hgt_batch_unit_table(hgt_batch *b, int64_t unit, int32_t table, u
         if (table == 0) {
             for (int a = 0; a < A; a++) {
                 if (allele_count) allele_count[a] = ac[a];
-                if (allele_first) allele_first[a] = af[a];
+                if (allele_first) allele_first[a] = ac[a] ? af[a] : -1;
             }
         } else {  // other tables: derive from the class rows just read
             for (int a = 0; a < A; a++) {
@@ -1990,6 +2015,30 @@ extern "C" int hgt_batch_unit_table(hgt_batch *b, int64_t unit, int32_t table, u
             }
         }
     }
+    return HGT_OK;
+}
+
+extern "C" int hgt_batch_set_skip_em(hgt_batch *b, int32_t skip) {
+    if (!b) return HGT_ERR_ARG;
+    b->skip_em = skip != 0;
+    return HGT_OK;
+}
+
+extern "C" int hgt_batch_unit_table_dev(const hgt_batch *b, int64_t unit, int32_t table, const uint64_t **class_bits,
+                                        const uint64_t **class_count, const int32_t **class_first, int32_t *n_classes) {
+    HGT_CHECK(unit_check(b, unit, true));
+    if (table < 0 || table > 3) {
+        hgt_set_error("hgt_batch_unit_table_dev: table must be 0..3");
+        return HGT_ERR_ARG;
+    }
+    const UnitHost &U = b->units[unit];
+    const LocusBatch &lb = b->lb[U.locus];
+    const int ut = U.local * 4 + table;
+    const int64_t base = lb.ut_base[ut];
+    if (class_bits) *class_bits = lb.d_bits.as<uint64_t>() + (size_t)base * lb.loc->wp;
+    if (class_count) *class_count = lb.d_count.as<uint64_t>() + base;
+    if (class_first) *class_first = lb.d_first.as<int32_t>() + base;
+    if (n_classes) *n_classes = (int32_t)std::min<int64_t>(lb.ut_ncls[ut], lb.ut_base[ut + 1] - base);
     return HGT_OK;
 }
 

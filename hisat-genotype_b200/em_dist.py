@@ -1,0 +1,180 @@
+"""EM abundance for ONE locus whose reads (hence class tables) are sharded over several GPUs.
+
+Every rank holds the Gene_cmpt classes of its own reads; classes that occur on several ranks simply appear several
+times, which the EM sums do not mind.  One next_prob() evaluation (reference hisatgenotype_typing_common.py:1311-1336)
+is then
+    local partial sweep over this rank's class rows  (CUDA: hgt_em_partial_dev, csrc/em.cu)
+    all-reduce of the per-allele sums                (torch.distributed: NCCL over NVLink; 8*A bytes, 64 KB at A = 8 k)
+    normalisation / SQUAREM / pruning                (identical on every rank: O(A) vector work)
+and the control flow below is the reference's loop (common:1351-1409) statement by statement, so a world of one
+rank reproduces hgt_em and a world of N ranks differs from it only by the association of the partial sums.
+
+The sweep is a backend object so that the distributed control flow can be exercised without a GPU
+(tests/test_dist_em.py runs it under gloo with a numpy sweep); the product backend is CudaSweep and has no
+fallback.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+MODE_INIT, MODE_NEXT, MODE_FIRSTK = 0, 1, 2
+FK_NONE = 0x7FFFFFFF
+
+
+class CudaSweep:
+    """Partial sweeps on this rank's device-resident class table (pointers from hgt_batch_unit_table_dev or tensors)."""
+
+    def __init__(self, n_alleles, bits_ptr, n_classes, count_u64_ptr=None, count_f64_ptr=None, key_ptr=None, key_offset=0,
+                 device=None, keep=()):
+        self.A = int(n_alleles)
+        self.wp = _lib.row_pitch(self.A)
+        self.C = int(n_classes)
+        self.bits_ptr, self.cnt_u64, self.cnt_f64, self.key_ptr = bits_ptr, count_u64_ptr, count_f64_ptr, key_ptr
+        self.key_offset = int(key_offset)
+        self.dev_index = _lib.default_device() if device is None else device
+        self.device = torch.device("cuda", self.dev_index)
+        self.ctx = _lib.ctx(self.dev_index)
+        L = _lib.lib()
+        L.hgt_em_partial_workspace_bytes.restype = ctypes.c_size_t
+        L.hgt_em_partial_workspace_bytes.argtypes = [ctypes.c_void_p, ctypes.c_int32]
+        L.hgt_em_partial_dev.restype = ctypes.c_int
+        L.hgt_em_partial_dev.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_int32] * 4 + [ctypes.c_void_p, ctypes.c_int32,
+                                                                                      ctypes.c_void_p, ctypes.c_void_p,
+                                                                                      ctypes.c_void_p]
+        self.L = L
+        self.ws = torch.empty(L.hgt_em_partial_workspace_bytes(self.ctx, self.A), dtype=torch.uint8, device=self.device)
+        self._keep = keep  # tensors that own the memory behind the raw pointers
+
+    @classmethod
+    def from_arrays(cls, class_bits, class_count, n_alleles, class_key=None, key_offset=0, device=None):
+        dev = torch.device("cuda", _lib.default_device() if device is None else device)
+        bits = torch.from_numpy(np.ascontiguousarray(class_bits, np.uint64).view(np.int64)).to(dev)
+        cnt = torch.from_numpy(np.ascontiguousarray(class_count, np.float64)).to(dev)
+        key = None if class_key is None else torch.from_numpy(np.ascontiguousarray(class_key, np.int32)).to(dev)
+        return cls(n_alleles, bits.data_ptr(), len(class_count), None, cnt.data_ptr(), None if key is None else key.data_ptr(),
+                   key_offset, dev.index, keep=(bits, cnt, key))
+
+    def sweep(self, mode, p):
+        acc = torch.empty(self.A, dtype=torch.float64, device=self.device)
+        aux = torch.empty(self.A, dtype=torch.int32, device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        rc = self.L.hgt_em_partial_dev(self.ctx, stream, self.bits_ptr, self.cnt_f64, self.cnt_u64, self.key_ptr,
+                                       self.key_offset, self.C, self.A, self.wp, None if p is None else p.data_ptr(), mode,
+                                       acc.data_ptr(), aux.data_ptr(), self.ws.data_ptr())
+        _lib.check(rc)
+        return acc, aux
+
+
+def _allreduce(t, op, group):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=op, group=group)
+    return t
+
+
+def single_abundance_sharded(backend, allele_len=None, remove_low=False, group=None, max_iter=1000):
+    """Returns (prob[A], in_result[A] bool, first_key[A] int32, iters) as torch tensors on backend.device.
+    Raises KeyError / ZeroDivisionError where the reference does (common:1365-1369, 1285-1297)."""
+    import torch.distributed as dist
+    SUM = dist.ReduceOp.SUM if dist.is_available() else None
+    MAX = dist.ReduceOp.MAX if dist.is_available() else None
+    MIN = dist.ReduceOp.MIN if dist.is_available() else None
+    dev = backend.device
+    A = backend.A
+    ln = None if allele_len is None else torch.as_tensor(np.asarray(allele_len, np.float64), device=dev)
+    zero = torch.zeros(A, dtype=torch.float64, device=dev)
+
+    def finish(q, keys):
+        if ln is not None:
+            q = q / ln
+        q = torch.where(keys, q, zero)
+        total = q.sum()
+        if bool(keys.any()) and float(total) == 0.0:
+            raise ZeroDivisionError("float division by zero")
+        return torch.where(keys, q / total, zero), keys
+
+    def next_prob(p, live):
+        pm = torch.where(live, p, zero)
+        acc, hit = backend.sweep(MODE_NEXT, pm)
+        _allreduce(acc, SUM, group)
+        _allreduce(hit, MAX, group)
+        return finish(pm * acc, live & (hit > 0))
+
+    acc, hit = backend.sweep(MODE_INIT, None)
+    _allreduce(acc, SUM, group)
+    _allreduce(hit, MAX, group)
+    p0, l0 = finish(acc, hit > 0)
+    diff, it = 1.0, 0
+    last = None
+    while diff > 0.0001 and it < max_iter:
+        p1, l1 = next_prob(p0, l0)
+        p2, l2 = next_prob(p1, l1)
+        if bool((l0 & ~(l1 & l2)).any()):
+            raise KeyError("allele vanished from next_prob output during SQUAREM step")
+        r = torch.where(l0, p1 - p0, zero)
+        v = torch.where(l0, p2 - p1 - r, zero)
+        ssr, ssv = float((r * r).sum()), float((v * v).sum())
+        if ssv > 0.0:
+            g = -np.sqrt(ssr / ssv)
+            p3 = torch.where(l0, torch.clamp(p0 - 2 * g * r + g * g * v, min=0.0), zero)
+            p1, l1 = next_prob(p3, l2)
+            last = (p3, l2)
+        else:
+            last = (p0, l0)
+        diff = float(torch.where(l0, torch.where(l1, (p0 - p1).abs(), p0), zero).sum())
+        p0, l0 = p1, l1
+        if it >= 10 and remove_low:
+            p0, l0 = _prune(p0, l0, zero)
+        it += 1
+    if remove_low:
+        p0, l0 = _prune(p0, l0, zero)
+    q = p0 / ln if ln is not None else p0
+    q = torch.where(l0, q, zero)
+    total = q.sum()
+    if bool(l0.any()) and float(total) == 0.0:
+        raise ZeroDivisionError("float division by zero")
+    prob = torch.where(l0, q / total, zero)
+    first = torch.full((A,), FK_NONE, dtype=torch.int32, device=dev)
+    if last is not None:
+        pm = torch.where(last[1], last[0], zero)
+        _, fk = backend.sweep(MODE_FIRSTK, pm)
+        _allreduce(fk, MIN, group)
+        first = torch.where(last[1], fk, first)
+    return prob, l0, first, it
+
+
+def _prune(p, live, zero):
+    if not bool(live.any()):
+        return p, live
+    mx = torch.where(live, p, torch.full_like(p, -1.0)).max()
+    keep = live & (p >= mx / 10.0)
+    return torch.where(keep, p, zero), keep
+
+
+def pileup_allreduce_hook(group=None):
+    """ctypes callback for hgt_batch_set_pileup_hook: sums the raw base counts of a read-sharded locus over the ranks
+    (the reference derives nt_set from the pileup of ALL reads, common:1124-1134)."""
+    import torch.distributed as dist
+
+    class _Alias:
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"data": (ptr, False), "shape": (n,), "typestr": "<i4", "version": 2}
+
+    @ctypes.CFUNCTYPE(ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p)
+    def hook(_arg, dev_counts, n_u32, _stream):
+        try:
+            t = torch.as_tensor(_Alias(dev_counts, int(n_u32)), device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)  # int32 wrap-around == uint32 sum
+            torch.cuda.synchronize()
+            return 0
+        except Exception:  # never unwind through the C frame
+            import traceback
+            traceback.print_exc()
+            return 1
+
+    return hook

@@ -84,6 +84,12 @@ def _bind(L):
     L.hgt_batch_unit_em.argtypes = [vp, i64, i32, vp, vp, vp, P(i32), P(i32)]
     L.hgt_batch_unit_abundance.restype = ctypes.c_int
     L.hgt_batch_unit_abundance.argtypes = [vp, i64, i32, vp, vp, P(i32)]
+    L.hgt_batch_set_skip_em.restype = ctypes.c_int
+    L.hgt_batch_set_skip_em.argtypes = [vp, i32]
+    L.hgt_batch_set_pileup_hook.restype = ctypes.c_int
+    L.hgt_batch_set_pileup_hook.argtypes = [vp, vp, vp]
+    L.hgt_batch_unit_table_dev.restype = ctypes.c_int
+    L.hgt_batch_unit_table_dev.argtypes = [vp, i64, i32, P(vp), P(vp), P(vp), P(i32)]
     L.hgt_host_walk.restype = ctypes.c_int
     L.hgt_host_walk.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, P(Params), vp, vp, P(vp)]
     L.hgt_walk_summary.restype = ctypes.c_int

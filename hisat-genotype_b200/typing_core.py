@@ -295,6 +295,43 @@ class Batch:
             combined[allele] = prob * exon_prob_sum
         return sorted(([a, p] for a, p in combined.items()), key=lambda x: x[1], reverse=True)
 
+    # ---- read-sharded locus (several ranks hold disjoint reads of the same unit) ---------------------
+    def set_pileup_allreduce(self, group=None):
+        """Sum the raw pileup counts over the ranks before nt_set is derived (needs torch.distributed initialised)."""
+        from . import em_dist
+        self._hook = em_dist.pileup_allreduce_hook(group)  # keep the callback alive
+        _lib.check(lib().hgt_batch_set_pileup_hook(self.handle, ctypes.cast(self._hook, ctypes.c_void_p), None))
+
+    def set_skip_em(self, skip=True):
+        _lib.check(lib().hgt_batch_set_skip_em(self.handle, 1 if skip else 0))
+
+    def unit_table_dev(self, u, table):
+        """(bits_ptr, count_u64_ptr, first_ptr, n_classes) of a device-resident table."""
+        b, c, f = ctypes.c_void_p(), ctypes.c_void_p(), ctypes.c_void_p()
+        n = ctypes.c_int32(0)
+        _lib.check(lib().hgt_batch_unit_table_dev(self.handle, u, table, ctypes.byref(b), ctypes.byref(c), ctypes.byref(f),
+                                                  ctypes.byref(n)))
+        return b.value, c.value, f.value, n.value
+
+    def sharded_abundance(self, u, table=TABLE_GENE, lengths=None, remove_low=False, group=None):
+        """single_abundance over the union of every rank's classes of unit u (the sharded EM of em_dist.py).
+        Returns (ranked [[allele, prob]], iterations); identical on every rank."""
+        import torch
+        import torch.distributed as dist
+        from . import em_dist
+        t = self.loci[self.unit_locus[u]]
+        bits, cnt, first, n = self.unit_table_dev(u, table)
+        offset = 0
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            mine = torch.tensor([self.unit_summary(u)["num_pairs"]], dtype=torch.int64, device="cuda")
+            every = [torch.zeros_like(mine) for _ in range(dist.get_world_size(group))]
+            dist.all_gather(every, mine, group=group)
+            offset = int(sum(int(x) for x in every[:dist.get_rank(group)]))
+        sweep = em_dist.CudaSweep(t.A, bits, n, count_u64_ptr=cnt, key_ptr=first, key_offset=offset, device=self.device)
+        ln = None if not lengths else np.asarray([lengths[x] for x in t.names], np.float64)
+        prob, live, fk, iters = em_dist.single_abundance_sharded(sweep, ln, remove_low, group)
+        return rank_result(t.names, prob.cpu().numpy(), live.cpu().numpy().astype(np.uint8), fk.cpu().numpy()), iters
+
     def unit_calls(self, u, max_n=None):
         """Gene_prob of the unit ranked natively (same result as unit_abundance); max_n limits the list length."""
         t = self.loci[self.unit_locus[u]]

@@ -94,6 +94,20 @@ int hgt_em_dev(hgt_ctx *ctx, void *stream, const uint64_t *class_bits, const dou
                int32_t fixed_iters, int32_t n_ctas, double *prob, uint8_t *in_result, int32_t *first_class,
                int32_t *iters_status /* [2]: iters, status */, void *workspace);
 
+/* Read-sharded locus: ONE partial sweep of next_prob() over the class rows that live on this device.
+ * mode 0: initial mass (common:1299-1309; p_in unused), 1: next_prob E/M sums (common:1311-1331), 2: smallest class
+ * key per allele (dict insertion order of the output, common:1324-1331).  p_in[n_alleles] holds the GLOBAL current
+ * probabilities with 0 for alleles that are not keys.  acc_out[a] = sum over local classes k with s_k > 0 that hold a
+ * of n_k / s_k (n_k / |class| in mode 0); aux_out[a] = 1 if any such class exists (modes 0, 1) or the smallest
+ * class_key + key_offset (mode 2; class_key NULL = class index).  The caller all-reduces acc_out (sum) and aux_out
+ * (max / min) over the ranks and finishes the step (hisat-genotype_b200/em_dist.py).  Exactly one of the two count
+ * arrays is non-NULL.  Device pointers, no synchronisation. */
+size_t hgt_em_partial_workspace_bytes(const hgt_ctx *ctx, int32_t n_alleles);
+int hgt_em_partial_dev(hgt_ctx *ctx, void *stream, const uint64_t *class_bits, const double *class_count_f64,
+                       const uint64_t *class_count_u64, const int32_t *class_key, int32_t key_offset, int32_t n_classes,
+                       int32_t n_alleles, int32_t wp, const double *p_in, int32_t mode, double *acc_out, int32_t *aux_out,
+                       void *workspace);
+
 /* ---- stage (a): per-read allele compatibility -----------------------------------------------------------
  * Replaces the per-read loop of typing() for index_type == "graph"
  *   reference hisatgenotype_modules/hisatgenotype_typing_core.py:598-1596 (add_count :626-677, add_stat
@@ -201,6 +215,12 @@ int hgt_batch_unit_summary(const hgt_batch *b, int64_t unit, int64_t *num_reads,
 int hgt_batch_unit_table(hgt_batch *b, int64_t unit, int32_t table, uint64_t *class_bits, int64_t *class_count,
                          int64_t *class_first, int64_t *allele_count, int64_t *allele_first);
 /* level 0: first-level EM; level 1: second-level EM (status 1 = not run for this unit, core:1752) */
+/* device pointers of one table of a finished (or executed) batch: class rows [n][wp], counts [n] (uint64) and
+ * first-seen pair indices [n]; valid until the batch is freed or executed again */
+int hgt_batch_unit_table_dev(const hgt_batch *b, int64_t unit, int32_t table, const uint64_t **class_bits,
+                             const uint64_t **class_count, const int32_t **class_first, int32_t *n_classes);
+/* skip != 0: execute/finish stop after the class tables (the caller runs the EM itself, e.g. the sharded EM) */
+int hgt_batch_set_skip_em(hgt_batch *b, int32_t skip);
 int hgt_batch_unit_em(const hgt_batch *b, int64_t unit, int32_t level, double *prob, uint8_t *in_result,
                       int32_t *first_class, int32_t *iters, int32_t *status);
 
