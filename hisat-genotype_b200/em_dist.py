@@ -79,46 +79,54 @@ def _allreduce(t, op, group):
 
 def single_abundance_sharded(backend, allele_len=None, remove_low=False, group=None, max_iter=1000):
     """Returns (prob[A], in_result[A] bool, first_key[A] int32, iters) as torch tensors on backend.device.
-    Raises KeyError / ZeroDivisionError where the reference does (common:1365-1369, 1285-1297)."""
+    Raises KeyError / ZeroDivisionError where the reference does (common:1365-1369, 1285-1297).
+    Per loop iteration: 3 sweeps + 3 all-reduces of 2*A doubles and two host synchronisations (the SQUAREM branch on
+    sum(v^2) > 0 and the convergence test are host decisions, exactly as in the reference's while loop)."""
     import torch.distributed as dist
     SUM = dist.ReduceOp.SUM if dist.is_available() else None
-    MAX = dist.ReduceOp.MAX if dist.is_available() else None
     MIN = dist.ReduceOp.MIN if dist.is_available() else None
     dev = backend.device
     A = backend.A
     ln = None if allele_len is None else torch.as_tensor(np.asarray(allele_len, np.float64), device=dev)
     zero = torch.zeros(A, dtype=torch.float64, device=dev)
+    bad = torch.zeros((), dtype=torch.bool, device=dev)  # "normalize() would divide by zero", checked once per iteration
+
+    def reduced_sweep(mode, pm):
+        acc, hit = backend.sweep(mode, pm)
+        both = torch.cat([acc, hit.to(torch.float64)])  # one all-reduce: sums and hit counts
+        _allreduce(both, SUM, group)
+        return both[:A], both[A:] > 0
 
     def finish(q, keys):
+        nonlocal bad
         if ln is not None:
             q = q / ln
         q = torch.where(keys, q, zero)
         total = q.sum()
-        if bool(keys.any()) and float(total) == 0.0:
-            raise ZeroDivisionError("float division by zero")
+        bad = bad | (keys.any() & (total == 0))
         return torch.where(keys, q / total, zero), keys
 
     def next_prob(p, live):
         pm = torch.where(live, p, zero)
-        acc, hit = backend.sweep(MODE_NEXT, pm)
-        _allreduce(acc, SUM, group)
-        _allreduce(hit, MAX, group)
-        return finish(pm * acc, live & (hit > 0))
+        acc, hit = reduced_sweep(MODE_NEXT, pm)
+        return finish(pm * acc, live & hit)
 
-    acc, hit = backend.sweep(MODE_INIT, None)
-    _allreduce(acc, SUM, group)
-    _allreduce(hit, MAX, group)
-    p0, l0 = finish(acc, hit > 0)
+    acc, hit = reduced_sweep(MODE_INIT, None)
+    p0, l0 = finish(acc, hit)
     diff, it = 1.0, 0
     last = None
     while diff > 0.0001 and it < max_iter:
         p1, l1 = next_prob(p0, l0)
         p2, l2 = next_prob(p1, l1)
-        if bool((l0 & ~(l1 & l2)).any()):
-            raise KeyError("allele vanished from next_prob output during SQUAREM step")
         r = torch.where(l0, p1 - p0, zero)
         v = torch.where(l0, p2 - p1 - r, zero)
-        ssr, ssv = float((r * r).sum()), float((v * v).sum())
+        scal = torch.stack([(r * r).sum(), (v * v).sum(), (l0 & ~(l1 & l2)).any().to(torch.float64),
+                            bad.to(torch.float64)]).cpu()  # host sync 1
+        if scal[3] != 0:
+            raise ZeroDivisionError("float division by zero")
+        if scal[2] != 0:
+            raise KeyError("allele vanished from next_prob output during SQUAREM step")
+        ssr, ssv = float(scal[0]), float(scal[1])
         if ssv > 0.0:
             g = -np.sqrt(ssr / ssv)
             p3 = torch.where(l0, torch.clamp(p0 - 2 * g * r + g * g * v, min=0.0), zero)
@@ -126,17 +134,18 @@ def single_abundance_sharded(backend, allele_len=None, remove_low=False, group=N
             last = (p3, l2)
         else:
             last = (p0, l0)
-        diff = float(torch.where(l0, torch.where(l1, (p0 - p1).abs(), p0), zero).sum())
+        d = torch.where(l0, torch.where(l1, (p0 - p1).abs(), p0), zero).sum()
         p0, l0 = p1, l1
         if it >= 10 and remove_low:
             p0, l0 = _prune(p0, l0, zero)
+        diff = float(d)  # host sync 2
         it += 1
     if remove_low:
         p0, l0 = _prune(p0, l0, zero)
     q = p0 / ln if ln is not None else p0
     q = torch.where(l0, q, zero)
     total = q.sum()
-    if bool(l0.any()) and float(total) == 0.0:
+    if bool(bad) or (bool(l0.any()) and float(total) == 0.0):
         raise ZeroDivisionError("float division by zero")
     prob = torch.where(l0, q / total, zero)
     first = torch.full((A,), FK_NONE, dtype=torch.int32, device=dev)
@@ -149,8 +158,7 @@ def single_abundance_sharded(backend, allele_len=None, remove_low=False, group=N
 
 
 def _prune(p, live, zero):
-    if not bool(live.any()):
-        return p, live
+    """select_alleles (common:1338-1346): keep p >= max/10 among the keys; no keys -> nothing to do."""
     mx = torch.where(live, p, torch.full_like(p, -1.0)).max()
     keep = live & (p >= mx / 10.0)
     return torch.where(keep, p, zero), keep
