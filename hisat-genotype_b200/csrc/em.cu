@@ -83,10 +83,8 @@ struct Smem {
     // ascending order, so all sums keep a fixed association
     const int32_t *row_off;   // [C+1]
     const int32_t *col_off;   // [2*wp+1]
-    const uint32_t *r_word;   // [nnzw]
-    const uint16_t *r_col;    // [nnzw] 32-bit word column of the entry
-    const uint32_t *c_word;   // [nnzw]
-    const uint16_t *c_row;    // [nnzw] class row of the entry
+    const uint64_t *r_ent;    // [nnzw] row-major:    low 32 bits = the word, high 32 bits = byte offset of p[32 * column]
+    const uint64_t *c_ent;    // [nnzw] column-major: low 32 bits = the word, high 32 bits = byte offset of w[row]
     const uint64_t *dense_g;  // global copy of the compacted dense rows (pitch = wp words), kept for one-off gathers
 };
 
@@ -148,33 +146,48 @@ __device__ __forceinline__ void em_accumulate(const EmArgs &a, const Smem &sm, i
     const uint32_t *slab32 = reinterpret_cast<const uint32_t *>(sm.slab);
     if (sm.row_off) {
         // ---- sparse resident form: cost follows the number of non-zero 32-bit words, not C x A -------------------
+        // One packed 64-bit entry per non-zero word; a whole warp takes an entry (word broadcast, lane = bit), so an
+        // entry costs LDS.64 + address add + LDS.64 + bit test + predicated DADD.  Four independent partial sums per
+        // row / two per column hide the DADD latency; the association is fixed, so results are reproducible.
         const int C = row_hi;
+        const unsigned char *p_lane = reinterpret_cast<const unsigned char *>(sm.p + lane);
+        int any_skipped = 0;
         for (int r = warp; r < C; r += EM_WARPS) {
             const int e0 = sm.row_off[r], e1 = sm.row_off[r + 1];
             double s = 0.0;
             if (mode == MODE_INIT) {
                 int pc = 0;
-                for (int e = e0 + lane; e < e1; e += 32) pc += __popc(sm.r_word[e]);
+                for (int e = e0 + lane; e < e1; e += 32) pc += __popc((uint32_t)sm.r_ent[e]);
                 for (int o = 16; o > 0; o >>= 1) pc += __shfl_xor_sync(0xffffffffu, pc, o);
                 s = (double)pc;
             } else {
-                double s1 = 0.0;
+                double s1 = 0.0, s2 = 0.0, s3 = 0.0;
                 int e = e0;
-                for (; e + 1 < e1; e += 2) {  // whole warp per entry: word broadcast, lane = bit
-                    const uint32_t m0 = sm.r_word[e], m1 = sm.r_word[e + 1];
-                    const int c0 = sm.r_col[e], c1 = sm.r_col[e + 1];
-                    if ((m0 >> lane) & 1u) s += sm.p[c0 * 32 + lane];
-                    if ((m1 >> lane) & 1u) s1 += sm.p[c1 * 32 + lane];
+                for (; e + 3 < e1; e += 4) {
+                    const uint64_t x0 = sm.r_ent[e], x1 = sm.r_ent[e + 1], x2 = sm.r_ent[e + 2], x3 = sm.r_ent[e + 3];
+                    const double p0 = *reinterpret_cast<const double *>(p_lane + (uint32_t)(x0 >> 32));
+                    const double p1 = *reinterpret_cast<const double *>(p_lane + (uint32_t)(x1 >> 32));
+                    const double p2 = *reinterpret_cast<const double *>(p_lane + (uint32_t)(x2 >> 32));
+                    const double p3 = *reinterpret_cast<const double *>(p_lane + (uint32_t)(x3 >> 32));
+                    if (((uint32_t)x0 >> lane) & 1u) s += p0;
+                    if (((uint32_t)x1 >> lane) & 1u) s1 += p1;
+                    if (((uint32_t)x2 >> lane) & 1u) s2 += p2;
+                    if (((uint32_t)x3 >> lane) & 1u) s3 += p3;
                 }
-                if (e < e1) {
-                    const uint32_t m0 = sm.r_word[e];
-                    if ((m0 >> lane) & 1u) s += sm.p[(int)sm.r_col[e] * 32 + lane];
+                for (; e < e1; e++) {
+                    const uint64_t x0 = sm.r_ent[e];
+                    const double p0 = *reinterpret_cast<const double *>(p_lane + (uint32_t)(x0 >> 32));
+                    if (((uint32_t)x0 >> lane) & 1u) s += p0;
                 }
-                s = warp_sum(s + s1);
+                s = warp_sum((s + s1) + (s2 + s3));
             }
-            if (lane == 0) sm.w[r] = s > 0.0 ? sm.cnt[r] / s : -1.0;  // negative = class skipped (s_k <= 0)
+            if (lane == 0) {
+                sm.w[r] = s > 0.0 ? sm.cnt[r] / s : -1.0;  // negative = class skipped (s_k <= 0)
+                if (!(s > 0.0)) any_skipped = 1;
+            }
         }
-        __syncthreads();
+        const int skipped = __syncthreads_or(any_skipped);
+        const unsigned char *w_base = reinterpret_cast<const unsigned char *>(sm.w);
 #pragma unroll
         for (int i = 0; i < NA; i++) {
             const int c = warp + 32 * i;  // thread (warp, lane), slot i  <->  allele c*32 + lane = tid + i*EM_THREADS
@@ -182,17 +195,39 @@ __device__ __forceinline__ void em_accumulate(const EmArgs &a, const Smem &sm, i
             const int e0 = sm.col_off[c], e1 = sm.col_off[c + 1];
             if (mode == MODE_FIRSTK) {
                 for (int e = e0; e < e1; e++) {
-                    const int r = sm.c_row[e];
+                    const uint64_t x = sm.c_ent[e];
+                    const int r = (int)((uint32_t)(x >> 32) >> 3);
                     if (sm.w[r] < 0.0) continue;
-                    if ((sm.c_word[e] >> lane) & 1u) fk[i] = min(fk[i], (a.class_first ? a.class_first[r] : r) + a.key_offset);
+                    if (((uint32_t)x >> lane) & 1u) fk[i] = min(fk[i], (a.class_first ? a.class_first[r] : r) + a.key_offset);
                 }
+            } else if (!skipped) {
+                double x0 = 0.0, x1 = 0.0;
+                uint32_t seen = 0u;
+                int e = e0;
+                for (; e + 1 < e1; e += 2) {
+                    const uint64_t y0 = sm.c_ent[e], y1 = sm.c_ent[e + 1];
+                    const double w0 = *reinterpret_cast<const double *>(w_base + (uint32_t)(y0 >> 32));
+                    const double w1 = *reinterpret_cast<const double *>(w_base + (uint32_t)(y1 >> 32));
+                    if (((uint32_t)y0 >> lane) & 1u) x0 += w0;
+                    if (((uint32_t)y1 >> lane) & 1u) x1 += w1;
+                    seen |= (uint32_t)y0 | (uint32_t)y1;
+                }
+                if (e < e1) {
+                    const uint64_t y0 = sm.c_ent[e];
+                    const double w0 = *reinterpret_cast<const double *>(w_base + (uint32_t)(y0 >> 32));
+                    if (((uint32_t)y0 >> lane) & 1u) x0 += w0;
+                    seen |= (uint32_t)y0;
+                }
+                acc[i] = x0 + x1;
+                if ((seen >> lane) & 1u) hit |= 1u << i;
             } else {
                 double x = 0.0;
                 bool h = false;
                 for (int e = e0; e < e1; e++) {
-                    const double w = sm.w[(int)sm.c_row[e]];
+                    const uint64_t y = sm.c_ent[e];
+                    const double w = *reinterpret_cast<const double *>(w_base + (uint32_t)(y >> 32));
                     if (w < 0.0) continue;
-                    if ((sm.c_word[e] >> lane) & 1u) {
+                    if (((uint32_t)y >> lane) & 1u) {
                         x += w;
                         h = true;
                     }
@@ -217,6 +252,7 @@ __device__ __forceinline__ void em_accumulate(const EmArgs &a, const Smem &sm, i
             loaded = true;
         }
         // ---- phase 1: warp per row ---------------------------------------------------------------------
+        int any_skipped = 0;
         for (int r = warp; r < nr; r += EM_WARPS) {
             const uint64_t *row = sm.slab + (size_t)r * wp;
             double s = 0.0;
@@ -243,11 +279,15 @@ __device__ __forceinline__ void em_accumulate(const EmArgs &a, const Smem &sm, i
                 const bool ok = s > 0.0;
                 sm.valid[r] = ok ? 1 : 0;
                 const double n = sm.cnt ? sm.cnt[r0 + r] : (a.cnt_u64 ? (double)a.cnt_u64[r0 + r] : a.cnt[r0 + r]);
-                sm.w[r] = ok ? n / s : 0.0;
+                sm.w[r] = ok ? n / s : -1.0;  // negative = class skipped (s_k <= 0)
+                if (!ok) any_skipped = 1;
             }
         }
-        __syncthreads();
+        const int skipped = __syncthreads_or(any_skipped);
         // ---- phase 2: thread per allele column -----------------------------------------------------------
+        // thread (warp, lane), slot i  <->  allele (warp + 32 i) * 32 + lane: all lanes of a warp read the same 32-bit
+        // word of a row (shared-memory broadcast) and test their own bit.  Rows are walked with one running pointer and
+        // the slot offsets are compile-time constants, so a (row, slot) step is LDS + bit test + predicated DADD.
         if (mode == MODE_FIRSTK) {
             for (int r = 0; r < nr; r++) {
                 if (!sm.valid[r]) continue;
@@ -262,22 +302,40 @@ __device__ __forceinline__ void em_accumulate(const EmArgs &a, const Smem &sm, i
                 }
             }
         } else {
-            for (int r = 0; r < nr; r++) {
-                if (!sm.valid[r]) continue;
-                const double w = sm.w[r];
+            const uint32_t *pr = slab32 + warp;
+            const int stride = 2 * wp;
+            uint32_t seen[NA];
 #pragma unroll
-                for (int i = 0; i < NA; i++) {
-                    const int al = tid + i * EM_THREADS;
-                    if (al < Apad) {
-                        const uint32_t w32 = slab32[(size_t)r * wp * 2 + (al >> 5)];  // one word per warp: broadcast
-                        if (w32 == 0u) continue;                                       // warp-uniform skip
-                        if ((w32 >> (al & 31)) & 1u) {
-                            acc[i] += w;
-                            hit |= 1u << i;
+            for (int i = 0; i < NA; i++) seen[i] = 0u;
+            const int nslot = min(NA, (stride - warp + 31) >> 5);  // slots whose word column lies inside the row
+            if (nslot == NA) {
+                for (int r = 0; r < nr; r++, pr += stride) {
+                    const double w = sm.w[r];
+                    if (skipped && w < 0.0) continue;
+#pragma unroll
+                    for (int i = 0; i < NA; i++) {
+                        const uint32_t w32 = pr[32 * i];
+                        if ((w32 >> lane) & 1u) acc[i] += w;
+                        seen[i] |= w32;
+                    }
+                }
+            } else {
+                for (int r = 0; r < nr; r++, pr += stride) {
+                    const double w = sm.w[r];
+                    if (skipped && w < 0.0) continue;
+#pragma unroll
+                    for (int i = 0; i < NA; i++) {
+                        if (i < nslot) {
+                            const uint32_t w32 = pr[32 * i];
+                            if ((w32 >> lane) & 1u) acc[i] += w;
+                            seen[i] |= w32;
                         }
                     }
                 }
             }
+#pragma unroll
+            for (int i = 0; i < NA; i++)
+                if ((seen[i] >> lane) & 1u) hit |= 1u << i;
         }
         __syncthreads();
     }
@@ -749,17 +807,15 @@ __device__ int em_compact_build(const EmArgs &a, Smem &sm, int32_t *lv, int C, i
     }
     __syncthreads();
     const int nnzw = row_off[C];
-    const size_t need = ((fixed + 15) & ~(size_t)15) + (size_t)nnzw * 12 + 16;
+    const size_t need = ((fixed + 15) & ~(size_t)15) + (size_t)nnzw * 16 + 16;
     if (need > R_bytes || C > 65535) {  // too dense for the sparse form: dense slab (overwrites the index)
         __syncthreads();
         for (int i = tid; i < C * wpc; i += EM_THREADS) sm.slab[i] = __ldcg(&dense[i]);
         __syncthreads();
         return An;
     }
-    uint32_t *r_word = reinterpret_cast<uint32_t *>(R + ((fixed + 15) & ~(size_t)15));
-    uint32_t *c_word = r_word + nnzw;
-    uint16_t *r_col = reinterpret_cast<uint16_t *>(c_word + nnzw);
-    uint16_t *c_row = r_col + nnzw;
+    uint64_t *r_ent = reinterpret_cast<uint64_t *>(R + ((fixed + 15) & ~(size_t)15));
+    uint64_t *c_ent = r_ent + nnzw;
     for (int r = warp; r < C; r += EM_WARPS) {
         int pos = row_off[r];
         for (int c0 = 0; c0 < wq; c0 += 32) {
@@ -768,19 +824,17 @@ __device__ int em_compact_build(const EmArgs &a, Smem &sm, int32_t *lv, int C, i
             const unsigned nzm = __ballot_sync(0xffffffffu, word != 0u);
             if (word != 0u) {
                 const int e = pos + __popc(nzm & ((1u << lane) - 1u));
-                r_word[e] = word;
-                r_col[e] = (uint16_t)c;
+                r_ent[e] = (uint64_t)word | ((uint64_t)((uint32_t)c * 256u) << 32);
                 const int ce = col_off[c] + (int)nzpre[(size_t)c * nb + (r >> 5)] +
                                __popc(nzbits[(size_t)c * nb + (r >> 5)] & ((1u << (r & 31)) - 1u));
-                c_word[ce] = word;
-                c_row[ce] = (uint16_t)r;
+                c_ent[ce] = (uint64_t)word | ((uint64_t)((uint32_t)r * 8u) << 32);
             }
             pos += __popc(nzm);
         }
     }
     __syncthreads();
     sm.row_off = row_off; sm.col_off = col_off;
-    sm.r_word = r_word; sm.r_col = r_col; sm.c_word = c_word; sm.c_row = c_row;
+    sm.r_ent = r_ent; sm.c_ent = c_ent;
     return An;
 }
 
@@ -798,8 +852,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
     sm.mbar = reinterpret_cast<uint64_t *>(smem_raw);
     sm.red = reinterpret_cast<double *>(smem_raw + 16);
     sm.lv = nullptr; sm.cnt = nullptr; sm.cm64 = nullptr; sm.c64 = nullptr;
-    sm.row_off = nullptr; sm.col_off = nullptr; sm.r_word = nullptr; sm.c_word = nullptr; sm.r_col = nullptr;
-    sm.c_row = nullptr; sm.dense_g = nullptr;
+    sm.row_off = nullptr; sm.col_off = nullptr; sm.r_ent = nullptr; sm.c_ent = nullptr; sm.dense_g = nullptr;
     bool compacted = false;
     if (!COOP && a.compact) {
         // ---- allele-compacted, fully shared-memory-resident problem ---------------------------------------------
@@ -1078,8 +1131,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_part_kernel(EmArgs a, int mo
     sm.mbar = reinterpret_cast<uint64_t *>(smem_raw);
     sm.red = reinterpret_cast<double *>(smem_raw + 16);
     sm.lv = nullptr; sm.cnt = nullptr; sm.cm64 = nullptr; sm.c64 = nullptr;
-    sm.row_off = nullptr; sm.col_off = nullptr; sm.r_word = nullptr; sm.c_word = nullptr; sm.r_col = nullptr;
-    sm.c_row = nullptr; sm.dense_g = nullptr;
+    sm.row_off = nullptr; sm.col_off = nullptr; sm.r_ent = nullptr; sm.c_ent = nullptr; sm.dense_g = nullptr;
     const int Apad = a.wp * 64;
     sm.p = sm.red + 40;
     sm.w = sm.p + Apad;
@@ -1194,9 +1246,9 @@ int em_plan_batched(const hgt_ctx *ctx, const EmShape &sh, EmArgs *a, int *na, s
     const size_t other = 16 + 40 * 8 + 4096 + Apadc * 12 + Cpad * 25 + 16;
     size_t need = other + dense;
     if (sh.wp <= 256 && need <= budget && dense <= EM_DENSE_SCRATCH && Apadc <= (size_t)16 * EM_THREADS) {
-        // room for the sparse form (12 B per non-zero 32-bit word + index) up to full density, if the SM has it
+        // room for the sparse form (16 B per non-zero 32-bit word + index) up to full density, if the SM has it
         const size_t nb = (Cpad + 31) / 32;
-        size_t want = 3 * dense + (Cpad + 1 + 2 * (size_t)wpc + 1 + 4 * (size_t)wpc * nb) * 4 + 64;
+        size_t want = 4 * dense + (Cpad + 1 + 2 * (size_t)wpc + 1 + 4 * (size_t)wpc * nb) * 4 + 64;
         want = (want + 15) & ~(size_t)15;
         size_t slab = dense;
         if (other + want <= budget) slab = want;

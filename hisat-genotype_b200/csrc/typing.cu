@@ -860,26 +860,50 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 // first[a] = first pair whose class holds a.  grid = (allele tiles, units, class chunks): a CTA folds one chunk of
 // COUNT_CHUNK classes into the totals with integer atomics (order-independent, so still exact).
 constexpr int COUNT_CHUNK = 512;
-__global__ void table_counts_kernel(int A, int wp, int table, ClassPool pool, unsigned long long *__restrict__ a_count,
-                                    int32_t *__restrict__ a_first) {
+constexpr int COUNT_THREADS = 256;  // alleles per CTA = 4 words of every class row
+constexpr int COUNT_TILE = 64;      // class rows staged in shared memory at a time
+__global__ void __launch_bounds__(COUNT_THREADS)
+    table_counts_kernel(int A, int wp, int table, ClassPool pool, unsigned long long *__restrict__ a_count,
+                        int32_t *__restrict__ a_first) {
+    // The 32-byte segment [4 words] of COUNT_TILE rows goes to shared memory with one load per thread (a full sector per
+    // row); every thread then scans the tile for its own allele out of shared memory, so the serial chain per thread is
+    // COUNT_CHUNK / COUNT_TILE global round trips instead of COUNT_CHUNK.
+    __shared__ uint64_t s_bits[COUNT_TILE][COUNT_THREADS / 64];
+    __shared__ unsigned long long s_cnt[COUNT_TILE];
+    __shared__ int32_t s_first[COUNT_TILE];
     const int u = blockIdx.y;
     const int ut = u * 4 + table;
-    const int a = blockIdx.x * blockDim.x + threadIdx.x;
+    const int t = threadIdx.x;
+    const int a = blockIdx.x * COUNT_THREADS + t;
+    const int word0 = blockIdx.x * (COUNT_THREADS / 64);
     const int64_t base = pool.ut_base[ut];
     const int n = min(pool.ut_ncls[ut], (int)(pool.ut_base[ut + 1] - base));
     const int k0 = blockIdx.z * COUNT_CHUNK, k1 = min(n, k0 + COUNT_CHUNK);
-    if (a >= A || k0 >= k1) return;
+    if (k0 >= k1) return;
     unsigned long long c = 0;
     int32_t f = 0x7fffffff;
-#pragma unroll 4
-    for (int k = k0; k < k1; k++) {
-        const uint64_t w = pool.bits[(size_t)(base + k) * wp + (a >> 6)];
-        if ((w >> (a & 63)) & 1ull) {
-            c += pool.count[base + k];
-            f = min(f, pool.first[base + k]);
+    const int lr = t >> 2, lw = t & 3;  // this thread's (row, word) of a tile load
+    const int my_word = t >> 6, my_bit = t & 63;
+    for (int kt = k0; kt < k1; kt += COUNT_TILE) {
+        const int nr = min(COUNT_TILE, k1 - kt);
+        uint64_t v = 0ull;
+        if (lr < nr && word0 + lw < wp) v = pool.bits[(size_t)(base + kt + lr) * wp + word0 + lw];
+        __syncthreads();  // the previous tile has been consumed
+        s_bits[lr][lw] = v;
+        if (t < nr) {
+            s_cnt[t] = pool.count[base + kt + t];
+            s_first[t] = pool.first[base + kt + t];
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int r = 0; r < nr; r++) {
+            if ((s_bits[r][my_word] >> my_bit) & 1ull) {
+                c += s_cnt[r];
+                f = min(f, s_first[r]);
+            }
         }
     }
-    if (c) {
+    if (c && a < A) {
         atomicAdd(&a_count[(size_t)u * A + a], c);
         atomicMin(&a_first[(size_t)u * A + a], f);
     }
@@ -1642,11 +1666,11 @@ static int batch_execute(hgt_batch *b, cudaStream_t st) {
             b->timer.begin(ctx, st, 3);
             int64_t max_pairs = 1;
             for (int u : lb.units) max_pairs = std::max<int64_t>(max_pairs, b->units[u].num_pairs);
-            dim3 grid((loc->A + 127) / 128, (unsigned)n_units,
+            dim3 grid((loc->A + COUNT_THREADS - 1) / COUNT_THREADS, (unsigned)n_units,
                       (unsigned)std::min<int64_t>((max_pairs + COUNT_CHUNK - 1) / COUNT_CHUNK, 65535));
             HGT_CUDA(cudaMemsetAsync(lb.d_acount.p, 0, n_units * (size_t)loc->A * 8, st));
             HGT_CUDA(cudaMemsetAsync(lb.d_afirst.p, 0x7f, n_units * (size_t)loc->A * 4, st));
-            table_counts_kernel<<<grid, 128, 0, st>>>(loc->A, loc->wp, 0, lb.pool(), lb.d_acount.as<unsigned long long>(),
+            table_counts_kernel<<<grid, COUNT_THREADS, 0, st>>>(loc->A, loc->wp, 0, lb.pool(), lb.d_acount.as<unsigned long long>(),
                                                       lb.d_afirst.as<int32_t>());
             ctx->launches++;
             b->timer.end(1);
