@@ -306,6 +306,7 @@ def run_oversized(args):
             ev[k][1].record()
         barrier()
     dev_ms = float(sum(x.elapsed_time(y) for x, y in ev))
+    em_trace_once(L, ctx, lambda: run_gpu(batch))
     launches = L.hgt_launch_count(ctx) - launches0
     stage_ms, stage_n = ctypes_array(8, "d"), ctypes_array(8, "q")
     h2d, d2h = ctypes.c_int64(0), ctypes.c_int64(0)
@@ -468,6 +469,7 @@ def main():
         barrier()
     step_ms = [a.elapsed_time(b) for a, b in ev]
     dev_ms = float(sum(step_ms))
+    em_trace_once(L, ctx, lambda: (batch.execute(stream), batch.finish(stream)))
     launches = L.hgt_launch_count(ctx) - launches0
     stage_ms = (ctypes_array(8, "d"))
     stage_n = (ctypes_array(8, "q"))
@@ -579,6 +581,23 @@ def main():
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def em_trace_once(L, ctx, run):
+    """HGT_EM_TRACE=1: one extra untimed step with the EM kernels' phase tracing on (hgt_em_trace); cycles of CTA 0 of
+    every em_kernel launch go to stderr."""
+    import ctypes
+    if not os.environ.get("HGT_EM_TRACE"):
+        return
+    L.hgt_em_trace.restype = ctypes.c_int
+    L.hgt_em_trace.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]
+    L.hgt_em_trace(ctx, 1, None)
+    run()
+    out = (ctypes.c_uint64 * 16)()
+    L.hgt_em_trace(ctx, 0, out)
+    names = ["stage_p", "phase1_sk", "phase2_acc", "coop_reduce", "normalise", "setup", "squarem_diff_prune", "compact64",
+             "kernel_total", "sweeps", "launches", "all_cta_ns_sum", "all_cta_ns_max", "all_ctas"]
+    sys.stderr.write("em_trace " + json.dumps({n: int(out[i]) for i, n in enumerate(names)}) + "\n")
 
 
 def ctypes_array(n, code):

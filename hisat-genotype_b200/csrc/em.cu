@@ -38,6 +38,44 @@ constexpr int EM_WARPS = EM_THREADS / 32;
 constexpr int MODE_INIT = 0, MODE_NEXT = 1, MODE_FIRSTK = 2;
 constexpr int32_t FK_NONE = 0x7fffffff;
 
+// ---- phase tracing (hgt_em_trace): CTA 0 of every em_kernel launch adds the SM clock cycles its thread 0 spends in
+// each phase; off by default (one uniform branch per phase boundary).
+// slots: 0 stage p, 1 phase 1 (s_k), 2 phase 2 (acc), 3 cross-CTA reduction, 4 normalise, 5 set-up, 6 SQUAREM/diff/prune,
+//        7 <=64-allele loop, 8 kernel total, 9 sweeps, 10 launches; over ALL CTAs: 11 sum of CTA lifetimes (ns), 12 longest
+//        CTA lifetime (ns), 13 CTAs
+__device__ unsigned long long g_em_trace[16];
+__device__ int g_em_trace_on;
+struct Trace {
+    bool on;
+    long long t;
+    unsigned long long ns0;
+    __device__ __forceinline__ void start() {
+        on = g_em_trace_on && blockIdx.x == 0 && threadIdx.x == 0;
+        t = on ? clock64() : 0;
+        ns0 = 0;
+        if (g_em_trace_on && threadIdx.x == 0) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns0));
+    }
+    __device__ __forceinline__ void finish() {  // every CTA
+        if (g_em_trace_on && threadIdx.x == 0) {
+            unsigned long long ns1;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns1));
+            atomicAdd(&g_em_trace[11], ns1 - ns0);
+            atomicMax(&g_em_trace[12], ns1 - ns0);
+            atomicAdd(&g_em_trace[13], 1ull);
+        }
+    }
+    __device__ __forceinline__ void mark(int k) {
+        if (on) {
+            const long long n = clock64();
+            atomicAdd(&g_em_trace[k], (unsigned long long)(n - t));
+            t = n;
+        }
+    }
+    __device__ __forceinline__ void count(int k) {
+        if (on) atomicAdd(&g_em_trace[k], 1ull);
+    }
+};
+
 struct EmArgs {
     const uint64_t *bits;
     const double *cnt;
@@ -83,10 +121,15 @@ struct Smem {
     // ascending order, so all sums keep a fixed association
     const int32_t *row_off;   // [C+1]
     const int32_t *col_off;   // [2*wp+1]
-    const uint64_t *r_ent;    // [nnzw] row-major:    low 32 bits = the word, high 32 bits = byte offset of p[32 * column]
+    const uint64_t *r_ent;    // [nnzw] row-major:    low 32 bits = the word, high 32 bits = byte offset of slot p_slot(32 * column)
     const uint64_t *c_ent;    // [nnzw] column-major: low 32 bits = the word, high 32 bits = byte offset of w[row]
     const uint64_t *dense_g;  // global copy of the compacted dense rows (pitch = wp words), kept for one-off gathers
 };
+
+// The staged probability vector is skewed by one slot per 32 alleles (slot of allele a = a + a/32): lanes that walk the
+// same bit of 32 different words then fall into different banks (stride 33 doubles instead of 32).
+__device__ __forceinline__ int p_slot(int a) { return a + (a >> 5); }
+__host__ __device__ constexpr size_t p_slots(size_t Apad) { return Apad + Apad / 32; }
 
 __device__ __forceinline__ int orig_allele(const Smem &sm, int al) { return sm.lv ? sm.lv[al] : al; }
 
@@ -128,13 +171,14 @@ __device__ __forceinline__ int block_or(int v) { return __syncthreads_or(v); }
 template <int NA>
 __device__ __forceinline__ void em_accumulate(const EmArgs &a, const Smem &sm, int mode, const double *pin,
                                               const uint8_t *livein, int row_lo, int row_hi, bool resident, bool &loaded,
-                                              uint32_t &parity, double (&acc)[NA], int32_t (&fk)[NA], uint32_t &hit) {
+                                              uint32_t &parity, double (&acc)[NA], int32_t (&fk)[NA], uint32_t &hit,
+                                              Trace &tr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int A = a.A, wp = a.wp;
     const int Apad = wp * 64;
     // stage the input vector (0 for alleles that are not keys of the input dict)
     if (mode != MODE_INIT) {
-        for (int i = tid; i < Apad; i += EM_THREADS) sm.p[i] = (i < A && (!livein || livein[i])) ? pin[i] : 0.0;
+        for (int i = tid; i < Apad; i += EM_THREADS) sm.p[p_slot(i)] = (i < A && (!livein || livein[i])) ? pin[i] : 0.0;
     }
     hit = 0;
 #pragma unroll
@@ -143,6 +187,7 @@ __device__ __forceinline__ void em_accumulate(const EmArgs &a, const Smem &sm, i
         fk[i] = FK_NONE;
     }
     __syncthreads();
+    tr.mark(0);
     const uint32_t *slab32 = reinterpret_cast<const uint32_t *>(sm.slab);
     if (sm.row_off) {
         // ---- sparse resident form: cost follows the number of non-zero 32-bit words, not C x A -------------------
@@ -187,6 +232,7 @@ __device__ __forceinline__ void em_accumulate(const EmArgs &a, const Smem &sm, i
             }
         }
         const int skipped = __syncthreads_or(any_skipped);
+        tr.mark(1);
         const unsigned char *w_base = reinterpret_cast<const unsigned char *>(sm.w);
 #pragma unroll
         for (int i = 0; i < NA; i++) {
@@ -237,6 +283,7 @@ __device__ __forceinline__ void em_accumulate(const EmArgs &a, const Smem &sm, i
             }
         }
         __syncthreads();
+        tr.mark(2);
         row_lo = row_hi;  // nothing left for the slab loop
     }
     for (int r0 = row_lo; r0 < row_hi; r0 += a.slab_rows) {
@@ -266,7 +313,7 @@ __device__ __forceinline__ void em_accumulate(const EmArgs &a, const Smem &sm, i
                 const uint32_t *row32 = reinterpret_cast<const uint32_t *>(row);
                 for (int j = lane; j < 2 * wp; j += 32) {
                     uint32_t m = row32[j];
-                    const double *pj = sm.p + j * 32;
+                    const double *pj = sm.p + j * 33;
                     while (m) {
                         const int b = __ffs((int)m) - 1;
                         m &= m - 1;
@@ -284,6 +331,7 @@ __device__ __forceinline__ void em_accumulate(const EmArgs &a, const Smem &sm, i
             }
         }
         const int skipped = __syncthreads_or(any_skipped);
+        tr.mark(1);
         // ---- phase 2: thread per allele column -----------------------------------------------------------
         // thread (warp, lane), slot i  <->  allele (warp + 32 i) * 32 + lane: all lanes of a warp read the same 32-bit
         // word of a row (shared-memory broadcast) and test their own bit.  Rows are walked with one running pointer and
@@ -338,6 +386,7 @@ __device__ __forceinline__ void em_accumulate(const EmArgs &a, const Smem &sm, i
                 if ((seen[i] >> lane) & 1u) hit |= 1u << i;
         }
         __syncthreads();
+        tr.mark(2);
     }
 }
 
@@ -346,45 +395,45 @@ __device__ __forceinline__ void em_accumulate(const EmArgs &a, const Smem &sm, i
 template <int NA, bool COOP>
 __device__ void em_sweep(const EmArgs &a, const Smem &sm, int mode, const double *pin, const uint8_t *livein,
                          double *pout, uint8_t *liveout, int32_t *fkout, int row_lo, int row_hi, bool resident,
-                         bool &loaded, uint32_t &parity, int *status) {
+                         bool &loaded, uint32_t &parity, int *status, Trace &tr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int A = a.A, wp = a.wp;
     const int Apad = wp * 64;
     double acc[NA];
     int32_t fk[NA];
     uint32_t hit = 0;
-    em_accumulate<NA>(a, sm, mode, pin, livein, row_lo, row_hi, resident, loaded, parity, acc, fk, hit);
+    em_accumulate<NA>(a, sm, mode, pin, livein, row_lo, row_hi, resident, loaded, parity, acc, fk, hit, tr);
+    tr.count(9);
     // ---- cross-CTA reduction (cooperative launch only) ------------------------------------------------------
     if (COOP) {
+        // Partials are laid out [allele][CTA] so that the reducing warp reads one contiguous run per allele.  In the
+        // INIT / NEXT modes the "met by a valid class" flag rides in the sign of zero: a CTA that did not meet the allele
+        // contributes -0.0, one that did contributes its sum (>= +0.0), and -0.0 survives an IEEE sum only if every
+        // term is -0.0.  FIRSTK exchanges the int32 keys instead of sums.
         cg::grid_group grid = cg::this_grid();
         const int G = gridDim.x, g = blockIdx.x;
 #pragma unroll
         for (int i = 0; i < NA; i++) {
             const int al = tid + i * EM_THREADS;
             if (al < A) {
-                a.part_acc[(size_t)g * Apad + al] = acc[i];
-                a.part_aux[(size_t)g * Apad + al] = (mode == MODE_FIRSTK) ? fk[i] : (int32_t)((hit >> i) & 1u);
+                if (mode == MODE_FIRSTK) a.part_aux[(size_t)al * G + g] = fk[i];
+                else a.part_acc[(size_t)al * G + g] = ((hit >> i) & 1u) ? acc[i] : -0.0;
             }
         }
         grid.sync();
         const int Ag = (A + G - 1) / G;
         const int a_lo = g * Ag, a_hi = min(A, a_lo + Ag);
         for (int al = a_lo + warp; al < a_hi; al += EM_WARPS) {
-            double s = 0.0;
-            int32_t x = (mode == MODE_FIRSTK) ? FK_NONE : 0;
-            for (int gg = lane; gg < G; gg += 32) {
-                s += a.part_acc[(size_t)gg * Apad + al];
-                const int32_t y = a.part_aux[(size_t)gg * Apad + al];
-                x = (mode == MODE_FIRSTK) ? min(x, y) : (x | y);
-            }
-            s = warp_sum(s);
-            for (int o = 16; o > 0; o >>= 1) {
-                const int32_t y = __shfl_xor_sync(0xffffffffu, x, o);
-                x = (mode == MODE_FIRSTK) ? min(x, y) : (x | y);
-            }
-            if (lane == 0) {
-                a.red_acc[al] = s;
-                a.red_aux[al] = x;
+            if (mode == MODE_FIRSTK) {
+                int32_t x = FK_NONE;
+                for (int gg = lane; gg < G; gg += 32) x = min(x, __ldcg(&a.part_aux[(size_t)al * G + gg]));
+                for (int o = 16; o > 0; o >>= 1) x = min(x, __shfl_xor_sync(0xffffffffu, x, o));
+                if (lane == 0) a.red_aux[al] = x;
+            } else {
+                double s = -0.0;
+                for (int gg = lane; gg < G; gg += 32) s += __ldcg(&a.part_acc[(size_t)al * G + gg]);
+                s = warp_sum(s);
+                if (lane == 0) a.red_acc[al] = s;
             }
         }
         grid.sync();
@@ -393,13 +442,16 @@ __device__ void em_sweep(const EmArgs &a, const Smem &sm, int mode, const double
         for (int i = 0; i < NA; i++) {
             const int al = tid + i * EM_THREADS;
             if (al < A) {
-                acc[i] = a.red_acc[al];
-                const int32_t x = a.red_aux[al];
-                if (mode == MODE_FIRSTK) fk[i] = x;
-                else if (x) hit |= 1u << i;
+                if (mode == MODE_FIRSTK) {
+                    fk[i] = __ldcg(&a.red_aux[al]);
+                } else {
+                    acc[i] = __ldcg(&a.red_acc[al]);
+                    if (!signbit(acc[i])) hit |= 1u << i;
+                }
             }
         }
     }
+    if (COOP) tr.mark(3);
     if (mode == MODE_FIRSTK) {
 #pragma unroll
         for (int i = 0; i < NA; i++) {
@@ -420,7 +472,7 @@ __device__ void em_sweep(const EmArgs &a, const Smem &sm, int mode, const double
         if (al < A) {
             key = ((hit >> i) & 1u) && (mode == MODE_INIT || livein[al]);
             if (key) {
-                q = (mode == MODE_INIT) ? acc[i] : sm.p[al] * acc[i];
+                q = (mode == MODE_INIT) ? acc[i] : sm.p[p_slot(al)] * acc[i];
                 if (a.len) q = q / a.len[orig_allele(sm, al)];
                 part += q;
                 nkeys = 1;
@@ -444,6 +496,7 @@ __device__ void em_sweep(const EmArgs &a, const Smem &sm, int mode, const double
         }
     }
     __syncthreads();
+    tr.mark(4);
 }
 
 // select_alleles (common:1338-1346): keep p >= max/10
@@ -824,7 +877,7 @@ __device__ int em_compact_build(const EmArgs &a, Smem &sm, int32_t *lv, int C, i
             const unsigned nzm = __ballot_sync(0xffffffffu, word != 0u);
             if (word != 0u) {
                 const int e = pos + __popc(nzm & ((1u << lane) - 1u));
-                r_ent[e] = (uint64_t)word | ((uint64_t)((uint32_t)c * 256u) << 32);
+                r_ent[e] = (uint64_t)word | ((uint64_t)((uint32_t)c * 264u) << 32);  // 33 slots per 32 alleles (p_slot)
                 const int ce = col_off[c] + (int)nzpre[(size_t)c * nb + (r >> 5)] +
                                __popc(nzbits[(size_t)c * nb + (r >> 5)] & ((1u << (r & 31)) - 1u));
                 c_ent[ce] = (uint64_t)word | ((uint64_t)((uint32_t)r * 8u) << 32);
@@ -848,6 +901,10 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
     __shared__ int s_status;
     __shared__ int s_int;
     if (tid == 0) s_status = HGT_OK;
+    Trace tr, tr_all;
+    tr.start();
+    tr_all = tr;
+    tr.count(10);
     Smem sm;
     sm.mbar = reinterpret_cast<uint64_t *>(smem_raw);
     sm.red = reinterpret_cast<double *>(smem_raw + 16);
@@ -861,7 +918,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
         unsigned char *q = smem_raw + 16 + 40 * 8;
         sm.c64 = q; q += 4096;
         int32_t *lv = reinterpret_cast<int32_t *>(q); q += Apadc * 4;
-        sm.p = reinterpret_cast<double *>(q); q += Apadc * 8;
+        sm.p = reinterpret_cast<double *>(q); q += p_slots(Apadc) * 8;
         sm.w = reinterpret_cast<double *>(q); q += Cpad * 8;
         sm.cnt = reinterpret_cast<double *>(q); q += Cpad * 8;
         sm.cm64 = reinterpret_cast<uint64_t *>(q); q += Cpad * 8;
@@ -888,7 +945,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
     } else {
         const int Apad0 = a.wp * 64;
         sm.p = sm.red + 40;
-        sm.w = sm.p + Apad0;
+        sm.w = sm.p + p_slots(Apad0);
         sm.slab = reinterpret_cast<uint64_t *>(sm.w + a.slab_rows);  // offset stays a multiple of 16 (slab_rows even)
         sm.valid = reinterpret_cast<uint8_t *>(sm.slab + (size_t)a.slab_rows * a.wp);
     }
@@ -912,8 +969,9 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
     uint8_t *l0 = a.live, *l1 = a.live + Apad, *l2 = a.live + 2 * (size_t)Apad;
     // In cooperative mode every CTA computes the same vectors and writes identical values to the shared
     // workspace; reads of those values are ordered by the sweep's grid syncs / __syncthreads.
+    tr.mark(5);
     em_sweep<NA, COOP>(a, sm, MODE_INIT, nullptr, nullptr, v0, l0, nullptr, row_lo, row_hi, resident, loaded,
-                       parity, &s_status);
+                       parity, &s_status, tr);
     double diff = 1.0;
     int iter = 0, sweeps = 0;
     const double *last_in = v0;
@@ -921,7 +979,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
     bool have_last = false;
     // bytes from sm.p to the end of the slab buffer can be re-used by the compact mode
     // (the allele-compacted layout has dedicated buffers for it instead, so its slab stays intact)
-    const size_t compact_room = (size_t)Apad * 8 + (size_t)a.slab_rows * 8 + (size_t)a.slab_rows * a.wp * 8;
+    const size_t compact_room = p_slots(Apad) * 8 + (size_t)a.slab_rows * 8 + (size_t)a.slab_rows * a.wp * 8;
     const bool compact_ok = !COOP && (compacted || (size_t)a.C * 24 + 64 * 64 <= compact_room);
     while (a.fixed_iters > 0 ? iter < a.fixed_iters : (diff > 0.0001 && iter < 1000)) {
         if (s_status != HGT_OK) break;
@@ -987,7 +1045,9 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
                 __syncthreads();
                 int last = 0;
                 const int iter_before = iter;
+                tr.mark(6);
                 compact_loop(a, c, diff, iter, sweeps, last, have_last, &s_status);
+                tr.mark(7);
                 const bool ran = iter > iter_before;  // otherwise the dense last_in / last_live stay valid
                 // ---- back to the dense representation for the epilogue ----------------------------------------
                 for (int al = tid; al < a.A; al += EM_THREADS) {
@@ -1014,10 +1074,11 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
                 break;
             }
         }
+        tr.mark(6);
         em_sweep<NA, COOP>(a, sm, MODE_NEXT, v0, l0, v1, l1, nullptr, row_lo, row_hi, resident, loaded, parity,
-                           &s_status);
+                           &s_status, tr);
         em_sweep<NA, COOP>(a, sm, MODE_NEXT, v1, l1, v2, l2, nullptr, row_lo, row_hi, resident, loaded, parity,
-                           &s_status);
+                           &s_status, tr);
         sweeps += 2;
         // SQUAREM extrapolation (common:1361-1383)
         double ssr = 0.0, ssv = 0.0;
@@ -1052,8 +1113,9 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
                 v3[al] = x;
             }
             __syncthreads();
+            tr.mark(6);
             em_sweep<NA, COOP>(a, sm, MODE_NEXT, v3, l2, v1, l1, nullptr, row_lo, row_hi, resident, loaded,
-                               parity, &s_status);
+                               parity, &s_status, tr);
             sweeps += 1;
             last_in = v3;
             last_live = l2;
@@ -1107,11 +1169,14 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
         // alleles (common:1324-1331); needed for the stable sort's tie-break (common:1409)
         if (have_last) {
             em_sweep<NA, COOP>(a, sm, MODE_FIRSTK, last_in, last_live, nullptr, nullptr, a.first_class, row_lo,
-                               row_hi, resident, loaded, parity, &s_status);
+                               row_hi, resident, loaded, parity, &s_status, tr);
         } else if (writer) {
             for (int al = tid; al < A_orig; al += EM_THREADS) a.first_class[al] = FK_NONE;
         }
     }
+    tr.mark(6);
+    tr_all.mark(8);
+    tr_all.finish();
     if (tid == 0 && (!COOP || blockIdx.x == 0)) {
         a.iters_status[0] = iter;
         a.iters_status[1] = s_status;
@@ -1134,7 +1199,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_part_kernel(EmArgs a, int mo
     sm.row_off = nullptr; sm.col_off = nullptr; sm.r_ent = nullptr; sm.c_ent = nullptr; sm.dense_g = nullptr;
     const int Apad = a.wp * 64;
     sm.p = sm.red + 40;
-    sm.w = sm.p + Apad;
+    sm.w = sm.p + p_slots(Apad);
     sm.slab = reinterpret_cast<uint64_t *>(sm.w + a.slab_rows);
     sm.valid = reinterpret_cast<uint8_t *>(sm.slab + (size_t)a.slab_rows * a.wp);
     if (tid == 0) {
@@ -1150,7 +1215,9 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_part_kernel(EmArgs a, int mo
     double acc[NA];
     int32_t fk[NA];
     uint32_t hit = 0;
-    em_accumulate<NA>(a, sm, mode, pin, nullptr, row_lo, row_hi, false, loaded, parity, acc, fk, hit);
+    Trace tr;
+    tr.on = false; tr.t = 0; tr.ns0 = 0;
+    em_accumulate<NA>(a, sm, mode, pin, nullptr, row_lo, row_hi, false, loaded, parity, acc, fk, hit, tr);
 #pragma unroll
     for (int i = 0; i < NA; i++) {
         const int al = tid + i * EM_THREADS;
@@ -1191,7 +1258,7 @@ int em_plan(const hgt_ctx *ctx, int rows_per_cta, int A, int wp, EmPlan *plan) {
     }
     int na = 1;
     while (na * EM_THREADS < Apad) na *= 2;
-    const size_t fixed = 16 + 40 * 8 + (size_t)Apad * 8;
+    const size_t fixed = 16 + 40 * 8 + p_slots(Apad) * 8;
     const size_t budget = ctx->smem_optin > 1024 ? ctx->smem_optin - 1024 : 0;
     if (fixed + 2 * ((size_t)wp * 8 + 9) > budget) {
         hgt_set_error("EM kernel: %d alleles do not fit shared memory", A);
@@ -1243,7 +1310,7 @@ int em_plan_batched(const hgt_ctx *ctx, const EmShape &sh, EmArgs *a, int *na, s
     const size_t Apadc = (size_t)wpc * 64;
     const size_t Cpad = sh.C < 2 ? 2 : (size_t)((sh.C + 1) & ~1);
     const size_t dense = Cpad * (size_t)wpc * 8;
-    const size_t other = 16 + 40 * 8 + 4096 + Apadc * 12 + Cpad * 25 + 16;
+    const size_t other = 16 + 40 * 8 + 4096 + Apadc * 4 + p_slots(Apadc) * 8 + Cpad * 25 + 16;
     size_t need = other + dense;
     if (sh.wp <= 256 && need <= budget && dense <= EM_DENSE_SCRATCH && Apadc <= (size_t)16 * EM_THREADS) {
         // room for the sparse form (16 B per non-zero 32-bit word + index) up to full density, if the SM has it
@@ -1609,6 +1676,22 @@ size_t hgt_em_problem_ws_bytes(int wp) {
     const size_t Apad = (size_t)wp * 64;
     return align_up(4 * Apad * 8 + 4 * Apad, 256) + em_compact_scratch_bytes(wp);
 }
+extern "C" int hgt_em_trace(hgt_ctx *ctx, int32_t enable, uint64_t *cycles16) {
+    if (!ctx) return HGT_ERR_ARG;
+    HGT_CUDA(cudaSetDevice(ctx->device));
+    HGT_CUDA(cudaDeviceSynchronize());
+    unsigned long long z[16];
+    if (cycles16) {
+        HGT_CUDA(cudaMemcpyFromSymbol(z, g_em_trace, sizeof(z)));
+        for (int i = 0; i < 16; i++) cycles16[i] = z[i];
+    }
+    memset(z, 0, sizeof(z));
+    HGT_CUDA(cudaMemcpyToSymbol(g_em_trace, z, sizeof(z)));
+    const int on = enable ? 1 : 0;
+    HGT_CUDA(cudaMemcpyToSymbol(g_em_trace_on, &on, sizeof(on)));
+    return HGT_OK;
+}
+
 size_t hgt_em_args_bytes(int n_problems) { return align_up((size_t)n_problems * sizeof(EmArgs), 256); }
 
 bool hgt_em_wants_coop(const hgt_ctx *ctx, int C, int A, int wp, int A_live_max) {

@@ -50,20 +50,23 @@ struct hgt_locus {
     std::vector<double> allele_len;      // [A] Gene_lengths
     hgt_ctx *ctx = nullptr;
     int32_t *d_var_pos = nullptr, *d_delr_right = nullptr, *d_delr_row = nullptr, *d_gn_rank = nullptr;
+    int32_t *d_lb = nullptr;  // [2][L + 2] lower-bound tables by position (variants, deletion right ends)
     uint64_t *d_st = nullptr, *d_mask = nullptr;
     double *d_allele_len = nullptr;
 };
 
 struct LocusDev {
     const int32_t *var_pos, *delr_right, *delr_row;
+    const int32_t *lb_var, *lb_del;  // [L + 2] each: number of variants / of deletion right ends below position x
     const uint64_t *st, *mask;
-    int V, wp, n_delr, levels;
+    int V, wp, n_delr, levels, L;
 };
 
 static LocusDev locus_dev(const hgt_locus *l) {
     LocusDev d;
     d.var_pos = l->d_var_pos; d.delr_right = l->d_delr_right; d.delr_row = l->d_delr_row;
     d.st = l->d_st; d.mask = l->d_mask; d.V = l->V; d.wp = l->wp; d.n_delr = l->n_delr; d.levels = l->levels;
+    d.lb_var = l->d_lb; d.lb_del = l->d_lb + (l->L + 2); d.L = l->L;
     return d;
 }
 
@@ -157,7 +160,7 @@ extern "C" void hgt_locus_free(hgt_locus *l) {
     if (!l) return;
     if (l->ctx) {
         cudaSetDevice(l->ctx->device);
-        cudaFree(l->d_var_pos); cudaFree(l->d_delr_right); cudaFree(l->d_delr_row); cudaFree(l->d_gn_rank);
+        cudaFree(l->d_var_pos); cudaFree(l->d_delr_right); cudaFree(l->d_delr_row); cudaFree(l->d_gn_rank); cudaFree(l->d_lb);
         cudaFree(l->d_st); cudaFree(l->d_mask); cudaFree(l->d_allele_len);
     }
     delete l;
@@ -269,6 +272,22 @@ extern "C" int hgt_locus_create(hgt_ctx *ctx, const hgt_locus_desc *d, hgt_locus
         e = (call);                                                                                \
         if (e != cudaSuccess) hgt_set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e)); \
     }
+    // lower_bound by position as a table: lb[x] = number of entries < x for x in [0, L + 1] (the kernels clamp x)
+    std::vector<int32_t> lb(2 * (size_t)(l->L + 2));
+    {
+        const size_t n = (size_t)l->L + 2;
+        size_t k = 0;
+        for (size_t x = 0; x < n; x++) {
+            while (k < (size_t)V && h.var_pos[k] < (int32_t)x) k++;
+            lb[x] = (int32_t)k;
+        }
+        k = 0;
+        for (size_t x = 0; x < n; x++) {
+            while (k < (size_t)l->n_delr && l->delr_right[k] < (int32_t)x) k++;
+            lb[n + x] = (int32_t)k;
+        }
+    }
+    LTRY(cudaMalloc(&l->d_lb, sizeof(int32_t) * lb.size()));
     LTRY(cudaMalloc(&l->d_var_pos, sizeof(int32_t) * std::max(V, 1)));
     LTRY(cudaMalloc(&l->d_delr_right, sizeof(int32_t) * std::max(l->n_delr, 1)));
     LTRY(cudaMalloc(&l->d_delr_row, sizeof(int32_t) * std::max(l->n_delr, 1)));
@@ -277,6 +296,7 @@ extern "C" int hgt_locus_create(hgt_ctx *ctx, const hgt_locus_desc *d, hgt_locus
     LTRY(cudaMalloc(&l->d_st, sizeof(uint64_t) * lvl_words * levels));
     LTRY(cudaMalloc(&l->d_allele_len, sizeof(double) * l->A));
     cudaStream_t st = ctx->stream;
+    LTRY(cudaMemcpyAsync(l->d_lb, lb.data(), sizeof(int32_t) * lb.size(), cudaMemcpyHostToDevice, st));
     if (V > 0) LTRY(cudaMemcpyAsync(l->d_var_pos, h.var_pos.data(), sizeof(int32_t) * V, cudaMemcpyHostToDevice, st));
     if (l->n_delr > 0) {
         LTRY(cudaMemcpyAsync(l->d_delr_right, l->delr_right.data(), sizeof(int32_t) * l->n_delr, cudaMemcpyHostToDevice, st));
@@ -610,81 +630,71 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
                   const int32_t *__restrict__ hap_right,
                   const int64_t *__restrict__ row_off, const int32_t *__restrict__ rows, int64_t n_haps,
                   uint64_t *__restrict__ out) {
-    extern __shared__ __align__(16) int32_t s_pos[];  // var_pos staged once per CTA (persistent grid)
-    for (int i = threadIdx.x; i < loc.V; i += blockDim.x) s_pos[i] = loc.var_pos[i];
-    __syncthreads();
+    // The two lower_bound searches per haplotype (variants, deletion right ends) are table look-ups by position
+    // (lb_var / lb_del, L + 2 entries each, L1/L2-resident): the kernel's instruction count is then the set algebra itself.
     const int lane = threadIdx.x & 31;
     const int wp = loc.wp;
     const size_t lvl = (size_t)max(loc.V, 1) * wp;
+    const int xmax = loc.L + 1;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t h = warp0; h < n_haps; h += nwarps) {
         const int left = hap_left[h], right = hap_right[h];
-        const int64_t r0 = row_off[h], r1 = row_off[h + 1];
-        const uint64_t *mask = loc.mask + (size_t)hap_table[h] * wp;
+        const int32_t *rw = rows + row_off[h];
+        const int k1 = (int)(row_off[h + 1] - row_off[h]);
+        const int xl = min(max(left, 0), xmax), xr = min(max(right + 1, 0), xmax);
+        const int lo = loc.lb_var[xl], hi = loc.lb_var[xr];
+        const uint64_t *mask = loc.mask + (size_t)hap_table[h] * wp + lane;
         uint64_t acc[WPL], neg[WPL];
 #pragma unroll
         for (int i = 0; i < WPL; i++) {
-            const int j = lane + 32 * i;
-            acc[i] = j < wp ? mask[j] : 0ull;
+            acc[i] = lane + 32 * i < wp ? mask[32 * i] : 0ull;
             neg[i] = 0ull;
         }
-        // positives
-        for (int64_t k = r0; k < r1; k++) {
-            const uint64_t *row = loc.st + (size_t)rows[k] * wp;
-#pragma unroll
-            for (int i = 0; i < WPL; i++) {
-                const int j = lane + 32 * i;
-                if (j < wp) acc[i] &= row[j];
-            }
-        }
-        // negatives with the left end inside [left, right]: rows [lo, hi) minus the haplotype's own rows
-        const int lo = lower_bound_dev(s_pos, loc.V, left), hi = lower_bound_dev(s_pos, loc.V, right + 1);
+        // positives, and the negatives with the left end inside [left, right]: rows [lo, hi) minus the haplotype's own
+        // rows, every gap as the OR of two sparse-table rows
         int prev = lo;
-        for (int64_t k = r0; k <= r1; k++) {
+        for (int k = 0; k <= k1; k++) {
             int endr = hi;
-            if (k < r1) {
-                endr = rows[k];
+            if (k < k1) {
+                endr = rw[k];
+                const uint64_t *row = loc.st + (size_t)endr * wp + lane;
+#pragma unroll
+                for (int i = 0; i < WPL; i++)
+                    if (lane + 32 * i < wp) acc[i] &= row[32 * i];
                 if (endr < lo) continue;
                 if (endr > hi) endr = hi;
             }
-            if (endr > prev) {
+            if (endr > prev && prev < hi) {
                 const int n = endr - prev;
                 const int lv = 31 - __clz(n);
-                const uint64_t *ra = loc.st + lv * lvl + (size_t)prev * wp;
-                const uint64_t *rb = loc.st + lv * lvl + (size_t)(endr - (1 << lv)) * wp;
+                const uint64_t *ra = loc.st + lv * lvl + (size_t)prev * wp + lane;
+                const uint64_t *rb = loc.st + lv * lvl + (size_t)(endr - (1 << lv)) * wp + lane;
 #pragma unroll
-                for (int i = 0; i < WPL; i++) {
-                    const int j = lane + 32 * i;
-                    if (j < wp) neg[i] |= ra[j] | rb[j];
-                }
+                for (int i = 0; i < WPL; i++)
+                    if (lane + 32 * i < wp) neg[i] |= ra[32 * i] | rb[32 * i];
             }
-            prev = endr + 1;
-            if (prev >= hi) break;
+            prev = max(prev, endr + 1);
         }
         // deletions that start left of the haplotype and end inside it
         if (loc.n_delr > 0) {
-            const int dlo = lower_bound_dev(loc.delr_right, loc.n_delr, left);
-            const int dhi = lower_bound_dev(loc.delr_right, loc.n_delr, right + 1);
+            const int dlo = loc.lb_del[xl], dhi = loc.lb_del[xr];
             for (int dd = dlo; dd < dhi; dd++) {
                 const int row = loc.delr_row[dd];
-                if (s_pos[row] >= left) continue;
+                if (loc.var_pos[row] >= left) continue;
                 bool own = false;
-                for (int64_t k = r0; k < r1; k++) own |= rows[k] == row;
+                for (int k = 0; k < k1; k++) own |= rw[k] == row;
                 if (own) continue;
-                const uint64_t *rp = loc.st + (size_t)row * wp;
+                const uint64_t *rp = loc.st + (size_t)row * wp + lane;
 #pragma unroll
-                for (int i = 0; i < WPL; i++) {
-                    const int j = lane + 32 * i;
-                    if (j < wp) neg[i] |= rp[j];
-                }
+                for (int i = 0; i < WPL; i++)
+                    if (lane + 32 * i < wp) neg[i] |= rp[32 * i];
             }
         }
+        uint64_t *o = out + (size_t)h * wp + lane;
 #pragma unroll
-        for (int i = 0; i < WPL; i++) {
-            const int j = lane + 32 * i;
-            if (j < wp) out[(size_t)h * wp + j] = acc[i] & ~neg[i];
-        }
+        for (int i = 0; i < WPL; i++)
+            if (lane + 32 * i < wp) o[32 * i] = acc[i] & ~neg[i];
     }
 }
 
@@ -1575,10 +1585,8 @@ static void launch_stage_a(hgt_batch *b, cudaStream_t st, LocusBatch &lb) {
     const int64_t H = lb.n_haps;
     b->timer.begin(ctx, st, 1);
     if (H > 0) {
-        const size_t smem = (size_t)std::max(ld.V, 1) * 4;
-        cudaFuncSetAttribute(compat_kernel<WPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         const int ctas = (int)std::min<int64_t>((H + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 4);
-        compat_kernel<WPL><<<ctas, WARPS_PER_CTA * 32, smem, st>>>(ld, lb.dj<int32_t>(lb.ja.o_ht), lb.dj<int32_t>(lb.ja.o_hl),
+        compat_kernel<WPL><<<ctas, WARPS_PER_CTA * 32, 0, st>>>(ld, lb.dj<int32_t>(lb.ja.o_ht), lb.dj<int32_t>(lb.ja.o_hl),
                                                                    lb.dj<int32_t>(lb.ja.o_hr), lb.dj<int64_t>(lb.ja.o_row_off),
                                                                    lb.dj<int32_t>(lb.ja.o_rows), H, lb.d_hapbits.as<uint64_t>());
         ctx->launches++;

@@ -64,6 +64,13 @@ void hgt_profile_read(const hgt_ctx *ctx, double *stage_ms, int64_t *stage_launc
  * pileup packing, pileup kernels + wait, walk, job packing, uploads + allocation, finish-side host work, unused */
 void hgt_profile_host(const hgt_ctx *ctx, double *host_ms);
 
+/* Phase tracing of the EM kernels (tooling, not on the typing path): returns in cycles16 the SM clock cycles CTA 0 of
+ * every em_kernel launch since the last call spent in [0] staging p, [1] the s_k pass, [2] the per-allele pass, [3] the
+ * cross-CTA reduction, [4] normalisation, [5] set-up, [6] SQUAREM/diff/prune, [7] the <=64-allele loop, [8] the whole
+ * kernel, then [9] sweeps and [10] launches, and over all CTAs [11] the sum and [12] the maximum of their lifetimes in
+ * ns and [13] their number; clears the counters and switches tracing on/off.  cycles16 may be NULL. */
+int hgt_em_trace(hgt_ctx *ctx, int32_t enable, uint64_t *cycles16);
+
 /* ---- stage (b): EM abundance ----------------------------------------------------------------------------
  * Replaces single_abundance(Gene_cmpt, remove_low_abundance_allele, Gene_length)
  *   reference hisatgenotype_modules/hisatgenotype_typing_common.py:1282-1410 (+ prob_diff :1272-1279).
