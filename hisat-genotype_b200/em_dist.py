@@ -46,9 +46,27 @@ class CudaSweep:
         L.hgt_em_partial_dev.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_int32] * 4 + [ctypes.c_void_p, ctypes.c_int32,
                                                                                       ctypes.c_void_p, ctypes.c_void_p,
                                                                                       ctypes.c_void_p]
+        L.hgt_em_shard_state_bytes.restype = ctypes.c_size_t
+        L.hgt_em_shard_state_bytes.argtypes = [ctypes.c_int32]
+        L.hgt_em_shard_sweep_dev.restype = ctypes.c_int
+        L.hgt_em_shard_sweep_dev.argtypes = [ctypes.c_void_p] * 6 + [ctypes.c_int32] * 6 + [ctypes.c_void_p, ctypes.c_void_p]
+        L.hgt_em_shard_vec_dev.restype = ctypes.c_int
+        L.hgt_em_shard_vec_dev.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p,
+                                           ctypes.c_void_p] + [ctypes.c_int32] * 4
         self.L = L
         self.ws = torch.empty(L.hgt_em_partial_workspace_bytes(self.ctx, self.A), dtype=torch.uint8, device=self.device)
         self._keep = keep  # tensors that own the memory behind the raw pointers
+        # device-resident loop state (csrc/em.cu, "State block"): vec[6][A] | red[2A] | scal[8] | fk[A] | live[5][A]
+        A = self.A
+        self.state = torch.zeros(L.hgt_em_shard_state_bytes(A), dtype=torch.uint8, device=self.device)
+        f64 = self.state[:(8 * A + 8) * 8].view(torch.float64)
+        self.vec = f64[:6 * A].view(6, A)
+        self.red = f64[6 * A:8 * A]
+        self.scal = f64[8 * A:8 * A + 8]
+        o_fk = (8 * A + 8) * 8
+        self.fk = self.state[o_fk:o_fk + 4 * A].view(torch.int32)
+        o_live = o_fk + 4 * ((A + 1) & ~1)
+        self.live = self.state[o_live:o_live + 5 * A].view(5, A)
 
     @classmethod
     def from_arrays(cls, class_bits, class_count, n_alleles, class_key=None, key_offset=0, device=None):
@@ -70,6 +88,70 @@ class CudaSweep:
         return acc, aux
 
 
+    # ---- device-resident loop: sweeps and O(A) vector steps are kernels of libhgt, nothing but the all-reduce is torch
+    def dev_sweep(self, mode, src):
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.L.hgt_em_shard_sweep_dev(self.ctx, stream, self.bits_ptr, self.cnt_f64, self.cnt_u64, self.key_ptr,
+                                                 self.key_offset, self.C, self.A, self.wp, mode, src, self.state.data_ptr(),
+                                                 self.ws.data_ptr()))
+
+    def dev_vec(self, op, len_ptr, src=0, dst=0, iteration=0, remove_low=False):
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.L.hgt_em_shard_vec_dev(self.ctx, stream, op, self.A, self.state.data_ptr(), len_ptr, src, dst,
+                                               iteration, 1 if remove_low else 0))
+
+
+SHARD_FINISH, SHARD_SQUAREM, SHARD_ADVANCE, SHARD_FINAL = 0, 1, 2, 3
+
+
+def _single_abundance_sharded_dev(backend, allele_len, remove_low, group, max_iter):
+    """The loop of single_abundance_sharded with every vector step on the device (hgt_em_shard_vec_dev): per iteration
+    3 x (partial sweep, all-reduce of red[2A], finish) + squarem + advance, and ONE 64-byte host read (diff, key error,
+    division by zero).  The third next_prob always runs; when sum(v^2) == 0 its result is dropped on the device, which is
+    what the reference's `if` does (common:1371-1383)."""
+    import torch.distributed as dist
+    SUM = dist.ReduceOp.SUM if dist.is_available() else None
+    MIN = dist.ReduceOp.MIN if dist.is_available() else None
+    b = backend
+    ln = None if allele_len is None else torch.as_tensor(np.asarray(allele_len, np.float64), device=b.device)
+    ln_ptr = None if ln is None else ln.data_ptr()
+    b.state.zero_()
+
+    def next_prob(src, dst):
+        b.dev_sweep(MODE_NEXT, src)
+        _allreduce(b.red, SUM, group)
+        b.dev_vec(SHARD_FINISH, ln_ptr, src, dst)
+
+    def check(scal):
+        if scal[3] != 0:
+            raise ZeroDivisionError("float division by zero")
+        if scal[2] != 0:
+            raise KeyError("allele vanished from next_prob output during SQUAREM step")
+
+    b.dev_sweep(MODE_INIT, -1)
+    _allreduce(b.red, SUM, group)
+    b.dev_vec(SHARD_FINISH, ln_ptr, -1, 0)
+    diff, it = 1.0, 0
+    while diff > 0.0001 and it < max_iter:
+        next_prob(0, 1)
+        next_prob(1, 2)
+        b.dev_vec(SHARD_SQUAREM, ln_ptr)
+        next_prob(3, 4)
+        b.dev_vec(SHARD_ADVANCE, ln_ptr, iteration=it, remove_low=remove_low)
+        scal = b.scal.cpu()  # the one host synchronisation of the iteration
+        check(scal)
+        diff = float(scal[4])
+        it += 1
+    b.dev_vec(SHARD_FINAL, ln_ptr, remove_low=remove_low)
+    first = torch.full((b.A,), FK_NONE, dtype=torch.int32, device=b.device)
+    if it > 0:
+        b.dev_sweep(MODE_FIRSTK, 5)
+        _allreduce(b.fk, MIN, group)
+        first = torch.where(b.live[4] != 0, b.fk, first)
+    check(b.scal.cpu())
+    return b.vec[1].clone(), b.live[0] != 0, first, it
+
+
 def _allreduce(t, op, group):
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
@@ -83,6 +165,8 @@ def single_abundance_sharded(backend, allele_len=None, remove_low=False, group=N
     Per loop iteration: 3 sweeps + 3 all-reduces of 2*A doubles and two host synchronisations (the SQUAREM branch on
     sum(v^2) > 0 and the convergence test are host decisions, exactly as in the reference's while loop)."""
     import torch.distributed as dist
+    if isinstance(backend, CudaSweep):
+        return _single_abundance_sharded_dev(backend, allele_len, remove_low, group, max_iter)
     SUM = dist.ReduceOp.SUM if dist.is_available() else None
     MIN = dist.ReduceOp.MIN if dist.is_available() else None
     dev = backend.device
