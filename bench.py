@@ -70,40 +70,62 @@ def simulate_units(loci, sims, n_samples, sample0):
 
 
 class ClockSampler:
+    """nvidia-smi clocks / throttle reasons in a side process.  It is started BEFORE the warm-up steps (the first NVML
+    query of a fresh nvidia-smi stalls kernel submission for tens of ms, which must not land in a timed step) and keeps
+    sampling every 100 ms; the `with` block marks the timed region and summary() reports the samples taken inside it
+    (all samples since start-up if the region was shorter than one interval, with "window" saying which)."""
+
     def __init__(self, device):
-        self.rows, self.stop = [], threading.Event()
+        self.rows, self.t0, self.t1 = [], None, None
         self.device = device
         self.proc = None
-
-    def __enter__(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
+            if os.environ.get("HGT_BENCH_NO_SMI"):
+                raise OSError("sampling switched off")
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + q,
-                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, universal_newlines=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except OSError:
             self.proc = None
+
+    def wait_first(self, timeout=5.0):
+        end = time.time() + timeout
+        while self.proc and not self.rows and time.time() < end:
+            time.sleep(0.02)
+
+    def __enter__(self):
+        self.t0 = time.time()
         return self
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def __exit__(self, *a):
+        self.t1 = time.time()
+
+    def close(self):
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=2)
             except Exception:
                 self.proc.kill()
+            self.proc = None
 
     def summary(self):
+        self.close()
+        inside = [r for t, r in self.rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.1]
+        window = "timed region"
+        if not inside:
+            inside, window = [r for _, r in self.rows], "warm-up + timed region (region shorter than the 100 ms interval)"
         sm, mx, reasons = [], 0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in inside:
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
@@ -114,7 +136,7 @@ class ClockSampler:
                     reasons.add(n)
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": window}
 
 
 def measured_peak():
@@ -283,22 +305,34 @@ def run_oversized(args):
     em_state = {"iters": 0, "calls": None}
 
     def run_gpu(bt):
+        t0 = time.perf_counter()
         bt.execute(stream)
+        t1 = time.perf_counter()
         bt.finish(stream)
+        t2 = time.perf_counter()
         if world > 1:
-            em_state["calls"], em_state["iters"] = bt.sharded_abundance(0)
+            em_state["calls"], em_state["iters"] = bt.sharded_abundance(0, max_n=2)
+            em_state["shard_ms"] = dict(bt.shard_ms, execute=(t1 - t0) * 1e3, finish=(t2 - t1) * 1e3,
+                                        call=(time.perf_counter() - t2) * 1e3)
 
     batch = new_batch()
     batch.prepare()
     tot = batch.totals()
     L.hgt_profile_enable(ctx, 1)
+    # the database and the alignment text are millions of long-lived Python objects: park them in the permanent
+    # generation so that a full collection (tens of ms) cannot fire inside a timed step
+    import gc
+    gc.collect()
+    gc.freeze()
+    sampler = ClockSampler(local)
+    sampler.wait_first()
     for _ in range(args.warmup):
         run_gpu(batch)
     L.hgt_profile_reset(ctx)
     launches0 = L.hgt_launch_count(ctx)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
-    with ClockSampler(local) as clocks:
+    with sampler as clocks:
         for k in range(args.steps):
             flush.zero_()
             ev[k][0].record()
@@ -364,6 +398,8 @@ def run_oversized(args):
                        "l2": "per-step inputs (%.1f GB of allele-set rows) exceed L2; a 512 MiB buffer is rewritten between "
                              "timed steps" % (tot["num_pairs"] * table.wp * 8 / 1e9)},
             "reads_per_step": reads_all, "classes_rank0": C, "em_iters_rank0": it,
+            "sharded_em_wall_ms_rank0": em_state.get("shard_ms"),
+            "step_ms_rank0": [round(x.elapsed_time(y), 3) for x, y in ev],
             "stage_ms_per_step_rank0": stage,
             # N = 1: the cooperative EM launch is the dominant kernel; N > 1: the EM runs as partial sweeps + NCCL
             # all-reduce (em_dist.py) outside the stage timers and stage (a) is what the timers see
@@ -463,6 +499,13 @@ def main():
     batch.prepare()
     tot = batch.totals()
     L.hgt_profile_enable(ctx, 1)
+    # the database and the alignment text are millions of long-lived Python objects: park them in the permanent
+    # generation so that a full collection (tens of ms) cannot fire inside a timed step
+    import gc
+    gc.collect()
+    gc.freeze()
+    sampler = ClockSampler(local)
+    sampler.wait_first()
     for _ in range(args.warmup):
         batch.execute(stream)
         batch.finish(stream)
@@ -470,7 +513,7 @@ def main():
     launches0 = L.hgt_launch_count(ctx)
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     barrier()
-    with ClockSampler(local) as clocks:
+    with sampler as clocks:
         for k in range(args.steps):
             flush.zero_()
             ev[k][0].record()
@@ -569,7 +612,7 @@ def main():
             "em_iters_per_sec": iters_all / (ms_per_step / 1000.0) if ms_per_step else None,
             "em_iters_per_step": iters_all,
             "em_iters_per_sec_kernel_time": em_iters / (em_ms / 1000.0) if em_ms > 0 else None,
-            "stage_ms_per_step_rank0": stage,
+            "stage_ms_per_step_rank0": stage, "step_ms_rank0": [round(x, 3) for x in step_ms],
             # dominant kernel by GPU time: the batched EM (two launches per step: first level on the exon tables, second
             # level on the projected tables).  Its problems are shared-memory resident, so DRAM traffic is far below the
             # algorithmic bytes and the HBM fraction is a distance-to-roofline figure, not a saturation claim.

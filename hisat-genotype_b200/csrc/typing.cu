@@ -919,6 +919,56 @@ __global__ void __launch_bounds__(COUNT_THREADS)
     }
 }
 
+// ---- EM result as a key list ------------------------------------------------------------------------------------------
+// After select_alleles a result has a handful of keys out of thousands of alleles, so finish() fetches (allele, first
+// key, probability) triples instead of three dense arrays: one CTA per unit compacts in_result in ascending allele order
+// (ballot + running base, no atomics, so the list order is fixed).  n_out receives the true count; a unit with more than
+// `cap` keys makes the host fall back to the dense copies.
+struct KeyOut {
+    int32_t allele, fk;
+    double prob;
+};
+constexpr int KEY_CAP = 256;
+constexpr int KEY_THREADS = 256;
+__global__ void __launch_bounds__(KEY_THREADS)
+    result_keys_kernel(int A, const double *__restrict__ prob, const uint8_t *__restrict__ inres,
+                       const int32_t *__restrict__ fk, const int32_t *__restrict__ iters_status, int cap,
+                       KeyOut *__restrict__ out, int32_t *__restrict__ n_out) {
+    __shared__ int s_warp[KEY_THREADS / 32];
+    __shared__ int s_base;
+    const int u = blockIdx.x, t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    if (iters_status[(size_t)u * 3 + 1] != HGT_OK) {  // EM failed or did not run: nothing to list
+        if (t == 0) n_out[u] = 0;
+        return;
+    }
+    if (t == 0) s_base = 0;
+    __syncthreads();
+    const size_t o = (size_t)u * A;
+    for (int a0 = 0; a0 < A; a0 += KEY_THREADS) {
+        const int a = a0 + t;
+        const bool k = a < A && inres[o + a];
+        const unsigned m = __ballot_sync(0xffffffffu, k);
+        if (lane == 0) s_warp[warp] = __popc(m);
+        __syncthreads();
+        int before = s_base;
+        for (int w = 0; w < warp; w++) before += s_warp[w];
+        const int pos = before + __popc(m & ((1u << lane) - 1u));
+        if (k && pos < cap) {
+            KeyOut e;
+            e.allele = a; e.fk = fk[o + a]; e.prob = prob[o + a];
+            out[(size_t)u * cap + pos] = e;
+        }
+        __syncthreads();
+        if (t == 0) {
+            int n = 0;
+            for (int w = 0; w < KEY_THREADS / 32; w++) n += s_warp[w];
+            s_base += n;
+        }
+        __syncthreads();
+    }
+    if (t == 0) n_out[u] = s_base;
+}
+
 // pileup-derived per-position flags the host walk needs: nt_set mask and the hla deletion-artefact flag
 // (core:1064-1077: del_count * 6 < nt_count)
 __global__ void pileup_flags_kernel(const uint32_t *__restrict__ counts, int64_t n_pos, uint8_t *__restrict__ mask,
@@ -1088,6 +1138,9 @@ struct LocusBatch {
     DevBuf d_prob, d_inres, d_fk, d_is, d_emws;      // EM over exon (hla) / gene (other) tables
     DevBuf d_prob2, d_inres2, d_fk2, d_is2, d_keep, d_ulist;  // second-level EM (hla)
     DevBuf d_acount, d_afirst;
+    DevBuf d_ck[2], d_cn[2];  // EM results as key lists (result_keys_kernel), first / second level
+    PinBuf h_ck[2], h_cn[2];
+    bool dense[2] = {true, true};  // the dense host arrays prob/inres/fk (prob2/...) hold this level's result
     std::deque<DevBuf> d_coopws;  // whole-GPU EM workspaces of oversized problems (allocated when class counts are known)
     uint32_t cap = 0;
     int n_live[4] = {0, 0, 0, 0};  // alleles that can be members of a class of table t (popcount of its mask)
@@ -1105,11 +1158,12 @@ struct LocusBatch {
         DevBuf *all[] = {&d_jobs, &d_hapbits,
                          &d_keys, &d_slot, &d_bits, &d_count, &d_first, &d_ut_ncls, &d_prob, &d_inres, &d_fk,
                          &d_is, &d_emws, &d_prob2, &d_inres2, &d_fk2, &d_is2, &d_keep, &d_ulist,
-                         &d_acount, &d_afirst};
+                         &d_acount, &d_afirst, &d_ck[0], &d_ck[1], &d_cn[0], &d_cn[1]};
         for (DevBuf *b : all) b->release();
         for (DevBuf &b : d_coopws) b.release();
         d_coopws.clear();
-        PinBuf *pins[] = {&h_jobs, &h_ncls, &h_prob, &h_inres, &h_fk, &h_is, &h_prob2, &h_inres2, &h_fk2, &h_is2, &h_keep, &h_ulist};
+        PinBuf *pins[] = {&h_jobs, &h_ncls, &h_prob, &h_inres, &h_fk, &h_is, &h_prob2, &h_inres2, &h_fk2, &h_is2, &h_keep, &h_ulist,
+                          &h_ck[0], &h_ck[1], &h_cn[0], &h_cn[1]};
         for (PinBuf *b : pins) b->release();
     }
     ClassPool pool() const {
@@ -1539,6 +1593,12 @@ static int batch_prepare(hgt_batch *b) {
             HGT_CHECK(lb.h_inres.alloc(n_units * A));
             HGT_CHECK(lb.h_fk.alloc(n_units * A * 4));
             HGT_CHECK(lb.h_is.alloc(n_units * 12));
+            for (int lv = 0; lv < (loc->is_hla ? 2 : 1); lv++) {
+                HGT_CHECK(lb.d_ck[lv].alloc(n_units * KEY_CAP * sizeof(KeyOut)));
+                HGT_CHECK(lb.d_cn[lv].alloc(n_units * 4));
+                HGT_CHECK(lb.h_ck[lv].alloc(n_units * KEY_CAP * sizeof(KeyOut)));
+                HGT_CHECK(lb.h_cn[lv].alloc(n_units * 4));
+            }
             lb.ut_ncls = lb.h_ncls.as<int32_t>(); lb.prob = lb.h_prob.as<double>(); lb.inres = lb.h_inres.as<uint8_t>();
             lb.fk = lb.h_fk.as<int32_t>(); lb.is = lb.h_is.as<int32_t>();
             memset(lb.ut_ncls, 0, n_units * 16);
@@ -1572,6 +1632,84 @@ static int batch_prepare(hgt_batch *b) {
         HGT_CUDA(cudaStreamSynchronize(st));
     }
     b->prepared = true;
+    return HGT_OK;
+}
+
+// ---- EM results: key lists when select_alleles ran (a handful of keys), dense arrays otherwise ---------------------------
+struct Ent {
+    int32_t a;
+    double p;
+    int32_t fk;
+};
+// keys of one unit's result of `level` (0 first, 1 second) in ascending allele order
+static void unit_keys(const LocusBatch &lb, int level, size_t local, std::vector<Ent> *out) {
+    out->clear();
+    const size_t A = (size_t)lb.loc->A;
+    if (lb.dense[level]) {
+        const double *p = (level ? lb.prob2 : lb.prob) + local * A;
+        const uint8_t *in = (level ? lb.inres2 : lb.inres) + local * A;
+        const int32_t *fk = (level ? lb.fk2 : lb.fk) + local * A;
+        for (int a = 0; a < (int)A; a++)
+            if (in[a]) out->push_back({a, p[a], fk[a]});
+        return;
+    }
+    const KeyOut *k = lb.h_ck[level].as<KeyOut>() + local * KEY_CAP;
+    const int n = lb.h_cn[level].as<int32_t>()[local];
+    for (int i = 0; i < n; i++) out->push_back({k[i].allele, k[i].prob, k[i].fk});
+}
+static void sort_ranked(std::vector<Ent> *v) {  // probability descending; ties in dict order (common:1408-1409)
+    std::sort(v->begin(), v->end(), [](const Ent &x, const Ent &y) {
+        if (x.p != y.p) return x.p > y.p;
+        if (x.fk != y.fk) return x.fk < y.fk;
+        return x.a < y.a;
+    });
+}
+
+// Brings the results of one EM level to the host and synchronises the stream.
+static int fetch_results(hgt_batch *b, cudaStream_t st, int level) {
+    hgt_ctx *ctx = b->ctx;
+    auto dense_copies = [&](LocusBatch &lb) -> int {
+        const size_t n_units = lb.units.size(), A = (size_t)lb.loc->A;
+        HGT_CUDA(d2h(level ? lb.prob2 : lb.prob, (level ? lb.d_prob2 : lb.d_prob).p, n_units * A * 8, st));
+        HGT_CUDA(d2h(level ? lb.inres2 : lb.inres, (level ? lb.d_inres2 : lb.d_inres).p, n_units * A, st));
+        HGT_CUDA(d2h(level ? lb.fk2 : lb.fk, (level ? lb.d_fk2 : lb.d_fk).p, n_units * A * 4, st));
+        lb.dense[level] = true;
+        return HGT_OK;
+    };
+    for (LocusBatch &lb : b->lb) {
+        if (lb.units.empty() || (level == 1 && lb.n_level2 == 0)) continue;
+        const size_t n_units = lb.units.size();
+        // without select_alleles nearly every allele stays a key (first level off the hla path): dense copies
+        const bool lists = level == 1 || (lb.loc->is_hla && b->remove_low);
+        if (lists) {
+            result_keys_kernel<<<(unsigned)n_units, KEY_THREADS, 0, st>>>(
+                lb.loc->A, (level ? lb.d_prob2 : lb.d_prob).as<double>(), (level ? lb.d_inres2 : lb.d_inres).as<uint8_t>(),
+                (level ? lb.d_fk2 : lb.d_fk).as<int32_t>(), (level ? lb.d_is2 : lb.d_is).as<int32_t>(), KEY_CAP,
+                lb.d_ck[level].as<KeyOut>(), lb.d_cn[level].as<int32_t>());
+            HGT_CUDA(cudaGetLastError());
+            ctx->launches++;
+            HGT_CUDA(d2h(lb.h_cn[level].p, lb.d_cn[level].p, n_units * 4, st));
+            HGT_CUDA(d2h(lb.h_ck[level].p, lb.d_ck[level].p, n_units * KEY_CAP * sizeof(KeyOut), st));
+            lb.dense[level] = false;
+        } else {
+            HGT_CHECK(dense_copies(lb));
+        }
+        HGT_CUDA(d2h(level ? lb.is2 : lb.is, (level ? lb.d_is2 : lb.d_is).p, n_units * 12, st));
+        if (level == 1) HGT_CUDA(d2h(lb.ut_ncls, lb.d_ut_ncls.p, n_units * 16, st));
+    }
+    HGT_CUDA(cudaStreamSynchronize(st));
+    bool again = false;
+    for (LocusBatch &lb : b->lb) {
+        if (lb.units.empty() || (level == 1 && lb.n_level2 == 0) || lb.dense[level]) continue;
+        const int32_t *cn = lb.h_cn[level].as<int32_t>();
+        bool over = false;
+        for (size_t i = 0; i < lb.units.size(); i++) over |= cn[i] > KEY_CAP;
+        if (over) {  // a unit kept more keys than a list holds: this locus goes the dense way
+            HGT_CHECK(dense_copies(lb));
+            again = true;
+        }
+    }
+    if (again) HGT_CUDA(cudaStreamSynchronize(st));
     return HGT_OK;
 }
 
@@ -1728,16 +1866,8 @@ static int batch_finish(hgt_batch *b, cudaStream_t st) {
         b->finished = true;
         return HGT_OK;
     }
-    for (LocusBatch &lb : b->lb) {
-        if (lb.units.empty()) continue;
-        const hgt_locus *loc = lb.loc;
-        const size_t n_units = lb.units.size(), A = (size_t)loc->A;
-        HGT_CUDA(d2h(lb.prob, lb.d_prob.p, n_units * A * 8, st));
-        HGT_CUDA(d2h(lb.inres, lb.d_inres.p, n_units * A, st));
-        HGT_CUDA(d2h(lb.fk, lb.d_fk.p, n_units * A * 4, st));
-        HGT_CUDA(d2h(lb.is, lb.d_is.p, n_units * 12, st));
-    }
-    HGT_CUDA(cudaStreamSynchronize(st));
+    for (LocusBatch &lb : b->lb) lb.n_level2 = 0;
+    HGT_CHECK(fetch_results(b, st, 0));
     b->timer.resolve();
     HostTimer ht_finish(ctx, 6);
     std::vector<EmDevProblem> probs;
@@ -1753,30 +1883,22 @@ static int batch_finish(hgt_batch *b, cudaStream_t st) {
         lb.has2.assign(n_units, 0);
         lb.slot2.assign(n_units, -1);
         lb.exon_prob_sum.assign(n_units, 0.0);
-        std::vector<int> order, lu, cmax, alive;
+        std::vector<int> lu, cmax, alive;
+        std::vector<Ent> order;
         for (size_t i = 0; i < n_units; i++) {
             if (lb.is[i * 3 + 1] != HGT_OK) continue;
-            const double *p = &lb.prob[i * A];
-            const uint8_t *in = &lb.inres[i * A];
-            const int32_t *fk = &lb.fk[i * A];
-            order.clear();
-            for (int a = 0; a < (int)A; a++)
-                if (in[a]) order.push_back(a);
-            std::sort(order.begin(), order.end(), [&](int x, int y) {
-                if (p[x] != p[y]) return p[x] > p[y];
-                if (fk[x] != fk[y]) return fk[x] < fk[y];
-                return x < y;
-            });
+            unit_keys(lb, 0, i, &order);
+            sort_ranked(&order);
             uint64_t *m = keep + (size_t)lb.n_level2 * wp;
             memset(m, 0, (size_t)wp * 8);
             bool any = false;
             double psum = 0.0;
             for (size_t r = 0; r < order.size(); r++) {
-                const int a = order[r];
-                if (r >= 10 && p[a] < 0.03) break;
+                const int a = order[r].a;
+                if (r >= 10 && order[r].p < 0.03) break;
                 if (loc->group_off[a + 1] - loc->group_off[a] <= 1) continue;
                 any = true;
-                psum += p[a];
+                psum += order[r].p;
                 for (int64_t g = loc->group_off[a]; g < loc->group_off[a + 1]; g++) {
                     const int mem = loc->group_member[g];
                     m[mem >> 6] |= 1ull << (mem & 63);
@@ -1821,16 +1943,7 @@ static int batch_finish(hgt_batch *b, cudaStream_t st) {
         const int64_t l0 = ctx->launches;
         HGT_CHECK(hgt_em_batch_dev(ctx, st, (int)probs.size(), probs.data(), b->h_em_args[1].p, b->d_em_args[1].p));
         b->timer.end((int)(ctx->launches - l0));
-        for (LocusBatch &lb : b->lb) {
-            if (lb.n_level2 == 0) continue;
-            const size_t n_units = lb.units.size(), A = (size_t)lb.loc->A;
-            HGT_CUDA(d2h(lb.prob2, lb.d_prob2.p, n_units * A * 8, st));
-            HGT_CUDA(d2h(lb.inres2, lb.d_inres2.p, n_units * A, st));
-            HGT_CUDA(d2h(lb.fk2, lb.d_fk2.p, n_units * A * 4, st));
-            HGT_CUDA(d2h(lb.is2, lb.d_is2.p, n_units * 12, st));
-            HGT_CUDA(d2h(lb.ut_ncls, lb.d_ut_ncls.p, n_units * 16, st));
-        }
-        HGT_CUDA(cudaStreamSynchronize(st));
+        HGT_CHECK(fetch_results(b, st, 1));
         b->timer.resolve();
     }
     b->finished = true;
@@ -2080,10 +2193,28 @@ extern "C" int hgt_batch_unit_em(const hgt_batch *b, int64_t unit, int32_t level
     const UnitHost &U = b->units[unit];
     const LocusBatch &lb = b->lb[U.locus];
     const size_t A = (size_t)lb.loc->A, o = (size_t)U.local * A;
+    // dense view of a result that came back as a key list
+    auto scatter = [&](int lv) {
+        if (prob) memset(prob, 0, A * 8);
+        if (in_result) memset(in_result, 0, A);
+        if (first_class)
+            for (size_t a = 0; a < A; a++) first_class[a] = 0x7fffffff;
+        std::vector<Ent> keys;
+        unit_keys(lb, lv, (size_t)U.local, &keys);
+        for (const Ent &e : keys) {
+            if (prob) prob[e.a] = e.p;
+            if (in_result) in_result[e.a] = 1;
+            if (first_class) first_class[e.a] = e.fk;
+        }
+    };
     if (level == 0) {
-        if (prob) memcpy(prob, &lb.prob[o], A * 8);
-        if (in_result) memcpy(in_result, &lb.inres[o], A);
-        if (first_class) memcpy(first_class, &lb.fk[o], A * 4);
+        if (!lb.dense[0] && lb.is[(size_t)U.local * 3 + 1] == HGT_OK) {
+            scatter(0);
+        } else {
+            if (prob) memcpy(prob, &lb.prob[o], A * 8);
+            if (in_result) memcpy(in_result, &lb.inres[o], A);
+            if (first_class) memcpy(first_class, &lb.fk[o], A * 4);
+        }
         if (iters) *iters = lb.is[(size_t)U.local * 3];
         if (status) *status = lb.is[(size_t)U.local * 3 + 1];
         return HGT_OK;
@@ -2093,9 +2224,13 @@ extern "C" int hgt_batch_unit_em(const hgt_batch *b, int64_t unit, int32_t level
         if (iters) *iters = 0;
         return HGT_OK;
     }
-    if (prob) memcpy(prob, &lb.prob2[o], A * 8);
-    if (in_result) memcpy(in_result, &lb.inres2[o], A);
-    if (first_class) memcpy(first_class, &lb.fk2[o], A * 4);
+    if (!lb.dense[1] && lb.is2[(size_t)U.local * 3 + 1] == HGT_OK) {
+        scatter(1);
+    } else {
+        if (prob) memcpy(prob, &lb.prob2[o], A * 8);
+        if (in_result) memcpy(in_result, &lb.inres2[o], A);
+        if (first_class) memcpy(first_class, &lb.fk2[o], A * 4);
+    }
     if (iters) *iters = lb.is2[(size_t)U.local * 3];
     if (status) *status = lb.is2[(size_t)U.local * 3 + 1];
     return HGT_OK;
@@ -2113,26 +2248,19 @@ extern "C" int hgt_batch_unit_abundance(const hgt_batch *b, int64_t unit, int32_
     const size_t A = (size_t)loc->A, o = (size_t)U.local * A;
     const int st1 = lb.is[(size_t)U.local * 3 + 1];
     if (st1 != HGT_OK) return st1;
-    struct Ent { int32_t a; double p; int32_t fk; };
-    auto ranked = [&](const double *p, const uint8_t *in, const int32_t *fk, std::vector<Ent> *out) {
-        out->clear();
-        for (int a = 0; a < (int)A; a++)
-            if (in[a]) out->push_back({a, p[a], fk[a]});
-        std::sort(out->begin(), out->end(), [](const Ent &x, const Ent &y) {
-            if (x.p != y.p) return x.p > y.p;
-            if (x.fk != y.fk) return x.fk < y.fk;
-            return x.a < y.a;
-        });
+    auto ranked = [&](int lv, std::vector<Ent> *out) {
+        unit_keys(lb, lv, (size_t)U.local, out);
+        sort_ranked(out);
     };
     std::vector<Ent> first, second, comb;
-    ranked(lb.prob + o, lb.inres + o, lb.fk + o, &first);
+    ranked(0, &first);
     const bool two = loc->is_hla && !lb.has2.empty() && lb.has2[U.local];
     if (!two) {
         comb.swap(first);
     } else {
         const int st2 = lb.is2[(size_t)U.local * 3 + 1];
         if (st2 != HGT_OK) return st2;
-        ranked(lb.prob2 + o, lb.inres2 + o, lb.fk2 + o, &second);
+        ranked(1, &second);
         const uint64_t *keep = lb.h_keep.as<uint64_t>() + (size_t)lb.slot2[U.local] * loc->wp;
         for (const Ent &e : first)
             if (!((keep[e.a >> 6] >> (e.a & 63)) & 1ull)) comb.push_back(e);

@@ -45,12 +45,15 @@ def em_arrays(class_bits, class_count, n_alleles, allele_len=None, remove_low=Fa
     return prob, inres, fk, iters.value
 
 
-def rank_result(names, prob, in_result, first_class):
+def rank_result(names, prob, in_result, first_class, max_n=None):
     """[[allele, prob], ...] sorted like `sorted(..., key=prob, reverse=True)` on the reference's dict:
     ties keep dict insertion order = (first class that touched the allele, position inside its key)."""
     idx = np.nonzero(in_result)[0]
-    order = sorted(idx.tolist(), key=lambda i: (-prob[i], int(first_class[i]), i))
-    return [[names[i], float(prob[i])] for i in order]
+    prob = np.asarray(prob, np.float64)
+    order = idx[np.lexsort((idx, np.asarray(first_class)[idx].astype(np.int64), -prob[idx]))]  # last key is the primary one
+    if max_n is not None:
+        order = order[:max_n]
+    return [[names[i], float(prob[i])] for i in order.tolist()]
 
 
 def single_abundance(Gene_cmpt, remove_low_abundance_allele=False, Gene_length={}):

@@ -313,12 +313,14 @@ class Batch:
                                                   ctypes.byref(n)))
         return b.value, c.value, f.value, n.value
 
-    def sharded_abundance(self, u, table=TABLE_GENE, lengths=None, remove_low=False, group=None):
+    def sharded_abundance(self, u, table=TABLE_GENE, lengths=None, remove_low=False, group=None, max_n=None):
         """single_abundance over the union of every rank's classes of unit u (the sharded EM of em_dist.py).
-        Returns (ranked [[allele, prob]], iterations); identical on every rank."""
+        Returns (ranked [[allele, prob]] (the first max_n entries when given), iterations); identical on every rank."""
         import torch
         import torch.distributed as dist
         from . import em_dist
+        import time
+        t0 = time.perf_counter()
         t = self.loci[self.unit_locus[u]]
         bits, cnt, first, n = self.unit_table_dev(u, table)
         offset = 0
@@ -329,8 +331,15 @@ class Batch:
             offset = int(sum(int(x) for x in every[:dist.get_rank(group)]))
         sweep = em_dist.CudaSweep(t.A, bits, n, count_u64_ptr=cnt, key_ptr=first, key_offset=offset, device=self.device)
         ln = None if not lengths else np.asarray([lengths[x] for x in t.names], np.float64)
+        t1 = time.perf_counter()
         prob, live, fk, iters = em_dist.single_abundance_sharded(sweep, ln, remove_low, group)
-        return rank_result(t.names, prob.cpu().numpy(), live.cpu().numpy().astype(np.uint8), fk.cpu().numpy()), iters
+        prob, live, fk = prob.cpu().numpy(), live.cpu().numpy().astype(np.uint8), fk.cpu().numpy()
+        t2 = time.perf_counter()
+        ranked = rank_result(t.names, prob, live, fk, max_n)
+        t3 = time.perf_counter()
+        # wall-clock split of the call, read by bench.py: set-up (offsets, workspace), EM loop incl. the final copy, ranking
+        self.shard_ms = {"setup": (t1 - t0) * 1e3, "em_loop": (t2 - t1) * 1e3, "rank": (t3 - t2) * 1e3}
+        return ranked, iters
 
     def unit_calls(self, u, max_n=None):
         """Gene_prob of the unit ranked natively (same result as unit_abundance); max_n limits the list length."""
