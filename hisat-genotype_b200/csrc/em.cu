@@ -208,8 +208,16 @@ __device__ __forceinline__ void em_accumulate(const EmArgs &a, const Smem &sm, i
             } else {
                 double s1 = 0.0, s2 = 0.0, s3 = 0.0;
                 int e = e0;
+                if ((e & 1) && e < e1) {  // entries are fetched in 16-byte pairs from here on (one broadcast wavefront each)
+                    const uint64_t x0 = sm.r_ent[e];
+                    const double p0 = *reinterpret_cast<const double *>(p_lane + (uint32_t)(x0 >> 32));
+                    if (((uint32_t)x0 >> lane) & 1u) s += p0;
+                    e++;
+                }
                 for (; e + 3 < e1; e += 4) {
-                    const uint64_t x0 = sm.r_ent[e], x1 = sm.r_ent[e + 1], x2 = sm.r_ent[e + 2], x3 = sm.r_ent[e + 3];
+                    const ulonglong2 q01 = *reinterpret_cast<const ulonglong2 *>(sm.r_ent + e);
+                    const ulonglong2 q23 = *reinterpret_cast<const ulonglong2 *>(sm.r_ent + e + 2);
+                    const uint64_t x0 = q01.x, x1 = q01.y, x2 = q23.x, x3 = q23.y;
                     const double p0 = *reinterpret_cast<const double *>(p_lane + (uint32_t)(x0 >> 32));
                     const double p1 = *reinterpret_cast<const double *>(p_lane + (uint32_t)(x1 >> 32));
                     const double p2 = *reinterpret_cast<const double *>(p_lane + (uint32_t)(x2 >> 32));
@@ -250,13 +258,33 @@ __device__ __forceinline__ void em_accumulate(const EmArgs &a, const Smem &sm, i
                 double x0 = 0.0, x1 = 0.0;
                 uint32_t seen = 0u;
                 int e = e0;
-                for (; e + 1 < e1; e += 2) {
-                    const uint64_t y0 = sm.c_ent[e], y1 = sm.c_ent[e + 1];
+                if ((e & 1) && e < e1) {
+                    const uint64_t y0 = sm.c_ent[e];
                     const double w0 = *reinterpret_cast<const double *>(w_base + (uint32_t)(y0 >> 32));
-                    const double w1 = *reinterpret_cast<const double *>(w_base + (uint32_t)(y1 >> 32));
-                    if (((uint32_t)y0 >> lane) & 1u) x0 += w0;
-                    if (((uint32_t)y1 >> lane) & 1u) x1 += w1;
-                    seen |= (uint32_t)y0 | (uint32_t)y1;
+                    if (((uint32_t)y0 >> lane) & 1u) x1 += w0;
+                    seen |= (uint32_t)y0;
+                    e++;
+                }
+                for (; e + 3 < e1; e += 4) {
+                    const ulonglong2 q01 = *reinterpret_cast<const ulonglong2 *>(sm.c_ent + e);
+                    const ulonglong2 q23 = *reinterpret_cast<const ulonglong2 *>(sm.c_ent + e + 2);
+                    const double w0 = *reinterpret_cast<const double *>(w_base + (uint32_t)(q01.x >> 32));
+                    const double w1 = *reinterpret_cast<const double *>(w_base + (uint32_t)(q01.y >> 32));
+                    const double w2 = *reinterpret_cast<const double *>(w_base + (uint32_t)(q23.x >> 32));
+                    const double w3 = *reinterpret_cast<const double *>(w_base + (uint32_t)(q23.y >> 32));
+                    if (((uint32_t)q01.x >> lane) & 1u) x0 += w0;
+                    if (((uint32_t)q01.y >> lane) & 1u) x1 += w1;
+                    if (((uint32_t)q23.x >> lane) & 1u) x0 += w2;
+                    if (((uint32_t)q23.y >> lane) & 1u) x1 += w3;
+                    seen |= (uint32_t)q01.x | (uint32_t)q01.y | (uint32_t)q23.x | (uint32_t)q23.y;
+                }
+                for (; e + 1 < e1; e += 2) {
+                    const ulonglong2 q01 = *reinterpret_cast<const ulonglong2 *>(sm.c_ent + e);
+                    const double w0 = *reinterpret_cast<const double *>(w_base + (uint32_t)(q01.x >> 32));
+                    const double w1 = *reinterpret_cast<const double *>(w_base + (uint32_t)(q01.y >> 32));
+                    if (((uint32_t)q01.x >> lane) & 1u) x0 += w0;
+                    if (((uint32_t)q01.y >> lane) & 1u) x1 += w1;
+                    seen |= (uint32_t)q01.x | (uint32_t)q01.y;
                 }
                 if (e < e1) {
                     const uint64_t y0 = sm.c_ent[e];
@@ -875,7 +903,7 @@ __device__ int em_compact_build(const EmArgs &a, Smem &sm, int32_t *lv, int C, i
     }
     __syncthreads();
     const int nnzw = row_off[C];
-    const size_t need = ((fixed + 15) & ~(size_t)15) + (size_t)nnzw * 16 + 16;
+    const size_t need = ((fixed + 15) & ~(size_t)15) + (size_t)nnzw * 16 + 32;
     if (need > R_bytes || C > 65535) {  // too dense for the sparse form: dense slab (overwrites the index)
         __syncthreads();
         for (int i = tid; i < C * wpc; i += EM_THREADS) sm.slab[i] = __ldcg(&dense[i]);
@@ -883,7 +911,7 @@ __device__ int em_compact_build(const EmArgs &a, Smem &sm, int32_t *lv, int C, i
         return An;
     }
     uint64_t *r_ent = reinterpret_cast<uint64_t *>(R + ((fixed + 15) & ~(size_t)15));
-    uint64_t *c_ent = r_ent + nnzw;
+    uint64_t *c_ent = r_ent + ((nnzw + 1) & ~1);  // both lists 16-byte aligned: entries are read in pairs
     for (int r = warp; r < C; r += EM_WARPS) {
         int pos = row_off[r];
         for (int c0 = 0; c0 < wq; c0 += 32) {

@@ -1641,6 +1641,16 @@ struct Ent {
     double p;
     int32_t fk;
 };
+// list capacity per unit: KEY_CAP, or less when HGT_KEY_CAP is set (tests force the dense fall-back with it)
+static int key_cap() {
+    static const int cap = [] {
+        const char *e = getenv("HGT_KEY_CAP");
+        const int v = e ? atoi(e) : KEY_CAP;
+        return v < 1 ? 1 : (v > KEY_CAP ? KEY_CAP : v);
+    }();
+    return cap;
+}
+
 // keys of one unit's result of `level` (0 first, 1 second) in ascending allele order
 static void unit_keys(const LocusBatch &lb, int level, size_t local, std::vector<Ent> *out) {
     out->clear();
@@ -1653,7 +1663,7 @@ static void unit_keys(const LocusBatch &lb, int level, size_t local, std::vector
             if (in[a]) out->push_back({a, p[a], fk[a]});
         return;
     }
-    const KeyOut *k = lb.h_ck[level].as<KeyOut>() + local * KEY_CAP;
+    const KeyOut *k = lb.h_ck[level].as<KeyOut>() + local * key_cap();
     const int n = lb.h_cn[level].as<int32_t>()[local];
     for (int i = 0; i < n; i++) out->push_back({k[i].allele, k[i].prob, k[i].fk});
 }
@@ -1668,6 +1678,7 @@ static void sort_ranked(std::vector<Ent> *v) {  // probability descending; ties 
 // Brings the results of one EM level to the host and synchronises the stream.
 static int fetch_results(hgt_batch *b, cudaStream_t st, int level) {
     hgt_ctx *ctx = b->ctx;
+    const int cap = key_cap();
     auto dense_copies = [&](LocusBatch &lb) -> int {
         const size_t n_units = lb.units.size(), A = (size_t)lb.loc->A;
         HGT_CUDA(d2h(level ? lb.prob2 : lb.prob, (level ? lb.d_prob2 : lb.d_prob).p, n_units * A * 8, st));
@@ -1684,7 +1695,7 @@ static int fetch_results(hgt_batch *b, cudaStream_t st, int level) {
         if (lists) {
             result_keys_kernel<<<(unsigned)n_units, KEY_THREADS, 0, st>>>(
                 lb.loc->A, (level ? lb.d_prob2 : lb.d_prob).as<double>(), (level ? lb.d_inres2 : lb.d_inres).as<uint8_t>(),
-                (level ? lb.d_fk2 : lb.d_fk).as<int32_t>(), (level ? lb.d_is2 : lb.d_is).as<int32_t>(), KEY_CAP,
+                (level ? lb.d_fk2 : lb.d_fk).as<int32_t>(), (level ? lb.d_is2 : lb.d_is).as<int32_t>(), cap,
                 lb.d_ck[level].as<KeyOut>(), lb.d_cn[level].as<int32_t>());
             HGT_CUDA(cudaGetLastError());
             ctx->launches++;
@@ -1703,7 +1714,7 @@ static int fetch_results(hgt_batch *b, cudaStream_t st, int level) {
         if (lb.units.empty() || (level == 1 && lb.n_level2 == 0) || lb.dense[level]) continue;
         const int32_t *cn = lb.h_cn[level].as<int32_t>();
         bool over = false;
-        for (size_t i = 0; i < lb.units.size(); i++) over |= cn[i] > KEY_CAP;
+        for (size_t i = 0; i < lb.units.size(); i++) over |= cn[i] > cap;
         if (over) {  // a unit kept more keys than a list holds: this locus goes the dense way
             HGT_CHECK(dense_copies(lb));
             again = true;

@@ -151,3 +151,18 @@ def test_batch_matches_reference(name, chunk_bytes):
     batch.close()
     for t in loci:
         t.close()
+
+
+def test_key_list_overflow_falls_back_to_dense():
+    """EM results normally come back as key lists (result_keys_kernel, <= 256 keys per unit); HGT_KEY_CAP=1 makes every
+    unit with two keys overflow, so the same batch scenarios must pass through the dense fall-back of fetch_results.
+    The capacity is read once per process, hence the child interpreter."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, HGT_KEY_CAP="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "pytest", os.path.join(root, "tests", "test_gpu_typing.py"), "-x", "-q", "-m", "gpu",
+                        "-k", "test_batch_matches_reference", "-p", "no:cacheprovider"], env=env, cwd=root,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
