@@ -624,77 +624,87 @@ __device__ __forceinline__ int lower_bound_dev(const int32_t *a, int n, int key)
 
 // ---- haplotype -> allele bitset (add_count, core:626-677; set form in SURVEY.md appendix A.5) ----------------
 // warp per haplotype; lane l owns words l, l+32, ... of the row (WPL words per lane).
+// Allele set of one haplotype (left, right, sorted variant rows rw[0..k1)) under table mask `mask` (already offset by the
+// lane): lane l holds words l, l+32, ... in set[].
+template <int WPL>
+__device__ __forceinline__ void hap_allele_set(const LocusDev &loc, int left, int right, const int32_t *__restrict__ rw, int k1,
+                                               const uint64_t *__restrict__ mask, int lane, uint64_t (&set)[WPL]) {
+    // The two lower_bound searches per haplotype (variants, deletion right ends) are table look-ups by position
+    // (lb_var / lb_del, L + 2 entries each, L1/L2-resident): the instruction count is then the set algebra itself.
+    const int wp = loc.wp;
+    const size_t lvl = (size_t)max(loc.V, 1) * wp;
+    const int xmax = loc.L + 1;
+    const int xl = min(max(left, 0), xmax), xr = min(max(right + 1, 0), xmax);
+    const int lo = loc.lb_var[xl], hi = loc.lb_var[xr];
+    uint64_t neg[WPL];
+#pragma unroll
+    for (int i = 0; i < WPL; i++) {
+        set[i] = lane + 32 * i < wp ? mask[32 * i] : 0ull;
+        neg[i] = 0ull;
+    }
+    // positives, and the negatives with the left end inside [left, right]: rows [lo, hi) minus the haplotype's own
+    // rows, every gap as the OR of two sparse-table rows
+    int prev = lo;
+    for (int k = 0; k <= k1; k++) {
+        int endr = hi;
+        if (k < k1) {
+            endr = rw[k];
+            const uint64_t *row = loc.st + (size_t)endr * wp + lane;
+#pragma unroll
+            for (int i = 0; i < WPL; i++)
+                if (lane + 32 * i < wp) set[i] &= row[32 * i];
+            if (endr < lo) continue;
+            if (endr > hi) endr = hi;
+        }
+        if (endr > prev && prev < hi) {
+            const int n = endr - prev;
+            const int lv = 31 - __clz(n);
+            const uint64_t *ra = loc.st + lv * lvl + (size_t)prev * wp + lane;
+            const uint64_t *rb = loc.st + lv * lvl + (size_t)(endr - (1 << lv)) * wp + lane;
+#pragma unroll
+            for (int i = 0; i < WPL; i++)
+                if (lane + 32 * i < wp) neg[i] |= ra[32 * i] | rb[32 * i];
+        }
+        prev = max(prev, endr + 1);
+    }
+    // deletions that start left of the haplotype and end inside it
+    if (loc.n_delr > 0) {
+        const int dlo = loc.lb_del[xl], dhi = loc.lb_del[xr];
+        for (int dd = dlo; dd < dhi; dd++) {
+            const int row = loc.delr_row[dd];
+            if (loc.var_pos[row] >= left) continue;
+            bool own = false;
+            for (int k = 0; k < k1; k++) own |= rw[k] == row;
+            if (own) continue;
+            const uint64_t *rp = loc.st + (size_t)row * wp + lane;
+#pragma unroll
+            for (int i = 0; i < WPL; i++)
+                if (lane + 32 * i < wp) neg[i] |= rp[32 * i];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < WPL; i++) set[i] &= ~neg[i];
+}
+
+// warp per haplotype -> hapbits (two-kernel form of stage (a), the default)
 template <int WPL>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
     compat_kernel(LocusDev loc, const int32_t *__restrict__ hap_table, const int32_t *__restrict__ hap_left,
                   const int32_t *__restrict__ hap_right,
                   const int64_t *__restrict__ row_off, const int32_t *__restrict__ rows, int64_t n_haps,
                   uint64_t *__restrict__ out) {
-    // The two lower_bound searches per haplotype (variants, deletion right ends) are table look-ups by position
-    // (lb_var / lb_del, L + 2 entries each, L1/L2-resident): the kernel's instruction count is then the set algebra itself.
     const int lane = threadIdx.x & 31;
     const int wp = loc.wp;
-    const size_t lvl = (size_t)max(loc.V, 1) * wp;
-    const int xmax = loc.L + 1;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
     for (int64_t h = warp0; h < n_haps; h += nwarps) {
-        const int left = hap_left[h], right = hap_right[h];
-        const int32_t *rw = rows + row_off[h];
-        const int k1 = (int)(row_off[h + 1] - row_off[h]);
-        const int xl = min(max(left, 0), xmax), xr = min(max(right + 1, 0), xmax);
-        const int lo = loc.lb_var[xl], hi = loc.lb_var[xr];
-        const uint64_t *mask = loc.mask + (size_t)hap_table[h] * wp + lane;
-        uint64_t acc[WPL], neg[WPL];
-#pragma unroll
-        for (int i = 0; i < WPL; i++) {
-            acc[i] = lane + 32 * i < wp ? mask[32 * i] : 0ull;
-            neg[i] = 0ull;
-        }
-        // positives, and the negatives with the left end inside [left, right]: rows [lo, hi) minus the haplotype's own
-        // rows, every gap as the OR of two sparse-table rows
-        int prev = lo;
-        for (int k = 0; k <= k1; k++) {
-            int endr = hi;
-            if (k < k1) {
-                endr = rw[k];
-                const uint64_t *row = loc.st + (size_t)endr * wp + lane;
-#pragma unroll
-                for (int i = 0; i < WPL; i++)
-                    if (lane + 32 * i < wp) acc[i] &= row[32 * i];
-                if (endr < lo) continue;
-                if (endr > hi) endr = hi;
-            }
-            if (endr > prev && prev < hi) {
-                const int n = endr - prev;
-                const int lv = 31 - __clz(n);
-                const uint64_t *ra = loc.st + lv * lvl + (size_t)prev * wp + lane;
-                const uint64_t *rb = loc.st + lv * lvl + (size_t)(endr - (1 << lv)) * wp + lane;
-#pragma unroll
-                for (int i = 0; i < WPL; i++)
-                    if (lane + 32 * i < wp) neg[i] |= ra[32 * i] | rb[32 * i];
-            }
-            prev = max(prev, endr + 1);
-        }
-        // deletions that start left of the haplotype and end inside it
-        if (loc.n_delr > 0) {
-            const int dlo = loc.lb_del[xl], dhi = loc.lb_del[xr];
-            for (int dd = dlo; dd < dhi; dd++) {
-                const int row = loc.delr_row[dd];
-                if (loc.var_pos[row] >= left) continue;
-                bool own = false;
-                for (int k = 0; k < k1; k++) own |= rw[k] == row;
-                if (own) continue;
-                const uint64_t *rp = loc.st + (size_t)row * wp + lane;
-#pragma unroll
-                for (int i = 0; i < WPL; i++)
-                    if (lane + 32 * i < wp) neg[i] |= rp[32 * i];
-            }
-        }
+        uint64_t set[WPL];
+        hap_allele_set<WPL>(loc, hap_left[h], hap_right[h], rows + row_off[h], (int)(row_off[h + 1] - row_off[h]),
+                            loc.mask + (size_t)hap_table[h] * wp + lane, lane, set);
         uint64_t *o = out + (size_t)h * wp + lane;
 #pragma unroll
         for (int i = 0; i < WPL; i++)
-            if (lane + 32 * i < wp) o[32 * i] = acc[i] & ~neg[i];
+            if (lane + 32 * i < wp) o[32 * i] = set[i];
     }
 }
 
@@ -824,6 +834,59 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
             const int j = lane + 32 * i;
             best[i] = j < wp ? mask[j] : 0ull;
         }
+#pragma unroll
+        for (int p = P - 1; p >= 0; p--) {
+            uint64_t any = 0;
+#pragma unroll
+            for (int i = 0; i < WPL; i++) any |= best[i] & plane[p][i];
+            if (__any_sync(0xffffffffu, any != 0ull)) {
+#pragma unroll
+                for (int i = 0; i < WPL; i++) best[i] &= plane[p][i];
+            }
+        }
+        pool_insert<WPL>(pool, wp, ut, best, 1ull, job_pair[job], lane);
+    }
+}
+
+// Fused stage (a): warp per job computes the allele set of each of the job's haplotypes in registers (hap_allele_set) and
+// feeds it straight into the bit-plane counter, so the sets never travel through HBM (add_count + add_stat in one pass).
+template <int WPL, int P>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+    pair_class_kernel(LocusDev loc, const int64_t *__restrict__ job_off, const int32_t *__restrict__ job_ut,
+                      const int32_t *__restrict__ job_pair, const int32_t *__restrict__ job_list, int64_t n_jobs,
+                      const int32_t *__restrict__ hap_left, const int32_t *__restrict__ hap_right,
+                      const int64_t *__restrict__ row_off, const int32_t *__restrict__ rows, ClassPool pool) {
+    const int lane = threadIdx.x & 31;
+    const int wp = loc.wp;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t q = warp0; q < n_jobs; q += nwarps) {
+        const int job = job_list[q];
+        const int64_t h0 = job_off[job], h1 = job_off[job + 1];
+        const int ut = job_ut[job];
+        const uint64_t *mask = loc.mask + (size_t)(ut & 3) * wp + lane;
+        uint64_t plane[P][WPL], best[WPL];
+#pragma unroll
+        for (int p = 0; p < P; p++)
+#pragma unroll
+            for (int i = 0; i < WPL; i++) plane[p][i] = 0ull;
+        for (int64_t h = h0; h < h1; h++) {
+            uint64_t set[WPL];
+            hap_allele_set<WPL>(loc, hap_left[h], hap_right[h], rows + row_off[h], (int)(row_off[h + 1] - row_off[h]), mask,
+                                lane, set);
+#pragma unroll
+            for (int i = 0; i < WPL; i++) {
+                uint64_t carry = set[i];
+#pragma unroll
+                for (int p = 0; p < P; p++) {
+                    const uint64_t t = plane[p][i] & carry;
+                    plane[p][i] ^= carry;
+                    carry = t;
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < WPL; i++) best[i] = lane + 32 * i < wp ? mask[32 * i] : 0ull;
 #pragma unroll
         for (int p = P - 1; p >= 0; p--) {
             uint64_t any = 0;
@@ -1242,6 +1305,20 @@ static int batch_threads(const hgt_params &p) {
 // ---- stage 1: intake + pileup (GPU) + walk (host threads) + job upload -----------------------------------------
 static inline size_t a16(size_t x) { return (x + 15) & ~(size_t)15; }
 
+// Stage (a) runs as two kernels (compat_kernel -> hapbits in HBM -> class_kernel).  HGT_STAGE_A=fused selects the
+// one-kernel form (pair_class_kernel, no hapbits buffer) for A/B measurements: on B200 it is SLOWER (5.15 vs 3.03 ms per
+// 128-sample step, 3.39 vs 1.66 ms on the 1 M-read locus) - 116-127 registers per thread halve the resident warps and
+// a warp walks its job's haplotypes one after the other instead of one warp per haplotype; both kernels are issue- and
+// latency-bound, so the 2 x H x wp x 8 bytes of HBM traffic the fusion saves do not pay for that.
+static bool stage_a_split() {
+    static const bool split = [] {
+        const char *e = getenv("HGT_STAGE_A");
+        return !(e && !strcmp(e, "fused"));
+    }();
+    return split;
+}
+
+
 static int batch_prepare(hgt_batch *b) {
     hgt_ctx *ctx = b->ctx;
     cudaStream_t st = ctx->stream;
@@ -1571,7 +1648,7 @@ static int batch_prepare(hgt_batch *b) {
             HGT_CHECK(lb.d_jobs.alloc(lb.ja.bytes));
             ctx->h2d_bytes += (int64_t)lb.ja.bytes;
             HGT_CUDA(cudaMemcpyAsync(lb.d_jobs.p, lb.h_jobs.p, lb.ja.bytes, cudaMemcpyHostToDevice, st));
-            HGT_CHECK(lb.d_hapbits.alloc((size_t)std::max<int64_t>(lb.n_haps, 1) * wp * 8));
+            if (stage_a_split()) HGT_CHECK(lb.d_hapbits.alloc((size_t)std::max<int64_t>(lb.n_haps, 1) * wp * 8));
             HGT_CHECK(lb.d_keys.alloc((size_t)lb.cap * 8));
             HGT_CHECK(lb.d_slot.alloc((size_t)lb.cap * 4));
             const size_t pr = (size_t)std::max<int64_t>(lb.n_rows_pool, 1);
@@ -1732,6 +1809,29 @@ static void launch_stage_a(hgt_batch *b, cudaStream_t st, LocusBatch &lb) {
     const LocusDev ld = locus_dev(loc);
     const int wp = loc->wp;
     const int64_t H = lb.n_haps;
+    if (!stage_a_split()) {
+        const ClassPool pool = lb.pool();
+        const int64_t ns = lb.n_small, nb = lb.n_big;
+        b->timer.begin(ctx, st, 2);
+        if (ns > 0) {
+            const int ctas = (int)std::min<int64_t>((ns + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 8);
+            pair_class_kernel<WPL, 3><<<ctas, WARPS_PER_CTA * 32, 0, st>>>(
+                ld, lb.dj<int64_t>(lb.ja.o_job_off), lb.dj<int32_t>(lb.ja.o_job_ut), lb.dj<int32_t>(lb.ja.o_job_pair),
+                lb.dj<int32_t>(lb.ja.o_job_list), ns, lb.dj<int32_t>(lb.ja.o_hl), lb.dj<int32_t>(lb.ja.o_hr),
+                lb.dj<int64_t>(lb.ja.o_row_off), lb.dj<int32_t>(lb.ja.o_rows), pool);
+            ctx->launches++;
+        }
+        if (nb > 0) {
+            const int ctas = (int)std::min<int64_t>((nb + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 8);
+            pair_class_kernel<WPL, 8><<<ctas, WARPS_PER_CTA * 32, 0, st>>>(
+                ld, lb.dj<int64_t>(lb.ja.o_job_off), lb.dj<int32_t>(lb.ja.o_job_ut), lb.dj<int32_t>(lb.ja.o_job_pair),
+                lb.dj<int32_t>(lb.ja.o_job_list) + ns, nb, lb.dj<int32_t>(lb.ja.o_hl), lb.dj<int32_t>(lb.ja.o_hr),
+                lb.dj<int64_t>(lb.ja.o_row_off), lb.dj<int32_t>(lb.ja.o_rows), pool);
+            ctx->launches++;
+        }
+        b->timer.end((ns > 0) + (nb > 0));
+        return;
+    }
     b->timer.begin(ctx, st, 1);
     if (H > 0) {
         const int ctas = (int)std::min<int64_t>((H + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 4);
