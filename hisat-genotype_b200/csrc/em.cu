@@ -87,6 +87,8 @@ struct EmArgs {
     unsigned slab_bytes;  // compact layout: bytes of the slab region (>= slab_rows x pitch x 8; the sparse form may use more)
     uint64_t *dense_ws;  // compact layout: global scratch for the gathered dense rows, slab_rows x pitch(A_live_max) words
     uint64_t *mv_ws;     // compact layout: global scratch, 6 x wp words (bit-compress masks of every source word)
+    int32_t *rep_ws;     // compact layout: global scratch [64 wp]: representative allele of every member allele, -1 = none
+    double *mult_ws;     // compact layout: global scratch [64 wp]: alleles represented by compact column j
     const unsigned long long *cnt_u64;  // class counts as integers (device-resident tables); overrides cnt
     const int32_t *C_ptr;               // number of classes read on the device at launch; overrides C
     const int32_t *class_first;         // tie-break key of each class (first pair index); default = class index
@@ -123,6 +125,7 @@ struct Smem {
     const int32_t *col_off;   // [2*wp+1]
     const uint64_t *r_ent;    // [nnzw] row-major:    low 32 bits = the word, high 32 bits = byte offset of slot p_slot(32 * column)
     const uint64_t *c_ent;    // [nnzw] column-major: low 32 bits = the word, high 32 bits = byte offset of w[row]
+    const double *mult;       // [A'] alleles merged into compact column j (identical membership columns); null = all 1
     const uint64_t *dense_g;  // global copy of the compacted dense rows (pitch = wp words), kept for one-off gathers
 };
 
@@ -177,8 +180,13 @@ __device__ __forceinline__ void em_accumulate(const EmArgs &a, const Smem &sm, i
     const int A = a.A, wp = a.wp;
     const int Apad = wp * 64;
     // stage the input vector (0 for alleles that are not keys of the input dict)
+    // (merged columns: the vectors hold the MASS of a column's alleles; the initial mass needs |class| = sum of the
+    // multiplicities, so INIT stages them and takes the weighted-sum path)
+    const bool weighted_init = mode == MODE_INIT && sm.mult != nullptr;
     if (mode != MODE_INIT) {
         for (int i = tid; i < Apad; i += EM_THREADS) sm.p[p_slot(i)] = (i < A && (!livein || livein[i])) ? pin[i] : 0.0;
+    } else if (weighted_init) {
+        for (int i = tid; i < Apad; i += EM_THREADS) sm.p[p_slot(i)] = i < A ? sm.mult[i] : 0.0;
     }
     hit = 0;
 #pragma unroll
@@ -193,14 +201,15 @@ __device__ __forceinline__ void em_accumulate(const EmArgs &a, const Smem &sm, i
         // ---- sparse resident form: cost follows the number of non-zero 32-bit words, not C x A -------------------
         // One packed 64-bit entry per non-zero word; a whole warp takes an entry (word broadcast, lane = bit), so an
         // entry costs LDS.64 + address add + LDS.64 + bit test + predicated DADD.  Four independent partial sums per
-        // row / two per column hide the DADD latency; the association is fixed, so results are reproducible.
+        // row hide the DADD latency there; a column keeps ONE running sum (see below); the association is fixed, so
+        // results are reproducible.
         const int C = row_hi;
         const unsigned char *p_lane = reinterpret_cast<const unsigned char *>(sm.p + lane);
         int any_skipped = 0;
         for (int r = warp; r < C; r += EM_WARPS) {
             const int e0 = sm.row_off[r], e1 = sm.row_off[r + 1];
             double s = 0.0;
-            if (mode == MODE_INIT) {
+            if (mode == MODE_INIT && !weighted_init) {
                 int pc = 0;
                 for (int e = e0 + lane; e < e1; e += 32) pc += __popc((uint32_t)sm.r_ent[e]);
                 for (int o = 16; o > 0; o >>= 1) pc += __shfl_xor_sync(0xffffffffu, pc, o);
@@ -255,13 +264,17 @@ __device__ __forceinline__ void em_accumulate(const EmArgs &a, const Smem &sm, i
                     if (((uint32_t)x >> lane) & 1u) fk[i] = min(fk[i], (a.class_first ? a.class_first[r] : r) + a.key_offset);
                 }
             } else if (!skipped) {
-                double x0 = 0.0, x1 = 0.0;
+                // ONE running sum per allele, rows in ascending order: alleles with identical membership columns must end
+                // with bit-identical sums (the reference's ties are exact and decide the ranking), and with partial sums
+                // chosen by entry parity the association would depend on the OTHER alleles of the 32-allele word.  The
+                // loads of four entries are issued together; only the predicated adds form the chain.
+                double x0 = 0.0;
                 uint32_t seen = 0u;
                 int e = e0;
                 if ((e & 1) && e < e1) {
                     const uint64_t y0 = sm.c_ent[e];
                     const double w0 = *reinterpret_cast<const double *>(w_base + (uint32_t)(y0 >> 32));
-                    if (((uint32_t)y0 >> lane) & 1u) x1 += w0;
+                    if (((uint32_t)y0 >> lane) & 1u) x0 += w0;
                     seen |= (uint32_t)y0;
                     e++;
                 }
@@ -273,26 +286,18 @@ __device__ __forceinline__ void em_accumulate(const EmArgs &a, const Smem &sm, i
                     const double w2 = *reinterpret_cast<const double *>(w_base + (uint32_t)(q23.x >> 32));
                     const double w3 = *reinterpret_cast<const double *>(w_base + (uint32_t)(q23.y >> 32));
                     if (((uint32_t)q01.x >> lane) & 1u) x0 += w0;
-                    if (((uint32_t)q01.y >> lane) & 1u) x1 += w1;
+                    if (((uint32_t)q01.y >> lane) & 1u) x0 += w1;
                     if (((uint32_t)q23.x >> lane) & 1u) x0 += w2;
-                    if (((uint32_t)q23.y >> lane) & 1u) x1 += w3;
+                    if (((uint32_t)q23.y >> lane) & 1u) x0 += w3;
                     seen |= (uint32_t)q01.x | (uint32_t)q01.y | (uint32_t)q23.x | (uint32_t)q23.y;
                 }
-                for (; e + 1 < e1; e += 2) {
-                    const ulonglong2 q01 = *reinterpret_cast<const ulonglong2 *>(sm.c_ent + e);
-                    const double w0 = *reinterpret_cast<const double *>(w_base + (uint32_t)(q01.x >> 32));
-                    const double w1 = *reinterpret_cast<const double *>(w_base + (uint32_t)(q01.y >> 32));
-                    if (((uint32_t)q01.x >> lane) & 1u) x0 += w0;
-                    if (((uint32_t)q01.y >> lane) & 1u) x1 += w1;
-                    seen |= (uint32_t)q01.x | (uint32_t)q01.y;
-                }
-                if (e < e1) {
+                for (; e < e1; e++) {
                     const uint64_t y0 = sm.c_ent[e];
                     const double w0 = *reinterpret_cast<const double *>(w_base + (uint32_t)(y0 >> 32));
                     if (((uint32_t)y0 >> lane) & 1u) x0 += w0;
                     seen |= (uint32_t)y0;
                 }
-                acc[i] = x0 + x1;
+                acc[i] = x0;
                 if ((seen >> lane) & 1u) hit |= 1u << i;
             } else {
                 double x = 0.0;
@@ -331,7 +336,7 @@ __device__ __forceinline__ void em_accumulate(const EmArgs &a, const Smem &sm, i
         for (int r = warp; r < nr; r += EM_WARPS) {
             const uint64_t *row = sm.slab + (size_t)r * wp;
             double s = 0.0;
-            if (mode == MODE_INIT) {
+            if (mode == MODE_INIT && !weighted_init) {
                 int pc = 0;
                 for (int j = lane; j < wp; j += 32) pc += __popcll(row[j]);
                 for (int o = 16; o > 0; o >>= 1) pc += __shfl_xor_sync(0xffffffffu, pc, o);
@@ -515,7 +520,7 @@ __device__ void em_sweep(const EmArgs &a, const Smem &sm, int mode, const double
         if (al < A) {
             key = ((hit >> i) & 1u) && (mode == MODE_INIT || livein[al]);
             if (key) {
-                q = (mode == MODE_INIT) ? acc[i] : sm.p[p_slot(al)] * acc[i];
+                q = (mode == MODE_INIT && !sm.mult) ? acc[i] : sm.p[p_slot(al)] * acc[i];  // INIT on merged columns: x multiplicity
                 if (a.len) q = q / a.len[orig_allele(sm, al)];
                 part += q;
                 nkeys = 1;
@@ -544,14 +549,15 @@ __device__ void em_sweep(const EmArgs &a, const Smem &sm, int mode, const double
 
 // select_alleles (common:1338-1346): keep p >= max/10
 __device__ void em_prune(const EmArgs &a, const Smem &sm, double *p, uint8_t *live) {
+    // merged columns: p holds the mass of sm.mult[al] equal alleles, the rule is per allele
     double mx = -1.0;
     for (int al = threadIdx.x; al < a.A; al += EM_THREADS)
-        if (live[al]) mx = fmax(mx, p[al]);
+        if (live[al]) mx = fmax(mx, sm.mult ? p[al] / sm.mult[al] : p[al]);
     mx = block_max(mx, sm.red);
     if (mx < 0.0) return;
     const double thr = mx / 10.0;
     for (int al = threadIdx.x; al < a.A; al += EM_THREADS) {
-        if (live[al] && !(p[al] >= thr)) {
+        if (live[al] && !((sm.mult ? p[al] / sm.mult[al] : p[al]) >= thr)) {
             live[al] = 0;
             p[al] = 0.0;
         }
@@ -731,10 +737,18 @@ __device__ void compact_loop(const EmArgs &a, Compact &c, double &diff, int &ite
     }
 }
 
+constexpr int DEDUP_CAP = 8192;         // hash slots; at most 6144 live alleles (load factor 0.75)
+constexpr int DEDUP_MAX_LIVE = 6144;
+constexpr int DEDUP_COLS = 4;           // 64-allele word columns per warp: wp <= 128
+__device__ __forceinline__ unsigned long long dedup_mix(unsigned long long x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
+    return x;
+}
+
 // Builds the allele-compacted problem in shared memory: the alleles that are members of at least one class
 // (every other allele keeps probability 0 for the whole run, common:1299-1309) are renumbered 0..A'-1 in
 // ascending order and every class row is gathered into A' bits.  Returns A'.
-__device__ int em_compact_build(const EmArgs &a, Smem &sm, int32_t *lv, int C, int *s_int) {
+__device__ int em_compact_build(const EmArgs &a, Smem &sm, int32_t *lv, int C, int *s_int, bool dedup, Trace &tr) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wp = a.wp;  // <= 256
     uint64_t *lw = reinterpret_cast<uint64_t *>(sm.c64);           // [256] OR of all rows
@@ -758,6 +772,125 @@ __device__ int em_compact_build(const EmArgs &a, Smem &sm, int32_t *lv, int C, i
             if (acc[i]) atomicOr(reinterpret_cast<unsigned long long *>(&lw[lane + 32 * i]), (unsigned long long)acc[i]);
     }
     __syncthreads();
+    tr.mark(5);
+    if (dedup) {
+        // ---- merge alleles with identical membership columns --------------------------------------------------------------
+        // Such alleles start with the same mass and receive the same factor in every next_prob(), so they stay equal for
+        // the whole run: only the smallest one of each set (the representative) stays in the live mask and carries the
+        // set's total mass (em_kernel keeps track of the multiplicities where a per-allele quantity is needed).
+        // Columns are compared through a 96-bit GF(2)-linear signature: bit t of allele a = parity of the rows that hold a
+        // and whose random word has bit t set (two distinct columns collide with probability 2^-96).  It is computed 64
+        // alleles at a time: a warp owns a 64-allele word column, lane t keeps the three 64-bit planes t, t+32 and t+64
+        // (plane ^= row word where the row's random word has that bit), the class rows come through shared memory in
+        // tiles, and a ballot transpose turns the planes into per-allele signatures.
+        int32_t *cnt32 = reinterpret_cast<int32_t *>(a.dense_ws);  // [64 wp] members merged into allele a (dense scratch)
+        const int Atot = wp * 64;
+        for (int al = tid; al < Atot; al += EM_THREADS) { cnt32[al] = 0; a.rep_ws[al] = -1; }
+        unsigned long long *xs = reinterpret_cast<unsigned long long *>(sm.w);  // per-row random words (free until the sweeps)
+        uint32_t *ys = reinterpret_cast<uint32_t *>(sm.cnt);
+        for (int r = tid; r < C; r += EM_THREADS) {
+            const unsigned long long x = dedup_mix((unsigned long long)r + 1ull);
+            xs[r] = x;
+            ys[r] = (uint32_t)dedup_mix(x ^ 0x9e3779b97f4a7c15ull);
+        }
+        uint64_t *tile = sm.slab;
+        const int T = min(C, (int)(a.slab_bytes / ((size_t)wp * 8)));
+        uint64_t pa[DEDUP_COLS], pb[DEDUP_COLS], pc[DEDUP_COLS];
+#pragma unroll
+        for (int c = 0; c < DEDUP_COLS; c++) pa[c] = pb[c] = pc[c] = 0ull;
+        for (int t0 = 0; t0 < C; t0 += T) {
+            const int nr = min(T, C - t0);
+            __syncthreads();
+            {  // wp is even and the rows are 16-byte aligned: 16-byte copies, four in flight per thread
+                const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(a.bits + (size_t)t0 * wp);
+                ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(tile);
+                const int n2 = nr * wp / 2;
+#pragma unroll 4
+                for (int i = tid; i < n2; i += EM_THREADS) dst[i] = __ldg(&src[i]);
+            }
+            __syncthreads();
+            // a warp owns the 4 adjacent word columns 4 warp .. 4 warp + 3: two 16-byte loads fetch them, and a row that is
+            // zero in all four (most rows of most column groups) costs nothing else
+            const int j0 = warp * DEDUP_COLS;
+            if (j0 < wp) {
+                const bool v1 = j0 + 1 < wp, v2 = j0 + 2 < wp, v3 = j0 + 3 < wp;
+                for (int r = 0; r < nr; r++) {
+                    const ulonglong2 *trow = reinterpret_cast<const ulonglong2 *>(tile + (size_t)r * wp + j0);
+                    const ulonglong2 q01 = trow[0], q23 = trow[1];
+                    const uint64_t w0 = q01.x, w1 = v1 ? q01.y : 0ull, w2 = v2 ? q23.x : 0ull, w3 = v3 ? q23.y : 0ull;
+                    if ((w0 | w1 | w2 | w3) == 0ull) continue;
+                    const unsigned long long x = xs[t0 + r];
+                    const uint32_t y = ys[t0 + r];
+                    const uint64_t m0 = ((x >> lane) & 1ull) ? ~0ull : 0ull, m1 = ((x >> (lane + 32)) & 1ull) ? ~0ull : 0ull,
+                                   m2 = ((y >> lane) & 1u) ? ~0ull : 0ull;
+                    pa[0] ^= w0 & m0; pb[0] ^= w0 & m1; pc[0] ^= w0 & m2;
+                    pa[1] ^= w1 & m0; pb[1] ^= w1 & m1; pc[1] ^= w1 & m2;
+                    pa[2] ^= w2 & m0; pb[2] ^= w2 & m1; pc[2] ^= w2 & m2;
+                    pa[3] ^= w3 & m0; pb[3] ^= w3 & m1; pc[3] ^= w3 & m2;
+                }
+            }
+        }
+        __syncthreads();
+        tr.mark(14);
+        unsigned long long *sig1 = reinterpret_cast<unsigned long long *>(sm.slab);  // [64 wp], the tile is done with
+        uint32_t *sig2 = reinterpret_cast<uint32_t *>(sig1 + Atot);
+#pragma unroll
+        for (int c = 0; c < DEDUP_COLS; c++) {
+            const int j = warp * DEDUP_COLS + c;
+            if (j >= wp) continue;
+            const uint64_t live = lw[j];
+            for (int b = 0; b < 64; b++) {
+                if (!((live >> b) & 1ull)) continue;  // warp-uniform
+                const unsigned m0 = __ballot_sync(0xffffffffu, (pa[c] >> b) & 1ull);
+                const unsigned m1 = __ballot_sync(0xffffffffu, (pb[c] >> b) & 1ull);
+                const unsigned m2 = __ballot_sync(0xffffffffu, (pc[c] >> b) & 1ull);
+                if (lane == 0) {
+                    sig1[j * 64 + b] = (unsigned long long)m0 | ((unsigned long long)m1 << 32);
+                    sig2[j * 64 + b] = m2;
+                }
+            }
+        }
+        __syncthreads();
+        // hash table in shared memory next to the signatures, one 32-bit word per slot: high half = the allele that
+        // claimed the slot (its signature is the slot's key), low half = the smallest allele met with that signature
+        // (atomicMin on the whole word: the high half is fixed once claimed)
+        uint32_t *occ = sig2 + Atot;
+        for (int i = tid; i < DEDUP_CAP; i += EM_THREADS) occ[i] = 0xffffffffu;
+        __syncthreads();
+        for (int al = tid; al < Atot; al += EM_THREADS) {
+            if (!((lw[al >> 6] >> (al & 63)) & 1ull)) continue;
+            const unsigned long long h1 = sig1[al];
+            const uint32_t h2 = sig2[al];
+            unsigned slot = (unsigned)dedup_mix(h1 + h2) & (DEDUP_CAP - 1);
+            while (true) {
+                const uint32_t prev = atomicCAS(&occ[slot], 0xffffffffu, ((uint32_t)al << 16) | (uint32_t)al);
+                if (prev == 0xffffffffu) break;
+                const int owner = (int)(prev >> 16);
+                if (sig1[owner] == h1 && sig2[owner] == h2) {
+                    atomicMin(&occ[slot], ((uint32_t)owner << 16) | (uint32_t)al);
+                    break;
+                }
+                slot = (slot + 1) & (DEDUP_CAP - 1);
+            }
+            a.rep_ws[al] = (int)slot;  // resolved to the representative allele below
+        }
+        __syncthreads();
+        for (int al = tid; al < Atot; al += EM_THREADS) {
+            const int slot = a.rep_ws[al];
+            if (slot < 0) continue;
+            const int rp = (int)(occ[slot] & 0xffffu);
+            a.rep_ws[al] = rp;
+            if (rp != al) atomicAdd(&cnt32[rp], 1);
+        }
+        __syncthreads();
+        // only the representatives stay live
+        for (int al = tid; al < Atot; al += EM_THREADS) {
+            const int rp = a.rep_ws[al];
+            if (rp >= 0 && rp != al) atomicAnd(reinterpret_cast<unsigned long long *>(&lw[al >> 6]), ~(1ull << (al & 63)));
+        }
+        __syncthreads();
+        tr.mark(15);
+    }
     if (warp == 0) {
         int run = 0;
         for (int j0 = 0; j0 < wp; j0 += 32) {
@@ -787,6 +920,12 @@ __device__ int em_compact_build(const EmArgs &a, Smem &sm, int32_t *lv, int C, i
         }
     }
     __syncthreads();
+    if (dedup) {  // alleles carried by compact column j (the merge counters live in the scratch that is zero-filled next)
+        const int32_t *cnt32 = reinterpret_cast<const int32_t *>(a.dense_ws);
+        for (int j = tid; j < An; j += EM_THREADS) a.mult_ws[j] = 1.0 + (double)cnt32[lv[j]];
+        __syncthreads();
+        sm.mult = a.mult_ws;
+    }
     const int wpc = max(2, ((An + 63) / 64 + 1) & ~1);
     // ---- gather every class row to A' bits (dense, in global scratch) ------------------------------------------------
     // bit-compress of a 64-bit word under the fixed mask live[j] (Hacker's Delight 7-4): the six move masks depend
@@ -953,6 +1092,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
     sm.red = reinterpret_cast<double *>(smem_raw + 16);
     sm.lv = nullptr; sm.cnt = nullptr; sm.cm64 = nullptr; sm.c64 = nullptr;
     sm.row_off = nullptr; sm.col_off = nullptr; sm.r_ent = nullptr; sm.c_ent = nullptr; sm.dense_g = nullptr;
+    sm.mult = nullptr;
     bool compacted = false;
     if (!COOP && a.compact) {
         // ---- allele-compacted, fully shared-memory-resident problem ---------------------------------------------
@@ -972,7 +1112,11 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
             a.in_result[al] = 0;
             a.first_class[al] = FK_NONE;
         }
-        const int An = em_compact_build(a, sm, lv, a.C, &s_int);
+        // identical columns are merged when there are no allele lengths (lengths differ inside a set) and the sizes fit
+        // the merge tables
+        const bool dedup = !a.len && a.rep_ws && a.wp <= DEDUP_COLS * EM_WARPS && a.A_live_max <= DEDUP_MAX_LIVE &&
+                           a.slab_bytes >= (size_t)a.wp * 64 * 12 + DEDUP_CAP * 4 && a.slab_bytes >= (size_t)a.wp * 8 * 32;
+        const int An = em_compact_build(a, sm, lv, a.C, &s_int, dedup, tr);
         if (An > a.A_live_max) {
             if (tid == 0) {
                 a.iters_status[0] = 0;
@@ -1028,7 +1172,8 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
         if (s_status != HGT_OK) break;
         if (compact_ok && (iter == 0 || (iter > 10 && a.remove_low))) {
             int cnt_live = 0;
-            for (int al = tid; al < a.A; al += EM_THREADS) cnt_live += l0[al] ? 1 : 0;
+            for (int al = tid; al < a.A; al += EM_THREADS)
+                if (l0[al]) cnt_live += (sm.mult && sm.mult[al] != 1.0) ? 1000 : 1;  // merged columns stay on the sweeps
             cnt_live = (int)block_sum((double)cnt_live, sm.red);
             if (cnt_live > 0 && cnt_live <= 64) {
                 // ---- build the compact problem ---------------------------------------------------------------
@@ -1131,8 +1276,14 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
                 if (!l1[al] || !l2[al]) keyerr = 1;
                 const double r = v1[al] - v0[al];
                 const double v = v2[al] - v1[al] - r;
-                ssr += r * r;
-                ssv += v * v;
+                if (sm.mult) {  // m equal alleles with r / m each: sum of squares = r^2 / m
+                    const double m = sm.mult[al];
+                    ssr += r * r / m;
+                    ssv += v * v / m;
+                } else {
+                    ssr += r * r;
+                    ssv += v * v;
+                }
             }
         }
         ssr = block_sum(ssr, sm.red);
@@ -1204,7 +1355,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
             for (int al = tid; al < a.A; al += EM_THREADS) {
                 const bool key = l0[al];
                 const int ao = orig_allele(sm, al);
-                a.prob[ao] = key ? (a.len ? v0[al] / a.len[ao] / total : v0[al] / total) : 0.0;
+                a.prob[ao] = key ? (a.len ? v0[al] / a.len[ao] / total : (sm.mult ? v0[al] / sm.mult[al] / total : v0[al] / total)) : 0.0;
                 a.in_result[ao] = key ? 1 : 0;
             }
         }
@@ -1215,6 +1366,17 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
                                row_hi, resident, loaded, parity, &s_status, tr);
         } else if (writer) {
             for (int al = tid; al < A_orig; al += EM_THREADS) a.first_class[al] = FK_NONE;
+        }
+        if (sm.mult) {  // merged columns: every member gets its representative's result
+            __syncthreads();
+            for (int al = tid; al < A_orig; al += EM_THREADS) {
+                const int rp = a.rep_ws[al];
+                if (rp >= 0 && rp != al) {
+                    a.prob[al] = a.prob[rp];
+                    a.in_result[al] = a.in_result[rp];
+                    a.first_class[al] = a.first_class[rp];
+                }
+            }
         }
     }
     tr.mark(6);
@@ -1240,6 +1402,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_part_kernel(EmArgs a, int mo
     sm.red = reinterpret_cast<double *>(smem_raw + 16);
     sm.lv = nullptr; sm.cnt = nullptr; sm.cm64 = nullptr; sm.c64 = nullptr;
     sm.row_off = nullptr; sm.col_off = nullptr; sm.r_ent = nullptr; sm.c_ent = nullptr; sm.dense_g = nullptr;
+    sm.mult = nullptr;
     const int Apad = a.wp * 64;
     sm.p = sm.red + 40;
     sm.w = sm.p + p_slots(Apad);
@@ -1413,10 +1576,13 @@ int em_launch_batched(hgt_ctx *ctx, cudaStream_t st, int n, const EmArgs *planne
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // global scratch of one allele-compacted problem: the gathered dense rows (never larger than the shared-memory
 // budget they were planned into) + the bit-compress masks
-inline size_t em_compact_scratch_bytes(int wp) { return align_up(EM_DENSE_SCRATCH + (size_t)wp * 48, 256); }
-inline void em_set_scratch(EmArgs *a, void *scratch) {
-    a->dense_ws = static_cast<uint64_t *>(scratch);
-    a->mv_ws = reinterpret_cast<uint64_t *>(static_cast<unsigned char *>(scratch) + EM_DENSE_SCRATCH);
+inline size_t em_compact_scratch_bytes(int wp) { return align_up(EM_DENSE_SCRATCH + (size_t)wp * 48 + (size_t)wp * 64 * 12, 256); }
+inline void em_set_scratch(EmArgs *a, void *scratch) {  // a->wp must be set
+    unsigned char *b = static_cast<unsigned char *>(scratch);
+    a->dense_ws = reinterpret_cast<uint64_t *>(b);
+    a->mv_ws = reinterpret_cast<uint64_t *>(b + EM_DENSE_SCRATCH);
+    a->mult_ws = reinterpret_cast<double *>(b + EM_DENSE_SCRATCH + (size_t)a->wp * 48);
+    a->rep_ws = reinterpret_cast<int32_t *>(b + EM_DENSE_SCRATCH + (size_t)a->wp * 48 + (size_t)a->wp * 64 * 8);
 }
 
 // workspace carve-up (device pointers) for one problem

@@ -177,3 +177,35 @@ def test_sharded_em_partial_sweeps(A, C, groups, remove_low, use_len):
         assert [a for a, _ in res] == [a for a, _ in ref]
         for (_, x), (_, y) in zip(res, ref):
             assert x == pytest.approx(y, rel=REL, abs=1e-9)
+
+
+@pytest.mark.parametrize("use_len", [False, True])
+@pytest.mark.parametrize("A,C", [(200, 60), (3000, 400)])
+def test_em_identical_columns_tie_exactly(A, C, use_len):
+    """Alleles that are members of exactly the same classes have EXACTLY equal abundances in the reference (same
+    arithmetic on the same numbers, common:1311-1336), and that tie decides their rank.  The kernel must keep the tie
+    bit-exact wherever the two alleles sit (different 32-allele words, other alleles of the word present or not), with
+    (no lengths) and without (lengths) the column merge, for any order of the class rows."""
+    from hisatgenotype_b200 import _lib
+    from hisatgenotype_b200.typing_common import em_arrays
+    rng = np.random.default_rng(A * 7 + C + (1 if use_len else 0))
+    member = rng.random((C, A)) < 0.08
+    member[:, 0] = True  # no empty class
+    twins = [(5, 150), (70, 71), (33, A - 1), (64, 129)]
+    for a, b in twins:
+        member[:, b] = member[:, a]
+    cnt = rng.integers(1, 40, C).astype(np.int64)
+    ln = np.full(A, 1000.0) if use_len else None  # equal lengths keep the twins tied
+    first = None
+    for trial in range(4):
+        order = rng.permutation(C) if trial else np.arange(C)
+        bits = _lib.pack_bits([np.nonzero(member[k])[0] for k in order], A)
+        prob, inres, fk, iters = em_arrays(bits, cnt[order], A, ln, False)
+        for a, b in twins:
+            assert inres[a] == inres[b]
+            assert prob[a] == prob[b], (trial, a, b, repr(prob[a]), repr(prob[b]))
+            assert fk[a] == fk[b]
+        if first is None:
+            first = prob
+        else:
+            np.testing.assert_allclose(prob, first, rtol=1e-6, atol=1e-20)  # the row order only moves the last bits
