@@ -1802,8 +1802,15 @@ static int fetch_results(hgt_batch *b, cudaStream_t st, int level) {
 }
 
 // ---- stage 2: GPU only, no host synchronisation -----------------------------------------------------------------
+static int tune_env(const char *name, int dflt) {  // grid-size experiments without a rebuild
+    const char *e = getenv(name);
+    const int v = e ? atoi(e) : dflt;
+    return v > 0 ? v : dflt;
+}
+
 template <int WPL>
 static void launch_stage_a(hgt_batch *b, cudaStream_t st, LocusBatch &lb) {
+    static const int class_per_sm = tune_env("HGT_CLASS_CTAS_PER_SM", 32), compat_per_sm = tune_env("HGT_COMPAT_CTAS_PER_SM", 16);
     hgt_ctx *ctx = b->ctx;
     const hgt_locus *loc = lb.loc;
     const LocusDev ld = locus_dev(loc);
@@ -1834,7 +1841,7 @@ static void launch_stage_a(hgt_batch *b, cudaStream_t st, LocusBatch &lb) {
     }
     b->timer.begin(ctx, st, 1);
     if (H > 0) {
-        const int ctas = (int)std::min<int64_t>((H + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 4);
+        const int ctas = (int)std::min<int64_t>((H + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * compat_per_sm);
         compat_kernel<WPL><<<ctas, WARPS_PER_CTA * 32, 0, st>>>(ld, lb.dj<int32_t>(lb.ja.o_ht), lb.dj<int32_t>(lb.ja.o_hl),
                                                                    lb.dj<int32_t>(lb.ja.o_hr), lb.dj<int64_t>(lb.ja.o_row_off),
                                                                    lb.dj<int32_t>(lb.ja.o_rows), H, lb.d_hapbits.as<uint64_t>());
@@ -1845,7 +1852,7 @@ static void launch_stage_a(hgt_batch *b, cudaStream_t st, LocusBatch &lb) {
     const int64_t ns = lb.n_small, nb = lb.n_big;
     b->timer.begin(ctx, st, 2);
     if (ns > 0) {
-        const int ctas = (int)std::min<int64_t>((ns + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 8);
+        const int ctas = (int)std::min<int64_t>((ns + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * class_per_sm);
         class_kernel<WPL, 3><<<ctas, WARPS_PER_CTA * 32, 0, st>>>(wp, loc->d_mask, lb.dj<int64_t>(lb.ja.o_job_off),
                                                                   lb.dj<int32_t>(lb.ja.o_job_ut), lb.dj<int32_t>(lb.ja.o_job_pair),
                                                                   lb.dj<int32_t>(lb.ja.o_job_list), ns, lb.d_hapbits.as<uint64_t>(), pool);
