@@ -284,7 +284,9 @@ def run_oversized(args):
     sim = synth.ReadSimulator(loc)
     text = sim.generate(truth, n_reads, seed=77 + rank, err_rate=ERR, read_len=READ_LEN, frag_len=FRAG_LEN, paired=False,
                         prefix="k%02d_" % rank)
-    params = TC.make_params(allow_discordant=True)
+    # host threads of the intake / walk stages: the ranks of one box share its cores
+    host_threads = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
+    params = TC.make_params(allow_discordant=True, n_threads=host_threads)
     stream = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 
@@ -427,7 +429,7 @@ def run_oversized(args):
                     "ms_per_step": float(e2e_vec[0]), "input": "host alignment text, %d bytes on rank 0" % len(text),
                     "host_stage_ms_rank0": {n: host_ms[i] / 2 for i, n in enumerate(
                         ["intake", "pileup_pack", "pileup_gpu", "walk", "job_pack", "upload_alloc", "finish_host_and_em2"])},
-                    "host_threads": os.cpu_count()},
+                    "host_threads": host_threads, "host_cores": os.cpu_count()},
             "gpu_launches": int(launches), "clocks": clocks.summary(), "example_call": calls[0],
         }
         print(json.dumps(line))
@@ -482,7 +484,9 @@ def main():
     sims = [{"sim": synth.ReadSimulator(l), "names": sorted(n for n in l.alleles if l.alleles[n])} for l in loci]
     S = args.samples
     units = simulate_units(loci, sims, S, rank * S)  # loci/sample sharding: no communication
-    params = TC.make_params()
+    # host threads of the intake / walk stages: the ranks of one box share its cores
+    host_threads = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
+    params = TC.make_params(n_threads=host_threads)
     stream = torch.cuda.current_stream().cuda_stream
     flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 
@@ -632,12 +636,12 @@ def main():
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d.value / n_e2e,
                     "d2h_bytes_per_step": d2h.value / n_e2e, "ms_per_step": float(e2e_vec[0]),
                     "input": "host alignment text, %d bytes per step on rank 0" % sum(len(t) for _, t in units),
-                    "wall_ms_rank0": e2e_wall, "host_stage_ms_rank0": e2e_host, "host_threads": os.cpu_count()},
+                    "wall_ms_rank0": e2e_wall, "host_stage_ms_rank0": e2e_host, "host_threads": host_threads, "host_cores": os.cpu_count()},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),
             "example_call": calls[0],
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # the CPU baseline is timed on rank 0 at N = 1 only
             build_oracle_loci(cont, loci)
             line["cpu_baseline"] = cpu_baseline(units[:args.cpu_baseline_units])
         print(json.dumps(line))
