@@ -798,7 +798,7 @@ __device__ __forceinline__ void pool_insert(const ClassPool &pool, int wp, int u
 
 // warp per job; a job = (unit, table, pair) with a list of haplotype bitsets; P bit-planes count up to 2^P-1
 template <int WPL, int P>
-__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, (WPL <= 4 && P <= 3) ? 5 : 1)
     class_kernel(int wp, const uint64_t *__restrict__ masks, const int64_t *__restrict__ job_off,
                  const int32_t *__restrict__ job_ut, const int32_t *__restrict__ job_pair,
                  const int32_t *__restrict__ job_list, int64_t n_jobs, const uint64_t *__restrict__ hapbits,
