@@ -56,6 +56,8 @@ def random_problem(rng, A, C, groups, dense_frac=0.05):
     (4000, 1500, 60, True, True),
     (8000, 2000, 60, True, True),    # BASELINE.md "EM large"
     (8192, 6000, 64, True, False),   # multi-CTA cooperative path, streaming slabs
+    (5000, 6000, 50, True, False),   # cooperative path, last warps without allele words
+    (9000, 5000, 60, False, False),  # cooperative path, 16 slots per thread
 ])
 def test_em_matches_c_oracle(A, C, groups, remove_low, use_len):
     import em_oracle
@@ -180,7 +182,7 @@ def test_sharded_em_partial_sweeps(A, C, groups, remove_low, use_len):
 
 
 @pytest.mark.parametrize("use_len", [False, True])
-@pytest.mark.parametrize("A,C", [(200, 60), (3000, 400)])
+@pytest.mark.parametrize("A,C", [(200, 60), (3000, 400), (8192, 3000)])  # the last one runs on all SMs
 def test_em_identical_columns_tie_exactly(A, C, use_len):
     """Alleles that are members of exactly the same classes have EXACTLY equal abundances in the reference (same
     arithmetic on the same numbers, common:1311-1336), and that tie decides their rank.  The kernel must keep the tie
