@@ -1,3 +1,10 @@
+"""Per-source-line view of a kernel from an `ncu --set full --import-source on` report (kernels built with -lineinfo).
+
+usage: tools/ncu_lines.py <report.ncu-rep> <source file> [top N]
+Reads `ncu -i <rep> --page source --csv --print-source cuda,sass` for the kernels matching `em_kernel`, sums the warp
+stall samples, executed instructions and barrier stalls of the SASS lines behind every CUDA source line and prints the
+top N lines by samples (used for profiles/*_lines.txt).
+"""
 import csv, collections, sys, subprocess
 rep, src_path = sys.argv[1], sys.argv[2]
 topn = int(sys.argv[3]) if len(sys.argv)>3 else 40
