@@ -89,14 +89,16 @@ class CudaSweep:
 
 
     # ---- device-resident loop: sweeps and O(A) vector steps are kernels of libhgt, nothing but the all-reduce is torch
-    def dev_sweep(self, mode, src):
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+    def dev_sweep(self, mode, src, stream=None):
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self.L.hgt_em_shard_sweep_dev(self.ctx, stream, self.bits_ptr, self.cnt_f64, self.cnt_u64, self.key_ptr,
                                                  self.key_offset, self.C, self.A, self.wp, mode, src, self.state.data_ptr(),
                                                  self.ws.data_ptr()))
 
-    def dev_vec(self, op, len_ptr, src=0, dst=0, iteration=0, remove_low=False):
-        stream = torch.cuda.current_stream(self.device).cuda_stream
+    def dev_vec(self, op, len_ptr, src=0, dst=0, iteration=0, remove_low=False, stream=None):
+        if stream is None:
+            stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self.L.hgt_em_shard_vec_dev(self.ctx, stream, op, self.A, self.state.data_ptr(), len_ptr, src, dst,
                                                iteration, 1 if remove_low else 0))
 
@@ -116,11 +118,12 @@ def _single_abundance_sharded_dev(backend, allele_len, remove_low, group, max_it
     ln = None if allele_len is None else torch.as_tensor(np.asarray(allele_len, np.float64), device=b.device)
     ln_ptr = None if ln is None else ln.data_ptr()
     b.state.zero_()
+    st = torch.cuda.current_stream(b.device).cuda_stream  # looked up once: every launch of the loop goes to this stream
 
     def next_prob(src, dst):
-        b.dev_sweep(MODE_NEXT, src)
+        b.dev_sweep(MODE_NEXT, src, st)
         _allreduce(b.red, SUM, group)
-        b.dev_vec(SHARD_FINISH, ln_ptr, src, dst)
+        b.dev_vec(SHARD_FINISH, ln_ptr, src, dst, stream=st)
 
     def check(scal):
         if scal[3] != 0:
@@ -128,27 +131,27 @@ def _single_abundance_sharded_dev(backend, allele_len, remove_low, group, max_it
         if scal[2] != 0:
             raise KeyError("allele vanished from next_prob output during SQUAREM step")
 
-    b.dev_sweep(MODE_INIT, -1)
+    b.dev_sweep(MODE_INIT, -1, st)
     _allreduce(b.red, SUM, group)
-    b.dev_vec(SHARD_FINISH, ln_ptr, -1, 0)
+    b.dev_vec(SHARD_FINISH, ln_ptr, -1, 0, stream=st)
     diff, it = 1.0, 0
     while diff > 0.0001 and it < max_iter:
         next_prob(0, 1)
         next_prob(1, 2)
-        b.dev_vec(SHARD_SQUAREM, ln_ptr)
+        b.dev_vec(SHARD_SQUAREM, ln_ptr, stream=st)
         next_prob(3, 4)
-        b.dev_vec(SHARD_ADVANCE, ln_ptr, iteration=it, remove_low=remove_low)
-        scal = b.scal.cpu()  # the one host synchronisation of the iteration
+        b.dev_vec(SHARD_ADVANCE, ln_ptr, iteration=it, remove_low=remove_low, stream=st)
+        scal = b.scal.tolist()  # the one host synchronisation of the iteration (64 bytes)
         check(scal)
         diff = float(scal[4])
         it += 1
-    b.dev_vec(SHARD_FINAL, ln_ptr, remove_low=remove_low)
+    b.dev_vec(SHARD_FINAL, ln_ptr, remove_low=remove_low, stream=st)
     first = torch.full((b.A,), FK_NONE, dtype=torch.int32, device=b.device)
     if it > 0:
-        b.dev_sweep(MODE_FIRSTK, 5)
+        b.dev_sweep(MODE_FIRSTK, 5, st)
         _allreduce(b.fk, MIN, group)
         first = torch.where(b.live[4] != 0, b.fk, first)
-    check(b.scal.cpu())
+    check(b.scal.tolist())
     return b.vec[1].clone(), b.live[0] != 0, first, it
 
 
