@@ -931,18 +931,19 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 
 // Gene_counts (core:1187-1190) of table (unit, 0): counts[a] = sum of class counts over classes holding a;
 // first[a] = first pair whose class holds a.  grid = (allele tiles, units, class chunks): a CTA folds one chunk of
-// COUNT_CHUNK classes into the totals with integer atomics (order-independent, so still exact).
-constexpr int COUNT_CHUNK = 512;
+// `chunk` classes into the totals with integer atomics (order-independent, so still exact).
+constexpr int COUNT_CHUNK_MIN = 128, COUNT_CHUNK_MAX = 512;  // classes per CTA: chosen per launch from the pair bound
 constexpr int COUNT_THREADS = 256;  // alleles per CTA = 4 words of every class row
 constexpr int COUNT_TILE = 64;      // class rows staged in shared memory at a time
 __global__ void __launch_bounds__(COUNT_THREADS)
-    table_counts_kernel(int A, int wp, int table, ClassPool pool, unsigned long long *__restrict__ a_count,
+    table_counts_kernel(int A, int wp, int table, int chunk, ClassPool pool, unsigned long long *__restrict__ a_count,
                         int32_t *__restrict__ a_first) {
     // The 32-byte segment [4 words] of COUNT_TILE rows goes to shared memory with one load per thread (a full sector per
     // row); every thread then scans the tile for its own allele out of shared memory, so the serial chain per thread is
-    // COUNT_CHUNK / COUNT_TILE global round trips instead of COUNT_CHUNK.
+    // chunk / COUNT_TILE global round trips instead of chunk.
     __shared__ uint64_t s_bits[COUNT_TILE][COUNT_THREADS / 64];
     __shared__ unsigned long long s_cnt[COUNT_TILE];
+    __shared__ unsigned long long s_nz[COUNT_THREADS / 64];  // per word column: the tile rows whose word is non-zero
     __shared__ int32_t s_first[COUNT_TILE];
     const int u = blockIdx.y;
     const int ut = u * 4 + table;
@@ -951,7 +952,7 @@ __global__ void __launch_bounds__(COUNT_THREADS)
     const int word0 = blockIdx.x * (COUNT_THREADS / 64);
     const int64_t base = pool.ut_base[ut];
     const int n = min(pool.ut_ncls[ut], (int)(pool.ut_base[ut + 1] - base));
-    const int k0 = blockIdx.z * COUNT_CHUNK, k1 = min(n, k0 + COUNT_CHUNK);
+    const int k0 = blockIdx.z * chunk, k1 = min(n, k0 + chunk);
     if (k0 >= k1) return;
     unsigned long long c = 0;
     int32_t f = 0x7fffffff;
@@ -962,14 +963,20 @@ __global__ void __launch_bounds__(COUNT_THREADS)
         uint64_t v = 0ull;
         if (lr < nr && word0 + lw < wp) v = pool.bits[(size_t)(base + kt + lr) * wp + word0 + lw];
         __syncthreads();  // the previous tile has been consumed
+        if (t < COUNT_THREADS / 64) s_nz[t] = 0ull;
+        __syncthreads();
         s_bits[lr][lw] = v;
+        if (v != 0ull) atomicOr(&s_nz[lw], 1ull << lr);
         if (t < nr) {
             s_cnt[t] = pool.count[base + kt + t];
             s_first[t] = pool.first[base + kt + t];
         }
         __syncthreads();
-#pragma unroll 8
-        for (int r = 0; r < nr; r++) {
+        // only the rows whose word of this thread's column is non-zero (the same rows for the 64 threads of a column)
+        unsigned long long m = s_nz[my_word];
+        while (m) {
+            const int r = __ffsll((long long)m) - 1;
+            m &= m - 1;
             if ((s_bits[r][my_word] >> my_bit) & 1ull) {
                 c += s_cnt[r];
                 f = min(f, s_first[r]);
@@ -1930,11 +1937,15 @@ static int batch_execute(hgt_batch *b, cudaStream_t st) {
             b->timer.begin(ctx, st, 3);
             int64_t max_pairs = 1;
             for (int u : lb.units) max_pairs = std::max<int64_t>(max_pairs, b->units[u].num_pairs);
-            dim3 grid((loc->A + COUNT_THREADS - 1) / COUNT_THREADS, (unsigned)n_units,
-                      (unsigned)std::min<int64_t>((max_pairs + COUNT_CHUNK - 1) / COUNT_CHUNK, 65535));
+            // classes per CTA: the serial chain of a CTA is chunk / COUNT_TILE dependent global round trips, so small
+            // chunks win as long as the grid (sized from the PAIR bound: class counts are known on the device only) does
+            // not drown in empty CTAs
+            int chunk = (int)std::min<int64_t>(COUNT_CHUNK_MAX, std::max<int64_t>(COUNT_CHUNK_MIN, (max_pairs / 256 + 63) / 64 * 64));
+            while ((max_pairs + chunk - 1) / chunk > 65535) chunk *= 2;
+            dim3 grid((loc->A + COUNT_THREADS - 1) / COUNT_THREADS, (unsigned)n_units, (unsigned)((max_pairs + chunk - 1) / chunk));
             HGT_CUDA(cudaMemsetAsync(lb.d_acount.p, 0, n_units * (size_t)loc->A * 8, st));
             HGT_CUDA(cudaMemsetAsync(lb.d_afirst.p, 0x7f, n_units * (size_t)loc->A * 4, st));
-            table_counts_kernel<<<grid, COUNT_THREADS, 0, st>>>(loc->A, loc->wp, 0, lb.pool(), lb.d_acount.as<unsigned long long>(),
+            table_counts_kernel<<<grid, COUNT_THREADS, 0, st>>>(loc->A, loc->wp, 0, chunk, lb.pool(), lb.d_acount.as<unsigned long long>(),
                                                       lb.d_afirst.as<int32_t>());
             ctx->launches++;
             b->timer.end(1);
