@@ -2051,7 +2051,7 @@ static int batch_finish(hgt_batch *b, cudaStream_t st) {
         HGT_CUDA(cudaMemcpyAsync(lb.d_keep.p, keep, n2 * wp * 8, cudaMemcpyHostToDevice, st));
         {
             b->timer.begin(ctx, st, 5);
-            dim3 grid(8, (unsigned)std::min<size_t>(n2, 16384));
+            dim3 grid(tune_env("HGT_PROJECT_CTAS", 16), (unsigned)std::min<size_t>(n2, 16384));
             const ClassPool pool = lb.pool();
             switch (wpl_of(wp)) {
                 case 1: project_kernel<1><<<grid, WARPS_PER_CTA * 32, 0, st>>>(wp, (int)n2, lb.d_ulist.as<int32_t>(), lb.d_keep.as<uint64_t>(), pool); break;
