@@ -152,7 +152,7 @@ def measured_peak():
 _ORACLE = {}
 
 
-def _oracle_unit(job):
+def _oracle_unit(job, keep=False):
     li, text = job
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import em_oracle
@@ -168,7 +168,11 @@ def _oracle_unit(job):
         _, it = em_oracle.single_abundance(cm, True, None)
         iters += it
     tb = time.perf_counter() - t0
-    return res["num_reads"], ta, iters, tb
+    if not keep:
+        return res["num_reads"], ta, iters, tb
+    # parity material (untimed): the three tables in dict order and the ranked calls of the EM driver
+    tabs = {k: (res["tables"][k].cmpt_items(ol), res["tables"][k].count_items(ol)) for k in ("gene", "exon", "primary")}
+    return res["num_reads"], ta, iters, tb, res["num_pairs"], tabs, O.locus_abundance(ol, res, True)
 
 
 def build_oracle_loci(cont, loci):
@@ -177,19 +181,52 @@ def build_oracle_loci(cont, loci):
     _ORACLE["loci"] = [O.OracleLocus(*locus_args(cont, loc.gene)) for loc in loci]
 
 
-def cpu_baseline(units):
-    """Oracle port on ONE core over a bounded sample of the same workload."""
+def cpu_baseline(units, batch=None):
+    """Oracle port on ONE core over a bounded sample of the same workload.  With `batch` (the GPU batch whose first
+    units are these units) every table, count list and ranked call of the sample is compared with the GPU's: the bench
+    checks what it times."""
     reads = ta = iters = tb = 0
-    for job in units:
-        r, a, i, b = _oracle_unit(job)
+    parity = {"units": 0, "tables": 0, "identical": True, "max_rel_abundance_err": 0.0, "first_difference": None}
+
+    def differ(what):
+        parity["identical"] = False
+        if parity["first_difference"] is None:
+            parity["first_difference"] = what
+
+    for u, job in enumerate(units):
+        out = _oracle_unit(job, keep=batch is not None)
+        r, a, i, b = out[:4]
         reads += r
         ta += a
         iters += i
         tb += b
-    return {"value": reads / ta if ta > 0 else None, "unit": "reads/s", "cores": 1, "kind": "port",
+        if batch is None:
+            continue
+        pairs, tabs, calls = out[4:]
+        s = batch.unit_summary(u)
+        if (s["num_reads"], s["num_pairs"]) != (r, pairs):
+            differ("unit %d: reads/pairs %s vs oracle %s" % (u, (s["num_reads"], s["num_pairs"]), (r, pairs)))
+        for t_i, key in enumerate(("gene", "exon", "primary")):
+            if list(map(list, batch.unit_gene_cmpt(u, t_i).items())) != tabs[key][0]:
+                differ("unit %d: Gene_cmpt of table %s" % (u, key))
+            if batch.unit_gene_counts(u, t_i) != tabs[key][1]:
+                differ("unit %d: Gene_counts of table %s" % (u, key))
+            parity["tables"] += 1
+        got = batch.unit_calls(u)
+        if [x for x, _ in got] != [x for x, _ in calls]:
+            differ("unit %d: ranked alleles %s vs oracle %s" % (u, got[:3], calls[:3]))
+        else:
+            for (_, x), (_, y) in zip(got, calls):
+                rel = abs(x - y) / max(abs(y), 1e-300)
+                parity["max_rel_abundance_err"] = max(parity["max_rel_abundance_err"], rel)
+                if rel > 1e-6 and abs(x - y) > 1e-12:
+                    differ("unit %d: abundance %r vs oracle %r" % (u, x, y))
+        parity["units"] += 1
+    base = {"value": reads / ta if ta > 0 else None, "unit": "reads/s", "cores": 1, "kind": "port",
             "sample": "%d (sample, locus) units = %d reads of the same workload, oracle/hgt_oracle.py stage (a); "
                       "EM via oracle/em_oracle.c" % (len(units), reads),
             "em_iters_per_sec": iters / tb if tb > 0 else None, "seconds": ta + tb}
+    return base, (parity if batch is not None else None)
 
 
 def run_reference_arm(args):
@@ -600,6 +637,7 @@ def main():
         dist.all_reduce(e2e_vec, op=dist.ReduceOp.MAX)
     e2e_value = reads_all / (float(e2e_vec[0]) / 1000.0)
 
+    parity_failed = False
     if rank == 0:
         peak, peak_src = measured_peak()
         a_ms = stage["compat"] + stage["class"]
@@ -643,12 +681,15 @@ def main():
         }
         if not args.no_cpu_baseline and world == 1:  # the CPU baseline is timed on rank 0 at N = 1 only
             build_oracle_loci(cont, loci)
-            line["cpu_baseline"] = cpu_baseline(units[:args.cpu_baseline_units])
+            line["cpu_baseline"], line["parity_checked"] = cpu_baseline(units[:args.cpu_baseline_units], batch)
         print(json.dumps(line))
+        if line.get("parity_checked") and not line["parity_checked"]["identical"]:
+            sys.stderr.write("bench: GPU results differ from the oracle: %s\n" % line["parity_checked"]["first_difference"])
+            parity_failed = True
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    return 0
+    return 1 if parity_failed else 0
 
 
 def ncu_traffic(kernel, workload, samples):

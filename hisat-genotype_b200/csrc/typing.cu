@@ -1195,7 +1195,7 @@ struct LocusBatch {
         size_t o_job_off = 0, o_row_off = 0, o_ut_base = 0, o_job_ut = 0, o_job_pair = 0, o_job_list = 0, o_hl = 0, o_hr = 0,
                o_ht = 0, o_rows = 0, bytes = 0;
     } ja;
-    int64_t n_jobs = 0, n_small = 0, n_big = 0, n_haps = 0, n_rows = 0;
+    int64_t n_jobs = 0, n_small = 0, n_big = 0, n_haps = 0, n_rows = 0, max_job_haps = 0;
     std::vector<int64_t> ut_base;  // [n_units*4 + 1]
     int64_t n_rows_pool = 0;
     PinBuf h_jobs;
@@ -1572,6 +1572,7 @@ static int batch_prepare(hgt_batch *b) {
                                 return HGT_ERR_UNSUPPORTED;
                             }
                             small += k <= 7;
+                            lb.max_job_haps = std::max(lb.max_job_haps, k);
                         }
                         H += (int64_t)T.hap_left.size();
                         RW += (int64_t)T.rows.size();
@@ -2191,6 +2192,21 @@ extern "C" int hgt_batch_totals(const hgt_batch *b, int64_t *n_units, int64_t *n
     if (n_haplotypes) *n_haplotypes = h;
     if (n_rows) *n_rows = rows;
     if (algorithmic_bytes) *algorithmic_bytes = bytes;
+    return HGT_OK;
+}
+
+extern "C" int hgt_batch_job_stats(const hgt_batch *b, int64_t out[4]) {
+    if (!b || !out || !b->prepared) {
+        hgt_set_error("hgt_batch_job_stats: batch is not prepared");
+        return HGT_ERR_ARG;
+    }
+    out[0] = out[1] = out[2] = out[3] = 0;
+    for (const LocusBatch &lb : b->lb) {
+        out[0] += lb.n_jobs;
+        out[1] += lb.n_big;
+        out[2] = std::max(out[2], lb.max_job_haps);
+        out[3] += lb.n_haps;
+    }
     return HGT_OK;
 }
 

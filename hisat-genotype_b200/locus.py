@@ -76,6 +76,8 @@ def _bind(L):
         getattr(L, fn).argtypes = [vp, vp]
     L.hgt_batch_totals.restype = ctypes.c_int
     L.hgt_batch_totals.argtypes = [vp] + [P(i64)] * 6
+    L.hgt_batch_job_stats.restype = ctypes.c_int
+    L.hgt_batch_job_stats.argtypes = [vp, P(i64 * 4)]
     L.hgt_batch_unit_summary.restype = ctypes.c_int
     L.hgt_batch_unit_summary.argtypes = [vp, i64, P(i64), P(i64), P(i32 * 4), P(i32 * 2), P(i32 * 2)]
     L.hgt_batch_unit_table.restype = ctypes.c_int

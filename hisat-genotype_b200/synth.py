@@ -104,10 +104,11 @@ def _compatible_subset(cands, variants):
 
 def make_locus(gene, seed, L=3500, n_alleles=200, n_groups=12, core_vars=60, pool_private=400,
                private_per_allele=3, del_frac=0.06, ins_frac=0.0, exons=None, chrom="chr6",
-               backbone_allele=True):
-    """One locus: alleles come in groups sharing a core variant set, plus a few toggles each."""
+               backbone_allele=True, alphabet=NT):
+    """One locus: alleles come in groups sharing a core variant set, plus a few toggles each.  A short `alphabet`
+    (e.g. "AC") makes the backbone repetitive, so deletions get many equivalent placements (Alts_left/right)."""
     rng = np.random.default_rng(seed)
-    bb = "".join(NT[i] for i in rng.integers(0, 4, size=L))
+    bb = "".join(alphabet[i] for i in rng.integers(0, len(alphabet), size=L))
     if exons is None:
         # three exons, first two primary (the ".locus" example of SURVEY appendix C, scaled to L)
         e = [(int(L * 0.09), int(L * 0.17), True), (int(L * 0.29), int(L * 0.37), True),

@@ -215,6 +215,11 @@ class Batch:
         keys = ("n_units", "num_reads", "num_pairs", "n_haplotypes", "n_rows", "algorithmic_bytes")
         return dict(zip(keys, (x.value for x in v)))
 
+    def job_stats(self):
+        v = (ctypes.c_int64 * 4)()
+        _lib.check(lib().hgt_batch_job_stats(self.handle, ctypes.byref(v)))
+        return dict(n_jobs=v[0], n_big_jobs=v[1], max_haplotypes_per_job=v[2], n_haplotypes=v[3])
+
     def unit_summary(self, u):
         nr, npairs = ctypes.c_int64(0), ctypes.c_int64(0)
         nc, it, stt = (ctypes.c_int32 * 4)(), (ctypes.c_int32 * 2)(), (ctypes.c_int32 * 2)()
@@ -504,6 +509,42 @@ def typing(simulation, full_path_base_fname, locus_list, genotype_genome, partia
         sys.stderr.write(text)
     if simulation:
         return test_passed
+
+
+def smoke_check(device=None):
+    """One small stage (a) + (b) run on the GPU checked against the oracle: a 2,100-allele synthetic hla locus (two
+    words per lane in the allele-set kernels), 300 read pairs, three tables bit-exact and the ranked calls identical.
+    Called by __graft_entry__.smoke(); the oracle is the checker only (tests / smoke / bench cpu_baseline)."""
+    import hgt_oracle as O  # oracle/ is on sys.path only inside smoke() and the tests
+    from . import synth
+    loc = synth.make_locus("A", 17, L=2500, n_alleles=2100, n_groups=30, core_vars=60, pool_private=700, del_frac=0.1)
+    cont = synth.reference_containers([loc], "hla")
+    g = "A"
+    args = ("hla", g, cont["refGenes"][g], cont["Genes"][g][cont["refGenes"][g]], cont["Vars"][g], cont["Var_list"][g],
+            cont["Links"], cont["Gene_names"][g], cont["Gene_lengths"][g], cont["refGene_loci"][g][4],
+            cont["refGene_loci"][g][5])
+    rng = np.random.default_rng(17)
+    names = sorted(n for n in loc.alleles if loc.alleles[n])
+    truth = [names[i] for i in rng.choice(len(names), 2, replace=False)]
+    sam = synth.simulate_sam(loc, truth, n_pairs=300, rng=rng, err_rate=0.004)
+    ol = O.OracleLocus(*args)
+    ref = O.type_locus(ol, sam, simulation=False)
+    t = LocusTables(*args, device=device)
+    batch = Batch([t], make_params(), True, device=device)
+    try:
+        batch.add_unit(0, sam)
+        batch.run()
+        s = batch.unit_summary(0)
+        assert (s["num_reads"], s["num_pairs"]) == (ref["num_reads"], ref["num_pairs"]), (s, ref["num_reads"])
+        for tb, key in ((TABLE_GENE, "gene"), (TABLE_EXON, "exon"), (TABLE_PRIMARY, "primary")):
+            assert list(map(list, batch.unit_gene_cmpt(0, tb).items())) == ref["tables"][key].cmpt_items(ol), key
+            assert batch.unit_gene_counts(0, tb) == ref["tables"][key].count_items(ol), key
+        calls = batch.unit_calls(0, 4)
+        assert len(calls) >= 1
+    finally:
+        batch.close()
+        t.close()
+    return {"reads": ref["num_reads"], "pairs": ref["num_pairs"], "top": calls[:2], "truth": truth}
 
 
 class HostWalk:

@@ -237,6 +237,9 @@ int hgt_batch_run(hgt_batch *b); /* prepare + execute + finish */
  * allele-set row per pair and table */
 int hgt_batch_totals(const hgt_batch *b, int64_t *n_units, int64_t *num_reads, int64_t *num_pairs,
                      int64_t *n_haplotypes, int64_t *n_rows, int64_t *algorithmic_bytes);
+/* (pair, table) jobs of a prepared batch: out[0] jobs, out[1] jobs with more than 7 haplotypes (the 8-bit-plane class
+ * kernel, core:1171-1236 with > 7 add_count calls per pair), out[2] largest haplotype count of a job, out[3] haplotypes */
+int hgt_batch_job_stats(const hgt_batch *b, int64_t out[4]);
 int hgt_batch_unit_summary(const hgt_batch *b, int64_t unit, int64_t *num_reads, int64_t *num_pairs,
                            int32_t n_classes[4], int32_t em_iters[2], int32_t em_status[2]);
 int hgt_batch_unit_table(hgt_batch *b, int64_t unit, int32_t table, uint64_t *class_bits, int64_t *class_count,

@@ -1015,3 +1015,44 @@ def single_abundance(cmpt, remove_low=False, lengths=None):
         prob = prune(prob)
     norm(prob)
     return sorted(([a, p] for a, p in prob.items()), key=lambda x: x[1], reverse=True), it
+
+
+# ------------------------------------------------------------------------------------------------
+# EM driver of typing() (core:1679-1789) on the tables of type_locus(): Gene_prob as the report ranks it.
+# `em` = a single_abundance implementation returning (ranked list, iterations); default the C restatement.
+# ------------------------------------------------------------------------------------------------
+def locus_abundance(loc, res, remove_low=True, em=None):
+    if em is None:
+        import em_oracle
+        em = em_oracle.single_abundance
+    gene_cmpt = dict(map(tuple, res["tables"]["gene"].cmpt_items(loc)))
+    if loc.base_fname != "hla":
+        # core:1783-1789 (a single class raises TypeError on Python 3: Gene_cmpt.keys()[0])
+        if len(gene_cmpt) <= 1:
+            if len(gene_cmpt) == 1:
+                raise TypeError("'dict_keys' object is not subscriptable")
+            return []
+        return em(gene_cmpt, False, {})[0]
+    exon_cmpt = dict(map(tuple, res["tables"]["exon"].cmpt_items(loc)))
+    exon_prob = em(exon_cmpt, remove_low, {})[0]                                     # core:1732-1737
+    exon_alleles, exon_prob_sum = set(), 0.0
+    for i, (allele, prob) in enumerate(exon_prob):                                  # core:1739-1749
+        if i >= 10 and prob < 0.03:
+            break
+        group = loc.allele_rep_groups[allele]
+        if len(group) <= 1:
+            continue
+        exon_prob_sum += prob
+        exon_alleles |= set(group)
+    if not exon_alleles:
+        return exon_prob
+    cmpt2 = {}
+    for key, cnt in gene_cmpt.items():                                              # core:1753-1766
+        k2 = "-".join(a for a in key.split("-") if a in exon_alleles)
+        if k2:
+            cmpt2[k2] = cmpt2.get(k2, 0) + cnt
+    full = em(cmpt2, True, loc.gene_lengths)[0]                                     # core:1767
+    comb = {a: p for a, p in exon_prob if a not in exon_alleles}                    # core:1771-1782
+    for a, p in full:
+        comb[a] = p * exon_prob_sum
+    return sorted(([a, p] for a, p in comb.items()), key=lambda x: x[1], reverse=True)

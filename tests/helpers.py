@@ -84,3 +84,32 @@ def tables_from_jobs(loc, walk, hla):
         out.append(([["-".join(loc.names_of(b)), c] for b, c in cmpt.items()],
                     [[loc.names[i], c] for i, c in counts.items()]))
     return out
+
+
+def synthetic_case(seed, A, L=2500, n_pairs=1000, base="hla", del_frac=0.1, alphabet="ACGT", n_groups=12, core_vars=60,
+                   pool_private=300, err_rate=0.004, paired=True):
+    """Database + reads from hisatgenotype_b200.synth (sizes the reference-captured goldens do not reach): returns
+    (LocusTables/OracleLocus constructor args, alignment lines, truth alleles)."""
+    from hisatgenotype_b200 import synth
+    loc = synth.make_locus("A", seed, L=L, n_alleles=A, n_groups=n_groups, core_vars=core_vars,
+                           pool_private=pool_private, del_frac=del_frac, alphabet=alphabet)
+    cont = synth.reference_containers([loc], base)
+    g = "A"
+    args = (base, g, cont["refGenes"][g], cont["Genes"][g][cont["refGenes"][g]], cont["Vars"][g], cont["Var_list"][g],
+            cont["Links"], cont["Gene_names"][g], cont["Gene_lengths"][g], cont["refGene_loci"][g][4],
+            cont["refGene_loci"][g][5])
+    rng = np.random.default_rng(seed)
+    names = sorted(n for n in loc.alleles if loc.alleles[n])
+    truth = [names[i] for i in rng.choice(len(names), 2, replace=False)]
+    sam = synth.simulate_sam(loc, truth, n_pairs=n_pairs, rng=rng, err_rate=err_rate, paired=paired)
+    return args, sam, truth
+
+
+def assert_tables_equal_oracle(run_tables, ref, ol, hla):
+    """run_tables(tb) -> (Gene_cmpt items, Gene_counts items) of the product; ref = hgt_oracle.type_locus result."""
+    for tb, key in ((0, "gene"), (1, "exon"), (2, "primary")):
+        if tb > 0 and not hla:
+            continue
+        cmpt, counts = run_tables(tb)
+        assert cmpt == ref["tables"][key].cmpt_items(ol), "Gene_cmpt of table %s differs" % key
+        assert counts == ref["tables"][key].count_items(ol), "Gene_counts of table %s differs" % key

@@ -106,3 +106,27 @@ def test_em_c_restatement_bit_exact(name):
     for call in g["em_calls"]:
         res, _ = em_oracle.single_abundance(call["cmpt"], call["remove_low"], call["lengths"])
         assert res == [[a, p] for a, p in call["result"]]
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_em_driver_reproduces_reference_reports(name):
+    """oracle/hgt_oracle.py::locus_abundance (the two-level EM driver, core:1679-1789) on the oracle's own tables must
+    reproduce the abundance lines the unmodified reference wrote (the report body of every captured run)."""
+    from hisatgenotype_b200 import report
+    g = load_golden(name)
+    p = g["params"]
+    n_loci = len(p["loci"])
+    reports = [g["reports"][k] for k in sorted(g["reports"], key=lambda s: int(s.split("test-")[1].split(".")[0]))]
+    for t_i, ref_text in enumerate(reports):
+        body = [report.aligner_line("hisat2", "graph")]
+        for cap in g["loci"][t_i * n_loci:(t_i + 1) * n_loci]:
+            loc, _ = build_oracle_locus(g, cap["gene"])
+            res = O.type_locus(loc, cap["sam"], simulation=p["simulation"], num_editdist=p["num_editdist"],
+                               error_correction=p["error_correction"], allow_discordant=p["discordant"])
+            prob = O.locus_abundance(loc, res, p["remove_low"])
+            block, _ = report.locus_block(res["num_reads"], res["num_pairs"], res["tables"]["gene"].count_items(loc), prob,
+                                          p["simulation"], cap["test_Gene_names"], p["output_allele_counts"],
+                                          p["best_alleles"])
+            body.append(block)
+        marker = "\n\t\thisat2 graph\n"
+        assert "".join(body) == ref_text[ref_text.index(marker):]
