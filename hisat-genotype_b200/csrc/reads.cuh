@@ -1,0 +1,290 @@
+// Kernels around walk_dev.cuh: line index of the text arena, record parse, pileup straight from the CIGAR text, run
+// heads / mate de-dup, the walk (common case + ambiguity pass), the pair stage (count pass, scans, fill pass), plus the
+// host emulation of the same sequence (hgt_host_walk, no GPU).  Included by typing.cu.
+//
+// Everything here is byte / integer work bound by HBM and L2 bandwidth: thread per line for the serial
+// state machines (a line is ~350 B, a warp's 32 lines ~11 KB: L1-resident while the warp scans them), warp per line
+// where lanes can share a record (pileup), 16-byte loads for the newline scan.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+#include "walk_dev.cuh"
+
+namespace hgtk {
+using namespace hgtd;
+
+constexpr int LINE_THREADS = 256;
+constexpr int CHUNK_BYTES = LINE_THREADS * 64;  // bytes of text per CTA of the newline kernels
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 16, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+// '\n' bytes of a 32-bit word, exact (no borrow artefacts): 0x80 in every byte that equals 0x0A
+__device__ __forceinline__ uint32_t nl_mask(uint32_t w) {
+    const uint32_t x = w ^ 0x0A0A0A0Au;
+    const uint32_t t = (x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    return ~(t | x | 0x7F7F7F7Fu);
+}
+
+// exclusive prefix sum of `v` over the CTA (blockDim.x = 256); *total receives the CTA sum
+__device__ __forceinline__ int block_exclusive_scan(int v, int *total) {
+    __shared__ int s_warp[LINE_THREADS / 32];
+    __shared__ int s_total;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < LINE_THREADS / 32 ? s_warp[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < LINE_THREADS / 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += y;
+        }
+        if (lane < LINE_THREADS / 32) s_warp[lane] = w;
+        if (lane == LINE_THREADS / 32 - 1) s_total = w;
+    }
+    __syncthreads();
+    const int base = warp ? s_warp[warp - 1] : 0;
+    *total = s_total;
+    __syncthreads();
+    return base + x - v;
+}
+
+// pass 1 of the line index: newlines per 16 KB chunk (text is 16-byte aligned and padded with '\n' to a multiple of 16)
+__global__ void __launch_bounds__(LINE_THREADS) count_newlines_kernel(const char *__restrict__ text, int64_t n_bytes,
+                                                                     int64_t *__restrict__ chunk_count) {
+    const int64_t base = (int64_t)blockIdx.x * CHUNK_BYTES + (int64_t)threadIdx.x * 64;
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int64_t o = base + k * 16;
+        if (o < n_bytes) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(text + o);
+            c += __popc(nl_mask(v.x)) + __popc(nl_mask(v.y)) + __popc(nl_mask(v.z)) + __popc(nl_mask(v.w));
+        }
+    }
+    int total;
+    block_exclusive_scan(c, &total);
+    if (threadIdx.x == 0) chunk_count[blockIdx.x] = total;
+}
+
+// pass 2: line_off[k + 1] = offset of the byte after the k-th newline (chunk_base = exclusive scan of the chunk counts)
+__global__ void __launch_bounds__(LINE_THREADS) index_lines_kernel(const char *__restrict__ text, int64_t n_bytes,
+                                                                  const int64_t *__restrict__ chunk_base,
+                                                                  int64_t *__restrict__ line_off) {
+    const int64_t base = (int64_t)blockIdx.x * CHUNK_BYTES + (int64_t)threadIdx.x * 64;
+    uint32_t m[16];
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int64_t o = base + k * 16;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (o < n_bytes) v = *reinterpret_cast<const uint4 *>(text + o);
+        m[4 * k] = nl_mask(v.x); m[4 * k + 1] = nl_mask(v.y); m[4 * k + 2] = nl_mask(v.z); m[4 * k + 3] = nl_mask(v.w);
+        if (o >= n_bytes) m[4 * k] = m[4 * k + 1] = m[4 * k + 2] = m[4 * k + 3] = 0;
+        c += __popc(m[4 * k]) + __popc(m[4 * k + 1]) + __popc(m[4 * k + 2]) + __popc(m[4 * k + 3]);
+    }
+    int total;
+    int64_t at = chunk_base[blockIdx.x] + block_exclusive_scan(c, &total);
+    if (blockIdx.x == 0 && threadIdx.x == 0) line_off[0] = 0;
+#pragma unroll
+    for (int w = 0; w < 16; w++) {
+        uint32_t x = m[w];
+        while (x) {
+            const int bit = __ffs((int)x) - 1;  // 7, 15, 23 or 31
+            x &= x - 1;
+            line_off[++at] = base + w * 4 + (bit >> 3) + 1;
+        }
+    }
+}
+
+// ---- exclusive scan of int64 arrays: out[0..n] (n + 1 entries, out[n] = total); in place allowed ----------------------------
+__global__ void __launch_bounds__(SCAN_THREADS) scan_partials_kernel(const int64_t *__restrict__ in, int64_t n,
+                                                                    int64_t *__restrict__ partial) {
+    __shared__ int64_t s[SCAN_THREADS / 32];
+    const int64_t t0 = (int64_t)blockIdx.x * SCAN_TILE;
+    int64_t v = 0;
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        const int64_t i = t0 + (int64_t)k * SCAN_THREADS + threadIdx.x;
+        if (i < n) v += in[i];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t t = 0;
+        for (int w = 0; w < SCAN_THREADS / 32; w++) t += s[w];
+        partial[blockIdx.x] = t;
+    }
+}
+// one CTA: exclusive scan of the partials in place, total to partial[n_part]
+__global__ void __launch_bounds__(1024) scan_single_kernel(int64_t *__restrict__ partial, int64_t n_part) {
+    __shared__ int64_t s_warp[32];
+    __shared__ int64_t s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int64_t b = 0; b < n_part; b += 1024) {
+        const int64_t i = b + threadIdx.x;
+        const int64_t v = i < n_part ? partial[i] : 0;
+        int64_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int64_t w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int64_t y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const int64_t base = s_carry + (warp ? s_warp[warp - 1] : 0);
+        if (i < n_part) partial[i] = base + x - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = base + x;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partial[n_part] = s_carry;
+}
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply_kernel(const int64_t *in, int64_t n,
+                                                                 const int64_t *__restrict__ partial, int64_t n_part,
+                                                                 int64_t *out) {  // in == out allowed
+    __shared__ int64_t s_warp[SCAN_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t t0 = (int64_t)blockIdx.x * SCAN_TILE + (int64_t)threadIdx.x * SCAN_ITEMS;  // thread owns 16 adjacent items
+    int64_t v[SCAN_ITEMS];
+    int64_t sum = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        v[k] = t0 + k < n ? in[t0 + k] : 0;
+        sum += v[k];
+    }
+    int64_t x = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int64_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    int64_t base = partial[blockIdx.x];
+    for (int w = 0; w < warp; w++) base += s_warp[w];
+    int64_t run = base + x - sum;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        if (t0 + k < n) out[t0 + k] = run;
+        run += v[k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = partial[n_part];
+}
+
+// ---- thread per line ---------------------------------------------------------------------------------------------------------
+__global__ void unit_lines_kernel(ReadsView R) {  // first line of every unit: lower_bound(line_off, unit_off[u])
+    const int u = blockIdx.x * blockDim.x + threadIdx.x;
+    if (u > R.n_units) return;
+    const int64_t key = R.unit_off[u];
+    int64_t lo = 0, hi = R.n_lines;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (R.line_off[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    R.unit_line0[u] = lo;
+}
+__global__ void __launch_bounds__(256) parse_kernel(ReadsView R, WalkParams P) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < R.n_lines; i += (int64_t)gridDim.x * blockDim.x)
+        parse_line(R, P, i);
+}
+__global__ void __launch_bounds__(256) head_kernel(ReadsView R) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < R.n_lines; i += (int64_t)gridDim.x * blockDim.x)
+        mark_head(R, i);
+}
+__global__ void __launch_bounds__(256) candidate_kernel(ReadsView R) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < R.n_lines; i += (int64_t)gridDim.x * blockDim.x)
+        mark_candidate(R, i);
+}
+__global__ void __launch_bounds__(128) walk_kernel(ReadsView R, WalkParams P) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < R.n_lines; i += (int64_t)gridDim.x * blockDim.x)
+        walk_record<false>(R, P, i, -1);
+}
+__global__ void __launch_bounds__(128) walk_slow_kernel(ReadsView R, WalkParams P, int n_slow) {
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_slow; k += gridDim.x * blockDim.x)
+        walk_record<true>(R, P, R.slow_list[k], k);
+}
+__global__ void __launch_bounds__(128) pair_count_kernel(ReadsView R) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < R.n_lines; i += (int64_t)gridDim.x * blockDim.x)
+        pair_jobs<false>(R, i);
+}
+__global__ void __launch_bounds__(128) pair_fill_kernel(ReadsView R) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < R.n_lines; i += (int64_t)gridDim.x * blockDim.x)
+        pair_jobs<true>(R, i);
+}
+
+// per-locus totals of the pair stage from the scanned arrays: out[l][6] = pairs, haplotypes, rows, small jobs, big jobs,
+// first line of the locus
+__global__ void locus_totals_kernel(ReadsView R, int n_loci, const int32_t *__restrict__ locus_unit0, int64_t *__restrict__ out) {
+    const int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l >= n_loci) return;
+    const int64_t a = R.unit_line0[locus_unit0[l]], b = R.unit_line0[locus_unit0[l + 1]];
+    out[l * 6 + 0] = R.s_pairs[b] - R.s_pairs[a];
+    out[l * 6 + 1] = R.s_haps[b] - R.s_haps[a];
+    out[l * 6 + 2] = R.s_rows[b] - R.s_rows[a];
+    out[l * 6 + 3] = R.s_small[b] - R.s_small[a];
+    out[l * 6 + 4] = R.s_big[b] - R.s_big[a];
+    out[l * 6 + 5] = a;
+}
+
+// ---- pileup (common:1100-1121) straight from the CIGAR text: warp per line, lanes over the bases of each M / D op ------------
+__global__ void __launch_bounds__(256) pileup_text_kernel(ReadsView R, uint32_t *__restrict__ counts_all) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < R.n_lines; r += nwarps) {
+        if (!(R.st[r] & ST_PU)) continue;
+        const RecFields f = R.rec[r];
+        const char *line = R.text + R.line_off[r];
+        const char *cig = line + f.cig_off, *seq = line + f.seq_off;
+        const int u = R.unit[r];
+        const int L = R.loci[R.unit_locus[u]].L;
+        uint32_t *counts = counts_all + (size_t)R.unit_pos0[u] * 6;
+        int gpos = f.pos, rpos = 0, len = 0;
+        for (int k = 0; k < f.cig_len; k++) {
+            const char c = cig[k];  // same address in every lane: one broadcast load
+            if (c >= '0' && c <= '9') {
+                len = len * 10 + (c - '0');
+                continue;
+            }
+            if (c == 'M' || c == 'D') {
+                for (int j = lane; j < len; j += 32) {
+                    const int g = gpos + j;
+                    if (g < L) {
+                        int code = 5;
+                        if (c == 'M') {
+                            const char ch = rpos + j < f.seq_len ? seq[rpos + j] : 'N';
+                            code = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 4;
+                        }
+                        atomicAdd(&counts[(size_t)g * 6 + code], 1u);
+                    }
+                }
+            }
+            if (c == 'M' || c == 'D' || c == 'N') gpos += len;
+            if (c == 'M' || c == 'I' || c == 'S') rpos += len;
+            len = 0;
+        }
+    }
+}
+
+}  // namespace hgtk

@@ -32,6 +32,8 @@
 #include "common.cuh"
 #include "em_internal.h"
 #include "walk.hpp"
+#include "walk_dev.cuh"
+#include "reads.cuh"
 
 using namespace hgt;
 
@@ -53,6 +55,13 @@ struct hgt_locus {
     int32_t *d_lb = nullptr;  // [2][L + 2] lower-bound tables by position (variants, deletion right ends)
     uint64_t *d_st = nullptr, *d_mask = nullptr;
     double *d_allele_len = nullptr;
+    // tables of the record walk (walk_dev.cuh): one blob, viewed through host pointers (emulation, tests) and device pointers
+    std::vector<unsigned char> wt_blob;
+    std::vector<size_t> wt_off;
+    uint32_t wt_hash_mask = 0;
+    int wt_n_alt[2] = {0, 0};
+    unsigned char *d_wt = nullptr;
+    hgtd::LocusWalk wt_host, wt_dev;
 };
 
 struct LocusDev {
@@ -161,9 +170,120 @@ extern "C" void hgt_locus_free(hgt_locus *l) {
     if (l->ctx) {
         cudaSetDevice(l->ctx->device);
         cudaFree(l->d_var_pos); cudaFree(l->d_delr_right); cudaFree(l->d_delr_row); cudaFree(l->d_gn_rank); cudaFree(l->d_lb);
-        cudaFree(l->d_st); cudaFree(l->d_mask); cudaFree(l->d_allele_len);
+        cudaFree(l->d_st); cudaFree(l->d_mask); cudaFree(l->d_allele_len); cudaFree(l->d_wt);
     }
     delete l;
+}
+
+// ---- tables of the record walk as one blob ----------------------------------------------------------------------------------
+namespace {
+struct Blob {
+    std::vector<unsigned char> data;
+    std::vector<size_t> off;
+    template <class T>
+    void add(const std::vector<T> &v) {
+        const size_t o = (data.size() + 15) & ~(size_t)15;
+        data.resize(o + std::max<size_t>(v.size() * sizeof(T), 16), 0);
+        if (!v.empty()) memcpy(data.data() + o, v.data(), v.size() * sizeof(T));
+        off.push_back(o);
+    }
+};
+struct AltFlat {
+    std::vector<int32_t> anchor, key_off{0}, tok_off{0}, tok_row, tok_num, alt_off{0}, alt_left, alt_right, altrow_off{0}, altrow;
+    std::vector<char> key_pool;
+    void build(const std::vector<AltEntry> &tab) {
+        for (const AltEntry &e : tab) {
+            anchor.push_back(e.anchor);
+            key_pool.insert(key_pool.end(), e.key.begin(), e.key.end());
+            key_off.push_back((int32_t)key_pool.size());
+            for (size_t t = 0; t < e.toks.size(); t++) {
+                tok_row.push_back(e.tok_rows[t]);
+                tok_num.push_back(atoi(e.toks[t].c_str()));
+            }
+            tok_off.push_back((int32_t)tok_row.size());
+            for (const AltHap &a : e.alts) {
+                alt_left.push_back(a.left);
+                alt_right.push_back(a.right);
+                altrow.insert(altrow.end(), a.rows.begin(), a.rows.end());
+                altrow_off.push_back((int32_t)altrow.size());
+            }
+            alt_off.push_back((int32_t)alt_left.size());
+        }
+    }
+};
+}  // namespace
+
+static void build_walk_tables(hgt_locus *l) {
+    const LocusHost &h = l->host;
+    const int V = l->V;
+    std::vector<int32_t> vpos(V), vlen(V), id_off{0};
+    std::vector<uint8_t> vtype(V), vflags(V);
+    std::vector<char> vbase(V), id_pool;
+    for (int i = 0; i < V; i++) {
+        vpos[i] = h.vars[i].pos; vlen[i] = h.vars[i].len; vtype[i] = h.vars[i].type; vbase[i] = h.vars[i].base;
+        vflags[i] = (uint8_t)((h.vars[i].in_links ? 1 : 0) | (h.vars[i].is_hv ? 2 : 0));
+        id_pool.insert(id_pool.end(), h.vars[i].id.begin(), h.vars[i].id.end());
+        id_off.push_back((int32_t)id_pool.size());
+    }
+    uint32_t cap = 16;
+    while (cap < 2u * (uint32_t)std::max(V, 1)) cap <<= 1;
+    std::vector<int32_t> id_hash(cap, -1);
+    for (int i = 0; i < V; i++) {  // a later duplicate id replaces the earlier one, like row_of[id] = i
+        const std::string &id = h.vars[i].id;
+        uint32_t slot = (uint32_t)(hgtd::fnv1a(id.data(), (int)id.size()) >> 17) & (cap - 1);
+        while (id_hash[slot] >= 0 && h.vars[id_hash[slot]].id != id) slot = (slot + 1) & (cap - 1);
+        id_hash[slot] = i;
+    }
+    AltFlat fl, fr;
+    fl.build(h.alts_left);
+    fr.build(h.alts_right);
+    std::vector<int32_t> ex, pex;
+    for (auto &e : h.exons) { ex.push_back(e.first); ex.push_back(e.second); }
+    for (auto &e : h.primary_exons) { pex.push_back(e.first); pex.push_back(e.second); }
+    std::vector<char> ref(h.ref.begin(), h.ref.end());
+    Blob b;
+    b.add(ref);                                                              // 0
+    b.add(vpos); b.add(vlen); b.add(vtype); b.add(vbase); b.add(vflags);     // 1..5
+    b.add(id_off); b.add(id_pool); b.add(id_hash);                           // 6..8
+    for (const AltFlat *f : {&fl, &fr}) {                                    // 9..20, 21..32
+        b.add(f->anchor); b.add(f == &fl ? h.altl_below : h.altr_below); b.add(f->key_off); b.add(f->key_pool);
+        b.add(f->tok_off); b.add(f->tok_row); b.add(f->tok_num); b.add(f->alt_off); b.add(f->alt_left); b.add(f->alt_right);
+        b.add(f->altrow_off); b.add(f->altrow);
+    }
+    b.add(ex); b.add(pex);                                                   // 33, 34
+    l->wt_blob.swap(b.data);
+    l->wt_off.swap(b.off);
+    l->wt_hash_mask = cap - 1;
+    l->wt_n_alt[0] = (int)fl.anchor.size();
+    l->wt_n_alt[1] = (int)fr.anchor.size();
+}
+
+// view of the blob through `base` (host copy or device copy)
+static hgtd::LocusWalk walk_view(const hgt_locus *l, const unsigned char *base) {
+    hgtd::LocusWalk w;
+    auto at = [&](int k) { return base + l->wt_off[k]; };
+    w.ref = reinterpret_cast<const char *>(at(0));
+    w.L = l->L;
+    w.is_hla = l->is_hla ? 1 : 0;
+    w.v.V = l->V;
+    w.v.pos = reinterpret_cast<const int32_t *>(at(1)); w.v.len = reinterpret_cast<const int32_t *>(at(2));
+    w.v.type = at(3); w.v.base = reinterpret_cast<const char *>(at(4)); w.v.flags = at(5);
+    w.v.id_off = reinterpret_cast<const int32_t *>(at(6)); w.v.id_pool = reinterpret_cast<const char *>(at(7));
+    w.v.id_hash = reinterpret_cast<const int32_t *>(at(8)); w.v.id_hash_mask = l->wt_hash_mask;
+    for (int side = 0; side < 2; side++) {
+        hgtd::AltTab &t = side ? w.ar : w.al;
+        const int k = 9 + 12 * side;
+        t.n = l->wt_n_alt[side];
+        t.anchor = reinterpret_cast<const int32_t *>(at(k)); t.below = reinterpret_cast<const int32_t *>(at(k + 1));
+        t.key_off = reinterpret_cast<const int32_t *>(at(k + 2)); t.key_pool = reinterpret_cast<const char *>(at(k + 3));
+        t.tok_off = reinterpret_cast<const int32_t *>(at(k + 4)); t.tok_row = reinterpret_cast<const int32_t *>(at(k + 5));
+        t.tok_num = reinterpret_cast<const int32_t *>(at(k + 6)); t.alt_off = reinterpret_cast<const int32_t *>(at(k + 7));
+        t.alt_left = reinterpret_cast<const int32_t *>(at(k + 8)); t.alt_right = reinterpret_cast<const int32_t *>(at(k + 9));
+        t.altrow_off = reinterpret_cast<const int32_t *>(at(k + 10)); t.altrow = reinterpret_cast<const int32_t *>(at(k + 11));
+    }
+    w.n_exons = (int)l->host.exons.size(); w.n_pexons = (int)l->host.primary_exons.size();
+    w.exons = reinterpret_cast<const int32_t *>(at(33)); w.pexons = reinterpret_cast<const int32_t *>(at(34));
+    return w;
 }
 
 extern "C" int hgt_locus_create(hgt_ctx *ctx, const hgt_locus_desc *d, hgt_locus **out) {
@@ -244,6 +364,8 @@ extern "C" int hgt_locus_create(hgt_ctx *ctx, const hgt_locus_desc *d, hgt_locus
     l->allele_len.assign(l->A, 1.0);
     if (d->allele_len) l->allele_len.assign(d->allele_len, d->allele_len + l->A);
     if (!ctx) {
+        build_walk_tables(l);
+        l->wt_host = walk_view(l, l->wt_blob.data());
         *out = l;
         return HGT_OK;
     }
@@ -313,6 +435,11 @@ extern "C" int hgt_locus_create(hgt_ctx *ctx, const hgt_locus_desc *d, hgt_locus
         }
         LTRY(cudaGetLastError());
     }
+    build_walk_tables(l);
+    LTRY(cudaMalloc(&l->d_wt, l->wt_blob.size()));
+    LTRY(cudaMemcpyAsync(l->d_wt, l->wt_blob.data(), l->wt_blob.size(), cudaMemcpyHostToDevice, st));
+    l->wt_host = walk_view(l, l->wt_blob.data());
+    if (e == cudaSuccess) l->wt_dev = walk_view(l, l->d_wt);
     LTRY(cudaStreamSynchronize(st));
 #undef LTRY
     if (e != cudaSuccess) {
@@ -324,293 +451,11 @@ extern "C" int hgt_locus_create(hgt_ctx *ctx, const hgt_locus_desc *d, hgt_locus
 }
 
 // ================================================================================================================
-// Host pipeline: alignment text -> per-pair haplotype jobs
-// ================================================================================================================
-struct TableJobs {
-    std::vector<int64_t> job_off{0};  // per pair: range of haplotypes
-    std::vector<int32_t> hap_left, hap_right;
-    std::vector<int64_t> row_off{0};
-    std::vector<int32_t> rows;
-    void add_hap(const LocusHost &L, const Haplotype &h, std::vector<int32_t> &tmp) {
-        hap_left.push_back(h.left);
-        hap_right.push_back(h.right);
-        tmp.clear();
-        for (int32_t id : h.ids)
-            if (id >= 0 && L.vars[id].in_links) tmp.push_back(id);
-        std::sort(tmp.begin(), tmp.end());
-        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-        rows.insert(rows.end(), tmp.begin(), tmp.end());
-        row_off.push_back((int64_t)rows.size());
-    }
-    void end_job() { job_off.push_back((int64_t)hap_left.size()); }
-};
-
-struct HostOut {
-    int64_t num_reads = 0, num_pairs = 0;
-    TableJobs tb[3];
-};
-
-struct Intake {
-    std::vector<Record> recs;
-};
-
-static int intake(const char *sam, size_t n, const hgt_params &pr, Intake *in) {
-    const char *p = sam, *end = sam + n;
-    while (p < end) {
-        const char *q = (const char *)memchr(p, '\n', end - p);
-        if (!q) q = end;
-        const char *a = p;
-        while (a < q && is_ws(*a)) a++;
-        if (a < q && *a != '@') {
-            Record r;
-            parse_record(a, q, pr.simulation != 0, pr.base_locus, &r);
-            if (!r.ok) {
-                hgt_set_error("malformed alignment record (fewer than 11 columns or bad integer): %.60s", a);
-                return HGT_ERR_PARSE;
-            }
-            in->recs.push_back(r);
-        }
-        p = q + 1;
-    }
-    return HGT_OK;
-}
-
-// Read id of the record that starts at `line` (first whitespace-separated token; cut at '|' in simulation mode,
-// core:808-809); empty for blank and header lines.
-static std::string_view line_read_id(const char *line, const char *end, bool simulation) {
-    const char *a = line;
-    while (a < end && *a != '\n' && is_ws(*a)) a++;
-    if (a >= end || *a == '\n' || *a == '@') return std::string_view();
-    const char *q = a;
-    while (q < end && !is_ws(*q)) q++;
-    size_t n = (size_t)(q - a);
-    if (simulation) {
-        const void *bar = memchr(a, '|', n);
-        if (bar) n = (size_t)((const char *)bar - a);
-    }
-    return std::string_view(a, n);
-}
-
-// Cut [sam, sam+n) into pieces of about `target` bytes at line starts where the read id changes.
-static void split_text(const char *sam, size_t n, size_t target, bool simulation,
-                       std::vector<std::pair<const char *, size_t>> *out) {
-    const char *p = sam, *end = sam + n;
-    if (target < 256) target = 256;
-    while (p < end) {
-        if ((size_t)(end - p) <= target + target / 2) {
-            out->push_back({p, (size_t)(end - p)});
-            return;
-        }
-        const char *q = (const char *)memchr(p + target, '\n', (size_t)(end - (p + target)));
-        if (!q) {
-            out->push_back({p, (size_t)(end - p)});
-            return;
-        }
-        q++;  // first line of the next piece; move on while it continues the previous line's read
-        while (q < end) {
-            const char *prev = q - 1;  // the '\n' that ends the previous line
-            const char *ps = prev;
-            while (ps > p && ps[-1] != '\n') ps--;
-            const std::string_view a = line_read_id(ps, end, simulation), b2 = line_read_id(q, end, simulation);
-            if (a.empty() || b2.empty() || a != b2) break;
-            const char *nx = (const char *)memchr(q, '\n', (size_t)(end - q));
-            if (!nx) {
-                q = end;
-                break;
-            }
-            q = nx + 1;
-        }
-        out->push_back({p, (size_t)(q - p)});
-        p = q;
-    }
-}
-
-static int op_code(char c) {
-    switch (c) {
-        case 'M': return 0;
-        case 'I': return 1;
-        case 'D': return 2;
-        case 'S': return 3;
-        case 'N': return 4;
-        default: return -1;
-    }
-}
-
-static int host_walk(const hgt_locus *loc, const Intake &in, const hgt_params &pr, const PileupView &pu, HostOut *out) {
-    const LocusHost &L = loc->host;
-    std::unordered_set<std::string_view> seen[3];
-    std::vector<NovelVar> novel;
-    std::vector<Haplotype> left_hts, right_hts, all_hts, exon_tmp;
-    std::vector<int32_t> tmp_rows;
-    std::string seq;
-    std::vector<CigarOp> cig;
-    std::vector<ZsItem> zs;
-    WalkResult w;
-    WalkError err;
-    Ambig amb;
-    AmbigScratch amb_scratch;
-    std::vector<Cmp> c2;
-    std::string_view prev_id;
-    bool have_prev = false;
-    auto get_var = [&](int32_t id) {
-        VarLite v;
-        if (id >= 0) {
-            v.type = L.vars[id].type; v.pos = L.vars[id].pos; v.len = L.vars[id].len;
-        } else {
-            const NovelVar &nv = novel[novel_index(id)];
-            v.type = nv.type; v.pos = nv.pos; v.len = nv.len;
-        }
-        return v;
-    };
-    auto add_unique_ht = [](std::vector<Haplotype> &set, Haplotype &&h) {
-        for (const Haplotype &x : set)
-            if (x == h) return;
-        set.push_back(std::move(h));
-    };
-    auto flush = [&]() {
-        all_hts.clear();
-        for (Haplotype &h : left_hts) add_unique_ht(all_hts, std::move(h));
-        for (Haplotype &h : right_hts) add_unique_ht(all_hts, std::move(h));
-        for (const Haplotype &h : all_hts) {
-            if (loc->is_hla) {
-                exon_tmp.clear();
-                exon_haplotypes(h, L.primary_exons, get_var, &exon_tmp);
-                for (const Haplotype &e : exon_tmp) out->tb[2].add_hap(L, e, tmp_rows);
-                exon_tmp.clear();
-                exon_haplotypes(h, L.exons, get_var, &exon_tmp);
-                for (const Haplotype &e : exon_tmp) out->tb[1].add_hap(L, e, tmp_rows);
-            }
-            out->tb[0].add_hap(L, h, tmp_rows);
-        }
-        for (int t = 0; t < 3; t++) out->tb[t].end_job();
-        out->num_pairs++;
-        left_hts.clear();
-        right_hts.clear();
-    };
-    for (const Record &r : in.recs) {
-        if (r.pos < 0) continue;
-        if (r.flag & 0x4) continue;
-        if (!r.has_NM || !r.has_NH) {
-            hgt_set_error("alignment of read %.*s lacks the NM or NH tag", r.qname_len, r.qname);
-            return HGT_ERR_PARSE;
-        }
-        if (r.NM > pr.num_editdist) continue;
-        if (r.NH > 1) continue;
-        if (!pr.allow_discordant && !(r.flag & 0x2)) continue;
-        const bool is_left = (r.flag & 0x40) != 0;
-        const int kind = is_left ? 0 : ((r.flag & 0x80) ? 1 : 2);
-        if (kind == 2 && !pr.allow_discordant) {
-            hgt_set_error("read %.*s is neither first nor second mate and --discordant is off", r.qname_len, r.qname);
-            return HGT_ERR_PARSE;
-        }
-        const std::string_view id(r.qname, r.qname_len);
-        if (!seen[kind].insert(id).second) continue;
-        if (!walk_record(L, r, pu, pr.error_correction != 0, seq, cig, zs, &w, &err)) {
-            hgt_set_error("%s", err.msg.c_str());
-            return err.code;
-        }
-        if (w.right_pos > (int32_t)L.ref.size()) continue;
-        if (w.ncorr > std::max(1, pr.num_editdist)) continue;
-        if (w.misaligned) continue;
-        // novel variants (core:1126-1164): only indels keep an identity; it is (type, pos, len)
-        for (Cmp &e : w.cmp) {
-            if ((e.type == C_INSERTION || e.type == C_DELETION) && e.var == VAR_UNKNOWN) {
-                const NovelVar nv{(uint8_t)(e.type == C_INSERTION ? T_INSERTION : T_DELETION), e.pos, e.len};
-                size_t k = 0;
-                for (; k < novel.size(); k++)
-                    if (novel[k] == nv) break;
-                if (k == novel.size()) novel.push_back(nv);
-                e.var = VAR_NOVEL_BASE - (int32_t)k;
-            }
-        }
-        out->num_reads++;
-        if (!have_prev || id != prev_id) {
-            if (have_prev) flush();
-            left_hts.clear();
-            right_hts.clear();
-        }
-        // cmp_list2 (core:1351-1368)
-        c2.clear();
-        for (const Cmp &e : w.cmp) {
-            if (e.type == C_MATCH || (e.type == C_MISMATCH && e.var < 0)) {
-                const int32_t ln = e.type == C_MATCH ? e.len : 1;
-                if (!c2.empty() && c2.back().type == C_MATCH) c2.back().len += ln;
-                else c2.push_back({C_MATCH, e.pos, ln, -1});
-            } else {
-                c2.push_back(e);
-            }
-        }
-        if (c2.empty()) {
-            hgt_set_error("read %.*s has an empty alignment", r.qname_len, r.qname);
-            return HGT_ERR_PARSE;
-        }
-        if (!identify_ambiguous_diffs(L, c2, &amb, &err, &amb_scratch)) {
-            hgt_set_error("%s (read %.*s)", err.msg.c_str(), r.qname_len, r.qname);
-            return err.code;
-        }
-        std::vector<Haplotype> &dst = is_left ? left_hts : right_hts;
-        for (const AltSide &a : amb.left) {
-            for (const AltSide &b : amb.right) {
-                Haplotype h;
-                h.left = a.pos;
-                h.right = b.pos;
-                h.ids = a.ids;
-                for (int32_t i = amb.cmp_left; i <= amb.cmp_right; i++)
-                    if (c2[i].type != C_MATCH) h.ids.push_back(c2[i].var);
-                h.ids.insert(h.ids.end(), b.ids.begin(), b.ids.end());
-                add_unique_ht(dst, std::move(h));
-            }
-        }
-        prev_id = id;
-        have_prev = true;
-    }
-    if (have_prev) flush();
-    return HGT_OK;
-}
-
-// ================================================================================================================
 // Kernels
 // ================================================================================================================
 namespace {
 
 constexpr int WARPS_PER_CTA = 8;
-
-// ---- pileup (common:1100-1121): warp per record, lanes over the bases of each CIGAR op -------------------
-__global__ void pileup_kernel(const int32_t *__restrict__ pos, const int64_t *__restrict__ cig_off,
-                              const uint32_t *__restrict__ cig, const int64_t *__restrict__ seq_off,
-                              const char *__restrict__ seq, const int32_t *__restrict__ rec_unit, int64_t n_rec,
-                              const int64_t *__restrict__ unit_pos0, const int32_t *__restrict__ unit_L,
-                              uint32_t *__restrict__ counts_all) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = warp0; r < n_rec; r += nwarps) {
-        int gpos = pos[r];
-        int64_t rpos = seq_off[r];
-        const int u = rec_unit[r];
-        const int L = unit_L[u];
-        uint32_t *counts = counts_all + (size_t)unit_pos0[u] * 6;
-        for (int64_t c = cig_off[r]; c < cig_off[r + 1]; c++) {
-            const uint32_t x = cig[c];
-            const int len = (int)(x >> 4), op = (int)(x & 15u);
-            if (op == 0 || op == 2) {
-                for (int j = lane; j < len; j += 32) {
-                    const int g = gpos + j;
-                    if (g < L) {
-                        int code = 5;
-                        if (op == 0) {
-                            const char ch = seq[rpos + j];
-                            code = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 4;
-                        }
-                        atomicAdd(&counts[(size_t)g * 6 + code], 1u);
-                    }
-                }
-            }
-            if (op == 0 || op == 2 || op == 4) gpos += len;
-            if (op == 0 || op == 1 || op == 3) rpos += len;
-        }
-    }
-}
 
 __device__ __forceinline__ int lower_bound_dev(const int32_t *a, int n, int key) {
     int lo = 0, hi = n;
@@ -1153,36 +998,39 @@ static int wpl_of(int wp) {
 // ================================================================================================================
 // Batch of (sample, locus) units
 // ================================================================================================================
-// A unit is one (sample, locus).  Its alignment text is cut into tasks at read-id boundaries (the input is name
-// sorted, core:458-468, so mates, duplicate records of a read and therefore pairs never straddle a cut); host threads
-// take tasks, not units, so one deep unit (the oversized locus) uses every core and shallow units balance.
-struct TaskHost {
-    int unit = 0;
-    const char *sam = nullptr;
-    size_t n_bytes = 0;
-    Intake in;
-    HostOut ho;
-    int rc = HGT_OK;
-    std::string err;
-    int64_t pair0 = 0;  // pairs of the unit before this task
-    // pileup packing (records that pass the weaker filters of common:1084-1098)
-    std::vector<uint32_t> pu_rec;   // indices into in.recs
-    std::vector<uint32_t> pu_cig;   // len << 4 | op
-    std::vector<uint32_t> pu_ncig;  // ops per record
-    int64_t pu_seq = 0;             // bases
-    int64_t pu_rec0 = 0, pu_cig0 = 0, pu_seq0 = 0;  // offsets inside the batch arena
-};
-
+// A unit is one (sample, locus).  Its alignment text goes to the device as it is (one arena per batch, units of one
+// locus adjacent); everything from the line index to the ranked alleles happens there.
 struct UnitHost {
     int locus = 0;
     const char *sam = nullptr;
     size_t n_bytes = 0;
     int local = 0;  // index inside its locus batch
-    size_t task0 = 0, task1 = 0;
+    int arena = 0;  // index in arena order (loci-major, add order inside a locus)
     int64_t num_reads = 0, num_pairs = 0;
-    const uint8_t *nt_mask = nullptr, *del_flag = nullptr;  // [L] views into the batch's page-locked pileup result
     std::vector<uint32_t> counts;  // kept only when requested (single-unit API / tests)
+    std::vector<uint8_t> nt_mask;
     int64_t pos0 = 0;              // first position of the unit in the batch-wide pileup arrays
+};
+
+// Device state of the record stage (reads.cuh / walk_dev.cuh): text arena, line index, per-line records, haplotypes.
+struct ReadsDev {
+    int64_t text_bytes = 0, n_chunks = 0, n_lines = 0, POS = 0;
+    int32_t n_slow = 0, max_job_haps = 0;
+    std::vector<int> unit_of_arena;
+    std::vector<int32_t> locus_unit0;  // [n_loci + 1] first arena index of every locus
+    std::vector<int64_t> unit_off;     // [nu + 1] byte offsets in the arena (arena order)
+    DevBuf d_text, d_chunk, d_line_off, d_unit, d_rec, d_st, d_hdr, d_hids, d_slow, d_slow_list, d_units, d_loci, d_small,
+        d_scan, d_partial, d_jobs_desc, d_cnt, d_mf;
+    PinBuf h_units, h_small, h_stage, h_loci, h_jobs_desc;
+    size_t o_uoff = 0, o_uline0 = 0, o_upos0 = 0, o_ulocus = 0, o_ulocal = 0, o_lu0 = 0, units_bytes = 0;
+    size_t s_reads = 0, s_pairs = 0, s_totals = 0, small_bytes = 0;  // offsets inside the small result block
+    void release() {
+        DevBuf *all[] = {&d_text, &d_chunk, &d_line_off, &d_unit, &d_rec, &d_st, &d_hdr, &d_hids, &d_slow, &d_slow_list,
+                         &d_units, &d_loci, &d_small, &d_scan, &d_partial, &d_jobs_desc, &d_cnt, &d_mf};
+        for (DevBuf *x : all) x->release();
+        PinBuf *pins[] = {&h_units, &h_small, &h_stage, &h_loci, &h_jobs_desc};
+        for (PinBuf *x : pins) x->release();
+    }
 };
 
 struct LocusBatch {
@@ -1250,8 +1098,8 @@ struct hgt_batch {
     hgt_params params;
     std::vector<hgt_locus *> loci;
     std::vector<UnitHost> units;
-    std::vector<TaskHost> tasks;
     std::vector<LocusBatch> lb;
+    ReadsDev rd;
     bool keep_counts = false;
     bool skip_em = false;
     int (*pileup_hook)(void *arg, void *dev_counts, size_t n_u32, void *stream) = nullptr;
@@ -1259,7 +1107,6 @@ struct hgt_batch {
     bool prepared = false, executed = false, finished = false;
     StageTimer timer;
     int remove_low = 1;
-    PinBuf h_pileup, h_pumask;  // pileup input arena / nt_set + deletion-artefact flags of every unit
     PinBuf h_em_args[2];   // kernel-argument staging of the two EM levels
     DevBuf d_em_args[2];
     ~hgt_batch() {
@@ -1268,19 +1115,13 @@ struct hgt_batch {
             cudaDeviceSynchronize();  // pooled blocks go back to the allocator: nothing may still be using them
         }
         for (LocusBatch &b : lb) b.release();
-        h_pileup.release();
-        h_pumask.release();
+        rd.release();
         for (int i = 0; i < 2; i++) {
             h_em_args[i].release();
             d_em_args[i].release();
         }
     }
 };
-
-static void set_task_error(TaskHost &t, int rc) {
-    t.rc = rc;
-    t.err = hgt_last_error();
-}
 
 // Parallel-for over units on host threads (intake and walk are independent per unit).
 template <class F>
@@ -1309,14 +1150,11 @@ static int batch_threads(const hgt_params &p) {
     return hc ? (int)hc : 1;
 }
 
-// ---- stage 1: intake + pileup (GPU) + walk (host threads) + job upload -----------------------------------------
+// ---- stage 1: text to the device, line count ----------------------------------------------------------------------------------
 static inline size_t a16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // Stage (a) runs as two kernels (compat_kernel -> hapbits in HBM -> class_kernel).  HGT_STAGE_A=fused selects the
-// one-kernel form (pair_class_kernel, no hapbits buffer) for A/B measurements: on B200 it is SLOWER (5.15 vs 3.03 ms per
-// 128-sample step, 3.39 vs 1.66 ms on the 1 M-read locus) - 116-127 registers per thread halve the resident warps and
-// a warp walks its job's haplotypes one after the other instead of one warp per haplotype; both kernels are issue- and
-// latency-bound, so the 2 x H x wp x 8 bytes of HBM traffic the fusion saves do not pay for that.
+// one-kernel form (pair_class_kernel, no hapbits buffer) for A/B measurements.
 static bool stage_a_split() {
     static const bool split = [] {
         const char *e = getenv("HGT_STAGE_A");
@@ -1325,11 +1163,35 @@ static bool stage_a_split() {
     return split;
 }
 
+// exclusive scan of n int64 values into out[0..n] (out[n] = total); in == out allowed
+static int dev_scan(hgt_ctx *ctx, cudaStream_t st, const int64_t *in, int64_t n, int64_t *out, DevBuf *partial) {
+    if (n <= 0) {
+        HGT_CUDA(cudaMemsetAsync(out, 0, 8, st));
+        return HGT_OK;
+    }
+    const int64_t n_part = (n + hgtk::SCAN_TILE - 1) / hgtk::SCAN_TILE;
+    HGT_CHECK(partial->alloc((size_t)(n_part + 1) * 8));
+    hgtk::scan_partials_kernel<<<(unsigned)n_part, hgtk::SCAN_THREADS, 0, st>>>(in, n, partial->as<int64_t>());
+    hgtk::scan_single_kernel<<<1, 1024, 0, st>>>(partial->as<int64_t>(), n_part);
+    hgtk::scan_apply_kernel<<<(unsigned)n_part, hgtk::SCAN_THREADS, 0, st>>>(in, n, partial->as<int64_t>(), n_part, out);
+    ctx->launches += 3;
+    HGT_CUDA(cudaGetLastError());
+    return HGT_OK;
+}
+
+static bool is_pinned_host(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost;
+}
 
 static int batch_prepare(hgt_batch *b) {
     hgt_ctx *ctx = b->ctx;
     cudaStream_t st = ctx->stream;
-    const int nthreads = batch_threads(b->params);
+    ReadsDev &rd = b->rd;
     const size_t nu = b->units.size();
     b->lb.assign(b->loci.size(), LocusBatch());
     for (size_t l = 0; l < b->loci.size(); l++) b->lb[l].loc = b->loci[l];
@@ -1338,312 +1200,394 @@ static int batch_prepare(hgt_batch *b) {
         b->units[u].local = (int)lb.units.size();
         lb.units.push_back((int)u);
     }
-    // tasks: every unit's text cut at read-id boundaries
-    b->tasks.clear();
-    {
-        const size_t target = b->params.chunk_bytes > 0 ? (size_t)b->params.chunk_bytes : (size_t)128 << 10;
-        std::vector<std::pair<const char *, size_t>> pieces;
-        for (size_t u = 0; u < nu; u++) {
-            UnitHost &U = b->units[u];
-            pieces.clear();
-            split_text(U.sam, U.n_bytes, target, b->params.simulation != 0, &pieces);
-            U.task0 = b->tasks.size();
-            for (auto &pc : pieces) {
-                b->tasks.emplace_back();
-                TaskHost &T = b->tasks.back();
-                T.unit = (int)u;
-                T.sam = pc.first;
-                T.n_bytes = pc.second;
-            }
-            U.task1 = b->tasks.size();
+    // arena order: the units of one locus are adjacent, so every per-locus quantity of the pair stage is a difference of
+    // two entries of a scan over lines
+    rd.unit_of_arena.clear();
+    rd.locus_unit0.assign(b->loci.size() + 1, 0);
+    for (size_t l = 0; l < b->loci.size(); l++) {
+        rd.locus_unit0[l] = (int32_t)rd.unit_of_arena.size();
+        for (int u : b->lb[l].units) {
+            b->units[u].arena = (int)rd.unit_of_arena.size();
+            rd.unit_of_arena.push_back(u);
         }
     }
-    const size_t nt = b->tasks.size();
-    // heaviest tasks first (dynamic scheduling then ends with the small ones)
-    std::vector<uint32_t> sched(nt);
-    std::iota(sched.begin(), sched.end(), 0u);
-    std::stable_sort(sched.begin(), sched.end(), [&](uint32_t x, uint32_t y) { return b->tasks[x].n_bytes > b->tasks[y].n_bytes; });
-    auto first_error = [&]() {
-        for (TaskHost &T : b->tasks)
-            if (T.rc != HGT_OK) {
-                hgt_set_error("%s", T.err.c_str());
-                return T.rc;
-            }
-        return (int)HGT_OK;
-    };
-    // ---- intake + pileup packing, pass 1 (parallel over tasks): parse the text, pick the pileup records, parse CIGARs
+    rd.locus_unit0[b->loci.size()] = (int32_t)nu;
+    rd.unit_off.assign(nu + 1, 0);
+    rd.POS = 0;
+    for (size_t a = 0; a < nu; a++) {
+        UnitHost &U = b->units[rd.unit_of_arena[a]];
+        rd.unit_off[a + 1] = rd.unit_off[a] + (int64_t)a16(U.n_bytes + 1);  // at least one '\n' closes every unit
+        U.pos0 = rd.POS;
+        rd.POS += b->loci[U.locus]->L;
+    }
+    rd.text_bytes = rd.unit_off[nu];
+    rd.n_lines = 0;
+    if (nu == 0) {
+        b->prepared = true;
+        return HGT_OK;
+    }
     {
         HostTimer ht(ctx, 0);
-        parallel_units(nthreads, nt, [&](size_t k) {
-            TaskHost &T = b->tasks[sched[k]];
-            int rc = intake(T.sam, T.n_bytes, b->params, &T.in);
-            if (rc != HGT_OK) {
-                set_task_error(T, rc);
-                return;
+        HGT_CHECK(rd.d_text.alloc((size_t)rd.text_bytes));
+        char *dt = rd.d_text.as<char>();
+        bool all_pinned = true;
+        for (const UnitHost &U : b->units) all_pinned &= U.n_bytes == 0 || is_pinned_host(U.sam);
+        ctx->h2d_bytes += rd.text_bytes;
+        if (all_pinned) {  // page-locked input: the DMA engine reads the caller's buffers directly
+            HGT_CUDA(cudaMemsetAsync(dt, '\n', (size_t)rd.text_bytes, st));
+            for (size_t a = 0; a < nu; a++) {
+                const UnitHost &U = b->units[rd.unit_of_arena[a]];
+                if (U.n_bytes) HGT_CUDA(cudaMemcpyAsync(dt + rd.unit_off[a], U.sam, U.n_bytes, cudaMemcpyHostToDevice, st));
             }
-            std::vector<CigarOp> cig;
-            for (size_t i = 0; i < T.in.recs.size(); i++) {
-                const Record &r = T.in.recs[i];
-                if (r.flag & 0x4) continue;
-                if (r.pos < 0) continue;
-                if (!b->params.allow_discordant && !(r.flag & 0x2)) continue;
-                if (!parse_cigar(r.cigar, r.cigar_len, &cig)) {
-                    hgt_set_error("malformed CIGAR in read %.*s", r.qname_len, r.qname);
-                    set_task_error(T, HGT_ERR_PARSE);
-                    return;
-                }
-                uint32_t n = 0;
-                for (const CigarOp &c : cig) {
-                    const int oc = op_code(c.op);
-                    if (oc < 0) continue;  // the reference's pileup ignores ops outside MIDNS (common:1107-1121)
-                    T.pu_cig.push_back(((uint32_t)c.len << 4) | (uint32_t)oc);
-                    n++;
-                }
-                T.pu_rec.push_back((uint32_t)i);
-                T.pu_ncig.push_back(n);
-                T.pu_seq += r.seq_len;
-            }
-        });
+        } else {  // pageable input: host threads assemble the arena image in page-locked memory, one copy
+            HGT_CHECK(rd.h_stage.alloc((size_t)rd.text_bytes));
+            char *hs = rd.h_stage.as<char>();
+            parallel_units(batch_threads(b->params), nu, [&](size_t a) {
+                const UnitHost &U = b->units[rd.unit_of_arena[a]];
+                if (U.n_bytes) memcpy(hs + rd.unit_off[a], U.sam, U.n_bytes);
+                memset(hs + rd.unit_off[a] + U.n_bytes, '\n', (size_t)(rd.unit_off[a + 1] - rd.unit_off[a]) - U.n_bytes);
+            });
+            HGT_CUDA(cudaMemcpyAsync(dt, hs, (size_t)rd.text_bytes, cudaMemcpyHostToDevice, st));
+        }
     }
-    HGT_CHECK(first_error());
-    // ---- pileup: one arena for all units of all loci, one copy, one launch -----------------------------------------
-    int64_t R = 0, CG = 0, SQ = 0, POS = 0;
-    for (TaskHost &T : b->tasks) {
-        T.pu_rec0 = R; T.pu_cig0 = CG; T.pu_seq0 = SQ;
-        R += (int64_t)T.pu_rec.size(); CG += (int64_t)T.pu_cig.size(); SQ += T.pu_seq;
-    }
-    for (UnitHost &U : b->units) {
-        U.pos0 = POS;
-        POS += b->loci[U.locus]->L;
-    }
-    const size_t o_pos = 0, o_ru = a16(o_pos + (size_t)R * 4), o_co = a16(o_ru + (size_t)R * 4),
-                 o_so = a16(o_co + (size_t)(R + 1) * 8), o_up = a16(o_so + (size_t)(R + 1) * 8),
-                 o_ul = a16(o_up + nu * 8), o_cg = a16(o_ul + nu * 4), o_sq = a16(o_cg + (size_t)CG * 4),
-                 pu_bytes = a16(o_sq + (size_t)SQ);
-    DevBuf d_pu, d_cnt, d_mf;
-    std::vector<uint32_t> counts_all;
     {
         HostTimer ht(ctx, 1);
-        HGT_CHECK(b->h_pileup.alloc(pu_bytes));
-        HGT_CHECK(b->h_pumask.alloc((size_t)POS * 2));
-        unsigned char *hp = static_cast<unsigned char *>(b->h_pileup.p);
-        int32_t *h_pos = reinterpret_cast<int32_t *>(hp + o_pos), *h_ru = reinterpret_cast<int32_t *>(hp + o_ru);
-        int64_t *h_co = reinterpret_cast<int64_t *>(hp + o_co), *h_so = reinterpret_cast<int64_t *>(hp + o_so);
-        int64_t *h_up = reinterpret_cast<int64_t *>(hp + o_up);
-        int32_t *h_ul = reinterpret_cast<int32_t *>(hp + o_ul);
-        uint32_t *h_cg = reinterpret_cast<uint32_t *>(hp + o_cg);
-        char *h_sq = reinterpret_cast<char *>(hp + o_sq);
-        h_co[R] = CG;
-        h_so[R] = SQ;
-        for (size_t u = 0; u < nu; u++) {
-            h_up[u] = b->units[u].pos0;
-            h_ul[u] = b->loci[b->units[u].locus]->L;
+        // unit tables and the loci's walk tables
+        rd.o_uoff = 0;
+        rd.o_uline0 = a16(rd.o_uoff + (nu + 1) * 8);
+        rd.o_upos0 = a16(rd.o_uline0 + (nu + 1) * 8);
+        rd.o_ulocus = a16(rd.o_upos0 + (nu + 1) * 8);
+        rd.o_ulocal = a16(rd.o_ulocus + nu * 4);
+        rd.o_lu0 = a16(rd.o_ulocal + nu * 4);
+        rd.units_bytes = a16(rd.o_lu0 + (b->loci.size() + 1) * 4);
+        HGT_CHECK(rd.h_units.alloc(rd.units_bytes));
+        HGT_CHECK(rd.d_units.alloc(rd.units_bytes));
+        unsigned char *hu = static_cast<unsigned char *>(rd.h_units.p);
+        memset(hu, 0, rd.units_bytes);
+        memcpy(hu + rd.o_uoff, rd.unit_off.data(), (nu + 1) * 8);
+        for (size_t a = 0; a < nu; a++) {
+            const UnitHost &U = b->units[rd.unit_of_arena[a]];
+            reinterpret_cast<int64_t *>(hu + rd.o_upos0)[a] = U.pos0;
+            reinterpret_cast<int32_t *>(hu + rd.o_ulocus)[a] = U.locus;
+            reinterpret_cast<int32_t *>(hu + rd.o_ulocal)[a] = U.local;
         }
-        parallel_units(nthreads, nt, [&](size_t k) {
-            TaskHost &T = b->tasks[sched[k]];
-            int64_t c = T.pu_cig0, q = T.pu_seq0;
-            if (!T.pu_cig.empty()) memcpy(h_cg + c, T.pu_cig.data(), T.pu_cig.size() * 4);
-            for (size_t i = 0; i < T.pu_rec.size(); i++) {
-                const Record &r = T.in.recs[T.pu_rec[i]];
-                const int64_t at = T.pu_rec0 + (int64_t)i;
-                h_pos[at] = r.pos;
-                h_ru[at] = (int32_t)T.unit;
-                h_co[at] = c;
-                h_so[at] = q;
-                memcpy(h_sq + q, r.seq, (size_t)r.seq_len);
-                c += T.pu_ncig[i];
-                q += r.seq_len;
-            }
-            std::vector<uint32_t>().swap(T.pu_cig);
-            std::vector<uint32_t>().swap(T.pu_rec);
-            std::vector<uint32_t>().swap(T.pu_ncig);
-        });
-    }
-    {
-        HostTimer ht(ctx, 2);
-        HGT_CHECK(d_pu.alloc(pu_bytes));
-        HGT_CHECK(d_cnt.alloc((size_t)POS * 24));
-        HGT_CHECK(d_mf.alloc((size_t)POS * 2));
-        unsigned char *dp = static_cast<unsigned char *>(d_pu.p);
-        ctx->h2d_bytes += (int64_t)pu_bytes;
-        HGT_CUDA(cudaMemcpyAsync(d_pu.p, b->h_pileup.p, pu_bytes, cudaMemcpyHostToDevice, st));
-        HGT_CUDA(cudaMemsetAsync(d_cnt.p, 0, (size_t)POS * 24, st));
-        b->timer.begin(ctx, st, 0);
-        if (R > 0) {
-            const int ctas = (int)std::min<int64_t>((R + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 8);
-            pileup_kernel<<<ctas, WARPS_PER_CTA * 32, 0, st>>>(
-                reinterpret_cast<int32_t *>(dp + o_pos), reinterpret_cast<int64_t *>(dp + o_co),
-                reinterpret_cast<uint32_t *>(dp + o_cg), reinterpret_cast<int64_t *>(dp + o_so),
-                reinterpret_cast<char *>(dp + o_sq), reinterpret_cast<int32_t *>(dp + o_ru), R,
-                reinterpret_cast<int64_t *>(dp + o_up), reinterpret_cast<int32_t *>(dp + o_ul), d_cnt.as<uint32_t>());
-            ctx->launches++;
-        }
-        if (b->pileup_hook) {  // read-sharded locus: the caller sums the raw counts over ranks
-            HGT_CUDA(cudaStreamSynchronize(st));
-            const int rc = b->pileup_hook(b->pileup_hook_arg, d_cnt.p, (size_t)POS * 6, st);
-            if (rc != 0) {
-                hgt_set_error("pileup hook failed with status %d", rc);
-                return HGT_ERR_ARG;
-            }
-        }
-        if (POS > 0) {
-            pileup_flags_kernel<<<(unsigned)((POS + 255) / 256), 256, 0, st>>>(d_cnt.as<uint32_t>(), POS, d_mf.as<uint8_t>(),
-                                                                               d_mf.as<uint8_t>() + POS);
-            ctx->launches++;
-        }
-        b->timer.end((R > 0) + (POS > 0));
+        memcpy(hu + rd.o_lu0, rd.locus_unit0.data(), (b->loci.size() + 1) * 4);
+        ctx->h2d_bytes += (int64_t)rd.units_bytes;
+        HGT_CUDA(cudaMemcpyAsync(rd.d_units.p, hu, rd.units_bytes, cudaMemcpyHostToDevice, st));
+        const size_t lw = b->loci.size() * sizeof(hgtd::LocusWalk);
+        HGT_CHECK(rd.h_loci.alloc(lw));
+        HGT_CHECK(rd.d_loci.alloc(lw));
+        for (size_t l = 0; l < b->loci.size(); l++) rd.h_loci.as<hgtd::LocusWalk>()[l] = b->loci[l]->wt_dev;
+        HGT_CUDA(cudaMemcpyAsync(rd.d_loci.p, rd.h_loci.p, lw, cudaMemcpyHostToDevice, st));
+        // line count: newlines per 16 KB chunk, scanned (the chunk bases feed the line index of execute)
+        rd.n_chunks = (rd.text_bytes + hgtk::CHUNK_BYTES - 1) / hgtk::CHUNK_BYTES;
+        HGT_CHECK(rd.d_chunk.alloc((size_t)(rd.n_chunks + 1) * 8));
+        hgtk::count_newlines_kernel<<<(unsigned)rd.n_chunks, hgtk::LINE_THREADS, 0, st>>>(rd.d_text.as<char>(), rd.text_bytes,
+                                                                                      rd.d_chunk.as<int64_t>());
+        ctx->launches++;
         HGT_CUDA(cudaGetLastError());
-        HGT_CUDA(d2h(b->h_pumask.p, d_mf.p, (size_t)POS * 2, st));
-        if (b->keep_counts) {
-            counts_all.resize((size_t)POS * 6);
-            HGT_CUDA(d2h(counts_all.data(), d_cnt.p, counts_all.size() * 4, st));
-        }
+        HGT_CHECK(dev_scan(ctx, st, rd.d_chunk.as<int64_t>(), rd.n_chunks, rd.d_chunk.as<int64_t>(), &rd.d_partial));
+        HGT_CHECK(rd.h_small.alloc(64));
+        HGT_CUDA(d2h(rd.h_small.p, rd.d_chunk.as<int64_t>() + rd.n_chunks, 8, st));
         HGT_CUDA(cudaStreamSynchronize(st));
-        b->timer.resolve();
-        d_pu.release(); d_cnt.release(); d_mf.release();
+        rd.n_lines = *rd.h_small.as<int64_t>();
     }
-    for (UnitHost &U : b->units) {
-        U.nt_mask = b->h_pumask.as<uint8_t>() + U.pos0;
-        U.del_flag = b->h_pumask.as<uint8_t>() + POS + U.pos0;
-        if (b->keep_counts) {
+    if (rd.n_lines > 0x7fffffff) {
+        hgt_set_error("more than 2^31 alignment lines in one batch: split the batch");
+        return HGT_ERR_UNSUPPORTED;
+    }
+    b->prepared = true;
+    return HGT_OK;
+}
+
+// ---- record stage of execute: line index -> parse -> pileup -> walk -> pair jobs -------------------------------------------------
+static const char *walk_error_text(int code, int *status) {
+    using namespace hgtd;
+    *status = HGT_ERR_PARSE;
+    switch (code) {
+        case E_RECORD: return "malformed alignment record (fewer than 11 columns or bad integer)";
+        case E_NO_NM_NH: return "alignment lacks the NM or NH tag";
+        case E_MATE_KIND: return "read is neither first nor second mate and --discordant is off";
+        case E_NO_MD: return "MD tag missing";
+        case E_CIGAR: return "malformed CIGAR";
+        case E_ZS_ITEM: return "malformed Zs item";
+        case E_ZS_OFFSET: return "malformed Zs offset";
+        case E_MD_SHORT: return "MD shorter than CIGAR";
+        case E_MD_PAST_READ: return "MD runs past the read";
+        case E_MD_BASE: return "MD reference base is not ACGT";
+        case E_ZS_NOT_S: return "Zs item is not a substitution";
+        case E_ZS_ID: return "Zs id is not a variant of this locus";
+        case E_ZS_NOT_I: return "Zs item is not an insertion";
+        case E_MD_CARET: return "MD lacks ^ for a deletion";
+        case E_CLIP_MIDDLE: return "soft clip in the middle of a CIGAR";
+        case E_CIGAR_OP: return "unsupported CIGAR operation";
+        case E_EMPTY: return "read has an empty alignment";
+        case E_ALT_INDEX: return "alt haplotype index out of range";
+        case E_ALT_TOKEN: return "alt haplotype token is not a variant";
+        case E_AMBIGUITY: *status = HGT_ERR_AMBIGUITY; return "ambiguous alternative haplotype sets (check_amb_uniqueness)";
+        case E_CAP_CMP: *status = HGT_ERR_UNSUPPORTED; return "more than 96 differences in one alignment";
+        case E_CAP_ENDS: *status = HGT_ERR_UNSUPPORTED; return "more than 16 alternative ends (or 16 variants in one) around a read";
+        case E_CAP_IDS: *status = HGT_ERR_UNSUPPORTED; return "more than 32 variants inside one read";
+        case E_LINE_LONG: *status = HGT_ERR_UNSUPPORTED; return "alignment line longer than 65535 bytes";
+        case E_NOVEL_RANGE: *status = HGT_ERR_UNSUPPORTED; return "novel indel outside the supported range (position < 2^19, length < 2^10)";
+        case E_PAIR_HTS: *status = HGT_ERR_UNSUPPORTED; return "a read pair expands to more than 255 haplotypes";
+        default: return "record stage failed";
+    }
+}
+
+// first token of a text line (the read name), for error messages
+static std::string line_name(const char *p, size_t n) {
+    size_t a = 0;
+    while (a < n && hgtd::is_ws(p[a])) a++;
+    size_t e = a;
+    while (e < n && !hgtd::is_ws(p[e])) e++;
+    return std::string(p + a, e - a);
+}
+
+static int report_walk_error(hgt_batch *b, unsigned long long err, cudaStream_t st) {
+    if (err == ~0ull) return HGT_OK;
+    const int64_t line = (int64_t)(err >> 8);
+    int status = HGT_ERR_PARSE;
+    const char *msg = walk_error_text((int)(err & 0xff), &status);
+    int64_t off[2] = {0, 0};
+    char buf[97];
+    memset(buf, 0, sizeof(buf));
+    if (cudaMemcpyAsync(off, b->rd.d_line_off.as<int64_t>() + line, 16, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+        cudaStreamSynchronize(st) == cudaSuccess) {
+        const size_t n = (size_t)std::min<int64_t>(96, off[1] - off[0]);
+        cudaMemcpyAsync(buf, b->rd.d_text.as<char>() + off[0], n, cudaMemcpyDeviceToHost, st);
+        cudaStreamSynchronize(st);
+    }
+    hgt_set_error("%s (read %s)", msg, line_name(buf, strlen(buf)).c_str());
+    return status;
+}
+
+static hgtd::ReadsView reads_view(hgt_batch *b) {
+    ReadsDev &rd = b->rd;
+    hgtd::ReadsView R;
+    memset(&R, 0, sizeof(R));
+    const size_t N = (size_t)rd.n_lines, nu = b->units.size();
+    R.text = rd.d_text.as<char>();
+    R.n_lines = rd.n_lines;
+    R.line_off = rd.d_line_off.as<int64_t>();
+    R.unit = rd.d_unit.as<int32_t>();
+    R.rec = rd.d_rec.as<hgtd::RecFields>();
+    R.st = rd.d_st.as<uint16_t>();
+    R.h_left = rd.d_hdr.as<int32_t>();
+    R.h_right = R.h_left + N;
+    R.h_n = R.h_right + N;
+    R.slow_slot = R.h_n + N;
+    R.h_ids = rd.d_hids.as<int32_t>();
+    R.slow = rd.d_slow.as<hgtd::SlowRec>();
+    R.slow_list = rd.d_slow_list.as<int32_t>();
+    unsigned char *sm = static_cast<unsigned char *>(rd.d_small.p);
+    R.err = reinterpret_cast<unsigned long long *>(sm);
+    R.n_slow = reinterpret_cast<int32_t *>(sm + 8);
+    R.max_job_haps = reinterpret_cast<int32_t *>(sm + 12);
+    R.unit_reads = reinterpret_cast<unsigned long long *>(sm + rd.s_reads);
+    R.unit_pairs = reinterpret_cast<unsigned long long *>(sm + rd.s_pairs);
+    unsigned char *du = static_cast<unsigned char *>(rd.d_units.p);
+    R.n_units = (int)nu;
+    R.unit_off = reinterpret_cast<int64_t *>(du + rd.o_uoff);
+    R.unit_line0 = reinterpret_cast<int64_t *>(du + rd.o_uline0);
+    R.unit_pos0 = reinterpret_cast<int64_t *>(du + rd.o_upos0);
+    R.unit_locus = reinterpret_cast<int32_t *>(du + rd.o_ulocus);
+    R.unit_local = reinterpret_cast<int32_t *>(du + rd.o_ulocal);
+    R.nt_mask = rd.d_mf.as<uint8_t>();
+    R.del_flag = rd.d_mf.as<uint8_t>() + rd.POS;
+    R.loci = rd.d_loci.as<hgtd::LocusWalk>();
+    int64_t *sc = rd.d_scan.as<int64_t>();
+    R.s_pairs = sc;
+    R.s_haps = sc + (N + 1);
+    R.s_rows = sc + 2 * (N + 1);
+    R.s_small = sc + 3 * (N + 1);
+    R.s_big = sc + 4 * (N + 1);
+    R.jobs = rd.d_jobs_desc.as<hgtd::LocusJobs>();
+    return R;
+}
+
+static int line_grid(hgt_ctx *ctx, int64_t n, int threads, int per_sm) {
+    return (int)std::max<int64_t>(1, std::min<int64_t>((n + threads - 1) / threads, (int64_t)ctx->sm_count * per_sm));
+}
+
+static int reads_execute(hgt_batch *b, cudaStream_t st) {
+    hgt_ctx *ctx = b->ctx;
+    ReadsDev &rd = b->rd;
+    const size_t nu = b->units.size(), nl = b->loci.size();
+    const int64_t N = rd.n_lines;
+    hgtd::WalkParams P;
+    P.num_editdist = b->params.num_editdist; P.error_correction = b->params.error_correction;
+    P.allow_discordant = b->params.allow_discordant; P.simulation = b->params.simulation; P.base_locus = b->params.base_locus;
+    // ---- buffers (from the context's pool: a second execute of the same batch re-uses all of them) --------------------------
+    HGT_CHECK(rd.d_line_off.alloc((size_t)(N + 1) * 8));
+    HGT_CHECK(rd.d_unit.alloc((size_t)std::max<int64_t>(N, 1) * 4));
+    HGT_CHECK(rd.d_rec.alloc((size_t)std::max<int64_t>(N, 1) * sizeof(hgtd::RecFields)));
+    HGT_CHECK(rd.d_st.alloc((size_t)std::max<int64_t>(N, 1) * 2));
+    HGT_CHECK(rd.d_hdr.alloc((size_t)std::max<int64_t>(N, 1) * 16));
+    HGT_CHECK(rd.d_hids.alloc((size_t)std::max<int64_t>(N, 1) * hgtd::MAXI * 4));
+    HGT_CHECK(rd.d_slow_list.alloc((size_t)std::max<int64_t>(N, 1) * 4));
+    HGT_CHECK(rd.d_scan.alloc((size_t)(N + 1) * 8 * 5));
+    HGT_CHECK(rd.d_cnt.alloc((size_t)std::max<int64_t>(rd.POS, 1) * 24));
+    HGT_CHECK(rd.d_mf.alloc((size_t)std::max<int64_t>(rd.POS, 1) * 2));
+    rd.s_reads = 16;
+    rd.s_pairs = rd.s_reads + nu * 8;
+    rd.s_totals = rd.s_pairs + nu * 8;
+    rd.small_bytes = rd.s_totals + nl * 6 * 8;
+    HGT_CHECK(rd.d_small.alloc(rd.small_bytes));
+    HGT_CHECK(rd.h_small.alloc(rd.small_bytes));
+    HGT_CHECK(rd.d_jobs_desc.alloc(nl * sizeof(hgtd::LocusJobs)));
+    HGT_CHECK(rd.h_jobs_desc.alloc(nl * sizeof(hgtd::LocusJobs)));
+    if (rd.d_slow.p == nullptr) HGT_CHECK(rd.d_slow.alloc(sizeof(hgtd::SlowRec)));
+    hgtd::ReadsView R = reads_view(b);
+    HGT_CUDA(cudaMemsetAsync(rd.d_small.p, 0, rd.small_bytes, st));
+    HGT_CUDA(cudaMemsetAsync(rd.d_small.p, 0xff, 8, st));
+    HGT_CUDA(cudaMemsetAsync(rd.d_cnt.p, 0, (size_t)std::max<int64_t>(rd.POS, 1) * 24, st));
+    // ---- line index, records, pileup --------------------------------------------------------------------------------------
+    b->timer.begin(ctx, st, 0);
+    int launches = 0;
+    ctx->launches += 5;
+    hgtk::index_lines_kernel<<<(unsigned)rd.n_chunks, hgtk::LINE_THREADS, 0, st>>>(rd.d_text.as<char>(), rd.text_bytes,
+                                                                               rd.d_chunk.as<int64_t>(), rd.d_line_off.as<int64_t>());
+    hgtk::unit_lines_kernel<<<(unsigned)((nu + 1 + 127) / 128), 128, 0, st>>>(R);
+    hgtk::parse_kernel<<<line_grid(ctx, N, 256, 8), 256, 0, st>>>(R, P);
+    hgtk::pileup_text_kernel<<<line_grid(ctx, N * 32, 256, 8), 256, 0, st>>>(R, rd.d_cnt.as<uint32_t>());
+    launches += 4;
+    HGT_CUDA(cudaGetLastError());
+    if (b->pileup_hook) {  // read-sharded locus: the caller sums the raw counts over ranks
+        HGT_CUDA(cudaStreamSynchronize(st));
+        const int rc = b->pileup_hook(b->pileup_hook_arg, rd.d_cnt.p, (size_t)rd.POS * 6, st);
+        if (rc != 0) {
+            hgt_set_error("pileup hook failed with status %d", rc);
+            return HGT_ERR_ARG;
+        }
+    }
+    if (rd.POS > 0) {
+        pileup_flags_kernel<<<(unsigned)((rd.POS + 255) / 256), 256, 0, st>>>(rd.d_cnt.as<uint32_t>(), rd.POS, rd.d_mf.as<uint8_t>(),
+                                                                             rd.d_mf.as<uint8_t>() + rd.POS);
+        launches++;
+    }
+    b->timer.end(launches);
+    if (b->keep_counts) {
+        for (UnitHost &U : b->units) {
             const size_t L = (size_t)b->loci[U.locus]->L;
-            U.counts.assign(counts_all.begin() + (size_t)U.pos0 * 6, counts_all.begin() + ((size_t)U.pos0 + L) * 6);
+            U.counts.resize(L * 6);
+            U.nt_mask.resize(L);
+            HGT_CUDA(d2h(U.counts.data(), rd.d_cnt.as<uint32_t>() + (size_t)U.pos0 * 6, L * 24, st));
+            HGT_CUDA(d2h(U.nt_mask.data(), rd.d_mf.as<uint8_t>() + U.pos0, L, st));
         }
     }
-    // ---- walk (parallel over tasks) ---------------------------------------------------------------------------------
+    // ---- runs, mate de-dup, the walk ------------------------------------------------------------------------------------------
+    b->timer.begin(ctx, st, 7);
+    hgtk::head_kernel<<<line_grid(ctx, N, 256, 8), 256, 0, st>>>(R);
+    hgtk::candidate_kernel<<<line_grid(ctx, N, 256, 8), 256, 0, st>>>(R);
+    hgtk::walk_kernel<<<line_grid(ctx, N, 128, 16), 128, 0, st>>>(R, P);
+    launches = 3;
+    ctx->launches += 3;
+    HGT_CUDA(cudaGetLastError());
+    HGT_CUDA(d2h(rd.h_small.p, rd.d_small.p, 16, st));
+    HGT_CUDA(cudaStreamSynchronize(st));  // number of records that need the ambiguity pass
     {
-        HostTimer ht(ctx, 3);
-        parallel_units(nthreads, nt, [&](size_t k) {
-            TaskHost &T = b->tasks[sched[k]];
-            const UnitHost &U = b->units[T.unit];
-            const hgt_locus *loc = b->loci[U.locus];
-            PileupView pu;
-            pu.nt_mask = U.nt_mask; pu.del_artefact = U.del_flag; pu.L = loc->L;
-            const int rc = host_walk(loc, T.in, b->params, pu, &T.ho);
-            if (rc != HGT_OK) set_task_error(T, rc);
-            std::vector<Record>().swap(T.in.recs);
-        });
+        const unsigned char *hs = static_cast<const unsigned char *>(rd.h_small.p);
+        HGT_CHECK(report_walk_error(b, *reinterpret_cast<const unsigned long long *>(hs), st));
+        rd.n_slow = *reinterpret_cast<const int32_t *>(hs + 8);
     }
-    HGT_CHECK(first_error());
-    for (UnitHost &U : b->units) {
-        U.num_reads = U.num_pairs = 0;
-        for (size_t t = U.task0; t < U.task1; t++) {
-            b->tasks[t].pair0 = U.num_pairs;
-            U.num_reads += b->tasks[t].ho.num_reads;
-            U.num_pairs += b->tasks[t].ho.num_pairs;
-        }
-        if (U.num_pairs > 0x7fffffff) {
-            hgt_set_error("a unit holds more than 2^31 read pairs");
+    if (rd.n_slow > 0) {
+        HGT_CHECK(rd.d_slow.alloc((size_t)rd.n_slow * sizeof(hgtd::SlowRec)));
+        R = reads_view(b);
+        hgtk::walk_slow_kernel<<<line_grid(ctx, rd.n_slow, 128, 16), 128, 0, st>>>(R, P, rd.n_slow);
+        launches++;
+        ctx->launches++;
+    }
+    hgtk::pair_count_kernel<<<line_grid(ctx, N, 128, 16), 128, 0, st>>>(R);
+    launches += 1 + 15 + 1 + 1;  // + five scans, locus totals, fill
+    ctx->launches += 3;         // (the scans count themselves)
+    HGT_CUDA(cudaGetLastError());
+    for (int k = 0; k < 5; k++) {
+        int64_t *a = rd.d_scan.as<int64_t>() + (size_t)k * (N + 1);
+        HGT_CHECK(dev_scan(ctx, st, a, N, a, &rd.d_partial));
+    }
+    hgtk::locus_totals_kernel<<<(unsigned)((nl + 63) / 64), 64, 0, st>>>(
+        R, (int)nl, reinterpret_cast<int32_t *>(static_cast<unsigned char *>(rd.d_units.p) + rd.o_lu0),
+        reinterpret_cast<int64_t *>(static_cast<unsigned char *>(rd.d_small.p) + rd.s_totals));
+    HGT_CUDA(cudaGetLastError());
+    HGT_CUDA(d2h(rd.h_small.p, rd.d_small.p, rd.small_bytes, st));
+    HGT_CUDA(cudaStreamSynchronize(st));  // sizes of the job arrays and class pools
+    const unsigned char *hs = static_cast<const unsigned char *>(rd.h_small.p);
+    HGT_CHECK(report_walk_error(b, *reinterpret_cast<const unsigned long long *>(hs), st));
+    rd.max_job_haps = *reinterpret_cast<const int32_t *>(hs + 12);
+    for (size_t a = 0; a < nu; a++) {
+        UnitHost &U = b->units[rd.unit_of_arena[a]];
+        U.num_reads = (int64_t) reinterpret_cast<const unsigned long long *>(hs + rd.s_reads)[a];
+        U.num_pairs = (int64_t) reinterpret_cast<const unsigned long long *>(hs + rd.s_pairs)[a];
+    }
+    // ---- job arrays per locus (device only), class pools, EM buffers ---------------------------------------------------------
+    hgtd::LocusJobs *hj = rd.h_jobs_desc.as<hgtd::LocusJobs>();
+    memset(hj, 0, nl * sizeof(hgtd::LocusJobs));
+    for (size_t l = 0; l < nl; l++) {
+        LocusBatch &lb = b->lb[l];
+        if (lb.units.empty()) continue;
+        const hgt_locus *loc = lb.loc;
+        const int n_tables = loc->is_hla ? 3 : 1;
+        const size_t n_units = lb.units.size();
+        const int64_t *tot = reinterpret_cast<const int64_t *>(hs + rd.s_totals) + l * 6;
+        const int64_t J = tot[0] * n_tables, H = tot[1], RW = tot[2];
+        if (J > 0x7fffffff || H > 0x7fffffff) {
+            hgt_set_error("more than 2^31 jobs or haplotypes in one locus batch: split the batch");
             return HGT_ERR_UNSUPPORTED;
         }
-    }
-    // ---- job arenas per locus: offsets (serial, tiny), then a parallel fill straight into page-locked memory --------
-    struct Fill { LocusBatch *lb; size_t i; const TaskHost *task; int64_t h0[3], r0[3], j0[3], s0[3], b0[3]; };
-    std::vector<Fill> fills;
-    {
-        HostTimer ht(ctx, 4);
-        for (LocusBatch &lb : b->lb) {
-            if (lb.units.empty()) continue;
-            const hgt_locus *loc = lb.loc;
-            const int n_tables = loc->is_hla ? 3 : 1;
-            const size_t n_units = lb.units.size();
-            lb.ut_base.assign(n_units * 4 + 1, 0);
-            int64_t H = 0, RW = 0, J = 0, NS = 0, NB = 0;
-            const size_t f0 = fills.size();
-            for (size_t i = 0; i < n_units; i++) {
-                const UnitHost &U = b->units[lb.units[i]];
-                for (int tb = 0; tb < 4; tb++) {
-                    const bool active = tb < n_tables || (tb == 3 && loc->is_hla);
-                    lb.ut_base[i * 4 + tb + 1] = lb.ut_base[i * 4 + tb] + (active ? U.num_pairs : 0);
-                }
-                for (size_t t = U.task0; t < U.task1; t++) {
-                    const TaskHost &TK = b->tasks[t];
-                    Fill f;
-                    f.lb = &lb; f.i = i; f.task = &TK;
-                    for (int tb = 0; tb < 3; tb++) {
-                        f.h0[tb] = H; f.r0[tb] = RW; f.j0[tb] = J; f.s0[tb] = NS; f.b0[tb] = NB;
-                        if (tb >= n_tables) continue;
-                        const TableJobs &T = TK.ho.tb[tb];
-                        int64_t small = 0;
-                        for (int64_t p = 0; p < TK.ho.num_pairs; p++) {
-                            const int64_t k = T.job_off[p + 1] - T.job_off[p];
-                            if (k > 255) {
-                                hgt_set_error("a read pair expands to %lld haplotypes (limit 255)", (long long)k);
-                                return HGT_ERR_UNSUPPORTED;
-                            }
-                            small += k <= 7;
-                            lb.max_job_haps = std::max(lb.max_job_haps, k);
-                        }
-                        H += (int64_t)T.hap_left.size();
-                        RW += (int64_t)T.rows.size();
-                        J += TK.ho.num_pairs;
-                        NS += small;
-                        NB += TK.ho.num_pairs - small;
-                    }
-                    fills.push_back(f);
-                }
-            }
-            if (J > 0x7fffffff || H > 0x7fffffff) {
-                hgt_set_error("more than 2^31 jobs or haplotypes in one locus batch: split the batch");
+        lb.n_jobs = J; lb.n_haps = H; lb.n_rows = RW; lb.n_small = tot[3]; lb.n_big = tot[4];
+        lb.max_job_haps = rd.max_job_haps;
+        lb.ut_base.assign(n_units * 4 + 1, 0);
+        for (size_t i = 0; i < n_units; i++) {
+            const UnitHost &U = b->units[lb.units[i]];
+            if (U.num_pairs > 0x7fffffff) {
+                hgt_set_error("a unit holds more than 2^31 read pairs");
                 return HGT_ERR_UNSUPPORTED;
             }
-            for (size_t k = f0; k < fills.size(); k++)
-                for (int tb = 0; tb < 3; tb++) fills[k].b0[tb] += NS;  // the > 7-haplotype jobs follow all small ones
-            lb.n_haps = H; lb.n_rows = RW; lb.n_jobs = J; lb.n_small = NS; lb.n_big = NB;
-            lb.n_rows_pool = lb.ut_base.back();
-            LocusBatch::JobArena &ja = lb.ja;
-            ja.o_job_off = 0;
-            ja.o_row_off = a16(ja.o_job_off + (size_t)(J + 1) * 8);
-            ja.o_ut_base = a16(ja.o_row_off + (size_t)(H + 1) * 8);
-            ja.o_job_ut = a16(ja.o_ut_base + (n_units * 4 + 1) * 8);
-            ja.o_job_pair = a16(ja.o_job_ut + (size_t)J * 4);
-            ja.o_job_list = a16(ja.o_job_pair + (size_t)J * 4);
-            ja.o_hl = a16(ja.o_job_list + (size_t)J * 4);
-            ja.o_hr = a16(ja.o_hl + (size_t)H * 4);
-            ja.o_ht = a16(ja.o_hr + (size_t)H * 4);
-            ja.o_rows = a16(ja.o_ht + (size_t)H * 4);
-            ja.bytes = a16(ja.o_rows + (size_t)RW * 4);
-            HGT_CHECK(lb.h_jobs.alloc(ja.bytes));
-            lb.hj<int64_t>(ja.o_job_off)[0] = 0;
-            lb.hj<int64_t>(ja.o_row_off)[0] = 0;
-            memcpy(lb.hj<int64_t>(ja.o_ut_base), lb.ut_base.data(), (n_units * 4 + 1) * 8);
-        }
-        parallel_units(nthreads, fills.size(), [&](size_t k) {
-            const Fill &f = fills[k];
-            LocusBatch &lb = *f.lb;
-            const LocusBatch::JobArena &ja = lb.ja;
-            const TaskHost &TK = *f.task;
-            const int n_tables = lb.loc->is_hla ? 3 : 1;
-            int64_t *job_off = lb.hj<int64_t>(ja.o_job_off), *row_off = lb.hj<int64_t>(ja.o_row_off);
-            int32_t *job_ut = lb.hj<int32_t>(ja.o_job_ut), *job_pair = lb.hj<int32_t>(ja.o_job_pair),
-                    *job_list = lb.hj<int32_t>(ja.o_job_list), *hl = lb.hj<int32_t>(ja.o_hl), *hr = lb.hj<int32_t>(ja.o_hr),
-                    *htb = lb.hj<int32_t>(ja.o_ht), *rows = lb.hj<int32_t>(ja.o_rows);
-            for (int tb = 0; tb < n_tables; tb++) {
-                const TableJobs &T = TK.ho.tb[tb];
-                const int64_t h0 = f.h0[tb], r0 = f.r0[tb], j0 = f.j0[tb];
-                const size_t nh = T.hap_left.size();
-                if (nh) {
-                    memcpy(hl + h0, T.hap_left.data(), nh * 4);
-                    memcpy(hr + h0, T.hap_right.data(), nh * 4);
-                }
-                for (size_t h = 0; h < nh; h++) {
-                    htb[h0 + h] = tb;
-                    row_off[h0 + h + 1] = r0 + T.row_off[h + 1];
-                }
-                if (!T.rows.empty()) memcpy(rows + r0, T.rows.data(), T.rows.size() * 4);
-                int64_t s = f.s0[tb], g = f.b0[tb];
-                for (int64_t p = 0; p < TK.ho.num_pairs; p++) {
-                    const int64_t job = j0 + p;
-                    job_ut[job] = (int32_t)(f.i * 4 + tb);
-                    job_pair[job] = (int32_t)(TK.pair0 + p);  // pair index inside the unit (first-seen order key)
-                    job_off[job + 1] = h0 + T.job_off[p + 1];
-                    if (T.job_off[p + 1] - T.job_off[p] <= 7) job_list[s++] = (int32_t)job;
-                    else job_list[g++] = (int32_t)job;
-                }
+            for (int tb = 0; tb < 4; tb++) {
+                const bool active = tb < n_tables || (tb == 3 && loc->is_hla);
+                lb.ut_base[i * 4 + tb + 1] = lb.ut_base[i * 4 + tb] + (active ? U.num_pairs : 0);
             }
-        });
+        }
+        lb.n_rows_pool = lb.ut_base.back();
+        LocusBatch::JobArena &ja = lb.ja;
+        ja.o_job_off = 0;
+        ja.o_row_off = a16(ja.o_job_off + (size_t)(J + 1) * 8);
+        ja.o_ut_base = a16(ja.o_row_off + (size_t)(H + 1) * 8);
+        ja.o_job_ut = a16(ja.o_ut_base + (n_units * 4 + 1) * 8);
+        ja.o_job_pair = a16(ja.o_job_ut + (size_t)J * 4);
+        ja.o_job_list = a16(ja.o_job_pair + (size_t)J * 4);
+        ja.o_hl = a16(ja.o_job_list + (size_t)J * 4);
+        ja.o_hr = a16(ja.o_hl + (size_t)H * 4);
+        ja.o_ht = a16(ja.o_hr + (size_t)H * 4);
+        ja.o_rows = a16(ja.o_ht + (size_t)H * 4);
+        ja.bytes = a16(ja.o_rows + (size_t)RW * 4);
+        HGT_CHECK(lb.d_jobs.alloc(ja.bytes));
+        HGT_CHECK(lb.h_jobs.alloc((n_units * 4 + 1) * 8));
+        memcpy(lb.h_jobs.p, lb.ut_base.data(), (n_units * 4 + 1) * 8);
+        ctx->h2d_bytes += (int64_t)((n_units * 4 + 1) * 8);
+        HGT_CUDA(cudaMemcpyAsync(lb.dj<int64_t>(ja.o_ut_base), lb.h_jobs.p, (n_units * 4 + 1) * 8, cudaMemcpyHostToDevice, st));
+        HGT_CUDA(cudaMemsetAsync(lb.dj<int64_t>(ja.o_job_off), 0, 8, st));
+        HGT_CUDA(cudaMemsetAsync(lb.dj<int64_t>(ja.o_row_off), 0, 8, st));
+        hgtd::LocusJobs &d = hj[l];
+        d.job_off = lb.dj<int64_t>(ja.o_job_off); d.row_off = lb.dj<int64_t>(ja.o_row_off);
+        d.job_ut = lb.dj<int32_t>(ja.o_job_ut); d.job_pair = lb.dj<int32_t>(ja.o_job_pair); d.job_list = lb.dj<int32_t>(ja.o_job_list);
+        d.hap_left = lb.dj<int32_t>(ja.o_hl); d.hap_right = lb.dj<int32_t>(ja.o_hr); d.hap_table = lb.dj<int32_t>(ja.o_ht);
+        d.rows = lb.dj<int32_t>(ja.o_rows);
+        d.n_small = lb.n_small;
+        d.n_tables = n_tables;
+        d.line0 = tot[5];
     }
-    // ---- device buffers (from the context's pool) and the uploads ---------------------------------------------------
+    HGT_CUDA(cudaMemcpyAsync(rd.d_jobs_desc.p, hj, nl * sizeof(hgtd::LocusJobs), cudaMemcpyHostToDevice, st));
+    hgtk::pair_fill_kernel<<<line_grid(ctx, N, 128, 16), 128, 0, st>>>(R);
+    b->timer.end(launches);
+    HGT_CUDA(cudaGetLastError());
+    return HGT_OK;
+}
+
+static int batch_alloc_tables(hgt_batch *b, cudaStream_t st) {
+    hgt_ctx *ctx = b->ctx;
+    const size_t nu = b->units.size();
     {
         HostTimer ht(ctx, 5);
         for (LocusBatch &lb : b->lb) {
@@ -1653,9 +1597,6 @@ static int batch_prepare(hgt_batch *b) {
             const size_t n_units = lb.units.size();
             lb.cap = 64;
             while ((int64_t)lb.cap < 2 * std::max<int64_t>(lb.n_rows_pool, 1)) lb.cap <<= 1;
-            HGT_CHECK(lb.d_jobs.alloc(lb.ja.bytes));
-            ctx->h2d_bytes += (int64_t)lb.ja.bytes;
-            HGT_CUDA(cudaMemcpyAsync(lb.d_jobs.p, lb.h_jobs.p, lb.ja.bytes, cudaMemcpyHostToDevice, st));
             if (stage_a_split()) HGT_CHECK(lb.d_hapbits.alloc((size_t)std::max<int64_t>(lb.n_haps, 1) * wp * 8));
             HGT_CHECK(lb.d_keys.alloc((size_t)lb.cap * 8));
             HGT_CHECK(lb.d_slot.alloc((size_t)lb.cap * 4));
@@ -1714,9 +1655,8 @@ static int batch_prepare(hgt_batch *b) {
             HGT_CHECK(b->h_em_args[i].alloc(hgt_em_args_bytes((int)nu)));
             HGT_CHECK(b->d_em_args[i].alloc(hgt_em_args_bytes((int)nu)));
         }
-        HGT_CUDA(cudaStreamSynchronize(st));
     }
-    b->prepared = true;
+    (void)st;
     return HGT_OK;
 }
 
@@ -1913,6 +1853,12 @@ static void em_problems(hgt_ctx *ctx, LocusBatch &lb, int table, const std::vect
 
 static int batch_execute(hgt_batch *b, cudaStream_t st) {
     hgt_ctx *ctx = b->ctx;
+    b->executed = false;
+    b->finished = false;
+    if (!b->units.empty()) {
+        HGT_CHECK(reads_execute(b, st));
+        HGT_CHECK(batch_alloc_tables(b, st));
+    }
     for (LocusBatch &lb : b->lb) {
         if (lb.units.empty()) continue;
         const hgt_locus *loc = lb.loc;
@@ -2471,7 +2417,7 @@ extern "C" int hgt_typing_pileup(const hgt_typing *t, uint32_t *counts, uint8_t 
     if (!t) return HGT_ERR_ARG;
     const UnitHost &U = t->batch->units[0];
     if (counts) memcpy(counts, U.counts.data(), U.counts.size() * 4);
-    if (nt_mask && U.nt_mask) memcpy(nt_mask, U.nt_mask, (size_t)t->batch->loci[U.locus]->L);
+    if (nt_mask && !U.nt_mask.empty()) memcpy(nt_mask, U.nt_mask.data(), U.nt_mask.size());
     return HGT_OK;
 }
 
@@ -2530,55 +2476,121 @@ extern "C" int hgt_typing_em(hgt_ctx *ctx, const hgt_typing *t, int32_t table, c
 }
 
 // ================================================================================================================
-// Host-only walk (tests of the host logic without a GPU)
+// Host emulation of the record stage (tests of the device logic without a GPU)
 // ================================================================================================================
+// hgt_host_walk runs the SAME __host__ __device__ functions the kernels call (walk_dev.cuh) in plain loops over host
+// memory, with a caller-supplied pileup.  It exists for tests/test_host_walk.py (no GPU in that environment); nothing
+// on the typing path calls it.
 struct hgt_walk {
-    HostOut ho;
+    int64_t num_reads = 0, num_pairs = 0;
+    struct Tab {
+        std::vector<int64_t> job_off{0}, row_off{0};
+        std::vector<int32_t> hap_left, hap_right, rows;
+    } tb[3];
 };
 
 extern "C" int hgt_host_walk(hgt_locus *loc, const char *sam, size_t n_bytes, const hgt_params *params,
                              const uint32_t *counts, const uint8_t *nt_mask, hgt_walk **out) {
-    if (!loc || !params || !out || !counts || !nt_mask) {
+    using namespace hgtd;
+    if (!loc || !params || !out || !counts || !nt_mask || (!sam && n_bytes)) {
         hgt_set_error("hgt_host_walk: null argument");
         return HGT_ERR_ARG;
     }
     *out = nullptr;
-    hgt_walk *w = new hgt_walk();
-    PileupView pu;
+    // arena: the text plus at least one closing newline, padded to 16 bytes
+    std::vector<char> text(a16(n_bytes + 1), '\n');
+    if (n_bytes) memcpy(text.data(), sam, n_bytes);
+    std::vector<int64_t> line_off{0};
+    for (size_t i = 0; i < text.size(); i++)
+        if (text[i] == '\n') line_off.push_back((int64_t)i + 1);
+    const int64_t N = (int64_t)line_off.size() - 1;
+    const size_t n1 = (size_t)std::max<int64_t>(N, 1);
     std::vector<uint8_t> flag(loc->L);
     for (int i = 0; i < loc->L; i++) {
         const uint32_t *c = counts + (size_t)i * 6;
         const uint64_t dels = c[5], nts = (uint64_t)c[0] + c[1] + c[2] + c[3] + c[4];
         flag[i] = dels * 6 < nts ? 1 : 0;
     }
-    pu.nt_mask = nt_mask; pu.del_artefact = flag.data(); pu.L = loc->L;
-    // the same task decomposition as the batch path: pieces cut at read-id boundaries, walked independently, then
-    // concatenated in order
-    std::vector<std::pair<const char *, size_t>> pieces;
-    split_text(sam, n_bytes, params->chunk_bytes > 0 ? (size_t)params->chunk_bytes : (size_t)128 << 10,
-               params->simulation != 0, &pieces);
-    for (auto &pc : pieces) {
-        Intake in;
-        HostOut part;
-        int rc = intake(pc.first, pc.second, *params, &in);
-        if (rc == HGT_OK) rc = host_walk(loc, in, *params, pu, &part);
-        if (rc != HGT_OK) {
-            delete w;
-            return rc;
+    std::vector<int32_t> unit(n1), hdr(n1 * 4), hids(n1 * MAXI), slow_list(n1);
+    std::vector<RecFields> rec(n1);
+    std::vector<uint16_t> stv(n1);
+    std::vector<int64_t> scan((size_t)(N + 1) * 5, 0);
+    int64_t unit_off[2] = {0, (int64_t)text.size()}, unit_line0[2] = {0, N}, unit_pos0[2] = {0, 0};
+    int32_t unit_locus[1] = {0}, unit_local[1] = {0}, n_slow = 0, max_job = 0;
+    unsigned long long err = ~0ull, unit_reads[1] = {0}, unit_pairs[1] = {0};
+    LocusJobs jobs;
+    memset(&jobs, 0, sizeof(jobs));
+    ReadsView R;
+    memset(&R, 0, sizeof(R));
+    R.text = text.data(); R.n_lines = N; R.line_off = line_off.data();
+    R.unit = unit.data(); R.rec = rec.data(); R.st = stv.data();
+    R.h_left = hdr.data(); R.h_right = R.h_left + n1; R.h_n = R.h_right + n1; R.slow_slot = R.h_n + n1;
+    R.h_ids = hids.data(); R.slow_list = slow_list.data(); R.n_slow = &n_slow;
+    R.n_units = 1; R.unit_off = unit_off; R.unit_line0 = unit_line0; R.unit_locus = unit_locus; R.unit_local = unit_local;
+    R.unit_pos0 = unit_pos0; R.nt_mask = nt_mask; R.del_flag = flag.data(); R.loci = &loc->wt_host;
+    R.err = &err; R.unit_reads = unit_reads; R.unit_pairs = unit_pairs;
+    R.s_pairs = scan.data(); R.s_haps = R.s_pairs + (N + 1); R.s_rows = R.s_haps + (N + 1); R.s_small = R.s_rows + (N + 1);
+    R.s_big = R.s_small + (N + 1);
+    R.max_job_haps = &max_job; R.jobs = &jobs;
+    WalkParams P;
+    P.num_editdist = params->num_editdist; P.error_correction = params->error_correction;
+    P.allow_discordant = params->allow_discordant; P.simulation = params->simulation; P.base_locus = params->base_locus;
+    auto fail = [&]() {
+        int status = HGT_ERR_PARSE;
+        const char *msg = walk_error_text((int)(err & 0xff), &status);
+        const int64_t line = (int64_t)(err >> 8);
+        hgt_set_error("%s (read %s)", msg,
+                      line_name(text.data() + line_off[line], (size_t)(line_off[line + 1] - line_off[line])).c_str());
+        return status;
+    };
+    for (int64_t i = 0; i < N; i++) parse_line(R, P, i);
+    for (int64_t i = 0; i < N; i++) mark_head(R, i);
+    for (int64_t i = 0; i < N; i++) mark_candidate(R, i);
+    for (int64_t i = 0; i < N; i++) walk_record<false>(R, P, i, -1);
+    if (err != ~0ull) return fail();
+    std::vector<SlowRec> slow((size_t)std::max(n_slow, 1));
+    R.slow = slow.data();
+    for (int k = 0; k < n_slow; k++) walk_record<true>(R, P, slow_list[k], k);
+    for (int64_t i = 0; i < N; i++) pair_jobs<false>(R, i);
+    if (err != ~0ull) return fail();
+    for (int k = 0; k < 5; k++) {
+        int64_t *a = scan.data() + (size_t)k * (N + 1), run = 0;
+        for (int64_t i = 0; i < N; i++) {
+            const int64_t v = a[i];
+            a[i] = run;
+            run += v;
         }
-        w->ho.num_reads += part.num_reads;
-        w->ho.num_pairs += part.num_pairs;
-        for (int t = 0; t < 3; t++) {
-            TableJobs &D = w->ho.tb[t];
-            const TableJobs &S = part.tb[t];
-            const int64_t h0 = (int64_t)D.hap_left.size(), r0 = (int64_t)D.rows.size();
-            for (size_t k = 1; k < S.job_off.size(); k++) D.job_off.push_back(h0 + S.job_off[k]);
-            D.hap_left.insert(D.hap_left.end(), S.hap_left.begin(), S.hap_left.end());
-            D.hap_right.insert(D.hap_right.end(), S.hap_right.begin(), S.hap_right.end());
-            for (size_t k = 1; k < S.row_off.size(); k++) D.row_off.push_back(r0 + S.row_off[k]);
-            D.rows.insert(D.rows.end(), S.rows.begin(), S.rows.end());
-        }
+        a[N] = run;
     }
+    const int T = loc->is_hla ? 3 : 1;
+    const int64_t pairs = R.s_pairs[N], J = pairs * T, H = R.s_haps[N], RW = R.s_rows[N];
+    std::vector<int64_t> job_off((size_t)J + 1, 0), row_off((size_t)H + 1, 0);
+    std::vector<int32_t> job_ut((size_t)std::max<int64_t>(J, 1)), job_pair((size_t)std::max<int64_t>(J, 1)),
+        job_list((size_t)std::max<int64_t>(J, 1)), hl((size_t)std::max<int64_t>(H, 1)), hr((size_t)std::max<int64_t>(H, 1)),
+        htb((size_t)std::max<int64_t>(H, 1)), rows((size_t)std::max<int64_t>(RW, 1));
+    jobs.job_off = job_off.data(); jobs.row_off = row_off.data(); jobs.job_ut = job_ut.data(); jobs.job_pair = job_pair.data();
+    jobs.job_list = job_list.data(); jobs.hap_left = hl.data(); jobs.hap_right = hr.data(); jobs.hap_table = htb.data();
+    jobs.rows = rows.data(); jobs.line0 = 0; jobs.n_small = R.s_small[N]; jobs.n_tables = T;
+    for (int64_t i = 0; i < N; i++) pair_jobs<true>(R, i);
+    if (err != ~0ull) return fail();
+    hgt_walk *w = new hgt_walk();
+    w->num_reads = (int64_t)unit_reads[0];
+    w->num_pairs = (int64_t)unit_pairs[0];
+    // regroup per table: job (pair p, table t) = p * T + t
+    for (int64_t p = 0; p < pairs; p++)
+        for (int t = 0; t < 3; t++) {
+            hgt_walk::Tab &D = w->tb[t];
+            if (t < T) {
+                const int64_t job = p * T + t;
+                for (int64_t h = job_off[job]; h < job_off[job + 1]; h++) {
+                    D.hap_left.push_back(hl[h]);
+                    D.hap_right.push_back(hr[h]);
+                    D.rows.insert(D.rows.end(), rows.begin() + row_off[h], rows.begin() + row_off[h + 1]);
+                    D.row_off.push_back((int64_t)D.rows.size());
+                }
+            }
+            D.job_off.push_back((int64_t)D.hap_left.size());
+        }
     *out = w;
     return HGT_OK;
 }
@@ -2586,11 +2598,11 @@ extern "C" int hgt_host_walk(hgt_locus *loc, const char *sam, size_t n_bytes, co
 extern "C" int hgt_walk_summary(const hgt_walk *w, int64_t *num_reads, int64_t *num_pairs, int64_t n_haps[3],
                                 int64_t n_rows[3]) {
     if (!w) return HGT_ERR_ARG;
-    if (num_reads) *num_reads = w->ho.num_reads;
-    if (num_pairs) *num_pairs = w->ho.num_pairs;
+    if (num_reads) *num_reads = w->num_reads;
+    if (num_pairs) *num_pairs = w->num_pairs;
     for (int t = 0; t < 3; t++) {
-        if (n_haps) n_haps[t] = (int64_t)w->ho.tb[t].hap_left.size();
-        if (n_rows) n_rows[t] = (int64_t)w->ho.tb[t].rows.size();
+        if (n_haps) n_haps[t] = (int64_t)w->tb[t].hap_left.size();
+        if (n_rows) n_rows[t] = (int64_t)w->tb[t].rows.size();
     }
     return HGT_OK;
 }
@@ -2598,12 +2610,12 @@ extern "C" int hgt_walk_summary(const hgt_walk *w, int64_t *num_reads, int64_t *
 extern "C" int hgt_walk_table(const hgt_walk *w, int32_t table, int64_t *job_off, int32_t *hap_left, int32_t *hap_right,
                               int64_t *row_off, int32_t *rows) {
     if (!w || table < 0 || table > 2) return HGT_ERR_ARG;
-    const TableJobs &J = w->ho.tb[table];
+    const hgt_walk::Tab &J = w->tb[table];
     if (job_off) memcpy(job_off, J.job_off.data(), J.job_off.size() * 8);
-    if (hap_left) memcpy(hap_left, J.hap_left.data(), J.hap_left.size() * 4);
-    if (hap_right) memcpy(hap_right, J.hap_right.data(), J.hap_right.size() * 4);
+    if (hap_left && !J.hap_left.empty()) memcpy(hap_left, J.hap_left.data(), J.hap_left.size() * 4);
+    if (hap_right && !J.hap_right.empty()) memcpy(hap_right, J.hap_right.data(), J.hap_right.size() * 4);
     if (row_off) memcpy(row_off, J.row_off.data(), J.row_off.size() * 8);
-    if (rows) memcpy(rows, J.rows.data(), J.rows.size() * 4);
+    if (rows && !J.rows.empty()) memcpy(rows, J.rows.data(), J.rows.size() * 4);
     return HGT_OK;
 }
 

@@ -1,0 +1,1357 @@
+// Stage (a), record half: alignment TEXT -> haplotypes, as code that runs on the GPU (one thread per alignment line).
+//
+// Restates, record by record, reference hisatgenotype_modules/hisatgenotype_typing_core.py:800-1406
+//   (line split + filters :804-874, CIGAR x MD x Zs walk :876-1095, error_correct :119-243, post-filters :1117-1124,
+//   novel variants :404-431 / :1126-1164, cmp_list2 :1351-1368, haplotype assembly :1386-1406, pair finalisation
+//   :1238-1347 / :1545-1587, get_exon_haplotypes :718-792) and hisatgenotype_typing_common.py:1663-1955
+//   (identify_ambigious_diffs) + hisatgenotype_validation_check.py:313-341 (check_amb_uniqueness).
+//
+// Every function is __host__ __device__: the kernels of reads.cuh call them with device pointers, and the host
+// emulation behind hgt_host_walk (no GPU; tests/test_host_walk.py) calls the SAME functions in plain loops, so the
+// device logic is pinned by the reference-captured goldens on a machine without a GPU as well.
+//
+// Data flow (all arrays indexed by line number i of the batch's text arena):
+//   parse_line        text line -> RecFields (field offsets, FLAG, POS, NM, NH) + filter flags (core:804-852)
+//   mark_head         run of equal read ids = one pair (core:1238; the input is name-grouped, core:458-468)
+//   mark_candidate    mate de-dup: first record of its mate kind inside the run (core:855-874)
+//   walk_record<0>    CIGAR x MD x Zs walk + error correction + post-filters -> ONE haplotype in the common case; records
+//                     whose ends touch an Alts_left / Alts_right anchor are queued for
+//   walk_record<1>    the same walk followed by identify_ambigious_diffs -> alternative left / right ends (factored form)
+//   pair_jobs<0 / 1>  per run: union of the mates' haplotypes, exon clipping, count pass / fill pass of the job arrays
+//                     the allele-set kernels consume (typing.cu)
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define HGT_HD __host__ __device__ __forceinline__
+#define HGT_HDN __host__ __device__ __noinline__
+#else
+#define HGT_HD inline
+#define HGT_HDN inline
+#endif
+
+namespace hgtd {
+
+// ---- capacities (exceeding one is HGT_ERR_UNSUPPORTED, never a silent truncation) -------------------------------------
+constexpr int MAXC = 96;   // cmp_list entries of one record
+constexpr int MAXI = 32;   // variant ids of a haplotype's middle part (between the ambiguous ends)
+constexpr int MAXS = 16;   // alternative ends per side of one record
+constexpr int MAXA = 16;   // variant ids of one alternative end
+constexpr int MAXHID = MAXI + 2 * MAXA;  // ids of a full haplotype
+constexpr int MAX_PAIR_HTS = 255;        // haplotypes of one pair and table (8 bit planes in class_kernel)
+
+enum : uint8_t { T_SINGLE = 0, T_DELETION = 1, T_INSERTION = 2 };
+enum : uint8_t { C_MATCH = 0, C_MISMATCH = 1, C_INSERTION = 2, C_DELETION = 3 };
+constexpr int32_t VAR_UNKNOWN = -1;
+// novel indel (type, pos, len) packed into a negative id: -2 - (ins << 29 | pos << 10 | len); pos < 2^19, len < 2^10
+HGT_HD bool novel_fits(int32_t pos, int32_t len) { return pos >= 0 && pos < (1 << 19) && len >= 0 && len < (1 << 10); }
+HGT_HD int32_t novel_code(bool ins, int32_t pos, int32_t len) { return -2 - (int32_t)(((ins ? 1u : 0u) << 29) | ((uint32_t)pos << 10) | (uint32_t)len); }
+HGT_HD bool is_novel(int32_t v) { return v <= -2; }
+
+enum : uint16_t {
+    ST_VALID = 1,   // the line is an alignment record (not blank, not a header)
+    ST_PRE = 2,     // passes the filters in front of the mate de-dup (core:814-852)
+    ST_PU = 4,      // passes the weaker filters of get_mpileup (common:1084-1098)
+    ST_HEAD = 8,    // first record of a run of equal read ids
+    ST_CAND = 16,   // first record of its mate kind in the run: goes through the walk
+    ST_SURV = 32,   // survived the walk and the post-filters: counts in num_reads, contributes haplotypes
+    ST_SLOW = 64,   // its ends touch Alts anchors: haplotypes live in a SlowRec
+};
+
+// error codes written by the device code (first failing line wins); messages and hgt_status on the host side
+enum : int {
+    E_NONE = 0, E_RECORD = 1, E_NO_NM_NH, E_MATE_KIND, E_NO_MD, E_CIGAR, E_ZS_ITEM, E_ZS_OFFSET, E_MD_SHORT, E_MD_PAST_READ,
+    E_MD_BASE, E_ZS_NOT_S, E_ZS_ID, E_ZS_NOT_I, E_MD_CARET, E_CLIP_MIDDLE, E_CIGAR_OP, E_EMPTY, E_ALT_INDEX, E_ALT_TOKEN,
+    E_AMBIGUITY, E_CAP_CMP, E_CAP_ENDS, E_CAP_IDS, E_LINE_LONG, E_NOVEL_RANGE, E_PAIR_HTS, E_COUNT_
+};
+
+// ---- atomics on both sides -----------------------------------------------------------------------------------------------
+HGT_HD void hd_min_u64(unsigned long long *p, unsigned long long v) {
+#ifdef __CUDA_ARCH__
+    atomicMin(p, v);
+#else
+    if (v < *p) *p = v;
+#endif
+}
+HGT_HD unsigned long long hd_add_u64(unsigned long long *p, unsigned long long v) {
+#ifdef __CUDA_ARCH__
+    return atomicAdd(p, v);
+#else
+    const unsigned long long o = *p;
+    *p += v;
+    return o;
+#endif
+}
+HGT_HD int32_t hd_add_i32(int32_t *p, int32_t v) {
+#ifdef __CUDA_ARCH__
+    return atomicAdd(p, v);
+#else
+    const int32_t o = *p;
+    *p += v;
+    return o;
+#endif
+}
+HGT_HD void hd_max_i32(int32_t *p, int32_t v) {
+#ifdef __CUDA_ARCH__
+    atomicMax(p, v);
+#else
+    if (v > *p) *p = v;
+#endif
+}
+
+// ---- per-locus tables of the walk (one blob per locus; pointers into host or device memory) ---------------------------
+struct VarTab {
+    int V;
+    const int32_t *pos, *len;   // [V] Var_list order
+    const uint8_t *type;        // [V] T_*
+    const char *base;           // [V] alt base of a single
+    const uint8_t *flags;       // [V] bit0 id is a key of Links, bit1 id starts with "hv"
+    const int32_t *id_off;      // [V+1] into id_pool
+    const char *id_pool;
+    const int32_t *id_hash;     // open addressing: row or -1
+    uint32_t id_hash_mask;
+};
+struct AltTab {  // Alts_left or Alts_right (common:1424-1657), entries sorted by anchor position
+    int n;
+    const int32_t *anchor;      // [n]
+    const int32_t *below;       // [L+2] number of anchors < x
+    const int32_t *key_off;     // [n+1] key string "529-hv8-hv22-606" in key_pool
+    const char *key_pool;
+    const int32_t *tok_off;     // [n+1] tokens of the key
+    const int32_t *tok_row;     // row of the token when it is a variant id of the locus, else -1
+    const int32_t *tok_num;     // atoi(token)
+    const int32_t *alt_off;     // [n+1] alternatives of the entry
+    const int32_t *alt_left, *alt_right;
+    const int32_t *altrow_off;  // [n_alts+1]
+    const int32_t *altrow;
+};
+struct LocusWalk {
+    const char *ref;
+    int L, is_hla;
+    VarTab v;
+    AltTab al, ar;
+    int n_exons, n_pexons;
+    const int32_t *exons, *pexons;  // [2*n] left,right inclusive
+};
+
+struct WalkParams {
+    int num_editdist, error_correction, allow_discordant, simulation, base_locus;
+};
+
+struct RecFields {  // 32 bytes per line
+    int32_t flag, pos;  // pos: 0-based on the backbone, after subtracting base_locus + 1
+    int16_t nm, nh;
+    uint16_t qn_off, qn_len, cig_off, cig_len, seq_off, seq_len, md_off, md_len, zs_off, zs_len;
+};
+
+struct AltEnd {  // element of left_alt_set (pos-ids) / right_alt_set (ids-pos)
+    int32_t pos, n;
+    int32_t ids[MAXA];
+};
+struct SlowRec {
+    int32_t n_left, n_right, n_mid, pad;
+    int32_t mid[MAXI];
+    AltEnd left[MAXS], right[MAXS];
+};
+
+struct LocusJobs {  // job arrays of one locus batch (typing.cu consumes them), all device (or host-emulation) pointers
+    int64_t *job_off, *row_off;                                        // [J+1], [H+1]
+    int32_t *job_ut, *job_pair, *job_list, *hap_left, *hap_right, *hap_table, *rows;
+    int64_t line0;     // first line of the locus in the arena
+    int64_t n_small;   // small jobs of the locus (<= 7 haplotypes) come first in job_list
+    int32_t n_tables, pad;
+};
+
+struct ReadsView {
+    const char *text;
+    int64_t n_lines;
+    const int64_t *line_off;   // [n_lines+1]; line i = [line_off[i], line_off[i+1] - 1), the byte before the end is '\n'
+    int32_t *unit;             // [n_lines]
+    RecFields *rec;
+    uint16_t *st;
+    // haplotype of a surviving common-case record
+    int32_t *h_left, *h_right, *h_n, *slow_slot;  // slow_slot >= 0: index into slow[]
+    int32_t *h_ids;            // [n_lines][MAXI]
+    SlowRec *slow;
+    int32_t *slow_list;        // lines queued for the ambiguity pass
+    int32_t *n_slow;
+    // units
+    int n_units;
+    const int64_t *unit_off;   // [n_units+1] byte range of every unit in the arena
+    int64_t *unit_line0;       // [n_units+1] first line of every unit
+    const int32_t *unit_locus, *unit_local;
+    const int64_t *unit_pos0;  // first position of the unit in the batch-wide pileup arrays
+    const uint8_t *nt_mask, *del_flag;
+    const LocusWalk *loci;
+    unsigned long long *err;   // (line << 8 | code), smallest wins; ~0 = none
+    unsigned long long *unit_reads, *unit_pairs;
+    // pair stage: per-line counts (non-zero at run heads), exclusive scans in place
+    int64_t *s_pairs, *s_haps, *s_rows, *s_small, *s_big;  // [n_lines+1]
+    int32_t *max_job_haps;
+    LocusJobs *jobs;           // [n_loci]
+};
+
+HGT_HD void set_error(const ReadsView &R, int64_t line, int code) {
+    hd_min_u64(R.err, ((unsigned long long)line << 8) | (unsigned long long)code);
+}
+
+// ---- small helpers -------------------------------------------------------------------------------------------------------
+HGT_HD bool is_ws(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; }
+HGT_HD bool is_dig(char c) { return c >= '0' && c <= '9'; }
+HGT_HD bool is_nt(char c) { return c == 'A' || c == 'C' || c == 'G' || c == 'T'; }
+HGT_HD int nt_code(char c) { return c == 'A' ? 0 : c == 'C' ? 1 : c == 'G' ? 2 : c == 'T' ? 3 : 4; }
+HGT_HD int ctz32(uint32_t m) {
+#ifdef __CUDA_ARCH__
+    return __ffs((int)m) - 1;
+#else
+    return __builtin_ctz(m);
+#endif
+}
+
+HGT_HD bool parse_int(const char *s, int n, int32_t *out) {
+    if (n <= 0) return false;
+    int i = 0;
+    bool neg = false;
+    if (s[0] == '-' || s[0] == '+') {
+        neg = s[0] == '-';
+        i = 1;
+    }
+    if (i >= n) return false;
+    int64_t v = 0;
+    for (; i < n; i++) {
+        if (!is_dig(s[i])) return false;
+        v = v * 10 + (s[i] - '0');
+        if (v > 2000000000LL) return false;
+    }
+    *out = (int32_t)(neg ? -v : v);
+    return true;
+}
+
+HGT_HD int lower_bound_i32(const int32_t *a, int n, int key) {
+    int lo = 0, hi = n;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+HGT_HD int32_t var_right(const VarTab &v, int r) { return v.type[r] == T_DELETION ? v.pos[r] + v.len[r] - 1 : v.pos[r]; }
+
+// Known `single` variant at pos with this base (core:159-169, 204-214, 949-961) else VAR_UNKNOWN.
+HGT_HD int32_t known_single(const VarTab &v, int32_t pos, char base) {
+    for (int j = lower_bound_i32(v.pos, v.V, pos); j < v.V && v.pos[j] == pos; j++)
+        if (v.type[j] == T_SINGLE && v.base[j] == base) return j;
+    return VAR_UNKNOWN;
+}
+HGT_HD int32_t known_indel(const VarTab &v, int32_t pos, uint8_t type, int32_t len) {
+    for (int j = lower_bound_i32(v.pos, v.V, pos); j < v.V && v.pos[j] == pos; j++)
+        if (v.type[j] == type && v.len[j] == len) return j;
+    return VAR_UNKNOWN;
+}
+
+HGT_HD uint64_t fnv1a(const char *p, int n) {
+    uint64_t h = 1469598103934665603ull;
+    for (int i = 0; i < n; i++) {
+        h ^= (unsigned char)p[i];
+        h *= 1099511628211ull;
+    }
+    return h;
+}
+// row of a variant id given as characters (Zs tag), -3 when it is not a variant of this locus
+HGT_HD int32_t row_of_chars(const VarTab &v, const char *p, int n) {
+    if (v.V <= 0) return -3;
+    uint32_t slot = (uint32_t)(fnv1a(p, n) >> 17) & v.id_hash_mask;
+    while (true) {
+        const int32_t r = v.id_hash[slot];
+        if (r < 0) return -3;
+        const int32_t o = v.id_off[r], m = v.id_off[r + 1] - o;
+        if (m == n) {
+            bool eq = true;
+            for (int k = 0; k < n && eq; k++) eq = v.id_pool[o + k] == p[k];
+            if (eq) return r;
+        }
+        slot = (slot + 1) & v.id_hash_mask;
+    }
+}
+
+// ---- line -> record fields + filters (core:804-852, common:1084-1098) ----------------------------------------------------
+HGT_HD void parse_line(const ReadsView &R, const WalkParams &P, int64_t i) {
+    const int64_t b = R.line_off[i], e = R.line_off[i + 1] - 1;
+    int lo = 0, hi = R.n_units;  // unit = last u with unit_off[u] <= b
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (R.unit_off[mid] <= b) lo = mid;
+        else hi = mid;
+    }
+    R.unit[i] = lo;
+    R.st[i] = 0;
+    R.slow_slot[i] = -1;
+    const char *s = R.text + b;
+    const int64_t n64 = e - b;
+    int64_t a = 0;
+    while (a < n64 && is_ws(s[a])) a++;
+    if (a >= n64 || s[a] == '@') return;  // blank line (arena padding) or header
+    if (n64 > 65535) {
+        set_error(R, i, E_LINE_LONG);
+        return;
+    }
+    const int n = (int)n64;
+    RecFields f;
+    f.flag = f.pos = 0;
+    f.nm = f.nh = 0;
+    f.qn_off = f.qn_len = f.cig_off = f.cig_len = f.seq_off = f.seq_len = f.md_off = f.md_len = f.zs_off = f.zs_len = 0;
+    bool has_nm = false, has_nh = false, bad = false;
+    int col = 0, p = (int)a;
+    while (p < n) {
+        while (p < n && is_ws(s[p])) p++;
+        if (p >= n) break;
+        int q = p;
+        while (q < n && !is_ws(s[q])) q++;
+        const int m = q - p;
+        if (col == 0) {
+            f.qn_off = (uint16_t)p;
+            int len = m;
+            if (P.simulation) {  // read_id.split('|')[0]  (core:808-809)
+                for (int k = 0; k < m; k++)
+                    if (s[p + k] == '|') {
+                        len = k;
+                        break;
+                    }
+            }
+            f.qn_len = (uint16_t)len;
+        } else if (col == 1) {
+            if (!parse_int(s + p, m, &f.flag)) bad = true;
+        } else if (col == 3) {
+            if (!parse_int(s + p, m, &f.pos)) bad = true;
+            f.pos -= P.base_locus + 1;
+        } else if (col == 5) {
+            f.cig_off = (uint16_t)p;
+            f.cig_len = (uint16_t)m;
+        } else if (col == 9) {
+            f.seq_off = (uint16_t)p;
+            f.seq_len = (uint16_t)m;
+        } else if (col >= 11 && m >= 5) {
+            const char c0 = s[p], c1 = s[p + 1];
+            int32_t v = 0;
+            if (c0 == 'Z' && c1 == 's') {
+                f.zs_off = (uint16_t)(p + 5);
+                f.zs_len = (uint16_t)(m - 5);
+            } else if (c0 == 'M' && c1 == 'D') {
+                f.md_off = (uint16_t)(p + 5);
+                f.md_len = (uint16_t)(m - 5);
+            } else if (c0 == 'N' && c1 == 'M') {
+                has_nm = parse_int(s + p + 5, m - 5, &v);
+                f.nm = (int16_t)(v > 32767 ? 32767 : (v < -32768 ? -32768 : v));
+            } else if (c0 == 'N' && c1 == 'H') {
+                has_nh = parse_int(s + p + 5, m - 5, &v);
+                f.nh = (int16_t)(v > 32767 ? 32767 : (v < -32768 ? -32768 : v));
+            }
+        }
+        if (bad) break;
+        col++;
+        p = q;
+    }
+    if (bad || col < 11) {
+        set_error(R, i, E_RECORD);
+        return;
+    }
+    R.rec[i] = f;
+    uint16_t st = ST_VALID;
+    const bool aligned = !(f.flag & 0x4), inside = f.pos >= 0, conc = P.allow_discordant || (f.flag & 0x2);
+    if (aligned && inside && conc) {  // get_mpileup's filters (common:1084-1098)
+        st |= ST_PU;
+        // CIGAR must parse: digits then an op character, repeatedly
+        bool have = false, ok = true;
+        for (int k = 0; k < f.cig_len && ok; k++) {
+            const char c = s[f.cig_off + k];
+            if (is_dig(c)) have = true;
+            else {
+                ok = have;
+                have = false;
+            }
+        }
+        if (!ok || have) {
+            set_error(R, i, E_CIGAR);
+            return;
+        }
+    }
+    if (inside && aligned) {  // main loop filters, in the reference's order (core:814-852)
+        if (!has_nm || !has_nh) {
+            set_error(R, i, E_NO_NM_NH);
+            return;
+        }
+        if (f.nm <= P.num_editdist && f.nh <= 1 && conc) {
+            if (!(f.flag & 0x40) && !(f.flag & 0x80) && !P.allow_discordant) {
+                set_error(R, i, E_MATE_KIND);
+                return;
+            }
+            st |= ST_PRE;
+        }
+    }
+    R.st[i] = st;
+}
+
+HGT_HD int mate_kind(int32_t flag) { return (flag & 0x40) ? 0 : ((flag & 0x80) ? 1 : 2); }
+
+// previous alignment record of the same unit, -1 if none
+HGT_HD int64_t prev_valid(const ReadsView &R, int64_t i) {
+    const int64_t first = R.unit_line0[R.unit[i]];
+    for (int64_t j = i - 1; j >= first; j--)
+        if (R.st[j] & ST_VALID) return j;
+    return -1;
+}
+
+// A run of consecutive records with the same read id is one pair (core:1238: the pair closes when a kept record
+// carries a new id; the text is grouped by name, core:458-468).
+HGT_HD void mark_head(const ReadsView &R, int64_t i) {
+    if (!(R.st[i] & ST_VALID)) return;
+    const int64_t j = prev_valid(R, i);
+    bool head = j < 0;
+    if (!head) {
+        const RecFields &x = R.rec[i], &y = R.rec[j];
+        head = x.qn_len != y.qn_len;
+        if (!head) {
+            const char *p = R.text + R.line_off[i] + x.qn_off, *q = R.text + R.line_off[j] + y.qn_off;
+            for (int k = 0; k < x.qn_len && !head; k++) head = p[k] != q[k];
+        }
+    }
+    if (head) R.st[i] |= ST_HEAD;
+}
+
+// Mate de-dup (core:855-874): a record is dropped when an earlier record of the run with the same mate kind passed
+// the filters in front of the de-dup.
+HGT_HD void mark_candidate(const ReadsView &R, int64_t i) {
+    const uint16_t st = R.st[i];
+    if (!(st & ST_PRE)) return;
+    const int kind = mate_kind(R.rec[i].flag);
+    bool dup = false;
+    if (!(st & ST_HEAD)) {
+        const int64_t first = R.unit_line0[R.unit[i]];
+        for (int64_t j = i - 1; j >= first && !dup; j--) {
+            const uint16_t sj = R.st[j];
+            if (!(sj & ST_VALID)) continue;
+            if ((sj & ST_PRE) && mate_kind(R.rec[j].flag) == kind) dup = true;
+            if (sj & ST_HEAD) break;
+        }
+    }
+    if (!dup) R.st[i] = st | ST_CAND;
+}
+
+// ---- the walk ---------------------------------------------------------------------------------------------------------------
+struct CmpList {
+    int32_t pos[MAXC], len[MAXC], var[MAXC];
+    uint8_t type[MAXC];
+    int n;
+};
+
+struct ZsCursor {  // streaming reader of "off|K|id,off|K|id,..."
+    const char *s;
+    int p, end;
+    bool have;
+    int32_t off;
+    char kind;
+    int id_p, id_n;
+};
+HGT_HD void zs_next(ZsCursor &z) {
+    if (z.p >= z.end) {
+        z.have = false;
+        return;
+    }
+    int q = z.p;
+    while (q < z.end && z.s[q] != ',') q++;
+    int b1 = z.p;
+    while (b1 < q && z.s[b1] != '|') b1++;
+    int32_t off = 0;
+    parse_int(z.s + z.p, b1 - z.p, &off);  // validated by zs_validate
+    z.off = off;
+    z.kind = z.s[b1 + 1];
+    z.id_p = b1 + 3;
+    z.id_n = q - (b1 + 3);
+    z.have = true;
+    z.p = q + 1;
+}
+// format check of every item up front (the host parser split the whole tag before the walk)
+HGT_HD int zs_validate(const char *s, int n) {
+    int p = 0;
+    while (p < n) {
+        int q = p;
+        while (q < n && s[q] != ',') q++;
+        int b1 = p;
+        while (b1 < q && s[b1] != '|') b1++;
+        if (b1 >= q) return E_ZS_ITEM;
+        if (b1 + 2 >= q || s[b1 + 2] != '|') return E_ZS_ITEM;
+        int32_t off;
+        if (!parse_int(s + p, b1 - p, &off)) return E_ZS_OFFSET;
+        p = q + 1;
+    }
+    return E_NONE;
+}
+
+HGT_HD bool cmp_push(CmpList &c, uint8_t type, int32_t pos, int32_t len, int32_t var) {
+    if (c.n >= MAXC) return false;
+    c.type[c.n] = type;
+    c.pos[c.n] = pos;
+    c.len[c.n] = len;
+    c.var[c.n] = var;
+    c.n++;
+    return true;
+}
+
+// error_correct (core:119-243) on the entries seg[0..seg.n) of one M segment, appended to `out` (adjacent matches of
+// the corrected segment merge, core:226-240).  Returns the number of corrections, -1 when `out` overflows.
+HGT_HD int error_correct(const LocusWalk &L, const char *seq, int seq_len, int32_t read_pos, const uint8_t *nt_mask,
+                         const CmpList &seg, CmpList &out) {
+    const int seg_start = out.n;
+    int ncorr = 0;
+    bool ok = true;
+    auto emit = [&](uint8_t type, int32_t pos, int32_t len, int32_t var) {
+        if (type == C_MATCH && out.n > seg_start && out.type[out.n - 1] == C_MATCH) out.len[out.n - 1] += len;
+        else ok &= cmp_push(out, type, pos, len, var);
+    };
+    for (int k = 0; k < seg.n; k++) {
+        const uint8_t ty = seg.type[k];
+        const int32_t epos = seg.pos[k], elen = seg.len[k];
+        if (epos >= L.L) {
+            for (int m = k; m < seg.n; m++) emit(seg.type[m], seg.pos[m], seg.len[m], seg.var[m]);
+            break;
+        }
+        if (ty == C_MATCH) {
+            int32_t last = 0;
+            for (int32_t j = 0; j < elen; j++) {
+                if (read_pos + j >= seq_len || epos + j >= L.L) continue;
+                const char bp = seq[read_pos + j];
+                const uint32_t m = nt_mask[epos + j];
+                const int c = nt_code(bp);
+                if (m != 0 && !(c < 4 && ((m >> c) & 1u))) {
+                    const char nb = (m & (m - 1)) ? 'N' : "ACGT"[ctz32(m)];
+                    ncorr++;
+                    const int32_t vid = nb != 'N' ? known_single(L.v, epos + j, nb) : VAR_UNKNOWN;
+                    if (j > last) emit(C_MATCH, epos + last, j - last, -1);
+                    emit(C_MISMATCH, epos + j, 1, vid);
+                    last = j + 1;
+                }
+            }
+            if (last < elen) emit(C_MATCH, epos + last, elen - last, -1);
+        } else {
+            const char bp = seq[read_pos];
+            const char ref_bp = L.ref[epos];
+            const uint32_t m = nt_mask[epos];
+            const int c = nt_code(bp);
+            uint8_t t2 = ty;
+            int32_t v2 = seg.var[k];
+            if (m != 0 && !(c < 4 && ((m >> c) & 1u))) {
+                const char nb = (m & (m - 1)) ? 'N' : "ACGT"[ctz32(m)];
+                if (nb == 'N') v2 = VAR_UNKNOWN;
+                else if (nb == ref_bp) {
+                    t2 = C_MATCH;
+                    v2 = -1;
+                    ncorr++;
+                } else v2 = known_single(L.v, epos, nb);
+            }
+            emit(t2, epos, t2 == C_MATCH ? 1 : elen, v2);
+        }
+        read_pos += elen;  // the ORIGINAL entry length (core:222)
+    }
+    return ok ? ncorr : -1;
+}
+
+struct WalkOut {
+    int32_t right_pos;
+    int ncorr;
+    bool misaligned;
+};
+
+// CIGAR x MD x Zs walk (core:876-1095).  Returns E_NONE or the error code.
+HGT_HDN int walk_cigar(const LocusWalk &L, const WalkParams &P, const char *line, const RecFields &f,
+                       const uint8_t *nt_mask, const uint8_t *del_flag, CmpList &cmp, CmpList &seg, WalkOut &w) {
+    if (f.md_len == 0) return E_NO_MD;
+    const char *MD = line + f.md_off;
+    const int MDn = f.md_len;
+    const char *seq = line + f.seq_off;
+    const int seq_len = f.seq_len;
+    const char *cig = line + f.cig_off;
+    const int cig_n = f.cig_len;
+    ZsCursor z;
+    z.s = line + f.zs_off;
+    z.p = 0;
+    z.end = f.zs_len;
+    z.have = false;
+    if (f.zs_len > 0) {
+        const int ze = zs_validate(z.s, f.zs_len);
+        if (ze != E_NONE) return ze;
+        zs_next(z);
+    }
+    int32_t zs_pos = z.have ? z.off : 0;
+    int md_i = 0;
+    int32_t md_len = 0, read_pos = 0, right_pos = f.pos;
+    cmp.n = 0;
+    w.ncorr = 0;
+    w.misaligned = false;
+    int cp = 0, ci = 0;
+    while (cp < cig_n) {
+        int32_t length = 0;
+        bool have = false;
+        while (cp < cig_n && is_dig(cig[cp])) {
+            length = length * 10 + (cig[cp] - '0');
+            have = true;
+            cp++;
+        }
+        if (!have || cp >= cig_n) return E_CIGAR;
+        const char op = cig[cp++];
+        const bool last_op = cp >= cig_n;
+        if (op == 'M') {
+            bool first = true;
+            int32_t used = 0;
+            CmpList &dst = P.error_correction ? seg : cmp;
+            if (P.error_correction) seg.n = 0;
+            while (true) {
+                if (!first || md_len == 0) {
+                    if (md_i >= MDn) return E_MD_SHORT;
+                    if (is_dig(MD[md_i])) {
+                        int32_t num = 0;
+                        while (md_i < MDn && is_dig(MD[md_i])) num = num * 10 + (MD[md_i++] - '0');
+                        md_len += num;
+                    }
+                }
+                if (md_len >= length) {
+                    md_len -= length;
+                    if (length > used && !cmp_push(dst, C_MATCH, right_pos + used, length - used, -1)) return E_CAP_CMP;
+                    break;
+                }
+                first = false;
+                if (read_pos + md_len >= seq_len) return E_MD_PAST_READ;
+                const char base = seq[read_pos + md_len];
+                if (md_i >= MDn || !is_nt(MD[md_i])) return E_MD_BASE;
+                md_i++;
+                if (md_len > used && !cmp_push(dst, C_MATCH, right_pos + used, md_len - used, -1)) return E_CAP_CMP;
+                int32_t vid = VAR_UNKNOWN;
+                if (read_pos + md_len == zs_pos && z.have) {
+                    if (z.kind != 'S') return E_ZS_NOT_S;
+                    vid = row_of_chars(L.v, z.s + z.id_p, z.id_n);
+                    if (vid < 0) return E_ZS_ID;
+                    zs_next(z);
+                    zs_pos += 1;
+                    if (z.have) zs_pos += z.off;
+                } else {
+                    vid = known_single(L.v, right_pos + md_len, base);
+                }
+                if (!cmp_push(dst, C_MISMATCH, right_pos + md_len, 1, vid)) return E_CAP_CMP;
+                used = md_len + 1;
+                md_len += 1;
+                if (md_len == length) {
+                    md_len = 0;
+                    break;
+                }
+            }
+            if (P.error_correction) {
+                const int nc = error_correct(L, seq, seq_len, read_pos, nt_mask, seg, cmp);
+                if (nc < 0) return E_CAP_CMP;
+                w.ncorr += nc;
+            }
+        } else if (op == 'I') {
+            int32_t vid = VAR_UNKNOWN;
+            if (read_pos == zs_pos && z.have) {
+                if (z.kind != 'I') return E_ZS_NOT_I;
+                vid = row_of_chars(L.v, z.s + z.id_p, z.id_n);
+                if (vid < 0) return E_ZS_ID;
+                zs_next(z);
+                if (z.have) zs_pos += z.off;
+            } else {
+                vid = known_indel(L.v, right_pos, T_INSERTION, length);
+            }
+            if (!cmp_push(cmp, C_INSERTION, right_pos, length, vid)) return E_CAP_CMP;
+            for (int32_t j = read_pos; j < read_pos + length && j < seq_len; j++)
+                if (seq[j] == 'N') w.misaligned = true;
+        } else if (op == 'D') {
+            if (md_i < MDn && MD[md_i] == '0') md_i++;
+            if (md_i >= MDn || MD[md_i] != '^') return E_MD_CARET;
+            md_i++;
+            while (md_i < MDn && is_nt(MD[md_i])) md_i++;
+            int32_t vid = VAR_UNKNOWN;
+            if (read_pos == zs_pos && z.have && z.kind == 'D') {
+                vid = row_of_chars(L.v, z.s + z.id_p, z.id_n);
+                if (vid < 0) return E_ZS_ID;
+                zs_next(z);
+                if (z.have) zs_pos += z.off;
+            } else {
+                vid = known_indel(L.v, right_pos, T_DELETION, length);
+            }
+            if (!cmp_push(cmp, C_DELETION, right_pos, length, vid)) return E_CAP_CMP;
+            // artificial-deletion rule, hla only (core:1064-1077)
+            if (right_pos >= 0 && right_pos < L.L && L.is_hla && del_flag[right_pos]) w.misaligned = true;
+        } else if (op == 'S') {
+            if (ci == 0) zs_pos += length;
+            else if (!last_op) return E_CLIP_MIDDLE;
+        } else {
+            return E_CIGAR_OP;
+        }
+        if (op == 'M' || op == 'N' || op == 'D') right_pos += length;
+        if (op == 'M' || op == 'I' || op == 'S') read_pos += length;
+        ci++;
+    }
+    w.right_pos = right_pos;
+    return E_NONE;
+}
+
+HGT_HD bool any_anchor(const AltTab &t, int L, int32_t lo, int32_t hi) {  // conservative outside the backbone
+    if (lo < 0 || hi >= L) return true;
+    if (hi < lo) return false;
+    return t.below[hi + 1] - t.below[lo] > 0;
+}
+HGT_HD bool id_is_hv(const VarTab &v, int32_t var) { return var >= 0 && ((v.flags[var] >> 1) & 1); }
+
+// Does the '-'-joined id string of rows ids[0..m) occur inside the entry's key (common:1734, 1856: str.find)?
+HGT_HD bool key_contains_ids(const VarTab &v, const AltTab &t, int e, const int32_t *ids, int m) {
+    const char *key = t.key_pool + t.key_off[e];
+    const int kn = t.key_off[e + 1] - t.key_off[e];
+    int total = m - 1;
+    for (int k = 0; k < m; k++) total += v.id_off[ids[k] + 1] - v.id_off[ids[k]];
+    for (int s = 0; s + total <= kn; s++) {
+        int p = s;
+        bool ok = true;
+        for (int k = 0; k < m && ok; k++) {
+            if (k) ok = key[p++] == '-';
+            const int32_t o = v.id_off[ids[k]], n = v.id_off[ids[k] + 1] - o;
+            for (int c = 0; c < n && ok; c++) ok = key[p++] == v.id_pool[o + c];
+        }
+        if (ok) return true;
+    }
+    return false;
+}
+
+HGT_HD bool end_equal(const AltEnd &x, int32_t pos, const int32_t *ids, int n) {
+    if (x.pos != pos || x.n != n) return false;
+    for (int k = 0; k < n; k++)
+        if (x.ids[k] != ids[k]) return false;
+    return true;
+}
+// set.add((pos, ids)); returns false on capacity overflow
+HGT_HD bool end_add(AltEnd *set, int32_t &n_set, int32_t pos, const int32_t *ids, int n) {
+    for (int k = 0; k < n_set; k++)
+        if (end_equal(set[k], pos, ids, n)) return true;
+    if (n_set >= MAXS || n > MAXA) return false;
+    set[n_set].pos = pos;
+    set[n_set].n = n;
+    for (int k = 0; k < n; k++) set[n_set].ids[k] = ids[k];
+    n_set++;
+    return true;
+}
+
+// identify_ambigious_diffs (common:1663-1955) on cmp_list2 `c`; alternative ends go to S.left / S.right, the kept
+// entry range to *cmp_left / *cmp_right.  Returns E_NONE or an error code.
+HGT_HDN int identify_ambiguous(const LocusWalk &L, const CmpList &c, SlowRec &S, int32_t *cmp_left_out, int32_t *cmp_right_out) {
+    const VarTab &V = L.v;
+    const int n = c.n;
+    int32_t cmp_left = 0, cmp_right = n - 1;
+    S.n_left = S.n_right = 0;
+    const int32_t left = c.pos[0], right = c.pos[n - 1] + c.len[n - 1] - 1;
+    // prefix sums over the entries: known ids, novel ids and sequence length of c[0..i)  (get_haplotype_and_seq,
+    // common:1679-1700)
+    int32_t all_ids[MAXC];
+    int32_t idn[MAXC + 1], nov[MAXC + 1], sl[MAXC + 1];
+    {
+        int na = 0;
+        idn[0] = nov[0] = sl[0] = 0;
+        for (int i = 0; i < n; i++) {
+            int32_t len = 0;
+            if (c.type[i] == C_MATCH) {
+                const int32_t a = c.pos[i] < 0 ? 0 : (c.pos[i] > L.L ? L.L : c.pos[i]);
+                const int32_t e = c.pos[i] + c.len[i];
+                const int32_t b = e < 0 ? 0 : (e > L.L ? L.L : e);
+                len = b > a ? b - a : 0;
+            } else if (c.type[i] == C_MISMATCH) {
+                len = 1;
+            }
+            int32_t novel = 0;
+            if (c.type[i] != C_MATCH && c.var[i] != VAR_UNKNOWN) {
+                if (c.var[i] >= 0) all_ids[na++] = c.var[i];
+                else novel = 1;
+            }
+            idn[i + 1] = na;
+            nov[i + 1] = nov[i] + novel;
+            sl[i + 1] = sl[i] + len;
+        }
+    }
+    int32_t tmp[MAXA + MAXC];
+    bool cap_ok = true;
+    // ---- left end ------------------------------------------------------------------------------------------
+    bool found = false;
+    if (L.al.n > 0) {
+        const AltTab &T = L.al;
+        for (int i = n - 1; i >= 0; i--) {
+            if (c.type[i] != C_MATCH) {
+                if (c.type[i] == C_INSERTION || !id_is_hv(V, c.var[i])) continue;
+            }
+            const int32_t cur_left = c.pos[i];
+            const int32_t cur_right = (c.type[i] == C_MATCH || c.type[i] == C_DELETION) ? c.pos[i] + c.len[i] - 1 : c.pos[i];
+            if (!any_anchor(T, L.L, cur_left, cur_right)) continue;
+            int start = lower_bound_i32(T.anchor, T.n, cur_right + 1) + 1;
+            if (start > T.n) start = T.n;
+            const bool has_novel = nov[i + 1] > 0;
+            const int32_t cur_len = sl[i + 1];
+            const int32_t *cur_ids = all_ids;
+            const int n_cur = idn[i + 1];
+            const int n_ids = n_cur + (has_novel ? 1 : 0);  // novel ids count as ids that never match
+            bool hit = false;
+            for (int j = start - 1; j >= 0; j--) {
+                if (T.anchor[j] < cur_left) break;
+                if (T.anchor[j] > cur_right) continue;
+                if (n_ids > 0) {
+                    if (has_novel || !key_contains_ids(V, T, j, cur_ids, n_cur)) continue;
+                }
+                const int32_t *tok_row = T.tok_row + T.tok_off[j], *tok_num = T.tok_num + T.tok_off[j];
+                const int ntok = T.tok_off[j + 1] - T.tok_off[j] - 1;  // key.split('-')[:-1]
+                if (n_cur + 1 == ntok) {
+                    if (left < tok_num[0]) continue;
+                } else {
+                    int k = ntok - n_cur - 1;
+                    if (k < 0) k += ntok;  // Python negative index
+                    if (k < 0 || k >= ntok) return E_ALT_INDEX;
+                    const int32_t row = tok_row[k];
+                    if (row < 0) return E_ALT_TOKEN;
+                    if (left <= var_right(V, row)) continue;
+                }
+                hit = true;
+                for (int a = T.alt_off[j]; a < T.alt_off[j + 1]; a++) {
+                    const int32_t *rows = T.altrow + T.altrow_off[a];
+                    const int nrow = T.altrow_off[a + 1] - T.altrow_off[a];
+                    int32_t seq_pos = cur_right - T.alt_right[a], cur_pos = T.alt_right[a];
+                    int first_kept = nrow;  // rows[first_kept..nrow) form the part covered by the read
+                    for (int t = nrow - 1; t >= 0; t--) {
+                        const int32_t r = rows[t];
+                        const int32_t vp = var_right(V, r);
+                        int32_t nxt = seq_pos + (cur_pos - vp);
+                        if (nxt >= cur_len) break;
+                        int32_t npos;
+                        if (V.type[r] == T_SINGLE) {
+                            nxt += 1;
+                            npos = vp - 1;
+                        } else npos = vp - V.len[r];
+                        first_kept = t;
+                        if (nxt >= cur_len) break;
+                        seq_pos = nxt;
+                        cur_pos = npos;
+                    }
+                    if (first_kept < nrow) {
+                        const int32_t seq_left = cur_len - seq_pos - 1;
+                        int m = 0;
+                        if (nrow - first_kept > MAXA) return E_CAP_ENDS;
+                        for (int t = first_kept; t < nrow; t++) tmp[m++] = rows[t];
+                        if (found)
+                            for (int q = i + 1; q < cmp_left; q++)
+                                if (c.type[q] != C_MATCH && id_is_hv(V, c.var[q])) {
+                                    if (m >= MAXA + MAXC) return E_CAP_IDS;
+                                    tmp[m++] = c.var[q];
+                                }
+                        cap_ok &= end_add(S.left, S.n_left, cur_pos - seq_left, tmp, m);
+                    }
+                }
+            }
+            if (hit) {
+                if (!found) {
+                    cmp_left = i + 1;
+                    // cur_ht_str; a hit implies the slice holds no novel id (the substring test would fail)
+                    cap_ok &= end_add(S.left, S.n_left, left, cur_ids, n_cur);
+                }
+                found = true;
+            }
+        }
+    }
+    if (!found) cap_ok &= end_add(S.left, S.n_left, left, tmp, 0);
+    // ---- right end -----------------------------------------------------------------------------------------
+    found = false;
+    if (L.ar.n > 0) {
+        const AltTab &T = L.ar;
+        for (int i = 0; i < n; i++) {
+            if (c.type[i] != C_MATCH) {
+                if (c.type[i] == C_INSERTION || !id_is_hv(V, c.var[i])) continue;
+            }
+            const int32_t cur_left = c.pos[i];
+            const int32_t cur_right = (c.type[i] == C_MATCH || c.type[i] == C_DELETION) ? c.pos[i] + c.len[i] - 1 : c.pos[i];
+            if (!any_anchor(T, L.L, cur_left, cur_right)) continue;
+            const int start = lower_bound_i32(T.anchor, T.n, cur_left);
+            if (start >= T.n || T.anchor[start] > cur_right) continue;
+            const bool has_novel = nov[n] - nov[i] > 0;
+            const int32_t cur_len = sl[n] - sl[i];
+            const int32_t *cur_ids = all_ids + idn[i];
+            const int n_cur = idn[n] - idn[i];
+            const int n_ids = n_cur + (has_novel ? 1 : 0);
+            bool hit = false;
+            for (int j = start; j < T.n; j++) {
+                if (T.anchor[j] > cur_right) break;
+                if (T.anchor[j] < cur_left) continue;
+                if (n_ids > 0) {
+                    if (has_novel || !key_contains_ids(V, T, j, cur_ids, n_cur)) continue;
+                }
+                const int32_t *tok_row = T.tok_row + T.tok_off[j], *tok_num = T.tok_num + T.tok_off[j];
+                const int ntok = T.tok_off[j + 1] - T.tok_off[j] - 1;  // key.split('-')[1:]
+                if (n_cur + 1 == ntok) {
+                    if (right > tok_num[ntok]) continue;
+                } else {
+                    const int k = n_cur;
+                    if (k >= ntok) return E_ALT_INDEX;
+                    const int32_t row = tok_row[1 + k];
+                    if (row < 0) return E_ALT_TOKEN;
+                    if (right >= V.pos[row]) continue;
+                }
+                hit = true;
+                for (int a = T.alt_off[j]; a < T.alt_off[j + 1]; a++) {
+                    const int32_t *rows = T.altrow + T.altrow_off[a];
+                    const int nrow = T.altrow_off[a + 1] - T.altrow_off[a];
+                    int32_t seq_pos = T.alt_left[a] - cur_left, cur_pos = T.alt_left[a];
+                    int kept = 0;
+                    for (int t = 0; t < nrow; t++) {
+                        const int32_t r = rows[t];
+                        int32_t nxt = seq_pos + (V.pos[r] - cur_pos);
+                        if (nxt >= cur_len) break;
+                        int32_t npos;
+                        if (V.type[r] == T_SINGLE) {
+                            nxt += 1;
+                            npos = V.pos[r] + 1;
+                        } else npos = V.pos[r] + V.len[r];
+                        kept = t + 1;
+                        if (nxt >= cur_len) break;
+                        seq_pos = nxt;
+                        cur_pos = npos;
+                    }
+                    if (kept > 0) {
+                        const int32_t seq_left = cur_len - seq_pos - 1;
+                        int m = 0;
+                        if (found)
+                            for (int q = cmp_right + 1; q < i; q++)
+                                if (c.type[q] != C_MATCH && id_is_hv(V, c.var[q])) {
+                                    if (m >= MAXC) return E_CAP_IDS;
+                                    tmp[m++] = c.var[q];
+                                }
+                        for (int t = 0; t < kept; t++) {
+                            if (m >= MAXA + MAXC) return E_CAP_IDS;
+                            tmp[m++] = rows[t];
+                        }
+                        cap_ok &= end_add(S.right, S.n_right, cur_pos + seq_left, tmp, m);
+                    }
+                }
+            }
+            if (hit) {
+                if (!found) {
+                    cmp_right = i - 1;
+                    cap_ok &= end_add(S.right, S.n_right, right, cur_ids, n_cur);
+                }
+                found = true;
+            }
+        }
+    }
+    if (!found) cap_ok &= end_add(S.right, S.n_right, right, tmp, 0);
+    if (cmp_right < cmp_left) {
+        cmp_left = 0;
+        S.n_left = 0;
+        cap_ok &= end_add(S.left, S.n_left, left, tmp, 0);
+    }
+    if (!cap_ok) return E_CAP_ENDS;
+    // check_amb_uniqueness (validation_check.py:313-341): no non-empty id list twice across both sides
+    for (int x = 0; x < S.n_left + S.n_right; x++) {
+        const AltEnd &ex = x < S.n_left ? S.left[x] : S.right[x - S.n_left];
+        if (ex.n == 0) continue;
+        for (int y = 0; y < x; y++) {
+            const AltEnd &ey = y < S.n_left ? S.left[y] : S.right[y - S.n_left];
+            if (ey.n != ex.n) continue;
+            bool eq = true;
+            for (int k = 0; k < ex.n && eq; k++) eq = ex.ids[k] == ey.ids[k];
+            if (eq) return E_AMBIGUITY;
+        }
+    }
+    *cmp_left_out = cmp_left;
+    *cmp_right_out = cmp_right;
+    return E_NONE;
+}
+
+// One candidate record through the walk.  SLOW = false: common case; records with an Alts anchor under one of their
+// ends are queued (slow_list) instead.  SLOW = true: line i is such a record and slot its SlowRec.
+template <bool SLOW>
+HGT_HD void walk_record(const ReadsView &R, const WalkParams &P, int64_t i, int32_t slot) {
+    const uint16_t st = R.st[i];
+    if (!(st & ST_CAND)) return;
+    const RecFields f = R.rec[i];
+    const int u = R.unit[i];
+    const LocusWalk &L = R.loci[R.unit_locus[u]];
+    const char *line = R.text + R.line_off[i];
+    const uint8_t *nt_mask = R.nt_mask + R.unit_pos0[u], *del_flag = R.del_flag + R.unit_pos0[u];
+    CmpList cmp, seg;
+    WalkOut w;
+    const int rc = walk_cigar(L, P, line, f, nt_mask, del_flag, cmp, seg, w);
+    if (rc != E_NONE) {
+        set_error(R, i, rc);
+        return;
+    }
+    // post-filters (core:1117-1124)
+    if (w.right_pos > L.L) return;
+    if (w.ncorr > (P.num_editdist > 1 ? P.num_editdist : 1)) return;
+    if (w.misaligned) return;
+    // novel variants (core:1126-1164): only indels keep an identity, (type, pos, len); unknown mismatches turn into
+    // matches below.  cmp_list2 (core:1351-1368) in place.
+    int n2 = 0;
+    for (int k = 0; k < cmp.n; k++) {
+        const uint8_t ty = cmp.type[k];
+        int32_t var = cmp.var[k];
+        if ((ty == C_INSERTION || ty == C_DELETION) && var == VAR_UNKNOWN) {
+            if (!novel_fits(cmp.pos[k], cmp.len[k])) {
+                set_error(R, i, E_NOVEL_RANGE);
+                return;
+            }
+            var = novel_code(ty == C_INSERTION, cmp.pos[k], cmp.len[k]);
+        }
+        if (ty == C_MATCH || (ty == C_MISMATCH && var < 0)) {
+            const int32_t ln = ty == C_MATCH ? cmp.len[k] : 1;
+            if (n2 > 0 && cmp.type[n2 - 1] == C_MATCH) cmp.len[n2 - 1] += ln;
+            else {
+                cmp.type[n2] = C_MATCH;
+                cmp.pos[n2] = cmp.pos[k];
+                cmp.len[n2] = ln;
+                cmp.var[n2] = -1;
+                n2++;
+            }
+        } else {
+            cmp.type[n2] = ty;
+            cmp.pos[n2] = cmp.pos[k];
+            cmp.len[n2] = cmp.len[k];
+            cmp.var[n2] = var;
+            n2++;
+        }
+    }
+    cmp.n = n2;
+    if (n2 == 0) {
+        set_error(R, i, E_EMPTY);
+        return;
+    }
+    if (!SLOW) {
+        // does identify_ambigious_diffs have anything to look at?  (an Alts anchor inside an eligible entry)
+        bool amb = false;
+        for (int k = 0; k < n2 && !amb; k++) {
+            if (cmp.type[k] != C_MATCH && (cmp.type[k] == C_INSERTION || !id_is_hv(L.v, cmp.var[k]))) continue;
+            const int32_t cl = cmp.pos[k];
+            const int32_t cr = (cmp.type[k] == C_MATCH || cmp.type[k] == C_DELETION) ? cl + cmp.len[k] - 1 : cl;
+            if (L.al.n > 0 && any_anchor(L.al, L.L, cl, cr)) amb = true;
+            if (L.ar.n > 0 && any_anchor(L.ar, L.L, cl, cr)) amb = true;
+        }
+        if (amb) {
+            R.slow_list[hd_add_i32(R.n_slow, 1)] = (int32_t)i;
+            return;
+        }
+        int m = 0;
+        for (int k = 0; k < n2; k++)
+            if (cmp.type[k] != C_MATCH) {
+                if (m >= MAXI) {
+                    set_error(R, i, E_CAP_IDS);
+                    return;
+                }
+                R.h_ids[i * MAXI + m++] = cmp.var[k];
+            }
+        R.h_left[i] = cmp.pos[0];
+        R.h_right[i] = cmp.pos[n2 - 1] + cmp.len[n2 - 1] - 1;
+        R.h_n[i] = m;
+        R.st[i] = st | ST_SURV;
+        hd_add_u64(&R.unit_reads[u], 1ull);
+    } else {
+        SlowRec &S = R.slow[slot];
+        int32_t cl = 0, cr = n2 - 1;
+        const int e = identify_ambiguous(L, cmp, S, &cl, &cr);
+        if (e != E_NONE) {
+            set_error(R, i, e);
+            return;
+        }
+        int m = 0;
+        for (int k = cl; k <= cr; k++)
+            if (cmp.type[k] != C_MATCH) {
+                if (m >= MAXI) {
+                    set_error(R, i, E_CAP_IDS);
+                    return;
+                }
+                S.mid[m++] = cmp.var[k];
+            }
+        S.n_mid = m;
+        R.slow_slot[i] = slot;
+        R.st[i] = st | ST_SURV | ST_SLOW;
+        hd_add_u64(&R.unit_reads[u], 1ull);
+    }
+}
+
+// ---- pair stage ------------------------------------------------------------------------------------------------------------
+struct HtRef {  // one haplotype of a record: alternative left end a, alternative right end b (0, 0 in the common case)
+    int64_t line;
+    int32_t slot, a, b;
+};
+HGT_HD int32_t ht_left(const ReadsView &R, const HtRef &h) { return h.slot < 0 ? R.h_left[h.line] : R.slow[h.slot].left[h.a].pos; }
+HGT_HD int32_t ht_right(const ReadsView &R, const HtRef &h) { return h.slot < 0 ? R.h_right[h.line] : R.slow[h.slot].right[h.b].pos; }
+HGT_HD int ht_nids(const ReadsView &R, const HtRef &h) {
+    if (h.slot < 0) return R.h_n[h.line];
+    const SlowRec &S = R.slow[h.slot];
+    return S.left[h.a].n + S.n_mid + S.right[h.b].n;
+}
+HGT_HD int32_t ht_id(const ReadsView &R, const HtRef &h, int k) {
+    if (h.slot < 0) return R.h_ids[h.line * MAXI + k];
+    const SlowRec &S = R.slow[h.slot];
+    if (k < S.left[h.a].n) return S.left[h.a].ids[k];
+    k -= S.left[h.a].n;
+    if (k < S.n_mid) return S.mid[k];
+    return S.right[h.b].ids[k - S.n_mid];
+}
+HGT_HD bool ht_equal(const ReadsView &R, const HtRef &x, const HtRef &y) {
+    if (ht_left(R, x) != ht_left(R, y) || ht_right(R, x) != ht_right(R, y)) return false;
+    const int n = ht_nids(R, x);
+    if (n != ht_nids(R, y)) return false;
+    for (int k = 0; k < n; k++)
+        if (ht_id(R, x, k) != ht_id(R, y, k)) return false;
+    return true;
+}
+
+struct VarLite {
+    uint8_t type;
+    int32_t pos, len;
+};
+HGT_HD VarLite var_lite(const VarTab &v, int32_t id) {
+    VarLite x;
+    if (id >= 0) {
+        x.type = v.type[id];
+        x.pos = v.pos[id];
+        x.len = v.len[id];
+    } else {
+        const uint32_t c = (uint32_t)(-2 - id);
+        x.type = (c >> 29) & 1u ? T_INSERTION : T_DELETION;
+        x.pos = (int32_t)((c >> 10) & 0x7ffffu);
+        x.len = (int32_t)(c & 0x3ffu);
+    }
+    return x;
+}
+
+// get_exon_haplotypes (core:718-792) for ONE exon: false when the haplotype does not overlap it, else the clipped
+// bounds and the kept id range [lo, hi).
+HGT_HD bool exon_clip(const ReadsView &R, const VarTab &V, const HtRef &h, int32_t e_left, int32_t e_right, int32_t *left_out,
+                      int32_t *right_out, int *lo_out, int *hi_out) {
+    int32_t left = ht_left(R, h), right = ht_right(R, h);
+    if (e_left > right || e_right < left) return false;
+    const int n = ht_nids(R, h);
+    int lo = 0, hi = n;
+    if (left < e_left) {
+        bool split = false;
+        for (int k = 0; k < n; k++) {
+            const VarLite v = var_lite(V, ht_id(R, h, k));
+            if ((v.type != T_DELETION && v.pos >= e_left) || (v.type == T_DELETION && v.pos - 1 >= e_left)) {
+                left = e_left;
+                lo = k;
+                split = true;
+                break;
+            }
+            if (v.type == T_DELETION && v.pos + v.len >= e_left) {
+                left = v.pos + v.len;
+                lo = k + 1;
+                split = true;
+                break;
+            }
+        }
+        if (!split) {
+            left = e_left;
+            lo = hi = 0;
+        }
+    }
+    if (right > e_right) {
+        bool split = false;
+        for (int k = hi; k-- > lo;) {
+            const VarLite v = var_lite(V, ht_id(R, h, k));
+            const int32_t r = v.type == T_DELETION ? v.pos + v.len - 1 : v.pos;
+            if ((v.type != T_DELETION && r <= e_right) || (v.type == T_DELETION && r + 1 <= e_right)) {
+                right = e_right;
+                hi = k + 1;
+                split = true;
+                break;
+            }
+            if (v.type == T_DELETION && r - v.len <= e_right) {
+                right = r - v.len;
+                hi = k;
+                split = true;
+                break;
+            }
+        }
+        if (!split) {
+            right = e_right;
+            lo = hi = 0;
+        }
+    }
+    *left_out = left;
+    *right_out = right;
+    *lo_out = lo;
+    *hi_out = hi;
+    return true;
+}
+
+// rows of Links the allele-set kernel ANDs: ids [lo, hi) that are known variants present in Links, sorted, unique
+HGT_HD int hap_rows(const ReadsView &R, const VarTab &V, const HtRef &h, int lo, int hi, int32_t *rows) {
+    int m = 0;
+    for (int k = lo; k < hi; k++) {
+        const int32_t id = ht_id(R, h, k);
+        if (id < 0 || !(V.flags[id] & 1)) continue;
+        int p = m;
+        while (p > 0 && rows[p - 1] > id) p--;
+        if (p > 0 && rows[p - 1] == id) continue;
+        for (int q = m; q > p; q--) rows[q] = rows[q - 1];
+        rows[p] = id;
+        m++;
+    }
+    return m;
+}
+
+// Pair finalisation (core:1238-1347, 1545-1587) for the run that starts at head line i.
+//   FILL = false: count pass - pairs, haplotypes, rows, small / big jobs of the run into the s_* arrays (scanned later)
+//   FILL = true : write the job arrays of the locus at the scanned offsets
+template <bool FILL>
+HGT_HD void pair_jobs(const ReadsView &R, int64_t i) {
+    if (!FILL) R.s_pairs[i] = R.s_haps[i] = R.s_rows[i] = R.s_small[i] = R.s_big[i] = 0;
+    if (!(R.st[i] & ST_HEAD)) return;
+    const int u = R.unit[i];
+    const int locus = R.unit_locus[u];
+    const LocusWalk &L = R.loci[locus];
+    const VarTab &V = L.v;
+    const int T = L.is_hla ? 3 : 1;
+    // surviving records of the run: the first-mate record feeds left_positive_hts, the others right_positive_hts
+    int64_t recs[3];
+    int nrec = 0;
+    {
+        int64_t left_rec = -1, others[2];
+        int no = 0;
+        const int64_t end = R.unit_line0[u + 1];
+        for (int64_t j = i; j < end; j++) {
+            const uint16_t sj = R.st[j];
+            if (j > i && (sj & ST_HEAD)) break;
+            if (!(sj & ST_SURV)) continue;
+            if (mate_kind(R.rec[j].flag) == 0) left_rec = j;
+            else if (no < 2) others[no++] = j;
+        }
+        if (left_rec >= 0) recs[nrec++] = left_rec;
+        for (int k = 0; k < no; k++) recs[nrec++] = others[k];
+    }
+    if (nrec == 0) return;
+    // enumerate the union of the mates' haplotypes; haplotype g is skipped when an earlier one equals it
+    int total = 0;
+    for (int r = 0; r < nrec; r++) {
+        const int32_t slot = R.slow_slot[recs[r]];
+        total += slot < 0 ? 1 : R.slow[slot].n_left * R.slow[slot].n_right;
+    }
+    auto ht_at = [&](int g) {
+        HtRef h;
+        h.line = recs[0];
+        h.slot = -1;
+        h.a = h.b = 0;
+        for (int r = 0; r < nrec; r++) {
+            const int32_t slot = R.slow_slot[recs[r]];
+            const int cnt = slot < 0 ? 1 : R.slow[slot].n_left * R.slow[slot].n_right;
+            if (g < cnt) {
+                h.line = recs[r];
+                h.slot = slot;
+                if (slot >= 0) {
+                    h.a = g / R.slow[slot].n_right;
+                    h.b = g % R.slow[slot].n_right;
+                }
+                return h;
+            }
+            g -= cnt;
+        }
+        return h;
+    };
+    auto is_dup = [&](int g, const HtRef &h) {
+        for (int q = 0; q < g; q++)
+            if (ht_equal(R, ht_at(q), h)) return true;
+        return false;
+    };
+    int32_t rows[MAXHID];
+    int64_t kt[3] = {0, 0, 0}, rows_total = 0;
+    for (int g = 0; g < total; g++) {
+        const HtRef h = ht_at(g);
+        if (ht_nids(R, h) > MAXHID) {
+            set_error(R, i, E_CAP_IDS);
+            return;
+        }
+        if (total > 1 && is_dup(g, h)) continue;
+        kt[0]++;
+        rows_total += hap_rows(R, V, h, 0, ht_nids(R, h), rows);
+        if (T == 3) {
+            for (int tb = 2; tb >= 1; tb--) {
+                const int ne = tb == 2 ? L.n_pexons : L.n_exons;
+                const int32_t *ex = tb == 2 ? L.pexons : L.exons;
+                for (int x = 0; x < ne; x++) {
+                    int32_t l2, r2;
+                    int lo, hi;
+                    if (!exon_clip(R, V, h, ex[2 * x], ex[2 * x + 1], &l2, &r2, &lo, &hi)) continue;
+                    kt[tb]++;
+                    rows_total += hap_rows(R, V, h, lo, hi, rows);
+                }
+            }
+        }
+    }
+    int n_small = 0;
+    int64_t kmax = 0;
+    for (int tb = 0; tb < T; tb++) {
+        if (kt[tb] > MAX_PAIR_HTS) {
+            set_error(R, i, E_PAIR_HTS);
+            return;
+        }
+        n_small += kt[tb] <= 7;
+        kmax = kt[tb] > kmax ? kt[tb] : kmax;
+    }
+    if (!FILL) {
+        R.s_pairs[i] = 1;
+        R.s_haps[i] = kt[0] + kt[1] + kt[2];
+        R.s_rows[i] = rows_total;
+        R.s_small[i] = n_small;
+        R.s_big[i] = T - n_small;
+        hd_add_u64(&R.unit_pairs[u], 1ull);
+        hd_max_i32(R.max_job_haps, (int32_t)kmax);
+        return;
+    }
+    // ---- fill -----------------------------------------------------------------------------------------------------------
+    const LocusJobs &J = R.jobs[locus];
+    const int64_t l0 = J.line0;
+    const int64_t pair_in_locus = R.s_pairs[i] - R.s_pairs[l0];
+    const int64_t pair_in_unit = R.s_pairs[i] - R.s_pairs[R.unit_line0[u]];
+    int64_t hap = R.s_haps[i] - R.s_haps[l0], row = R.s_rows[i] - R.s_rows[l0];
+    int64_t small = R.s_small[i] - R.s_small[l0], big = J.n_small + (R.s_big[i] - R.s_big[l0]);
+    for (int tb = 0; tb < T; tb++) {
+        const int64_t job = pair_in_locus * T + tb;
+        J.job_ut[job] = R.unit_local[u] * 4 + tb;
+        J.job_pair[job] = (int32_t)pair_in_unit;
+        if (kt[tb] <= 7) J.job_list[small++] = (int32_t)job;
+        else J.job_list[big++] = (int32_t)job;
+        for (int g = 0; g < total; g++) {
+            const HtRef h = ht_at(g);
+            if (total > 1 && is_dup(g, h)) continue;
+            if (tb == 0) {
+                J.hap_left[hap] = ht_left(R, h);
+                J.hap_right[hap] = ht_right(R, h);
+                J.hap_table[hap] = 0;
+                const int m = hap_rows(R, V, h, 0, ht_nids(R, h), rows);
+                for (int k = 0; k < m; k++) J.rows[row + k] = rows[k];
+                row += m;
+                hap++;
+                J.row_off[hap] = row;
+            } else {
+                const int ne = tb == 2 ? L.n_pexons : L.n_exons;
+                const int32_t *ex = tb == 2 ? L.pexons : L.exons;
+                for (int x = 0; x < ne; x++) {
+                    int32_t l2, r2;
+                    int lo, hi;
+                    if (!exon_clip(R, V, h, ex[2 * x], ex[2 * x + 1], &l2, &r2, &lo, &hi)) continue;
+                    J.hap_left[hap] = l2;
+                    J.hap_right[hap] = r2;
+                    J.hap_table[hap] = tb;
+                    const int m = hap_rows(R, V, h, lo, hi, rows);
+                    for (int k = 0; k < m; k++) J.rows[row + k] = rows[k];
+                    row += m;
+                    hap++;
+                    J.row_off[hap] = row;
+                }
+            }
+        }
+        J.job_off[job + 1] = hap;
+    }
+}
+
+}  // namespace hgtd
