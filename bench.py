@@ -31,6 +31,9 @@ LOCI = [  # gene, backbone length, alleles, allele groups  (SURVEY.md 8d, config
 ]
 READ_LEN, FRAG_LEN, COVERAGE, ERR = 100, 350, 30, 0.005
 DB_SEED = 7
+# GPU stages bracketed with CUDA events (hgt_profile_read) and host stages (hgt_profile_host), see include/hgt.h
+STAGES = ["records", "compat", "class", "counts", "em1", "project", "em2", "walk"]
+HOST_STAGES = ["text_h2d_issue", "tables_linecount_wait", "", "", "", "alloc", "finish_host_and_em2", ""]
 
 
 def build_database(scale=1.0):
@@ -356,6 +359,7 @@ def run_oversized(args):
 
     batch = new_batch()
     batch.prepare()
+    run_gpu(batch)
     tot = batch.totals()
     L.hgt_profile_enable(ctx, 1)
     # the database and the alignment text are millions of long-lived Python objects: park them in the permanent
@@ -384,8 +388,7 @@ def run_oversized(args):
     stage_ms, stage_n = ctypes_array(8, "d"), ctypes_array(8, "q")
     h2d, d2h = ctypes.c_int64(0), ctypes.c_int64(0)
     L.hgt_profile_read(ctx, stage_ms, stage_n, ctypes.byref(h2d), ctypes.byref(d2h))
-    stage = {n: stage_ms[i] / args.steps for i, n in enumerate(
-        ["pileup", "compat", "class", "counts", "em1", "project", "em2"])}
+    stage = {n: stage_ms[i] / args.steps for i, n in enumerate(STAGES)}
     summ = batch.unit_summary(0)
     C, it = summ["n_classes"][0], (em_state["iters"] if world > 1 else summ["em_iters"][0])
     em_bytes = it * (3 * C * (table.wp * 8 + 8) + 6 * table.A * 8)
@@ -464,8 +467,7 @@ def run_oversized(args):
             "e2e": {"value": reads_all / (float(e2e_vec[0]) / 1000.0), "unit": "reads/s",
                     "h2d_bytes_per_step": h2d.value / 2, "d2h_bytes_per_step": d2h.value / 2,
                     "ms_per_step": float(e2e_vec[0]), "input": "host alignment text, %d bytes on rank 0" % len(text),
-                    "host_stage_ms_rank0": {n: host_ms[i] / 2 for i, n in enumerate(
-                        ["intake", "pileup_pack", "pileup_gpu", "walk", "job_pack", "upload_alloc", "finish_host_and_em2"])},
+                    "host_stage_ms_rank0": {n: host_ms[i] / 2 for i, n in enumerate(HOST_STAGES) if n},
                     "host_threads": host_threads, "host_cores": os.cpu_count()},
             "gpu_launches": int(launches), "clocks": clocks.summary(), "example_call": calls[0],
         }
@@ -533,11 +535,17 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    # ---- value: alignments already packed and resident in HBM -----------------------------------------------------
+    # the step's input: every unit's alignment text in ONE page-locked host allocation (the e2e copies start there)
+    pinned = _lib.PinnedText(sum(len(t) + 16 for _, t in units))
+    unit_ptrs = [(li,) + pinned.add(text) for li, text in units]
+
+    # ---- value: alignment text already resident in HBM -> ranked alleles ------------------------------------------------
     batch = TC.Batch(tables, params, True, device=local)
-    for li, text in units:
-        batch.add_unit(li, text)
+    for li, addr, n in unit_ptrs:
+        batch.add_unit_ptr(li, addr, n)
     batch.prepare()
+    batch.execute(stream)
+    batch.finish(stream)
     tot = batch.totals()
     L.hgt_profile_enable(ctx, 1)
     # the database and the alignment text are millions of long-lived Python objects: park them in the permanent
@@ -571,8 +579,7 @@ def main():
     import ctypes
     h2d, d2h = ctypes.c_int64(0), ctypes.c_int64(0)
     L.hgt_profile_read(ctx, stage_ms, stage_n, ctypes.byref(h2d), ctypes.byref(d2h))
-    stage = {n: stage_ms[i] / args.steps for i, n in enumerate(
-        ["pileup", "compat", "class", "counts", "em1", "project", "em2"])}
+    stage = {n: stage_ms[i] / args.steps for i, n in enumerate(STAGES)}
     # EM bookkeeping
     em_iters = em_bytes = 0
     for u in range(len(units)):
@@ -608,8 +615,8 @@ def main():
         a.record()
         t0 = time.perf_counter()
         bt = TC.Batch(tables, params, True, device=local)
-        for li, text in units:
-            bt.add_unit(li, text)
+        for li, addr, n in unit_ptrs:
+            bt.add_unit_ptr(li, addr, n)
         t1 = time.perf_counter()
         bt.prepare()
         t2 = time.perf_counter()
@@ -628,8 +635,7 @@ def main():
         bt.close()
     host_ms = ctypes_array(8, "d")
     L.hgt_profile_host(ctx, host_ms)
-    e2e_host = {n: host_ms[i] / n_e2e for i, n in enumerate(
-        ["intake", "pileup_pack", "pileup_gpu", "walk", "job_pack", "upload_alloc", "finish_host_and_em2"])}
+    e2e_host = {n: host_ms[i] / n_e2e for i, n in enumerate(HOST_STAGES) if n}
     e2e_wall = {n: v / n_e2e for n, v in wall.items()}
     L.hgt_profile_read(ctx, stage_ms, stage_n, ctypes.byref(h2d), ctypes.byref(d2h))
     e2e_vec = torch.tensor([sum(e2e_ms) / len(e2e_ms)], dtype=torch.float64, device="cuda")
@@ -673,7 +679,7 @@ def main():
                                  "share_of_step": a_ms / ms_per_step if ms_per_step else None},
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": h2d.value / n_e2e,
                     "d2h_bytes_per_step": d2h.value / n_e2e, "ms_per_step": float(e2e_vec[0]),
-                    "input": "host alignment text, %d bytes per step on rank 0" % sum(len(t) for _, t in units),
+                    "input": "page-locked host alignment text, %d bytes per step on rank 0" % sum(len(t) for _, t in units),
                     "wall_ms_rank0": e2e_wall, "host_stage_ms_rank0": e2e_host, "host_threads": host_threads, "host_cores": os.cpu_count()},
             "gpu_launches": int(launches),
             "clocks": clocks.summary(),

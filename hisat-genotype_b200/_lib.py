@@ -59,6 +59,10 @@ def lib():
         L.hgt_em_dev.restype = c_int
         L.hgt_em_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p, c_i32, c_i32,
                                  c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+        L.hgt_host_alloc.restype = c_int
+        L.hgt_host_alloc.argtypes = [c_size_t, P(c_void_p)]
+        L.hgt_host_free.restype = None
+        L.hgt_host_free.argtypes = [c_void_p]
         L.hgt_profile_enable.restype = None
         L.hgt_profile_enable.argtypes = [c_void_p, c_int]
         L.hgt_profile_reset.restype = None
@@ -97,6 +101,37 @@ def ctx(device=None):
         check(lib().hgt_init(dev, ctypes.byref(h)))
         _ctx[key] = h
     return _ctx[key]
+
+
+class PinnedText:
+    """Alignment text of many units in ONE page-locked allocation (hgt_host_alloc): the copy engine reads it directly.
+    add(bytes) -> (address, length) to hand to Batch.add_unit_ptr()."""
+
+    def __init__(self, capacity):
+        self.cap = int(capacity)
+        self.used = 0
+        self.base = c_void_p()
+        check(lib().hgt_host_alloc(self.cap, ctypes.byref(self.base)))
+
+    def add(self, data):
+        n = len(data)
+        if self.used + n > self.cap:
+            raise MemoryError("PinnedText: capacity %d exceeded" % self.cap)
+        addr = self.base.value + self.used
+        ctypes.memmove(addr, data, n)
+        self.used += (n + 15) & ~15
+        return addr, n
+
+    def close(self):
+        if self.base is not None and self.base.value:
+            lib().hgt_host_free(self.base)
+            self.base = c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def ptr(a):

@@ -100,6 +100,16 @@ extern "C" void hgt_free(hgt_ctx *ctx) {
     delete ctx;
 }
 
+extern "C" int hgt_host_alloc(size_t n_bytes, void **out) {
+    if (!out) return HGT_ERR_ARG;
+    *out = nullptr;
+    HGT_CUDA(cudaHostAlloc(out, n_bytes ? n_bytes : 16, cudaHostAllocPortable));
+    return HGT_OK;
+}
+extern "C" void hgt_host_free(void *p) {
+    if (p) cudaFreeHost(p);
+}
+
 extern "C" int64_t hgt_launch_count(const hgt_ctx *ctx) { return ctx ? ctx->launches : 0; }
 extern "C" int hgt_sm_count(const hgt_ctx *ctx) { return ctx ? ctx->sm_count : 0; }
 

@@ -251,6 +251,15 @@ static void build_walk_tables(hgt_locus *l) {
         b.add(f->altrow_off); b.add(f->altrow);
     }
     b.add(ex); b.add(pex);                                                   // 33, 34
+    std::vector<int32_t> lbv((size_t)l->L + 2);
+    {
+        size_t k = 0;
+        for (size_t x = 0; x < lbv.size(); x++) {
+            while (k < (size_t)V && h.var_pos[k] < (int32_t)x) k++;
+            lbv[x] = (int32_t)k;
+        }
+    }
+    b.add(lbv);                                                              // 35
     l->wt_blob.swap(b.data);
     l->wt_off.swap(b.off);
     l->wt_hash_mask = cap - 1;
@@ -267,6 +276,7 @@ static hgtd::LocusWalk walk_view(const hgt_locus *l, const unsigned char *base) 
     w.is_hla = l->is_hla ? 1 : 0;
     w.v.V = l->V;
     w.v.pos = reinterpret_cast<const int32_t *>(at(1)); w.v.len = reinterpret_cast<const int32_t *>(at(2));
+    w.v.lb = reinterpret_cast<const int32_t *>(at(35)); w.v.L = l->L;
     w.v.type = at(3); w.v.base = reinterpret_cast<const char *>(at(4)); w.v.flags = at(5);
     w.v.id_off = reinterpret_cast<const int32_t *>(at(6)); w.v.id_pool = reinterpret_cast<const char *>(at(7));
     w.v.id_hash = reinterpret_cast<const int32_t *>(at(8)); w.v.id_hash_mask = l->wt_hash_mask;
@@ -1163,6 +1173,12 @@ static bool stage_a_split() {
     return split;
 }
 
+static int tune_env(const char *name, int dflt) {  // grid-size experiments without a rebuild
+    const char *e = getenv(name);
+    const int v = e ? atoi(e) : dflt;
+    return v > 0 ? v : dflt;
+}
+
 // exclusive scan of n int64 values into out[0..n] (out[n] = total); in == out allowed
 static int dev_scan(hgt_ctx *ctx, cudaStream_t st, const int64_t *in, int64_t n, int64_t *out, DevBuf *partial) {
     if (n <= 0) {
@@ -1449,7 +1465,21 @@ static int reads_execute(hgt_batch *b, cudaStream_t st) {
     hgtk::index_lines_kernel<<<(unsigned)rd.n_chunks, hgtk::LINE_THREADS, 0, st>>>(rd.d_text.as<char>(), rd.text_bytes,
                                                                                rd.d_chunk.as<int64_t>(), rd.d_line_off.as<int64_t>());
     hgtk::unit_lines_kernel<<<(unsigned)((nu + 1 + 127) / 128), 128, 0, st>>>(R);
-    hgtk::parse_kernel<<<line_grid(ctx, N, 256, 8), 256, 0, st>>>(R, P);
+    // shared-memory image of a CTA's 128 lines: 15 % above the average, at least 16 KB (HGT_STAGE_KB overrides)
+    static const int stage_kb_env = tune_env("HGT_STAGE_KB", 0), stage_ctas = tune_env("HGT_STAGE_CTAS_PER_SM", 4);
+    int stage_bytes = (int)std::min<int64_t>(
+        160 << 10, std::max<int64_t>(16 << 10, (rd.text_bytes / std::max<int64_t>(N, 1) * 147 + 1023) / 1024 * 1024 + 1024));
+    if (stage_kb_env > 0) stage_bytes = stage_kb_env << 10;
+    static const int walk_stage_off = tune_env("HGT_WALK_STAGE_OFF", 0);
+    static int stage_attr = 0;
+    if (stage_attr < stage_bytes) {
+        HGT_CUDA(cudaFuncSetAttribute(hgtk::parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_bytes));
+        HGT_CUDA(cudaFuncSetAttribute(hgtk::walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_bytes));
+        stage_attr = stage_bytes;
+    }
+    const int stage_grid = (int)std::max<int64_t>(1, std::min<int64_t>((N + hgtk::STAGE_LINES - 1) / hgtk::STAGE_LINES,
+                                                                     (int64_t)ctx->sm_count * stage_ctas));
+    hgtk::parse_kernel<<<stage_grid, hgtk::STAGE_LINES, stage_bytes, st>>>(R, P, stage_bytes);
     hgtk::pileup_text_kernel<<<line_grid(ctx, N * 32, 256, 8), 256, 0, st>>>(R, rd.d_cnt.as<uint32_t>());
     launches += 4;
     HGT_CUDA(cudaGetLastError());
@@ -1480,7 +1510,10 @@ static int reads_execute(hgt_batch *b, cudaStream_t st) {
     b->timer.begin(ctx, st, 7);
     hgtk::head_kernel<<<line_grid(ctx, N, 256, 8), 256, 0, st>>>(R);
     hgtk::candidate_kernel<<<line_grid(ctx, N, 256, 8), 256, 0, st>>>(R);
-    hgtk::walk_kernel<<<line_grid(ctx, N, 128, 16), 128, 0, st>>>(R, P);
+    if (walk_stage_off)
+        hgtk::walk_kernel<<<line_grid(ctx, N, 128, 16), hgtk::STAGE_LINES, 0, st>>>(R, P, 0);
+    else
+        hgtk::walk_kernel<<<stage_grid, hgtk::STAGE_LINES, stage_bytes, st>>>(R, P, stage_bytes);
     launches = 3;
     ctx->launches += 3;
     HGT_CUDA(cudaGetLastError());
@@ -1750,11 +1783,6 @@ static int fetch_results(hgt_batch *b, cudaStream_t st, int level) {
 }
 
 // ---- stage 2: GPU only, no host synchronisation -----------------------------------------------------------------
-static int tune_env(const char *name, int dflt) {  // grid-size experiments without a rebuild
-    const char *e = getenv(name);
-    const int v = e ? atoi(e) : dflt;
-    return v > 0 ? v : dflt;
-}
 
 template <int WPL>
 static void launch_stage_a(hgt_batch *b, cudaStream_t st, LocusBatch &lb) {
@@ -2543,14 +2571,26 @@ extern "C" int hgt_host_walk(hgt_locus *loc, const char *sam, size_t n_bytes, co
                       line_name(text.data() + line_off[line], (size_t)(line_off[line + 1] - line_off[line])).c_str());
         return status;
     };
-    for (int64_t i = 0; i < N; i++) parse_line(R, P, i);
+    const bool times = getenv("HGT_WALK_TIMES") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto ms = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::milli>(b - a).count();
+    };
+    const auto t0 = now();
+    for (int64_t i = 0; i < N; i++) parse_line(R, P, R.text, i);
+    const auto t1 = now();
     for (int64_t i = 0; i < N; i++) mark_head(R, i);
     for (int64_t i = 0; i < N; i++) mark_candidate(R, i);
-    for (int64_t i = 0; i < N; i++) walk_record<false>(R, P, i, -1);
+    const auto t2 = now();
+    for (int64_t i = 0; i < N; i++) walk_record<false>(R, P, R.text, i, -1);
+    const auto t3 = now();
+    if (times)
+        fprintf(stderr, "emulation: %lld lines, parse %.2f ms, head+cand %.2f ms, walk %.2f ms (%d to the second pass)\n",
+                (long long)N, ms(t0, t1), ms(t1, t2), ms(t2, t3), n_slow);
     if (err != ~0ull) return fail();
     std::vector<SlowRec> slow((size_t)std::max(n_slow, 1));
     R.slow = slow.data();
-    for (int k = 0; k < n_slow; k++) walk_record<true>(R, P, slow_list[k], k);
+    for (int k = 0; k < n_slow; k++) walk_record<true>(R, P, R.text, slow_list[k], k);
     for (int64_t i = 0; i < N; i++) pair_jobs<false>(R, i);
     if (err != ~0ull) return fail();
     for (int k = 0; k < 5; k++) {

@@ -103,6 +103,8 @@ HGT_HD void hd_max_i32(int32_t *p, int32_t v) {
 struct VarTab {
     int V;
     const int32_t *pos, *len;   // [V] Var_list order
+    const int32_t *lb;          // [L+2] number of variants with pos < x (lower_bound by position as a table)
+    int L;
     const uint8_t *type;        // [V] T_*
     const char *base;           // [V] alt base of a single
     const uint8_t *flags;       // [V] bit0 id is a key of Links, bit1 id starts with "hv"
@@ -148,10 +150,15 @@ struct AltEnd {  // element of left_alt_set (pos-ids) / right_alt_set (ids-pos)
     int32_t pos, n;
     int32_t ids[MAXA];
 };
-struct SlowRec {
-    int32_t n_left, n_right, n_mid, pad;
+template <int NS>
+struct EndSets {  // result of identify_ambigious_diffs: alternative left ends x alternative right ends
+    int32_t n_left, n_right;
+    AltEnd left[NS + 1], right[NS + 1];  // + 1: the spare slot a candidate element is built in
+};
+struct SlowRec {  // a record with more than one haplotype, factored: left end x middle x right end
+    int32_t n_mid, pad;
     int32_t mid[MAXI];
-    AltEnd left[MAXS], right[MAXS];
+    EndSets<MAXS> e;
 };
 
 struct LocusJobs {  // job arrays of one locus batch (typing.cu consumes them), all device (or host-emulation) pointers
@@ -190,6 +197,20 @@ struct ReadsView {
     int32_t *max_job_haps;
     LocusJobs *jobs;           // [n_loci]
 };
+
+// index of a new entry of the slow list; on the device the lanes of a warp that arrive together share one atomic
+HGT_HD int32_t slow_list_push(int32_t *counter) {
+#ifdef __CUDA_ARCH__
+    const unsigned act = __activemask();
+    const int lane = threadIdx.x & 31, leader = __ffs((int)act) - 1;
+    int32_t base = 0;
+    if (lane == leader) base = atomicAdd(counter, __popc(act));
+    base = __shfl_sync(act, base, leader);
+    return base + __popc(act & ((1u << lane) - 1u));
+#else
+    return (*counter)++;
+#endif
+}
 
 HGT_HD void set_error(const ReadsView &R, int64_t line, int code) {
     hd_min_u64(R.err, ((unsigned long long)line << 8) | (unsigned long long)code);
@@ -240,13 +261,14 @@ HGT_HD int lower_bound_i32(const int32_t *a, int n, int key) {
 HGT_HD int32_t var_right(const VarTab &v, int r) { return v.type[r] == T_DELETION ? v.pos[r] + v.len[r] - 1 : v.pos[r]; }
 
 // Known `single` variant at pos with this base (core:159-169, 204-214, 949-961) else VAR_UNKNOWN.
+HGT_HD int var_lower_bound(const VarTab &v, int32_t pos) { return pos < 0 ? 0 : (pos > v.L + 1 ? v.V : v.lb[pos]); }
 HGT_HD int32_t known_single(const VarTab &v, int32_t pos, char base) {
-    for (int j = lower_bound_i32(v.pos, v.V, pos); j < v.V && v.pos[j] == pos; j++)
+    for (int j = var_lower_bound(v, pos); j < v.V && v.pos[j] == pos; j++)
         if (v.type[j] == T_SINGLE && v.base[j] == base) return j;
     return VAR_UNKNOWN;
 }
 HGT_HD int32_t known_indel(const VarTab &v, int32_t pos, uint8_t type, int32_t len) {
-    for (int j = lower_bound_i32(v.pos, v.V, pos); j < v.V && v.pos[j] == pos; j++)
+    for (int j = var_lower_bound(v, pos); j < v.V && v.pos[j] == pos; j++)
         if (v.type[j] == type && v.len[j] == len) return j;
     return VAR_UNKNOWN;
 }
@@ -277,7 +299,7 @@ HGT_HD int32_t row_of_chars(const VarTab &v, const char *p, int n) {
 }
 
 // ---- line -> record fields + filters (core:804-852, common:1084-1098) ----------------------------------------------------
-HGT_HD void parse_line(const ReadsView &R, const WalkParams &P, int64_t i) {
+HGT_HD void parse_line(const ReadsView &R, const WalkParams &P, const char *text, int64_t i) {
     const int64_t b = R.line_off[i], e = R.line_off[i + 1] - 1;
     int lo = 0, hi = R.n_units;  // unit = last u with unit_off[u] <= b
     while (hi - lo > 1) {
@@ -288,7 +310,7 @@ HGT_HD void parse_line(const ReadsView &R, const WalkParams &P, int64_t i) {
     R.unit[i] = lo;
     R.st[i] = 0;
     R.slow_slot[i] = -1;
-    const char *s = R.text + b;
+    const char *s = text + b;
     const int64_t n64 = e - b;
     int64_t a = 0;
     while (a < n64 && is_ws(s[a])) a++;
@@ -440,11 +462,18 @@ HGT_HD void mark_candidate(const ReadsView &R, int64_t i) {
 }
 
 // ---- the walk ---------------------------------------------------------------------------------------------------------------
-struct CmpList {
-    int32_t pos[MAXC], len[MAXC], var[MAXC];
-    uint8_t type[MAXC];
+struct CmpList {  // three words per entry: the touched part of a thread's list stays small (local memory, L1-resident)
+    int32_t pos[MAXC], var[MAXC];
+    uint32_t lt[MAXC];  // len << 2 | type
     int n;
 };
+HGT_HD uint8_t c_type(const CmpList &c, int k) { return (uint8_t)(c.lt[k] & 3u); }
+HGT_HD int32_t c_len(const CmpList &c, int k) { return (int32_t)(c.lt[k] >> 2); }
+HGT_HD void c_set(CmpList &c, int k, uint8_t type, int32_t pos, int32_t len, int32_t var) {
+    c.pos[k] = pos;
+    c.var[k] = var;
+    c.lt[k] = ((uint32_t)len << 2) | type;
+}
 
 struct ZsCursor {  // streaming reader of "off|K|id,off|K|id,..."
     const char *s;
@@ -491,70 +520,69 @@ HGT_HD int zs_validate(const char *s, int n) {
 
 HGT_HD bool cmp_push(CmpList &c, uint8_t type, int32_t pos, int32_t len, int32_t var) {
     if (c.n >= MAXC) return false;
-    c.type[c.n] = type;
-    c.pos[c.n] = pos;
-    c.len[c.n] = len;
-    c.var[c.n] = var;
+    c_set(c, c.n, type, pos, len, var);
     c.n++;
     return true;
 }
 
-// error_correct (core:119-243) on the entries seg[0..seg.n) of one M segment, appended to `out` (adjacent matches of
-// the corrected segment merge, core:226-240).  Returns the number of corrections, -1 when `out` overflows.
-HGT_HD int error_correct(const LocusWalk &L, const char *seq, int seq_len, int32_t read_pos, const uint8_t *nt_mask,
-                         const CmpList &seg, CmpList &out) {
-    const int seg_start = out.n;
-    int ncorr = 0;
-    bool ok = true;
-    auto emit = [&](uint8_t type, int32_t pos, int32_t len, int32_t var) {
-        if (type == C_MATCH && out.n > seg_start && out.type[out.n - 1] == C_MATCH) out.len[out.n - 1] += len;
-        else ok &= cmp_push(out, type, pos, len, var);
-    };
-    for (int k = 0; k < seg.n; k++) {
-        const uint8_t ty = seg.type[k];
-        const int32_t epos = seg.pos[k], elen = seg.len[k];
-        if (epos >= L.L) {
-            for (int m = k; m < seg.n; m++) emit(seg.type[m], seg.pos[m], seg.len[m], seg.var[m]);
-            break;
-        }
-        if (ty == C_MATCH) {
-            int32_t last = 0;
-            for (int32_t j = 0; j < elen; j++) {
-                if (read_pos + j >= seq_len || epos + j >= L.L) continue;
-                const char bp = seq[read_pos + j];
-                const uint32_t m = nt_mask[epos + j];
-                const int c = nt_code(bp);
-                if (m != 0 && !(c < 4 && ((m >> c) & 1u))) {
-                    const char nb = (m & (m - 1)) ? 'N' : "ACGT"[ctz32(m)];
-                    ncorr++;
-                    const int32_t vid = nb != 'N' ? known_single(L.v, epos + j, nb) : VAR_UNKNOWN;
-                    if (j > last) emit(C_MATCH, epos + last, j - last, -1);
-                    emit(C_MISMATCH, epos + j, 1, vid);
-                    last = j + 1;
-                }
-            }
-            if (last < elen) emit(C_MATCH, epos + last, elen - last, -1);
-        } else {
-            const char bp = seq[read_pos];
-            const char ref_bp = L.ref[epos];
-            const uint32_t m = nt_mask[epos];
-            const int c = nt_code(bp);
-            uint8_t t2 = ty;
-            int32_t v2 = seg.var[k];
-            if (m != 0 && !(c < 4 && ((m >> c) & 1u))) {
-                const char nb = (m & (m - 1)) ? 'N' : "ACGT"[ctz32(m)];
-                if (nb == 'N') v2 = VAR_UNKNOWN;
-                else if (nb == ref_bp) {
-                    t2 = C_MATCH;
-                    v2 = -1;
-                    ncorr++;
-                } else v2 = known_single(L.v, epos, nb);
-            }
-            emit(t2, epos, t2 == C_MATCH ? 1 : elen, v2);
-        }
-        read_pos += elen;  // the ORIGINAL entry length (core:222)
+// error_correct (core:119-243), streamed: the entries of one M segment are fed one by one as the walk produces them and
+// the corrected entries go straight to `out` (adjacent matches of the corrected segment merge, core:226-240).
+struct EcState {
+    int seg_start;     // out.n when the segment began
+    int32_t read_pos;  // read cursor inside the segment
+    int ncorr;
+    bool verbatim;     // an entry beyond the backbone was met: the rest of the segment is copied (core:136-139)
+    bool ok;           // false when `out` overflowed
+};
+HGT_HD void ec_emit(EcState &E, CmpList &out, uint8_t type, int32_t pos, int32_t len, int32_t var) {
+    if (type == C_MATCH && out.n > E.seg_start && c_type(out, out.n - 1) == C_MATCH)
+        out.lt[out.n - 1] += (uint32_t)len << 2;
+    else E.ok &= cmp_push(out, type, pos, len, var);
+}
+HGT_HD void ec_feed(const LocusWalk &L, const char *seq, int seq_len, const uint8_t *nt_mask, EcState &E, CmpList &out,
+                    uint8_t ty, int32_t epos, int32_t elen, int32_t var) {
+    if (!E.verbatim && epos >= L.L) E.verbatim = true;
+    if (E.verbatim) {
+        ec_emit(E, out, ty, epos, elen, var);
+        return;
     }
-    return ok ? ncorr : -1;
+    const int32_t read_pos = E.read_pos;
+    if (ty == C_MATCH) {
+        int32_t last = 0;
+        for (int32_t j = 0; j < elen; j++) {
+            if (read_pos + j >= seq_len || epos + j >= L.L) continue;
+            const uint32_t m = nt_mask[epos + j];
+            if (m == 0) continue;
+            const int c = nt_code(seq[read_pos + j]);
+            if (!(c < 4 && ((m >> c) & 1u))) {
+                const char nb = (m & (m - 1)) ? 'N' : "ACGT"[ctz32(m)];
+                E.ncorr++;
+                const int32_t vid = nb != 'N' ? known_single(L.v, epos + j, nb) : VAR_UNKNOWN;
+                if (j > last) ec_emit(E, out, C_MATCH, epos + last, j - last, -1);
+                ec_emit(E, out, C_MISMATCH, epos + j, 1, vid);
+                last = j + 1;
+            }
+        }
+        if (last < elen) ec_emit(E, out, C_MATCH, epos + last, elen - last, -1);
+    } else {
+        const char bp = seq[read_pos];
+        const char ref_bp = L.ref[epos];
+        const uint32_t m = nt_mask[epos];
+        const int c = nt_code(bp);
+        uint8_t t2 = ty;
+        int32_t v2 = var;
+        if (m != 0 && !(c < 4 && ((m >> c) & 1u))) {
+            const char nb = (m & (m - 1)) ? 'N' : "ACGT"[ctz32(m)];
+            if (nb == 'N') v2 = VAR_UNKNOWN;
+            else if (nb == ref_bp) {
+                t2 = C_MATCH;
+                v2 = -1;
+                E.ncorr++;
+            } else v2 = known_single(L.v, epos, nb);
+        }
+        ec_emit(E, out, t2, epos, t2 == C_MATCH ? 1 : elen, v2);
+    }
+    E.read_pos += elen;  // the ORIGINAL entry length (core:222)
 }
 
 struct WalkOut {
@@ -565,7 +593,7 @@ struct WalkOut {
 
 // CIGAR x MD x Zs walk (core:876-1095).  Returns E_NONE or the error code.
 HGT_HDN int walk_cigar(const LocusWalk &L, const WalkParams &P, const char *line, const RecFields &f,
-                       const uint8_t *nt_mask, const uint8_t *del_flag, CmpList &cmp, CmpList &seg, WalkOut &w) {
+                       const uint8_t *nt_mask, const uint8_t *del_flag, CmpList &cmp, WalkOut &w) {
     if (f.md_len == 0) return E_NO_MD;
     const char *MD = line + f.md_off;
     const int MDn = f.md_len;
@@ -604,8 +632,20 @@ HGT_HDN int walk_cigar(const LocusWalk &L, const WalkParams &P, const char *line
         if (op == 'M') {
             bool first = true;
             int32_t used = 0;
-            CmpList &dst = P.error_correction ? seg : cmp;
-            if (P.error_correction) seg.n = 0;
+            EcState E;
+            E.seg_start = cmp.n;
+            E.read_pos = read_pos;
+            E.ncorr = 0;
+            E.verbatim = false;
+            E.ok = true;
+            // an entry of the segment: through the error correction, or straight to the list when it is off
+            auto feed = [&](uint8_t ty, int32_t pos, int32_t len, int32_t var) {
+                if (P.error_correction) {
+                    ec_feed(L, seq, seq_len, nt_mask, E, cmp, ty, pos, len, var);
+                    return E.ok;
+                }
+                return cmp_push(cmp, ty, pos, len, var);
+            };
             while (true) {
                 if (!first || md_len == 0) {
                     if (md_i >= MDn) return E_MD_SHORT;
@@ -617,7 +657,7 @@ HGT_HDN int walk_cigar(const LocusWalk &L, const WalkParams &P, const char *line
                 }
                 if (md_len >= length) {
                     md_len -= length;
-                    if (length > used && !cmp_push(dst, C_MATCH, right_pos + used, length - used, -1)) return E_CAP_CMP;
+                    if (length > used && !feed(C_MATCH, right_pos + used, length - used, -1)) return E_CAP_CMP;
                     break;
                 }
                 first = false;
@@ -625,7 +665,7 @@ HGT_HDN int walk_cigar(const LocusWalk &L, const WalkParams &P, const char *line
                 const char base = seq[read_pos + md_len];
                 if (md_i >= MDn || !is_nt(MD[md_i])) return E_MD_BASE;
                 md_i++;
-                if (md_len > used && !cmp_push(dst, C_MATCH, right_pos + used, md_len - used, -1)) return E_CAP_CMP;
+                if (md_len > used && !feed(C_MATCH, right_pos + used, md_len - used, -1)) return E_CAP_CMP;
                 int32_t vid = VAR_UNKNOWN;
                 if (read_pos + md_len == zs_pos && z.have) {
                     if (z.kind != 'S') return E_ZS_NOT_S;
@@ -637,7 +677,7 @@ HGT_HDN int walk_cigar(const LocusWalk &L, const WalkParams &P, const char *line
                 } else {
                     vid = known_single(L.v, right_pos + md_len, base);
                 }
-                if (!cmp_push(dst, C_MISMATCH, right_pos + md_len, 1, vid)) return E_CAP_CMP;
+                if (!feed(C_MISMATCH, right_pos + md_len, 1, vid)) return E_CAP_CMP;
                 used = md_len + 1;
                 md_len += 1;
                 if (md_len == length) {
@@ -645,11 +685,7 @@ HGT_HDN int walk_cigar(const LocusWalk &L, const WalkParams &P, const char *line
                     break;
                 }
             }
-            if (P.error_correction) {
-                const int nc = error_correct(L, seq, seq_len, read_pos, nt_mask, seg, cmp);
-                if (nc < 0) return E_CAP_CMP;
-                w.ncorr += nc;
-            }
+            w.ncorr += E.ncorr;
         } else if (op == 'I') {
             int32_t vid = VAR_UNKNOWN;
             if (read_pos == zs_pos && z.have) {
@@ -702,104 +738,110 @@ HGT_HD bool any_anchor(const AltTab &t, int L, int32_t lo, int32_t hi) {  // con
 }
 HGT_HD bool id_is_hv(const VarTab &v, int32_t var) { return var >= 0 && ((v.flags[var] >> 1) & 1); }
 
-// Does the '-'-joined id string of rows ids[0..m) occur inside the entry's key (common:1734, 1856: str.find)?
-HGT_HD bool key_contains_ids(const VarTab &v, const AltTab &t, int e, const int32_t *ids, int m) {
+// Known variant ids of the entries c[lo..hi] in order (cmp_list2: a non-match entry carries a known row >= 0 or a novel
+// indel code < -1).  get_haplotype_and_seq (common:1679-1700) restated without temporary lists.
+HGT_HD int count_known(const CmpList &c, int lo, int hi) {
+    int n = 0;
+    for (int k = lo; k <= hi; k++) n += (c_type(c, k) != C_MATCH && c.var[k] >= 0);
+    return n;
+}
+HGT_HD bool has_novel(const CmpList &c, int lo, int hi) {
+    for (int k = lo; k <= hi; k++)
+        if (c_type(c, k) != C_MATCH && c.var[k] < -1) return true;
+    return false;
+}
+HGT_HD int32_t seq_len_of(const CmpList &c, int lo, int hi, int L) {
+    int32_t total = 0;
+    for (int k = lo; k <= hi; k++) {
+        const uint8_t ty = c_type(c, k);
+        if (ty == C_MATCH) {
+            const int32_t a = c.pos[k] < 0 ? 0 : (c.pos[k] > L ? L : c.pos[k]);
+            const int32_t e = c.pos[k] + c_len(c, k);
+            const int32_t b = e < 0 ? 0 : (e > L ? L : e);
+            total += b > a ? b - a : 0;
+        } else if (ty == C_MISMATCH) {
+            total += 1;
+        }
+    }
+    return total;
+}
+
+// Does the '-'-joined id string of the known ids of c[lo..hi] occur inside the entry's key (common:1734, 1856: str.find)?
+HGT_HD bool key_contains_ids(const VarTab &v, const AltTab &t, int e, const CmpList &c, int lo, int hi, int m) {
     const char *key = t.key_pool + t.key_off[e];
     const int kn = t.key_off[e + 1] - t.key_off[e];
     int total = m - 1;
-    for (int k = 0; k < m; k++) total += v.id_off[ids[k] + 1] - v.id_off[ids[k]];
+    for (int k = lo; k <= hi; k++)
+        if (c_type(c, k) != C_MATCH && c.var[k] >= 0) total += v.id_off[c.var[k] + 1] - v.id_off[c.var[k]];
     for (int s = 0; s + total <= kn; s++) {
         int p = s;
-        bool ok = true;
-        for (int k = 0; k < m && ok; k++) {
-            if (k) ok = key[p++] == '-';
-            const int32_t o = v.id_off[ids[k]], n = v.id_off[ids[k] + 1] - o;
-            for (int c = 0; c < n && ok; c++) ok = key[p++] == v.id_pool[o + c];
+        bool ok = true, first = true;
+        for (int k = lo; k <= hi && ok; k++) {
+            if (c_type(c, k) == C_MATCH || c.var[k] < 0) continue;
+            if (!first) ok = key[p++] == '-';
+            first = false;
+            const int32_t o = v.id_off[c.var[k]], n = v.id_off[c.var[k] + 1] - o;
+            for (int q = 0; q < n && ok; q++) ok = key[p++] == v.id_pool[o + q];
         }
         if (ok) return true;
     }
     return false;
 }
 
-HGT_HD bool end_equal(const AltEnd &x, int32_t pos, const int32_t *ids, int n) {
-    if (x.pos != pos || x.n != n) return false;
-    for (int k = 0; k < n; k++)
-        if (x.ids[k] != ids[k]) return false;
+// A candidate element of left_alt_set / right_alt_set is built in the spare slot set[n_set] and committed unless an equal
+// element is already there (set semantics); returns false when the set is full.
+HGT_HD bool end_id(AltEnd &x, int32_t id) {
+    if (x.n >= MAXA) return false;
+    x.ids[x.n++] = id;
     return true;
 }
-// set.add((pos, ids)); returns false on capacity overflow
-HGT_HD bool end_add(AltEnd *set, int32_t &n_set, int32_t pos, const int32_t *ids, int n) {
-    for (int k = 0; k < n_set; k++)
-        if (end_equal(set[k], pos, ids, n)) return true;
-    if (n_set >= MAXS || n > MAXA) return false;
-    set[n_set].pos = pos;
-    set[n_set].n = n;
-    for (int k = 0; k < n; k++) set[n_set].ids[k] = ids[k];
+HGT_HD bool end_commit(AltEnd *set, int32_t &n_set, int cap) {
+    const AltEnd &x = set[n_set];
+    for (int k = 0; k < n_set; k++) {
+        if (set[k].pos != x.pos || set[k].n != x.n) continue;
+        bool eq = true;
+        for (int q = 0; q < x.n && eq; q++) eq = set[k].ids[q] == x.ids[q];
+        if (eq) return true;
+    }
+    if (n_set >= cap) return false;
     n_set++;
     return true;
 }
 
 // identify_ambigious_diffs (common:1663-1955) on cmp_list2 `c`; alternative ends go to S.left / S.right, the kept
-// entry range to *cmp_left / *cmp_right.  Returns E_NONE or an error code.
-HGT_HDN int identify_ambiguous(const LocusWalk &L, const CmpList &c, SlowRec &S, int32_t *cmp_left_out, int32_t *cmp_right_out) {
+// entry range to *cmp_left / *cmp_right.  Returns E_NONE or an error code (E_CAP_ENDS: S is too small).
+template <int NS>
+HGT_HDN int identify_ambiguous(const LocusWalk &L, const CmpList &c, EndSets<NS> &S, int32_t *cmp_left_out, int32_t *cmp_right_out) {
     const VarTab &V = L.v;
     const int n = c.n;
     int32_t cmp_left = 0, cmp_right = n - 1;
     S.n_left = S.n_right = 0;
-    const int32_t left = c.pos[0], right = c.pos[n - 1] + c.len[n - 1] - 1;
-    // prefix sums over the entries: known ids, novel ids and sequence length of c[0..i)  (get_haplotype_and_seq,
-    // common:1679-1700)
-    int32_t all_ids[MAXC];
-    int32_t idn[MAXC + 1], nov[MAXC + 1], sl[MAXC + 1];
-    {
-        int na = 0;
-        idn[0] = nov[0] = sl[0] = 0;
-        for (int i = 0; i < n; i++) {
-            int32_t len = 0;
-            if (c.type[i] == C_MATCH) {
-                const int32_t a = c.pos[i] < 0 ? 0 : (c.pos[i] > L.L ? L.L : c.pos[i]);
-                const int32_t e = c.pos[i] + c.len[i];
-                const int32_t b = e < 0 ? 0 : (e > L.L ? L.L : e);
-                len = b > a ? b - a : 0;
-            } else if (c.type[i] == C_MISMATCH) {
-                len = 1;
-            }
-            int32_t novel = 0;
-            if (c.type[i] != C_MATCH && c.var[i] != VAR_UNKNOWN) {
-                if (c.var[i] >= 0) all_ids[na++] = c.var[i];
-                else novel = 1;
-            }
-            idn[i + 1] = na;
-            nov[i + 1] = nov[i] + novel;
-            sl[i + 1] = sl[i] + len;
-        }
-    }
-    int32_t tmp[MAXA + MAXC];
+    const int32_t left = c.pos[0], right = c.pos[n - 1] + c_len(c, n - 1) - 1;
     bool cap_ok = true;
     // ---- left end ------------------------------------------------------------------------------------------
     bool found = false;
     if (L.al.n > 0) {
         const AltTab &T = L.al;
         for (int i = n - 1; i >= 0; i--) {
-            if (c.type[i] != C_MATCH) {
-                if (c.type[i] == C_INSERTION || !id_is_hv(V, c.var[i])) continue;
+            const uint8_t ty = c_type(c, i);
+            if (ty != C_MATCH) {
+                if (ty == C_INSERTION || !id_is_hv(V, c.var[i])) continue;
             }
             const int32_t cur_left = c.pos[i];
-            const int32_t cur_right = (c.type[i] == C_MATCH || c.type[i] == C_DELETION) ? c.pos[i] + c.len[i] - 1 : c.pos[i];
+            const int32_t cur_right = (ty == C_MATCH || ty == C_DELETION) ? c.pos[i] + c_len(c, i) - 1 : c.pos[i];
             if (!any_anchor(T, L.L, cur_left, cur_right)) continue;
             int start = lower_bound_i32(T.anchor, T.n, cur_right + 1) + 1;
             if (start > T.n) start = T.n;
-            const bool has_novel = nov[i + 1] > 0;
-            const int32_t cur_len = sl[i + 1];
-            const int32_t *cur_ids = all_ids;
-            const int n_cur = idn[i + 1];
-            const int n_ids = n_cur + (has_novel ? 1 : 0);  // novel ids count as ids that never match
+            const bool novel = has_novel(c, 0, i);
+            const int32_t cur_len = seq_len_of(c, 0, i, L.L);
+            const int n_cur = count_known(c, 0, i);
+            const int n_ids = n_cur + (novel ? 1 : 0);  // novel ids count as ids that never match
             bool hit = false;
             for (int j = start - 1; j >= 0; j--) {
                 if (T.anchor[j] < cur_left) break;
                 if (T.anchor[j] > cur_right) continue;
                 if (n_ids > 0) {
-                    if (has_novel || !key_contains_ids(V, T, j, cur_ids, n_cur)) continue;
+                    if (novel || !key_contains_ids(V, T, j, c, 0, i, n_cur)) continue;
                 }
                 const int32_t *tok_row = T.tok_row + T.tok_off[j], *tok_num = T.tok_num + T.tok_off[j];
                 const int ntok = T.tok_off[j + 1] - T.tok_off[j] - 1;  // key.split('-')[:-1]
@@ -836,16 +878,15 @@ HGT_HDN int identify_ambiguous(const LocusWalk &L, const CmpList &c, SlowRec &S,
                     }
                     if (first_kept < nrow) {
                         const int32_t seq_left = cur_len - seq_pos - 1;
-                        int m = 0;
-                        if (nrow - first_kept > MAXA) return E_CAP_ENDS;
-                        for (int t = first_kept; t < nrow; t++) tmp[m++] = rows[t];
+                        AltEnd &x = S.left[S.n_left];
+                        x.pos = cur_pos - seq_left;
+                        x.n = 0;
+                        bool ok = true;
+                        for (int t = first_kept; t < nrow; t++) ok &= end_id(x, rows[t]);
                         if (found)
                             for (int q = i + 1; q < cmp_left; q++)
-                                if (c.type[q] != C_MATCH && id_is_hv(V, c.var[q])) {
-                                    if (m >= MAXA + MAXC) return E_CAP_IDS;
-                                    tmp[m++] = c.var[q];
-                                }
-                        cap_ok &= end_add(S.left, S.n_left, cur_pos - seq_left, tmp, m);
+                                if (c_type(c, q) != C_MATCH && id_is_hv(V, c.var[q])) ok &= end_id(x, c.var[q]);
+                        cap_ok &= ok && end_commit(S.left, S.n_left, NS);
                     }
                 }
             }
@@ -853,37 +894,47 @@ HGT_HDN int identify_ambiguous(const LocusWalk &L, const CmpList &c, SlowRec &S,
                 if (!found) {
                     cmp_left = i + 1;
                     // cur_ht_str; a hit implies the slice holds no novel id (the substring test would fail)
-                    cap_ok &= end_add(S.left, S.n_left, left, cur_ids, n_cur);
+                    AltEnd &x = S.left[S.n_left];
+                    x.pos = left;
+                    x.n = 0;
+                    bool ok = true;
+                    for (int q = 0; q <= i; q++)
+                        if (c_type(c, q) != C_MATCH && c.var[q] >= 0) ok &= end_id(x, c.var[q]);
+                    cap_ok &= ok && end_commit(S.left, S.n_left, NS);
                 }
                 found = true;
             }
         }
     }
-    if (!found) cap_ok &= end_add(S.left, S.n_left, left, tmp, 0);
+    if (!found) {
+        S.left[S.n_left].pos = left;
+        S.left[S.n_left].n = 0;
+        cap_ok &= end_commit(S.left, S.n_left, NS);
+    }
     // ---- right end -----------------------------------------------------------------------------------------
     found = false;
     if (L.ar.n > 0) {
         const AltTab &T = L.ar;
         for (int i = 0; i < n; i++) {
-            if (c.type[i] != C_MATCH) {
-                if (c.type[i] == C_INSERTION || !id_is_hv(V, c.var[i])) continue;
+            const uint8_t ty = c_type(c, i);
+            if (ty != C_MATCH) {
+                if (ty == C_INSERTION || !id_is_hv(V, c.var[i])) continue;
             }
             const int32_t cur_left = c.pos[i];
-            const int32_t cur_right = (c.type[i] == C_MATCH || c.type[i] == C_DELETION) ? c.pos[i] + c.len[i] - 1 : c.pos[i];
+            const int32_t cur_right = (ty == C_MATCH || ty == C_DELETION) ? c.pos[i] + c_len(c, i) - 1 : c.pos[i];
             if (!any_anchor(T, L.L, cur_left, cur_right)) continue;
             const int start = lower_bound_i32(T.anchor, T.n, cur_left);
             if (start >= T.n || T.anchor[start] > cur_right) continue;
-            const bool has_novel = nov[n] - nov[i] > 0;
-            const int32_t cur_len = sl[n] - sl[i];
-            const int32_t *cur_ids = all_ids + idn[i];
-            const int n_cur = idn[n] - idn[i];
-            const int n_ids = n_cur + (has_novel ? 1 : 0);
+            const bool novel = has_novel(c, i, n - 1);
+            const int32_t cur_len = seq_len_of(c, i, n - 1, L.L);
+            const int n_cur = count_known(c, i, n - 1);
+            const int n_ids = n_cur + (novel ? 1 : 0);
             bool hit = false;
             for (int j = start; j < T.n; j++) {
                 if (T.anchor[j] > cur_right) break;
                 if (T.anchor[j] < cur_left) continue;
                 if (n_ids > 0) {
-                    if (has_novel || !key_contains_ids(V, T, j, cur_ids, n_cur)) continue;
+                    if (novel || !key_contains_ids(V, T, j, c, i, n - 1, n_cur)) continue;
                 }
                 const int32_t *tok_row = T.tok_row + T.tok_off[j], *tok_num = T.tok_num + T.tok_off[j];
                 const int ntok = T.tok_off[j + 1] - T.tok_off[j] - 1;  // key.split('-')[1:]
@@ -918,35 +969,43 @@ HGT_HDN int identify_ambiguous(const LocusWalk &L, const CmpList &c, SlowRec &S,
                     }
                     if (kept > 0) {
                         const int32_t seq_left = cur_len - seq_pos - 1;
-                        int m = 0;
+                        AltEnd &x = S.right[S.n_right];
+                        x.pos = cur_pos + seq_left;
+                        x.n = 0;
+                        bool ok = true;
                         if (found)
                             for (int q = cmp_right + 1; q < i; q++)
-                                if (c.type[q] != C_MATCH && id_is_hv(V, c.var[q])) {
-                                    if (m >= MAXC) return E_CAP_IDS;
-                                    tmp[m++] = c.var[q];
-                                }
-                        for (int t = 0; t < kept; t++) {
-                            if (m >= MAXA + MAXC) return E_CAP_IDS;
-                            tmp[m++] = rows[t];
-                        }
-                        cap_ok &= end_add(S.right, S.n_right, cur_pos + seq_left, tmp, m);
+                                if (c_type(c, q) != C_MATCH && id_is_hv(V, c.var[q])) ok &= end_id(x, c.var[q]);
+                        for (int t = 0; t < kept; t++) ok &= end_id(x, rows[t]);
+                        cap_ok &= ok && end_commit(S.right, S.n_right, NS);
                     }
                 }
             }
             if (hit) {
                 if (!found) {
                     cmp_right = i - 1;
-                    cap_ok &= end_add(S.right, S.n_right, right, cur_ids, n_cur);
+                    AltEnd &x = S.right[S.n_right];
+                    x.pos = right;
+                    x.n = 0;
+                    bool ok = true;
+                    for (int q = i; q < n; q++)
+                        if (c_type(c, q) != C_MATCH && c.var[q] >= 0) ok &= end_id(x, c.var[q]);
+                    cap_ok &= ok && end_commit(S.right, S.n_right, NS);
                 }
                 found = true;
             }
         }
     }
-    if (!found) cap_ok &= end_add(S.right, S.n_right, right, tmp, 0);
+    if (!found) {
+        S.right[S.n_right].pos = right;
+        S.right[S.n_right].n = 0;
+        cap_ok &= end_commit(S.right, S.n_right, NS);
+    }
     if (cmp_right < cmp_left) {
         cmp_left = 0;
-        S.n_left = 0;
-        cap_ok &= end_add(S.left, S.n_left, left, tmp, 0);
+        S.left[0].pos = left;
+        S.left[0].n = 0;
+        S.n_left = 1;
     }
     if (!cap_ok) return E_CAP_ENDS;
     // check_amb_uniqueness (validation_check.py:313-341): no non-empty id list twice across both sides
@@ -966,20 +1025,21 @@ HGT_HDN int identify_ambiguous(const LocusWalk &L, const CmpList &c, SlowRec &S,
     return E_NONE;
 }
 
-// One candidate record through the walk.  SLOW = false: common case; records with an Alts anchor under one of their
-// ends are queued (slow_list) instead.  SLOW = true: line i is such a record and slot its SlowRec.
+// One candidate record through the walk.  SLOW = false: every record; the few that come out of identify_ambigious_diffs
+// with more than one haplotype (or need more room) are queued (slow_list).  SLOW = true: line i is such a record and
+// slot its SlowRec.  `text` = base the line offsets are relative to (the arena, or its shared-memory image).
 template <bool SLOW>
-HGT_HD void walk_record(const ReadsView &R, const WalkParams &P, int64_t i, int32_t slot) {
+HGT_HD void walk_record(const ReadsView &R, const WalkParams &P, const char *text, int64_t i, int32_t slot) {
     const uint16_t st = R.st[i];
     if (!(st & ST_CAND)) return;
     const RecFields f = R.rec[i];
     const int u = R.unit[i];
     const LocusWalk &L = R.loci[R.unit_locus[u]];
-    const char *line = R.text + R.line_off[i];
+    const char *line = text + R.line_off[i];
     const uint8_t *nt_mask = R.nt_mask + R.unit_pos0[u], *del_flag = R.del_flag + R.unit_pos0[u];
-    CmpList cmp, seg;
+    CmpList cmp;
     WalkOut w;
-    const int rc = walk_cigar(L, P, line, f, nt_mask, del_flag, cmp, seg, w);
+    const int rc = walk_cigar(L, P, line, f, nt_mask, del_flag, cmp, w);
     if (rc != E_NONE) {
         set_error(R, i, rc);
         return;
@@ -992,31 +1052,22 @@ HGT_HD void walk_record(const ReadsView &R, const WalkParams &P, int64_t i, int3
     // matches below.  cmp_list2 (core:1351-1368) in place.
     int n2 = 0;
     for (int k = 0; k < cmp.n; k++) {
-        const uint8_t ty = cmp.type[k];
+        const uint8_t ty = c_type(cmp, k);
+        const int32_t pos = cmp.pos[k], len = c_len(cmp, k);
         int32_t var = cmp.var[k];
         if ((ty == C_INSERTION || ty == C_DELETION) && var == VAR_UNKNOWN) {
-            if (!novel_fits(cmp.pos[k], cmp.len[k])) {
+            if (!novel_fits(pos, len)) {
                 set_error(R, i, E_NOVEL_RANGE);
                 return;
             }
-            var = novel_code(ty == C_INSERTION, cmp.pos[k], cmp.len[k]);
+            var = novel_code(ty == C_INSERTION, pos, len);
         }
         if (ty == C_MATCH || (ty == C_MISMATCH && var < 0)) {
-            const int32_t ln = ty == C_MATCH ? cmp.len[k] : 1;
-            if (n2 > 0 && cmp.type[n2 - 1] == C_MATCH) cmp.len[n2 - 1] += ln;
-            else {
-                cmp.type[n2] = C_MATCH;
-                cmp.pos[n2] = cmp.pos[k];
-                cmp.len[n2] = ln;
-                cmp.var[n2] = -1;
-                n2++;
-            }
+            const int32_t ln = ty == C_MATCH ? len : 1;
+            if (n2 > 0 && c_type(cmp, n2 - 1) == C_MATCH) cmp.lt[n2 - 1] += (uint32_t)ln << 2;
+            else c_set(cmp, n2++, C_MATCH, pos, ln, -1);
         } else {
-            cmp.type[n2] = ty;
-            cmp.pos[n2] = cmp.pos[k];
-            cmp.len[n2] = cmp.len[k];
-            cmp.var[n2] = var;
-            n2++;
+            c_set(cmp, n2++, ty, pos, len, var);
         }
     }
     cmp.n = n2;
@@ -1028,41 +1079,70 @@ HGT_HD void walk_record(const ReadsView &R, const WalkParams &P, int64_t i, int3
         // does identify_ambigious_diffs have anything to look at?  (an Alts anchor inside an eligible entry)
         bool amb = false;
         for (int k = 0; k < n2 && !amb; k++) {
-            if (cmp.type[k] != C_MATCH && (cmp.type[k] == C_INSERTION || !id_is_hv(L.v, cmp.var[k]))) continue;
+            const uint8_t ty = c_type(cmp, k);
+            if (ty != C_MATCH && (ty == C_INSERTION || !id_is_hv(L.v, cmp.var[k]))) continue;
             const int32_t cl = cmp.pos[k];
-            const int32_t cr = (cmp.type[k] == C_MATCH || cmp.type[k] == C_DELETION) ? cl + cmp.len[k] - 1 : cl;
+            const int32_t cr = (ty == C_MATCH || ty == C_DELETION) ? cl + c_len(cmp, k) - 1 : cl;
             if (L.al.n > 0 && any_anchor(L.al, L.L, cl, cr)) amb = true;
             if (L.ar.n > 0 && any_anchor(L.ar, L.L, cl, cr)) amb = true;
         }
+        int32_t *ids_out = R.h_ids + i * MAXI;
+        int m = 0;
+        int32_t h_left = cmp.pos[0], h_right = cmp.pos[n2 - 1] + c_len(cmp, n2 - 1) - 1;
+        int32_t cl = 0, cr = n2 - 1;
+        bool ok = true;
         if (amb) {
-            R.slow_list[hd_add_i32(R.n_slow, 1)] = (int32_t)i;
+            // identify_ambigious_diffs with room for two ends per side: nearly every read that covers an anchor still
+            // comes out with ONE haplotype; the others (and only they) go to the second pass, which has the room
+            EndSets<2> S;
+            const int e = identify_ambiguous<2>(L, cmp, S, &cl, &cr);
+            if (e == E_CAP_ENDS || (e == E_NONE && S.n_left * S.n_right > 1)) {
+                R.slow_list[slow_list_push(R.n_slow)] = (int32_t)i;
+                return;
+            }
+            if (e != E_NONE) {
+                set_error(R, i, e);
+                return;
+            }
+            h_left = S.left[0].pos;
+            h_right = S.right[0].pos;
+            for (int k = 0; k < S.left[0].n; k++) ids_out[m++] = S.left[0].ids[k];  // MAXA <= MAXI
+            for (int k = cl; k <= cr; k++)
+                if (c_type(cmp, k) != C_MATCH) {
+                    if (m < MAXI) ids_out[m++] = cmp.var[k];
+                    else ok = false;
+                }
+            for (int k = 0; k < S.right[0].n; k++) {
+                if (m < MAXI) ids_out[m++] = S.right[0].ids[k];
+                else ok = false;
+            }
+        } else {
+            for (int k = 0; k < n2; k++)
+                if (c_type(cmp, k) != C_MATCH) {
+                    if (m < MAXI) ids_out[m++] = cmp.var[k];
+                    else ok = false;
+                }
+        }
+        if (!ok) {
+            set_error(R, i, E_CAP_IDS);
             return;
         }
-        int m = 0;
-        for (int k = 0; k < n2; k++)
-            if (cmp.type[k] != C_MATCH) {
-                if (m >= MAXI) {
-                    set_error(R, i, E_CAP_IDS);
-                    return;
-                }
-                R.h_ids[i * MAXI + m++] = cmp.var[k];
-            }
-        R.h_left[i] = cmp.pos[0];
-        R.h_right[i] = cmp.pos[n2 - 1] + cmp.len[n2 - 1] - 1;
+        R.h_left[i] = h_left;
+        R.h_right[i] = h_right;
         R.h_n[i] = m;
         R.st[i] = st | ST_SURV;
         hd_add_u64(&R.unit_reads[u], 1ull);
     } else {
         SlowRec &S = R.slow[slot];
         int32_t cl = 0, cr = n2 - 1;
-        const int e = identify_ambiguous(L, cmp, S, &cl, &cr);
+        const int e = identify_ambiguous<MAXS>(L, cmp, S.e, &cl, &cr);
         if (e != E_NONE) {
             set_error(R, i, e);
             return;
         }
         int m = 0;
         for (int k = cl; k <= cr; k++)
-            if (cmp.type[k] != C_MATCH) {
+            if (c_type(cmp, k) != C_MATCH) {
                 if (m >= MAXI) {
                     set_error(R, i, E_CAP_IDS);
                     return;
@@ -1081,20 +1161,20 @@ struct HtRef {  // one haplotype of a record: alternative left end a, alternativ
     int64_t line;
     int32_t slot, a, b;
 };
-HGT_HD int32_t ht_left(const ReadsView &R, const HtRef &h) { return h.slot < 0 ? R.h_left[h.line] : R.slow[h.slot].left[h.a].pos; }
-HGT_HD int32_t ht_right(const ReadsView &R, const HtRef &h) { return h.slot < 0 ? R.h_right[h.line] : R.slow[h.slot].right[h.b].pos; }
+HGT_HD int32_t ht_left(const ReadsView &R, const HtRef &h) { return h.slot < 0 ? R.h_left[h.line] : R.slow[h.slot].e.left[h.a].pos; }
+HGT_HD int32_t ht_right(const ReadsView &R, const HtRef &h) { return h.slot < 0 ? R.h_right[h.line] : R.slow[h.slot].e.right[h.b].pos; }
 HGT_HD int ht_nids(const ReadsView &R, const HtRef &h) {
     if (h.slot < 0) return R.h_n[h.line];
     const SlowRec &S = R.slow[h.slot];
-    return S.left[h.a].n + S.n_mid + S.right[h.b].n;
+    return S.e.left[h.a].n + S.n_mid + S.e.right[h.b].n;
 }
 HGT_HD int32_t ht_id(const ReadsView &R, const HtRef &h, int k) {
     if (h.slot < 0) return R.h_ids[h.line * MAXI + k];
     const SlowRec &S = R.slow[h.slot];
-    if (k < S.left[h.a].n) return S.left[h.a].ids[k];
-    k -= S.left[h.a].n;
+    if (k < S.e.left[h.a].n) return S.e.left[h.a].ids[k];
+    k -= S.e.left[h.a].n;
     if (k < S.n_mid) return S.mid[k];
-    return S.right[h.b].ids[k - S.n_mid];
+    return S.e.right[h.b].ids[k - S.n_mid];
 }
 HGT_HD bool ht_equal(const ReadsView &R, const HtRef &x, const HtRef &y) {
     if (ht_left(R, x) != ht_left(R, y) || ht_right(R, x) != ht_right(R, y)) return false;
@@ -1234,7 +1314,7 @@ HGT_HD void pair_jobs(const ReadsView &R, int64_t i) {
     int total = 0;
     for (int r = 0; r < nrec; r++) {
         const int32_t slot = R.slow_slot[recs[r]];
-        total += slot < 0 ? 1 : R.slow[slot].n_left * R.slow[slot].n_right;
+        total += slot < 0 ? 1 : R.slow[slot].e.n_left * R.slow[slot].e.n_right;
     }
     auto ht_at = [&](int g) {
         HtRef h;
@@ -1243,13 +1323,13 @@ HGT_HD void pair_jobs(const ReadsView &R, int64_t i) {
         h.a = h.b = 0;
         for (int r = 0; r < nrec; r++) {
             const int32_t slot = R.slow_slot[recs[r]];
-            const int cnt = slot < 0 ? 1 : R.slow[slot].n_left * R.slow[slot].n_right;
+            const int cnt = slot < 0 ? 1 : R.slow[slot].e.n_left * R.slow[slot].e.n_right;
             if (g < cnt) {
                 h.line = recs[r];
                 h.slot = slot;
                 if (slot >= 0) {
-                    h.a = g / R.slow[slot].n_right;
-                    h.b = g % R.slow[slot].n_right;
+                    h.a = g / R.slow[slot].e.n_right;
+                    h.b = g % R.slow[slot].e.n_right;
                 }
                 return h;
             }

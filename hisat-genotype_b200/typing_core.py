@@ -187,6 +187,15 @@ class Batch:
         self.unit_locus.append(locus_index)
         return int(u)
 
+    def add_unit_ptr(self, locus_index, address, n_bytes):
+        """Alignment text that already lives in (ideally page-locked, _lib.PinnedText) host memory; the caller keeps it
+        valid until prepare() returns."""
+        u = lib().hgt_batch_add_unit(self.handle, locus_index, ctypes.c_void_p(address), n_bytes)
+        if u < 0:
+            _lib.check(int(u))
+        self.unit_locus.append(locus_index)
+        return int(u)
+
     def _call(self, rc):
         if rc == _lib.HGT_ERR_AMBIGUITY:
             raise SystemExit("Error: %s" % _lib.last_error())

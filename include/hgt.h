@@ -53,15 +53,17 @@ void hgt_free(hgt_ctx *ctx);
 int64_t hgt_launch_count(const hgt_ctx *ctx);
 int hgt_sm_count(const hgt_ctx *ctx);
 /* Measurement hooks for bench.py: with profiling on, batch execute/finish bracket each GPU stage with CUDA
- * events on the launching stream.  stage_ms / stage_launches [8]: pileup, haplotype->allele-set (compat),
- * per-pair class + de-duplication, Gene_counts, first-level EM, projection, second-level EM, unused.
+ * events on the launching stream.  stage_ms / stage_launches [8]: [0] line index + record parse + pileup, [1]
+ * haplotype->allele-set (compat), [2] per-pair class + de-duplication, [3] Gene_counts, [4] first-level EM, [5]
+ * projection, [6] second-level EM, [7] run heads + mate de-dup + walk + ambiguity pass + pair jobs.
  * h2d/d2h_bytes count every host<->device copy the library issued since the last reset. */
 void hgt_profile_enable(hgt_ctx *ctx, int on);
 void hgt_profile_reset(hgt_ctx *ctx);
 void hgt_profile_read(const hgt_ctx *ctx, double *stage_ms, int64_t *stage_launches, int64_t *h2d_bytes,
                       int64_t *d2h_bytes);
-/* wall-clock milliseconds the host stages of prepare/finish took since the last reset, host_ms[8]: record intake,
- * pileup packing, pileup kernels + wait, walk, job packing, uploads + allocation, finish-side host work, unused */
+/* wall-clock milliseconds the host stages of prepare/execute/finish took since the last reset, host_ms[8]: [0] text to
+ * the device (issue of the copies, staging of pageable input), [1] unit tables + line count (includes the wait for the
+ * copies), [5] table / pool allocation, [6] finish-side host work; the others are unused */
 void hgt_profile_host(const hgt_ctx *ctx, double *host_ms);
 
 /* Phase tracing of the EM kernels (tooling, not on the typing path): returns in cycles16 the SM clock cycles CTA 0 of
@@ -70,6 +72,12 @@ void hgt_profile_host(const hgt_ctx *ctx, double *host_ms);
  * kernel, then [9] sweeps and [10] launches, and over all CTAs [11] the sum and [12] the maximum of their lifetimes in
  * ns and [13] their number; clears the counters and switches tracing on/off.  cycles16 may be NULL. */
 int hgt_em_trace(hgt_ctx *ctx, int32_t enable, uint64_t *cycles16);
+
+/* Page-locked host memory for alignment text: hgt_batch_add_unit() accepts any host pointer, but text that lives in
+ * memory from hgt_host_alloc() (or any other page-locked allocation, e.g. cudaHostAlloc / torch pin_memory) is read by
+ * the GPU's copy engine directly; pageable text is first assembled in a page-locked staging arena by host threads. */
+int hgt_host_alloc(size_t n_bytes, void **out);
+void hgt_host_free(void *p);
 
 /* ---- stage (b): EM abundance ----------------------------------------------------------------------------
  * Replaces single_abundance(Gene_cmpt, remove_low_abundance_allele, Gene_length)
@@ -181,9 +189,9 @@ typedef struct {
     int32_t allow_discordant;  /* --discordant */
     int32_t simulation;        /* read ids are cut at the first '|' (core:808-809) */
     int32_t base_locus;        /* 0 unless typing inside a genotype genome (core:437-441) */
-    int32_t n_threads;         /* host threads for record intake and walk; <= 0 = library default */
-    int32_t chunk_bytes;       /* alignment text of a unit is walked in tasks of about this size, cut where the read
-                                  id changes (input is name sorted); <= 0 = library default (128 KiB) */
+    int32_t n_threads;         /* host threads that stage PAGEABLE input text into page-locked memory; <= 0 = library
+                                  default; unused when the text is already page-locked */
+    int32_t chunk_bytes;       /* unused (kept for ABI stability: the record walk no longer runs in host tasks) */
 } hgt_params;
 
 /* ctx may be NULL: the locus then only carries the host tables (used by hgt_host_walk). */
@@ -211,12 +219,16 @@ int hgt_typing_em(hgt_ctx *ctx, const hgt_typing *t, int32_t table, const uint64
 /* ---- batches of (sample, locus) units ----------------------------------------------------------------------
  * The production shape of the path: the reference types one (sample, locus) at a time inside Pool workers
  * (hisatgenotype:613-665, core:370); here any number of units over any number of loci go through the GPU
- * together.  prepare = text intake, pileup (GPU), walk (host threads), upload of the packed haplotype jobs;
- * execute = GPU only, no host synchronisation: haplotype->allele-set, per-pair class, class de-duplication,
- * Gene_counts and the first-level EM (exon table on the hla path, Gene table otherwise) for every unit;
+ * together.  prepare = the alignment text goes to the device as it is (one arena, one line count);
+ * execute = GPU only: line index, record parse + filters, pileup, mate de-dup, CIGAR x MD x Zs walk with error
+ * correction, ambiguity expansion, pair jobs, haplotype->allele-set, per-pair class, class de-duplication, Gene_counts
+ * and the first-level EM (exon table on the hla path, Gene table otherwise) for every unit; the host only reads back
+ * sizes (three small synchronisations) to allocate the next buffers;
  * finish = results back and, on the hla path, projection + second-level EM (core:1739-1782).
- * execute and finish may be repeated on a prepared batch (bench).  Table 3 = the projected Gene table the
- * second-level EM ran on.  sam_text buffers must stay valid until prepare returns. */
+ * execute and finish may be repeated on a prepared batch (bench: text resident in HBM).  Table 3 = the projected Gene
+ * table the second-level EM ran on.  sam_text buffers must stay valid until prepare returns.  The text of one unit
+ * must be grouped by read name like the reference's input (`samtools view | sort -k1,1 -s`, core:458-468): a run of
+ * consecutive lines with one read id is one pair. */
 typedef struct hgt_batch hgt_batch;
 int hgt_batch_create(hgt_ctx *ctx, int32_t n_loci, hgt_locus *const *loci, const hgt_params *params,
                      int32_t remove_low_abundance_alleles, hgt_batch **out);
@@ -233,7 +245,7 @@ int hgt_batch_prepare(hgt_batch *b);
 int hgt_batch_execute(hgt_batch *b, void *stream);
 int hgt_batch_finish(hgt_batch *b, void *stream);
 int hgt_batch_run(hgt_batch *b); /* prepare + execute + finish */
-/* totals over the batch; algorithmic_bytes = SURVEY.md 8d figure for stage (a): packed records read plus one
+/* totals over the batch (valid after execute); algorithmic_bytes = SURVEY.md 8d figure for stage (a): packed records read plus one
  * allele-set row per pair and table */
 int hgt_batch_totals(const hgt_batch *b, int64_t *n_units, int64_t *num_reads, int64_t *num_pairs,
                      int64_t *n_haplotypes, int64_t *n_rows, int64_t *algorithmic_bytes);
@@ -260,10 +272,11 @@ int hgt_batch_unit_em(const hgt_batch *b, int64_t unit, int32_t level, double *p
 int hgt_batch_unit_abundance(const hgt_batch *b, int64_t unit, int32_t cap, int32_t *allele, double *prob,
                              int32_t *n_total);
 
-/* Host-only half of stage (a) with a caller-supplied pileup (no GPU needed): intake, filters, walk, error
- * correction, ambiguity expansion, exon clipping.  Output is the job list the GPU consumes, flattened:
- * for table tb: jobs tb_job_off[n_pairs+1] -> haplotypes (left, right, row_off[..+1] -> rows).  Buffers are
- * owned by the returned handle. */
+/* Host EMULATION of the record stage with a caller-supplied pileup (no GPU needed; test infrastructure, not on the
+ * typing path): the same __host__ __device__ functions the kernels call (csrc/walk_dev.cuh: parse, filters, mate
+ * de-dup, walk, error correction, ambiguity expansion, exon clipping, pair jobs) run in plain loops.  Output is the
+ * job list the allele-set kernels consume, regrouped per table: jobs tb_job_off[n_pairs+1] -> haplotypes (left,
+ * right, row_off[..+1] -> rows).  Buffers are owned by the returned handle. */
 typedef struct hgt_walk hgt_walk;
 int hgt_host_walk(hgt_locus *locus, const char *sam_text, size_t n_bytes, const hgt_params *params,
                   const uint32_t *counts, const uint8_t *nt_mask, hgt_walk **out);
