@@ -258,6 +258,75 @@ __global__ void __launch_bounds__(256) candidate_kernel(ReadsView R) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < R.n_lines; i += (int64_t)gridDim.x * blockDim.x)
         mark_candidate(R, i);
 }
+// Error-correction bits of the warp's 32 records (EcMask, walk_dev.cuh): record by record, all lanes parse the CIGAR
+// together (same bytes: one broadcast load) and cover 32 consecutive read bases of an M segment per step - SEQ and the
+// representative-base sets are read coalesced, one ballot gives 32 bits.  Lane r keeps the words of record r.
+__device__ __forceinline__ EcMask warp_ec_masks(const ReadsView &R, const WalkParams &P, const char *text, int64_t i, bool cand) {
+    const int lane = threadIdx.x & 31;
+    EcMask mine;
+    mine.w0 = mine.w1 = mine.w2 = mine.w3 = 0;
+    mine.valid = false;
+    const char *line = text;
+    const uint8_t *ntm = R.nt_mask;
+    int32_t cig_off = 0, cig_n = 0, seq_off = 0, seq_len = 0, pos = 0, Lb = 0;
+    if (cand) {
+        const RecFields f = R.rec[i];
+        const int u = R.unit[i];
+        line = text + R.line_off[i];
+        ntm = R.nt_mask + R.unit_pos0[u];
+        cig_off = f.cig_off; cig_n = f.cig_len; seq_off = f.seq_off; seq_len = f.seq_len; pos = f.pos;
+        Lb = R.loci[R.unit_locus[u]].L;
+        mine.valid = P.error_correction && seq_len <= ECM_MAX_SEQ;
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, mine.valid);
+    while (todo) {
+        const int r = __ffs((int)todo) - 1;
+        todo &= todo - 1;
+        const char *ln = (const char *)__shfl_sync(0xffffffffu, (unsigned long long)line, r);
+        const uint8_t *nm = (const uint8_t *)__shfl_sync(0xffffffffu, (unsigned long long)ntm, r);
+        const char *cig = ln + __shfl_sync(0xffffffffu, cig_off, r);
+        const int cn = __shfl_sync(0xffffffffu, cig_n, r);
+        const char *seq = ln + __shfl_sync(0xffffffffu, seq_off, r);
+        const int sl = __shfl_sync(0xffffffffu, seq_len, r);
+        const int Lr = __shfl_sync(0xffffffffu, Lb, r);
+        int32_t right_pos = __shfl_sync(0xffffffffu, pos, r), read_pos = 0;
+        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        int cp = 0;
+        while (cp < cn) {
+            int32_t length = 0;
+            char c = cig[cp];
+            while (is_dig(c)) {
+                if (length < (1 << 24)) length = length * 10 + (c - '0');
+                cp++;
+                if (cp >= cn) break;
+                c = cig[cp];
+            }
+            if (cp >= cn) break;
+            cp++;
+            if (c == 'M') {
+                const int32_t seg_end = min(read_pos + length, sl);
+                for (int32_t base = read_pos & ~31; base < seg_end; base += 32) {
+                    const int32_t rp = base + lane;
+                    const bool in = rp >= read_pos && rp < seg_end;
+                    const bool flag = in && ec_flag(seq, sl, nm, Lr, rp, right_pos + (rp - read_pos));
+                    const uint32_t b = __ballot_sync(0xffffffffu, flag);
+                    const int w = base >> 5;
+                    if (w == 0) a0 |= b;
+                    else if (w == 1) a1 |= b;
+                    else if (w == 2) a2 |= b;
+                    else a3 |= b;
+                }
+            }
+            if (c == 'M' || c == 'N' || c == 'D') right_pos += length;
+            if (c == 'M' || c == 'I' || c == 'S') read_pos += length;
+        }
+        if (lane == r) {
+            mine.w0 = a0; mine.w1 = a1; mine.w2 = a2; mine.w3 = a3;
+        }
+    }
+    return mine;
+}
+
 __global__ void __launch_bounds__(STAGE_LINES) walk_kernel(ReadsView R, WalkParams P, int smem_bytes) {
     extern __shared__ __align__(128) char s_text[];
     __shared__ uint64_t mbar;
@@ -268,12 +337,19 @@ __global__ void __launch_bounds__(STAGE_LINES) walk_kernel(ReadsView R, WalkPara
         const int64_t i0 = blk * STAGE_LINES, i1 = min(i0 + (int64_t)STAGE_LINES, R.n_lines);
         const char *base = stage_lines(sg, R, i0, i1);
         const int64_t i = i0 + threadIdx.x;
-        if (i < i1) walk_record<false>(R, P, base, i, -1);
+        const bool cand = i < i1 && (R.st[i] & ST_CAND);
+        const EcMask M = warp_ec_masks(R, P, base, i, cand);
+        if (cand) walk_record<false>(R, P, base, i, -1, M);
     }
 }
 __global__ void __launch_bounds__(128) walk_slow_kernel(ReadsView R, WalkParams P, int n_slow) {
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_slow; k += gridDim.x * blockDim.x)
-        walk_record<true>(R, P, R.text, R.slow_list[k], k);
+    const int n_round = (n_slow + 31) & ~31;  // whole warps: the lanes compute the masks together
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_round; k += gridDim.x * blockDim.x) {
+        const bool on = k < n_slow;
+        const int64_t i = on ? R.slow_list[k] : 0;
+        const EcMask M = warp_ec_masks(R, P, R.text, i, on);
+        if (on) walk_record<true>(R, P, R.text, i, k, M);
+    }
 }
 __global__ void __launch_bounds__(128) pair_count_kernel(ReadsView R) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < R.n_lines; i += (int64_t)gridDim.x * blockDim.x)

@@ -59,6 +59,7 @@ struct hgt_locus {
     std::vector<unsigned char> wt_blob;
     std::vector<size_t> wt_off;
     uint32_t wt_hash_mask = 0;
+    int32_t wt_num_lo = 0, wt_num_n = 0, wt_tok_regular = 0;
     int wt_n_alt[2] = {0, 0};
     unsigned char *d_wt = nullptr;
     hgtd::LocusWalk wt_host, wt_dev;
@@ -230,7 +231,7 @@ static void build_walk_tables(hgt_locus *l) {
     std::vector<int32_t> id_hash(cap, -1);
     for (int i = 0; i < V; i++) {  // a later duplicate id replaces the earlier one, like row_of[id] = i
         const std::string &id = h.vars[i].id;
-        uint32_t slot = (uint32_t)(hgtd::fnv1a(id.data(), (int)id.size()) >> 17) & (cap - 1);
+        uint32_t slot = hgtd::id_slot(id.data(), (int)id.size(), cap - 1);
         while (id_hash[slot] >= 0 && h.vars[id_hash[slot]].id != id) slot = (slot + 1) & (cap - 1);
         id_hash[slot] = i;
     }
@@ -260,6 +261,39 @@ static void build_walk_tables(hgt_locus *l) {
         }
     }
     b.add(lbv);                                                              // 35
+    // regular ids: direct table number -> row
+    std::vector<int32_t> num_row;
+    l->wt_num_lo = 0;
+    {
+        int64_t lo = INT64_MAX, hi = -1;
+        bool regular = V > 0;
+        std::vector<int64_t> num((size_t)V);
+        for (int i = 0; i < V && regular; i++) {
+            num[i] = hgtd::regular_id_number(h.vars[i].id.data(), (int)h.vars[i].id.size());
+            regular = num[i] >= 0;
+            lo = std::min(lo, num[i]); hi = std::max(hi, num[i]);
+        }
+        if (regular && hi - lo + 1 <= 8 * (int64_t)V + 1024 && hi < (1ll << 31)) {
+            num_row.assign((size_t)(hi - lo + 1), -1);
+            for (int i = 0; i < V && regular; i++) {
+                regular = num_row[(size_t)(num[i] - lo)] < 0;  // unique
+                num_row[(size_t)(num[i] - lo)] = i;
+            }
+            if (regular) l->wt_num_lo = (int32_t)lo;
+            else num_row.clear();
+        }
+    }
+    if (getenv("HGT_IRREGULAR_IDS")) num_row.clear();  // tests: the general paths (id hash table, character substring rule)
+    l->wt_num_n = (int32_t)num_row.size();
+    l->wt_tok_regular = l->wt_num_n > 0;
+    for (const std::vector<AltEntry> *tab : {&h.alts_left, &h.alts_right})
+        for (const AltEntry &e : *tab)
+            for (size_t t = 0; t < e.toks.size(); t++) {
+                bool digits = !e.toks[t].empty();
+                for (char ch : e.toks[t]) digits &= ch >= '0' && ch <= '9';
+                if (e.tok_rows[t] < 0 && !digits) l->wt_tok_regular = 0;
+            }
+    b.add(num_row);                                                          // 36
     l->wt_blob.swap(b.data);
     l->wt_off.swap(b.off);
     l->wt_hash_mask = cap - 1;
@@ -280,6 +314,8 @@ static hgtd::LocusWalk walk_view(const hgt_locus *l, const unsigned char *base) 
     w.v.type = at(3); w.v.base = reinterpret_cast<const char *>(at(4)); w.v.flags = at(5);
     w.v.id_off = reinterpret_cast<const int32_t *>(at(6)); w.v.id_pool = reinterpret_cast<const char *>(at(7));
     w.v.id_hash = reinterpret_cast<const int32_t *>(at(8)); w.v.id_hash_mask = l->wt_hash_mask;
+    w.v.num_row = reinterpret_cast<const int32_t *>(at(36)); w.v.num_lo = l->wt_num_lo; w.v.num_n = l->wt_num_n;
+    w.v.tok_regular = l->wt_tok_regular;
     for (int side = 0; side < 2; side++) {
         hgtd::AltTab &t = side ? w.ar : w.al;
         const int k = 9 + 12 * side;
@@ -2582,7 +2618,12 @@ extern "C" int hgt_host_walk(hgt_locus *loc, const char *sam, size_t n_bytes, co
     for (int64_t i = 0; i < N; i++) mark_head(R, i);
     for (int64_t i = 0; i < N; i++) mark_candidate(R, i);
     const auto t2 = now();
-    for (int64_t i = 0; i < N; i++) walk_record<false>(R, P, R.text, i, -1);
+    // HGT_EMU_NO_ECMASK: the walk reads the bases itself (the path of reads longer than 128 bases)
+    const bool use_mask = getenv("HGT_EMU_NO_ECMASK") == nullptr;
+    hgtd::EcMask no_mask;
+    no_mask.w0 = no_mask.w1 = no_mask.w2 = no_mask.w3 = 0;
+    no_mask.valid = false;
+    for (int64_t i = 0; i < N; i++) walk_record<false>(R, P, R.text, i, -1, use_mask ? record_ec_mask(R, P, R.text, i) : no_mask);
     const auto t3 = now();
     if (times)
         fprintf(stderr, "emulation: %lld lines, parse %.2f ms, head+cand %.2f ms, walk %.2f ms (%d to the second pass)\n",
@@ -2590,7 +2631,8 @@ extern "C" int hgt_host_walk(hgt_locus *loc, const char *sam, size_t n_bytes, co
     if (err != ~0ull) return fail();
     std::vector<SlowRec> slow((size_t)std::max(n_slow, 1));
     R.slow = slow.data();
-    for (int k = 0; k < n_slow; k++) walk_record<true>(R, P, R.text, slow_list[k], k);
+    for (int k = 0; k < n_slow; k++)
+        walk_record<true>(R, P, R.text, slow_list[k], k, use_mask ? record_ec_mask(R, P, R.text, slow_list[k]) : no_mask);
     for (int64_t i = 0; i < N; i++) pair_jobs<false>(R, i);
     if (err != ~0ull) return fail();
     for (int k = 0; k < 5; k++) {

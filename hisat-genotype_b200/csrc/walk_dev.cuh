@@ -112,6 +112,11 @@ struct VarTab {
     const char *id_pool;
     const int32_t *id_hash;     // open addressing: row or -1
     uint32_t id_hash_mask;
+    // "regular" ids (every id is "hv<decimal>", no leading zeros, unique - what extract_vars writes, process:1088-1102):
+    // row = num_row[number - num_lo]; num_n == 0 when the locus has any other id (the hash table is used then)
+    const int32_t *num_row;
+    int32_t num_lo, num_n;
+    int32_t tok_regular;        // regular ids and every token of the Alts keys is a number or an id of the locus
 };
 struct AltTab {  // Alts_left or Alts_right (common:1424-1657), entries sorted by anchor position
     int n;
@@ -281,10 +286,36 @@ HGT_HD uint64_t fnv1a(const char *p, int n) {
     }
     return h;
 }
+HGT_HD uint32_t id_slot(const char *p, int n, uint32_t mask) {  // FNV-1a alone clusters on "hv<N>": finish with a mixer
+    uint64_t h = fnv1a(p, n);
+    h ^= h >> 33;
+    h *= 0xff51afd7ed558ccdull;
+    h ^= h >> 33;
+    h *= 0xc4ceb9fe1a85ec53ull;
+    h ^= h >> 33;
+    return (uint32_t)h & mask;
+}
+// "hv<decimal>" without leading zeros -> the number, else -1
+HGT_HD int64_t regular_id_number(const char *p, int n) {
+    if (n < 3 || n > 12 || p[0] != 'h' || p[1] != 'v') return -1;
+    if (p[2] == '0' && n > 3) return -1;
+    int64_t x = 0;
+    for (int k = 2; k < n; k++) {
+        if (!is_dig(p[k])) return -1;
+        x = x * 10 + (p[k] - '0');
+    }
+    return x;
+}
 // row of a variant id given as characters (Zs tag), -3 when it is not a variant of this locus
 HGT_HD int32_t row_of_chars(const VarTab &v, const char *p, int n) {
     if (v.V <= 0) return -3;
-    uint32_t slot = (uint32_t)(fnv1a(p, n) >> 17) & v.id_hash_mask;
+    if (v.num_n > 0) {
+        const int64_t x = regular_id_number(p, n) - v.num_lo;
+        if (x < 0 || x >= v.num_n) return -3;
+        const int32_t r = v.num_row[x];
+        return r < 0 ? -3 : r;
+    }
+    uint32_t slot = id_slot(p, n, v.id_hash_mask);
     while (true) {
         const int32_t r = v.id_hash[slot];
         if (r < 0) return -3;
@@ -527,6 +558,53 @@ HGT_HD bool cmp_push(CmpList &c, uint8_t type, int32_t pos, int32_t len, int32_t
 
 // error_correct (core:119-243), streamed: the entries of one M segment are fed one by one as the walk produces them and
 // the corrected entries go straight to `out` (adjacent matches of the corrected segment merge, core:226-240).
+// Mismatch-with-the-pileup bits of a read, one per SEQ index (bit set: the aligned backbone position has a non-empty
+// representative-base set that does not hold the read's base, core:146-151 / 190-195).  They depend on the CIGAR alone, so
+// the lanes of a warp compute them together, coalesced, for each of the warp's records (reads.cuh: warp_ec_masks) and the
+// serial walk scans bits instead of bases.  valid = false (reads longer than 128 bases): the walk reads the bases itself.
+struct EcMask {
+    uint32_t w0, w1, w2, w3;
+    bool valid;
+};
+HGT_HD uint32_t ecm_word(const EcMask &m, int k) { return k == 0 ? m.w0 : k == 1 ? m.w1 : k == 2 ? m.w2 : m.w3; }
+HGT_HD void ecm_or(EcMask &m, int k, uint32_t b) {
+    if (k == 0) m.w0 |= b;
+    else if (k == 1) m.w1 |= b;
+    else if (k == 2) m.w2 |= b;
+    else if (k == 3) m.w3 |= b;
+}
+constexpr int ECM_MAX_SEQ = 128;
+HGT_HD bool ec_flag(const char *seq, int seq_len, const uint8_t *nt_mask, int L, int32_t rp, int32_t ep) {
+    if (rp >= seq_len || ep < 0 || ep >= L) return false;
+    const uint32_t m = nt_mask[ep];
+    const int c = nt_code(seq[rp]);
+    return m != 0 && !(c < 4 && ((m >> c) & 1u));
+}
+// one record, one thread (host emulation; the device computes the same bits with warp_ec_masks)
+HGT_HD EcMask ec_mask_serial(const char *cig, int cig_n, const char *seq, int seq_len, const uint8_t *nt_mask, int L, int32_t pos) {
+    EcMask m;
+    m.w0 = m.w1 = m.w2 = m.w3 = 0;
+    m.valid = seq_len <= ECM_MAX_SEQ;
+    if (!m.valid) return m;
+    int cp = 0;
+    int32_t read_pos = 0, right_pos = pos;
+    while (cp < cig_n) {
+        int32_t length = 0;
+        while (cp < cig_n && is_dig(cig[cp])) {
+            if (length < (1 << 24)) length = length * 10 + (cig[cp] - '0');
+            cp++;
+        }
+        if (cp >= cig_n) break;
+        const char op = cig[cp++];
+        if (op == 'M')
+            for (int32_t j = 0; j < length && read_pos + j < seq_len; j++)
+                if (ec_flag(seq, seq_len, nt_mask, L, read_pos + j, right_pos + j)) ecm_or(m, (read_pos + j) >> 5, 1u << ((read_pos + j) & 31));
+        if (op == 'M' || op == 'N' || op == 'D') right_pos += length;
+        if (op == 'M' || op == 'I' || op == 'S') read_pos += length;
+    }
+    return m;
+}
+
 struct EcState {
     int seg_start;     // out.n when the segment began
     int32_t read_pos;  // read cursor inside the segment
@@ -539,8 +617,18 @@ HGT_HD void ec_emit(EcState &E, CmpList &out, uint8_t type, int32_t pos, int32_t
         out.lt[out.n - 1] += (uint32_t)len << 2;
     else E.ok &= cmp_push(out, type, pos, len, var);
 }
-HGT_HD void ec_feed(const LocusWalk &L, const char *seq, int seq_len, const uint8_t *nt_mask, EcState &E, CmpList &out,
-                    uint8_t ty, int32_t epos, int32_t elen, int32_t var) {
+// the correction of one base of a match entry (core:146-169)
+HGT_HD void ec_fix_base(const LocusWalk &L, const uint8_t *nt_mask, EcState &E, CmpList &out, int32_t epos, int32_t j, int32_t &last) {
+    const uint32_t m = nt_mask[epos + j];
+    const char nb = (m & (m - 1)) ? 'N' : "ACGT"[ctz32(m)];
+    E.ncorr++;
+    const int32_t vid = nb != 'N' ? known_single(L.v, epos + j, nb) : VAR_UNKNOWN;
+    if (j > last) ec_emit(E, out, C_MATCH, epos + last, j - last, -1);
+    ec_emit(E, out, C_MISMATCH, epos + j, 1, vid);
+    last = j + 1;
+}
+HGT_HD void ec_feed(const LocusWalk &L, const char *seq, int seq_len, const uint8_t *nt_mask, const EcMask &M, EcState &E,
+                    CmpList &out, uint8_t ty, int32_t epos, int32_t elen, int32_t var) {
     if (!E.verbatim && epos >= L.L) E.verbatim = true;
     if (E.verbatim) {
         ec_emit(E, out, ty, epos, elen, var);
@@ -549,32 +637,34 @@ HGT_HD void ec_feed(const LocusWalk &L, const char *seq, int seq_len, const uint
     const int32_t read_pos = E.read_pos;
     if (ty == C_MATCH) {
         int32_t last = 0;
-        for (int32_t j = 0; j < elen; j++) {
-            if (read_pos + j >= seq_len || epos + j >= L.L) continue;
-            const uint32_t m = nt_mask[epos + j];
-            if (m == 0) continue;
-            const int c = nt_code(seq[read_pos + j]);
-            if (!(c < 4 && ((m >> c) & 1u))) {
-                const char nb = (m & (m - 1)) ? 'N' : "ACGT"[ctz32(m)];
-                E.ncorr++;
-                const int32_t vid = nb != 'N' ? known_single(L.v, epos + j, nb) : VAR_UNKNOWN;
-                if (j > last) ec_emit(E, out, C_MATCH, epos + last, j - last, -1);
-                ec_emit(E, out, C_MISMATCH, epos + j, 1, vid);
-                last = j + 1;
+        if (M.valid) {
+            const int32_t end = read_pos + elen < ECM_MAX_SEQ ? read_pos + elen : ECM_MAX_SEQ;  // bits at or past seq_len are 0
+            for (int w = read_pos >> 5; (w << 5) < end; w++) {
+                uint32_t bits = ecm_word(M, w);
+                if ((w << 5) < read_pos) bits &= ~0u << (read_pos & 31);
+                if (((w + 1) << 5) > end) bits &= ~0u >> (((w + 1) << 5) - end);
+                while (bits) {
+                    const int b = ctz32(bits);
+                    bits &= bits - 1;
+                    ec_fix_base(L, nt_mask, E, out, epos, (w << 5) + b - read_pos, last);
+                }
             }
+        } else {
+            for (int32_t j = 0; j < elen; j++)
+                if (ec_flag(seq, seq_len, nt_mask, L.L, read_pos + j, epos + j)) ec_fix_base(L, nt_mask, E, out, epos, j, last);
         }
         if (last < elen) ec_emit(E, out, C_MATCH, epos + last, elen - last, -1);
     } else {
-        const char bp = seq[read_pos];
-        const char ref_bp = L.ref[epos];
-        const uint32_t m = nt_mask[epos];
-        const int c = nt_code(bp);
         uint8_t t2 = ty;
         int32_t v2 = var;
-        if (m != 0 && !(c < 4 && ((m >> c) & 1u))) {
+        // the walk checked read_pos < seq_len for a mismatch entry; epos < L.L here
+        const bool off = M.valid ? ((ecm_word(M, read_pos >> 5) >> (read_pos & 31)) & 1u) != 0
+                                 : ec_flag(seq, seq_len, nt_mask, L.L, read_pos, epos);
+        if (off) {
+            const uint32_t m = nt_mask[epos];
             const char nb = (m & (m - 1)) ? 'N' : "ACGT"[ctz32(m)];
             if (nb == 'N') v2 = VAR_UNKNOWN;
-            else if (nb == ref_bp) {
+            else if (nb == L.ref[epos]) {
                 t2 = C_MATCH;
                 v2 = -1;
                 E.ncorr++;
@@ -593,7 +683,7 @@ struct WalkOut {
 
 // CIGAR x MD x Zs walk (core:876-1095).  Returns E_NONE or the error code.
 HGT_HDN int walk_cigar(const LocusWalk &L, const WalkParams &P, const char *line, const RecFields &f,
-                       const uint8_t *nt_mask, const uint8_t *del_flag, CmpList &cmp, WalkOut &w) {
+                       const uint8_t *nt_mask, const uint8_t *del_flag, const EcMask M, CmpList &cmp, WalkOut &w) {
     if (f.md_len == 0) return E_NO_MD;
     const char *MD = line + f.md_off;
     const int MDn = f.md_len;
@@ -641,7 +731,7 @@ HGT_HDN int walk_cigar(const LocusWalk &L, const WalkParams &P, const char *line
             // an entry of the segment: through the error correction, or straight to the list when it is off
             auto feed = [&](uint8_t ty, int32_t pos, int32_t len, int32_t var) {
                 if (P.error_correction) {
-                    ec_feed(L, seq, seq_len, nt_mask, E, cmp, ty, pos, len, var);
+                    ec_feed(L, seq, seq_len, nt_mask, M, E, cmp, ty, pos, len, var);
                     return E.ok;
                 }
                 return cmp_push(cmp, ty, pos, len, var);
@@ -767,7 +857,8 @@ HGT_HD int32_t seq_len_of(const CmpList &c, int lo, int hi, int L) {
 }
 
 // Does the '-'-joined id string of the known ids of c[lo..hi] occur inside the entry's key (common:1734, 1856: str.find)?
-HGT_HD bool key_contains_ids(const VarTab &v, const AltTab &t, int e, const CmpList &c, int lo, int hi, int m) {
+// Character form: any ids.
+HGT_HD bool key_contains_ids_chars(const VarTab &v, const AltTab &t, int e, const CmpList &c, int lo, int hi, int m) {
     const char *key = t.key_pool + t.key_off[e];
     const int kn = t.key_off[e + 1] - t.key_off[e];
     int total = m - 1;
@@ -782,6 +873,44 @@ HGT_HD bool key_contains_ids(const VarTab &v, const AltTab &t, int e, const CmpL
             first = false;
             const int32_t o = v.id_off[c.var[k]], n = v.id_off[c.var[k] + 1] - o;
             for (int q = 0; q < n && ok; q++) ok = key[p++] == v.id_pool[o + q];
+        }
+        if (ok) return true;
+    }
+    return false;
+}
+HGT_HD bool id_is_prefix(const VarTab &v, int32_t a, int32_t b) {  // id string of row a is a prefix of the id string of row b
+    const int32_t oa = v.id_off[a], na = v.id_off[a + 1] - oa, ob = v.id_off[b], nb = v.id_off[b + 1] - ob;
+    if (na > nb) return false;
+    for (int q = 0; q < na; q++)
+        if (v.id_pool[oa + q] != v.id_pool[ob + q]) return false;
+    return true;
+}
+// Token form, exact when the ids are regular ("hv<N>", unique) and every key token is a number or an id of the locus
+// (VarTab::tok_regular): 'h' occurs only at the start of an id token, so a match starts at a token; every id but the last
+// must then equal its key token, and the last must be a PREFIX of its key token ("hv1" is found inside "hv12").
+HGT_HD bool key_contains_ids(const VarTab &v, const AltTab &t, int e, const CmpList &c, int lo, int hi, int m) {
+    if (!v.tok_regular) return key_contains_ids_chars(v, t, e, c, lo, hi, m);
+    const int32_t *tr = t.tok_row + t.tok_off[e];
+    const int nt = t.tok_off[e + 1] - t.tok_off[e];
+    int k0 = lo;  // first known id of the slice
+    while (c_type(c, k0) == C_MATCH || c.var[k0] < 0) k0++;
+    const int32_t r0 = c.var[k0];
+    for (int s = 0; s + m <= nt; s++) {
+        const int32_t t0 = tr[s];
+        if (t0 < 0) continue;
+        if (m == 1) {
+            if (t0 == r0 || id_is_prefix(v, r0, t0)) return true;
+            continue;
+        }
+        if (t0 != r0) continue;
+        int p = s + 1, seen = 1;
+        bool ok = true;
+        for (int k = k0 + 1; k <= hi && ok; k++) {
+            if (c_type(c, k) == C_MATCH || c.var[k] < 0) continue;
+            const int32_t row = tr[p++];
+            seen++;
+            if (row < 0) ok = false;
+            else if (row != c.var[k]) ok = seen == m && id_is_prefix(v, c.var[k], row);
         }
         if (ok) return true;
     }
@@ -1025,11 +1154,24 @@ HGT_HDN int identify_ambiguous(const LocusWalk &L, const CmpList &c, EndSets<NS>
     return E_NONE;
 }
 
+// EcMask of record i by one thread (host emulation of warp_ec_masks)
+HGT_HD EcMask record_ec_mask(const ReadsView &R, const WalkParams &P, const char *text, int64_t i) {
+    EcMask m;
+    m.w0 = m.w1 = m.w2 = m.w3 = 0;
+    m.valid = false;
+    if (!(R.st[i] & ST_CAND) || !P.error_correction) return m;
+    const RecFields f = R.rec[i];
+    const int u = R.unit[i];
+    const char *line = text + R.line_off[i];
+    return ec_mask_serial(line + f.cig_off, f.cig_len, line + f.seq_off, f.seq_len, R.nt_mask + R.unit_pos0[u],
+                          R.loci[R.unit_locus[u]].L, f.pos);
+}
+
 // One candidate record through the walk.  SLOW = false: every record; the few that come out of identify_ambigious_diffs
 // with more than one haplotype (or need more room) are queued (slow_list).  SLOW = true: line i is such a record and
 // slot its SlowRec.  `text` = base the line offsets are relative to (the arena, or its shared-memory image).
 template <bool SLOW>
-HGT_HD void walk_record(const ReadsView &R, const WalkParams &P, const char *text, int64_t i, int32_t slot) {
+HGT_HD void walk_record(const ReadsView &R, const WalkParams &P, const char *text, int64_t i, int32_t slot, const EcMask &M) {
     const uint16_t st = R.st[i];
     if (!(st & ST_CAND)) return;
     const RecFields f = R.rec[i];
@@ -1039,7 +1181,7 @@ HGT_HD void walk_record(const ReadsView &R, const WalkParams &P, const char *tex
     const uint8_t *nt_mask = R.nt_mask + R.unit_pos0[u], *del_flag = R.del_flag + R.unit_pos0[u];
     CmpList cmp;
     WalkOut w;
-    const int rc = walk_cigar(L, P, line, f, nt_mask, del_flag, cmp, w);
+    const int rc = walk_cigar(L, P, line, f, nt_mask, del_flag, M, cmp, w);
     if (rc != E_NONE) {
         set_error(R, i, rc);
         return;

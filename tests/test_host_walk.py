@@ -1,5 +1,6 @@
-"""CPU-side parity of the native host half of stage (a) (csrc/walk.hpp via hgt_host_walk): alignment text ->
-haplotype jobs, checked against the reference goldens by finishing the allele-set algebra in Python."""
+"""CPU-side parity of the record stage (csrc/walk_dev.cuh, the __host__ __device__ functions the kernels call, run in plain
+loops by hgt_host_walk): alignment text -> haplotype jobs, checked against the reference goldens by finishing the
+allele-set algebra in Python."""
 import numpy as np
 import pytest
 
@@ -21,12 +22,17 @@ def test_locus_tables_match_reference(name):
         t.close()
 
 
-@pytest.mark.parametrize("chunk_bytes", [0, 3000])
+@pytest.mark.parametrize("general", [False, True])
 @pytest.mark.parametrize("name", GOLDEN_NAMES)
-def test_host_walk_tables(name, chunk_bytes):
-    """chunk_bytes = 3000 cuts every unit into dozens of tasks at read-id boundaries (the decomposition the batch path
-    uses to spread one unit over all host threads); the result must not change."""
+def test_host_walk_tables(name, general, monkeypatch):
+    """general = True takes the paths for databases whose variant ids are not "hv<N>" (id hash table, character form of
+    the substring rule of identify_ambigious_diffs) and for reads longer than 128 bases (error correction base by base
+    instead of through the per-read mismatch bits); the result must not change."""
     from hisatgenotype_b200.typing_core import HostWalk, make_params
+    if general:
+        monkeypatch.setenv("HGT_IRREGULAR_IDS", "1")
+        monkeypatch.setenv("HGT_EMU_NO_ECMASK", "1")
+    chunk_bytes = 0
     g = load_golden(name)
     p = g["params"]
     db = golden_db(g)
