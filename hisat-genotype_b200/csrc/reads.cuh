@@ -260,36 +260,41 @@ __global__ void __launch_bounds__(256) candidate_kernel(ReadsView R) {
 }
 // Error-correction bits of the warp's 32 records (EcMask, walk_dev.cuh): record by record, all lanes parse the CIGAR
 // together (same bytes: one broadcast load) and cover 32 consecutive read bases of an M segment per step - SEQ and the
-// representative-base sets are read coalesced, one ballot gives 32 bits.  Lane r keeps the words of record r.
-__device__ __forceinline__ EcMask warp_ec_masks(const ReadsView &R, const WalkParams &P, const char *text, int64_t i, bool cand) {
+// representative-base sets are read coalesced, one ballot gives 32 bits.  Lane r keeps the words of record r.  The
+// parameters of the 32 records go through shared memory (two 16-byte broadcast loads per record instead of ten shuffles).
+struct EcParams {
+    const char *line;
+    const uint8_t *ntm;
+    int32_t pos, L;
+    uint16_t cig_off, cig_n, seq_off, seq_len;
+};
+static_assert(sizeof(EcParams) == 32, "EcParams is read as two 16-byte words");
+__device__ __forceinline__ EcMask warp_ec_masks(const ReadsView &R, const WalkParams &P, const char *text, int64_t i, bool cand,
+                                                EcParams *s_warp /* [32], this warp's */) {
     const int lane = threadIdx.x & 31;
     EcMask mine;
     mine.w0 = mine.w1 = mine.w2 = mine.w3 = 0;
     mine.valid = false;
-    const char *line = text;
-    const uint8_t *ntm = R.nt_mask;
-    int32_t cig_off = 0, cig_n = 0, seq_off = 0, seq_len = 0, pos = 0, Lb = 0;
     if (cand) {
         const RecFields f = R.rec[i];
         const int u = R.unit[i];
-        line = text + R.line_off[i];
-        ntm = R.nt_mask + R.unit_pos0[u];
-        cig_off = f.cig_off; cig_n = f.cig_len; seq_off = f.seq_off; seq_len = f.seq_len; pos = f.pos;
-        Lb = R.loci[R.unit_locus[u]].L;
-        mine.valid = P.error_correction && seq_len <= ECM_MAX_SEQ;
+        EcParams p;
+        p.line = text + R.line_off[i];
+        p.ntm = R.nt_mask + R.unit_pos0[u];
+        p.pos = f.pos;
+        p.L = R.loci[R.unit_locus[u]].L;
+        p.cig_off = f.cig_off; p.cig_n = f.cig_len; p.seq_off = f.seq_off; p.seq_len = f.seq_len;
+        s_warp[lane] = p;
+        mine.valid = P.error_correction && f.seq_len <= ECM_MAX_SEQ;
     }
-    unsigned todo = __ballot_sync(0xffffffffu, mine.valid);
+    unsigned todo = __ballot_sync(0xffffffffu, mine.valid);  // (also orders the shared-memory writes before the reads)
     while (todo) {
         const int r = __ffs((int)todo) - 1;
         todo &= todo - 1;
-        const char *ln = (const char *)__shfl_sync(0xffffffffu, (unsigned long long)line, r);
-        const uint8_t *nm = (const uint8_t *)__shfl_sync(0xffffffffu, (unsigned long long)ntm, r);
-        const char *cig = ln + __shfl_sync(0xffffffffu, cig_off, r);
-        const int cn = __shfl_sync(0xffffffffu, cig_n, r);
-        const char *seq = ln + __shfl_sync(0xffffffffu, seq_off, r);
-        const int sl = __shfl_sync(0xffffffffu, seq_len, r);
-        const int Lr = __shfl_sync(0xffffffffu, Lb, r);
-        int32_t right_pos = __shfl_sync(0xffffffffu, pos, r), read_pos = 0;
+        const EcParams p = s_warp[r];
+        const char *cig = p.line + p.cig_off, *seq = p.line + p.seq_off;
+        const int cn = p.cig_n, sl = p.seq_len;
+        int32_t right_pos = p.pos, read_pos = 0;
         uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
         int cp = 0;
         while (cp < cn) {
@@ -304,11 +309,20 @@ __device__ __forceinline__ EcMask warp_ec_masks(const ReadsView &R, const WalkPa
             if (cp >= cn) break;
             cp++;
             if (c == 'M') {
-                const int32_t seg_end = min(read_pos + length, sl);
-                for (int32_t base = read_pos & ~31; base < seg_end; base += 32) {
+                const int32_t shift = right_pos - read_pos;  // backbone position of read base rp = rp + shift
+                // read bases of the segment that exist and lie on the backbone: [lo, hi)
+                const int32_t lo = max(read_pos, -shift), hi = min(min(read_pos + length, sl), p.L - shift);
+                for (int32_t base = lo & ~31; base < hi; base += 32) {
                     const int32_t rp = base + lane;
-                    const bool in = rp >= read_pos && rp < seg_end;
-                    const bool flag = in && ec_flag(seq, sl, nm, Lr, rp, right_pos + (rp - read_pos));
+                    bool flag = false;
+                    if ((uint32_t)(rp - lo) < (uint32_t)(hi - lo)) {
+                        const uint32_t m = p.ntm[rp + shift], ch = (unsigned char)seq[rp];
+                        // A 0x41, C 0x43, G 0x47, T 0x54: bits 1-2 give 0, 1, 3, 2 -> x ^ (x >> 1) = 0, 1, 2, 3; the
+                        // letters themselves are bits 1, 3, 7, 20 of a 32-bit table indexed by the low five bits
+                        const uint32_t x = (ch >> 1) & 3u, code = x ^ (x >> 1);
+                        const bool acgt = (ch >> 5) == 2u && ((0x0010008Au >> (ch & 31u)) & 1u);
+                        flag = m != 0 && !(acgt && ((m >> code) & 1u));
+                    }
                     const uint32_t b = __ballot_sync(0xffffffffu, flag);
                     const int w = base >> 5;
                     if (w == 0) a0 |= b;
@@ -324,12 +338,14 @@ __device__ __forceinline__ EcMask warp_ec_masks(const ReadsView &R, const WalkPa
             mine.w0 = a0; mine.w1 = a1; mine.w2 = a2; mine.w3 = a3;
         }
     }
+    __syncwarp();
     return mine;
 }
 
 __global__ void __launch_bounds__(STAGE_LINES) walk_kernel(ReadsView R, WalkParams P, int smem_bytes) {
     extern __shared__ __align__(128) char s_text[];
     __shared__ uint64_t mbar;
+    __shared__ __align__(16) EcParams s_ecp[STAGE_LINES];
     Stage sg;
     stage_init(sg, &mbar, s_text, smem_bytes);
     const int64_t n_blk = (R.n_lines + STAGE_LINES - 1) / STAGE_LINES;
@@ -338,17 +354,30 @@ __global__ void __launch_bounds__(STAGE_LINES) walk_kernel(ReadsView R, WalkPara
         const char *base = stage_lines(sg, R, i0, i1);
         const int64_t i = i0 + threadIdx.x;
         const bool cand = i < i1 && (R.st[i] & ST_CAND);
-        const EcMask M = warp_ec_masks(R, P, base, i, cand);
-        if (cand) walk_record<false>(R, P, base, i, -1, M);
+        const EcMask M = warp_ec_masks(R, P, base, i, cand, s_ecp + (threadIdx.x & ~31));
+        if (cand) walk_record<0>(R, P, base, i, -1, M);
     }
 }
+// second pass: records with an Alts anchor in reach (amb_list, filled by walk_kernel; its length stays on the device)
+__global__ void __launch_bounds__(128) walk_amb_kernel(ReadsView R, WalkParams P) {
+    __shared__ __align__(16) EcParams s_ecp[128];
+    const int n = *R.n_amb, n_round = (n + 31) & ~31;  // whole warps: the lanes compute the masks together
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_round; k += gridDim.x * blockDim.x) {
+        const bool on = k < n;
+        const int64_t i = on ? R.amb_list[k] : 0;
+        const EcMask M = warp_ec_masks(R, P, R.text, i, on, s_ecp + (threadIdx.x & ~31));
+        if (on) walk_record<1>(R, P, R.text, i, -1, M);
+    }
+}
+// third pass: records with several haplotypes
 __global__ void __launch_bounds__(128) walk_slow_kernel(ReadsView R, WalkParams P, int n_slow) {
-    const int n_round = (n_slow + 31) & ~31;  // whole warps: the lanes compute the masks together
+    __shared__ __align__(16) EcParams s_ecp[128];
+    const int n_round = (n_slow + 31) & ~31;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_round; k += gridDim.x * blockDim.x) {
         const bool on = k < n_slow;
         const int64_t i = on ? R.slow_list[k] : 0;
-        const EcMask M = warp_ec_masks(R, P, R.text, i, on);
-        if (on) walk_record<true>(R, P, R.text, i, k, M);
+        const EcMask M = warp_ec_masks(R, P, R.text, i, on, s_ecp + (threadIdx.x & ~31));
+        if (on) walk_record<2>(R, P, R.text, i, k, M);
     }
 }
 __global__ void __launch_bounds__(128) pair_count_kernel(ReadsView R) {

@@ -294,6 +294,30 @@ static void build_walk_tables(hgt_locus *l) {
                 if (e.tok_rows[t] < 0 && !digits) l->wt_tok_regular = 0;
             }
     b.add(num_row);                                                          // 36
+    std::vector<int32_t> id_num((size_t)V, 0);
+    if (l->wt_num_n > 0)
+        for (int i = 0; i < V; i++) id_num[i] = (int32_t)hgtd::regular_id_number(h.vars[i].id.data(), (int)h.vars[i].id.size());
+    b.add(id_num);                                                           // 37
+    // read ends identify_ambigious_diffs can act on (AltTab::end_flag)
+    {
+        auto vright = [&](int32_t r) { return h.vars[r].type == hgtd::T_DELETION ? h.vars[r].pos + h.vars[r].len - 1 : h.vars[r].pos; };
+        std::vector<uint8_t> fl_left((size_t)l->L + 2, 0), fl_right((size_t)l->L + 2, 0);
+        for (const AltEntry &e : h.alts_left) {
+            const int ntok = (int)e.toks.size() - 1;  // key.split('-')[:-1]
+            if (ntok < 1) continue;
+            int64_t bound = atoi(e.toks[0].c_str());
+            for (int k = 1; k < ntok; k++) bound = e.tok_rows[k] < 0 ? 0 : std::min<int64_t>(bound, (int64_t)vright(e.tok_rows[k]) + 1);
+            for (int64_t x = std::max<int64_t>(bound, 0); x <= std::min<int64_t>(e.anchor, l->L + 1); x++) fl_left[(size_t)x] = 1;
+        }
+        for (const AltEntry &e : h.alts_right) {
+            const int ntok = (int)e.toks.size() - 1;  // key.split('-')[1:]
+            if (ntok < 1) continue;
+            int64_t bound = atoi(e.toks[ntok].c_str());
+            for (int k = 1; k < ntok; k++) bound = e.tok_rows[k] < 0 ? l->L + 1 : std::max<int64_t>(bound, (int64_t)h.vars[e.tok_rows[k]].pos - 1);
+            for (int64_t x = std::max<int64_t>(e.anchor, 0); x <= std::min<int64_t>(bound, l->L + 1); x++) fl_right[(size_t)x] = 1;
+        }
+        b.add(fl_left); b.add(fl_right);                                     // 38, 39
+    }
     l->wt_blob.swap(b.data);
     l->wt_off.swap(b.off);
     l->wt_hash_mask = cap - 1;
@@ -314,7 +338,7 @@ static hgtd::LocusWalk walk_view(const hgt_locus *l, const unsigned char *base) 
     w.v.type = at(3); w.v.base = reinterpret_cast<const char *>(at(4)); w.v.flags = at(5);
     w.v.id_off = reinterpret_cast<const int32_t *>(at(6)); w.v.id_pool = reinterpret_cast<const char *>(at(7));
     w.v.id_hash = reinterpret_cast<const int32_t *>(at(8)); w.v.id_hash_mask = l->wt_hash_mask;
-    w.v.num_row = reinterpret_cast<const int32_t *>(at(36)); w.v.num_lo = l->wt_num_lo; w.v.num_n = l->wt_num_n;
+    w.v.num_row = reinterpret_cast<const int32_t *>(at(36)); w.v.id_num = reinterpret_cast<const int32_t *>(at(37)); w.v.num_lo = l->wt_num_lo; w.v.num_n = l->wt_num_n;
     w.v.tok_regular = l->wt_tok_regular;
     for (int side = 0; side < 2; side++) {
         hgtd::AltTab &t = side ? w.ar : w.al;
@@ -326,6 +350,7 @@ static hgtd::LocusWalk walk_view(const hgt_locus *l, const unsigned char *base) 
         t.tok_num = reinterpret_cast<const int32_t *>(at(k + 6)); t.alt_off = reinterpret_cast<const int32_t *>(at(k + 7));
         t.alt_left = reinterpret_cast<const int32_t *>(at(k + 8)); t.alt_right = reinterpret_cast<const int32_t *>(at(k + 9));
         t.altrow_off = reinterpret_cast<const int32_t *>(at(k + 10)); t.altrow = reinterpret_cast<const int32_t *>(at(k + 11));
+        t.end_flag = at(38 + side);
     }
     w.n_exons = (int)l->host.exons.size(); w.n_pexons = (int)l->host.primary_exons.size();
     w.exons = reinterpret_cast<const int32_t *>(at(33)); w.pexons = reinterpret_cast<const int32_t *>(at(34));
@@ -1431,10 +1456,12 @@ static hgtd::ReadsView reads_view(hgt_batch *b) {
     R.slow_slot = R.h_n + N;
     R.h_ids = rd.d_hids.as<int32_t>();
     R.slow = rd.d_slow.as<hgtd::SlowRec>();
-    R.slow_list = rd.d_slow_list.as<int32_t>();
+    R.amb_list = rd.d_slow_list.as<int32_t>();
+    R.slow_list = R.amb_list + std::max<size_t>(N, 1);
     unsigned char *sm = static_cast<unsigned char *>(rd.d_small.p);
     R.err = reinterpret_cast<unsigned long long *>(sm);
     R.n_slow = reinterpret_cast<int32_t *>(sm + 8);
+    R.n_amb = reinterpret_cast<int32_t *>(sm + 16);
     R.max_job_haps = reinterpret_cast<int32_t *>(sm + 12);
     R.unit_reads = reinterpret_cast<unsigned long long *>(sm + rd.s_reads);
     R.unit_pairs = reinterpret_cast<unsigned long long *>(sm + rd.s_pairs);
@@ -1477,11 +1504,11 @@ static int reads_execute(hgt_batch *b, cudaStream_t st) {
     HGT_CHECK(rd.d_st.alloc((size_t)std::max<int64_t>(N, 1) * 2));
     HGT_CHECK(rd.d_hdr.alloc((size_t)std::max<int64_t>(N, 1) * 16));
     HGT_CHECK(rd.d_hids.alloc((size_t)std::max<int64_t>(N, 1) * hgtd::MAXI * 4));
-    HGT_CHECK(rd.d_slow_list.alloc((size_t)std::max<int64_t>(N, 1) * 4));
+    HGT_CHECK(rd.d_slow_list.alloc((size_t)std::max<int64_t>(N, 1) * 8));
     HGT_CHECK(rd.d_scan.alloc((size_t)(N + 1) * 8 * 5));
     HGT_CHECK(rd.d_cnt.alloc((size_t)std::max<int64_t>(rd.POS, 1) * 24));
     HGT_CHECK(rd.d_mf.alloc((size_t)std::max<int64_t>(rd.POS, 1) * 2));
-    rd.s_reads = 16;
+    rd.s_reads = 32;
     rd.s_pairs = rd.s_reads + nu * 8;
     rd.s_totals = rd.s_pairs + nu * 8;
     rd.small_bytes = rd.s_totals + nl * 6 * 8;
@@ -1550,8 +1577,9 @@ static int reads_execute(hgt_batch *b, cudaStream_t st) {
         hgtk::walk_kernel<<<line_grid(ctx, N, 128, 16), hgtk::STAGE_LINES, 0, st>>>(R, P, 0);
     else
         hgtk::walk_kernel<<<stage_grid, hgtk::STAGE_LINES, stage_bytes, st>>>(R, P, stage_bytes);
-    launches = 3;
-    ctx->launches += 3;
+    hgtk::walk_amb_kernel<<<line_grid(ctx, N, 128, 16), 128, 0, st>>>(R, P);  // its length is read on the device
+    launches = 4;
+    ctx->launches += 4;
     HGT_CUDA(cudaGetLastError());
     HGT_CUDA(d2h(rd.h_small.p, rd.d_small.p, 16, st));
     HGT_CUDA(cudaStreamSynchronize(st));  // number of records that need the ambiguity pass
@@ -2575,12 +2603,12 @@ extern "C" int hgt_host_walk(hgt_locus *loc, const char *sam, size_t n_bytes, co
         const uint64_t dels = c[5], nts = (uint64_t)c[0] + c[1] + c[2] + c[3] + c[4];
         flag[i] = dels * 6 < nts ? 1 : 0;
     }
-    std::vector<int32_t> unit(n1), hdr(n1 * 4), hids(n1 * MAXI), slow_list(n1);
+    std::vector<int32_t> unit(n1), hdr(n1 * 4), hids(n1 * MAXI), slow_list(n1), amb_list(n1);
     std::vector<RecFields> rec(n1);
     std::vector<uint16_t> stv(n1);
     std::vector<int64_t> scan((size_t)(N + 1) * 5, 0);
     int64_t unit_off[2] = {0, (int64_t)text.size()}, unit_line0[2] = {0, N}, unit_pos0[2] = {0, 0};
-    int32_t unit_locus[1] = {0}, unit_local[1] = {0}, n_slow = 0, max_job = 0;
+    int32_t unit_locus[1] = {0}, unit_local[1] = {0}, n_slow = 0, n_amb = 0, max_job = 0;
     unsigned long long err = ~0ull, unit_reads[1] = {0}, unit_pairs[1] = {0};
     LocusJobs jobs;
     memset(&jobs, 0, sizeof(jobs));
@@ -2590,6 +2618,7 @@ extern "C" int hgt_host_walk(hgt_locus *loc, const char *sam, size_t n_bytes, co
     R.unit = unit.data(); R.rec = rec.data(); R.st = stv.data();
     R.h_left = hdr.data(); R.h_right = R.h_left + n1; R.h_n = R.h_right + n1; R.slow_slot = R.h_n + n1;
     R.h_ids = hids.data(); R.slow_list = slow_list.data(); R.n_slow = &n_slow;
+    R.amb_list = amb_list.data(); R.n_amb = &n_amb;
     R.n_units = 1; R.unit_off = unit_off; R.unit_line0 = unit_line0; R.unit_locus = unit_locus; R.unit_local = unit_local;
     R.unit_pos0 = unit_pos0; R.nt_mask = nt_mask; R.del_flag = flag.data(); R.loci = &loc->wt_host;
     R.err = &err; R.unit_reads = unit_reads; R.unit_pairs = unit_pairs;
@@ -2623,16 +2652,18 @@ extern "C" int hgt_host_walk(hgt_locus *loc, const char *sam, size_t n_bytes, co
     hgtd::EcMask no_mask;
     no_mask.w0 = no_mask.w1 = no_mask.w2 = no_mask.w3 = 0;
     no_mask.valid = false;
-    for (int64_t i = 0; i < N; i++) walk_record<false>(R, P, R.text, i, -1, use_mask ? record_ec_mask(R, P, R.text, i) : no_mask);
+    for (int64_t i = 0; i < N; i++) walk_record<0>(R, P, R.text, i, -1, use_mask ? record_ec_mask(R, P, R.text, i) : no_mask);
+    for (int k = 0; k < n_amb; k++)
+        walk_record<1>(R, P, R.text, amb_list[k], -1, use_mask ? record_ec_mask(R, P, R.text, amb_list[k]) : no_mask);
     const auto t3 = now();
     if (times)
-        fprintf(stderr, "emulation: %lld lines, parse %.2f ms, head+cand %.2f ms, walk %.2f ms (%d to the second pass)\n",
-                (long long)N, ms(t0, t1), ms(t1, t2), ms(t2, t3), n_slow);
+        fprintf(stderr, "emulation: %lld lines, parse %.2f ms, head+cand %.2f ms, walk %.2f ms (%d to the second pass, %d to the third)\n",
+                (long long)N, ms(t0, t1), ms(t1, t2), ms(t2, t3), n_amb, n_slow);
     if (err != ~0ull) return fail();
     std::vector<SlowRec> slow((size_t)std::max(n_slow, 1));
     R.slow = slow.data();
     for (int k = 0; k < n_slow; k++)
-        walk_record<true>(R, P, R.text, slow_list[k], k, use_mask ? record_ec_mask(R, P, R.text, slow_list[k]) : no_mask);
+        walk_record<2>(R, P, R.text, slow_list[k], k, use_mask ? record_ec_mask(R, P, R.text, slow_list[k]) : no_mask);
     for (int64_t i = 0; i < N; i++) pair_jobs<false>(R, i);
     if (err != ~0ull) return fail();
     for (int k = 0; k < 5; k++) {

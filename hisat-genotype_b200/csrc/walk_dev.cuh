@@ -115,6 +115,7 @@ struct VarTab {
     // "regular" ids (every id is "hv<decimal>", no leading zeros, unique - what extract_vars writes, process:1088-1102):
     // row = num_row[number - num_lo]; num_n == 0 when the locus has any other id (the hash table is used then)
     const int32_t *num_row;
+    const int32_t *id_num;      // [V] the number of every id (regular ids only)
     int32_t num_lo, num_n;
     int32_t tok_regular;        // regular ids and every token of the Alts keys is a number or an id of the locus
 };
@@ -122,6 +123,8 @@ struct AltTab {  // Alts_left or Alts_right (common:1424-1657), entries sorted b
     int n;
     const int32_t *anchor;      // [n]
     const int32_t *below;       // [L+2] number of anchors < x
+    const uint8_t *end_flag;    // [L+2] 1 where a read END (left end for Alts_left, right end for Alts_right) can make
+                                //       identify_ambigious_diffs do anything: bound_j <= x <= anchor_j for some entry j
     const int32_t *key_off;     // [n+1] key string "529-hv8-hv22-606" in key_pool
     const char *key_pool;
     const int32_t *tok_off;     // [n+1] tokens of the key
@@ -185,8 +188,8 @@ struct ReadsView {
     int32_t *h_left, *h_right, *h_n, *slow_slot;  // slow_slot >= 0: index into slow[]
     int32_t *h_ids;            // [n_lines][MAXI]
     SlowRec *slow;
-    int32_t *slow_list;        // lines queued for the ambiguity pass
-    int32_t *n_slow;
+    int32_t *amb_list, *slow_list;  // lines queued for the second pass (an Alts anchor in reach) / the third (several haplotypes)
+    int32_t *n_amb, *n_slow;
     // units
     int n_units;
     const int64_t *unit_off;   // [n_units+1] byte range of every unit in the arena
@@ -297,7 +300,7 @@ HGT_HD uint32_t id_slot(const char *p, int n, uint32_t mask) {  // FNV-1a alone 
 }
 // "hv<decimal>" without leading zeros -> the number, else -1
 HGT_HD int64_t regular_id_number(const char *p, int n) {
-    if (n < 3 || n > 12 || p[0] != 'h' || p[1] != 'v') return -1;
+    if (n < 3 || n > 11 || p[0] != 'h' || p[1] != 'v') return -1;
     if (p[2] == '0' && n > 3) return -1;
     int64_t x = 0;
     for (int k = 2; k < n; k++) {
@@ -307,7 +310,7 @@ HGT_HD int64_t regular_id_number(const char *p, int n) {
     return x;
 }
 // row of a variant id given as characters (Zs tag), -3 when it is not a variant of this locus
-HGT_HD int32_t row_of_chars(const VarTab &v, const char *p, int n) {
+HGT_HDN int32_t row_of_chars(const VarTab &v, const char *p, int n) {
     if (v.V <= 0) return -3;
     if (v.num_n > 0) {
         const int64_t x = regular_id_number(p, n) - v.num_lo;
@@ -728,15 +731,10 @@ HGT_HDN int walk_cigar(const LocusWalk &L, const WalkParams &P, const char *line
             E.ncorr = 0;
             E.verbatim = false;
             E.ok = true;
-            // an entry of the segment: through the error correction, or straight to the list when it is off
-            auto feed = [&](uint8_t ty, int32_t pos, int32_t len, int32_t var) {
-                if (P.error_correction) {
-                    ec_feed(L, seq, seq_len, nt_mask, M, E, cmp, ty, pos, len, var);
-                    return E.ok;
-                }
-                return cmp_push(cmp, ty, pos, len, var);
-            };
-            while (true) {
+            // Each turn of the loop yields up to two entries (a match run, then a mismatch or nothing); they go through the
+            // error correction - or straight to the list when it is off - at ONE place (the code of ec_feed exists once).
+            bool more = true;
+            while (more) {
                 if (!first || md_len == 0) {
                     if (md_i >= MDn) return E_MD_SHORT;
                     if (is_dig(MD[md_i])) {
@@ -745,34 +743,51 @@ HGT_HDN int walk_cigar(const LocusWalk &L, const WalkParams &P, const char *line
                         md_len += num;
                     }
                 }
+                int32_t m_pos = 0, m_len = 0, x_pos = 0, x_var = VAR_UNKNOWN;
+                bool have_x = false;
                 if (md_len >= length) {
                     md_len -= length;
-                    if (length > used && !feed(C_MATCH, right_pos + used, length - used, -1)) return E_CAP_CMP;
-                    break;
-                }
-                first = false;
-                if (read_pos + md_len >= seq_len) return E_MD_PAST_READ;
-                const char base = seq[read_pos + md_len];
-                if (md_i >= MDn || !is_nt(MD[md_i])) return E_MD_BASE;
-                md_i++;
-                if (md_len > used && !feed(C_MATCH, right_pos + used, md_len - used, -1)) return E_CAP_CMP;
-                int32_t vid = VAR_UNKNOWN;
-                if (read_pos + md_len == zs_pos && z.have) {
-                    if (z.kind != 'S') return E_ZS_NOT_S;
-                    vid = row_of_chars(L.v, z.s + z.id_p, z.id_n);
-                    if (vid < 0) return E_ZS_ID;
-                    zs_next(z);
-                    zs_pos += 1;
-                    if (z.have) zs_pos += z.off;
+                    m_pos = right_pos + used;
+                    m_len = length - used;
+                    more = false;
                 } else {
-                    vid = known_single(L.v, right_pos + md_len, base);
+                    first = false;
+                    if (read_pos + md_len >= seq_len) return E_MD_PAST_READ;
+                    const char base = seq[read_pos + md_len];
+                    if (md_i >= MDn || !is_nt(MD[md_i])) return E_MD_BASE;
+                    md_i++;
+                    m_pos = right_pos + used;
+                    m_len = md_len - used;
+                    if (read_pos + md_len == zs_pos && z.have) {
+                        if (z.kind != 'S') return E_ZS_NOT_S;
+                        x_var = row_of_chars(L.v, z.s + z.id_p, z.id_n);
+                        if (x_var < 0) return E_ZS_ID;
+                        zs_next(z);
+                        zs_pos += 1;
+                        if (z.have) zs_pos += z.off;
+                    } else {
+                        x_var = known_single(L.v, right_pos + md_len, base);
+                    }
+                    have_x = true;
+                    x_pos = right_pos + md_len;
+                    used = md_len + 1;
+                    md_len += 1;
+                    if (md_len == length) {
+                        md_len = 0;
+                        more = false;
+                    }
                 }
-                if (!feed(C_MISMATCH, right_pos + md_len, 1, vid)) return E_CAP_CMP;
-                used = md_len + 1;
-                md_len += 1;
-                if (md_len == length) {
-                    md_len = 0;
-                    break;
+                for (int e = 0; e < 2; e++) {
+                    const bool is_x = e == 1;
+                    if (is_x ? !have_x : m_len <= 0) continue;
+                    const uint8_t ty = is_x ? C_MISMATCH : C_MATCH;
+                    const int32_t pos = is_x ? x_pos : m_pos, len = is_x ? 1 : m_len, var = is_x ? x_var : -1;
+                    bool fed;
+                    if (P.error_correction) {
+                        ec_feed(L, seq, seq_len, nt_mask, M, E, cmp, ty, pos, len, var);
+                        fed = E.ok;
+                    } else fed = cmp_push(cmp, ty, pos, len, var);
+                    if (!fed) return E_CAP_CMP;
                 }
             }
             w.ncorr += E.ncorr;
@@ -879,6 +894,14 @@ HGT_HD bool key_contains_ids_chars(const VarTab &v, const AltTab &t, int e, cons
     return false;
 }
 HGT_HD bool id_is_prefix(const VarTab &v, int32_t a, int32_t b) {  // id string of row a is a prefix of the id string of row b
+    if (v.num_n > 0) {  // "hv<x>" vs "hv<y>", no leading zeros: x is y with trailing digits cut off
+        const int32_t x = v.id_num[a];
+        int32_t y = v.id_num[b];
+        if (x == y) return true;
+        if (x == 0) return false;
+        while (y > x) y /= 10;
+        return y == x;
+    }
     const int32_t oa = v.id_off[a], na = v.id_off[a + 1] - oa, ob = v.id_off[b], nb = v.id_off[b + 1] - ob;
     if (na > nb) return false;
     for (int q = 0; q < na; q++)
@@ -1167,10 +1190,15 @@ HGT_HD EcMask record_ec_mask(const ReadsView &R, const WalkParams &P, const char
                           R.loci[R.unit_locus[u]].L, f.pos);
 }
 
-// One candidate record through the walk.  SLOW = false: every record; the few that come out of identify_ambigious_diffs
-// with more than one haplotype (or need more room) are queued (slow_list).  SLOW = true: line i is such a record and
-// slot its SlowRec.  `text` = base the line offsets are relative to (the arena, or its shared-memory image).
-template <bool SLOW>
+// One candidate record through the walk, in up to three passes (each a kernel whose warps do one kind of work):
+//   MODE 0  every candidate record: walk -> ONE haplotype when no Alts anchor lies inside an eligible entry (most records);
+//           the others are queued (amb_list)
+//   MODE 1  a queued record: the walk again, then identify_ambigious_diffs with room for two ends per side - nearly every
+//           read that covers an anchor still comes out with ONE haplotype; the others (and only they) are queued (slow_list)
+//   MODE 2  a record of the slow list (slot = its SlowRec): the full-size identify_ambigious_diffs, haplotypes factored as
+//           left ends x middle x right ends
+// `text` = base the line offsets are relative to (the arena, or its shared-memory image).
+template <int MODE>
 HGT_HD void walk_record(const ReadsView &R, const WalkParams &P, const char *text, int64_t i, int32_t slot, const EcMask &M) {
     const uint16_t st = R.st[i];
     if (!(st & ST_CAND)) return;
@@ -1217,53 +1245,25 @@ HGT_HD void walk_record(const ReadsView &R, const WalkParams &P, const char *tex
         set_error(R, i, E_EMPTY);
         return;
     }
-    if (!SLOW) {
-        // does identify_ambigious_diffs have anything to look at?  (an Alts anchor inside an eligible entry)
-        bool amb = false;
-        for (int k = 0; k < n2 && !amb; k++) {
-            const uint8_t ty = c_type(cmp, k);
-            if (ty != C_MATCH && (ty == C_INSERTION || !id_is_hv(L.v, cmp.var[k]))) continue;
-            const int32_t cl = cmp.pos[k];
-            const int32_t cr = (ty == C_MATCH || ty == C_DELETION) ? cl + c_len(cmp, k) - 1 : cl;
-            if (L.al.n > 0 && any_anchor(L.al, L.L, cl, cr)) amb = true;
-            if (L.ar.n > 0 && any_anchor(L.ar, L.L, cl, cr)) amb = true;
-        }
+    if (MODE == 0) {
         int32_t *ids_out = R.h_ids + i * MAXI;
         int m = 0;
-        int32_t h_left = cmp.pos[0], h_right = cmp.pos[n2 - 1] + c_len(cmp, n2 - 1) - 1;
-        int32_t cl = 0, cr = n2 - 1;
         bool ok = true;
-        if (amb) {
-            // identify_ambigious_diffs with room for two ends per side: nearly every read that covers an anchor still
-            // comes out with ONE haplotype; the others (and only they) go to the second pass, which has the room
-            EndSets<2> S;
-            const int e = identify_ambiguous<2>(L, cmp, S, &cl, &cr);
-            if (e == E_CAP_ENDS || (e == E_NONE && S.n_left * S.n_right > 1)) {
-                R.slow_list[slow_list_push(R.n_slow)] = (int32_t)i;
-                return;
-            }
-            if (e != E_NONE) {
-                set_error(R, i, e);
-                return;
-            }
-            h_left = S.left[0].pos;
-            h_right = S.right[0].pos;
-            for (int k = 0; k < S.left[0].n; k++) ids_out[m++] = S.left[0].ids[k];  // MAXA <= MAXI
-            for (int k = cl; k <= cr; k++)
-                if (c_type(cmp, k) != C_MATCH) {
-                    if (m < MAXI) ids_out[m++] = cmp.var[k];
-                    else ok = false;
-                }
-            for (int k = 0; k < S.right[0].n; k++) {
-                if (m < MAXI) ids_out[m++] = S.right[0].ids[k];
+        for (int k = 0; k < n2; k++)
+            if (c_type(cmp, k) != C_MATCH) {
+                if (m < MAXI) ids_out[m++] = cmp.var[k];
                 else ok = false;
             }
-        } else {
-            for (int k = 0; k < n2; k++)
-                if (c_type(cmp, k) != C_MATCH) {
-                    if (m < MAXI) ids_out[m++] = cmp.var[k];
-                    else ok = false;
-                }
+        // Does identify_ambigious_diffs have anything to do?  An entry j of Alts_left only acts on a read whose left end
+        // lies between the entry's bound and its anchor (the extent tests of common:1745-1760: left >= first token, or
+        // left > right end of a key variant; the anchor lies inside the read), and symmetrically for Alts_right and the
+        // right end (common:1867-1882).  end_flag marks those positions (typing.cu: build_walk_tables).
+        const int32_t h_left = cmp.pos[0], h_right = cmp.pos[n2 - 1] + c_len(cmp, n2 - 1) - 1;
+        bool amb = h_left < 0 || h_right >= L.L || h_right < h_left;
+        if (!amb) amb = (L.al.n > 0 && L.al.end_flag[h_left]) || (L.ar.n > 0 && L.ar.end_flag[h_right]);
+        if (amb) {
+            R.amb_list[slow_list_push(R.n_amb)] = (int32_t)i;
+            return;
         }
         if (!ok) {
             set_error(R, i, E_CAP_IDS);
@@ -1271,6 +1271,40 @@ HGT_HD void walk_record(const ReadsView &R, const WalkParams &P, const char *tex
         }
         R.h_left[i] = h_left;
         R.h_right[i] = h_right;
+        R.h_n[i] = m;
+        R.st[i] = st | ST_SURV;
+        hd_add_u64(&R.unit_reads[u], 1ull);
+    } else if (MODE == 1) {
+        int32_t *ids_out = R.h_ids + i * MAXI;
+        int m = 0;
+        int32_t cl = 0, cr = n2 - 1;
+        bool ok = true;
+        EndSets<2> S;
+        const int e = identify_ambiguous<2>(L, cmp, S, &cl, &cr);
+        if (e == E_CAP_ENDS || (e == E_NONE && S.n_left * S.n_right > 1)) {
+            R.slow_list[slow_list_push(R.n_slow)] = (int32_t)i;
+            return;
+        }
+        if (e != E_NONE) {
+            set_error(R, i, e);
+            return;
+        }
+        for (int k = 0; k < S.left[0].n; k++) ids_out[m++] = S.left[0].ids[k];  // MAXA <= MAXI
+        for (int k = cl; k <= cr; k++)
+            if (c_type(cmp, k) != C_MATCH) {
+                if (m < MAXI) ids_out[m++] = cmp.var[k];
+                else ok = false;
+            }
+        for (int k = 0; k < S.right[0].n; k++) {
+            if (m < MAXI) ids_out[m++] = S.right[0].ids[k];
+            else ok = false;
+        }
+        if (!ok) {
+            set_error(R, i, E_CAP_IDS);
+            return;
+        }
+        R.h_left[i] = S.left[0].pos;
+        R.h_right[i] = S.right[0].pos;
         R.h_n[i] = m;
         R.st[i] = st | ST_SURV;
         hd_add_u64(&R.unit_reads[u], 1ull);
