@@ -59,6 +59,10 @@ def lib():
         L.hgt_em_dev.restype = c_int
         L.hgt_em_dev.argtypes = [c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p, c_i32, c_i32,
                                  c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+        L.hgt_batch_add_units.restype = c_i64
+        L.hgt_batch_add_units.argtypes = [c_void_p, c_i64, c_void_p, c_void_p, c_void_p]
+        L.hgt_batch_abundances.restype = c_int
+        L.hgt_batch_abundances.argtypes = [c_void_p, c_i32, c_void_p, c_void_p, c_void_p, c_void_p]
         L.hgt_host_alloc.restype = c_int
         L.hgt_host_alloc.argtypes = [c_size_t, P(c_void_p)]
         L.hgt_host_free.restype = None
@@ -101,6 +105,15 @@ def ctx(device=None):
         check(lib().hgt_init(dev, ctypes.byref(h)))
         _ctx[key] = h
     return _ctx[key]
+
+
+def new_ctx(device=None):
+    """An additional context on the device (own stream, own buffer pool, own counters): batches on different contexts may
+    run from different host threads at the same time (typing_core.BatchPipeline).  Loci may be shared between them."""
+    dev = default_device() if device is None else device
+    h = c_void_p()
+    check(lib().hgt_init(dev, ctypes.byref(h)))
+    return h
 
 
 class PinnedText:

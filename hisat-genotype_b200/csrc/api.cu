@@ -1,6 +1,8 @@
 // Context, error plumbing and small helpers of libhgt.
 #include <stdarg.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 static thread_local char g_err[1024] = "";
@@ -48,6 +50,24 @@ void MemPool::drain() {
     free_dev.clear();
     free_pin.clear();
     held_dev = held_pin = 0;
+}
+
+__global__ void small_h2d_kernel(unsigned char *dst, const unsigned char *src, size_t bytes) {
+    const size_t tid = blockIdx.x * (size_t)blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+    if ((((uintptr_t)dst | (uintptr_t)src) & 15) == 0) {
+        const size_t n16 = bytes / 16;
+        for (size_t i = tid; i < n16; i += nth) reinterpret_cast<uint4 *>(dst)[i] = reinterpret_cast<const uint4 *>(src)[i];
+        for (size_t i = n16 * 16 + tid; i < bytes; i += nth) dst[i] = src[i];
+    } else {
+        for (size_t i = tid; i < bytes; i += nth) dst[i] = src[i];
+    }
+}
+cudaError_t hgt_small_h2d(void *dst_dev, const void *src_pinned, size_t bytes, cudaStream_t st) {
+    if (bytes == 0) return cudaSuccess;
+    const unsigned blocks = (unsigned)std::min<size_t>((bytes / 16 + 255) / 256 + 1, 64);
+    small_h2d_kernel<<<blocks, 256, 0, st>>>(static_cast<unsigned char *>(dst_dev), static_cast<const unsigned char *>(src_pinned),
+                                            bytes);
+    return cudaGetLastError();
 }
 
 extern "C" const char *hgt_last_error(void) { return g_err; }

@@ -42,6 +42,13 @@ struct hgt_ctx {
 
 void hgt_set_error(const char *fmt, ...);
 
+// Small host->device transfers of execute / finish (job descriptors, EM arguments: bytes to a few hundred KB) are done by
+// a kernel that reads the PAGE-LOCKED source over PCIe itself.  A cudaMemcpyAsync would queue on the host-to-device copy
+// engine behind the bulk text transfer of ANOTHER batch in flight (typing_core.BatchPipeline) and stall this batch's
+// kernels for the length of that transfer.  src must come from cudaMallocHost / cudaHostAlloc and stay untouched until
+// the stream has passed this point (the rule of cudaMemcpyAsync).
+cudaError_t hgt_small_h2d(void *dst_dev, const void *src_pinned, size_t bytes, cudaStream_t st);
+
 #include <chrono>
 struct HostTimer {  // wall-clock bracket of one host stage, accumulated into ctx->host_ms (bench.py reads it)
     hgt_ctx *ctx;

@@ -1552,7 +1552,7 @@ int em_plan_batched(const hgt_ctx *ctx, const EmShape &sh, EmArgs *a, int *na, s
 // Launches n planned problems (one CTA each): grouped by register variant, heaviest problems first inside a group.
 // h_args (host, pinned or otherwise alive until the stream has passed the copy) and d_args hold n EmArgs.
 int em_launch_batched(hgt_ctx *ctx, cudaStream_t st, int n, const EmArgs *planned, const int *na, const size_t *smem,
-                      EmArgs *h_args, EmArgs *d_args) {
+                      EmArgs *h_args, EmArgs *d_args, bool h_pinned) {
     std::vector<int> order(n);
     for (int i = 0; i < n; i++) order[i] = i;
     std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
@@ -1560,7 +1560,8 @@ int em_launch_batched(hgt_ctx *ctx, cudaStream_t st, int n, const EmArgs *planne
         return (double)planned[x].C * planned[x].A_live_max > (double)planned[y].C * planned[y].A_live_max;
     });
     for (int i = 0; i < n; i++) h_args[i] = planned[order[i]];
-    HGT_CUDA(cudaMemcpyAsync(d_args, h_args, (size_t)n * sizeof(EmArgs), cudaMemcpyHostToDevice, st));
+    if (h_pinned) HGT_CUDA(hgt_small_h2d(d_args, h_args, (size_t)n * sizeof(EmArgs), st));
+    else HGT_CUDA(cudaMemcpyAsync(d_args, h_args, (size_t)n * sizeof(EmArgs), cudaMemcpyHostToDevice, st));
     // one launch: the widest register variant serves every problem (narrower ones just skip slots), so all SMs
     // stay busy instead of running the variants back to back
     int na_max = 1;
@@ -1810,7 +1811,7 @@ extern "C" int hgt_em_batch(hgt_ctx *ctx, int32_t n_problems, const uint64_t *cl
         if (allele_len) TRY(cudaMemcpyAsync(d + o_len, allele_len, (size_t)Atot * 8, cudaMemcpyHostToDevice, st));
         TRY(cudaMemsetAsync(d + o_is, 0, (size_t)n_problems * 12, st));
         rc = em_launch_batched(ctx, st, n_problems, args.data(), nas.data(), smems.data(), h_args.data(),
-                               reinterpret_cast<EmArgs *>(d + o_args));
+                               reinterpret_cast<EmArgs *>(d + o_args), false);
         if (rc != HGT_OK) break;
         TRY(cudaMemcpyAsync(prob, d + o_prob, (size_t)Atot * 8, cudaMemcpyDeviceToHost, st));
         TRY(cudaMemcpyAsync(in_result, d + o_in, (size_t)Atot, cudaMemcpyDeviceToHost, st));
@@ -2149,10 +2150,10 @@ int hgt_em_batch_dev(hgt_ctx *ctx, cudaStream_t st, int n_problems, const EmDevP
     }
     EmArgs *h = static_cast<EmArgs *>(h_args), *d = static_cast<EmArgs *>(d_args);
     const int nb = (int)args.size();
-    if (nb > 0) HGT_CHECK(em_launch_batched(ctx, st, nb, args.data(), nas.data(), smems.data(), h, d));
+    if (nb > 0) HGT_CHECK(em_launch_batched(ctx, st, nb, args.data(), nas.data(), smems.data(), h, d, true));
     for (size_t k = 0; k < coop.size(); k++) {
         h[nb + k] = coop[k];
-        HGT_CUDA(cudaMemcpyAsync(d + nb + k, h + nb + k, sizeof(EmArgs), cudaMemcpyHostToDevice, st));
+        HGT_CUDA(hgt_small_h2d(d + nb + k, h + nb + k, sizeof(EmArgs), st));
         HGT_CHECK(em_launch<true>(ctx, st, d + nb + k, coop_g[k], coop_na[k], coop_smem[k]));
     }
     return HGT_OK;

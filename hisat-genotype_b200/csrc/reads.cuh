@@ -280,6 +280,17 @@ __device__ __forceinline__ EcMask warp_ec_masks(const ReadsView &R, const WalkPa
         const int u = R.unit[i];
         EcParams p;
         p.line = text + R.line_off[i];
+        if (text == R.text) {
+            // First touch of the line comes from HBM: every lane starts the loads of its own line's cache lines NOW (the
+            // values are not used), so the record-by-record loop below and the walk after it find them in L1 / L2.
+            const int64_t len = R.line_off[i + 1] - R.line_off[i];
+            for (int64_t o = 0; o < len; o += 128) {
+                unsigned d;
+                asm volatile("ld.global.b32 %0, [%1];" : "=r"(d) : "l"((unsigned long long)(p.line + o) & ~3ull));
+            }
+            unsigned d;
+            asm volatile("ld.global.b32 %0, [%1];" : "=r"(d) : "l"((unsigned long long)(p.line + len - 1) & ~3ull));
+        }
         p.ntm = R.nt_mask + R.unit_pos0[u];
         p.pos = f.pos;
         p.L = R.loci[R.unit_locus[u]].L;

@@ -1663,7 +1663,7 @@ static int reads_execute(hgt_batch *b, cudaStream_t st) {
         HGT_CHECK(lb.h_jobs.alloc((n_units * 4 + 1) * 8));
         memcpy(lb.h_jobs.p, lb.ut_base.data(), (n_units * 4 + 1) * 8);
         ctx->h2d_bytes += (int64_t)((n_units * 4 + 1) * 8);
-        HGT_CUDA(cudaMemcpyAsync(lb.dj<int64_t>(ja.o_ut_base), lb.h_jobs.p, (n_units * 4 + 1) * 8, cudaMemcpyHostToDevice, st));
+        HGT_CUDA(hgt_small_h2d(lb.dj<int64_t>(ja.o_ut_base), lb.h_jobs.p, (n_units * 4 + 1) * 8, st));
         HGT_CUDA(cudaMemsetAsync(lb.dj<int64_t>(ja.o_job_off), 0, 8, st));
         HGT_CUDA(cudaMemsetAsync(lb.dj<int64_t>(ja.o_row_off), 0, 8, st));
         hgtd::LocusJobs &d = hj[l];
@@ -1675,7 +1675,7 @@ static int reads_execute(hgt_batch *b, cudaStream_t st) {
         d.n_tables = n_tables;
         d.line0 = tot[5];
     }
-    HGT_CUDA(cudaMemcpyAsync(rd.d_jobs_desc.p, hj, nl * sizeof(hgtd::LocusJobs), cudaMemcpyHostToDevice, st));
+    HGT_CUDA(hgt_small_h2d(rd.d_jobs_desc.p, hj, nl * sizeof(hgtd::LocusJobs), st));
     hgtk::pair_fill_kernel<<<line_grid(ctx, N, 128, 16), 128, 0, st>>>(R);
     b->timer.end(launches);
     HGT_CUDA(cudaGetLastError());
@@ -2086,8 +2086,8 @@ static int batch_finish(hgt_batch *b, cudaStream_t st) {
         if (lb.n_level2 == 0) continue;
         const size_t n2 = (size_t)lb.n_level2;
         if (g_acct) g_acct->h2d_bytes += (int64_t)(n2 * 4 + n2 * wp * 8);
-        HGT_CUDA(cudaMemcpyAsync(lb.d_ulist.p, ulist, n2 * 4, cudaMemcpyHostToDevice, st));
-        HGT_CUDA(cudaMemcpyAsync(lb.d_keep.p, keep, n2 * wp * 8, cudaMemcpyHostToDevice, st));
+        HGT_CUDA(hgt_small_h2d(lb.d_ulist.p, ulist, n2 * 4, st));
+        HGT_CUDA(hgt_small_h2d(lb.d_keep.p, keep, n2 * wp * 8, st));
         {
             b->timer.begin(ctx, st, 5);
             dim3 grid(tune_env("HGT_PROJECT_CTAS", 16), (unsigned)std::min<size_t>(n2, 16384));
@@ -2169,6 +2169,23 @@ extern "C" int64_t hgt_batch_add_unit(hgt_batch *b, int32_t locus_index, const c
     u.n_bytes = n_bytes;
     b->units.push_back(std::move(u));
     return (int64_t)b->units.size() - 1;
+}
+
+extern "C" int64_t hgt_batch_add_units(hgt_batch *b, int64_t n, const int32_t *locus_index, const char *const *sam_text,
+                                       const size_t *n_bytes) {
+    if (!b || n < 0 || (n > 0 && (!locus_index || !sam_text || !n_bytes))) {
+        hgt_set_error("hgt_batch_add_units: bad argument");
+        return HGT_ERR_ARG;
+    }
+    const int64_t first = (int64_t)b->units.size();
+    for (int64_t k = 0; k < n; k++) {
+        const int64_t u = hgt_batch_add_unit(b, locus_index[k], sam_text[k], n_bytes[k]);
+        if (u < 0) {
+            b->units.resize((size_t)first);
+            return u;
+        }
+    }
+    return first;
 }
 
 extern "C" int hgt_batch_prepare(hgt_batch *b) {
@@ -2455,6 +2472,19 @@ extern "C" int hgt_batch_unit_abundance(const hgt_batch *b, int64_t unit, int32_
         if (allele) allele[k] = comb[k].a;
         if (prob) prob[k] = comb[k].p;
     }
+    return HGT_OK;
+}
+
+extern "C" int hgt_batch_abundances(const hgt_batch *b, int32_t cap, int32_t *allele, double *prob, int32_t *n_total,
+                                    int32_t *status) {
+    if (!b || !b->finished || cap < 0 || !n_total || !status || (cap > 0 && (!allele || !prob))) {
+        hgt_set_error("hgt_batch_abundances: bad argument or batch not finished");
+        return HGT_ERR_ARG;
+    }
+    const int64_t nu = (int64_t)b->units.size();
+    parallel_units(std::min<int>(batch_threads(b->params), 8), (size_t)nu, [&](size_t u) {
+        status[u] = hgt_batch_unit_abundance(b, (int64_t)u, cap, allele + u * (size_t)cap, prob + u * (size_t)cap, &n_total[u]);
+    });
     return HGT_OK;
 }
 

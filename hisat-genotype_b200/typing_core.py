@@ -10,6 +10,7 @@ There is no CPU fallback: everything below needs libhgt.so and a B200.
 from __future__ import annotations
 
 import ctypes
+import time
 
 import numpy as np
 
@@ -166,13 +167,13 @@ def locus_abundance(run: TypingRun, remove_low_abundance_alleles=True):
 class Batch:
     """Many (sample, locus) units through the GPU together (hgt_batch_* in include/hgt.h)."""
 
-    def __init__(self, loci, params=None, remove_low_abundance_alleles=True, device=None):
+    def __init__(self, loci, params=None, remove_low_abundance_alleles=True, device=None, ctx=None):
         self.loci = list(loci)
         self.params = params or make_params()
         self.device = device
         arr = (ctypes.c_void_p * len(self.loci))(*[t.handle for t in self.loci])
         self.handle = ctypes.c_void_p()
-        _lib.check(lib().hgt_batch_create(_lib.ctx(device), len(self.loci), arr, ctypes.byref(self.params),
+        _lib.check(lib().hgt_batch_create(ctx or _lib.ctx(device), len(self.loci), arr, ctypes.byref(self.params),
                                           1 if remove_low_abundance_alleles else 0, ctypes.byref(self.handle)))
         self._texts = []
         self.unit_locus = []
@@ -378,7 +379,36 @@ class Batch:
         return [[t.names[int(idx[i])], float(prob[i])] for i in range(k)]
 
     def top_calls(self, max_n=2):
-        return [self.unit_calls(u, max_n) for u in range(len(self.unit_locus))]
+        """unit_calls(u, max_n) of every unit, through one library call (hgt_batch_abundances)."""
+        nu, cap = len(self.unit_locus), int(max_n)
+        idx = np.zeros((max(nu, 1), max(cap, 1)), np.int32)
+        prob = np.zeros((max(nu, 1), max(cap, 1)), np.float64)
+        n = np.zeros(max(nu, 1), np.int32)
+        st = np.zeros(max(nu, 1), np.int32)
+        _lib.check(lib().hgt_batch_abundances(self.handle, cap, _lib.ptr(idx), _lib.ptr(prob), _lib.ptr(n), _lib.ptr(st)))
+        out = []
+        idx_l, prob_l, n_l, st_l = idx.tolist(), prob.tolist(), n.tolist(), st.tolist()
+        for u in range(nu):
+            t = self.loci[self.unit_locus[u]]
+            if st_l[u] != 0 or not t.is_hla:
+                out.append(self.unit_calls(u, max_n))  # raises what the reference raises / the single-class rule
+                continue
+            k = min(cap, n_l[u])
+            names = t.names
+            out.append([[names[idx_l[u][i]], prob_l[u][i]] for i in range(k)])
+        return out
+
+    def add_units_ptr(self, units):
+        """[(locus_index, address, n_bytes), ...] in one library call."""
+        n = len(units)
+        li = (ctypes.c_int32 * n)(*[u[0] for u in units])
+        ad = (ctypes.c_void_p * n)(*[u[1] for u in units])
+        nb = (ctypes.c_size_t * n)(*[u[2] for u in units])
+        first = lib().hgt_batch_add_units(self.handle, n, li, ad, nb)
+        if first < 0:
+            _lib.check(int(first))
+        self.unit_locus.extend(u[0] for u in units)
+        return int(first)
 
     def close(self):
         if self.handle is not None and self.handle.value:
@@ -390,6 +420,90 @@ class Batch:
             self.close()
         except Exception:
             pass
+
+
+class BatchPipeline:
+    """A stream of batches with `depth` of them in flight.  Each lane is a host thread with its own library context (own
+    CUDA stream, own buffer pool), so the host-to-device copy of batch k+1 runs on the copy engine while the kernels of
+    batch k run, and the host work of one batch (result read-back, Python) overlaps the GPU work of the other.  The loci
+    (device tables) are shared.  Results come back in submission order.
+
+        pipe = BatchPipeline(tables, params, depth=2)
+        for calls in pipe.map(batches, lambda batch: batch.top_calls(2)):   # batches: iterables of (locus, addr, n) or (locus, text)
+            ...
+    """
+
+    def __init__(self, loci, params=None, remove_low_abundance_alleles=True, device=None, depth=3):
+        import threading
+        self.loci, self.params, self.remove_low, self.device = list(loci), params or make_params(), remove_low_abundance_alleles, device
+        self.depth = max(1, int(depth))
+        self._local = threading.local()
+        self.trace = None  # set to a list: [t_start, t_prepared, t_executed, t_finished, t_results] of every batch
+        self._ctxs = []
+        self._lock = threading.Lock()
+        self._copy_turn = threading.Lock()
+
+    def contexts(self):
+        return list(self._ctxs)
+
+    def _ctx(self):
+        c = getattr(self._local, "ctx", None)
+        if c is None:
+            c = _lib.new_ctx(self.device)
+            self._local.ctx = c
+            with self._lock:
+                self._ctxs.append(c)
+        return c
+
+    def _one(self, units, fn):
+        b = Batch(self.loci, self.params, self.remove_low, device=self.device, ctx=self._ctx())
+        try:
+            t = [time.perf_counter()]
+            if units and all(len(unit) == 3 for unit in units):
+                b.add_units_ptr(units)
+            else:
+                for unit in units:
+                    if len(unit) == 3:
+                        b.add_unit_ptr(*unit)
+                    else:
+                        b.add_unit(*unit)
+            with self._copy_turn:  # one bulk host-to-device transfer at a time: the lanes fall out of step, so the
+                b.prepare()        # transfer of one batch runs under the kernels of the others
+            t.append(time.perf_counter())
+            b.execute()
+            t.append(time.perf_counter())
+            b.finish()
+            t.append(time.perf_counter())
+            out = fn(b)
+            t.append(time.perf_counter())
+            if self.trace is not None:
+                self.trace.append(t)
+            return out
+        finally:
+            b.close()
+
+    def map(self, batches, fn):
+        from collections import deque
+        from concurrent.futures import ThreadPoolExecutor
+        pool = getattr(self, "_pool", None)
+        if pool is None:
+            pool = self._pool = ThreadPoolExecutor(self.depth)
+        pending = deque()
+        for units in batches:
+            pending.append(pool.submit(self._one, units, fn))
+            if len(pending) >= self.depth:
+                yield pending.popleft().result()
+        while pending:
+            yield pending.popleft().result()
+
+    def close(self):
+        pool = getattr(self, "_pool", None)
+        if pool is not None:
+            pool.shutdown(wait=True)
+            self._pool = None
+        for c in self._ctxs:
+            lib().hgt_free(c)
+        self._ctxs = []
 
 
 def typing_from_alignments(base_fname, locus_tables, locus_list, alignments, simulation, num_editdist=2,

@@ -234,6 +234,9 @@ int hgt_batch_create(hgt_ctx *ctx, int32_t n_loci, hgt_locus *const *loci, const
                      int32_t remove_low_abundance_alleles, hgt_batch **out);
 void hgt_batch_free(hgt_batch *b);
 int64_t hgt_batch_add_unit(hgt_batch *b, int32_t locus_index, const char *sam_text, size_t n_bytes);
+/* n units in one call; returns the index of the first one (the others follow) or a negative status */
+int64_t hgt_batch_add_units(hgt_batch *b, int64_t n, const int32_t *locus_index, const char *const *sam_text,
+                            const size_t *n_bytes);
 /* Read-sharded locus (several processes hold disjoint reads of the same (sample, locus)): error
  * correction depends on the pileup of ALL reads (common:1124-1134), so prepare calls the hook once, after the raw
  * base counts of this process are on the device and before nt_set is derived; the hook sums dev_counts
@@ -271,6 +274,11 @@ int hgt_batch_unit_em(const hgt_batch *b, int64_t unit, int32_t level, double *p
  * status of the unit (HGT_ERR_KEY / HGT_ERR_ZERODIV mirror the reference's exceptions). */
 int hgt_batch_unit_abundance(const hgt_batch *b, int64_t unit, int32_t cap, int32_t *allele, double *prob,
                              int32_t *n_total);
+/* The same for every unit of the batch in one call (a typing service reads the calls of thousands of units per batch):
+ * allele / prob are [n_units][cap], n_total / status [n_units]; status[u] is what hgt_batch_unit_abundance returns for
+ * unit u (0, HGT_ERR_KEY, HGT_ERR_ZERODIV).  The function itself fails only on bad arguments. */
+int hgt_batch_abundances(const hgt_batch *b, int32_t cap, int32_t *allele, double *prob, int32_t *n_total,
+                         int32_t *status);
 
 /* Host EMULATION of the record stage with a caller-supplied pileup (no GPU needed; test infrastructure, not on the
  * typing path): the same __host__ __device__ functions the kernels call (csrc/walk_dev.cuh: parse, filters, mate

@@ -143,6 +143,8 @@ def test_batch_matches_reference(name, chunk_bytes):
         assert batch.unit_calls(u) == ab  # native ranking == Python combination rule (core:1771-1782)
         assert batch.unit_calls(u, 2) == ab[:2]
     assert em_i == len(g["em_calls"])
+    # every unit's calls through one library call (hgt_batch_abundances)
+    assert batch.top_calls(3) == [batch.unit_calls(u, 3) for u in range(len(g["loci"]))]
     # repeat execute+finish on the prepared batch: identical tables (pools are reset)
     batch.execute()
     batch.finish()
@@ -198,5 +200,60 @@ def test_batch_ranking_is_stable_over_runs():
                 em_i += 1
                 assert [a for a, _ in res] == [a for a, _ in ref]
         batch.close()
+    for t in loci:
+        t.close()
+
+
+def test_pipeline_matches_single_batches():
+    """BatchPipeline (several batches in flight, one host thread + library context + CUDA stream each, loci shared):
+    results come back in submission order and equal those of the batches run one at a time; pageable text and
+    page-locked text (add_units_ptr) give the same."""
+    from hisatgenotype_b200 import _lib
+    from hisatgenotype_b200 import typing_core as TC
+    g = load_golden("hla_pair_err")
+    p = g["params"]
+    db = golden_db(g)
+    genes = []
+    for cap in g["loci"]:
+        if cap["gene"] not in genes:
+            genes.append(cap["gene"])
+    names = {cap["gene"]: cap["Gene_names"] for cap in g["loci"]}
+    loci = [product_locus(g, db, gene, names[gene]) for gene in genes]
+    params = TC.make_params(p["num_editdist"], p["error_correction"], p["discordant"], p["simulation"])
+    caps = g["loci"]
+    # batches of different composition: rotate and truncate the scenario's units
+    batches = []
+    for k in range(7):
+        rot = caps[k % len(caps):] + caps[:k % len(caps)]
+        batches.append([(genes.index(c["gene"]), c["sam"]) for c in rot[:1 + k % len(caps)]])
+
+    def summarise(b):
+        return [(b.unit_summary(u)["num_reads"], b.unit_summary(u)["num_pairs"],
+                 list(map(list, b.unit_gene_cmpt(u, TC.TABLE_GENE).items()))) for u in range(len(b.unit_locus))], b.top_calls(4)
+
+    want = []
+    for units in batches:
+        b = TC.Batch(loci, params, p["remove_low"])
+        for li, sam in units:
+            b.add_unit(li, sam)
+        b.run()
+        want.append(summarise(b))
+        b.close()
+    pipe = TC.BatchPipeline(loci, params, p["remove_low"], depth=3)
+    got = list(pipe.map(batches, summarise))
+    assert len(pipe.contexts()) >= 1
+    # the same batches with the text in one page-locked allocation
+    texts = [[(li, TC._sam_bytes(sam)) for li, sam in units] for units in batches]
+    pinned = _lib.PinnedText(sum(len(t) + 16 for units in texts for _, t in units))
+    ptr_batches = [[(li,) + pinned.add(t) for li, t in units] for units in texts]
+    got_ptr = list(pipe.map(ptr_batches, summarise))
+    pipe.close()
+    pinned.close()
+    for w, a, b in zip(want, got, got_ptr):
+        assert w[0] == a[0] == b[0]
+        for x, y, z in zip(w[1], a[1], b[1]):
+            assert [n for n, _ in x] == [n for n, _ in y] == [n for n, _ in z]
+            for (_, px), (_, py), (_, pz) in zip(x, y, z):
+                assert px == pytest.approx(py, rel=1e-9) and px == pytest.approx(pz, rel=1e-9)
     for t in loci:
         t.close()
