@@ -2213,6 +2213,10 @@ extern "C" int hgt_batch_finish(hgt_batch *b, void *stream) {
         hgt_set_error("hgt_batch_finish: batch was not executed");
         return HGT_ERR_ARG;
     }
+    if (b->finished) {  // a second finish would project into the same table-3 regions again and double their counts
+        hgt_set_error("hgt_batch_finish: already finished; call hgt_batch_execute again first");
+        return HGT_ERR_ARG;
+    }
     HGT_CUDA(cudaSetDevice(b->ctx->device));
     g_acct = b->ctx;
     return batch_finish(b, stream ? static_cast<cudaStream_t>(stream) : b->ctx->stream);

@@ -558,25 +558,82 @@ def typing_from_alignments(base_fname, locus_tables, locus_list, alignments, sim
     return "".join(text), test_passed
 
 
+_TYPING_PARAMS = ("simulation", "full_path_base_fname", "locus_list", "genotype_genome", "partial", "partial_alleles",
+                  "refGenes", "Genes", "Gene_names", "Gene_lengths", "refGene_loci", "Vars", "Var_list", "Links", "aligners",
+                  "num_editdist", "assembly", "output_base", "error_correction", "keep_alignment", "allow_discordant",
+                  "type_primary_exons", "remove_low_abundance_alleles", "display_alleles", "fastq", "read_fname",
+                  "alignment_fname", "num_frag_list", "read_len", "fragment_len", "threads", "best_alleles", "verbose",
+                  "assembly_verbose", "out_dir", "dbversion", "output_allele_counts", "test_i")  # core:249-286
+
+
+def is_contracted_call(a):
+    """Is this typing() call on the path this package implements?  The other branches of the reference's typing() stay on
+    the reference: --assembly (core:1408-1540, 1791-2074), genotype-genome typing (core:372-377, 627-630),
+    CODIS pair distances (core:451-456, 680-716), linear indexes / bowtie2 (core:1597-1648), and the debug prints of
+    verbose >= 2 (core:609, 820, 1195)."""
+    base_fname = a["full_path_base_fname"].split("/")[-1]
+    return (not a["assembly"] and a["genotype_genome"] == "" and base_fname != "codis" and (a["verbose"] or 0) < 2
+            and len(a["aligners"]) > 0 and all(index_type == "graph" and aligner == "hisat2" for aligner, index_type in a["aligners"]))
+
+
+def typing_dispatch(reference_module, reference_typing, *args, **kwargs):
+    """What the drop-in module installs as typing(): the contracted path on the GPU, everything else to the reference's own
+    typing() (same positional / keyword arguments, same return value)."""
+    if len(args) > len(_TYPING_PARAMS):
+        raise TypeError("typing() takes %d positional arguments but %d were given" % (len(_TYPING_PARAMS), len(args)))
+    a = dict(zip(_TYPING_PARAMS, args))
+    for k, v in kwargs.items():
+        if k not in _TYPING_PARAMS or k in a:
+            raise TypeError("typing() got an unexpected or repeated argument '%s'" % k)
+        a[k] = v
+    a.setdefault("test_i", 0)
+    missing = [k for k in _TYPING_PARAMS if k not in a]
+    if missing:
+        raise TypeError("typing() missing required arguments: %s" % ", ".join(missing))
+    if not is_contracted_call(a):
+        return reference_typing(*args, **kwargs)
+    return typing(*[a[k] for k in _TYPING_PARAMS], _reference=reference_module)
+
+
+def genotyping_locus(*args, **kwargs):
+    """The reference's genotyping_locus (core:2278-2309: database loading, simulation harness, one typing() call per sample
+    or test) with typing() and single_abundance() replaced: a pass-through to the drop-in module, which must be first on
+    sys.path together with the reference's hisatgenotype_modules (shim/_hgt_shim.py)."""
+    import hisatgenotype_typing_core as drop_in
+    if not hasattr(drop_in, "_product"):
+        raise ImportError("hisatgenotype_typing_core on sys.path is not the drop-in module of hisat-genotype_b200/shim "
+                          "(or HGT_DISABLE is set)")
+    return drop_in.genotyping_locus(*args, **kwargs)
+
+
 def typing(simulation, full_path_base_fname, locus_list, genotype_genome, partial, partial_alleles, refGenes, Genes,
            Gene_names, Gene_lengths, refGene_loci, Vars, Var_list, Links, aligners, num_editdist, assembly, output_base,
            error_correction, keep_alignment, allow_discordant, type_primary_exons, remove_low_abundance_alleles,
            display_alleles, fastq, read_fname, alignment_fname, num_frag_list, read_len, fragment_len, threads,
-           best_alleles, verbose, assembly_verbose, out_dir, dbversion, output_allele_counts, test_i=0):
-    """Drop-in for the reference's typing() (core:249-2171) on the contracted path: graph index, no assembly, not the
-    genotype-genome / CODIS branches.  Alignment itself stays on the reference path (its own align_reads + samtools);
-    everything between the alignment file and the report runs through libhgt on the GPU."""
+           best_alleles, verbose, assembly_verbose, out_dir, dbversion, output_allele_counts, test_i=0, _reference=None):
+    """Drop-in for the reference's typing() (core:249-2171) on the contracted path (is_contracted_call): same arguments,
+    same `.report` file, same return value (test_passed in simulation mode, else None).  Alignment itself stays on the
+    reference path (its align_reads + samtools); everything between the alignment file and the report runs through libhgt
+    on the GPU.  _reference = the reference's hisatgenotype_typing_core module (given by the drop-in module; found on
+    sys.path otherwise): its align_reads is used and its VERSION files are printed in the header (core:309-325)."""
     import os
     import subprocess
     import sys
 
     from . import report
-    if assembly or genotype_genome != "":
-        raise NotImplementedError("--assembly and genotype-genome typing stay on the reference path")
-    import hisatgenotype_typing_common as ref_common  # the reference module: alignment is not re-implemented
+    a = dict(zip(_TYPING_PARAMS, (simulation, full_path_base_fname, locus_list, genotype_genome, partial, partial_alleles,
+                                  refGenes, Genes, Gene_names, Gene_lengths, refGene_loci, Vars, Var_list, Links, aligners,
+                                  num_editdist, assembly, output_base, error_correction, keep_alignment, allow_discordant,
+                                  type_primary_exons, remove_low_abundance_alleles, display_alleles, fastq, read_fname,
+                                  alignment_fname, num_frag_list, read_len, fragment_len, threads, best_alleles, verbose,
+                                  assembly_verbose, out_dir, dbversion, output_allele_counts, test_i)))
+    if _reference is None:
+        import hisatgenotype_typing_core as mod
+        _reference = getattr(mod, "_reference", mod)
+    if not is_contracted_call(a):
+        return _reference.typing(*[a[k] for k in _TYPING_PARAMS])
+    ref_common = _reference.typing_common  # the module the reference's typing() calls align_reads through (core:358)
     base_fname = full_path_base_fname.split("/")[-1]
-    if base_fname == "codis":
-        raise NotImplementedError("CODIS pair-distance logic stays on the reference path")
     report_base = "%s/%s-%s." % (out_dir, output_base, base_fname)
     if simulation:
         core_fid = str(test_i + 1)
@@ -584,47 +641,49 @@ def typing(simulation, full_path_base_fname, locus_list, genotype_genome, partia
     else:
         core_fid = "_".join(read_fname[0].split("/")[-1].split(".")[:-1])
     report_base += core_fid
-    version_dir = "/".join(os.path.dirname(ref_common.__file__).split("/")[:-1])
+    version_dir = "/".join(os.path.dirname(_reference.__file__).split("/")[:-1])  # core:310-312
     hg_version = open(version_dir + "/VERSION").read()
     h2_version = open(version_dir + "/hisat2/VERSION").read()
     out = [report.header(h2_version, hg_version, dbversion, " ".join(sys.argv))]
     test_passed = {}
     tables = {}
-    for aligner, index_type in aligners:
-        if index_type != "graph":
-            raise NotImplementedError("linear-index typing stays on the reference path")
-        remove_alignment_file = False
-        aln = alignment_fname
-        if aln == "":
-            remove_alignment_file = True
-            aln = "%s_output.bam" % base_fname if simulation else "%s.bam" % core_fid
-            ref_common.align_reads(aligner, simulation, full_path_base_fname + "." + index_type, index_type, base_fname,
-                                   read_fname, fastq, threads, aln, verbose)
-        alignments = {}
-        for entry in locus_list:
-            gene = entry[0].split("*")[0] if simulation else entry
-            if gene in alignments:
-                continue
-            if gene not in tables:
-                ref_allele = refGenes[gene]
-                loc = refGene_loci[gene]
-                tables[gene] = LocusTables(base_fname, gene, ref_allele, Genes[gene][ref_allele], Vars[gene], Var_list[gene],
-                                           Links, Gene_names[gene], Gene_lengths[gene], loc[-2], loc[-1])
-            if not os.path.exists(aln + ".bai"):
-                os.system("samtools index %s" % aln)
-            view = subprocess.Popen(["samtools", "view", aln, refGenes[gene]], stdout=subprocess.PIPE,
-                                    stderr=subprocess.DEVNULL)
-            srt = subprocess.Popen(["sort", "-k", "1,1", "-s"], stdin=view.stdout, stdout=subprocess.PIPE,
-                                   stderr=subprocess.DEVNULL)
-            alignments[gene] = srt.communicate()[0]
-        body, passed = typing_from_alignments(base_fname, tables, locus_list, alignments, simulation, num_editdist,
-                                              error_correction, allow_discordant, remove_low_abundance_alleles,
-                                              best_alleles, output_allele_counts, aligner, index_type)
-        out.append(body)
-        for k, v in passed.items():
-            test_passed[k] = test_passed.get(k, 0) + v
-        if not keep_alignment and remove_alignment_file:
-            os.system("rm %s*" % aln)
+    try:
+        for aligner, index_type in aligners:
+            remove_alignment_file = False
+            aln = alignment_fname
+            if aln == "":
+                remove_alignment_file = True
+                aln = "%s_output.bam" % base_fname if simulation else "%s.bam" % core_fid
+                ref_common.align_reads(aligner, simulation, full_path_base_fname + "." + index_type, index_type, base_fname,
+                                       read_fname, fastq, threads, aln, verbose)
+            alignments = {}
+            for entry in locus_list:
+                gene = entry[0].split("*")[0] if simulation else entry
+                if gene in alignments:
+                    continue
+                if gene not in tables:
+                    ref_allele = refGenes[gene]
+                    loc = refGene_loci[gene]
+                    tables[gene] = LocusTables(base_fname, gene, ref_allele, Genes[gene][ref_allele], Vars[gene], Var_list[gene],
+                                               Links, Gene_names[gene], Gene_lengths[gene], loc[-2], loc[-1])
+                if not os.path.exists(aln + ".bai"):
+                    os.system("samtools index %s" % aln)
+                view = subprocess.Popen(["samtools", "view", aln, refGenes[gene]], stdout=subprocess.PIPE,
+                                        stderr=subprocess.DEVNULL)
+                srt = subprocess.Popen(["sort", "-k", "1,1", "-s"], stdin=view.stdout, stdout=subprocess.PIPE,
+                                       stderr=subprocess.DEVNULL)
+                alignments[gene] = srt.communicate()[0]
+            body, passed = typing_from_alignments(base_fname, tables, locus_list, alignments, simulation, num_editdist,
+                                                  error_correction, allow_discordant, remove_low_abundance_alleles,
+                                                  best_alleles, output_allele_counts, aligner, index_type)
+            out.append(body)
+            for k, v in passed.items():
+                test_passed[k] = test_passed.get(k, 0) + v
+            if not keep_alignment and remove_alignment_file:
+                os.system("rm %s*" % aln)
+    finally:
+        for t in tables.values():
+            t.close()
     text = "".join(out)
     with open("%s.report" % report_base, "w") as f:
         f.write(text)

@@ -150,6 +150,10 @@ def test_batch_matches_reference(name, chunk_bytes):
     batch.finish()
     for u, cap in enumerate(g["loci"]):
         assert list(map(list, batch.unit_gene_cmpt(u, TC.TABLE_GENE).items())) == cap["Gene_cmpt"]
+    # finish() without a new execute() would project into the same second-level tables again: refused
+    from hisatgenotype_b200 import _lib
+    with pytest.raises(_lib.HgtError):
+        batch.finish()
     batch.close()
     for t in loci:
         t.close()
