@@ -843,32 +843,27 @@ HGT_HD bool any_anchor(const AltTab &t, int L, int32_t lo, int32_t hi) {  // con
 }
 HGT_HD bool id_is_hv(const VarTab &v, int32_t var) { return var >= 0 && ((v.flags[var] >> 1) & 1); }
 
-// Known variant ids of the entries c[lo..hi] in order (cmp_list2: a non-match entry carries a known row >= 0 or a novel
-// indel code < -1).  get_haplotype_and_seq (common:1679-1700) restated without temporary lists.
-HGT_HD int count_known(const CmpList &c, int lo, int hi) {
-    int n = 0;
-    for (int k = lo; k <= hi; k++) n += (c_type(c, k) != C_MATCH && c.var[k] >= 0);
-    return n;
-}
-HGT_HD bool has_novel(const CmpList &c, int lo, int hi) {
-    for (int k = lo; k <= hi; k++)
-        if (c_type(c, k) != C_MATCH && c.var[k] < -1) return true;
-    return false;
-}
-HGT_HD int32_t seq_len_of(const CmpList &c, int lo, int hi, int L) {
-    int32_t total = 0;
-    for (int k = lo; k <= hi; k++) {
-        const uint8_t ty = c_type(c, k);
-        if (ty == C_MATCH) {
-            const int32_t a = c.pos[k] < 0 ? 0 : (c.pos[k] > L ? L : c.pos[k]);
-            const int32_t e = c.pos[k] + c_len(c, k);
-            const int32_t b = e < 0 ? 0 : (e > L ? L : e);
-            total += b > a ? b - a : 0;
-        } else if (ty == C_MISMATCH) {
-            total += 1;
-        }
+// Totals of a slice of the list that identify_ambigious_diffs asks for at every entry (get_haplotype_and_seq,
+// common:1679-1700): known ids, novel ids, read bases.  The walk over the entries adds / removes one entry at a time.
+struct SliceTotals {
+    int known, novel;
+    int32_t seq_len;
+};
+HGT_HD void slice_add(SliceTotals &t, const CmpList &c, int k, int L, int sign) {
+    const uint8_t ty = c_type(c, k);
+    if (ty == C_MATCH) {
+        const int32_t a = c.pos[k] < 0 ? 0 : (c.pos[k] > L ? L : c.pos[k]);
+        const int32_t e = c.pos[k] + c_len(c, k);
+        const int32_t b = e < 0 ? 0 : (e > L ? L : e);
+        t.seq_len += sign * (b > a ? b - a : 0);
+    } else {
+        if (ty == C_MISMATCH) t.seq_len += sign;
+        if (c.var[k] >= 0) t.known += sign;
+        else if (c.var[k] < -1) t.novel += sign;
     }
-    return total;
+}
+HGT_HD int anchors_below(const AltTab &t, int L, int32_t x) {  // number of anchors < x
+    return (x >= 0 && x <= L + 1) ? t.below[x] : lower_bound_i32(t.anchor, t.n, x);
 }
 
 // Does the '-'-joined id string of the known ids of c[lo..hi] occur inside the entry's key (common:1734, 1856: str.find)?
@@ -911,12 +906,12 @@ HGT_HD bool id_is_prefix(const VarTab &v, int32_t a, int32_t b) {  // id string 
 // Token form, exact when the ids are regular ("hv<N>", unique) and every key token is a number or an id of the locus
 // (VarTab::tok_regular): 'h' occurs only at the start of an id token, so a match starts at a token; every id but the last
 // must then equal its key token, and the last must be a PREFIX of its key token ("hv1" is found inside "hv12").
-HGT_HD bool key_contains_ids(const VarTab &v, const AltTab &t, int e, const CmpList &c, int lo, int hi, int m) {
+// k0 = the entry of the first known id of the slice (the caller keeps it while it walks the entries).
+HGT_HD bool key_contains_ids(const VarTab &v, const AltTab &t, int e, const CmpList &c, int lo, int hi, int m, int k0) {
     if (!v.tok_regular) return key_contains_ids_chars(v, t, e, c, lo, hi, m);
     const int32_t *tr = t.tok_row + t.tok_off[e];
     const int nt = t.tok_off[e + 1] - t.tok_off[e];
-    int k0 = lo;  // first known id of the slice
-    while (c_type(c, k0) == C_MATCH || c.var[k0] < 0) k0++;
+    if (m > nt) return false;
     const int32_t r0 = c.var[k0];
     for (int s = 0; s + m <= nt; s++) {
         const int32_t t0 = tr[s];
@@ -974,7 +969,15 @@ HGT_HDN int identify_ambiguous(const LocusWalk &L, const CmpList &c, EndSets<NS>
     bool found = false;
     if (L.al.n > 0) {
         const AltTab &T = L.al;
-        for (int i = n - 1; i >= 0; i--) {
+        SliceTotals tot;  // of c[0..i]
+        tot.known = tot.novel = 0;
+        tot.seq_len = 0;
+        int first_known = n;  // entry of the first known id of the list (every left slice starts at entry 0)
+        for (int k = n - 1; k >= 0; k--) {
+            slice_add(tot, c, k, L.L, +1);
+            if (c_type(c, k) != C_MATCH && c.var[k] >= 0) first_known = k;
+        }
+        for (int i = n - 1; i >= 0; slice_add(tot, c, i, L.L, -1), i--) {
             const uint8_t ty = c_type(c, i);
             if (ty != C_MATCH) {
                 if (ty == C_INSERTION || !id_is_hv(V, c.var[i])) continue;
@@ -982,31 +985,36 @@ HGT_HDN int identify_ambiguous(const LocusWalk &L, const CmpList &c, EndSets<NS>
             const int32_t cur_left = c.pos[i];
             const int32_t cur_right = (ty == C_MATCH || ty == C_DELETION) ? c.pos[i] + c_len(c, i) - 1 : c.pos[i];
             if (!any_anchor(T, L.L, cur_left, cur_right)) continue;
-            int start = lower_bound_i32(T.anchor, T.n, cur_right + 1) + 1;
+            int start = anchors_below(T, L.L, cur_right + 1) + 1;
             if (start > T.n) start = T.n;
-            const bool novel = has_novel(c, 0, i);
-            const int32_t cur_len = seq_len_of(c, 0, i, L.L);
-            const int n_cur = count_known(c, 0, i);
+            const bool novel = tot.novel > 0;
+            const int32_t cur_len = tot.seq_len;
+            const int n_cur = tot.known;
             const int n_ids = n_cur + (novel ? 1 : 0);  // novel ids count as ids that never match
             bool hit = false;
             for (int j = start - 1; j >= 0; j--) {
                 if (T.anchor[j] < cur_left) break;
                 if (T.anchor[j] > cur_right) continue;
-                if (n_ids > 0) {
-                    if (novel || !key_contains_ids(V, T, j, c, 0, i, n_cur)) continue;
-                }
+                // The extent test (common:1745-1760) first - a few loads, and it rejects most entries - then the substring
+                // test; the error returns of the extent test only count once the substring test has passed, as before.
                 const int32_t *tok_row = T.tok_row + T.tok_off[j], *tok_num = T.tok_num + T.tok_off[j];
                 const int ntok = T.tok_off[j + 1] - T.tok_off[j] - 1;  // key.split('-')[:-1]
+                int extent_err = E_NONE;
+                bool extent_ok = true;
                 if (n_cur + 1 == ntok) {
-                    if (left < tok_num[0]) continue;
+                    extent_ok = !(left < tok_num[0]);
                 } else {
                     int k = ntok - n_cur - 1;
                     if (k < 0) k += ntok;  // Python negative index
-                    if (k < 0 || k >= ntok) return E_ALT_INDEX;
-                    const int32_t row = tok_row[k];
-                    if (row < 0) return E_ALT_TOKEN;
-                    if (left <= var_right(V, row)) continue;
+                    if (k < 0 || k >= ntok) extent_err = E_ALT_INDEX;
+                    else if (tok_row[k] < 0) extent_err = E_ALT_TOKEN;
+                    else extent_ok = !(left <= var_right(V, tok_row[k]));
                 }
+                if (extent_err == E_NONE && !extent_ok) continue;
+                if (n_ids > 0) {
+                    if (novel || !key_contains_ids(V, T, j, c, 0, i, n_cur, first_known)) continue;
+                }
+                if (extent_err != E_NONE) return extent_err;
                 hit = true;
                 for (int a = T.alt_off[j]; a < T.alt_off[j + 1]; a++) {
                     const int32_t *rows = T.altrow + T.altrow_off[a];
@@ -1067,7 +1075,12 @@ HGT_HDN int identify_ambiguous(const LocusWalk &L, const CmpList &c, EndSets<NS>
     found = false;
     if (L.ar.n > 0) {
         const AltTab &T = L.ar;
-        for (int i = 0; i < n; i++) {
+        SliceTotals tot;  // of c[i..n-1]
+        tot.known = tot.novel = 0;
+        tot.seq_len = 0;
+        for (int k = 0; k < n; k++) slice_add(tot, c, k, L.L, +1);
+        int next_known = 0;  // entry of the first known id at or after entry i
+        for (int i = 0; i < n; slice_add(tot, c, i, L.L, -1), i++) {
             const uint8_t ty = c_type(c, i);
             if (ty != C_MATCH) {
                 if (ty == C_INSERTION || !id_is_hv(V, c.var[i])) continue;
@@ -1075,30 +1088,35 @@ HGT_HDN int identify_ambiguous(const LocusWalk &L, const CmpList &c, EndSets<NS>
             const int32_t cur_left = c.pos[i];
             const int32_t cur_right = (ty == C_MATCH || ty == C_DELETION) ? c.pos[i] + c_len(c, i) - 1 : c.pos[i];
             if (!any_anchor(T, L.L, cur_left, cur_right)) continue;
-            const int start = lower_bound_i32(T.anchor, T.n, cur_left);
+            const int start = anchors_below(T, L.L, cur_left);
             if (start >= T.n || T.anchor[start] > cur_right) continue;
-            const bool novel = has_novel(c, i, n - 1);
-            const int32_t cur_len = seq_len_of(c, i, n - 1, L.L);
-            const int n_cur = count_known(c, i, n - 1);
+            const bool novel = tot.novel > 0;
+            const int32_t cur_len = tot.seq_len;
+            const int n_cur = tot.known;
             const int n_ids = n_cur + (novel ? 1 : 0);
+            if (next_known < i) next_known = i;
+            while (next_known < n && (c_type(c, next_known) == C_MATCH || c.var[next_known] < 0)) next_known++;
             bool hit = false;
             for (int j = start; j < T.n; j++) {
                 if (T.anchor[j] > cur_right) break;
                 if (T.anchor[j] < cur_left) continue;
-                if (n_ids > 0) {
-                    if (novel || !key_contains_ids(V, T, j, c, i, n - 1, n_cur)) continue;
-                }
                 const int32_t *tok_row = T.tok_row + T.tok_off[j], *tok_num = T.tok_num + T.tok_off[j];
                 const int ntok = T.tok_off[j + 1] - T.tok_off[j] - 1;  // key.split('-')[1:]
+                int extent_err = E_NONE;
+                bool extent_ok = true;
                 if (n_cur + 1 == ntok) {
-                    if (right > tok_num[ntok]) continue;
+                    extent_ok = !(right > tok_num[ntok]);
                 } else {
                     const int k = n_cur;
-                    if (k >= ntok) return E_ALT_INDEX;
-                    const int32_t row = tok_row[1 + k];
-                    if (row < 0) return E_ALT_TOKEN;
-                    if (right >= V.pos[row]) continue;
+                    if (k >= ntok) extent_err = E_ALT_INDEX;
+                    else if (tok_row[1 + k] < 0) extent_err = E_ALT_TOKEN;
+                    else extent_ok = !(right >= V.pos[tok_row[1 + k]]);
                 }
+                if (extent_err == E_NONE && !extent_ok) continue;
+                if (n_ids > 0) {
+                    if (novel || !key_contains_ids(V, T, j, c, i, n - 1, n_cur, next_known)) continue;
+                }
+                if (extent_err != E_NONE) return extent_err;
                 hit = true;
                 for (int a = T.alt_off[j]; a < T.alt_off[j + 1]; a++) {
                     const int32_t *rows = T.altrow + T.altrow_off[a];
