@@ -391,13 +391,13 @@ __global__ void __launch_bounds__(128) walk_slow_kernel(ReadsView R, WalkParams 
         if (on) walk_record<2>(R, P, R.text, i, k, M);
     }
 }
-__global__ void __launch_bounds__(128) pair_count_kernel(ReadsView R) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < R.n_lines; i += (int64_t)gridDim.x * blockDim.x)
-        pair_jobs<false>(R, i);
+__global__ void __launch_bounds__(128) pair_count_kernel(ReadsView R) {  // thread per run (head_list)
+    const int n = *R.n_heads;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) pair_jobs<false>(R, R.head_list[k]);
 }
 __global__ void __launch_bounds__(128) pair_fill_kernel(ReadsView R) {
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < R.n_lines; i += (int64_t)gridDim.x * blockDim.x)
-        pair_jobs<true>(R, i);
+    const int n = *R.n_heads;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) pair_jobs<true>(R, R.head_list[k]);
 }
 
 // per-locus totals of the pair stage from the scanned arrays: out[l][6] = pairs, haplotypes, rows, small jobs, big jobs,

@@ -1462,6 +1462,8 @@ static hgtd::ReadsView reads_view(hgt_batch *b) {
     R.err = reinterpret_cast<unsigned long long *>(sm);
     R.n_slow = reinterpret_cast<int32_t *>(sm + 8);
     R.n_amb = reinterpret_cast<int32_t *>(sm + 16);
+    R.n_heads = reinterpret_cast<int32_t *>(sm + 20);
+    R.head_list = R.slow_list + std::max<size_t>(N, 1);
     R.max_job_haps = reinterpret_cast<int32_t *>(sm + 12);
     R.unit_reads = reinterpret_cast<unsigned long long *>(sm + rd.s_reads);
     R.unit_pairs = reinterpret_cast<unsigned long long *>(sm + rd.s_pairs);
@@ -1504,7 +1506,7 @@ static int reads_execute(hgt_batch *b, cudaStream_t st) {
     HGT_CHECK(rd.d_st.alloc((size_t)std::max<int64_t>(N, 1) * 2));
     HGT_CHECK(rd.d_hdr.alloc((size_t)std::max<int64_t>(N, 1) * 16));
     HGT_CHECK(rd.d_hids.alloc((size_t)std::max<int64_t>(N, 1) * hgtd::MAXI * 4));
-    HGT_CHECK(rd.d_slow_list.alloc((size_t)std::max<int64_t>(N, 1) * 8));
+    HGT_CHECK(rd.d_slow_list.alloc((size_t)std::max<int64_t>(N, 1) * 12));  // amb_list, slow_list, head_list
     HGT_CHECK(rd.d_scan.alloc((size_t)(N + 1) * 8 * 5));
     HGT_CHECK(rd.d_cnt.alloc((size_t)std::max<int64_t>(rd.POS, 1) * 24));
     HGT_CHECK(rd.d_mf.alloc((size_t)std::max<int64_t>(rd.POS, 1) * 2));
@@ -1595,6 +1597,7 @@ static int reads_execute(hgt_batch *b, cudaStream_t st) {
         launches++;
         ctx->launches++;
     }
+    HGT_CUDA(cudaMemsetAsync(rd.d_scan.p, 0, (size_t)(N + 1) * 8 * 5, st));
     hgtk::pair_count_kernel<<<line_grid(ctx, N, 128, 16), 128, 0, st>>>(R);
     launches += 1 + 15 + 1 + 1;  // + five scans, locus totals, fill
     ctx->launches += 3;         // (the scans count themselves)
@@ -2637,12 +2640,12 @@ extern "C" int hgt_host_walk(hgt_locus *loc, const char *sam, size_t n_bytes, co
         const uint64_t dels = c[5], nts = (uint64_t)c[0] + c[1] + c[2] + c[3] + c[4];
         flag[i] = dels * 6 < nts ? 1 : 0;
     }
-    std::vector<int32_t> unit(n1), hdr(n1 * 4), hids(n1 * MAXI), slow_list(n1), amb_list(n1);
+    std::vector<int32_t> unit(n1), hdr(n1 * 4), hids(n1 * MAXI), slow_list(n1), amb_list(n1), head_list(n1);
     std::vector<RecFields> rec(n1);
     std::vector<uint16_t> stv(n1);
     std::vector<int64_t> scan((size_t)(N + 1) * 5, 0);
     int64_t unit_off[2] = {0, (int64_t)text.size()}, unit_line0[2] = {0, N}, unit_pos0[2] = {0, 0};
-    int32_t unit_locus[1] = {0}, unit_local[1] = {0}, n_slow = 0, n_amb = 0, max_job = 0;
+    int32_t unit_locus[1] = {0}, unit_local[1] = {0}, n_slow = 0, n_amb = 0, n_heads = 0, max_job = 0;
     unsigned long long err = ~0ull, unit_reads[1] = {0}, unit_pairs[1] = {0};
     LocusJobs jobs;
     memset(&jobs, 0, sizeof(jobs));
@@ -2653,6 +2656,7 @@ extern "C" int hgt_host_walk(hgt_locus *loc, const char *sam, size_t n_bytes, co
     R.h_left = hdr.data(); R.h_right = R.h_left + n1; R.h_n = R.h_right + n1; R.slow_slot = R.h_n + n1;
     R.h_ids = hids.data(); R.slow_list = slow_list.data(); R.n_slow = &n_slow;
     R.amb_list = amb_list.data(); R.n_amb = &n_amb;
+    R.head_list = head_list.data(); R.n_heads = &n_heads;
     R.n_units = 1; R.unit_off = unit_off; R.unit_line0 = unit_line0; R.unit_locus = unit_locus; R.unit_local = unit_local;
     R.unit_pos0 = unit_pos0; R.nt_mask = nt_mask; R.del_flag = flag.data(); R.loci = &loc->wt_host;
     R.err = &err; R.unit_reads = unit_reads; R.unit_pairs = unit_pairs;
@@ -2698,7 +2702,7 @@ extern "C" int hgt_host_walk(hgt_locus *loc, const char *sam, size_t n_bytes, co
     R.slow = slow.data();
     for (int k = 0; k < n_slow; k++)
         walk_record<2>(R, P, R.text, slow_list[k], k, use_mask ? record_ec_mask(R, P, R.text, slow_list[k]) : no_mask);
-    for (int64_t i = 0; i < N; i++) pair_jobs<false>(R, i);
+    for (int k = 0; k < n_heads; k++) pair_jobs<false>(R, head_list[k]);
     if (err != ~0ull) return fail();
     for (int k = 0; k < 5; k++) {
         int64_t *a = scan.data() + (size_t)k * (N + 1), run = 0;
@@ -2718,7 +2722,7 @@ extern "C" int hgt_host_walk(hgt_locus *loc, const char *sam, size_t n_bytes, co
     jobs.job_off = job_off.data(); jobs.row_off = row_off.data(); jobs.job_ut = job_ut.data(); jobs.job_pair = job_pair.data();
     jobs.job_list = job_list.data(); jobs.hap_left = hl.data(); jobs.hap_right = hr.data(); jobs.hap_table = htb.data();
     jobs.rows = rows.data(); jobs.line0 = 0; jobs.n_small = R.s_small[N]; jobs.n_tables = T;
-    for (int64_t i = 0; i < N; i++) pair_jobs<true>(R, i);
+    for (int k = 0; k < n_heads; k++) pair_jobs<true>(R, head_list[k]);
     if (err != ~0ull) return fail();
     hgt_walk *w = new hgt_walk();
     w->num_reads = (int64_t)unit_reads[0];

@@ -190,6 +190,7 @@ struct ReadsView {
     SlowRec *slow;
     int32_t *amb_list, *slow_list;  // lines queued for the second pass (an Alts anchor in reach) / the third (several haplotypes)
     int32_t *n_amb, *n_slow;
+    int32_t *head_list, *n_heads;   // run heads (any order): the pair stage runs one thread per run
     // units
     int n_units;
     const int64_t *unit_off;   // [n_units+1] byte range of every unit in the arena
@@ -473,7 +474,10 @@ HGT_HD void mark_head(const ReadsView &R, int64_t i) {
             for (int k = 0; k < x.qn_len && !head; k++) head = p[k] != q[k];
         }
     }
-    if (head) R.st[i] |= ST_HEAD;
+    if (head) {
+        R.st[i] |= ST_HEAD;
+        R.head_list[slow_list_push(R.n_heads)] = (int32_t)i;
+    }
 }
 
 // Mate de-dup (core:855-874): a record is dropped when an earlier record of the run with the same mate kind passed
@@ -1351,31 +1355,49 @@ HGT_HD void walk_record(const ReadsView &R, const WalkParams &P, const char *tex
 }
 
 // ---- pair stage ------------------------------------------------------------------------------------------------------------
-struct HtRef {  // one haplotype of a record: alternative left end a, alternative right end b (0, 0 in the common case)
-    int64_t line;
-    int32_t slot, a, b;
+// One haplotype of a record, materialised: bounds + variant ids in read order.  The common-case record has exactly one
+// (h_left / h_right / h_ids of its line); a SlowRec has n_left x n_right (left end a, middle, right end b).
+struct Hap {
+    int32_t left, right;
+    int n;
+    int32_t ids[MAXHID];
 };
-HGT_HD int32_t ht_left(const ReadsView &R, const HtRef &h) { return h.slot < 0 ? R.h_left[h.line] : R.slow[h.slot].e.left[h.a].pos; }
-HGT_HD int32_t ht_right(const ReadsView &R, const HtRef &h) { return h.slot < 0 ? R.h_right[h.line] : R.slow[h.slot].e.right[h.b].pos; }
-HGT_HD int ht_nids(const ReadsView &R, const HtRef &h) {
-    if (h.slot < 0) return R.h_n[h.line];
-    const SlowRec &S = R.slow[h.slot];
-    return S.e.left[h.a].n + S.n_mid + S.e.right[h.b].n;
+HGT_HD int haps_of(const ReadsView &R, int64_t line) {
+    const int32_t slot = R.slow_slot[line];
+    return slot < 0 ? 1 : R.slow[slot].e.n_left * R.slow[slot].e.n_right;
 }
-HGT_HD int32_t ht_id(const ReadsView &R, const HtRef &h, int k) {
-    if (h.slot < 0) return R.h_ids[h.line * MAXI + k];
-    const SlowRec &S = R.slow[h.slot];
-    if (k < S.e.left[h.a].n) return S.e.left[h.a].ids[k];
-    k -= S.e.left[h.a].n;
-    if (k < S.n_mid) return S.mid[k];
-    return S.e.right[h.b].ids[k - S.n_mid];
+// haplotype g of the record on `line`; false when it has more than MAXHID ids
+HGT_HDN bool hap_load(const ReadsView &R, int64_t line, int g, Hap &h) {
+    const int32_t slot = R.slow_slot[line];
+    if (slot < 0) {
+        h.left = R.h_left[line];
+        h.right = R.h_right[line];
+        h.n = R.h_n[line];  // <= MAXI
+        const int32_t *src = R.h_ids + line * MAXI;
+#pragma unroll 1
+        for (int k = 0; k < h.n; k++) h.ids[k] = src[k];
+        return true;
+    }
+    const SlowRec &S = R.slow[slot];
+    const AltEnd &A = S.e.left[g / S.e.n_right], &B = S.e.right[g % S.e.n_right];
+    h.left = A.pos;
+    h.right = B.pos;
+    h.n = A.n + S.n_mid + B.n;
+    if (h.n > MAXHID) return false;
+    int m = 0;
+#pragma unroll 1
+    for (int k = 0; k < A.n; k++) h.ids[m++] = A.ids[k];
+#pragma unroll 1
+    for (int k = 0; k < S.n_mid; k++) h.ids[m++] = S.mid[k];
+#pragma unroll 1
+    for (int k = 0; k < B.n; k++) h.ids[m++] = B.ids[k];
+    return true;
 }
-HGT_HD bool ht_equal(const ReadsView &R, const HtRef &x, const HtRef &y) {
-    if (ht_left(R, x) != ht_left(R, y) || ht_right(R, x) != ht_right(R, y)) return false;
-    const int n = ht_nids(R, x);
-    if (n != ht_nids(R, y)) return false;
-    for (int k = 0; k < n; k++)
-        if (ht_id(R, x, k) != ht_id(R, y, k)) return false;
+HGT_HD bool hap_equal(const Hap &x, const Hap &y) {
+    if (x.left != y.left || x.right != y.right || x.n != y.n) return false;
+#pragma unroll 1
+    for (int k = 0; k < x.n; k++)
+        if (x.ids[k] != y.ids[k]) return false;
     return true;
 }
 
@@ -1400,16 +1422,16 @@ HGT_HD VarLite var_lite(const VarTab &v, int32_t id) {
 
 // get_exon_haplotypes (core:718-792) for ONE exon: false when the haplotype does not overlap it, else the clipped
 // bounds and the kept id range [lo, hi).
-HGT_HD bool exon_clip(const ReadsView &R, const VarTab &V, const HtRef &h, int32_t e_left, int32_t e_right, int32_t *left_out,
-                      int32_t *right_out, int *lo_out, int *hi_out) {
-    int32_t left = ht_left(R, h), right = ht_right(R, h);
+HGT_HDN bool exon_clip(const VarTab &V, const Hap &h, int32_t e_left, int32_t e_right, int32_t *left_out, int32_t *right_out,
+                       int *lo_out, int *hi_out) {
+    int32_t left = h.left, right = h.right;
     if (e_left > right || e_right < left) return false;
-    const int n = ht_nids(R, h);
+    const int n = h.n;
     int lo = 0, hi = n;
     if (left < e_left) {
         bool split = false;
         for (int k = 0; k < n; k++) {
-            const VarLite v = var_lite(V, ht_id(R, h, k));
+            const VarLite v = var_lite(V, h.ids[k]);
             if ((v.type != T_DELETION && v.pos >= e_left) || (v.type == T_DELETION && v.pos - 1 >= e_left)) {
                 left = e_left;
                 lo = k;
@@ -1431,7 +1453,7 @@ HGT_HD bool exon_clip(const ReadsView &R, const VarTab &V, const HtRef &h, int32
     if (right > e_right) {
         bool split = false;
         for (int k = hi; k-- > lo;) {
-            const VarLite v = var_lite(V, ht_id(R, h, k));
+            const VarLite v = var_lite(V, h.ids[k]);
             const int32_t r = v.type == T_DELETION ? v.pos + v.len - 1 : v.pos;
             if ((v.type != T_DELETION && r <= e_right) || (v.type == T_DELETION && r + 1 <= e_right)) {
                 right = e_right;
@@ -1459,10 +1481,11 @@ HGT_HD bool exon_clip(const ReadsView &R, const VarTab &V, const HtRef &h, int32
 }
 
 // rows of Links the allele-set kernel ANDs: ids [lo, hi) that are known variants present in Links, sorted, unique
-HGT_HD int hap_rows(const ReadsView &R, const VarTab &V, const HtRef &h, int lo, int hi, int32_t *rows) {
+// (ids come in read order, i.e. nearly sorted: the insertion rarely moves anything)
+HGT_HDN int hap_rows(const VarTab &V, const Hap &h, int lo, int hi, int32_t *rows) {
     int m = 0;
     for (int k = lo; k < hi; k++) {
-        const int32_t id = ht_id(R, h, k);
+        const int32_t id = h.ids[k];
         if (id < 0 || !(V.flags[id] & 1)) continue;
         int p = m;
         while (p > 0 && rows[p - 1] > id) p--;
@@ -1477,10 +1500,13 @@ HGT_HD int hap_rows(const ReadsView &R, const VarTab &V, const HtRef &h, int lo,
 // Pair finalisation (core:1238-1347, 1545-1587) for the run that starts at head line i.
 //   FILL = false: count pass - pairs, haplotypes, rows, small / big jobs of the run into the s_* arrays (scanned later)
 //   FILL = true : write the job arrays of the locus at the scanned offsets
+// Both passes walk the same sequence: distinct haplotypes of the run (union of the mates' sets, core:1250-1251), each
+// materialised once; per haplotype the Gene-table entry, then its clips to the exons and to the primary exons.  Each
+// table of the pair keeps its own contiguous range of the job arrays (job_off), so the fill pass first repeats the
+// counting (cheap: one or two haplotypes in the common run) to place its three cursors, then writes.
 template <bool FILL>
 HGT_HD void pair_jobs(const ReadsView &R, int64_t i) {
-    if (!FILL) R.s_pairs[i] = R.s_haps[i] = R.s_rows[i] = R.s_small[i] = R.s_big[i] = 0;
-    if (!(R.st[i] & ST_HEAD)) return;
+    if (!(R.st[i] & ST_HEAD)) return;  // (the s_* arrays are zeroed before the count pass)
     const int u = R.unit[i];
     const int locus = R.unit_locus[u];
     const LocusWalk &L = R.loci[locus];
@@ -1504,127 +1530,104 @@ HGT_HD void pair_jobs(const ReadsView &R, int64_t i) {
         for (int k = 0; k < no; k++) recs[nrec++] = others[k];
     }
     if (nrec == 0) return;
-    // enumerate the union of the mates' haplotypes; haplotype g is skipped when an earlier one equals it
     int total = 0;
-    for (int r = 0; r < nrec; r++) {
-        const int32_t slot = R.slow_slot[recs[r]];
-        total += slot < 0 ? 1 : R.slow[slot].e.n_left * R.slow[slot].e.n_right;
-    }
-    auto ht_at = [&](int g) {
-        HtRef h;
-        h.line = recs[0];
-        h.slot = -1;
-        h.a = h.b = 0;
-        for (int r = 0; r < nrec; r++) {
-            const int32_t slot = R.slow_slot[recs[r]];
-            const int cnt = slot < 0 ? 1 : R.slow[slot].e.n_left * R.slow[slot].e.n_right;
-            if (g < cnt) {
-                h.line = recs[r];
-                h.slot = slot;
-                if (slot >= 0) {
-                    h.a = g / R.slow[slot].e.n_right;
-                    h.b = g % R.slow[slot].e.n_right;
-                }
-                return h;
-            }
-            g -= cnt;
-        }
-        return h;
-    };
-    auto is_dup = [&](int g, const HtRef &h) {
-        for (int q = 0; q < g; q++)
-            if (ht_equal(R, ht_at(q), h)) return true;
-        return false;
-    };
+    for (int r = 0; r < nrec; r++) total += haps_of(R, recs[r]);
+    // per-table cursors of the fill pass
+    int64_t hap_cur[3] = {0, 0, 0}, row_cur[3] = {0, 0, 0};
+    int64_t kt[3] = {0, 0, 0}, rt[3] = {0, 0, 0};
+    int64_t pair_in_locus = 0;
+    Hap h, other;
     int32_t rows[MAXHID];
-    int64_t kt[3] = {0, 0, 0}, rows_total = 0;
-    for (int g = 0; g < total; g++) {
-        const HtRef h = ht_at(g);
-        if (ht_nids(R, h) > MAXHID) {
-            set_error(R, i, E_CAP_IDS);
-            return;
-        }
-        if (total > 1 && is_dup(g, h)) continue;
-        kt[0]++;
-        rows_total += hap_rows(R, V, h, 0, ht_nids(R, h), rows);
-        if (T == 3) {
-            for (int tb = 2; tb >= 1; tb--) {
-                const int ne = tb == 2 ? L.n_pexons : L.n_exons;
-                const int32_t *ex = tb == 2 ? L.pexons : L.exons;
-                for (int x = 0; x < ne; x++) {
-                    int32_t l2, r2;
-                    int lo, hi;
-                    if (!exon_clip(R, V, h, ex[2 * x], ex[2 * x + 1], &l2, &r2, &lo, &hi)) continue;
-                    kt[tb]++;
-                    rows_total += hap_rows(R, V, h, lo, hi, rows);
+    // pass 0 (both modes): per-table totals of the run; pass 1 (FILL only): the writes
+    for (int pass = 0; pass < (FILL ? 2 : 1); pass++) {
+        const bool write = FILL && pass == 1;
+        int64_t kt_run[3] = {0, 0, 0};
+        int flat = 0;  // index of the haplotype over all records of the run
+        for (int r = 0; r < nrec; r++) {
+            const int cnt = haps_of(R, recs[r]);
+            for (int g = 0; g < cnt; g++, flat++) {
+                if (!hap_load(R, recs[r], g, h)) {
+                    set_error(R, i, E_CAP_IDS);
+                    return;
+                }
+                // an earlier equal haplotype of the run makes this one a duplicate (set union)
+                bool dup = false;
+                if (total > 1) {
+                    int f2 = 0;
+                    for (int r2 = 0; r2 <= r && !dup; r2++) {
+                        const int cnt2 = haps_of(R, recs[r2]);
+                        for (int g2 = 0; g2 < cnt2 && f2 < flat && !dup; g2++, f2++)
+                            dup = hap_load(R, recs[r2], g2, other) && hap_equal(other, h);
+                    }
+                }
+                if (dup) continue;
+                for (int tb = 0; tb < T; tb++) {
+                    const int ne = tb == 0 ? 1 : (tb == 2 ? L.n_pexons : L.n_exons);
+                    const int32_t *ex = tb == 2 ? L.pexons : L.exons;
+                    for (int x = 0; x < ne; x++) {
+                        int32_t l2 = h.left, r2 = h.right;
+                        int lo = 0, hi = h.n;
+                        if (tb > 0 && !exon_clip(V, h, ex[2 * x], ex[2 * x + 1], &l2, &r2, &lo, &hi)) continue;
+                        const int m = hap_rows(V, h, lo, hi, rows);
+                        if (write) {
+                            const LocusJobs &J = R.jobs[locus];
+                            const int64_t hp = hap_cur[tb]++;
+                            J.hap_left[hp] = l2;
+                            J.hap_right[hp] = r2;
+                            J.hap_table[hp] = tb;
+                            for (int k = 0; k < m; k++) J.rows[row_cur[tb] + k] = rows[k];
+                            row_cur[tb] += m;
+                            J.row_off[hp + 1] = row_cur[tb];
+                        } else {
+                            kt_run[tb]++;
+                            rt[tb] += m;
+                        }
+                    }
                 }
             }
         }
-    }
-    int n_small = 0;
-    int64_t kmax = 0;
-    for (int tb = 0; tb < T; tb++) {
-        if (kt[tb] > MAX_PAIR_HTS) {
-            set_error(R, i, E_PAIR_HTS);
-            return;
-        }
-        n_small += kt[tb] <= 7;
-        kmax = kt[tb] > kmax ? kt[tb] : kmax;
-    }
-    if (!FILL) {
-        R.s_pairs[i] = 1;
-        R.s_haps[i] = kt[0] + kt[1] + kt[2];
-        R.s_rows[i] = rows_total;
-        R.s_small[i] = n_small;
-        R.s_big[i] = T - n_small;
-        hd_add_u64(&R.unit_pairs[u], 1ull);
-        hd_max_i32(R.max_job_haps, (int32_t)kmax);
-        return;
-    }
-    // ---- fill -----------------------------------------------------------------------------------------------------------
-    const LocusJobs &J = R.jobs[locus];
-    const int64_t l0 = J.line0;
-    const int64_t pair_in_locus = R.s_pairs[i] - R.s_pairs[l0];
-    const int64_t pair_in_unit = R.s_pairs[i] - R.s_pairs[R.unit_line0[u]];
-    int64_t hap = R.s_haps[i] - R.s_haps[l0], row = R.s_rows[i] - R.s_rows[l0];
-    int64_t small = R.s_small[i] - R.s_small[l0], big = J.n_small + (R.s_big[i] - R.s_big[l0]);
-    for (int tb = 0; tb < T; tb++) {
-        const int64_t job = pair_in_locus * T + tb;
-        J.job_ut[job] = R.unit_local[u] * 4 + tb;
-        J.job_pair[job] = (int32_t)pair_in_unit;
-        if (kt[tb] <= 7) J.job_list[small++] = (int32_t)job;
-        else J.job_list[big++] = (int32_t)job;
-        for (int g = 0; g < total; g++) {
-            const HtRef h = ht_at(g);
-            if (total > 1 && is_dup(g, h)) continue;
-            if (tb == 0) {
-                J.hap_left[hap] = ht_left(R, h);
-                J.hap_right[hap] = ht_right(R, h);
-                J.hap_table[hap] = 0;
-                const int m = hap_rows(R, V, h, 0, ht_nids(R, h), rows);
-                for (int k = 0; k < m; k++) J.rows[row + k] = rows[k];
-                row += m;
-                hap++;
-                J.row_off[hap] = row;
-            } else {
-                const int ne = tb == 2 ? L.n_pexons : L.n_exons;
-                const int32_t *ex = tb == 2 ? L.pexons : L.exons;
-                for (int x = 0; x < ne; x++) {
-                    int32_t l2, r2;
-                    int lo, hi;
-                    if (!exon_clip(R, V, h, ex[2 * x], ex[2 * x + 1], &l2, &r2, &lo, &hi)) continue;
-                    J.hap_left[hap] = l2;
-                    J.hap_right[hap] = r2;
-                    J.hap_table[hap] = tb;
-                    const int m = hap_rows(R, V, h, lo, hi, rows);
-                    for (int k = 0; k < m; k++) J.rows[row + k] = rows[k];
-                    row += m;
-                    hap++;
-                    J.row_off[hap] = row;
+        if (pass == 0) {
+            for (int tb = 0; tb < 3; tb++) kt[tb] = kt_run[tb];
+            int n_small = 0;
+            int64_t kmax = 0;
+            for (int tb = 0; tb < T; tb++) {
+                if (kt[tb] > MAX_PAIR_HTS) {
+                    set_error(R, i, E_PAIR_HTS);
+                    return;
                 }
+                n_small += kt[tb] <= 7;
+                kmax = kt[tb] > kmax ? kt[tb] : kmax;
+            }
+            if (!FILL) {
+                R.s_pairs[i] = 1;
+                R.s_haps[i] = kt[0] + kt[1] + kt[2];
+                R.s_rows[i] = rt[0] + rt[1] + rt[2];
+                R.s_small[i] = n_small;
+                R.s_big[i] = T - n_small;
+                hd_add_u64(&R.unit_pairs[u], 1ull);
+                hd_max_i32(R.max_job_haps, (int32_t)kmax);
+                return;
+            }
+            // fill: job headers and the three cursors (tables of a pair are laid out one after the other)
+            const LocusJobs &J = R.jobs[locus];
+            const int64_t l0 = J.line0;
+            pair_in_locus = R.s_pairs[i] - R.s_pairs[l0];
+            const int64_t pair_in_unit = R.s_pairs[i] - R.s_pairs[R.unit_line0[u]];
+            int64_t hap = R.s_haps[i] - R.s_haps[l0], row = R.s_rows[i] - R.s_rows[l0];
+            int64_t small = R.s_small[i] - R.s_small[l0], big = J.n_small + (R.s_big[i] - R.s_big[l0]);
+            for (int tb = 0; tb < T; tb++) {
+                const int64_t job = pair_in_locus * T + tb;
+                J.job_ut[job] = R.unit_local[u] * 4 + tb;
+                J.job_pair[job] = (int32_t)pair_in_unit;
+                if (kt[tb] <= 7) J.job_list[small++] = (int32_t)job;
+                else J.job_list[big++] = (int32_t)job;
+                hap_cur[tb] = hap;
+                row_cur[tb] = row;
+                hap += kt[tb];
+                row += rt[tb];
+                J.job_off[job + 1] = hap;
             }
         }
-        J.job_off[job + 1] = hap;
     }
 }
 
