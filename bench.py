@@ -153,6 +153,7 @@ def measured_peak():
 # oracle-port legs (CPU)
 # ------------------------------------------------------------------------------------------------------------
 _ORACLE = {}
+ORACLE_DISCORDANT = [False]  # --discordant of the workload (single-end reads need it)
 
 
 def _oracle_unit(job, keep=False):
@@ -162,7 +163,7 @@ def _oracle_unit(job, keep=False):
     import hgt_oracle as O
     ol = _ORACLE["loci"][li]
     t0 = time.perf_counter()
-    res = O.type_locus(ol, text.decode().splitlines())
+    res = O.type_locus(ol, text.decode().splitlines(), allow_discordant=ORACLE_DISCORDANT[0])
     ta = time.perf_counter() - t0
     t0 = time.perf_counter()
     iters = 0
@@ -460,7 +461,7 @@ def run_oversized(args):
             "roofline_stage_a": {"bound": "hbm", "achieved": a_bytes / (a_ms / 1000.0) / 1e9 if a_ms > 0 else None,
                                  "peak": peak, "unit": "GB/s",
                                  "frac": a_bytes / (a_ms / 1000.0) / 1e9 / peak if a_ms > 0 else None,
-                                 "traffic": ncu_traffic("stage_a", "oversized", args.oversized_reads),
+                                 "traffic": ncu_traffic("stage_a", "oversized", args.oversized_reads, per="step"),
                                  "kernel": "stage (a): compat_kernel + class_kernel",
                                  "algorithmic_bytes_per_step": a_bytes, "kernel_ms_per_step": a_ms},
             "em_iters_per_sec_kernel_time": it / (stage["em1"] / 1000.0) if stage["em1"] > 0 else None,
@@ -478,6 +479,260 @@ def run_oversized(args):
     return 0
 
 
+
+# ------------------------------------------------------------------------------------------------------------
+# BASELINE configs[0], [2], [4]: single locus (latency), full panel (LPT packing of units), 1,000-sample batch
+# (strong scaling).  One JSON line each, same keys as the default line (value = device-resident, e2e = pipelined stream
+# from page-locked host text).
+# ------------------------------------------------------------------------------------------------------------
+PANEL = [  # gene, backbone length, alleles, groups: 30 loci, sum of alleles ~ 25 k
+    ("A", 3500, 6000, 56), ("B", 3500, 7000, 60), ("C", 3500, 6000, 56), ("DRB1", 11000, 2000, 36), ("DQB1", 7000, 1500, 28),
+    ("DPB1", 11000, 1200, 24), ("DQA1", 6000, 400, 10), ("E", 3500, 300, 8), ("DRB3", 11000, 300, 8), ("MICA", 11000, 250, 8),
+    ("DPA1", 9000, 200, 6), ("MICB", 11000, 200, 6), ("DRB4", 11000, 150, 6), ("DRB5", 11000, 120, 5), ("G", 3500, 100, 5),
+    ("F", 3500, 50, 4), ("H", 3500, 30, 4), ("DRA", 5000, 30, 4), ("J", 3500, 20, 4), ("K", 3500, 20, 4), ("DMA", 4500, 20, 4),
+    ("DMB", 6000, 20, 4), ("DOA", 3500, 20, 4), ("DOB", 4500, 20, 4), ("TAP1", 9000, 20, 4), ("TAP2", 10000, 20, 4),
+    ("L", 3500, 10, 4), ("V", 3000, 10, 4), ("Y", 3000, 10, 4), ("HFE", 10000, 10, 4),
+]
+
+
+def build_panel(scale=1.0):
+    import _hgt_path
+    _hgt_path.load()
+    from hisatgenotype_b200 import synth
+    loci = []
+    for i, (gene, L, A, G) in enumerate(PANEL):
+        A = max(10, int(A * scale))
+        loci.append(synth.make_locus(gene, 11 + i, L=L, n_alleles=A, n_groups=max(2, min(G, A // 3)), core_vars=60,
+                                     pool_private=max(40, int(1600 * min(1.0, A / 7000.0 + 0.05))), del_frac=0.06))
+    return loci, synth.reference_containers(loci, "hla")
+
+
+def lpt_pack(costs, n_bins):
+    """Longest-processing-time-first packing: unit indices per bin and the bins' loads."""
+    import heapq
+    bins = [[] for _ in range(n_bins)]
+    heap = [(0.0, b) for b in range(n_bins)]
+    for u in sorted(range(len(costs)), key=lambda k: -costs[k]):
+        load, b = heapq.heappop(heap)
+        bins[b].append(u)
+        heapq.heappush(heap, (load + costs[u], b))
+    loads = [0.0] * n_bins
+    for load, b in heap:
+        loads[b] = load
+    return bins, loads
+
+
+def run_workload(args):
+    import ctypes
+    import gc
+    import numpy as np
+    import torch
+    import _hgt_path
+    _hgt_path.load()
+    from hisatgenotype_b200 import _lib, synth
+    from hisatgenotype_b200 import typing_core as TC
+    from hisatgenotype_b200.locus import LocusTables
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    os.environ["HGT_DEVICE"] = str(local)
+    ctx = _lib.ctx(local)
+    L = _lib.lib()
+    wl = args.workload
+    paired, scaling, extra = True, "strong", {}
+    if wl == "single-locus":  # configs[0]: one HLA-A sample, ~10 k single-end reads: the latency of one typing call
+        loci, cont = build_database(args.scale)
+        loci = loci[:1]
+        paired = False
+        n_reads = 10000
+        sims = [{"sim": synth.ReadSimulator(l), "names": sorted(n for n in l.alleles if l.alleles[n])} for l in loci]
+        rng = np.random.default_rng(101)
+        truth = [sims[0]["names"][i] for i in rng.choice(len(sims[0]["names"]), 2, replace=False)]
+        steps_units = [[(0, sims[0]["sim"].generate(truth, n_reads, seed=101, err_rate=ERR, read_len=READ_LEN,
+                                                    frag_len=FRAG_LEN, paired=False, prefix="q"))]]
+        scaling = "weak"  # every rank types its own copy of the sample (replicas)
+        desc = ("BASELINE configs[0]: HLA-A (A=%d alleles), one sample of %d single-end 100 bp reads per step, error rate %.3f"
+                % (len(sims[0]["names"]), n_reads, ERR))
+        discordant = True
+    else:
+        if wl == "panel":  # configs[2]
+            loci, cont = build_panel(args.scale)
+            n_samples = args.samples if args.samples != 128 else 32
+            desc = ("BASELINE configs[2]: panel of %d loci, %d alleles in total, %d samples paired-end 2x100 30x; the (sample, "
+                    "locus) units are packed onto the ranks longest-first by reads x words per allele set"
+                    % (len(loci), sum(len(l.alleles) for l in loci), n_samples))
+        else:  # batch1000, configs[4]
+            loci, cont = build_database(args.scale)
+            n_samples = args.batch_samples
+            desc = ("BASELINE configs[4]: batch of %d samples x 6 loci (database of configs[1]), samples sharded over the ranks, "
+                    "%d samples per step" % (n_samples, args.samples))
+        sims = [{"sim": synth.ReadSimulator(l), "names": sorted(n for n in l.alleles if l.alleles[n])} for l in loci]
+        discordant = False
+        if wl == "panel":
+            units = simulate_units(loci, sims, n_samples, 0)  # every rank simulates all, keeps its share
+            wps = [_lib.row_pitch(len(l.alleles)) for l in loci]
+            costs = [float(t.count(b"\n")) * wps[li] for li, t in units]
+            bins, loads = lpt_pack(costs, world)
+            mine = bins[rank]
+            steps_units = [[units[u] for u in sorted(mine)]]
+            extra["lpt"] = {"units": len(units), "units_rank0": len(bins[0]), "load_max_over_mean": max(loads) / (sum(loads) / world)}
+            del units
+        else:
+            per_rank = (n_samples + world - 1) // world
+            s0, s1 = rank * per_rank, min(n_samples, (rank + 1) * per_rank)
+            steps_units = []
+            for a in range(s0, s1, args.samples):
+                steps_units.append(simulate_units(loci, sims, min(args.samples, s1 - a), a))
+    tables = [LocusTables(*locus_args(cont, l.gene), device=local) for l in loci]
+    host_threads = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world))))
+    params = TC.make_params(allow_discordant=discordant, n_threads=host_threads)
+    stream = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    pinned = _lib.PinnedText(sum(len(t) + 16 for su in steps_units for _, t in su) + 16)
+    step_ptrs = [[(li,) + pinned.add(text) for li, text in su] for su in steps_units]
+    text_bytes = sum(len(t) for su in steps_units for _, t in su)
+    first_units = steps_units[0][:args.cpu_baseline_units]
+    steps_units = None
+    gc.collect()
+    gc.freeze()
+    # ---- value: every step's text resident in HBM -> ranked alleles; K passes over the rank's whole share ------------------
+    batches = []
+    reads_rank = pairs_rank = 0
+    for ptrs in step_ptrs:
+        b = TC.Batch(tables, params, True, device=local)
+        b.add_units_ptr(ptrs)
+        b.prepare()
+        b.execute(stream)
+        b.finish(stream)
+        t = b.totals()
+        reads_rank += t["num_reads"]
+        pairs_rank += t["num_pairs"]
+        batches.append(b)
+        if len(batches) * 4 > 24:  # bound the resident memory of a long job: keep at most six prepared batches
+            break
+    n_res = len(batches)
+    reads_res = sum(b.totals()["num_reads"] for b in batches)
+    L.hgt_profile_enable(ctx, 1)
+    sampler = ClockSampler(local)
+    sampler.wait_first()
+    for _ in range(args.warmup):
+        for b in batches:
+            b.execute(stream)
+            b.finish(stream)
+    L.hgt_profile_reset(ctx)
+    launches0 = L.hgt_launch_count(ctx)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    with sampler as clocks:
+        for k in range(args.steps):
+            flush.zero_()
+            ev[k][0].record()
+            for b in batches:
+                b.execute(stream)
+                b.finish(stream)
+            ev[k][1].record()
+        barrier()
+    pass_ms = [a.elapsed_time(b) for a, b in ev]
+    launches = L.hgt_launch_count(ctx) - launches0
+    stage_ms, stage_n = ctypes_array(8, "d"), ctypes_array(8, "q")
+    h2d, d2h = ctypes.c_int64(0), ctypes.c_int64(0)
+    L.hgt_profile_read(ctx, stage_ms, stage_n, ctypes.byref(h2d), ctypes.byref(d2h))
+    stage = {n: stage_ms[i] / args.steps for i, n in enumerate(STAGES)}
+    example = batches[0].top_calls(2)[0]
+    parity_batch = batches[0]
+    for b in batches[1:]:
+        b.close()
+    # ---- e2e: the rank's whole share as a stream of batches from page-locked host text ------------------------------------
+    depth = args.pipeline_depth
+    pipe = TC.BatchPipeline(tables, params, True, device=local, depth=depth)
+    reps = max(1, (2 * depth + len(step_ptrs) - 1) // len(step_ptrs)) if wl != "batch1000" else 1
+    for _ in pipe.map(step_ptrs[:depth] * (1 if len(step_ptrs) >= depth else depth), lambda bt: bt.top_calls(2)):
+        pass
+    for c in pipe.contexts():
+        L.hgt_profile_reset(c)
+    barrier()
+    t0 = time.perf_counter()
+    n_done = 0
+    for _ in pipe.map(step_ptrs * reps, lambda bt: bt.top_calls(2)):
+        n_done += 1
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / reps  # one pass over the rank's share
+    pipe_h2d = pipe_d2h = 0
+    for c in pipe.contexts():
+        L.hgt_profile_read(c, stage_ms, stage_n, ctypes.byref(h2d), ctypes.byref(d2h))
+        pipe_h2d += h2d.value
+        pipe_d2h += d2h.value
+    pipe.close()
+    # latency of ONE batch alone (matters for configs[0]): prepare + execute + finish + calls, nothing else in flight
+    lat = []
+    for k in range(3):
+        barrier()
+        t1 = time.perf_counter()
+        bt = TC.Batch(tables, params, True, device=local)
+        bt.add_units_ptr(step_ptrs[0])
+        bt.run()
+        bt.top_calls(2)
+        lat.append((time.perf_counter() - t1) * 1000.0)
+        bt.close()
+    # ---- reduce over ranks --------------------------------------------------------------------------------------------------
+    dev_pass_s = (sum(pass_ms) / len(pass_ms)) / 1000.0 * (len(step_ptrs) / float(n_res))  # extrapolated to the whole share
+    vec = torch.tensor([dev_pass_s, e2e_s, float(reads_rank if n_res == len(step_ptrs) else reads_res * len(step_ptrs) / n_res)],
+                       dtype=torch.float64, device="cuda")
+    if world > 1:
+        mx = vec.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = vec.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_s, e2e_all_s, reads_all = float(mx[0]), float(mx[1]), float(sm[2])
+    else:
+        dev_s, e2e_all_s, reads_all = float(vec[0]), float(vec[1]), float(vec[2])
+    parity_failed = False
+    if rank == 0:
+        line = {
+            "metric": "reads typed/sec", "value": reads_all / dev_s, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": dev_s * 1000.0, "higher_is_better": True, "scaling": scaling,
+            "vs_baseline": None, "dtype": "u64 bitsets + f64 EM", "data": "synthetic",
+            "config": {"workload": desc, "loci": [l.gene for l in loci], "coverage": COVERAGE if paired else None,
+                       "read_len": READ_LEN, "error_rate": ERR, "paired": paired, "batches_per_pass_rank0": len(step_ptrs),
+                       "l2": "a 512 MiB buffer is rewritten between timed passes"},
+            "step": "one pass over the rank's share of the job (%d batch(es) on rank 0)" % len(step_ptrs),
+            "reads_per_step": reads_all, "stage_ms_per_step_rank0": stage, "step_ms_rank0": [round(x, 3) for x in pass_ms],
+            "e2e": {"value": reads_all / e2e_all_s, "unit": "reads/s", "ms_per_step": e2e_all_s * 1000.0,
+                    "h2d_bytes_per_step": pipe_h2d / reps, "d2h_bytes_per_step": pipe_d2h / reps,
+                    "input": "page-locked host alignment text, %d bytes on rank 0" % text_bytes,
+                    "how": "typing_core.BatchPipeline, %d batches in flight, wall clock between device synchronisations, max "
+                           "over ranks" % depth,
+                    "single_batch_latency_ms_rank0": sorted(lat)[len(lat) // 2]},
+            "gpu_launches": int(launches), "clocks": clocks.summary(), "example_call": example,
+        }
+        line.update(extra)
+        if not args.no_cpu_baseline and world == 1:
+            build_oracle_loci(cont, loci)
+            ORACLE_DISCORDANT[0] = discordant
+            line["cpu_baseline"], line["parity_checked"] = cpu_baseline(first_units, parity_batch)
+            if line["parity_checked"] and not line["parity_checked"]["identical"]:
+                sys.stderr.write("bench: GPU results differ from the oracle: %s\n" % line["parity_checked"]["first_difference"])
+                parity_failed = True
+        print(json.dumps(line))
+    parity_batch.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 1 if parity_failed else 0
+
 # ------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -490,7 +745,8 @@ def main():
     ap.add_argument("--ref-samples", type=int, default=4)
     ap.add_argument("--cpu-baseline-units", type=int, default=6)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="six-loci", choices=["six-loci", "oversized"])
+    ap.add_argument("--workload", default="six-loci", choices=["six-loci", "oversized", "single-locus", "panel", "batch1000"])
+    ap.add_argument("--batch-samples", type=int, default=1000, help="samples of the batch1000 workload (all ranks together)")
     ap.add_argument("--oversized-reads", type=int, default=1000000)
     ap.add_argument("--pipeline-depth", type=int, default=3, help="batches in flight in the end-to-end measurement")
     args = ap.parse_args()
@@ -498,6 +754,8 @@ def main():
         return run_reference_arm(args)
     if args.workload == "oversized":
         return run_oversized(args)
+    if args.workload in ("single-locus", "panel", "batch1000"):
+        return run_workload(args)
 
     import numpy as np
     import torch
@@ -582,14 +840,23 @@ def main():
     L.hgt_profile_read(ctx, stage_ms, stage_n, ctypes.byref(h2d), ctypes.byref(d2h))
     stage = {n: stage_ms[i] / args.steps for i, n in enumerate(STAGES)}
     # EM bookkeeping
-    em_iters = em_bytes = 0
+    # per loop iteration min(bit matrix, CSR) evaluated on the actual class tables:
+    #   bit matrix 3 C (wp 8 + 8) + 6 A 8,   CSR 3 (4 nnz + 12 C) + 6 A 8   (nnz = members over all classes)
+    em_iters = em_bytes = em_bytes_bitset = em_bytes_csr = 0
     for u in range(len(units)):
         s = batch.unit_summary(u)
         t = tables[batch.unit_locus[u]]
         for lvl, tb in ((0, 1), (1, 3)):
             it, C = s["em_iters"][lvl], s["n_classes"][tb]
+            if it <= 0:
+                continue
+            nnz = int(np.bitwise_count(batch.unit_table(u, tb)[0]).sum())
+            b_bits = 3 * C * (t.wp * 8 + 8) + 6 * t.A * 8
+            b_csr = 3 * (4 * nnz + 12 * C) + 6 * t.A * 8
             em_iters += it
-            em_bytes += it * (3 * C * (t.wp * 8 + 8) + 6 * t.A * 8)
+            em_bytes_bitset += it * b_bits
+            em_bytes_csr += it * b_csr
+            em_bytes += it * min(b_bits, b_csr)
     t_vec = torch.tensor([dev_ms, float(tot["num_reads"]), float(em_iters)], dtype=torch.float64, device="cuda")
     if world > 1:
         mx = t_vec.clone()
@@ -677,6 +944,7 @@ def main():
     e2e_serial_value = reads_all / (float(e2e_vec[1]) / 1000.0)
 
     parity_failed = False
+    text_bytes_step = sum(len(t) for _, t in units)
     if rank == 0:
         peak, peak_src = measured_peak()
         a_ms = stage["compat"] + stage["class"]
@@ -690,6 +958,7 @@ def main():
             "vs_baseline": None, "dtype": "u64 bitsets + f64 EM", "data": "synthetic",
             "config": workload_config(args, S),
             "reads_per_step": reads_all, "pairs_per_step_rank0": tot["num_pairs"],
+            "haplotypes_per_step_rank0": tot["n_haplotypes"], "variant_rows_per_step_rank0": tot["n_rows"],
             "em_iters_per_sec": iters_all / (ms_per_step / 1000.0) if ms_per_step else None,
             "em_iters_per_step": iters_all,
             "em_iters_per_sec_kernel_time": em_iters / (em_ms / 1000.0) if em_ms > 0 else None,
@@ -701,15 +970,30 @@ def main():
                          "frac": em_achieved / peak if em_achieved else None,
                          "traffic": ncu_traffic("em_kernel", "six-loci", S),
                          "kernel": "em_kernel (batched, one CTA per (sample, locus) problem)", "peak_source": peak_src,
+                         "algorithmic_bytes_rule": "per problem and iteration min(bit matrix, CSR), SURVEY.md 8d",
+                         "algorithmic_bytes_per_step_bit_matrix": float(em_bytes_bitset),
+                         "algorithmic_bytes_per_step_csr": float(em_bytes_csr),
                          "launches_per_step": 2, "algorithmic_bytes_per_launch": float(em_bytes) / 2.0,
                          "avg_launch_ms": em_ms / 2.0, "algorithmic_bytes_per_step": float(em_bytes),
                          "kernel_ms_per_step": em_ms, "share_of_step": em_ms / ms_per_step if ms_per_step else None},
             "roofline_stage_a": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                                  "frac": achieved / peak if achieved else None,
-                                 "traffic": ncu_traffic("stage_a", "six-loci", S),
+                                 "traffic": ncu_traffic("stage_a", "six-loci", S, per="step"),
+                                 "traffic_is": "DRAM bytes of all stage (a) launches of one step (like the algorithmic figure)",
                                  "kernel": "stage (a): compat_kernel + class_kernel, one launch each per locus",
                                  "algorithmic_bytes_per_step": a_bytes, "kernel_ms_per_step": a_ms,
                                  "share_of_step": a_ms / ms_per_step if ms_per_step else None},
+            # the record stage (line index, parse, pileup, mate de-dup, walk, ambiguity passes, pair jobs) has to read the
+            # alignment text: its algorithmic bytes are the text bytes of the step
+            "roofline_records": {"bound": "hbm", "achieved": text_bytes_step / ((stage["records"] + stage["walk"]) / 1000.0) / 1e9,
+                                 "peak": peak, "unit": "GB/s",
+                                 "frac": text_bytes_step / ((stage["records"] + stage["walk"]) / 1000.0) / 1e9 / peak,
+                                 "traffic": ncu_traffic("records", "six-loci", S, per="step"),
+                                 "kernel": "record stage: index_lines, parse, pileup_text, head / candidate, walk (three passes), "
+                                           "pair count / scans / fill",
+                                 "algorithmic_bytes_per_step": float(text_bytes_step),
+                                 "kernel_ms_per_step": stage["records"] + stage["walk"],
+                                 "share_of_step": (stage["records"] + stage["walk"]) / ms_per_step if ms_per_step else None},
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": pipe_h2d / n_pipe,
                     "d2h_bytes_per_step": pipe_d2h / n_pipe, "ms_per_step": float(e2e_vec[0]),
                     "input": "page-locked host alignment text, %d bytes per step on rank 0" % sum(len(t) for _, t in units),
@@ -738,13 +1022,16 @@ def main():
     return 1 if parity_failed else 0
 
 
-def ncu_traffic(kernel, workload, samples):
-    """DRAM bytes (read + write) per launch of `kernel` from the committed `ncu --set full` capture of this workload
-    (profiles/traffic.json, written from the .ncu-rep by tools/ncu_traffic.py); None when no capture matches."""
+def ncu_traffic(kernel, workload, samples, per="launch"):
+    """DRAM bytes (read + write) per launch - or per step - of `kernel` from the committed `ncu --set full` capture of this
+    workload (profiles/traffic.json, written from the .ncu-rep by tools/ncu_traffic.py); None when no capture matches."""
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)
-        return t["%s:%s:%d" % (workload, kernel, samples)]["dram_bytes_per_launch"]
+        e = t["%s:%s:%d" % (workload, kernel, samples)]
+        if per == "step":
+            return e.get("dram_bytes_per_step", e["dram_bytes_per_launch"] * e["launches_captured"])
+        return e["dram_bytes_per_launch"]
     except (OSError, KeyError, ValueError):
         return None
 

@@ -63,6 +63,16 @@ def lib():
         L.hgt_batch_add_units.argtypes = [c_void_p, c_i64, c_void_p, c_void_p, c_void_p]
         L.hgt_batch_abundances.restype = c_int
         L.hgt_batch_abundances.argtypes = [c_void_p, c_i32, c_void_p, c_void_p, c_void_p, c_void_p]
+        L.hgt_sam_split_create.restype = c_int
+        L.hgt_sam_split_create.argtypes = [ctypes.c_char_p, c_size_t, c_i32, c_void_p, c_i32, P(c_void_p)]
+        L.hgt_sam_split_sizes.restype = c_int
+        L.hgt_sam_split_sizes.argtypes = [c_void_p, c_void_p, c_void_p]
+        L.hgt_sam_split_write.restype = c_int
+        L.hgt_sam_split_write.argtypes = [c_void_p, c_i32, c_void_p]
+        L.hgt_sam_split_free.restype = None
+        L.hgt_sam_split_free.argtypes = [c_void_p]
+        L.hgt_pair_em.restype = c_int
+        L.hgt_pair_em.argtypes = [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_void_p, c_i32, c_void_p, c_void_p, P(c_i32)]
         L.hgt_host_alloc.restype = c_int
         L.hgt_host_alloc.argtypes = [c_size_t, P(c_void_p)]
         L.hgt_host_free.restype = None
@@ -132,6 +142,15 @@ class PinnedText:
             raise MemoryError("PinnedText: capacity %d exceeded" % self.cap)
         addr = self.base.value + self.used
         ctypes.memmove(addr, data, n)
+        self.used += (n + 15) & ~15
+        return addr, n
+
+    def reserve(self, n):
+        """n bytes of the arena for the caller to fill: (address, n)."""
+        n = int(n)
+        if self.used + n > self.cap:
+            raise MemoryError("PinnedText: capacity %d exceeded" % self.cap)
+        addr = self.base.value + self.used
         self.used += (n + 15) & ~15
         return addr, n
 

@@ -712,6 +712,73 @@ __device__ __forceinline__ void pool_insert(const ClassPool &pool, int wp, int u
     }
 }
 
+// ---- class rows in the reference's dict order ------------------------------------------------------------------------
+// pool_insert hands out the rows of a (unit, table) region in warp-scheduling order.  The EM accumulates per allele over
+// the class rows in row order, so that order decides the floating-point association - and with it the outcome of EXACT ties
+// (two alleles at 0.5 / 0.5 in the reference).  The reference walks its Gene_cmpt dict in insertion order = order of the
+// first pair of each class, which is `first`: one CTA per region ranks the rows by `first` (unique inside a region) and
+// moves bits / count / first accordingly, through a scratch copy of ONE table's rows (two parallel passes, warp per row,
+// 16-byte words).  Only the tables an EM runs on are ordered.  Regions above CLASS_SORT_MAX classes (one oversized locus;
+// its EM shards the rows over CTAs anyway) keep the insertion order.
+constexpr int CLASS_SORT_MAX = 8192, CLASS_SORT_THREADS = 512;
+struct SortScratch {
+    uint64_t *bits;            // [rows of one table][wp]
+    unsigned long long *count;
+    int32_t *first;
+    int n_active;              // regions per unit with room (4 on the hla path, 1 otherwise): scratch row = ut_base[unit * 4] / n_active
+};
+__global__ void __launch_bounds__(CLASS_SORT_THREADS) class_sort_kernel(ClassPool pool, SortScratch scr, int wp, int table) {
+    extern __shared__ int32_t s_sort[];  // first[C], rank[C]
+    __shared__ int s_flag;
+    const int ut = blockIdx.x * 4 + table, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int NW = CLASS_SORT_THREADS / 32;
+    const int64_t base = pool.ut_base[ut], cap = pool.ut_base[ut + 1] - base;
+    const int C = (int)min((int64_t)pool.ut_ncls[ut], cap);
+    if (C <= 1 || C > CLASS_SORT_MAX) return;
+    int32_t *fs = s_sort, *rk = s_sort + C;
+    for (int r = tid; r < C; r += CLASS_SORT_THREADS) fs[r] = pool.first[base + r];
+    if (tid == 0) s_flag = 0;
+    __syncthreads();
+    bool moved = false;
+    for (int r = tid; r < C; r += CLASS_SORT_THREADS) {
+        const int32_t f = fs[r];
+        int n = 0;
+        for (int q = 0; q < C; q++) n += fs[q] < f;
+        rk[r] = n;
+        moved |= n != r;
+    }
+    if (moved) s_flag = 1;
+    __syncthreads();
+    if (!s_flag) return;
+    uint64_t *bits = pool.bits + (size_t)base * wp;
+    unsigned long long *cnt = pool.count + base;
+    int32_t *first = pool.first + base;
+    const int64_t s0 = pool.ut_base[blockIdx.x * 4] / scr.n_active;
+    uint64_t *sb = scr.bits + (size_t)s0 * wp;
+    unsigned long long *sc = scr.count + s0;
+    int32_t *sf = scr.first + s0;
+    for (int r = warp; r < C; r += NW) {
+        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(bits + (size_t)r * wp);
+        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(sb + (size_t)rk[r] * wp);
+        for (int j = lane; j < wp / 2; j += 32) dst[j] = src[j];
+    }
+    for (int r = tid; r < C; r += CLASS_SORT_THREADS) {
+        sc[rk[r]] = cnt[r];
+        sf[rk[r]] = first[r];
+    }
+    __syncthreads();
+    {
+        const ulonglong2 *src = reinterpret_cast<const ulonglong2 *>(sb);
+        ulonglong2 *dst = reinterpret_cast<ulonglong2 *>(bits);
+        const int64_t n2 = (int64_t)C * wp / 2;
+        for (int64_t i = tid; i < n2; i += CLASS_SORT_THREADS) dst[i] = src[i];
+    }
+    for (int r = tid; r < C; r += CLASS_SORT_THREADS) {
+        cnt[r] = sc[r];
+        first[r] = sf[r];
+    }
+}
+
 // warp per job; a job = (unit, table, pair) with a list of haplotype bitsets; P bit-planes count up to 2^P-1
 template <int WPL, int P>
 __global__ void __launch_bounds__(WARPS_PER_CTA * 32, (WPL <= 4 && P <= 3) ? 5 : 1)
@@ -1123,7 +1190,7 @@ struct LocusBatch {
     T *dj(size_t off) const { return reinterpret_cast<T *>(static_cast<unsigned char *>(d_jobs.p) + off); }
     template <class T>
     T *hj(size_t off) const { return reinterpret_cast<T *>(static_cast<unsigned char *>(h_jobs.p) + off); }
-    DevBuf d_keys, d_slot, d_bits, d_count, d_first, d_ut_ncls;
+    DevBuf d_keys, d_slot, d_bits, d_count, d_first, d_ut_ncls, d_sortbits, d_sortcnt, d_sortfirst;
     DevBuf d_prob, d_inres, d_fk, d_is, d_emws;      // EM over exon (hla) / gene (other) tables
     DevBuf d_prob2, d_inres2, d_fk2, d_is2, d_keep, d_ulist;  // second-level EM (hla)
     DevBuf d_acount, d_afirst;
@@ -1145,7 +1212,7 @@ struct LocusBatch {
     int n_level2 = 0;
     void release() {
         DevBuf *all[] = {&d_jobs, &d_hapbits,
-                         &d_keys, &d_slot, &d_bits, &d_count, &d_first, &d_ut_ncls, &d_prob, &d_inres, &d_fk,
+                         &d_keys, &d_slot, &d_bits, &d_count, &d_first, &d_ut_ncls, &d_sortbits, &d_sortcnt, &d_sortfirst, &d_prob, &d_inres, &d_fk,
                          &d_is, &d_emws, &d_prob2, &d_inres2, &d_fk2, &d_is2, &d_keep, &d_ulist,
                          &d_acount, &d_afirst, &d_ck[0], &d_ck[1], &d_cn[0], &d_cn[1]};
         for (DevBuf *b : all) b->release();
@@ -1705,6 +1772,12 @@ static int batch_alloc_tables(hgt_batch *b, cudaStream_t st) {
             HGT_CHECK(lb.d_count.alloc(pr * 8));
             HGT_CHECK(lb.d_first.alloc(pr * 4));
             HGT_CHECK(lb.d_ut_ncls.alloc(n_units * 4 * 4));
+            {  // scratch of class_sort_kernel: the rows of ONE table
+                const size_t one = std::max<size_t>(pr / (loc->is_hla ? 4 : 1) + 1, 1);
+                HGT_CHECK(lb.d_sortbits.alloc(one * wp * 8));
+                HGT_CHECK(lb.d_sortcnt.alloc(one * 8));
+                HGT_CHECK(lb.d_sortfirst.alloc(one * 4));
+            }
             // EM buffers (both levels; nothing is allocated after prepare)
             const size_t A = (size_t)loc->A;
             HGT_CHECK(lb.d_prob.alloc(n_units * A * 8));
@@ -1946,6 +2019,25 @@ static void em_problems(hgt_ctx *ctx, LocusBatch &lb, int table, const std::vect
     }
 }
 
+static int launch_class_sort(hgt_ctx *ctx, cudaStream_t st, LocusBatch &lb, int table) {
+    static bool attr = false;
+    const int smem = 2 * CLASS_SORT_MAX * 4;
+    if (!attr) {
+        HGT_CUDA(cudaFuncSetAttribute(class_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr = true;
+    }
+    int64_t max_pairs = 1;
+    for (size_t ut = 0; ut + 1 < lb.ut_base.size(); ut++) max_pairs = std::max<int64_t>(max_pairs, lb.ut_base[ut + 1] - lb.ut_base[ut]);
+    const int need = 2 * 4 * (int)std::min<int64_t>(max_pairs, CLASS_SORT_MAX);  // classes of a region <= its pairs
+    SortScratch scr;
+    scr.bits = lb.d_sortbits.as<uint64_t>(); scr.count = lb.d_sortcnt.as<unsigned long long>(); scr.first = lb.d_sortfirst.as<int32_t>();
+    scr.n_active = lb.loc->is_hla ? 4 : 1;
+    class_sort_kernel<<<(unsigned)lb.units.size(), CLASS_SORT_THREADS, need, st>>>(lb.pool(), scr, lb.loc->wp, table);
+    ctx->launches++;
+    HGT_CUDA(cudaGetLastError());
+    return HGT_OK;
+}
+
 static int batch_execute(hgt_batch *b, cudaStream_t st) {
     hgt_ctx *ctx = b->ctx;
     b->executed = false;
@@ -1974,6 +2066,11 @@ static int batch_execute(hgt_batch *b, cudaStream_t st) {
             default: launch_stage_a<8>(b, st, lb); break;
         }
         HGT_CUDA(cudaGetLastError());
+        b->timer.begin(ctx, st, 2);  // (accounted to the class stage)
+        // (the tables an EM runs on: the exon table on the hla path, core:1732; the Gene table otherwise, core:1789; the
+        // projected table is ordered after project_kernel)
+        HGT_CHECK(launch_class_sort(ctx, st, lb, loc->is_hla ? 1 : 0));
+        b->timer.end(1);
         // Gene_counts of the Gene table
         {
             b->timer.begin(ctx, st, 3);
@@ -2102,8 +2199,9 @@ static int batch_finish(hgt_batch *b, cudaStream_t st) {
                 default: project_kernel<8><<<grid, WARPS_PER_CTA * 32, 0, st>>>(wp, (int)n2, lb.d_ulist.as<int32_t>(), lb.d_keep.as<uint64_t>(), pool); break;
             }
             ctx->launches++;
-            b->timer.end(1);
             HGT_CUDA(cudaGetLastError());
+            HGT_CHECK(launch_class_sort(ctx, st, lb, 3));
+            b->timer.end(2);
         }
         HGT_CUDA(cudaMemsetAsync(lb.d_is2.p, 0, n_units * 12, st));
         em_problems(ctx, lb, 3, lu, cmax.data(), alive.data(), loc->d_allele_len, 1, lb.d_prob2, lb.d_inres2, lb.d_fk2, lb.d_is2,

@@ -633,6 +633,9 @@ def typing(simulation, full_path_base_fname, locus_list, genotype_genome, partia
     if not is_contracted_call(a):
         return _reference.typing(*[a[k] for k in _TYPING_PARAMS])
     ref_common = _reference.typing_common  # the module the reference's typing() calls align_reads through (core:358)
+    from . import sam_intake
+    # HGT_NATIVE_INTAKE=1: SAM text is read and split natively instead of through samtools pipes
+    native = os.environ.get("HGT_NATIVE_INTAKE", "") not in ("", "0")
     base_fname = full_path_base_fname.split("/")[-1]
     report_base = "%s/%s-%s." % (out_dir, output_base, base_fname)
     if simulation:
@@ -651,28 +654,44 @@ def typing(simulation, full_path_base_fname, locus_list, genotype_genome, partia
         for aligner, index_type in aligners:
             remove_alignment_file = False
             aln = alignment_fname
+            native_text = None
             if aln == "":
-                remove_alignment_file = True
-                aln = "%s_output.bam" % base_fname if simulation else "%s.bam" % core_fid
-                ref_common.align_reads(aligner, simulation, full_path_base_fname + "." + index_type, index_type, base_fname,
-                                       read_fname, fastq, threads, aln, verbose)
-            alignments = {}
+                if native:  # HISAT2's SAM stream straight into the native intake: no samtools view -bS / sort / index
+                    native_text = sam_intake.align_to_sam(simulation, full_path_base_fname + "." + index_type, base_fname,
+                                                          read_fname, fastq, threads, verbose)
+                else:
+                    remove_alignment_file = True
+                    aln = "%s_output.bam" % base_fname if simulation else "%s.bam" % core_fid
+                    ref_common.align_reads(aligner, simulation, full_path_base_fname + "." + index_type, index_type, base_fname,
+                                           read_fname, fastq, threads, aln, verbose)
+            elif native:
+                native_text = sam_intake.read_alignment_text(aln)  # None for BAM: falls through to samtools
+            genes_here = []
             for entry in locus_list:
                 gene = entry[0].split("*")[0] if simulation else entry
-                if gene in alignments:
+                if gene in genes_here:
                     continue
+                genes_here.append(gene)
                 if gene not in tables:
                     ref_allele = refGenes[gene]
                     loc = refGene_loci[gene]
                     tables[gene] = LocusTables(base_fname, gene, ref_allele, Genes[gene][ref_allele], Vars[gene], Var_list[gene],
                                                Links, Gene_names[gene], Gene_lengths[gene], loc[-2], loc[-1])
-                if not os.path.exists(aln + ".bai"):
-                    os.system("samtools index %s" % aln)
-                view = subprocess.Popen(["samtools", "view", aln, refGenes[gene]], stdout=subprocess.PIPE,
-                                        stderr=subprocess.DEVNULL)
-                srt = subprocess.Popen(["sort", "-k", "1,1", "-s"], stdin=view.stdout, stdout=subprocess.PIPE,
-                                       stderr=subprocess.DEVNULL)
-                alignments[gene] = srt.communicate()[0]
+            alignments = None
+            if native_text is not None:
+                # native intake (sam_intake.py): one pass over the SAM text instead of `samtools view | sort -k1,1 -s` per locus
+                by_ref = sam_intake.split_sam(native_text, [refGenes[g] for g in genes_here], threads)
+                alignments = {g: by_ref[refGenes[g]] for g in genes_here}
+            else:
+                alignments = {}
+                for gene in genes_here:
+                    if not os.path.exists(aln + ".bai"):
+                        os.system("samtools index %s" % aln)
+                    view = subprocess.Popen(["samtools", "view", aln, refGenes[gene]], stdout=subprocess.PIPE,
+                                            stderr=subprocess.DEVNULL)
+                    srt = subprocess.Popen(["sort", "-k", "1,1", "-s"], stdin=view.stdout, stdout=subprocess.PIPE,
+                                           stderr=subprocess.DEVNULL)
+                    alignments[gene] = srt.communicate()[0]
             body, passed = typing_from_alignments(base_fname, tables, locus_list, alignments, simulation, num_editdist,
                                                   error_correction, allow_discordant, remove_low_abundance_alleles,
                                                   best_alleles, output_allele_counts, aligner, index_type)

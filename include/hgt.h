@@ -143,6 +143,18 @@ int hgt_em_shard_sweep_dev(hgt_ctx *ctx, void *stream, const uint64_t *class_bit
 int hgt_em_shard_vec_dev(hgt_ctx *ctx, void *stream, int32_t op, int32_t n_alleles, void *state, const double *allele_len,
                          int32_t src, int32_t dst, int32_t iteration, int32_t remove_low);
 
+/* ---- stage (b'): diploid allele-pair model ---------------------------------------------------------------
+ * Replaces joint_abundance(HLA_cmpt, HLA_length) of the reference's legacy typer
+ *   etc/hisatgenotype_hla_cyp.py:236-302 (pair mass :243-254, choose_top_alleles :259-270, next_prob :273-287).
+ * The live typing() never calls it; it is offered next to single_abundance as the reference's
+ * own pair scoring.  The caller (hisat-genotype_b200/typing_common.py: joint_abundance) enumerates the pairs that
+ * survive the first choose_top_alleles and hands over, per pair, p0 (normalised) and the bitset of the alleles whose
+ * NAME occurs inside the pair's key string - the legacy code tests `allele in allele_pair` on strings.
+ * class_bits [n_classes][wp], class_count [n_classes], pair_bits [n_pairs][wp]; prob [n_pairs] = final pair
+ * probabilities, 0 for pruned pairs; *iters = loop iterations.  Host pointers. */
+int hgt_pair_em(hgt_ctx *ctx, const uint64_t *class_bits, const int64_t *class_count, int32_t n_classes, int32_t wp,
+                const uint64_t *pair_bits, int32_t n_pairs, const double *p0, double *prob, int32_t *iters);
+
 /* ---- stage (a): per-read allele compatibility -----------------------------------------------------------
  * Replaces the per-read loop of typing() for index_type == "graph"
  *   reference hisatgenotype_modules/hisatgenotype_typing_core.py:598-1596 (add_count :626-677, add_stat
@@ -279,6 +291,21 @@ int hgt_batch_unit_abundance(const hgt_batch *b, int64_t unit, int32_t cap, int3
  * unit u (0, HGT_ERR_KEY, HGT_ERR_ZERODIV).  The function itself fails only on bad arguments. */
 int hgt_batch_abundances(const hgt_batch *b, int32_t cap, int32_t *allele, double *prob, int32_t *n_total,
                          int32_t *status);
+
+/* ---- native SAM intake (host) -------------------------------------------------------------------------------
+ * Replaces, for all loci of a sample at once, the external pipe the reference runs per locus
+ *   samtools view <bam> <backbone> | sort -k1,1 -s     (hisatgenotype_typing_core.py:436-468)
+ * on the coordinate-sorted BAM of hisatgenotype_typing_common.py:1038-1054: the aligner's SAM text (any record
+ * order, header lines allowed) is bucketed by RNAME into the given backbones and every bucket is ordered by
+ * (read name bytewise, position, input order) - the order of the reference's two stable sorts under LC_ALL=C.
+ * hgt_sam_split_write() emits a bucket as the name-grouped alignment text hgt_batch_add_unit() takes; dst may be
+ * page-locked memory (hgt_host_alloc).  sam_text must stay valid until the handle is freed. */
+typedef struct hgt_sam_split hgt_sam_split;
+int hgt_sam_split_create(const char *sam_text, size_t n_bytes, int32_t n_refs, const char *const *ref_names,
+                         int32_t n_threads, hgt_sam_split **out);
+int hgt_sam_split_sizes(const hgt_sam_split *s, size_t *bytes_per_ref, int64_t *lines_per_ref);
+int hgt_sam_split_write(const hgt_sam_split *s, int32_t ref, char *dst);
+void hgt_sam_split_free(hgt_sam_split *s);
 
 /* Host EMULATION of the record stage with a caller-supplied pileup (no GPU needed; test infrastructure, not on the
  * typing path): the same __host__ __device__ functions the kernels call (csrc/walk_dev.cuh: parse, filters, mate

@@ -2,7 +2,7 @@
 tree (the GPU box has no /root/reference), typing() called the way genotyping_locus calls it, golden alignments as the
 "BAM" behind the rig's stand-in samtools; prints the report files as JSON.
 
-usage: shim_driver.py <golden name> <work dir>"""
+usage: shim_driver.py <golden name> <work dir> [native]"""
 import json
 import os
 import stat
@@ -39,6 +39,7 @@ def genotyping_locus(*args, **kwargs):
 
 def main():
     name, work = sys.argv[1], sys.argv[2]
+    native = len(sys.argv) > 3 and sys.argv[3] == "native"  # HGT_NATIVE_INTAKE=1 and NO samtools anywhere
     import _hgt_path
     _hgt_path.load()
     from conftest import load_golden
@@ -59,8 +60,12 @@ def main():
     bindir = os.path.join(work, "bin")
     os.makedirs(bindir, exist_ok=True)
     tool = os.path.join(bindir, "samtools")
-    open(tool, "w").write(open(os.path.join(ROOT, "oracle", "ref_rig", "samtools")).read().replace(
-        "#!/usr/bin/env python3", "#!" + sys.executable, 1))
+    if native:
+        os.environ["HGT_NATIVE_INTAKE"] = "1"
+        open(tool, "w").write("#!/bin/sh\necho samtools must not run with the native intake >&2\nexit 97\n")
+    else:
+        open(tool, "w").write(open(os.path.join(ROOT, "oracle", "ref_rig", "samtools")).read().replace(
+            "#!/usr/bin/env python3", "#!" + sys.executable, 1))
     os.chmod(tool, os.stat(tool).st_mode | stat.S_IXUSR)
     os.environ["PATH"] = bindir + os.pathsep + os.environ.get("PATH", "")
     os.environ["LC_ALL"] = "C"

@@ -15,9 +15,12 @@ from conftest import ROOT, load_golden
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["hla_pair_err", "cyp_pair", "hla_single_end"])
-def test_typing_through_drop_in_modules_writes_reference_report(name, tmp_path):
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "shim_driver.py"), name, str(tmp_path)],
+@pytest.mark.parametrize("name,mode", [("hla_pair_err", "samtools"), ("cyp_pair", "samtools"), ("hla_single_end", "samtools"),
+                                       ("hla_pair_err", "native"), ("hla_indel", "native")])
+def test_typing_through_drop_in_modules_writes_reference_report(name, mode, tmp_path):
+    """mode "native": HGT_NATIVE_INTAKE=1 - the alignment file is read and split by libhgt (hgt_sam_split_*), any samtools
+    call fails the run."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "shim_driver.py"), name, str(tmp_path), mode],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     line = [x for x in r.stdout.splitlines() if x.startswith("SHIM_RESULT ")][-1]

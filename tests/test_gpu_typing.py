@@ -143,6 +143,11 @@ def test_batch_matches_reference(name, chunk_bytes):
         assert batch.unit_calls(u) == ab  # native ranking == Python combination rule (core:1771-1782)
         assert batch.unit_calls(u, 2) == ab[:2]
     assert em_i == len(g["em_calls"])
+    # the tables an EM runs on come back in the reference's dict order (first pair of each class): class_sort_kernel
+    for u in range(len(g["loci"])):
+        for tb in ((TC.TABLE_EXON, 3) if p["base"] == "hla" else (TC.TABLE_GENE,)):
+            first = batch.unit_table(u, tb)[2]
+            assert (np.diff(first) > 0).all(), (u, tb)
     # every unit's calls through one library call (hgt_batch_abundances)
     assert batch.top_calls(3) == [batch.unit_calls(u, 3) for u in range(len(g["loci"]))]
     # repeat execute+finish on the prepared batch: identical tables (pools are reset)

@@ -27,13 +27,15 @@ def launches(rep):
 
 def main():
     workload, size, reps = sys.argv[1], int(sys.argv[2]), sys.argv[3:]
-    groups = {"em_kernel": [], "stage_a": []}
+    groups = {"em_kernel": [], "stage_a": [], "records": []}
     for rep in reps:
         for name, b, t in launches(rep):
             if "em_kernel" in name:
                 groups["em_kernel"].append((name, b, t))
             elif "compat_kernel" in name or "class_kernel" in name:
                 groups["stage_a"].append((name, b, t))
+            elif "hgtk::" in name or name.split("(")[0] in ("pileup_flags_kernel",):
+                groups["records"].append((name, b, t))
     path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "traffic.json")
     data = json.load(open(path)) if os.path.exists(path) else {}
     for g, ls in groups.items():
@@ -41,6 +43,8 @@ def main():
             continue
         data["%s:%s:%d" % (workload, g, size)] = {
             "dram_bytes_per_launch": sum(b for _, b, _ in ls) / len(ls), "launches_captured": len(ls),
+            # the captures are taken with `bench.py --steps 1 --warmup 0` and a launch count that covers exactly the step
+            "dram_bytes_per_step": sum(b for _, b, _ in ls),
             "launch_times": [t for _, _, t in ls][:12], "reports": [os.path.basename(r) for r in reps]}
     json.dump(data, open(path, "w"), indent=1, sort_keys=True)
     print(json.dumps(data, indent=1, sort_keys=True))
