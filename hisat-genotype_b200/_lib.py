@@ -71,6 +71,8 @@ def lib():
         L.hgt_sam_split_write.argtypes = [c_void_p, c_i32, c_void_p]
         L.hgt_sam_split_free.restype = None
         L.hgt_sam_split_free.argtypes = [c_void_p]
+        L.hgt_batch_unit_reads.restype = c_int
+        L.hgt_batch_unit_reads.argtypes = [c_void_p, c_i64] + [c_void_p] * 10
         L.hgt_pair_em.restype = c_int
         L.hgt_pair_em.argtypes = [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_void_p, c_i32, c_void_p, c_void_p, P(c_i32)]
         L.hgt_host_alloc.restype = c_int

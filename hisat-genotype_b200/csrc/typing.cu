@@ -2402,6 +2402,89 @@ extern "C" int hgt_batch_unit_summary(const hgt_batch *b, int64_t unit, int64_t 
     return HGT_OK;
 }
 
+// Per-read haplotypes of a unit: what the reference's typing() holds per surviving alignment when it builds the assembly
+// nodes (left_positive_hts / right_positive_hts of the read, core:1386-1406 -> :1408-1540).  Read back from the record
+// stage's device arrays (the walk's output), slow records expanded to left ends x middle x right ends.
+extern "C" int hgt_batch_unit_reads(hgt_batch *b, int64_t unit, int64_t *n_records, int64_t *n_haps, int64_t *n_ids,
+                                    int64_t *rec_line, int32_t *rec_flag, int64_t *rec_hap_off, int32_t *hap_left,
+                                    int32_t *hap_right, int64_t *hap_id_off, int32_t *ids) {
+    if (!b || unit < 0 || unit >= (int64_t)b->units.size() || !b->executed) {
+        hgt_set_error("hgt_batch_unit_reads: bad unit index or batch not executed");
+        return HGT_ERR_ARG;
+    }
+    using namespace hgtd;
+    HGT_CUDA(cudaSetDevice(b->ctx->device));
+    cudaStream_t st = b->ctx->stream;
+    ReadsDev &rd = b->rd;
+    const UnitHost &U = b->units[unit];
+    const size_t N = (size_t)rd.n_lines;
+    int64_t l01[2] = {0, 0};
+    HGT_CUDA(cudaMemcpyAsync(l01, reinterpret_cast<int64_t *>(static_cast<unsigned char *>(rd.d_units.p) + rd.o_uline0) + U.arena, 16,
+                             cudaMemcpyDeviceToHost, st));
+    HGT_CUDA(cudaStreamSynchronize(st));
+    const size_t l0 = (size_t)l01[0], n = (size_t)(l01[1] - l01[0]);
+    std::vector<uint16_t> stv(std::max<size_t>(n, 1));
+    std::vector<RecFields> rec(std::max<size_t>(n, 1));
+    std::vector<int32_t> hl(std::max<size_t>(n, 1)), hr(hl.size()), hn(hl.size()), slot(hl.size()), hid(hl.size() * MAXI);
+    if (n > 0) {
+        const int32_t *hdr = rd.d_hdr.as<int32_t>();
+        HGT_CUDA(cudaMemcpyAsync(stv.data(), rd.d_st.as<uint16_t>() + l0, n * 2, cudaMemcpyDeviceToHost, st));
+        HGT_CUDA(cudaMemcpyAsync(rec.data(), rd.d_rec.as<RecFields>() + l0, n * sizeof(RecFields), cudaMemcpyDeviceToHost, st));
+        HGT_CUDA(cudaMemcpyAsync(hl.data(), hdr + l0, n * 4, cudaMemcpyDeviceToHost, st));
+        HGT_CUDA(cudaMemcpyAsync(hr.data(), hdr + N + l0, n * 4, cudaMemcpyDeviceToHost, st));
+        HGT_CUDA(cudaMemcpyAsync(hn.data(), hdr + 2 * N + l0, n * 4, cudaMemcpyDeviceToHost, st));
+        HGT_CUDA(cudaMemcpyAsync(slot.data(), hdr + 3 * N + l0, n * 4, cudaMemcpyDeviceToHost, st));
+        HGT_CUDA(cudaMemcpyAsync(hid.data(), rd.d_hids.as<int32_t>() + l0 * MAXI, n * MAXI * 4, cudaMemcpyDeviceToHost, st));
+        HGT_CUDA(cudaStreamSynchronize(st));
+    }
+    std::vector<SlowRec> slow;
+    std::vector<int64_t> slow_of(n, -1);
+    for (size_t i = 0; i < n; i++)
+        if ((stv[i] & ST_SURV) && slot[i] >= 0) {
+            slow_of[i] = (int64_t)slow.size();
+            slow.emplace_back();
+            HGT_CUDA(cudaMemcpyAsync(&slow.back(), rd.d_slow.as<SlowRec>() + slot[i], sizeof(SlowRec), cudaMemcpyDeviceToHost, st));
+            HGT_CUDA(cudaStreamSynchronize(st));  // (emplace_back may move the vector: one record at a time)
+        }
+    int64_t nr = 0, nh = 0, ni = 0;
+    for (size_t i = 0; i < n; i++) {
+        if (!(stv[i] & ST_SURV)) continue;
+        if (rec_line) rec_line[nr] = (int64_t)i;
+        if (rec_flag) rec_flag[nr] = rec[i].flag;
+        if (rec_hap_off) rec_hap_off[nr] = nh;
+        if (slow_of[i] < 0) {
+            if (hap_left) hap_left[nh] = hl[i];
+            if (hap_right) hap_right[nh] = hr[i];
+            if (hap_id_off) hap_id_off[nh] = ni;
+            for (int k = 0; k < hn[i]; k++, ni++)
+                if (ids) ids[ni] = hid[i * MAXI + k];
+            nh++;
+        } else {
+            const SlowRec &S = slow[(size_t)slow_of[i]];
+            for (int a = 0; a < S.e.n_left; a++)
+                for (int c = 0; c < S.e.n_right; c++) {
+                    if (hap_left) hap_left[nh] = S.e.left[a].pos;
+                    if (hap_right) hap_right[nh] = S.e.right[c].pos;
+                    if (hap_id_off) hap_id_off[nh] = ni;
+                    for (int k = 0; k < S.e.left[a].n; k++, ni++)
+                        if (ids) ids[ni] = S.e.left[a].ids[k];
+                    for (int k = 0; k < S.n_mid; k++, ni++)
+                        if (ids) ids[ni] = S.mid[k];
+                    for (int k = 0; k < S.e.right[c].n; k++, ni++)
+                        if (ids) ids[ni] = S.e.right[c].ids[k];
+                    nh++;
+                }
+        }
+        nr++;
+    }
+    if (rec_hap_off) rec_hap_off[nr] = nh;
+    if (hap_id_off) hap_id_off[nh] = ni;
+    if (n_records) *n_records = nr;
+    if (n_haps) *n_haps = nh;
+    if (n_ids) *n_ids = ni;
+    return HGT_OK;
+}
+
 extern "C" int hgt_batch_unit_table(hgt_batch *b, int64_t unit, int32_t table, uint64_t *class_bits, int64_t *class_count,
                                     int64_t *class_first, int64_t *allele_count, int64_t *allele_first) {
     HGT_CHECK(unit_check(b, unit, true));

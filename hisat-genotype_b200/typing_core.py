@@ -378,6 +378,46 @@ class Batch:
         k = min(cap, n.value)
         return [[t.names[int(idx[i])], float(prob[i])] for i in range(k)]
 
+    def unit_read_haplotypes(self, u, var_ids=None):
+        """Per surviving alignment record of unit u, in text order: (line index in the unit's text, FLAG, [haplotype, ...]) -
+        the left_positive_hts / right_positive_hts the reference's typing() holds when it builds the assembly nodes
+        (core:1386-1406 -> 1408-1540).  A haplotype is the reference's string "left-id-...-right" when
+        var_ids (variant ids in Var_list order, LocusTables.var_ids) is given, else (left, [rows], right).  A novel indel
+        (no id in the database; the reference numbers those in encounter order, core:404-431) appears as
+        "nvI<pos>_<len>" / "nvD<pos>_<len>"."""
+        n = [ctypes.c_int64(0) for _ in range(3)]
+        _lib.check(lib().hgt_batch_unit_reads(self.handle, u, ctypes.byref(n[0]), ctypes.byref(n[1]), ctypes.byref(n[2]),
+                                              None, None, None, None, None, None, None))
+        nr, nh, ni = (x.value for x in n)
+        line = np.zeros(max(nr, 1), np.int64)
+        flag = np.zeros(max(nr, 1), np.int32)
+        hoff = np.zeros(nr + 1, np.int64)
+        hl = np.zeros(max(nh, 1), np.int32)
+        hr = np.zeros(max(nh, 1), np.int32)
+        ioff = np.zeros(nh + 1, np.int64)
+        ids = np.zeros(max(ni, 1), np.int32)
+        _lib.check(lib().hgt_batch_unit_reads(self.handle, u, ctypes.byref(n[0]), ctypes.byref(n[1]), ctypes.byref(n[2]),
+                                              _lib.ptr(line), _lib.ptr(flag), _lib.ptr(hoff), _lib.ptr(hl), _lib.ptr(hr),
+                                              _lib.ptr(ioff), _lib.ptr(ids)))
+
+        def name(i):
+            if i >= 0:
+                return var_ids[i]
+            c = -2 - i
+            return "nv%s%d_%d" % ("I" if (c >> 29) & 1 else "D", (c >> 10) & 0x7ffff, c & 0x3ff)
+
+        out = []
+        for r in range(nr):
+            haps = []
+            for h in range(hoff[r], hoff[r + 1]):
+                rows = ids[ioff[h]:ioff[h + 1]].tolist()
+                if var_ids is None:
+                    haps.append((int(hl[h]), rows, int(hr[h])))
+                else:
+                    haps.append("-".join([str(int(hl[h]))] + [name(i) for i in rows] + [str(int(hr[h]))]))
+            out.append((int(line[r]), int(flag[r]), haps))
+        return out
+
     def top_calls(self, max_n=2):
         """unit_calls(u, max_n) of every unit, through one library call (hgt_batch_abundances)."""
         nu, cap = len(self.unit_locus), int(max_n)

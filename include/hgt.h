@@ -281,6 +281,16 @@ int hgt_batch_set_skip_em(hgt_batch *b, int32_t skip);
 int hgt_batch_unit_em(const hgt_batch *b, int64_t unit, int32_t level, double *prob, uint8_t *in_result,
                       int32_t *first_class, int32_t *iters, int32_t *status);
 
+/* Per-read haplotypes of a unit, for callers that continue with the reference's assembly: for every
+ * surviving alignment record, in text order, the haplotypes typing() holds for it when it builds the assembly nodes
+ * (left_positive_hts / right_positive_hts, core:1386-1406 -> :1408-1540).  Call once with NULL arrays for the sizes, then
+ * with arrays of n_records (+1 for rec_hap_off), n_haps (+1 for hap_id_off) and n_ids entries.  rec_line = line of
+ * the unit's text; ids = variant rows (Var_list order) in haplotype order, or a novel indel as
+ * -2 - (is_insertion << 29 | pos << 10 | len).  Valid after execute. */
+int hgt_batch_unit_reads(hgt_batch *b, int64_t unit, int64_t *n_records, int64_t *n_haps, int64_t *n_ids, int64_t *rec_line,
+                         int32_t *rec_flag, int64_t *rec_hap_off, int32_t *hap_left, int32_t *hap_right,
+                         int64_t *hap_id_off, int32_t *ids);
+
 /* Gene_prob of one unit as typing() ranks it (core:1771-1782 on the hla path, core:1789 otherwise): allele indices and
  * probabilities in report order; at most cap entries are written, *n_total is the full length.  Returns the EM
  * status of the unit (HGT_ERR_KEY / HGT_ERR_ZERODIV mirror the reference's exceptions). */

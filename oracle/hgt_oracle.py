@@ -830,7 +830,7 @@ class Table:
 
 
 def type_locus(loc, sam_lines, simulation=False, num_editdist=2, error_correction=True, allow_discordant=False,
-               base_locus=0, collect=None):
+               base_locus=0, collect=None, collect_hts=None):
     """Stage (a) for one locus.  Returns dict with tables 'gene', 'exon', 'primary', num_reads, num_pairs."""
     hla = loc.base_fname == "hla"
     counts, nt_sets = get_mpileup(sam_lines, len(loc.ref_seq), base_locus, allow_discordant)
@@ -879,7 +879,7 @@ def type_locus(loc, sam_lines, simulation=False, num_editdist=2, error_correctio
             if collect is not None:
                 collect.append((pair_index, k, best))
 
-    for line in sam_lines:
+    for line_i, line in enumerate(sam_lines):
         rec = parse_record(line, simulation, base_locus)
         if rec.pos < 0:
             continue
@@ -929,10 +929,14 @@ def type_locus(loc, sam_lines, simulation=False, num_editdist=2, error_correctio
                 c2.append(list(e))
         l, r, la, ra = identify_ambiguous_diffs(loc, c2)
         mid = [e[3] for e in c2[l:r + 1] if e[0] != MATCH]
+        own = set()
         for a in la:
             for b in ra:
                 ht = "-".join(a.split("-") + mid + b.split("-"))
                 (left_hts if is_left else right_hts).add(ht)
+                own.add(ht)
+        if collect_hts is not None:  # the read's own haplotype strings (core:1386-1406)
+            collect_hts.append((line_i, rec.flag, sorted(own)))
         prev_id = rec.read_id
     if prev_id is not None:
         flush(num_pairs)
