@@ -9,6 +9,8 @@ Each reader takes the *text* of a file so that tests can feed fixtures without t
   read_links        <- hisatgenotype_typing_common.py:388-403   (.link)
   read_backbone     <- hisatgenotype_typing_common.py:313-334   (_backbone.fa)
   build_genes       <- hisatgenotype_typing_core.py:2199-2237, 2462-2485
+  read_haplotypes / read_index_variants   <- hisatgenotype_typing_process.py:1088-1102, 1215-1220 (.haplotype, .index.snp)
+  write_database_text   the files of process.py:1055-1106, 1242-1244 from the containers (round trip of the readers)
 """
 from __future__ import annotations
 
@@ -119,6 +121,47 @@ def build_genes(Genes, Vars, Var_list, Links, allele_names):
     Gene_names = {g: list(d.keys()) for g, d in Genes.items()}
     Gene_lengths = {g: {a: len(s) for a, s in d.items()} for g, d in Genes.items()}
     return Gene_names, Gene_lengths
+
+
+def read_haplotypes(text):
+    """.haplotype: `htN \\t backbone \\t left \\t right \\t id,id,...` (written by process.py:1215-1220, read by hisat2-build
+    --haplotype): {gene: [[ht_id, left, right, [var ids]], ...]} in file order."""
+    out = {}
+    for line in text.strip("\n").split("\n"):
+        if not line:
+            continue
+        ht_id, name, left, right, ids = line.split("\t")
+        out.setdefault(name.split("*")[0], []).append([ht_id, int(left), int(right), [v for v in ids.split(",") if v]])
+    return out
+
+
+def read_index_variants(text):
+    """.index.snp: the subset of .snp that went into the graph index (same five columns, process.py:1088-1102); HISAT2 names
+    these ids in the Zs tag of its alignments.  Returns the set of ids per gene."""
+    Vars, _ = read_variants(text)
+    return {gene: set(v) for gene, v in Vars.items()}
+
+
+def write_database_text(d):
+    """The inverse of load_database_text for the files this package reads: {extension: text} from the containers (variants
+    in Var_list order, one allele name per line).  Round trip: load_database_text(write_database_text(d)) == d."""
+    locus, snp, link, backbone, alleles = [], [], [], [], []
+    for gene, name in d["refGenes"].items():
+        _, chrom, left, right, exons, primary = d["refGene_loci"][gene]
+        ex = ",".join("%d-%d%s" % (a, b, "p" if [a, b] in primary else "") for a, b in exons)
+        seq = d["Genes"][gene][name]
+        locus.append("%s\t%s\t%d\t%d\t%d\t%s\t+" % (name, chrom, left, right, len(seq), ex))
+        backbone.append(">%s" % name)
+        backbone += [seq[i:i + 60] for i in range(0, len(seq), 60)]
+        for pos, var_id in d["Var_list"].get(gene, []):
+            t, p, data = d["Vars"][gene][var_id]
+            snp.append("%s\t%s\t%s\t%d\t%s" % (var_id, t, name, p, data))
+            if var_id in d["Links"]:
+                link.append("%s\t%s" % (var_id, " ".join(d["Links"][var_id])))
+        alleles += [a for a in d["Gene_names"][gene] if a != name and not a.endswith("*GRCh38")]
+    return {".locus": "\n".join(locus) + "\n", ".snp": "\n".join(snp) + "\n", ".link": "\n".join(link) + "\n",
+            "_backbone.fa": "\n".join(backbone) + "\n", ".allele": "\n".join(alleles) + "\n",
+            ".partial": "".join(a + "\n" for a in sorted(d.get("partial_alleles", ())))}
 
 
 def load_database_text(db):

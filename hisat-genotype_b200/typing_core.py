@@ -340,7 +340,8 @@ class Batch:
         bits, cnt, first, n = self.unit_table_dev(u, table)
         offset = 0
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            mine = torch.tensor([self.unit_summary(u)["num_pairs"]], dtype=torch.int64, device="cuda")
+            dev = torch.device("cuda", self.device if self.device is not None else _lib.default_device())
+            mine = torch.tensor([self.unit_summary(u)["num_pairs"]], dtype=torch.int64, device=dev)
             every = [torch.zeros_like(mine) for _ in range(dist.get_world_size(group))]
             dist.all_gather(every, mine, group=group)
             offset = int(sum(int(x) for x in every[:dist.get_rank(group)]))

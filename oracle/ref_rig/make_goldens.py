@@ -57,6 +57,14 @@ SCENARIOS = {
                    del_frac=0.10)],
         run=["--loci", "A", "--debug", "pair,test_size:1,set_seed:3,single-end", "--err", "0.5",
              "--no-error-correction", "--keep-low", "--discordant", "--all-counts"]),
+    # wide locus: 2,200 alleles = 35 words per allele set, two words per lane in the allele-set kernels and multi-word
+    # paths everywhere (the other scenarios stay below 66 alleles); pins the oracle and the CUDA path at a width the
+    # benchmark shapes use, against the unmodified reference
+    "hla_wide": dict(
+        base="hla",
+        loci=[dict(gene="A", seed=61, L=2200, n_alleles=2200, n_groups=30, core_vars=60, pool_private=700,
+                   del_frac=0.10)],
+        run=["--loci", "A", "--debug", "pair,test_size:1,set_seed:23", "--err", "0.4", "--all-counts"]),
     # deeper coverage so that the pileup thresholds (depth>=20) and error correction actually fire
     "hla_deep": dict(
         base="hla",

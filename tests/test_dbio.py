@@ -1,0 +1,35 @@
+"""Database file readers / writer (hisat-genotype_b200/dbio.py): round trip on the databases of the goldens and the
+extra index files the synthetic writer produces (.haplotype, .index.snp)."""
+import os
+
+import pytest
+
+from conftest import GOLDEN_NAMES, load_golden
+from helpers import golden_db
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_round_trip(name):
+    from hisatgenotype_b200 import dbio
+    d = golden_db(load_golden(name))
+    again = dbio.load_database_text(dbio.write_database_text(d))
+    for k in ("refGenes", "refGene_loci", "Vars", "Var_list", "Links", "Genes", "Gene_lengths", "partial_alleles"):
+        assert again[k] == d[k], k
+    assert {g: sorted(v) for g, v in again["Gene_names"].items()} == {g: sorted(v) for g, v in d["Gene_names"].items()}
+
+
+def test_haplotype_and_index_snp_files(tmp_path):
+    from hisatgenotype_b200 import dbio, synth
+    loc = synth.make_locus("A", 5, L=900, n_alleles=20, n_groups=4, core_vars=12, pool_private=20, del_frac=0.2)
+    synth.write_database([loc], "hla", str(tmp_path))
+    prefix = os.path.join(str(tmp_path), "hla")
+    d = dbio.load_database(prefix)
+    hts = dbio.read_haplotypes(open(prefix + ".haplotype").read())
+    idx = dbio.read_index_variants(open(prefix + ".index.snp").read())
+    assert set(hts) == {"A"} and len(hts["A"]) > 0
+    for ht_id, left, right, ids in hts["A"]:
+        assert ht_id.startswith("ht") and 0 <= left <= right < len(loc.backbone)
+        for v in ids:
+            assert v in d["Vars"]["A"]
+            assert left <= d["Vars"]["A"][v][1] <= right
+    assert idx["A"] <= set(d["Vars"]["A"]) and len(idx["A"]) > 0
