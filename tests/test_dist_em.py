@@ -64,8 +64,18 @@ def _worker(rank, world, port, seed, remove_low, use_len, out):
     members, counts = make_problem(seed)
     A = 90
     lo, hi = (0, len(members) // 2) if rank == 0 else (len(members) // 2, len(members))
-    # rank 1 also holds a copy of rank 0's first classes: duplicates across shards must not matter once counts add up
-    sweep = NumpySweep(members[lo:hi], counts[lo:hi], list(range(lo, hi)), A)
+    # the first eight classes live on BOTH ranks with their count split (shards of one locus see the same class from
+    # different read pairs): duplicates across shards must not matter once the counts add up
+    idx = list(range(lo, hi))
+    cnt = [counts[k] for k in idx]
+    dup = list(range(8))
+    if rank == 0:
+        cnt = [c // 2 if k in dup else c for k, c in zip(idx, cnt)]
+    else:
+        idx = dup + idx
+        cnt = [counts[k] - counts[k] // 2 for k in dup] + cnt
+    keep = [j for j, c in enumerate(cnt) if c > 0]
+    sweep = NumpySweep([members[idx[j]] for j in keep], [cnt[j] for j in keep], [idx[j] for j in keep], A)
     ln = (1000.0 + np.arange(A) % 7) if use_len else None
     prob, live, fk, iters = em_dist.single_abundance_sharded(sweep, ln, remove_low)
     if rank == 0:
