@@ -258,92 +258,136 @@ __global__ void __launch_bounds__(256) candidate_kernel(ReadsView R) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < R.n_lines; i += (int64_t)gridDim.x * blockDim.x)
         mark_candidate(R, i);
 }
-// Error-correction bits of the warp's 32 records (EcMask, walk_dev.cuh): record by record, all lanes parse the CIGAR
-// together (same bytes: one broadcast load) and cover 32 consecutive read bases of an M segment per step - SEQ and the
-// representative-base sets are read coalesced, one ballot gives 32 bits.  Lane r keeps the words of record r.  The
-// parameters of the 32 records go through shared memory (two 16-byte broadcast loads per record instead of ten shuffles).
+// Error-correction bits of the warp's 32 records (EcMask, walk_dev.cuh).
+//   1. every lane parses the CIGAR of ITS record into at most three M segments (read range, backbone shift) - 32 records in
+//      parallel, the (short, divergent) byte loads all in flight together - and parks them in shared memory;
+//   2. record by record the whole warp covers a segment in one step: lane l takes the four read bases 4l .. 4l+3 of the
+//      segment (two aligned 32-bit loads + funnel shift each for SEQ and for the representative-base sets, coalesced over the
+//      warp), tests them, and three shuffle steps gather the 32 nibbles into four words, which the owner lane ORs into its
+//      mask at the segment's read offset.
+// Reads longer than 128 bases, more than three M segments, or a malformed CIGAR leave valid = false: the walk then tests the
+// bases itself (and reports the CIGAR error).
 struct EcParams {
-    const char *line;
+    const char *seq;
     const uint8_t *ntm;
-    int32_t pos, L;
-    uint16_t cig_off, cig_n, seq_off, seq_len;
+    int32_t L, nseg;
+    struct Seg {
+        uint16_t r0, r1;  // read bases [r0, r1)
+        int32_t shift;    // backbone position = read index + shift
+    } seg[3];
+    int32_t pad[2];
 };
-static_assert(sizeof(EcParams) == 32, "EcParams is read as two 16-byte words");
+static_assert(sizeof(EcParams) == 56, "EcParams layout");
+__device__ __forceinline__ uint32_t load4_unaligned(const void *p) {  // bytes p[0..3] as a little-endian word
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t *w = reinterpret_cast<const uint32_t *>(a & ~(uintptr_t)3);
+    const uint32_t lo = w[0], hi = w[1];
+    return __funnelshift_r(lo, hi, (uint32_t)(a & 3) * 8u);
+}
 __device__ __forceinline__ EcMask warp_ec_masks(const ReadsView &R, const WalkParams &P, const char *text, int64_t i, bool cand,
                                                 EcParams *s_warp /* [32], this warp's */) {
     const int lane = threadIdx.x & 31;
     EcMask mine;
     mine.w0 = mine.w1 = mine.w2 = mine.w3 = 0;
     mine.valid = false;
-    if (cand) {
+    if (cand && P.error_correction) {
         const RecFields f = R.rec[i];
         const int u = R.unit[i];
+        const char *line = text + R.line_off[i];
         EcParams p;
-        p.line = text + R.line_off[i];
-        if (text == R.text) {
-            // First touch of the line comes from HBM: every lane starts the loads of its own line's cache lines NOW (the
-            // values are not used), so the record-by-record loop below and the walk after it find them in L1 / L2.
-            const int64_t len = R.line_off[i + 1] - R.line_off[i];
-            for (int64_t o = 0; o < len; o += 128) {
-                unsigned d;
-                asm volatile("ld.global.b32 %0, [%1];" : "=r"(d) : "l"((unsigned long long)(p.line + o) & ~3ull));
-            }
-            unsigned d;
-            asm volatile("ld.global.b32 %0, [%1];" : "=r"(d) : "l"((unsigned long long)(p.line + len - 1) & ~3ull));
-        }
+        p.seq = line + f.seq_off;
         p.ntm = R.nt_mask + R.unit_pos0[u];
-        p.pos = f.pos;
         p.L = R.loci[R.unit_locus[u]].L;
-        p.cig_off = f.cig_off; p.cig_n = f.cig_len; p.seq_off = f.seq_off; p.seq_len = f.seq_len;
-        s_warp[lane] = p;
-        mine.valid = P.error_correction && f.seq_len <= ECM_MAX_SEQ;
-    }
-    unsigned todo = __ballot_sync(0xffffffffu, mine.valid);  // (also orders the shared-memory writes before the reads)
-    while (todo) {
-        const int r = __ffs((int)todo) - 1;
-        todo &= todo - 1;
-        const EcParams p = s_warp[r];
-        const char *cig = p.line + p.cig_off, *seq = p.line + p.seq_off;
-        const int cn = p.cig_n, sl = p.seq_len;
-        int32_t right_pos = p.pos, read_pos = 0;
-        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        p.nseg = 0;
+        p.pad[0] = p.pad[1] = 0;
+        bool ok = f.seq_len <= ECM_MAX_SEQ;
+        const char *cig = line + f.cig_off;
+        const int cn = f.cig_len, sl = f.seq_len;
+        int32_t right_pos = f.pos, read_pos = 0;
         int cp = 0;
-        while (cp < cn) {
+        while (ok && cp < cn) {
             int32_t length = 0;
             char c = cig[cp];
+            bool have = false;
             while (is_dig(c)) {
+                have = true;
                 if (length < (1 << 24)) length = length * 10 + (c - '0');
                 cp++;
                 if (cp >= cn) break;
                 c = cig[cp];
             }
-            if (cp >= cn) break;
+            if (!have || cp >= cn) {
+                ok = false;  // malformed: the walk reports it
+                break;
+            }
             cp++;
             if (c == 'M') {
-                const int32_t shift = right_pos - read_pos;  // backbone position of read base rp = rp + shift
-                // read bases of the segment that exist and lie on the backbone: [lo, hi)
+                // read bases of the segment that exist and lie on the backbone
+                const int32_t shift = right_pos - read_pos;
                 const int32_t lo = max(read_pos, -shift), hi = min(min(read_pos + length, sl), p.L - shift);
-                for (int32_t base = lo & ~31; base < hi; base += 32) {
-                    const int32_t rp = base + lane;
-                    bool flag = false;
-                    if ((uint32_t)(rp - lo) < (uint32_t)(hi - lo)) {
-                        const uint32_t m = p.ntm[rp + shift], ch = (unsigned char)seq[rp];
-                        // A 0x41, C 0x43, G 0x47, T 0x54: bits 1-2 give 0, 1, 3, 2 -> x ^ (x >> 1) = 0, 1, 2, 3; the
-                        // letters themselves are bits 1, 3, 7, 20 of a 32-bit table indexed by the low five bits
-                        const uint32_t x = (ch >> 1) & 3u, code = x ^ (x >> 1);
-                        const bool acgt = (ch >> 5) == 2u && ((0x0010008Au >> (ch & 31u)) & 1u);
-                        flag = m != 0 && !(acgt && ((m >> code) & 1u));
+                if (hi > lo) {
+                    if (p.nseg >= 3) ok = false;
+                    else {
+                        p.seg[p.nseg].r0 = (uint16_t)lo;
+                        p.seg[p.nseg].r1 = (uint16_t)hi;
+                        p.seg[p.nseg].shift = shift;
+                        p.nseg++;
                     }
-                    const uint32_t b = __ballot_sync(0xffffffffu, flag);
-                    const int w = base >> 5;
-                    if (w == 0) a0 |= b;
-                    else if (w == 1) a1 |= b;
-                    else if (w == 2) a2 |= b;
-                    else a3 |= b;
                 }
             }
             if (c == 'M' || c == 'N' || c == 'D') right_pos += length;
             if (c == 'M' || c == 'I' || c == 'S') read_pos += length;
+        }
+        if (ok) s_warp[lane] = p;
+        mine.valid = ok;
+    }
+    unsigned todo = __ballot_sync(0xffffffffu, mine.valid);  // (also orders the shared-memory writes before the reads)
+    while (todo) {
+        const int r = __ffs((int)todo) - 1;
+        todo &= todo - 1;
+        const EcParams *p = s_warp + r;
+        const char *seq = p->seq;
+        const uint8_t *ntm = p->ntm;
+        const int nseg = p->nseg;
+        uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+        for (int sg = 0; sg < nseg; sg++) {
+            const int r0 = p->seg[sg].r0, r1 = p->seg[sg].r1, shift = p->seg[sg].shift;
+            const int rp = r0 + 4 * lane;  // this lane's four read bases
+            uint32_t f = 0;
+            if (rp < r1) {
+                const uint32_t sv = load4_unaligned(seq + rp), mv = load4_unaligned(ntm + rp + shift);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const uint32_t ch = (sv >> (8 * k)) & 0xffu, m = (mv >> (8 * k)) & 0xffu;
+                    // A 0x41, C 0x43, G 0x47, T 0x54: bits 1-2 give 0, 1, 3, 2 -> x ^ (x >> 1) = 0, 1, 2, 3; the letters
+                    // themselves are bits 1, 3, 7, 20 of a 32-bit table indexed by the low five bits
+                    const uint32_t x = (ch >> 1) & 3u, code = x ^ (x >> 1);
+                    const bool acgt = (ch >> 5) == 2u && ((0x0010008Au >> (ch & 31u)) & 1u);
+                    const bool flag = m != 0 && !(acgt && ((m >> code) & 1u));
+                    f |= (flag ? 1u : 0u) << k;
+                }
+                const int nv = r1 - rp;  // bases of this lane inside the segment
+                if (nv < 4) f &= (1u << nv) - 1u;
+            }
+            // nibbles of 8 consecutive lanes -> one word (at lanes 0, 8, 16, 24)
+            uint32_t x = f | (__shfl_down_sync(0xffffffffu, f, 1) << 4);
+            x |= __shfl_down_sync(0xffffffffu, x, 2) << 8;
+            x |= __shfl_down_sync(0xffffffffu, x, 4) << 16;
+            const uint32_t v0 = __shfl_sync(0xffffffffu, x, 0), v1 = __shfl_sync(0xffffffffu, x, 8),
+                           v2 = __shfl_sync(0xffffffffu, x, 16), v3 = __shfl_sync(0xffffffffu, x, 24);
+            // segment-relative bits -> read index: shift the 128-bit vector left by r0 (bits past 127 belong to no base)
+            const int ws = r0 >> 5, bs = r0 & 31;
+            uint32_t t0 = v0, t1 = v1, t2 = v2, t3 = v3;
+            if (bs) {
+                t3 = (v3 << bs) | (v2 >> (32 - bs));
+                t2 = (v2 << bs) | (v1 >> (32 - bs));
+                t1 = (v1 << bs) | (v0 >> (32 - bs));
+                t0 = v0 << bs;
+            }
+            if (ws == 0) { a0 |= t0; a1 |= t1; a2 |= t2; a3 |= t3; }
+            else if (ws == 1) { a1 |= t0; a2 |= t1; a3 |= t2; }
+            else if (ws == 2) { a2 |= t0; a3 |= t1; }
+            else a3 |= t0;
         }
         if (lane == r) {
             mine.w0 = a0; mine.w1 = a1; mine.w2 = a2; mine.w3 = a3;
