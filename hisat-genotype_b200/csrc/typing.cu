@@ -542,16 +542,51 @@ __device__ __forceinline__ int lower_bound_dev(const int32_t *a, int n, int key)
 // warp per haplotype; lane l owns words l, l+32, ... of the row (WPL words per lane).
 // Allele set of one haplotype (left, right, sorted variant rows rw[0..k1)) under table mask `mask` (already offset by the
 // lane): lane l holds words l, l+32, ... in set[].
-template <int WPL>
-__device__ __forceinline__ void hap_allele_set(const LocusDev &loc, int left, int right, const int32_t *__restrict__ rw, int k1,
-                                               const uint64_t *__restrict__ mask, int lane, uint64_t (&set)[WPL]) {
-    // The two lower_bound searches per haplotype (variants, deletion right ends) are table look-ups by position
-    // (lb_var / lb_del, L + 2 entries each, L1/L2-resident): the instruction count is then the set algebra itself.
-    const int wp = loc.wp;
-    const size_t lvl = (size_t)max(loc.V, 1) * wp;
+// Bounds of a haplotype by position: variant rows [lo, hi) lie inside [left, right], deletions [dlo, dhi) of the
+// right-end order end inside it.  Two table look-ups each (lb_var / lb_del, L + 2 entries, L1/L2-resident) instead of
+// binary searches.
+struct HapBounds {
+    int lo, hi, dlo, dhi;
+};
+__device__ __forceinline__ HapBounds hap_bounds(const LocusDev &loc, int left, int right) {
     const int xmax = loc.L + 1;
     const int xl = min(max(left, 0), xmax), xr = min(max(right + 1, 0), xmax);
-    const int lo = loc.lb_var[xl], hi = loc.lb_var[xr];
+    HapBounds b;
+    b.lo = loc.lb_var[xl];
+    b.hi = loc.lb_var[xr];
+    b.dlo = b.dhi = 0;
+    if (loc.n_delr > 0) {
+        b.dlo = loc.lb_del[xl];
+        b.dhi = loc.lb_del[xr];
+    }
+    return b;
+}
+
+// Lane l tests deletion d0 + l of the right-end order ([d0, dhi) end inside the haplotype): does it start left of the
+// haplotype without being one of its own rows?  Returns the ballot; `row` = the lane's candidate.
+template <class RowFn>
+__device__ __forceinline__ unsigned del_rows_left_of(const LocusDev &loc, int d0, int dhi, int left, RowFn ROW, int k1, int lane,
+                                                     int &row) {
+    const int dd = d0 + lane;
+    bool q = false;
+    row = 0;
+    if (dd < dhi) {
+        row = loc.delr_row[dd];
+        q = loc.var_pos[row] < left;
+    }
+    if (__any_sync(0xffffffffu, q))
+        for (int k = 0; k < k1; k++) q &= ROW(k) != row;
+    return __ballot_sync(0xffffffffu, q);
+}
+
+// Set algebra of one haplotype.  ROW(k) yields its k-th sorted variant row (k < k1): a pointer read in compat_kernel,
+// registers for the first two rows in job_class_kernel.
+template <int WPL, class RowFn>
+__device__ __forceinline__ void hap_allele_set_core(const LocusDev &loc, int left, const HapBounds &hb, RowFn ROW, int k1,
+                                                    const uint64_t *__restrict__ mask, int lane, uint64_t (&set)[WPL]) {
+    const int wp = loc.wp;
+    const size_t lvl = (size_t)max(loc.V, 1) * wp;
+    const int lo = hb.lo, hi = hb.hi;
     uint64_t neg[WPL];
 #pragma unroll
     for (int i = 0; i < WPL; i++) {
@@ -564,7 +599,7 @@ __device__ __forceinline__ void hap_allele_set(const LocusDev &loc, int left, in
     for (int k = 0; k <= k1; k++) {
         int endr = hi;
         if (k < k1) {
-            endr = rw[k];
+            endr = ROW(k);
             const uint64_t *row = loc.st + (size_t)endr * wp + lane;
 #pragma unroll
             for (int i = 0; i < WPL; i++)
@@ -583,16 +618,15 @@ __device__ __forceinline__ void hap_allele_set(const LocusDev &loc, int left, in
         }
         prev = max(prev, endr + 1);
     }
-    // deletions that start left of the haplotype and end inside it
-    if (loc.n_delr > 0) {
-        const int dlo = loc.lb_del[xl], dhi = loc.lb_del[xr];
-        for (int dd = dlo; dd < dhi; dd++) {
-            const int row = loc.delr_row[dd];
-            if (loc.var_pos[row] >= left) continue;
-            bool own = false;
-            for (int k = 0; k < k1; k++) own |= rw[k] == row;
-            if (own) continue;
-            const uint64_t *rp = loc.st + (size_t)row * wp + lane;
+    // deletions that start left of the haplotype and end inside it: the candidates (right end inside) are tested 32 at a
+    // time, one per lane - a read spans a dozen of them and hardly any qualifies
+    for (int d0 = hb.dlo; d0 < hb.dhi; d0 += 32) {
+        int row = 0;
+        unsigned qm = del_rows_left_of(loc, d0, hb.dhi, left, ROW, k1, lane, row);
+        while (qm) {
+            const int src = __ffs((int)qm) - 1;
+            qm &= qm - 1;
+            const uint64_t *rp = loc.st + (size_t)__shfl_sync(0xffffffffu, row, src) * wp + lane;
 #pragma unroll
             for (int i = 0; i < WPL; i++)
                 if (lane + 32 * i < wp) neg[i] |= rp[32 * i];
@@ -600,6 +634,13 @@ __device__ __forceinline__ void hap_allele_set(const LocusDev &loc, int left, in
     }
 #pragma unroll
     for (int i = 0; i < WPL; i++) set[i] &= ~neg[i];
+}
+
+template <int WPL>
+__device__ __forceinline__ void hap_allele_set(const LocusDev &loc, int left, int right, const int32_t *__restrict__ rw, int k1,
+                                               const uint64_t *__restrict__ mask, int lane, uint64_t (&set)[WPL]) {
+    const HapBounds hb = hap_bounds(loc, left, right);
+    hap_allele_set_core<WPL>(loc, left, hb, [rw](int k) { return rw[k]; }, k1, mask, lane, set);
 }
 
 // warp per haplotype -> hapbits (two-kernel form of stage (a), the default)
@@ -629,8 +670,7 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
 // rows of table `ut` are allocated contiguously inside a region reserved for it (its number of pairs bounds the
 // number of classes), so the EM kernel can stream them without a gather.
 struct ClassPool {
-    unsigned long long *keys;  // open-addressing table, 0 = empty
-    int32_t *slot_class;       // absolute class row once its bits are written, -1 before
+    unsigned long long *keys;  // open-addressing table, 0 = empty; else tag (high 36 bits) | id field (POOL_ID_BITS)
     uint32_t cap_mask;
     uint64_t *bits;            // [rows][wp]
     unsigned long long *count; // [rows]
@@ -638,32 +678,56 @@ struct ClassPool {
     const int64_t *ut_base;    // [n_ut] first row of each (unit, table) region
     int32_t *ut_ncls;          // [n_ut] classes created so far
 };
+// A slot word carries the hash tag of its class AND the class row (absolute row + 1), so a hit costs the CAS round trip
+// plus the row compare and nothing in between.  PENDING = the owner has not published the row yet (readers spin on the
+// slot word); OVERFLOW = the owner's region was full (readers move on, so an overflow can never hang a kernel).
+constexpr int POOL_ID_BITS = 28;
+constexpr unsigned long long POOL_ID_MASK = (1ull << POOL_ID_BITS) - 1, POOL_PENDING = POOL_ID_MASK,
+                             POOL_OVERFLOW = POOL_ID_MASK - 1;
+constexpr int64_t POOL_MAX_ROWS = (int64_t)POOL_ID_MASK - 2;
 
 __device__ __forceinline__ uint64_t mix64(uint64_t x) {
     x ^= x >> 33; x *= 0xff51afd7ed558ccdULL; x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ULL; x ^= x >> 33;
     return x;
 }
 
-// Insert bitset `best` (WPL words per lane) into table `ut`; adds `add` to its count and lowers its first index.
+// Insert in two halves so that a caller can keep the first CAS in flight behind other work (job_class_kernel).
+struct PoolProbe {
+    unsigned long long tag, prev;  // prev: what lane 0's CAS found in the first slot
+    uint32_t slot;
+};
 template <int WPL>
-__device__ __forceinline__ void pool_insert(const ClassPool &pool, int wp, int ut, const uint64_t (&best)[WPL],
-                                            unsigned long long add, int first, int lane) {
+__device__ __forceinline__ void pool_probe_issue(const ClassPool &pool, int wp, int ut, const uint64_t (&best)[WPL], int lane,
+                                                 PoolProbe &pp) {
+    // multilinear hash of the row: per 32-bit half an odd key derived from its position, 32 x 32 -> 64-bit multiply-adds
+    // (two IMAD.WIDE per word instead of a 64-bit mixer); the warp sum is mixed once below.  Equal tags are always
+    // confirmed by comparing the rows, so the hash only has to spread.
     uint64_t hsh = 0;
 #pragma unroll
     for (int i = 0; i < WPL; i++) {
-        const int j = lane + 32 * i;
-        if (j < wp) hsh += mix64(best[i] + 0x9e3779b97f4a7c15ULL * (uint64_t)(j + 1));
+        const uint32_t j = (uint32_t)(lane + 32 * i);
+        if ((int)j < wp) {
+            const uint32_t k1 = (2u * j + 1u) * 0x9E3779B1u | 1u, k2 = (2u * j + 2u) * 0x85EBCA77u | 1u;
+            hsh += (uint64_t)(uint32_t)best[i] * k1 + (uint64_t)(uint32_t)(best[i] >> 32) * k2;
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) hsh += __shfl_xor_sync(0xffffffffu, hsh, o);
-    const unsigned long long key = mix64(hsh + 0x632be59bd9b4e019ULL * (uint64_t)(ut + 1)) | 1ull;
-    uint32_t slot = (uint32_t)(key >> 20) & pool.cap_mask;
-    const int64_t base = pool.ut_base[ut], limit = pool.ut_base[ut + 1];
+    const unsigned long long h = mix64(hsh + 0x632be59bd9b4e019ULL * (uint64_t)(ut + 1));
+    pp.tag = (h | (1ull << POOL_ID_BITS)) & ~POOL_ID_MASK;
+    pp.slot = (uint32_t)(h >> 31) & pool.cap_mask;
+    pp.prev = 0;
+    if (lane == 0) pp.prev = atomicCAS(&pool.keys[pp.slot], 0ull, pp.tag | POOL_PENDING);
+}
+// Second half: adds `add` to the class's count and lowers its first index.  [base, limit) = rows of table `ut`.
+template <int WPL>
+__device__ __forceinline__ void pool_probe_resolve(const ClassPool &pool, int wp, int ut, int64_t base, int64_t limit,
+                                                   const uint64_t (&best)[WPL], unsigned long long add, int first, int lane,
+                                                   const PoolProbe &pp) {
+    uint32_t slot = pp.slot;
+    unsigned long long prev = __shfl_sync(0xffffffffu, pp.prev, 0);
     int64_t cid = -1;
     while (true) {
-        unsigned long long prev = 0;
-        if (lane == 0) prev = atomicCAS(&pool.keys[slot], 0ull, key);
-        prev = __shfl_sync(0xffffffffu, prev, 0);
         if (prev == 0ull) {  // we own the slot: publish a new class row
             int c = 0;
             if (lane == 0) c = atomicAdd(&pool.ut_ncls[ut], 1);
@@ -677,21 +741,27 @@ __device__ __forceinline__ void pool_insert(const ClassPool &pool, int wp, int u
                 }
                 __threadfence();
                 __syncwarp();
-                if (lane == 0) atomicExch(&pool.slot_class[slot], (int32_t)cid);
+                if (lane == 0) atomicExch(&pool.keys[slot], pp.tag | (unsigned long long)(cid + 1));
+            } else {  // region full (cannot happen while regions are sized by the pair bound): readers see it and move on
+                if (lane == 0) atomicExch(&pool.keys[slot], pp.tag | POOL_OVERFLOW);
+                cid = -1;
             }
             break;
         }
-        if (prev == key) {
-            int c = -1;
-            if (lane == 0) {
-                while ((c = *((volatile int32_t *)&pool.slot_class[slot])) < 0) {
+        if ((prev & ~POOL_ID_MASK) == pp.tag) {
+            unsigned long long idf = prev & POOL_ID_MASK;
+            if (idf == POOL_PENDING) {
+                if (lane == 0) {
+                    while (((prev = *((volatile unsigned long long *)&pool.keys[slot])) & POOL_ID_MASK) == POOL_PENDING) {
+                    }
+                    __threadfence();
                 }
-                __threadfence();
+                idf = __shfl_sync(0xffffffffu, prev, 0) & POOL_ID_MASK;
             }
-            c = __shfl_sync(0xffffffffu, c, 0);
-            // the slot holds a published (fully written) row; it is ours iff it lies in our table's region and
-            // carries the same bits
-            bool same = c >= base && c < limit;
+            // the slot holds a published (fully written) row; it is ours iff it lies in our table's region and carries
+            // the same bits
+            const int64_t c = (int64_t)idf - 1;
+            bool same = idf != POOL_OVERFLOW && c >= base && c < limit;
             if (same) {
 #pragma unroll
                 for (int i = 0; i < WPL; i++) {
@@ -705,11 +775,23 @@ __device__ __forceinline__ void pool_insert(const ClassPool &pool, int wp, int u
             }
         }
         slot = (slot + 1) & pool.cap_mask;
+        prev = 0;
+        if (lane == 0) prev = atomicCAS(&pool.keys[slot], 0ull, pp.tag | POOL_PENDING);
+        prev = __shfl_sync(0xffffffffu, prev, 0);
     }
-    if (lane == 0 && cid < limit) {
+    if (lane == 0 && cid >= 0) {
         atomicAdd(&pool.count[cid], add);
         atomicMin(&pool.first[cid], first);
     }
+}
+
+// Insert bitset `best` (WPL words per lane) into table `ut`; adds `add` to its count and lowers its first index.
+template <int WPL>
+__device__ __forceinline__ void pool_insert(const ClassPool &pool, int wp, int ut, const uint64_t (&best)[WPL],
+                                            unsigned long long add, int first, int lane) {
+    PoolProbe pp;
+    pool_probe_issue<WPL>(pool, wp, ut, best, lane, pp);
+    pool_probe_resolve<WPL>(pool, wp, ut, pool.ut_base[ut], pool.ut_base[ut + 1], best, add, first, lane, pp);
 }
 
 // ---- class rows in the reference's dict order ------------------------------------------------------------------------
@@ -838,11 +920,13 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
     pair_class_kernel(LocusDev loc, const int64_t *__restrict__ job_off, const int32_t *__restrict__ job_ut,
                       const int32_t *__restrict__ job_pair, const int32_t *__restrict__ job_list, int64_t n_jobs,
                       const int32_t *__restrict__ hap_left, const int32_t *__restrict__ hap_right,
-                      const int64_t *__restrict__ row_off, const int32_t *__restrict__ rows, ClassPool pool) {
+                      const int64_t *__restrict__ row_off, const int32_t *__restrict__ rows, ClassPool pool,
+                      const int32_t *__restrict__ n_jobs_dev) {
     const int lane = threadIdx.x & 31;
     const int wp = loc.wp;
     const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
     const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    if (n_jobs_dev) n_jobs = min(n_jobs, (int64_t)*n_jobs_dev);  // list written by job_class_kernel
     for (int64_t q = warp0; q < n_jobs; q += nwarps) {
         const int job = job_list[q];
         const int64_t h0 = job_off[job], h1 = job_off[job + 1];
@@ -882,6 +966,229 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
         }
         pool_insert<WPL>(pool, wp, ut, best, 1ull, job_pair[job], lane);
     }
+}
+
+// Stage (a) in ONE pass for the common job - zero, one or two haplotypes per (pair, table); on a 2x100 bp run that is
+// 90-99 % of the jobs (Gene table: one haplotype per mate; exon tables: mostly none).  The class is then plain set
+// algebra - none: the table mask; one: its set; two: A and B when that is not empty, else A or B; the mask when all of
+// it is empty (add_stat's max_count rule, core:1196-1209) - so no per-allele counter is needed, the sets never leave
+// the registers and nothing but NEW class rows is written to HBM.  Both kernels of the two-kernel form were bound by
+// their chain of dependent L2 round trips (job -> offsets -> haplotype -> rows -> table rows | job -> set -> CAS -> slot
+// -> row compare), so the chain is cut, not just the bytes:
+//   * a warp takes 32 consecutive jobs; lane i fetches ALL scalars of job i (job, offsets, table, pair, region, and per
+//     haplotype: ends, position bounds, first two variant rows) - a handful of dependent loads per 32 jobs instead of per
+//     job - and the jobs are then replayed one at a time from shuffles;
+//   * jobs without a haplotype all insert the table mask: the lanes of a block that share (unit, table) insert once;
+//   * the CAS of job j's insert stays in flight while job j + 1 reads its table rows (pool_probe_issue / _resolve), and a
+//     hit resolves from the CAS result alone (tagged slot words).
+// Jobs with three or more haplotypes are queued for pair_class_kernel (bit-plane counter).
+struct HapMeta {  // lane-resident scalars of one haplotype
+    int left, lo, hi, pk, r0, rw0, rw1;  // pk = rows (6 bits) | deletions ending inside << 6 (6 bits) | first of them << 12
+};
+__device__ __forceinline__ bool hap_meta_load(const LocusDev &loc, const int32_t *__restrict__ hap_left,
+                                              const int32_t *__restrict__ hap_right, const int64_t *__restrict__ row_off,
+                                              const int32_t *__restrict__ rows, int64_t h, HapMeta &m) {
+    m.left = hap_left[h];
+    const HapBounds hb = hap_bounds(loc, m.left, hap_right[h]);
+    const int64_t r0 = row_off[h];
+    const int k1 = (int)(row_off[h + 1] - r0);
+    m.lo = hb.lo;
+    m.hi = hb.hi;
+    m.r0 = (int)r0;
+    m.rw0 = k1 > 0 ? rows[r0] : 0;
+    m.rw1 = k1 > 1 ? rows[r0 + 1] : 0;
+    const int nd = hb.dhi - hb.dlo;
+    m.pk = k1 | (nd << 6) | (hb.dlo << 12);
+    return k1 < 64 && nd < 64 && hb.dlo < (1 << 19);
+}
+// Set algebra of one haplotype with the table-row loads batched.  hap_allele_set_core waits for every row before it
+// knows the next address (one L2 round trip per row, 3k + 2 rows per haplotype); here the warp first walks the
+// haplotype's scalars - uniform integer work - and leaves the e-th row to fetch with lane e (row id in the sparse table,
+// sign bit = "AND it", else "OR it into the negatives"), then fetches the rows B at a time: B x WPL independent loads per
+// round trip.  More than 32 rows (never seen) takes hap_allele_set_core.
+template <int WPL, int B>
+__device__ __forceinline__ void hap_meta_set(const LocusDev &loc, const int32_t *__restrict__ rows, const HapMeta &m, int j,
+                                             const uint64_t *__restrict__ mask, int lane, uint64_t (&set)[WPL]) {
+    const int left = __shfl_sync(0xffffffffu, m.left, j);
+    const int pk = __shfl_sync(0xffffffffu, m.pk, j);
+    const int lo = __shfl_sync(0xffffffffu, m.lo, j), hi = __shfl_sync(0xffffffffu, m.hi, j);
+    const int dlo = pk >> 12, dhi = dlo + ((pk >> 6) & 63), k1 = pk & 63;
+    const int a0 = __shfl_sync(0xffffffffu, m.rw0, j), a1 = __shfl_sync(0xffffffffu, m.rw1, j);
+    const int32_t *rw = rows + __shfl_sync(0xffffffffu, m.r0, j);
+    auto ROW = [=](int k) { return k == 0 ? a0 : (k == 1 ? a1 : rw[k]); };
+    const int wp = loc.wp;
+    const int V1 = max(loc.V, 1);
+    int mine = 0, n = 0;  // entry of this lane: (level * V + row) | AND flag in the sign bit
+    bool fits = true;
+    for (int d0 = dlo; d0 < dhi; d0 += 32) {  // deletions that start left of the haplotype and end inside it
+        int row = 0;
+        const unsigned qm = del_rows_left_of(loc, d0, dhi, left, ROW, k1, lane, row);
+        const int cnt = __popc(qm);
+        if (cnt) {
+            if (n + cnt > 32) {
+                fits = false;
+                break;
+            }
+            const int v = __shfl_sync(0xffffffffu, row, __fns(qm, 0, lane - n + 1) & 31);
+            if (lane >= n && lane < n + cnt) mine = v;
+            n += cnt;
+        }
+    }
+    if (!fits || n + 3 * k1 + 2 > 32) {
+        HapBounds hb = {lo, hi, dlo, dhi};
+        hap_allele_set_core<WPL>(loc, left, hb, ROW, k1, mask, lane, set);
+        return;
+    }
+    int prev = lo;
+    for (int k = 0; k <= k1; k++) {
+        int endr = hi;
+        if (k < k1) {
+            endr = ROW(k);
+            if (n == lane) mine = endr | (int)0x80000000;
+            n++;
+            if (endr < lo) continue;
+            if (endr > hi) endr = hi;
+        }
+        if (endr > prev && prev < hi) {
+            const int lv = 31 - __clz(endr - prev);
+            if (n == lane) mine = lv * V1 + prev;
+            if (n + 1 == lane) mine = lv * V1 + endr - (1 << lv);
+            n += 2;
+        }
+        prev = max(prev, endr + 1);
+    }
+    uint64_t neg[WPL];
+#pragma unroll
+    for (int i = 0; i < WPL; i++) {
+        set[i] = lane + 32 * i < wp ? mask[32 * i] : 0ull;
+        neg[i] = 0ull;
+    }
+    const uint64_t *st = loc.st + lane;
+    for (int e0 = 0; e0 < n; e0 += B) {
+        uint64_t v[B][WPL];
+        int ent[B];
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            ent[b] = __shfl_sync(0xffffffffu, mine, (e0 + b) & 31);
+            const uint64_t *row = st + (size_t)(ent[b] & 0x7fffffff) * wp;
+            const bool on = e0 + b < n;
+#pragma unroll
+            for (int i = 0; i < WPL; i++) v[b][i] = (on && lane + 32 * i < wp) ? row[32 * i] : 0ull;
+        }
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+            if (e0 + b < n) {
+                if (ent[b] < 0) {
+#pragma unroll
+                    for (int i = 0; i < WPL; i++) set[i] &= v[b][i];
+                } else {
+#pragma unroll
+                    for (int i = 0; i < WPL; i++) neg[i] |= v[b][i];
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < WPL; i++) set[i] &= ~neg[i];
+}
+
+template <int WPL, int MINB>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32, WPL <= 4 ? MINB : 2)
+    job_class_kernel(LocusDev loc, const int64_t *__restrict__ job_off, const int32_t *__restrict__ job_ut,
+                     const int32_t *__restrict__ job_pair, const int32_t *__restrict__ job_list, int64_t n_jobs,
+                     const int32_t *__restrict__ hap_left, const int32_t *__restrict__ hap_right,
+                     const int64_t *__restrict__ row_off, const int32_t *__restrict__ rows, ClassPool pool,
+                     int32_t *__restrict__ multi_n, int32_t *__restrict__ multi_list) {
+    const int lane = threadIdx.x & 31;
+    const int wp = loc.wp;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t nblk = (n_jobs + 31) >> 5;
+    bool pending = false;
+    PoolProbe pp;
+    uint64_t pbest[WPL];
+    int p_ut = 0, p_pair = 0, p_base = 0, p_limit = 0, p_add = 0;
+    for (int64_t blk = warp0; blk < nblk; blk += nwarps) {
+        const int64_t q = (blk << 5) + lane;
+        int job = 0, nh = -1, ut = 0, pair = 0, base = 0, limit = 0, add = 1;
+        HapMeta m0 = {0, 0, 0, 0, 0, 0, 0}, m1 = m0;
+        if (q < n_jobs) {
+            job = job_list[q];
+            const int64_t h0 = job_off[job];
+            nh = (int)(job_off[job + 1] - h0);
+            ut = job_ut[job];
+            pair = job_pair[job];
+            base = (int)pool.ut_base[ut];
+            limit = (int)pool.ut_base[ut + 1];
+            bool ok = true;
+            if (nh == 1 || nh == 2) ok = hap_meta_load(loc, hap_left, hap_right, row_off, rows, h0, m0);
+            if (nh == 2) ok &= hap_meta_load(loc, hap_left, hap_right, row_off, rows, h0 + 1, m1);
+            if (!ok) nh = 99;  // (scalars beyond the packed form: take the general kernel)
+        }
+        {  // jobs with several haplotypes go to the bit-plane kernel
+            const unsigned multi = __ballot_sync(0xffffffffu, nh > 2);
+            if (multi) {
+                int at = 0;
+                if (lane == 0) at = atomicAdd(multi_n, __popc(multi));
+                at = __shfl_sync(0xffffffffu, at, 0);
+                if (nh > 2) multi_list[at + __popc(multi & ((1u << lane) - 1u))] = job;
+            }
+        }
+        {  // jobs without a haplotype: one insert per (unit, table) of the block, by the first of its lanes (smallest pair)
+            const unsigned none = __ballot_sync(0xffffffffu, nh == 0);
+            if (nh == 0) {
+                const unsigned grp = __match_any_sync(none, ut);
+                add = __popc(grp);
+                if ((__ffs((int)grp) - 1) != lane) nh = -1;
+            }
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, nh >= 0 && nh <= 2);
+        while (todo) {
+            const int j = __ffs((int)todo) - 1;
+            todo &= todo - 1;
+            const int nh_j = __shfl_sync(0xffffffffu, nh, j);
+            const int ut_j = __shfl_sync(0xffffffffu, ut, j);
+            const uint64_t *mask = loc.mask + (size_t)(ut_j & 3) * wp + lane;
+            uint64_t set[WPL];
+            bool empty = true;
+            if (nh_j >= 1) {
+                hap_meta_set<WPL, (MINB <= 2 ? 4 : 2)>(loc, rows, m0, j, mask, lane, set);
+                uint64_t any = 0;
+                if (nh_j == 2) {
+                    uint64_t other[WPL], any2 = 0;
+                    hap_meta_set<WPL, (MINB <= 2 ? 4 : 2)>(loc, rows, m1, j, mask, lane, other);
+#pragma unroll
+                    for (int i = 0; i < WPL; i++) {
+                        any2 |= set[i] & other[i];
+                        any |= set[i] | other[i];
+                    }
+                    const bool both = __any_sync(0xffffffffu, any2 != 0ull);
+#pragma unroll
+                    for (int i = 0; i < WPL; i++) set[i] = both ? (set[i] & other[i]) : (set[i] | other[i]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < WPL; i++) any |= set[i];
+                }
+                empty = !__any_sync(0xffffffffu, any != 0ull);
+            }
+            if (empty) {  // max_count == 0: every allele of the table (core:1203-1209)
+#pragma unroll
+                for (int i = 0; i < WPL; i++) set[i] = lane + 32 * i < wp ? mask[32 * i] : 0ull;
+            }
+            if (pending)
+                pool_probe_resolve<WPL>(pool, wp, p_ut, p_base, p_limit, pbest, (unsigned long long)p_add, p_pair, lane, pp);
+            pool_probe_issue<WPL>(pool, wp, ut_j, set, lane, pp);
+#pragma unroll
+            for (int i = 0; i < WPL; i++) pbest[i] = set[i];
+            p_ut = ut_j;
+            p_pair = __shfl_sync(0xffffffffu, pair, j);
+            p_base = __shfl_sync(0xffffffffu, base, j);
+            p_limit = __shfl_sync(0xffffffffu, limit, j);
+            p_add = __shfl_sync(0xffffffffu, add, j);
+            pending = true;
+        }
+    }
+    if (pending) pool_probe_resolve<WPL>(pool, wp, p_ut, p_base, p_limit, pbest, (unsigned long long)p_add, p_pair, lane, pp);
 }
 
 // Projection of the Gene table onto a kept allele set (core:1753-1766): every class of table src_ut is ANDed with
@@ -1179,7 +1486,7 @@ struct LocusBatch {
     // job_list (<= 7 haplotypes first, then the rest) | hap_left | hap_right | hap_table | rows
     struct JobArena {
         size_t o_job_off = 0, o_row_off = 0, o_ut_base = 0, o_job_ut = 0, o_job_pair = 0, o_job_list = 0, o_hl = 0, o_hr = 0,
-               o_ht = 0, o_rows = 0, bytes = 0;
+               o_ht = 0, o_rows = 0, o_multi = 0, bytes = 0;
     } ja;
     int64_t n_jobs = 0, n_small = 0, n_big = 0, n_haps = 0, n_rows = 0, max_job_haps = 0;
     std::vector<int64_t> ut_base;  // [n_units*4 + 1]
@@ -1190,7 +1497,7 @@ struct LocusBatch {
     T *dj(size_t off) const { return reinterpret_cast<T *>(static_cast<unsigned char *>(d_jobs.p) + off); }
     template <class T>
     T *hj(size_t off) const { return reinterpret_cast<T *>(static_cast<unsigned char *>(h_jobs.p) + off); }
-    DevBuf d_keys, d_slot, d_bits, d_count, d_first, d_ut_ncls, d_sortbits, d_sortcnt, d_sortfirst;
+    DevBuf d_keys, d_bits, d_count, d_first, d_ut_ncls, d_sortbits, d_sortcnt, d_sortfirst;
     DevBuf d_prob, d_inres, d_fk, d_is, d_emws;      // EM over exon (hla) / gene (other) tables
     DevBuf d_prob2, d_inres2, d_fk2, d_is2, d_keep, d_ulist;  // second-level EM (hla)
     DevBuf d_acount, d_afirst;
@@ -1212,7 +1519,7 @@ struct LocusBatch {
     int n_level2 = 0;
     void release() {
         DevBuf *all[] = {&d_jobs, &d_hapbits,
-                         &d_keys, &d_slot, &d_bits, &d_count, &d_first, &d_ut_ncls, &d_sortbits, &d_sortcnt, &d_sortfirst, &d_prob, &d_inres, &d_fk,
+                         &d_keys, &d_bits, &d_count, &d_first, &d_ut_ncls, &d_sortbits, &d_sortcnt, &d_sortfirst, &d_prob, &d_inres, &d_fk,
                          &d_is, &d_emws, &d_prob2, &d_inres2, &d_fk2, &d_is2, &d_keep, &d_ulist,
                          &d_acount, &d_afirst, &d_ck[0], &d_ck[1], &d_cn[0], &d_cn[1]};
         for (DevBuf *b : all) b->release();
@@ -1224,7 +1531,7 @@ struct LocusBatch {
     }
     ClassPool pool() const {
         ClassPool p;
-        p.keys = d_keys.as<unsigned long long>(); p.slot_class = d_slot.as<int32_t>(); p.cap_mask = cap - 1;
+        p.keys = d_keys.as<unsigned long long>(); p.cap_mask = cap - 1;
         p.bits = d_bits.as<uint64_t>(); p.count = d_count.as<unsigned long long>(); p.first = d_first.as<int32_t>();
         p.ut_base = dj<int64_t>(ja.o_ut_base); p.ut_ncls = d_ut_ncls.as<int32_t>();
         return p;
@@ -1291,15 +1598,19 @@ static int batch_threads(const hgt_params &p) {
 // ---- stage 1: text to the device, line count ----------------------------------------------------------------------------------
 static inline size_t a16(size_t x) { return (x + 15) & ~(size_t)15; }
 
-// Stage (a) runs as two kernels (compat_kernel -> hapbits in HBM -> class_kernel).  HGT_STAGE_A=fused selects the
-// one-kernel form (pair_class_kernel, no hapbits buffer) for A/B measurements.
-static bool stage_a_split() {
-    static const bool split = [] {
-        const char *e = getenv("HGT_STAGE_A");
-        return !(e && !strcmp(e, "fused"));
-    }();
-    return split;
+// Stage (a) forms.  Default: two kernels (compat_kernel -> hapbits in HBM -> class_kernel).  HGT_STAGE_A=job selects
+// job_class_kernel (0 / 1 / 2 haplotypes per job, sets stay in registers) + pair_class_kernel for the rest: a fifth of the
+// DRAM traffic, but measured SLOWER on B200 (3.6 vs 2.6 ms per 128-sample step) - every form is bound by warp
+// instructions and L2 round trips per haplotype, not by HBM bytes.  HGT_STAGE_A=fused = the bit-plane kernel
+// for every job.  All three give identical tables (tests/test_gpu_wide.py).
+enum { STAGE_A_JOB = 0, STAGE_A_SPLIT = 1, STAGE_A_FUSED = 2 };
+static int stage_a_mode() {
+    const char *e = getenv("HGT_STAGE_A");  // (read on every call: the tests switch it between batches)
+    if (e && !strcmp(e, "job")) return STAGE_A_JOB;
+    if (e && !strcmp(e, "fused")) return STAGE_A_FUSED;
+    return STAGE_A_SPLIT;
 }
+static bool stage_a_split() { return stage_a_mode() == STAGE_A_SPLIT; }
 
 static int tune_env(const char *name, int dflt) {  // grid-size experiments without a rebuild
     const char *e = getenv(name);
@@ -1698,7 +2009,7 @@ static int reads_execute(hgt_batch *b, cudaStream_t st) {
         const size_t n_units = lb.units.size();
         const int64_t *tot = reinterpret_cast<const int64_t *>(hs + rd.s_totals) + l * 6;
         const int64_t J = tot[0] * n_tables, H = tot[1], RW = tot[2];
-        if (J > 0x7fffffff || H > 0x7fffffff) {
+        if (J > 0x7fffffff || H > 0x7fffffff || RW > 0x7fffffff) {
             hgt_set_error("more than 2^31 jobs or haplotypes in one locus batch: split the batch");
             return HGT_ERR_UNSUPPORTED;
         }
@@ -1717,6 +2028,10 @@ static int reads_execute(hgt_batch *b, cudaStream_t st) {
             }
         }
         lb.n_rows_pool = lb.ut_base.back();
+        if (lb.n_rows_pool > POOL_MAX_ROWS) {
+            hgt_set_error("more than 2^28 class rows in one locus batch: split the batch");
+            return HGT_ERR_UNSUPPORTED;
+        }
         LocusBatch::JobArena &ja = lb.ja;
         ja.o_job_off = 0;
         ja.o_row_off = a16(ja.o_job_off + (size_t)(J + 1) * 8);
@@ -1728,7 +2043,8 @@ static int reads_execute(hgt_batch *b, cudaStream_t st) {
         ja.o_hr = a16(ja.o_hl + (size_t)H * 4);
         ja.o_ht = a16(ja.o_hr + (size_t)H * 4);
         ja.o_rows = a16(ja.o_ht + (size_t)H * 4);
-        ja.bytes = a16(ja.o_rows + (size_t)RW * 4);
+        ja.o_multi = a16(ja.o_rows + (size_t)RW * 4);  // [0] = length, [4..] = jobs with >= 2 haplotypes (job_class_kernel)
+        ja.bytes = a16(ja.o_multi + (size_t)(J + 4) * 4);
         HGT_CHECK(lb.d_jobs.alloc(ja.bytes));
         HGT_CHECK(lb.h_jobs.alloc((n_units * 4 + 1) * 8));
         memcpy(lb.h_jobs.p, lb.ut_base.data(), (n_units * 4 + 1) * 8);
@@ -1766,7 +2082,6 @@ static int batch_alloc_tables(hgt_batch *b, cudaStream_t st) {
             while ((int64_t)lb.cap < 2 * std::max<int64_t>(lb.n_rows_pool, 1)) lb.cap <<= 1;
             if (stage_a_split()) HGT_CHECK(lb.d_hapbits.alloc((size_t)std::max<int64_t>(lb.n_haps, 1) * wp * 8));
             HGT_CHECK(lb.d_keys.alloc((size_t)lb.cap * 8));
-            HGT_CHECK(lb.d_slot.alloc((size_t)lb.cap * 4));
             const size_t pr = (size_t)std::max<int64_t>(lb.n_rows_pool, 1);
             HGT_CHECK(lb.d_bits.alloc(pr * wp * 8));
             HGT_CHECK(lb.d_count.alloc(pr * 8));
@@ -1932,27 +2247,49 @@ static void launch_stage_a(hgt_batch *b, cudaStream_t st, LocusBatch &lb) {
     const LocusDev ld = locus_dev(loc);
     const int wp = loc->wp;
     const int64_t H = lb.n_haps;
-    if (!stage_a_split()) {
+    const int mode = stage_a_mode();
+    if (mode != STAGE_A_SPLIT) {
         const ClassPool pool = lb.pool();
         const int64_t ns = lb.n_small, nb = lb.n_big;
+        int n_launch = 0;
         b->timer.begin(ctx, st, 2);
+        const int32_t *small_list = lb.dj<int32_t>(lb.ja.o_job_list), *small_n = nullptr;
+        if (ns > 0 && mode == STAGE_A_JOB) {
+            static const int job_per_sm = tune_env("HGT_JOB_CTAS_PER_SM", 16);
+            int32_t *multi = lb.dj<int32_t>(lb.ja.o_multi);
+            cudaMemsetAsync(multi, 0, 16, st);
+            const int64_t blocks = (ns + 31) / 32;
+            const int ctas = (int)std::min<int64_t>((blocks + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * job_per_sm);
+            static const int minb = tune_env("HGT_JOB_MINB", 3);  // resident CTAs per SM the kernel is compiled for (64 / 80 / 128 registers)
+            auto kern = minb == 3 ? job_class_kernel<WPL, 3> : (minb == 2 ? job_class_kernel<WPL, 2> : job_class_kernel<WPL, 4>);
+            kern<<<ctas, WARPS_PER_CTA * 32, 0, st>>>(
+                ld, lb.dj<int64_t>(lb.ja.o_job_off), lb.dj<int32_t>(lb.ja.o_job_ut), lb.dj<int32_t>(lb.ja.o_job_pair), small_list, ns,
+                lb.dj<int32_t>(lb.ja.o_hl), lb.dj<int32_t>(lb.ja.o_hr), lb.dj<int64_t>(lb.ja.o_row_off), lb.dj<int32_t>(lb.ja.o_rows),
+                pool, multi, multi + 4);
+            small_list = multi + 4;
+            small_n = multi;
+            n_launch++;
+        }
         if (ns > 0) {
-            const int ctas = (int)std::min<int64_t>((ns + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 8);
+            // (job form: the list length is on the device; 2-3 % of the jobs, so a small grid)
+            const int64_t est = small_n ? std::max<int64_t>(ns / 8, 1) : ns;
+            const int ctas = (int)std::min<int64_t>((est + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 8);
             pair_class_kernel<WPL, 3><<<ctas, WARPS_PER_CTA * 32, 0, st>>>(
-                ld, lb.dj<int64_t>(lb.ja.o_job_off), lb.dj<int32_t>(lb.ja.o_job_ut), lb.dj<int32_t>(lb.ja.o_job_pair),
-                lb.dj<int32_t>(lb.ja.o_job_list), ns, lb.dj<int32_t>(lb.ja.o_hl), lb.dj<int32_t>(lb.ja.o_hr),
-                lb.dj<int64_t>(lb.ja.o_row_off), lb.dj<int32_t>(lb.ja.o_rows), pool);
-            ctx->launches++;
+                ld, lb.dj<int64_t>(lb.ja.o_job_off), lb.dj<int32_t>(lb.ja.o_job_ut), lb.dj<int32_t>(lb.ja.o_job_pair), small_list, ns,
+                lb.dj<int32_t>(lb.ja.o_hl), lb.dj<int32_t>(lb.ja.o_hr), lb.dj<int64_t>(lb.ja.o_row_off), lb.dj<int32_t>(lb.ja.o_rows),
+                pool, small_n);
+            n_launch++;
         }
         if (nb > 0) {
             const int ctas = (int)std::min<int64_t>((nb + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 8);
             pair_class_kernel<WPL, 8><<<ctas, WARPS_PER_CTA * 32, 0, st>>>(
                 ld, lb.dj<int64_t>(lb.ja.o_job_off), lb.dj<int32_t>(lb.ja.o_job_ut), lb.dj<int32_t>(lb.ja.o_job_pair),
                 lb.dj<int32_t>(lb.ja.o_job_list) + ns, nb, lb.dj<int32_t>(lb.ja.o_hl), lb.dj<int32_t>(lb.ja.o_hr),
-                lb.dj<int64_t>(lb.ja.o_row_off), lb.dj<int32_t>(lb.ja.o_rows), pool);
-            ctx->launches++;
+                lb.dj<int64_t>(lb.ja.o_row_off), lb.dj<int32_t>(lb.ja.o_rows), pool, nullptr);
+            n_launch++;
         }
-        b->timer.end((ns > 0) + (nb > 0));
+        ctx->launches += n_launch;
+        b->timer.end(n_launch);
         return;
     }
     b->timer.begin(ctx, st, 1);
@@ -2054,7 +2391,6 @@ static int batch_execute(hgt_batch *b, cudaStream_t st) {
         for (DevBuf &x : lb.d_coopws) x.release();  // (a repeated execute: the previous finish has synchronised)
         lb.d_coopws.clear();
         HGT_CUDA(cudaMemsetAsync(lb.d_keys.p, 0, (size_t)lb.cap * 8, st));
-        HGT_CUDA(cudaMemsetAsync(lb.d_slot.p, 0xff, (size_t)lb.cap * 4, st));
         HGT_CUDA(cudaMemsetAsync(lb.d_count.p, 0, pr * 8, st));
         HGT_CUDA(cudaMemsetAsync(lb.d_first.p, 0x7f, pr * 4, st));
         HGT_CUDA(cudaMemsetAsync(lb.d_ut_ncls.p, 0, n_units * 16, st));

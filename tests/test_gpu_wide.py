@@ -76,3 +76,27 @@ def test_many_haplotype_pairs(A, base):
                                            batch.unit_gene_counts(0, tb)), ref, ol, hla)
     batch.close()
     t.close()
+
+
+@pytest.mark.parametrize("form", ["job", "fused"])
+@pytest.mark.parametrize("A,base", [(2100, "hla"), (7000, "cyp")])
+def test_stage_a_forms_agree(A, base, form, monkeypatch):
+    """The default stage (a) is the two-kernel form (compat_kernel -> hapbits -> class_kernel); job_class_kernel (0 / 1 / 2
+    haplotypes per job in registers) + pair_class_kernel and the all-bit-plane form stay selectable (HGT_STAGE_A) and must
+    give the same tables."""
+    from hisatgenotype_b200 import typing_core as TC
+    from hisatgenotype_b200.locus import LocusTables
+    monkeypatch.setenv("HGT_STAGE_A", form)
+    args, sam, truth = synthetic_case(100 + A % 97, A, L=3000, n_pairs=700, base=base, del_frac=0.08,
+                                      n_groups=40, core_vars=70, pool_private=1200)
+    ol = O.OracleLocus(*args)
+    t = LocusTables(*args)
+    hla = base == "hla"
+    ref = O.type_locus(ol, sam, simulation=False)
+    batch = TC.Batch([t], TC.make_params(), True)
+    batch.add_unit(0, sam)
+    batch.run()
+    assert_tables_equal_oracle(lambda tb: (list(map(list, batch.unit_gene_cmpt(0, tb).items())),
+                                           batch.unit_gene_counts(0, tb)), ref, ol, hla)
+    batch.close()
+    t.close()
