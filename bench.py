@@ -734,6 +734,45 @@ def run_workload(args):
     return 1 if parity_failed else 0
 
 # ------------------------------------------------------------------------------------------------------------
+def oversized_subrecord(args, rank, world):
+    """BASELINE configs[3] (one oversized locus, reads sharded over the ranks, strong scaling) as a sub-record of the default
+    line, so that `bench.py --gpus N` also reports the one workload with a data-path exchange (class-table merge + the
+    peer-memory EM).  Every rank starts `bench.py --workload oversized` as a CHILD process with its own rendezvous port and
+    a time limit: a failure there can cost the sub-record, never the main line."""
+    import subprocess
+    if args.oversized_sub_reads <= 0:
+        return None
+    env = {k: v for k, v in os.environ.items() if not k.startswith("TORCHELASTIC_")}  # (rank 0 of the children hosts their store)
+    if world > 1:
+        env["MASTER_PORT"] = str(int(os.environ.get("MASTER_PORT", "29500")) + 1)
+    env["HGT_BENCH_NO_SMI"] = "1"
+    cmd = [sys.executable, os.path.abspath(__file__), "--workload", "oversized", "--gpus", str(world), "--steps", "3", "--warmup", "3",
+           "--no-cpu-baseline", "--oversized-reads", str(args.oversized_sub_reads)]
+    t0 = time.perf_counter()
+    try:
+        out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=420)
+    except subprocess.TimeoutExpired:
+        return {"error": "timed out after 420 s"} if rank == 0 else None
+    if rank != 0:
+        return None
+    rec = None
+    for ln in out.stdout.splitlines():
+        if ln.startswith("{"):
+            try:
+                rec = json.loads(ln)
+            except ValueError:
+                pass
+    if rec is None:
+        return {"error": "no line (exit %d): %s" % (out.returncode, out.stderr.strip().splitlines()[-1:] or "")}
+    keep = ("metric", "value", "unit", "n_gpus", "ms_per_step", "scaling", "reads_per_step", "classes_rank0", "em_iters_rank0",
+            "sharded_em_wall_ms_rank0", "stage_ms_per_step_rank0", "step_ms_rank0", "example_call")
+    sub = {k: rec[k] for k in keep if k in rec}
+    sub["workload"] = rec["config"]["workload"]
+    sub["e2e"] = {k: rec["e2e"][k] for k in ("value", "unit", "ms_per_step") if k in rec.get("e2e", {})}
+    sub["wall_s"] = round(time.perf_counter() - t0, 1)
+    return sub
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -749,6 +788,9 @@ def main():
     ap.add_argument("--batch-samples", type=int, default=1000, help="samples of the batch1000 workload (all ranks together)")
     ap.add_argument("--oversized-reads", type=int, default=1000000)
     ap.add_argument("--pipeline-depth", type=int, default=3, help="batches in flight in the end-to-end measurement")
+    ap.add_argument("--oversized-sub-reads", type=int, default=10000000,
+                    help="reads of the read-sharded oversized locus reported as the `oversized` sub-record of the default "
+                         "line (0 = skip)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -945,6 +987,9 @@ def main():
 
     parity_failed = False
     text_bytes_step = sum(len(t) for _, t in units)
+    barrier()
+    over = oversized_subrecord(args, rank, world)  # (child processes; every rank takes part)
+    barrier()
     if rank == 0:
         peak, peak_src = measured_peak()
         a_ms = stage["compat"] + stage["class"]
@@ -1009,6 +1054,8 @@ def main():
             "clocks": clocks.summary(),
             "example_call": calls[0],
         }
+        if over is not None:
+            line["oversized"] = over
         if not args.no_cpu_baseline and world == 1:  # the CPU baseline is timed on rank 0 at N = 1 only
             build_oracle_loci(cont, loci)
             line["cpu_baseline"], line["parity_checked"] = cpu_baseline(units[:args.cpu_baseline_units], batch)

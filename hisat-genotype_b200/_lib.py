@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhgt.so")
 
 HGT_OK, HGT_ERR_CUDA, HGT_ERR_KEY, HGT_ERR_ZERODIV, HGT_ERR_ARG = 0, -1, -2, -3, -4
-HGT_ERR_UNSUPPORTED, HGT_ERR_PARSE, HGT_ERR_AMBIGUITY, HGT_ERR_NOMEM = -5, -6, -7, -8
+HGT_ERR_UNSUPPORTED, HGT_ERR_PARSE, HGT_ERR_AMBIGUITY, HGT_ERR_NOMEM, HGT_ERR_PEER = -5, -6, -7, -8, -9
 
 c_void_p, c_int, c_i32, c_i64, c_size_t = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int32, ctypes.c_int64,
                                            ctypes.c_size_t)

@@ -76,6 +76,46 @@ struct Trace {
     }
 };
 
+// ---- read-sharded locus: the per-allele sums of a sweep are exchanged through NVLink peer memory -------------------------
+// Every rank (one process per GPU) owns one exchange block, cudaMalloc'ed by hgt_em_peer_alloc and mapped into the other
+// processes through CUDA IPC: uint32 flags[EM_PEER_MAX][EM_PEER_G] | int32 abort | uint32 seq | pad to 256 B |
+// double data[2][Apad]  (seq = exchanges done so far: a launch continues the numbering of the previous one, so stale
+// flags can never satisfy a wait).
+// One exchange (sequence number q, parity q & 1), per CTA g - all ranks run the same grid, so CTA g owns the same slice of
+// the alleles everywhere: the CTA stores its slice of the locally reduced sums into ITS OWN rank's data[parity]; after a
+// system-scope fence it writes q into flags[own rank][g] of every peer's block (one remote store per peer), waits until
+// its own block holds flags[r][g] >= q for every peer r, and adds up the slice over the ranks in rank order straight from
+// the peers' blocks (remote loads, all in flight together) - so all ranks obtain bit-identical sums and take the same
+// branches of the loop, and the only grid-wide step of the exchange is the sync the single-GPU kernel has anyway.
+// data[parity] is rewritten two exchanges later, by which time CTA g of every peer has signalled the exchange in
+// between, i.e. finished reading.  A peer that does not arrive within EM_PEER_TIMEOUT_NS raises the abort word: the wait
+// ends, every CTA sees the word after the next grid sync and the kernel returns HGT_ERR_PEER instead of hanging the GPU.
+constexpr int EM_PEER_MAX = 16, EM_PEER_G = 256;  // ranks, CTAs per rank
+constexpr unsigned long long EM_PEER_TIMEOUT_NS = 4000000000ull;
+constexpr size_t EM_PEER_FLAG_BYTES = (size_t)EM_PEER_MAX * EM_PEER_G * 4, EM_PEER_HDR = EM_PEER_FLAG_BYTES + 256;
+struct EmPeer {
+    int rank, world;
+    unsigned char *block[EM_PEER_MAX];  // block[r] = rank r's exchange block as mapped in this process
+};
+__device__ __forceinline__ void st_release_sys(uint32_t *p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_sys_f64(const double *p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ int32_t ld_sys_s32(const int32_t *p) {
+    int32_t v;
+    asm volatile("ld.relaxed.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
 struct EmArgs {
     const uint64_t *bits;
     const double *cnt;
@@ -93,6 +133,7 @@ struct EmArgs {
     const int32_t *C_ptr;               // number of classes read on the device at launch; overrides C
     const int32_t *class_first;         // tie-break key of each class (first pair index); default = class index
     int32_t key_offset;                 // added to every class key (read-sharded locus: pairs of the lower ranks)
+    const EmPeer *peer;                 // cooperative launch on a read-sharded locus: exchange blocks of all ranks (else null)
     double *prob;
     uint8_t *in_result;
     int32_t *first_class;
@@ -438,12 +479,65 @@ __device__ __forceinline__ void em_accumulate(const EmArgs &a, const Smem &sm, i
     }
 }
 
+// The exchange step of a sweep on a read-sharded locus (see EmPeer).  Not inlined: it runs once per sweep, and inlined its
+// sixteen in-flight remote loads would raise the register pressure of every em_kernel<.., true> instance.
+__device__ __noinline__ void peer_exchange(const EmArgs &a, const EmPeer *px, int mode, uint32_t q, int a_lo, int a_hi, int Apad,
+                                           int g) {
+    const int tid = threadIdx.x;
+    // slice g of this rank <-> slice g of every peer (same grid on every rank): no grid-wide step in between
+    __threadfence_system();  // (by the lanes that wrote the slice)
+    __syncthreads();
+    uint32_t *my_flags = reinterpret_cast<uint32_t *>(px->block[px->rank]);
+    int32_t *my_abort = reinterpret_cast<int32_t *>(px->block[px->rank] + EM_PEER_FLAG_BYTES);
+    if (tid < px->world && tid != px->rank) {
+        st_release_sys(reinterpret_cast<uint32_t *>(px->block[tid]) + px->rank * EM_PEER_G + g, q);
+        unsigned long long t0, t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while (ld_acquire_sys(my_flags + tid * EM_PEER_G + g) < q) {
+            if (*reinterpret_cast<volatile int32_t *>(my_abort)) break;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            if (t1 - t0 > EM_PEER_TIMEOUT_NS) {
+                atomicExch(my_abort, 1);
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    const size_t off = EM_PEER_HDR + (size_t)(q & 1u) * Apad * 8;
+    for (int al = a_lo + tid; al < a_hi; al += EM_THREADS) {
+        // all remote loads in flight together, then the sum in rank order (the same association on every rank)
+        if (mode == MODE_FIRSTK) {
+            int32_t x = FK_NONE;
+            for (int r0 = 0; r0 < px->world; r0 += 8) {
+                int32_t v[8];
+#pragma unroll
+                for (int r = 0; r < 8; r++)
+                    v[r] = r0 + r < px->world ? ld_sys_s32(reinterpret_cast<const int32_t *>(px->block[r0 + r] + off) + al) : FK_NONE;
+#pragma unroll
+                for (int r = 0; r < 8; r++) x = min(x, v[r]);
+            }
+            a.red_aux[al] = x;
+        } else {
+            double s = -0.0;
+            for (int r0 = 0; r0 < px->world; r0 += 8) {
+                double v[8];
+#pragma unroll
+                for (int r = 0; r < 8; r++)
+                    v[r] = r0 + r < px->world ? ld_sys_f64(reinterpret_cast<const double *>(px->block[r0 + r] + off) + al) : -0.0;
+#pragma unroll
+                for (int r = 0; r < 8; r++) s += v[r];  // (-0.0 is the neutral element, also for the sign-of-zero flag)
+            }
+            a.red_acc[al] = s;
+        }
+    }
+}
+
 // One sweep over this CTA's class rows.  mode INIT: initial mass (common:1299-1309); NEXT: next_prob
 // (common:1311-1336); FIRSTK: only the dict insertion order of next_prob's output.
 template <int NA, bool COOP>
 __device__ void em_sweep(const EmArgs &a, const Smem &sm, int mode, const double *pin, const uint8_t *livein,
                          double *pout, uint8_t *liveout, int32_t *fkout, int row_lo, int row_hi, bool resident,
-                         bool &loaded, uint32_t &parity, int *status, Trace &tr) {
+                         bool &loaded, uint32_t &parity, int *status, Trace &tr, uint32_t &xseq) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int A = a.A, wp = a.wp;
     const int Apad = wp * 64;
@@ -471,20 +565,33 @@ __device__ void em_sweep(const EmArgs &a, const Smem &sm, int mode, const double
         grid.sync();
         const int Ag = (A + G - 1) / G;
         const int a_lo = g * Ag, a_hi = min(A, a_lo + Ag);
+        // (read-sharded locus: the slice goes to this rank's exchange block first, see EmPeer)
+        const EmPeer *px = a.peer;
+        const uint32_t q = xseq + 1;
+        double *x_acc = px ? reinterpret_cast<double *>(px->block[px->rank] + EM_PEER_HDR) + (size_t)(q & 1u) * Apad : a.red_acc;
+        int32_t *x_aux = px ? reinterpret_cast<int32_t *>(x_acc) : a.red_aux;
         for (int al = a_lo + warp; al < a_hi; al += EM_WARPS) {
             if (mode == MODE_FIRSTK) {
                 int32_t x = FK_NONE;
                 for (int gg = lane; gg < G; gg += 32) x = min(x, __ldcg(&a.part_aux[(size_t)al * G + gg]));
                 for (int o = 16; o > 0; o >>= 1) x = min(x, __shfl_xor_sync(0xffffffffu, x, o));
-                if (lane == 0) a.red_aux[al] = x;
+                if (lane == 0) x_aux[al] = x;
             } else {
                 double s = -0.0;
                 for (int gg = lane; gg < G; gg += 32) s += __ldcg(&a.part_acc[(size_t)al * G + gg]);
                 s = warp_sum(s);
-                if (lane == 0) a.red_acc[al] = s;
+                if (lane == 0) x_acc[al] = s;
             }
         }
+        if (px) {
+            xseq = q;
+            peer_exchange(a, px, mode, q, a_lo, a_hi, Apad, g);
+        }
         grid.sync();
+        if (px && *reinterpret_cast<volatile int32_t *>(px->block[px->rank] + EM_PEER_FLAG_BYTES)) {
+            if (tid == 0) *status = HGT_ERR_PEER;  // (every CTA reads the same word after the grid sync)
+            __syncthreads();
+        }
         hit = 0;
 #pragma unroll
         for (int i = 0; i < NA; i++) {
@@ -1152,13 +1259,15 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
     const bool resident = compacted || (row_hi - row_lo) <= a.slab_rows;
     bool loaded = compacted;
     uint32_t parity = 0;
+    uint32_t xseq = 0;  // exchanges done (read-sharded locus); continues from the block's last sequence number
+    if (COOP && a.peer) xseq = *reinterpret_cast<const volatile uint32_t *>(a.peer->block[a.peer->rank] + EM_PEER_FLAG_BYTES + 4);
     double *v0 = a.vec, *v1 = a.vec + Apad, *v2 = a.vec + 2 * (size_t)Apad, *v3 = a.vec + 3 * (size_t)Apad;
     uint8_t *l0 = a.live, *l1 = a.live + Apad, *l2 = a.live + 2 * (size_t)Apad;
     // In cooperative mode every CTA computes the same vectors and writes identical values to the shared
     // workspace; reads of those values are ordered by the sweep's grid syncs / __syncthreads.
     tr.mark(5);
     em_sweep<NA, COOP>(a, sm, MODE_INIT, nullptr, nullptr, v0, l0, nullptr, row_lo, row_hi, resident, loaded,
-                       parity, &s_status, tr);
+                       parity, &s_status, tr, xseq);
     double diff = 1.0;
     int iter = 0, sweeps = 0;
     const double *last_in = v0;
@@ -1264,9 +1373,9 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
         }
         tr.mark(6);
         em_sweep<NA, COOP>(a, sm, MODE_NEXT, v0, l0, v1, l1, nullptr, row_lo, row_hi, resident, loaded, parity,
-                           &s_status, tr);
+                           &s_status, tr, xseq);
         em_sweep<NA, COOP>(a, sm, MODE_NEXT, v1, l1, v2, l2, nullptr, row_lo, row_hi, resident, loaded, parity,
-                           &s_status, tr);
+                           &s_status, tr, xseq);
         sweeps += 2;
         // SQUAREM extrapolation (common:1361-1383)
         double ssr = 0.0, ssv = 0.0;
@@ -1309,7 +1418,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
             __syncthreads();
             tr.mark(6);
             em_sweep<NA, COOP>(a, sm, MODE_NEXT, v3, l2, v1, l1, nullptr, row_lo, row_hi, resident, loaded,
-                               parity, &s_status, tr);
+                               parity, &s_status, tr, xseq);
             sweeps += 1;
             last_in = v3;
             last_live = l2;
@@ -1363,7 +1472,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
         // alleles (common:1324-1331); needed for the stable sort's tie-break (common:1409)
         if (have_last) {
             em_sweep<NA, COOP>(a, sm, MODE_FIRSTK, last_in, last_live, nullptr, nullptr, a.first_class, row_lo,
-                               row_hi, resident, loaded, parity, &s_status, tr);
+                               row_hi, resident, loaded, parity, &s_status, tr, xseq);
         } else if (writer) {
             for (int al = tid; al < A_orig; al += EM_THREADS) a.first_class[al] = FK_NONE;
         }
@@ -1386,6 +1495,7 @@ __global__ void __launch_bounds__(EM_THREADS, 1) em_kernel(const EmArgs *__restr
         a.iters_status[0] = iter;
         a.iters_status[1] = s_status;
         a.iters_status[2] = sweeps;
+        if (COOP && a.peer) *reinterpret_cast<uint32_t *>(a.peer->block[a.peer->rank] + EM_PEER_FLAG_BYTES + 4) = xseq;
     }
 }
 
@@ -1599,7 +1709,7 @@ struct EmWs {
 };
 size_t em_ws_bytes(int sm_count, int A) {
     const size_t Apad = (size_t)hgt_row_pitch(A) * 64;
-    size_t b = 256;                                   // args
+    size_t b = 512;                                   // args (+ the EmPeer of a read-sharded launch)
     b += align_up(4 * Apad * 8, 256);                 // vec
     b += align_up(4 * Apad, 256);                     // live
     b += align_up((size_t)sm_count * Apad * 8, 256);  // part_acc
@@ -1612,7 +1722,7 @@ EmWs em_ws_carve(void *ws, int sm_count, int A) {
     const size_t Apad = (size_t)hgt_row_pitch(A) * 64;
     unsigned char *p = static_cast<unsigned char *>(ws);
     EmWs w;
-    w.d_args = reinterpret_cast<EmArgs *>(p); p += 256;
+    w.d_args = reinterpret_cast<EmArgs *>(p); p += 512;
     w.vec = reinterpret_cast<double *>(p); p += align_up(4 * Apad * 8, 256);
     w.live = p; p += align_up(4 * Apad, 256);
     w.part_acc = reinterpret_cast<double *>(p); p += align_up((size_t)sm_count * Apad * 8, 256);
@@ -1658,7 +1768,7 @@ extern "C" int hgt_em_dev(hgt_ctx *ctx, void *stream, const uint64_t *class_bits
     EmArgs a;
     a.bits = class_bits; a.cnt = class_count; a.len = allele_len;
     a.C = n_classes; a.A = n_alleles; a.wp = wp; a.remove_low = remove_low; a.fixed_iters = fixed_iters;
-    a.cnt_u64 = nullptr; a.C_ptr = nullptr; a.class_first = nullptr; a.key_offset = 0;
+    a.cnt_u64 = nullptr; a.C_ptr = nullptr; a.class_first = nullptr; a.key_offset = 0; a.peer = nullptr;
     a.prob = prob; a.in_result = in_result; a.first_class = first_class; a.iters_status = iters_status;
     a.vec = w.vec; a.live = w.live; a.part_acc = w.part_acc; a.part_aux = w.part_aux;
     a.red_acc = w.red_acc; a.red_aux = w.red_aux;
@@ -1676,6 +1786,107 @@ extern "C" int hgt_em_dev(hgt_ctx *ctx, void *stream, const uint64_t *class_bits
     }
     HGT_CUDA(cudaMemcpyAsync(w.d_args, &a, sizeof(a), cudaMemcpyHostToDevice, st));
     if (G == 1) return em_launch<false>(ctx, st, w.d_args, 1, plan.na, plan.smem);
+    return em_launch<true>(ctx, st, w.d_args, G, plan.na, plan.smem);
+}
+
+// ---- read-sharded locus across GPUs: the whole loop as ONE cooperative launch per rank (EmPeer) ----------------------------
+extern "C" size_t hgt_em_peer_block_bytes(int32_t n_alleles) {
+    const size_t Apad = (size_t)hgt_row_pitch(n_alleles < 1 ? 1 : n_alleles) * 64;
+    return EM_PEER_HDR + 2 * Apad * 8;
+}
+extern "C" int hgt_em_peer_alloc(hgt_ctx *ctx, int32_t n_alleles, void **block, unsigned char handle[64]) {
+    if (!ctx || !block || !handle || n_alleles < 1) {
+        hgt_set_error("hgt_em_peer_alloc: bad argument");
+        return HGT_ERR_ARG;
+    }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    HGT_CUDA(cudaSetDevice(ctx->device));
+    void *p = nullptr;
+    const size_t n = hgt_em_peer_block_bytes(n_alleles);
+    HGT_CUDA(cudaMalloc(&p, n));  // (own allocation, not the pool: an IPC handle names a whole cudaMalloc block)
+    HGT_CUDA(cudaMemset(p, 0, n));
+    HGT_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t h;
+    HGT_CUDA(cudaIpcGetMemHandle(&h, p));
+    memcpy(handle, &h, 64);
+    *block = p;
+    return HGT_OK;
+}
+extern "C" int hgt_em_peer_open(hgt_ctx *ctx, const unsigned char handle[64], void **block) {
+    if (!ctx || !block || !handle) {
+        hgt_set_error("hgt_em_peer_open: bad argument");
+        return HGT_ERR_ARG;
+    }
+    HGT_CUDA(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    HGT_CUDA(cudaIpcOpenMemHandle(block, h, cudaIpcMemLazyEnablePeerAccess));
+    return HGT_OK;
+}
+extern "C" int hgt_em_peer_close(hgt_ctx *ctx, void *block) {
+    if (!ctx || !block) return HGT_ERR_ARG;
+    HGT_CUDA(cudaSetDevice(ctx->device));
+    HGT_CUDA(cudaIpcCloseMemHandle(block));
+    return HGT_OK;
+}
+extern "C" int hgt_em_peer_free(hgt_ctx *ctx, void *block) {
+    if (!ctx || !block) return HGT_ERR_ARG;
+    HGT_CUDA(cudaSetDevice(ctx->device));
+    HGT_CUDA(cudaFree(block));
+    return HGT_OK;
+}
+
+extern "C" int hgt_em_peer_dev(hgt_ctx *ctx, void *stream, const uint64_t *class_bits, const double *class_count_f64,
+                               const uint64_t *class_count_u64, const int32_t *class_key, int32_t key_offset,
+                               int32_t n_classes, int32_t n_alleles, int32_t wp, const double *allele_len, int32_t remove_low,
+                               int32_t rank, int32_t world, void *const *blocks, double *prob, uint8_t *in_result,
+                               int32_t *first_class, int32_t *iters_status, void *workspace) {
+    if (!ctx || !blocks || !prob || !in_result || !first_class || !iters_status || !workspace || world < 1 ||
+        world > EM_PEER_MAX || rank < 0 || rank >= world || n_classes < 0 ||
+        (n_classes > 0 && (!class_bits || (!class_count_f64 && !class_count_u64)))) {
+        hgt_set_error("hgt_em_peer_dev: bad argument (at most %d ranks)", EM_PEER_MAX);
+        return HGT_ERR_ARG;
+    }
+    if (wp != hgt_row_pitch(n_alleles) || n_alleles < 1) {
+        hgt_set_error("hgt_em_peer_dev: need n_alleles >= 1 and wp == hgt_row_pitch(n_alleles)");
+        return HGT_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int G = ctx->sm_count;  // all SMs even for a handful of rows; the SAME grid on every rank (slices pair up by CTA)
+    if (G > EM_PEER_G) {
+        hgt_set_error("hgt_em_peer_dev: more than %d SMs", EM_PEER_G);
+        return HGT_ERR_UNSUPPORTED;
+    }
+    EmPlan plan;
+    HGT_CHECK(em_plan(ctx, std::max(1, (n_classes + G - 1) / G), n_alleles, wp, &plan));
+    EmWs w = em_ws_carve(workspace, ctx->sm_count, n_alleles);
+    EmArgs a;
+    memset(&a, 0, sizeof(a));
+    a.bits = class_bits; a.cnt = class_count_f64; a.len = allele_len;
+    a.cnt_u64 = reinterpret_cast<const unsigned long long *>(class_count_u64);
+    a.class_first = class_key; a.key_offset = key_offset;
+    a.C = n_classes; a.A = n_alleles; a.wp = wp; a.remove_low = remove_low; a.fixed_iters = 0;
+    a.prob = prob; a.in_result = in_result; a.first_class = first_class; a.iters_status = iters_status;
+    a.vec = w.vec; a.live = w.live; a.part_acc = w.part_acc; a.part_aux = w.part_aux;
+    a.red_acc = w.red_acc; a.red_aux = w.red_aux;
+    em_set_scratch(&a, w.scratch);
+    a.compact = 0; a.A_live_max = n_alleles; a.slab_bytes = 0; a.slab_rows = plan.slab_rows;
+    // EmArgs at d_args, EmPeer right behind it (the 256-byte args slot of the workspace holds both)
+    static_assert(sizeof(EmArgs) + sizeof(EmPeer) <= 512, "args slot");
+    EmPeer px;
+    memset(&px, 0, sizeof(px));
+    px.rank = rank; px.world = world;
+    for (int r = 0; r < world; r++) {
+        if (!blocks[r]) {
+            hgt_set_error("hgt_em_peer_dev: exchange block of rank %d is null", r);
+            return HGT_ERR_ARG;
+        }
+        px.block[r] = static_cast<unsigned char *>(blocks[r]);
+    }
+    EmPeer *d_px = reinterpret_cast<EmPeer *>(reinterpret_cast<unsigned char *>(w.d_args) + 256);
+    a.peer = d_px;
+    HGT_CUDA(cudaMemcpyAsync(d_px, &px, sizeof(px), cudaMemcpyHostToDevice, st));
+    HGT_CUDA(cudaMemcpyAsync(w.d_args, &a, sizeof(a), cudaMemcpyHostToDevice, st));
     return em_launch<true>(ctx, st, w.d_args, G, plan.na, plan.smem);
 }
 
@@ -1785,7 +1996,7 @@ extern "C" int hgt_em_batch(hgt_ctx *ctx, int32_t n_problems, const uint64_t *cl
         a.cnt = reinterpret_cast<double *>(d + o_cnt) + class_off[i];
         a.len = allele_len ? reinterpret_cast<double *>(d + o_len) + allele_off[i] : nullptr;
         a.C = C; a.A = A; a.wp = wp; a.remove_low = remove_low ? remove_low[i] : 0; a.fixed_iters = 0;
-        a.cnt_u64 = nullptr; a.C_ptr = nullptr; a.class_first = nullptr; a.key_offset = 0;
+        a.cnt_u64 = nullptr; a.C_ptr = nullptr; a.class_first = nullptr; a.key_offset = 0; a.peer = nullptr;
         a.prob = reinterpret_cast<double *>(d + o_prob) + allele_off[i];
         a.in_result = d + o_in + allele_off[i];
         a.first_class = reinterpret_cast<int32_t *>(d + o_fk) + allele_off[i];
@@ -2115,7 +2326,7 @@ int hgt_em_batch_dev(hgt_ctx *ctx, cudaStream_t st, int n_problems, const EmDevP
         const size_t Apad = (size_t)pr[i].wp * 64;
         a.bits = pr[i].bits; a.cnt = nullptr; a.len = pr[i].len;
         a.C = pr[i].C_max; a.A = pr[i].A; a.wp = pr[i].wp; a.remove_low = pr[i].remove_low; a.fixed_iters = 0;
-        a.cnt_u64 = pr[i].cnt; a.C_ptr = pr[i].C_ptr; a.class_first = pr[i].class_first; a.key_offset = 0;
+        a.cnt_u64 = pr[i].cnt; a.C_ptr = pr[i].C_ptr; a.class_first = pr[i].class_first; a.key_offset = 0; a.peer = nullptr;
         a.prob = pr[i].prob; a.in_result = pr[i].in_result; a.first_class = pr[i].first_class;
         a.iters_status = pr[i].iters_status;
         a.part_acc = nullptr; a.part_aux = nullptr; a.red_acc = nullptr; a.red_aux = nullptr;

@@ -1219,6 +1219,38 @@ __global__ void __launch_bounds__(WARPS_PER_CTA * 32)
     }
 }
 
+// Read-sharded locus: adopt the gathered class rows this rank owns (owner = row hash mod world) into a fresh one-region
+// pool; equal rows of different shards merge (counts add, first index = the smallest).  Warp per input row.
+template <int WPL>
+__global__ void __launch_bounds__(WARPS_PER_CTA * 32)
+    class_merge_kernel(int wp, const uint64_t *__restrict__ rows_in, const unsigned long long *__restrict__ count_in,
+                       const int32_t *__restrict__ first_in, int64_t n_in, int rank, int world, ClassPool pool) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t k = warp0; k < n_in; k += nwarps) {
+        uint64_t row[WPL];
+#pragma unroll
+        for (int i = 0; i < WPL; i++) {
+            const int j = lane + 32 * i;
+            row[i] = j < wp ? rows_in[(size_t)k * wp + j] : 0ull;
+        }
+        PoolProbe pp;
+        // (the owner is taken from the tag, not from the slot: the slot depends on the table size)
+        uint64_t hsh = 0;
+#pragma unroll
+        for (int i = 0; i < WPL; i++) {
+            const uint32_t j = (uint32_t)(lane + 32 * i);
+            if ((int)j < wp) hsh += mix64(row[i] ^ (0x9e3779b97f4a7c15ULL * (uint64_t)(j + 1)));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) hsh += __shfl_xor_sync(0xffffffffu, hsh, o);
+        if ((int)(mix64(hsh) % (uint64_t)world) != rank) continue;
+        pool_probe_issue<WPL>(pool, wp, 0, row, lane, pp);
+        pool_probe_resolve<WPL>(pool, wp, 0, pool.ut_base[0], pool.ut_base[1], row, count_in[k], first_in[k], lane, pp);
+    }
+}
+
 // Gene_counts (core:1187-1190) of table (unit, 0): counts[a] = sum of class counts over classes holding a;
 // first[a] = first pair whose class holds a.  grid = (allele tiles, units, class chunks): a CTA folds one chunk of
 // `chunk` classes into the totals with integer atomics (order-independent, so still exact).
@@ -1913,7 +1945,9 @@ static int reads_execute(hgt_batch *b, cudaStream_t st) {
     int stage_bytes = (int)std::min<int64_t>(
         160 << 10, std::max<int64_t>(16 << 10, (rd.text_bytes / std::max<int64_t>(N, 1) * 147 + 1023) / 1024 * 1024 + 1024));
     if (stage_kb_env > 0) stage_bytes = stage_kb_env << 10;
-    static const int walk_stage_off = tune_env("HGT_WALK_STAGE_OFF", 0);
+    // the walk reads its lines straight from global memory: after the three-pass split the TMA-staged image measured
+    // slower for it (5.97 vs 4.69 ms of walk per step); HGT_WALK_STAGE=1 brings it back for A/B runs
+    static const int walk_stage_off = !getenv("HGT_WALK_STAGE") && !getenv("HGT_WALK_STAGE_ON");
     static int stage_attr = 0;
     if (stage_attr < stage_bytes) {
         HGT_CUDA(cudaFuncSetAttribute(hgtk::parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_bytes));
@@ -3288,3 +3322,58 @@ extern "C" int hgt_walk_table(const hgt_walk *w, int32_t table, int64_t *job_off
 }
 
 extern "C" void hgt_walk_free(hgt_walk *w) { delete w; }
+
+// ================================================================================================================
+// Read-sharded locus: merge of the ranks' class tables (include/hgt.h)
+// ================================================================================================================
+static inline uint32_t merge_cap(int64_t n_in) {
+    uint32_t cap = 64;
+    while ((int64_t)cap < 2 * std::max<int64_t>(n_in, 1)) cap <<= 1;
+    return cap;
+}
+extern "C" size_t hgt_class_merge_workspace_bytes(int64_t n_in) { return (size_t)merge_cap(n_in) * 8 + 256; }
+
+extern "C" int hgt_class_merge_dev(hgt_ctx *ctx, void *stream, const uint64_t *rows_in, const uint64_t *count_in,
+                                   const int32_t *first_in, int64_t n_in, int32_t n_alleles, int32_t wp, int32_t rank,
+                                   int32_t world, uint64_t *rows_out, uint64_t *count_out, int32_t *first_out, int32_t *n_out,
+                                   void *workspace) {
+    if (!ctx || n_in < 0 || world < 1 || rank < 0 || rank >= world || !n_out || !workspace ||
+        (n_in > 0 && (!rows_in || !count_in || !first_in || !rows_out || !count_out || !first_out))) {
+        hgt_set_error("hgt_class_merge_dev: bad argument");
+        return HGT_ERR_ARG;
+    }
+    if (wp != hgt_row_pitch(n_alleles) || n_in > POOL_MAX_ROWS) {
+        hgt_set_error("hgt_class_merge_dev: need wp == hgt_row_pitch(n_alleles) and at most 2^28 rows");
+        return HGT_ERR_ARG;
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // workspace: ut_base[2] (int64) | pad to 256 | keys[cap]
+    unsigned char *w = static_cast<unsigned char *>(workspace);
+    const uint32_t cap = merge_cap(n_in);
+    const int64_t base[2] = {0, n_in};
+    HGT_CUDA(cudaMemcpyAsync(w, base, 16, cudaMemcpyHostToDevice, st));  // (pageable source: copied before the call returns)
+    HGT_CUDA(cudaMemsetAsync(w + 256, 0, (size_t)cap * 8, st));
+    HGT_CUDA(cudaMemsetAsync(n_out, 0, 4, st));
+    if (n_in == 0) return HGT_OK;
+    HGT_CUDA(cudaMemsetAsync(count_out, 0, (size_t)n_in * 8, st));
+    HGT_CUDA(cudaMemsetAsync(first_out, 0x7f, (size_t)n_in * 4, st));
+    ClassPool pool;
+    pool.keys = reinterpret_cast<unsigned long long *>(w + 256);
+    pool.cap_mask = cap - 1;
+    pool.bits = rows_out;
+    pool.count = reinterpret_cast<unsigned long long *>(count_out);
+    pool.first = first_out;
+    pool.ut_base = reinterpret_cast<const int64_t *>(w);
+    pool.ut_ncls = n_out;
+    const int ctas = (int)std::min<int64_t>((n_in + WARPS_PER_CTA - 1) / WARPS_PER_CTA, (int64_t)ctx->sm_count * 8);
+    const unsigned long long *cnt = reinterpret_cast<const unsigned long long *>(count_in);
+    switch (wpl_of(wp)) {
+        case 1: class_merge_kernel<1><<<ctas, WARPS_PER_CTA * 32, 0, st>>>(wp, rows_in, cnt, first_in, n_in, rank, world, pool); break;
+        case 2: class_merge_kernel<2><<<ctas, WARPS_PER_CTA * 32, 0, st>>>(wp, rows_in, cnt, first_in, n_in, rank, world, pool); break;
+        case 4: class_merge_kernel<4><<<ctas, WARPS_PER_CTA * 32, 0, st>>>(wp, rows_in, cnt, first_in, n_in, rank, world, pool); break;
+        default: class_merge_kernel<8><<<ctas, WARPS_PER_CTA * 32, 0, st>>>(wp, rows_in, cnt, first_in, n_in, rank, world, pool); break;
+    }
+    HGT_CUDA(cudaGetLastError());
+    ctx->launches++;
+    return HGT_OK;
+}

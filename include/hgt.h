@@ -38,7 +38,8 @@ typedef enum {
     HGT_ERR_UNSUPPORTED = -5,   /* shape outside what the kernels are built for (message says which) */
     HGT_ERR_PARSE = -6,         /* malformed alignment record (the reference would assert) */
     HGT_ERR_AMBIGUITY = -7,     /* check_amb_uniqueness would exit(1) (validation_check.py:313-341) */
-    HGT_ERR_NOMEM = -8
+    HGT_ERR_NOMEM = -8,
+    HGT_ERR_PEER = -9           /* a rank of a read-sharded locus did not reach an exchange in time (hgt_em_peer_dev) */
 } hgt_status;
 
 const char *hgt_last_error(void);
@@ -142,6 +143,40 @@ int hgt_em_shard_sweep_dev(hgt_ctx *ctx, void *stream, const uint64_t *class_bit
                            int32_t n_alleles, int32_t wp, int32_t mode, int32_t src, void *state, void *workspace);
 int hgt_em_shard_vec_dev(hgt_ctx *ctx, void *stream, int32_t op, int32_t n_alleles, void *state, const double *allele_len,
                          int32_t src, int32_t dst, int32_t iteration, int32_t remove_low);
+
+/* Read-sharded locus, the whole loop as ONE cooperative launch per rank (one process per GPU).  The reference has no
+ * counterpart: it is single_abundance (common:1282-1410) run on class rows that live on several GPUs.  Every rank owns an
+ * exchange block (hgt_em_peer_alloc; its 64-byte CUDA IPC handle is passed to the other ranks by the caller, e.g. with
+ * torch.distributed.all_gather, and mapped there with hgt_em_peer_open).  hgt_em_peer_dev then runs hgt_em_dev's loop on
+ * this rank's rows; after every partial sweep the per-allele sums (8 * n_alleles bytes per rank) are summed over the ranks
+ * in rank order through the peer-mapped blocks (NVLink loads, flags with release / acquire at system scope), so every
+ * rank holds bit-identical vectors, takes the same branches and writes the same prob / in_result / first_class.
+ * blocks[r] = rank r's block as mapped in THIS process (blocks[rank] = the own block).  All ranks must call it with the
+ * same n_alleles, remove_low and allele_len; n_classes may be 0.  class_key + key_offset = global index of the class's
+ * first read pair (dict order of the reference).  iters_status[1] = HGT_ERR_PEER when a rank does not reach an exchange
+ * within 4 s (the kernel gives up instead of hanging the GPU).  `workspace` as for hgt_em_dev. */
+size_t hgt_em_peer_block_bytes(int32_t n_alleles);
+int hgt_em_peer_alloc(hgt_ctx *ctx, int32_t n_alleles, void **block, unsigned char handle[64]);
+int hgt_em_peer_open(hgt_ctx *ctx, const unsigned char handle[64], void **block);
+int hgt_em_peer_close(hgt_ctx *ctx, void *block);
+int hgt_em_peer_free(hgt_ctx *ctx, void *block);
+int hgt_em_peer_dev(hgt_ctx *ctx, void *stream, const uint64_t *class_bits, const double *class_count_f64,
+                    const uint64_t *class_count_u64, const int32_t *class_key, int32_t key_offset, int32_t n_classes,
+                    int32_t n_alleles, int32_t wp, const double *allele_len, int32_t remove_low, int32_t rank, int32_t world,
+                    void *const *blocks, double *prob, uint8_t *in_result, int32_t *first_class,
+                    int32_t *iters_status /* [3]: iters, status, sweeps */, void *workspace);
+
+/* Read-sharded locus: class tables of all ranks -> the rows THIS rank owns, duplicates merged (Gene_cmpt[key] += count
+ * of core:1171-1236 across shards; first = smallest first-pair index).  A class belongs to rank (hash of its row) mod
+ * world, so after the call the ranks hold disjoint row sets whose union is the Gene_cmpt of all reads - the EM then costs
+ * 1 / world of the rows per rank instead of nearly all of them on every rank.  rows_in[n_in][wp], count_in[n_in],
+ * first_in[n_in] (global pair indices): the gathered tables (e.g. torch.distributed.all_gather of every rank's
+ * hgt_batch_unit_table_dev).  Output arrays must hold n_in entries; *n_out (device int32) receives the row count.
+ * `workspace`: hgt_class_merge_workspace_bytes(n_in).  Device pointers, no synchronisation. */
+size_t hgt_class_merge_workspace_bytes(int64_t n_in);
+int hgt_class_merge_dev(hgt_ctx *ctx, void *stream, const uint64_t *rows_in, const uint64_t *count_in, const int32_t *first_in,
+                        int64_t n_in, int32_t n_alleles, int32_t wp, int32_t rank, int32_t world, uint64_t *rows_out,
+                        uint64_t *count_out, int32_t *first_out, int32_t *n_out, void *workspace);
 
 /* ---- stage (b'): diploid allele-pair model ---------------------------------------------------------------
  * Replaces joint_abundance(HLA_cmpt, HLA_length) of the reference's legacy typer

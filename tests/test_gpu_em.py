@@ -211,3 +211,75 @@ def test_em_identical_columns_tie_exactly(A, C, use_len):
             first = prob
         else:
             np.testing.assert_allclose(prob, first, rtol=1e-6, atol=1e-12)  # the row order only moves the last bits (tiny values: SQUAREM cancellation)
+
+
+@pytest.mark.parametrize("A,C,remove_low,use_len", [(700, 300, True, False), (8192, 6000, True, False), (3000, 900, False, True)])
+def test_peer_kernel_single_rank_equals_hgt_em(A, C, remove_low, use_len):
+    """hgt_em_peer_dev with a world of ONE rank: the exchange step only reads the rank's own block, so the result must
+    equal hgt_em (same loop, same sums) - iterations, keys, order and values.  The two-rank case needs two GPUs
+    (tests/test_gpu_multi.py)."""
+    import torch
+    from hisatgenotype_b200 import _lib, em_dist
+    from hisatgenotype_b200.typing_common import _index_alleles, em_arrays, rank_result
+    rng = np.random.default_rng(A + C)
+    cmpt, lengths = random_problem(rng, A, C, 30)
+    keys = list(cmpt)
+    names, index = _index_alleles(keys)
+    n = len(names)
+    wp = _lib.row_pitch(n)
+    bits = _lib.pack_bits([[index[a] for a in k.split("-")] for k in keys], n)
+    cnt = np.asarray([cmpt[k] for k in keys], np.int64)
+    ln = [lengths[x] for x in names] if use_len else None
+    prob, inres, fk, iters = em_arrays(bits, cnt, n, ln, remove_low)
+    dev = torch.device("cuda", _lib.default_device())
+    d_bits = torch.from_numpy(bits.view(np.int64).reshape(-1)).to(dev)
+    d_cnt = torch.from_numpy(cnt).to(dev)
+    for rep in range(2):  # the second call continues the block's sequence numbers
+        p2, l2, f2, it2 = em_dist.single_abundance_peer(n, wp, d_bits.data_ptr(), d_cnt.data_ptr(), None, 0, len(keys), dev.index,
+                                                        ln, remove_low)
+        assert it2 == iters
+        got = rank_result(names, p2.cpu().numpy(), l2.cpu().numpy().astype(np.uint8), f2.cpu().numpy())
+        want = rank_result(names, prob, inres, fk)
+        assert [a for a, _ in got] == [a for a, _ in want]
+        for (_, x), (_, y) in zip(got, want):
+            assert x == pytest.approx(y, rel=1e-9, abs=1e-15)
+
+
+@pytest.mark.parametrize("A,world", [(300, 2), (7000, 3)])
+def test_class_merge_partitions_and_merges(A, world):
+    """hgt_class_merge_dev for every rank of a world on the same gathered rows (duplicates inside and across the
+    'shards'): the ranks' outputs are disjoint, their union is the merged table (counts added, smallest first index)."""
+    import torch
+    from hisatgenotype_b200 import _lib, em_dist
+    rng = np.random.default_rng(A)
+    wp = _lib.row_pitch(A)
+    distinct = 500
+    base = np.zeros((distinct, wp), np.uint64)
+    for r in range(distinct):
+        mem = rng.choice(A, size=int(rng.integers(1, 60)), replace=False)
+        for a in mem:
+            base[r, a >> 6] |= np.uint64(1) << np.uint64(a & 63)
+    pick = rng.integers(0, distinct, size=1800)
+    rows = base[pick]
+    cnt = rng.integers(1, 50, size=pick.size).astype(np.int64)
+    first = rng.permutation(pick.size).astype(np.int32)
+    want = {}
+    for k in range(pick.size):
+        key = rows[k].tobytes()
+        c, f = want.get(key, (0, 1 << 30))
+        want[key] = (c + int(cnt[k]), min(f, int(first[k])))
+    dev = torch.device("cuda", _lib.default_device())
+    g_bits = torch.from_numpy(rows.view(np.int64).reshape(-1)).to(dev)
+    g_cnt = torch.from_numpy(cnt).to(dev)
+    g_first = torch.from_numpy(first).to(dev)
+    got = {}
+    for rank in range(world):
+        o_bits, o_cnt, o_first, m = em_dist.merge_rows(g_bits, g_cnt, g_first, pick.size, A, wp, rank, world, dev.index)
+        ob = o_bits.cpu().numpy().view(np.uint64).reshape(-1, wp)[:m]
+        oc, of = o_cnt.cpu().numpy()[:m], o_first.cpu().numpy()[:m]
+        assert m > 0
+        for k in range(m):
+            key = ob[k].tobytes()
+            assert key not in got
+            got[key] = (int(oc[k]), int(of[k]))
+    assert got == want
