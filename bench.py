@@ -1014,6 +1014,8 @@ def main():
             "roofline": {"bound": "hbm", "achieved": em_achieved, "peak": peak, "unit": "GB/s",
                          "frac": em_achieved / peak if em_achieved else None,
                          "traffic": ncu_traffic("em_kernel", "six-loci", S),
+                         # the problems live in shared memory: distance to the on-chip ceilings from the same ncu capture
+                         "on_chip": ncu_traffic("em_kernel", "six-loci", S, per="on_chip"),
                          "kernel": "em_kernel (batched, one CTA per (sample, locus) problem)", "peak_source": peak_src,
                          "algorithmic_bytes_rule": "per problem and iteration min(bit matrix, CSR), SURVEY.md 8d",
                          "algorithmic_bytes_per_step_bit_matrix": float(em_bytes_bitset),
@@ -1025,7 +1027,7 @@ def main():
                                  "frac": achieved / peak if achieved else None,
                                  "traffic": ncu_traffic("stage_a", "six-loci", S, per="step"),
                                  "traffic_is": "DRAM bytes of all stage (a) launches of one step (like the algorithmic figure)",
-                                 "kernel": "stage (a): compat_kernel + class_kernel, one launch each per locus",
+                                 "kernel": "set stage: compat_kernel + class_kernel (+ class_sort_kernel), one launch each per locus",
                                  "algorithmic_bytes_per_step": a_bytes, "kernel_ms_per_step": a_ms,
                                  "share_of_step": a_ms / ms_per_step if ms_per_step else None},
             # the record stage (line index, parse, pileup, mate de-dup, walk, ambiguity passes, pair jobs) has to read the
@@ -1076,6 +1078,8 @@ def ncu_traffic(kernel, workload, samples, per="launch"):
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
             t = json.load(f)
         e = t["%s:%s:%d" % (workload, kernel, samples)]
+        if per == "on_chip":
+            return e.get("on_chip")
         if per == "step":
             return e.get("dram_bytes_per_step", e["dram_bytes_per_launch"] * e["launches_captured"])
         return e["dram_bytes_per_launch"]

@@ -51,6 +51,8 @@ def lib():
         L.hgt_em.restype = c_int
         L.hgt_em.argtypes = [c_void_p, c_void_p, c_void_p, c_i32, c_i32, c_i32, c_void_p, c_i32, c_void_p, c_void_p,
                              c_void_p, P(c_i32)]
+        L.hgt_em_f64.restype = c_int
+        L.hgt_em_f64.argtypes = L.hgt_em.argtypes
         L.hgt_em_batch.restype = c_int
         L.hgt_em_batch.argtypes = [c_void_p, c_i32, c_void_p, c_void_p, c_void_p, c_void_p, c_i32, c_void_p, c_void_p,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]

@@ -1893,6 +1893,19 @@ extern "C" int hgt_em_peer_dev(hgt_ctx *ctx, void *stream, const uint64_t *class
 extern "C" int hgt_em(hgt_ctx *ctx, const uint64_t *class_bits, const int64_t *class_count, int32_t n_classes,
                       int32_t n_alleles, int32_t wp, const double *allele_len, int32_t remove_low, double *prob,
                       uint8_t *in_result, int32_t *first_class, int32_t *iters) {
+    if (n_classes > 0 && !class_count) {
+        hgt_set_error("hgt_em: null class_count");
+        return HGT_ERR_ARG;
+    }
+    std::vector<double> cnt((size_t)std::max(n_classes, 0));
+    for (int i = 0; i < n_classes; i++) cnt[i] = (double)class_count[i];
+    return hgt_em_f64(ctx, class_bits, cnt.data(), n_classes, n_alleles, wp, allele_len, remove_low, prob, in_result, first_class,
+                      iters);
+}
+
+extern "C" int hgt_em_f64(hgt_ctx *ctx, const uint64_t *class_bits, const double *class_count, int32_t n_classes,
+                          int32_t n_alleles, int32_t wp, const double *allele_len, int32_t remove_low, double *prob,
+                          uint8_t *in_result, int32_t *first_class, int32_t *iters) {
     if (!ctx) {
         hgt_set_error("hgt_em: null context");
         return HGT_ERR_ARG;
@@ -1912,8 +1925,7 @@ extern "C" int hgt_em(hgt_ctx *ctx, const uint64_t *class_bits, const int64_t *c
                  o_in = o_prob + align_up((size_t)n_alleles * 8, 256), o_fk = o_in + align_up(n_alleles, 256),
                  o_is = o_fk + align_up((size_t)n_alleles * 4, 256), o_ws = o_is + 256, total = o_ws + wsb;
     HGT_CUDA(cudaMalloc(&d, total));
-    std::vector<double> cnt(n_classes);
-    for (int i = 0; i < n_classes; i++) cnt[i] = (double)class_count[i];
+    const double *cnt_h = class_count;
     int rc = HGT_OK;
     int32_t is[3] = {0, 0, 0};
     do {
@@ -1927,7 +1939,7 @@ extern "C" int hgt_em(hgt_ctx *ctx, const uint64_t *class_bits, const int64_t *c
         }                                                                                         \
     }
         TRY(cudaMemcpyAsync(d + o_bits, class_bits, nb, cudaMemcpyHostToDevice, st));
-        TRY(cudaMemcpyAsync(d + o_cnt, cnt.data(), (size_t)n_classes * 8, cudaMemcpyHostToDevice, st));
+        TRY(cudaMemcpyAsync(d + o_cnt, cnt_h, (size_t)n_classes * 8, cudaMemcpyHostToDevice, st));
         if (allele_len) TRY(cudaMemcpyAsync(d + o_len, allele_len, (size_t)n_alleles * 8, cudaMemcpyHostToDevice, st));
         rc = hgt_em_dev(ctx, st, reinterpret_cast<uint64_t *>(d + o_bits), reinterpret_cast<double *>(d + o_cnt),
                         n_classes, n_alleles, wp, allele_len ? reinterpret_cast<double *>(d + o_len) : nullptr,

@@ -29,13 +29,13 @@ def em_arrays(class_bits, class_count, n_alleles, allele_len=None, remove_low=Fa
     wp = _lib.row_pitch(n_alleles)
     bits = np.ascontiguousarray(class_bits, np.uint64)
     assert bits.shape == (C, wp)
-    cnt = np.ascontiguousarray(class_count, np.int64)
+    cnt = np.ascontiguousarray(class_count, np.float64)  # the reference does float(count): fractional counts are legal
     ln = None if allele_len is None else np.ascontiguousarray(allele_len, np.float64)
     prob = np.zeros(n_alleles, np.float64)
     inres = np.zeros(n_alleles, np.uint8)
     fk = np.zeros(n_alleles, np.int32)
     iters = ctypes.c_int32(0)
-    rc = L.hgt_em(_lib.ctx(device), _lib.ptr(bits), _lib.ptr(cnt), C, n_alleles, wp, _lib.ptr(ln),
+    rc = L.hgt_em_f64(_lib.ctx(device), _lib.ptr(bits), _lib.ptr(cnt), C, n_alleles, wp, _lib.ptr(ln),
                   1 if remove_low else 0, _lib.ptr(prob), _lib.ptr(inres), _lib.ptr(fk), ctypes.byref(iters))
     if rc == _lib.HGT_ERR_KEY:
         raise KeyError(_lib.last_error())
@@ -45,12 +45,14 @@ def em_arrays(class_bits, class_count, n_alleles, allele_len=None, remove_low=Fa
     return prob, inres, fk, iters.value
 
 
-def rank_result(names, prob, in_result, first_class, max_n=None):
+def rank_result(names, prob, in_result, first_class, max_n=None, key_pos=None):
     """[[allele, prob], ...] sorted like `sorted(..., key=prob, reverse=True)` on the reference's dict:
-    ties keep dict insertion order = (first class that touched the allele, position inside its key)."""
+    ties keep dict insertion order = (first class that touched the allele, position inside its key).  key_pos[a] = that
+    position when the keys are not name-sorted (default: the sorted-name index, which is the position for sorted keys)."""
     idx = np.nonzero(in_result)[0]
     prob = np.asarray(prob, np.float64)
-    order = idx[np.lexsort((idx, np.asarray(first_class)[idx].astype(np.int64), -prob[idx]))]  # last key is the primary one
+    third = idx if key_pos is None else np.asarray(key_pos)[idx]
+    order = idx[np.lexsort((third, np.asarray(first_class)[idx].astype(np.int64), -prob[idx]))]  # last key is the primary one
     if max_n is not None:
         order = order[:max_n]
     return [[names[i], float(prob[i])] for i in order.tolist()]
@@ -63,14 +65,19 @@ def single_abundance(Gene_cmpt, remove_low_abundance_allele=False, Gene_length={
     names, index = _index_alleles(keys)
     A = len(names)
     bits = _lib.pack_bits([[index[a] for a in k.split("-")] for k in keys], A)
-    cnt = np.asarray([Gene_cmpt[k] for k in keys], np.int64)
+    cnt = np.asarray([Gene_cmpt[k] for k in keys], np.float64)
     ln = None
     if len(Gene_length) > 0:
         for a in names:
             assert a in Gene_length
         ln = np.asarray([Gene_length[a] for a in names], np.float64)
     prob, inres, fk, _ = em_arrays(bits, cnt, A, ln, bool(remove_low_abundance_allele))
-    return rank_result(names, prob, inres, fk)
+    # ties: position of the allele inside the key of the first class that holds it (keys need not be name-sorted)
+    key_pos = np.arange(A)
+    for a in np.nonzero(inres)[0].tolist():
+        if 0 <= fk[a] < len(keys):
+            key_pos[a] = keys[fk[a]].split("-").index(names[a])
+    return rank_result(names, prob, inres, fk, key_pos=key_pos)
 
 
 MAX_PAIRS = 1 << 22

@@ -91,6 +91,11 @@ void hgt_host_free(void *p);
 int hgt_em(hgt_ctx *ctx, const uint64_t *class_bits, const int64_t *class_count, int32_t n_classes,
            int32_t n_alleles, int32_t wp, const double *allele_len, int32_t remove_low, double *prob,
            uint8_t *in_result, int32_t *first_class, int32_t *iters);
+/* The same with class counts as doubles: the reference does float(count) (common:1304, 1318), so fractional counts are
+ * legal input of single_abundance. */
+int hgt_em_f64(hgt_ctx *ctx, const uint64_t *class_bits, const double *class_count, int32_t n_classes,
+           int32_t n_alleles, int32_t wp, const double *allele_len, int32_t remove_low, double *prob,
+           uint8_t *in_result, int32_t *first_class, int32_t *iters);
 
 /* Batched form: n_problems independent EM problems in one launch (one CTA per problem).  Problem i uses
  * classes [class_off[i], class_off[i+1]) of the concatenated class arrays and alleles

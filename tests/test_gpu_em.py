@@ -283,3 +283,23 @@ def test_class_merge_partitions_and_merges(A, world):
             assert key not in got
             got[key] = (int(oc[k]), int(of[k]))
     assert got == want
+
+
+def test_single_abundance_fractional_counts_and_unsorted_keys():
+    """The reference does float(count) and breaks exact ties by dict insertion order = position inside the key string of the
+    first class that holds the allele: fractional counts must not be truncated and keys need not be name-sorted."""
+    import em_oracle
+    from hisatgenotype_b200.typing_common import single_abundance
+    rng = np.random.default_rng(77)
+    cmpt, _ = random_problem(rng, 300, 90, 6)
+    cmpt = {k: 0.25 * c + 0.5 for k, c in cmpt.items()}  # truncated to integers this would be a different problem
+    ref, _ = em_oracle.single_abundance(cmpt, True, {})
+    res = single_abundance(cmpt, True, {})
+    _check(res, ref)
+    trunc = single_abundance({k: int(c) for k, c in cmpt.items() if int(c) > 0}, True, {})
+    assert any(abs(p - q) > 1e-4 for (_, p), (_, q) in zip(res, trunc)) or len(res) != len(trunc)
+    tie = {"Z*09-A*01": 3}  # exact tie 0.5 / 0.5: the reference lists Z*09 first (it comes first in the key)
+    ref, _ = em_oracle.single_abundance(tie, False, {})
+    res = single_abundance(tie, False, {})
+    assert [a for a, _ in ref] == ["Z*09", "A*01"]
+    _check(res, ref)
