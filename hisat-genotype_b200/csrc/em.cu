@@ -485,7 +485,9 @@ __device__ __noinline__ void peer_exchange(const EmArgs &a, const EmPeer *px, in
                                            int g) {
     const int tid = threadIdx.x;
     // slice g of this rank <-> slice g of every peer (same grid on every rank): no grid-wide step in between
-    __threadfence_system();  // (by the lanes that wrote the slice)
+    // the slice was written by lane 0 of every warp: those lanes fence at system scope, the CTA barrier orders them before the
+    // release store of the flag (release is cumulative over what happens-before it)
+    if ((tid & 31) == 0) __threadfence_system();
     __syncthreads();
     uint32_t *my_flags = reinterpret_cast<uint32_t *>(px->block[px->rank]);
     int32_t *my_abort = reinterpret_cast<int32_t *>(px->block[px->rank] + EM_PEER_FLAG_BYTES);

@@ -413,13 +413,75 @@ __global__ void __launch_bounds__(STAGE_LINES) walk_kernel(ReadsView R, WalkPara
         if (cand) walk_record<0>(R, P, base, i, -1, M);
     }
 }
+// ---- list passes by position ---------------------------------------------------------------------------------------------------
+// walk_kernel queues records in arrival order; the reads of a unit are name-grouped, i.e. at random positions, so the 32
+// records of a warp of the second / third pass would walk 32 different stretches of the Alts tables - different trip
+// counts (2 of 32 lanes active in those loops) and no sharing of the table lines.  A counting sort by (locus, position / 32)
+// puts neighbours on the backbone into the same warp.  Three small kernels, list length read on the device.
+constexpr int SORT_BUCKETS = 16384;
+__device__ __forceinline__ int list_sort_key(const ReadsView &R, int32_t i) {
+    const int locus = R.unit_locus[R.unit[i]] & 31;
+    int p = R.rec[i].pos >> 5;
+    p = p < 0 ? 0 : (p > 511 ? 511 : p);
+    return (locus << 9) | p;
+}
+__global__ void __launch_bounds__(256) list_hist_kernel(ReadsView R, const int32_t *__restrict__ list, const int32_t *__restrict__ n_ptr,
+                                                        int32_t *__restrict__ hist) {
+    const int n = *n_ptr;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x)
+        atomicAdd(&hist[list_sort_key(R, list[k])], 1);
+}
+__global__ void __launch_bounds__(1024) list_scan_kernel(int32_t *__restrict__ hist) {  // counts -> exclusive offsets, one CTA
+    __shared__ int32_t s_warp[32];
+    constexpr int PER = SORT_BUCKETS / 1024;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    int32_t v[PER], sum = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        v[k] = hist[t * PER + k];
+        sum += v[k];
+    }
+    int32_t x = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int32_t w = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int32_t y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += y;
+        }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    int32_t run = (warp ? s_warp[warp - 1] : 0) + x - sum;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        hist[t * PER + k] = run;
+        run += v[k];
+    }
+}
+__global__ void __launch_bounds__(256) list_scatter_kernel(ReadsView R, const int32_t *__restrict__ list, const int32_t *__restrict__ n_ptr,
+                                                           int32_t *__restrict__ cursor, int32_t *__restrict__ out) {
+    const int n = *n_ptr;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const int32_t i = list[k];
+        out[atomicAdd(&cursor[list_sort_key(R, i)], 1)] = i;
+    }
+}
+
 // second pass: records with an Alts anchor in reach (amb_list, filled by walk_kernel; its length stays on the device)
 __global__ void __launch_bounds__(128) walk_amb_kernel(ReadsView R, WalkParams P) {
     __shared__ __align__(16) EcParams s_ecp[128];
     const int n = *R.n_amb, n_round = (n + 31) & ~31;  // whole warps: the lanes compute the masks together
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_round; k += gridDim.x * blockDim.x) {
         const bool on = k < n;
-        const int64_t i = on ? R.amb_list[k] : 0;
+        const int64_t i = on ? (R.list_sorted ? R.list_sorted[k] : R.amb_list[k]) : 0;
         const EcMask M = warp_ec_masks(R, P, R.text, i, on, s_ecp + (threadIdx.x & ~31));
         if (on) walk_record<1>(R, P, R.text, i, -1, M);
     }
@@ -430,7 +492,7 @@ __global__ void __launch_bounds__(128) walk_slow_kernel(ReadsView R, WalkParams 
     const int n_round = (n_slow + 31) & ~31;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n_round; k += gridDim.x * blockDim.x) {
         const bool on = k < n_slow;
-        const int64_t i = on ? R.slow_list[k] : 0;
+        const int64_t i = on ? (R.list_sorted ? R.list_sorted[k] : R.slow_list[k]) : 0;
         const EcMask M = warp_ec_masks(R, P, R.text, i, on, s_ecp + (threadIdx.x & ~31));
         if (on) walk_record<2>(R, P, R.text, i, k, M);
     }

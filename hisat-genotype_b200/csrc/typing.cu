@@ -1874,6 +1874,7 @@ static hgtd::ReadsView reads_view(hgt_batch *b) {
     R.n_amb = reinterpret_cast<int32_t *>(sm + 16);
     R.n_heads = reinterpret_cast<int32_t *>(sm + 20);
     R.head_list = R.slow_list + std::max<size_t>(N, 1);
+    R.list_sorted = nullptr;
     R.max_job_haps = reinterpret_cast<int32_t *>(sm + 12);
     R.unit_reads = reinterpret_cast<unsigned long long *>(sm + rd.s_reads);
     R.unit_pairs = reinterpret_cast<unsigned long long *>(sm + rd.s_pairs);
@@ -1916,7 +1917,8 @@ static int reads_execute(hgt_batch *b, cudaStream_t st) {
     HGT_CHECK(rd.d_st.alloc((size_t)std::max<int64_t>(N, 1) * 2));
     HGT_CHECK(rd.d_hdr.alloc((size_t)std::max<int64_t>(N, 1) * 16));
     HGT_CHECK(rd.d_hids.alloc((size_t)std::max<int64_t>(N, 1) * hgtd::MAXI * 4));
-    HGT_CHECK(rd.d_slow_list.alloc((size_t)std::max<int64_t>(N, 1) * 12));  // amb_list, slow_list, head_list
+    // amb_list, slow_list, head_list, the sorted copy of the running list pass, bucket counters
+    HGT_CHECK(rd.d_slow_list.alloc((size_t)std::max<int64_t>(N, 1) * 16 + (size_t)hgtk::SORT_BUCKETS * 4));
     HGT_CHECK(rd.d_scan.alloc((size_t)(N + 1) * 8 * 5));
     HGT_CHECK(rd.d_cnt.alloc((size_t)std::max<int64_t>(rd.POS, 1) * 24));
     HGT_CHECK(rd.d_mf.alloc((size_t)std::max<int64_t>(rd.POS, 1) * 2));
@@ -1991,9 +1993,20 @@ static int reads_execute(hgt_batch *b, cudaStream_t st) {
         hgtk::walk_kernel<<<line_grid(ctx, N, 128, 16), hgtk::STAGE_LINES, 0, st>>>(R, P, 0);
     else
         hgtk::walk_kernel<<<stage_grid, hgtk::STAGE_LINES, stage_bytes, st>>>(R, P, stage_bytes);
-    hgtk::walk_amb_kernel<<<line_grid(ctx, N, 128, 16), 128, 0, st>>>(R, P);  // its length is read on the device
+    static const bool list_sort = !getenv("HGT_LIST_SORT_OFF");
+    int32_t *sorted = rd.d_slow_list.as<int32_t>() + 3 * std::max<size_t>(N, 1), *buckets = sorted + std::max<size_t>(N, 1);
     launches = 4;
-    ctx->launches += 4;
+    if (list_sort) {  // second pass in backbone order (its length is read on the device)
+        HGT_CUDA(cudaMemsetAsync(buckets, 0, (size_t)hgtk::SORT_BUCKETS * 4, st));
+        hgtk::list_hist_kernel<<<line_grid(ctx, N / 8 + 1, 256, 4), 256, 0, st>>>(R, R.amb_list, R.n_amb, buckets);
+        hgtk::list_scan_kernel<<<1, 1024, 0, st>>>(buckets);
+        hgtk::list_scatter_kernel<<<line_grid(ctx, N / 8 + 1, 256, 4), 256, 0, st>>>(R, R.amb_list, R.n_amb, buckets, sorted);
+        R.list_sorted = sorted;
+        launches += 3;
+    }
+    hgtk::walk_amb_kernel<<<line_grid(ctx, N, 128, 16), 128, 0, st>>>(R, P);  // its length is read on the device
+    R.list_sorted = nullptr;
+    ctx->launches += launches;
     HGT_CUDA(cudaGetLastError());
     HGT_CUDA(d2h(rd.h_small.p, rd.d_small.p, 16, st));
     HGT_CUDA(cudaStreamSynchronize(st));  // number of records that need the ambiguity pass
@@ -2005,7 +2018,17 @@ static int reads_execute(hgt_batch *b, cudaStream_t st) {
     if (rd.n_slow > 0) {
         HGT_CHECK(rd.d_slow.alloc((size_t)rd.n_slow * sizeof(hgtd::SlowRec)));
         R = reads_view(b);
+        if (list_sort) {
+            HGT_CUDA(cudaMemsetAsync(buckets, 0, (size_t)hgtk::SORT_BUCKETS * 4, st));
+            hgtk::list_hist_kernel<<<line_grid(ctx, rd.n_slow, 256, 4), 256, 0, st>>>(R, R.slow_list, R.n_slow, buckets);
+            hgtk::list_scan_kernel<<<1, 1024, 0, st>>>(buckets);
+            hgtk::list_scatter_kernel<<<line_grid(ctx, rd.n_slow, 256, 4), 256, 0, st>>>(R, R.slow_list, R.n_slow, buckets, sorted);
+            R.list_sorted = sorted;
+            launches += 3;
+            ctx->launches += 3;
+        }
         hgtk::walk_slow_kernel<<<line_grid(ctx, rd.n_slow, 128, 16), 128, 0, st>>>(R, P, rd.n_slow);
+        R.list_sorted = nullptr;
         launches++;
         ctx->launches++;
     }
