@@ -1100,7 +1100,8 @@ def em_trace_once(L, ctx, run):
     out = (ctypes.c_uint64 * 16)()
     L.hgt_em_trace(ctx, 0, out)
     names = ["stage_p", "phase1_sk", "phase2_acc", "coop_reduce", "normalise", "setup", "squarem_diff_prune", "compact64",
-             "kernel_total", "sweeps", "launches", "all_cta_ns_sum", "all_cta_ns_max", "all_ctas", "dedup_signatures", "dedup_table"]
+             "kernel_total", "sweeps", "launches", "all_cta_ns_sum", "all_cta_ns_max", "all_ctas",
+             "dedup_signatures|coop_partials_sync1", "dedup_table|coop_slice_exchange"]
     sys.stderr.write("em_trace " + json.dumps({n: int(out[i]) for i, n in enumerate(names)}) + "\n")
 
 

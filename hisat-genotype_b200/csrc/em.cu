@@ -550,7 +550,7 @@ __device__ void em_sweep(const EmArgs &a, const Smem &sm, int mode, const double
     tr.count(9);
     // ---- cross-CTA reduction (cooperative launch only) ------------------------------------------------------
     if (COOP) {
-        // Partials are laid out [allele][CTA] so that the reducing warp reads one contiguous run per allele.  In the
+        // Partials are laid out [CTA][allele]: coalesced stores, and the reducing warps read whole sectors (below).  In the
         // INIT / NEXT modes the "met by a valid class" flag rides in the sign of zero: a CTA that did not meet the allele
         // contributes -0.0, one that did contributes its sum (>= +0.0), and -0.0 survives an IEEE sum only if every
         // term is -0.0.  FIRSTK exchanges the int32 keys instead of sums.
@@ -560,35 +560,61 @@ __device__ void em_sweep(const EmArgs &a, const Smem &sm, int mode, const double
         for (int i = 0; i < NA; i++) {
             const int al = tid + i * EM_THREADS;
             if (al < A) {
-                if (mode == MODE_FIRSTK) a.part_aux[(size_t)al * G + g] = fk[i];
-                else a.part_acc[(size_t)al * G + g] = ((hit >> i) & 1u) ? acc[i] : -0.0;
+                if (mode == MODE_FIRSTK) a.part_aux[(size_t)g * Apad + al] = fk[i];
+                else a.part_acc[(size_t)g * Apad + al] = ((hit >> i) & 1u) ? acc[i] : -0.0;
             }
         }
         grid.sync();
-        const int Ag = (A + G - 1) / G;
-        const int a_lo = g * Ag, a_hi = min(A, a_lo + Ag);
+        tr.mark(14);  // (cooperative launches: partials written + first grid sync; the batched form uses the slot for the merge)
+        // slices of whole 4-allele groups: a reducing warp takes four alleles at a time, lane = CTA, so that every 32-byte
+        // sector of the partials is written once (coalesced, [CTA][allele]) and read once
+        const int Ag = (((A + G - 1) / G) + 3) & ~3;
+        const int a_lo = min(A, g * Ag), a_hi = min(A, a_lo + Ag);
         // (read-sharded locus: the slice goes to this rank's exchange block first, see EmPeer)
         const EmPeer *px = a.peer;
         const uint32_t q = xseq + 1;
         double *x_acc = px ? reinterpret_cast<double *>(px->block[px->rank] + EM_PEER_HDR) + (size_t)(q & 1u) * Apad : a.red_acc;
         int32_t *x_aux = px ? reinterpret_cast<int32_t *>(x_acc) : a.red_aux;
-        for (int al = a_lo + warp; al < a_hi; al += EM_WARPS) {
+        for (int al = a_lo + 4 * warp; al < a_hi; al += 4 * EM_WARPS) {
             if (mode == MODE_FIRSTK) {
-                int32_t x = FK_NONE;
-                for (int gg = lane; gg < G; gg += 32) x = min(x, __ldcg(&a.part_aux[(size_t)al * G + gg]));
-                for (int o = 16; o > 0; o >>= 1) x = min(x, __shfl_xor_sync(0xffffffffu, x, o));
-                if (lane == 0) x_aux[al] = x;
+                int32_t x0 = FK_NONE, x1 = FK_NONE, x2 = FK_NONE, x3 = FK_NONE;
+                for (int gg = lane; gg < G; gg += 32) {
+                    const int4 v = __ldcg(reinterpret_cast<const int4 *>(a.part_aux + (size_t)gg * Apad + al));
+                    x0 = min(x0, v.x); x1 = min(x1, v.y); x2 = min(x2, v.z); x3 = min(x3, v.w);
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    x0 = min(x0, __shfl_xor_sync(0xffffffffu, x0, o));
+                    x1 = min(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+                    x2 = min(x2, __shfl_xor_sync(0xffffffffu, x2, o));
+                    x3 = min(x3, __shfl_xor_sync(0xffffffffu, x3, o));
+                }
+                if (lane == 0) {
+                    x_aux[al] = x0;
+                    if (al + 1 < a_hi) x_aux[al + 1] = x1;
+                    if (al + 2 < a_hi) x_aux[al + 2] = x2;
+                    if (al + 3 < a_hi) x_aux[al + 3] = x3;
+                }
             } else {
-                double s = -0.0;
-                for (int gg = lane; gg < G; gg += 32) s += __ldcg(&a.part_acc[(size_t)al * G + gg]);
-                s = warp_sum(s);
-                if (lane == 0) x_acc[al] = s;
+                double s0 = -0.0, s1 = -0.0, s2 = -0.0, s3 = -0.0;
+                for (int gg = lane; gg < G; gg += 32) {
+                    const double2 *src = reinterpret_cast<const double2 *>(a.part_acc + (size_t)gg * Apad + al);
+                    const double2 u = __ldcg(src), v = __ldcg(src + 1);
+                    s0 += u.x; s1 += u.y; s2 += v.x; s3 += v.y;
+                }
+                s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+                if (lane == 0) {
+                    x_acc[al] = s0;
+                    if (al + 1 < a_hi) x_acc[al + 1] = s1;
+                    if (al + 2 < a_hi) x_acc[al + 2] = s2;
+                    if (al + 3 < a_hi) x_acc[al + 3] = s3;
+                }
             }
         }
         if (px) {
             xseq = q;
             peer_exchange(a, px, mode, q, a_lo, a_hi, Apad, g);
         }
+        tr.mark(15);  // (cooperative launches: slice reduction + exchange)
         grid.sync();
         if (px && *reinterpret_cast<volatile int32_t *>(px->block[px->rank] + EM_PEER_FLAG_BYTES)) {
             if (tid == 0) *status = HGT_ERR_PEER;  // (every CTA reads the same word after the grid sync)
