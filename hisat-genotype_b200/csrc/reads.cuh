@@ -499,11 +499,11 @@ __global__ void __launch_bounds__(128) walk_slow_kernel(ReadsView R, WalkParams 
 }
 __global__ void __launch_bounds__(128) pair_count_kernel(ReadsView R) {  // thread per run (head_list)
     const int n = *R.n_heads;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) pair_jobs<false>(R, R.head_list[k]);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) pair_jobs<false>(R, R.head_list[k], k);
 }
 __global__ void __launch_bounds__(128) pair_fill_kernel(ReadsView R) {
     const int n = *R.n_heads;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) pair_jobs<true>(R, R.head_list[k]);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) pair_jobs<true>(R, R.head_list[k], k);
 }
 
 // per-locus totals of the pair stage from the scanned arrays: out[l][6] = pairs, haplotypes, rows, small jobs, big jobs,

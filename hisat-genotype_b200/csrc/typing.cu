@@ -1875,6 +1875,7 @@ static hgtd::ReadsView reads_view(hgt_batch *b) {
     R.n_heads = reinterpret_cast<int32_t *>(sm + 20);
     R.head_list = R.slow_list + std::max<size_t>(N, 1);
     R.list_sorted = nullptr;
+    R.pair_cnt = R.amb_list + 4 * std::max<size_t>(N, 1) + hgtk::SORT_BUCKETS;
     R.max_job_haps = reinterpret_cast<int32_t *>(sm + 12);
     R.unit_reads = reinterpret_cast<unsigned long long *>(sm + rd.s_reads);
     R.unit_pairs = reinterpret_cast<unsigned long long *>(sm + rd.s_pairs);
@@ -1918,7 +1919,8 @@ static int reads_execute(hgt_batch *b, cudaStream_t st) {
     HGT_CHECK(rd.d_hdr.alloc((size_t)std::max<int64_t>(N, 1) * 16));
     HGT_CHECK(rd.d_hids.alloc((size_t)std::max<int64_t>(N, 1) * hgtd::MAXI * 4));
     // amb_list, slow_list, head_list, the sorted copy of the running list pass, bucket counters
-    HGT_CHECK(rd.d_slow_list.alloc((size_t)std::max<int64_t>(N, 1) * 16 + (size_t)hgtk::SORT_BUCKETS * 4));
+    // (+ the per-run table totals the count pass leaves for the fill pass)
+    HGT_CHECK(rd.d_slow_list.alloc((size_t)std::max<int64_t>(N, 1) * 28 + (size_t)hgtk::SORT_BUCKETS * 4));
     HGT_CHECK(rd.d_scan.alloc((size_t)(N + 1) * 8 * 5));
     HGT_CHECK(rd.d_cnt.alloc((size_t)std::max<int64_t>(rd.POS, 1) * 24));
     HGT_CHECK(rd.d_mf.alloc((size_t)std::max<int64_t>(rd.POS, 1) * 2));
@@ -3230,6 +3232,8 @@ extern "C" int hgt_host_walk(hgt_locus *loc, const char *sam, size_t n_bytes, co
     R.h_left = hdr.data(); R.h_right = R.h_left + n1; R.h_n = R.h_right + n1; R.slow_slot = R.h_n + n1;
     R.h_ids = hids.data(); R.slow_list = slow_list.data(); R.n_slow = &n_slow;
     R.amb_list = amb_list.data(); R.n_amb = &n_amb;
+    std::vector<int32_t> pair_cnt((size_t)n1 * 3);
+    R.pair_cnt = pair_cnt.data();
     R.head_list = head_list.data(); R.n_heads = &n_heads;
     R.n_units = 1; R.unit_off = unit_off; R.unit_line0 = unit_line0; R.unit_locus = unit_locus; R.unit_local = unit_local;
     R.unit_pos0 = unit_pos0; R.nt_mask = nt_mask; R.del_flag = flag.data(); R.loci = &loc->wt_host;
@@ -3276,7 +3280,7 @@ extern "C" int hgt_host_walk(hgt_locus *loc, const char *sam, size_t n_bytes, co
     R.slow = slow.data();
     for (int k = 0; k < n_slow; k++)
         walk_record<2>(R, P, R.text, slow_list[k], k, use_mask ? record_ec_mask(R, P, R.text, slow_list[k]) : no_mask);
-    for (int k = 0; k < n_heads; k++) pair_jobs<false>(R, head_list[k]);
+    for (int k = 0; k < n_heads; k++) pair_jobs<false>(R, head_list[k], k);
     if (err != ~0ull) return fail();
     for (int k = 0; k < 5; k++) {
         int64_t *a = scan.data() + (size_t)k * (N + 1), run = 0;
@@ -3296,7 +3300,7 @@ extern "C" int hgt_host_walk(hgt_locus *loc, const char *sam, size_t n_bytes, co
     jobs.job_off = job_off.data(); jobs.row_off = row_off.data(); jobs.job_ut = job_ut.data(); jobs.job_pair = job_pair.data();
     jobs.job_list = job_list.data(); jobs.hap_left = hl.data(); jobs.hap_right = hr.data(); jobs.hap_table = htb.data();
     jobs.rows = rows.data(); jobs.line0 = 0; jobs.n_small = R.s_small[N]; jobs.n_tables = T;
-    for (int k = 0; k < n_heads; k++) pair_jobs<true>(R, head_list[k]);
+    for (int k = 0; k < n_heads; k++) pair_jobs<true>(R, head_list[k], k);
     if (err != ~0ull) return fail();
     hgt_walk *w = new hgt_walk();
     w->num_reads = (int64_t)unit_reads[0];

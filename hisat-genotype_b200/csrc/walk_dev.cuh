@@ -204,6 +204,7 @@ struct ReadsView {
     unsigned long long *unit_reads, *unit_pairs;
     // pair stage: per-line counts (non-zero at run heads), exclusive scans in place
     int64_t *s_pairs, *s_haps, *s_rows, *s_small, *s_big;  // [n_lines+1]
+    int32_t *pair_cnt;  // [n_heads][3]: per run and table, haplotypes | rows << 8 (count pass -> fill pass)
     int32_t *max_job_haps;
     LocusJobs *jobs;           // [n_loci]
 };
@@ -1506,7 +1507,7 @@ HGT_HDN int hap_rows(const VarTab &V, const Hap &h, int lo, int hi, int32_t *row
 // table of the pair keeps its own contiguous range of the job arrays (job_off), so the fill pass first repeats the
 // counting (cheap: one or two haplotypes in the common run) to place its three cursors, then writes.
 template <bool FILL>
-HGT_HD void pair_jobs(const ReadsView &R, int64_t i) {
+HGT_HD void pair_jobs(const ReadsView &R, int64_t i, int64_t head_k) {
     if (!(R.st[i] & ST_HEAD)) return;  // (the s_* arrays are zeroed before the count pass)
     const int u = R.unit[i];
     const int locus = R.unit_locus[u];
@@ -1539,96 +1540,100 @@ HGT_HD void pair_jobs(const ReadsView &R, int64_t i) {
     int64_t pair_in_locus = 0;
     Hap h, other;
     int32_t rows[MAXHID];
-    // pass 0 (both modes): per-table totals of the run; pass 1 (FILL only): the writes
-    for (int pass = 0; pass < (FILL ? 2 : 1); pass++) {
-        const bool write = FILL && pass == 1;
-        int64_t kt_run[3] = {0, 0, 0};
-        int flat = 0;  // index of the haplotype over all records of the run
-        for (int r = 0; r < nrec; r++) {
-            const int cnt = haps_of(R, recs[r]);
-            for (int g = 0; g < cnt; g++, flat++) {
-                if (!hap_load(R, recs[r], g, h)) {
-                    set_error(R, i, E_CAP_IDS);
-                    return;
-                }
-                // an earlier equal haplotype of the run makes this one a duplicate (set union)
-                bool dup = false;
-                if (total > 1) {
-                    int f2 = 0;
-                    for (int r2 = 0; r2 <= r && !dup; r2++) {
-                        const int cnt2 = haps_of(R, recs[r2]);
-                        for (int g2 = 0; g2 < cnt2 && f2 < flat && !dup; g2++, f2++)
-                            dup = hap_load(R, recs[r2], g2, other) && hap_equal(other, h);
-                    }
-                }
-                if (dup) continue;
-                for (int tb = 0; tb < T; tb++) {
-                    const int ne = tb == 0 ? 1 : (tb == 2 ? L.n_pexons : L.n_exons);
-                    const int32_t *ex = tb == 2 ? L.pexons : L.exons;
-                    for (int x = 0; x < ne; x++) {
-                        int32_t l2 = h.left, r2 = h.right;
-                        int lo = 0, hi = h.n;
-                        if (tb > 0 && !exon_clip(V, h, ex[2 * x], ex[2 * x + 1], &l2, &r2, &lo, &hi)) continue;
-                        const int m = hap_rows(V, h, lo, hi, rows);
-                        if (write) {
-                            const LocusJobs &J = R.jobs[locus];
-                            const int64_t hp = hap_cur[tb]++;
-                            J.hap_left[hp] = l2;
-                            J.hap_right[hp] = r2;
-                            J.hap_table[hp] = tb;
-                            for (int k = 0; k < m; k++) J.rows[row_cur[tb] + k] = rows[k];
-                            row_cur[tb] += m;
-                            J.row_off[hp + 1] = row_cur[tb];
-                        } else {
-                            kt_run[tb]++;
-                            rt[tb] += m;
-                        }
-                    }
-                }
-            }
+    // Count pass: per-table totals of the run, kept in pair_cnt (haplotypes | rows << 8 per table).  Fill pass: cursors from
+    // those totals, then ONE walk over the haplotypes that writes (it used to repeat the counting walk first).
+    if (FILL) {
+        for (int tb = 0; tb < 3; tb++) {
+            const int32_t c = R.pair_cnt[head_k * 3 + tb];
+            kt[tb] = c & 255;
+            rt[tb] = c >> 8;
         }
-        if (pass == 0) {
-            for (int tb = 0; tb < 3; tb++) kt[tb] = kt_run[tb];
-            int n_small = 0;
-            int64_t kmax = 0;
-            for (int tb = 0; tb < T; tb++) {
-                if (kt[tb] > MAX_PAIR_HTS) {
-                    set_error(R, i, E_PAIR_HTS);
-                    return;
-                }
-                n_small += kt[tb] <= 7;
-                kmax = kt[tb] > kmax ? kt[tb] : kmax;
-            }
-            if (!FILL) {
-                R.s_pairs[i] = 1;
-                R.s_haps[i] = kt[0] + kt[1] + kt[2];
-                R.s_rows[i] = rt[0] + rt[1] + rt[2];
-                R.s_small[i] = n_small;
-                R.s_big[i] = T - n_small;
-                hd_add_u64(&R.unit_pairs[u], 1ull);
-                hd_max_i32(R.max_job_haps, (int32_t)kmax);
+        // job headers and the three cursors (tables of a pair are laid out one after the other)
+        const LocusJobs &J = R.jobs[locus];
+        const int64_t l0 = J.line0;
+        pair_in_locus = R.s_pairs[i] - R.s_pairs[l0];
+        const int64_t pair_in_unit = R.s_pairs[i] - R.s_pairs[R.unit_line0[u]];
+        int64_t hap = R.s_haps[i] - R.s_haps[l0], row = R.s_rows[i] - R.s_rows[l0];
+        int64_t small = R.s_small[i] - R.s_small[l0], big = J.n_small + (R.s_big[i] - R.s_big[l0]);
+        for (int tb = 0; tb < T; tb++) {
+            const int64_t job = pair_in_locus * T + tb;
+            J.job_ut[job] = R.unit_local[u] * 4 + tb;
+            J.job_pair[job] = (int32_t)pair_in_unit;
+            if (kt[tb] <= 7) J.job_list[small++] = (int32_t)job;
+            else J.job_list[big++] = (int32_t)job;
+            hap_cur[tb] = hap;
+            row_cur[tb] = row;
+            hap += kt[tb];
+            row += rt[tb];
+            J.job_off[job + 1] = hap;
+        }
+    }
+    const bool write = FILL;
+    int64_t kt_run[3] = {0, 0, 0};
+    int flat = 0;  // index of the haplotype over all records of the run
+    for (int r = 0; r < nrec; r++) {
+        const int cnt = haps_of(R, recs[r]);
+        for (int g = 0; g < cnt; g++, flat++) {
+            if (!hap_load(R, recs[r], g, h)) {
+                set_error(R, i, E_CAP_IDS);
                 return;
             }
-            // fill: job headers and the three cursors (tables of a pair are laid out one after the other)
-            const LocusJobs &J = R.jobs[locus];
-            const int64_t l0 = J.line0;
-            pair_in_locus = R.s_pairs[i] - R.s_pairs[l0];
-            const int64_t pair_in_unit = R.s_pairs[i] - R.s_pairs[R.unit_line0[u]];
-            int64_t hap = R.s_haps[i] - R.s_haps[l0], row = R.s_rows[i] - R.s_rows[l0];
-            int64_t small = R.s_small[i] - R.s_small[l0], big = J.n_small + (R.s_big[i] - R.s_big[l0]);
+            // an earlier equal haplotype of the run makes this one a duplicate (set union)
+            bool dup = false;
+            if (total > 1) {
+                int f2 = 0;
+                for (int r2 = 0; r2 <= r && !dup; r2++) {
+                    const int cnt2 = haps_of(R, recs[r2]);
+                    for (int g2 = 0; g2 < cnt2 && f2 < flat && !dup; g2++, f2++)
+                        dup = hap_load(R, recs[r2], g2, other) && hap_equal(other, h);
+                }
+            }
+            if (dup) continue;
             for (int tb = 0; tb < T; tb++) {
-                const int64_t job = pair_in_locus * T + tb;
-                J.job_ut[job] = R.unit_local[u] * 4 + tb;
-                J.job_pair[job] = (int32_t)pair_in_unit;
-                if (kt[tb] <= 7) J.job_list[small++] = (int32_t)job;
-                else J.job_list[big++] = (int32_t)job;
-                hap_cur[tb] = hap;
-                row_cur[tb] = row;
-                hap += kt[tb];
-                row += rt[tb];
-                J.job_off[job + 1] = hap;
+                const int ne = tb == 0 ? 1 : (tb == 2 ? L.n_pexons : L.n_exons);
+                const int32_t *ex = tb == 2 ? L.pexons : L.exons;
+                for (int x = 0; x < ne; x++) {
+                    int32_t l2 = h.left, r2 = h.right;
+                    int lo = 0, hi = h.n;
+                    if (tb > 0 && !exon_clip(V, h, ex[2 * x], ex[2 * x + 1], &l2, &r2, &lo, &hi)) continue;
+                    const int m = hap_rows(V, h, lo, hi, rows);
+                    if (write) {
+                        const LocusJobs &J = R.jobs[locus];
+                        const int64_t hp = hap_cur[tb]++;
+                        J.hap_left[hp] = l2;
+                        J.hap_right[hp] = r2;
+                        J.hap_table[hp] = tb;
+                        for (int k = 0; k < m; k++) J.rows[row_cur[tb] + k] = rows[k];
+                        row_cur[tb] += m;
+                        J.row_off[hp + 1] = row_cur[tb];
+                    } else {
+                        kt_run[tb]++;
+                        rt[tb] += m;
+                    }
+                }
             }
         }
+    }
+    if (!FILL) {
+        for (int tb = 0; tb < 3; tb++) kt[tb] = kt_run[tb];
+        int n_small = 0;
+        int64_t kmax = 0;
+        for (int tb = 0; tb < T; tb++) {
+            if (kt[tb] > MAX_PAIR_HTS) {
+                set_error(R, i, E_PAIR_HTS);
+                return;
+            }
+            n_small += kt[tb] <= 7;
+            kmax = kt[tb] > kmax ? kt[tb] : kmax;
+        }
+        for (int tb = 0; tb < 3; tb++) R.pair_cnt[head_k * 3 + tb] = (int32_t)(kt[tb] | (rt[tb] << 8));
+        R.s_pairs[i] = 1;
+        R.s_haps[i] = kt[0] + kt[1] + kt[2];
+        R.s_rows[i] = rt[0] + rt[1] + rt[2];
+        R.s_small[i] = n_small;
+        R.s_big[i] = T - n_small;
+        hd_add_u64(&R.unit_pairs[u], 1ull);
+        hd_max_i32(R.max_job_haps, (int32_t)kmax);
     }
 }
 
