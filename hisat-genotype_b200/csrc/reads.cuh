@@ -237,7 +237,48 @@ __device__ __forceinline__ const char *stage_lines(Stage &s, const ReadsView &R,
     return s.smem - b;
 }
 
-__global__ void __launch_bounds__(STAGE_LINES) parse_kernel(ReadsView R, WalkParams P, int smem_bytes) {
+// ---- pileup (common:1100-1121) straight from the CIGAR text: warp per line, lanes over the bases of each M / D op ------------
+// one line of the pileup by one warp; `line` may point into the shared-memory image of the CTA's lines
+__device__ __forceinline__ void pileup_line(const ReadsView &R, int64_t r, const char *line, uint32_t *__restrict__ counts_all, int lane) {
+    const RecFields f = R.rec[r];
+    const char *cig = line + f.cig_off, *seq = line + f.seq_off;
+    const int u = R.unit[r];
+    const int L = R.loci[R.unit_locus[u]].L;
+    uint32_t *counts = counts_all + (size_t)R.unit_pos0[u] * 6;
+    int gpos = f.pos, rpos = 0, len = 0;
+    for (int k = 0; k < f.cig_len; k++) {
+        const char c = cig[k];  // same address in every lane: one broadcast load
+        if (c >= '0' && c <= '9') {
+            len = len * 10 + (c - '0');
+            continue;
+        }
+        if (c == 'M' || c == 'D') {
+            for (int j = lane; j < len; j += 32) {
+                const int g = gpos + j;
+                if (g < L) {
+                    int code = 5;
+                    if (c == 'M') {
+                        const char ch = rpos + j < f.seq_len ? seq[rpos + j] : 'N';
+                        code = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 4;
+                    }
+                    atomicAdd(&counts[(size_t)g * 6 + code], 1u);
+                }
+            }
+        }
+        if (c == 'M' || c == 'D' || c == 'N') gpos += len;
+        if (c == 'M' || c == 'I' || c == 'S') rpos += len;
+        len = 0;
+    }
+}
+__global__ void __launch_bounds__(256) pileup_text_kernel(ReadsView R, uint32_t *__restrict__ counts_all) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp0; r < R.n_lines; r += nwarps)
+        if (R.st[r] & ST_PU) pileup_line(R, r, R.text + R.line_off[r], counts_all, lane);
+}
+
+__global__ void __launch_bounds__(STAGE_LINES) parse_kernel(ReadsView R, WalkParams P, int smem_bytes, uint32_t *__restrict__ counts_all) {
     extern __shared__ __align__(128) char s_text[];
     __shared__ uint64_t mbar;
     Stage sg;
@@ -248,6 +289,14 @@ __global__ void __launch_bounds__(STAGE_LINES) parse_kernel(ReadsView R, WalkPar
         const char *base = stage_lines(sg, R, i0, i1);
         const int64_t i = i0 + threadIdx.x;
         if (i < i1) parse_line(R, P, base, i);
+        if (counts_all) {
+            // pileup of the same lines while their image is in shared memory (one pass over the text less): warp per line;
+            // the record fields written by the CTA's other threads are visible after the barrier
+            __syncthreads();
+            const int lane = threadIdx.x & 31;
+            for (int64_t r = i0 + (threadIdx.x >> 5); r < i1; r += STAGE_LINES / 32)
+                if (R.st[r] & ST_PU) pileup_line(R, r, base + R.line_off[r], counts_all, lane);
+        }
     }
 }
 __global__ void __launch_bounds__(256) head_kernel(ReadsView R) {
@@ -520,44 +569,5 @@ __global__ void locus_totals_kernel(ReadsView R, int n_loci, const int32_t *__re
     out[l * 6 + 5] = a;
 }
 
-// ---- pileup (common:1100-1121) straight from the CIGAR text: warp per line, lanes over the bases of each M / D op ------------
-__global__ void __launch_bounds__(256) pileup_text_kernel(ReadsView R, uint32_t *__restrict__ counts_all) {
-    const int lane = threadIdx.x & 31;
-    const int64_t warp0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
-    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = warp0; r < R.n_lines; r += nwarps) {
-        if (!(R.st[r] & ST_PU)) continue;
-        const RecFields f = R.rec[r];
-        const char *line = R.text + R.line_off[r];
-        const char *cig = line + f.cig_off, *seq = line + f.seq_off;
-        const int u = R.unit[r];
-        const int L = R.loci[R.unit_locus[u]].L;
-        uint32_t *counts = counts_all + (size_t)R.unit_pos0[u] * 6;
-        int gpos = f.pos, rpos = 0, len = 0;
-        for (int k = 0; k < f.cig_len; k++) {
-            const char c = cig[k];  // same address in every lane: one broadcast load
-            if (c >= '0' && c <= '9') {
-                len = len * 10 + (c - '0');
-                continue;
-            }
-            if (c == 'M' || c == 'D') {
-                for (int j = lane; j < len; j += 32) {
-                    const int g = gpos + j;
-                    if (g < L) {
-                        int code = 5;
-                        if (c == 'M') {
-                            const char ch = rpos + j < f.seq_len ? seq[rpos + j] : 'N';
-                            code = ch == 'A' ? 0 : ch == 'C' ? 1 : ch == 'G' ? 2 : ch == 'T' ? 3 : 4;
-                        }
-                        atomicAdd(&counts[(size_t)g * 6 + code], 1u);
-                    }
-                }
-            }
-            if (c == 'M' || c == 'D' || c == 'N') gpos += len;
-            if (c == 'M' || c == 'I' || c == 'S') rpos += len;
-            len = 0;
-        }
-    }
-}
 
 }  // namespace hgtk

@@ -1960,9 +1960,19 @@ static int reads_execute(hgt_batch *b, cudaStream_t st) {
     }
     const int stage_grid = (int)std::max<int64_t>(1, std::min<int64_t>((N + hgtk::STAGE_LINES - 1) / hgtk::STAGE_LINES,
                                                                      (int64_t)ctx->sm_count * stage_ctas));
-    hgtk::parse_kernel<<<stage_grid, hgtk::STAGE_LINES, stage_bytes, st>>>(R, P, stage_bytes);
-    hgtk::pileup_text_kernel<<<line_grid(ctx, N * 32, 256, 8), 256, 0, st>>>(R, rd.d_cnt.as<uint32_t>());
-    launches += 4;
+    // The pileup is its own pass (warp per line, 8 CTAs of 256 threads per SM).  HGT_PILEUP_FUSED=1 runs it inside the parse
+    // kernel on the shared-memory image of the lines - one pass over the text less (-0.5 GB of DRAM traffic per step), but
+    // SLOWER: the staged kernel holds 16 warps per SM and the histogram atomics need more in flight (records 1.65 vs 1.39 ms).
+    static const bool pileup_split = getenv("HGT_PILEUP_FUSED") == nullptr;
+    hgtk::parse_kernel<<<stage_grid, hgtk::STAGE_LINES, stage_bytes, st>>>(R, P, stage_bytes,
+                                                                            pileup_split ? nullptr : rd.d_cnt.as<uint32_t>());
+    if (pileup_split) {
+        hgtk::pileup_text_kernel<<<line_grid(ctx, N * 32, 256, 8), 256, 0, st>>>(R, rd.d_cnt.as<uint32_t>());
+        ctx->launches++;
+        launches++;
+    }
+    launches += 3;
+    ctx->launches -= 1;
     HGT_CUDA(cudaGetLastError());
     if (b->pileup_hook) {  // read-sharded locus: the caller sums the raw counts over ranks
         HGT_CUDA(cudaStreamSynchronize(st));
