@@ -266,3 +266,35 @@ def test_pipeline_matches_single_batches():
                 assert px == pytest.approx(py, rel=1e-9) and px == pytest.approx(pz, rel=1e-9)
     for t in loci:
         t.close()
+
+
+def test_batch_ragged_and_empty_units():
+    """Units of very different sizes in one batch - an empty one, a single record, an odd cut through a pair, a full
+    sample - and a malformed record: each unit's totals and tables equal the oracle's on the same lines; the malformed
+    batch is refused with the reference's assertion (HGT_ERR_PARSE), not typed."""
+    from hisatgenotype_b200 import _lib
+    from hisatgenotype_b200 import typing_core as TC
+    from hisatgenotype_b200.locus import LocusTables
+    from helpers import assert_tables_equal_oracle, synthetic_case
+    args, sam, truth = synthetic_case(41, 500, L=2500, n_pairs=400, base="hla", del_frac=0.1)
+    ol = O.OracleLocus(*args)
+    t = LocusTables(*args)
+    cuts = [[], sam[:1], sam[:7], sam, sam[100:101], sam[200:460]]
+    batch = TC.Batch([t], TC.make_params(), True)
+    for lines in cuts:
+        batch.add_unit(0, lines)
+    batch.run()
+    for u, lines in enumerate(cuts):
+        ref = O.type_locus(ol, lines, simulation=False)
+        s = batch.unit_summary(u)
+        assert s["num_reads"] == ref["num_reads"] and s["num_pairs"] == ref["num_pairs"], (u, s, ref["num_reads"])
+        assert_tables_equal_oracle(lambda tb: (list(map(list, batch.unit_gene_cmpt(u, tb).items())),
+                                               batch.unit_gene_counts(u, tb)), ref, ol, True)
+    batch.close()
+    bad = "\t".join(sam[3].split("\t")[:8])
+    batch = TC.Batch([t], TC.make_params(), True)
+    batch.add_unit(0, sam[:3] + [bad] + sam[4:20])
+    with pytest.raises((_lib.HgtError, AssertionError)):
+        batch.run()
+    batch.close()
+    t.close()
