@@ -309,38 +309,56 @@ class PeerGroup:
         return cls._cache[key]
 
 
+def gather_class_tables(bits, cnt, first, wp, group=None):
+    """All ranks' class tables, concatenated in rank order: (rows int64 [n_total * wp], count int64 [n_total], first int32
+    [n_total], n_total).  Inputs are torch tensors of this rank (any device the group's backend serves: CUDA under NCCL, CPU
+    under gloo - tests/test_dist_em.py); tables may have different lengths, also zero."""
+    import torch.distributed as dist
+    dev = bits.device
+    world = dist.get_world_size(group)
+    n = int(cnt.numel())
+    n_t = torch.tensor([n], dtype=torch.int64, device=dev)
+    n_all = [torch.zeros_like(n_t) for _ in range(world)]
+    dist.all_gather(n_all, n_t, group=group)
+    n_all = [int(x) for x in n_all]
+    n_max = max(max(n_all), 1)
+    p_bits = torch.zeros(n_max * wp, dtype=torch.int64, device=dev)
+    p_cnt = torch.zeros(n_max, dtype=torch.int64, device=dev)
+    p_first = torch.zeros(n_max, dtype=torch.int32, device=dev)
+    if n > 0:
+        p_bits[:n * wp] = bits.reshape(-1)
+        p_cnt[:n] = cnt
+        p_first[:n] = first
+    g_bits = [torch.empty_like(p_bits) for _ in range(world)]
+    g_cnt = [torch.empty_like(p_cnt) for _ in range(world)]
+    g_first = [torch.empty_like(p_first) for _ in range(world)]
+    dist.all_gather(g_bits, p_bits, group=group)
+    dist.all_gather(g_cnt, p_cnt, group=group)
+    dist.all_gather(g_first, p_first, group=group)
+    # drop the padding rows
+    return (torch.cat([g_bits[r][:n_all[r] * wp] for r in range(world)]), torch.cat([g_cnt[r][:n_all[r]] for r in range(world)]),
+            torch.cat([g_first[r][:n_all[r]] for r in range(world)]), sum(n_all))
+
+
 def merge_class_tables(A, wp, bits_ptr, cnt_ptr, first_ptr, n, key_offset, dev_index, group=None):
     """All ranks' class tables -> the rows this rank owns, duplicates merged (hgt_class_merge_dev).  Returns torch
-    tensors (rows int64 [m, wp], count int64 [m], first int32 [m]) and m.  The tables travel once per call with NCCL
+    tensors (rows int64 [m * wp], count int64 [m], first int32 [m]) and m.  The tables travel once per call with NCCL
     all_gather (bulk transfer: what NCCL is for); the latency-critical per-sweep exchange of the EM is the peer kernel."""
     import torch.distributed as dist
     dev = torch.device("cuda", dev_index)
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     n = int(n)
-    n_t = torch.tensor([n], dtype=torch.int64, device=dev)
-    n_all = torch.empty(world, dtype=torch.int64, device=dev)
-    dist.all_gather_into_tensor(n_all, n_t, group=group)
-    n_all = [int(x) for x in n_all.tolist()]
-    n_max = max(max(n_all), 1)
-    bits = torch.zeros(n_max * wp, dtype=torch.int64, device=dev)
-    cnt = torch.zeros(n_max, dtype=torch.int64, device=dev)
-    first = torch.zeros(n_max, dtype=torch.int32, device=dev)
     if n > 0:
-        bits[:n * wp] = _alias(bits_ptr, n * wp, "<i8", dev)
-        cnt[:n] = _alias(cnt_ptr, n, "<i8", dev)
-        first[:n] = _alias(first_ptr, n, "<i4", dev) + int(key_offset)
-    g_bits = torch.empty(world * n_max * wp, dtype=torch.int64, device=dev)
-    g_cnt = torch.empty(world * n_max, dtype=torch.int64, device=dev)
-    g_first = torch.empty(world * n_max, dtype=torch.int32, device=dev)
-    dist.all_gather_into_tensor(g_bits, bits, group=group)
-    dist.all_gather_into_tensor(g_cnt, cnt, group=group)
-    dist.all_gather_into_tensor(g_first, first, group=group)
-    if any(x != n_max for x in n_all):  # ragged: drop the padding rows
-        g_bits = torch.cat([g_bits[r * n_max * wp:(r * n_max + n_all[r]) * wp] for r in range(world)])
-        g_cnt = torch.cat([g_cnt[r * n_max:r * n_max + n_all[r]] for r in range(world)])
-        g_first = torch.cat([g_first[r * n_max:r * n_max + n_all[r]] for r in range(world)])
-    o_bits, o_cnt, o_first, m = merge_rows(g_bits, g_cnt, g_first, sum(n_all), A, wp, rank, world, dev_index)
+        bits = _alias(bits_ptr, n * wp, "<i8", dev)
+        cnt = _alias(cnt_ptr, n, "<i8", dev)
+        first = _alias(first_ptr, n, "<i4", dev) + int(key_offset)  # global pair indices
+    else:
+        bits = torch.zeros(0, dtype=torch.int64, device=dev)
+        cnt = torch.zeros(0, dtype=torch.int64, device=dev)
+        first = torch.zeros(0, dtype=torch.int32, device=dev)
+    g_bits, g_cnt, g_first, n_in = gather_class_tables(bits, cnt, first, wp, group)
+    o_bits, o_cnt, o_first, m = merge_rows(g_bits, g_cnt, g_first, n_in, A, wp, rank, world, dev_index)
     # rows in the order of their first pair (unique, = the reference's dict order): the kernel hands rows out in warp-scheduling
     # order, and the row order decides the floating-point association of the EM sums - sorted, a run repeats bit for bit
     order = torch.argsort(o_first[:m])
