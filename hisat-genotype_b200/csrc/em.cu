@@ -2346,13 +2346,17 @@ extern "C" int hgt_em_trace(hgt_ctx *ctx, int32_t enable, uint64_t *cycles16) {
 
 size_t hgt_em_args_bytes(int n_problems) { return align_up((size_t)n_problems * sizeof(EmArgs), 256); }
 
-bool hgt_em_wants_coop(const hgt_ctx *ctx, int C, int A, int wp, int A_live_max) {
+bool hgt_em_wants_coop(const hgt_ctx *ctx, int C, int A, int wp, int A_live_max, int n_problems) {
     EmArgs a;
     int na = 1;
     size_t smem = 0;
     const EmShape sh{C < 1 ? 1 : C, A, wp, A_live_max};
     if (em_plan_batched(ctx, sh, &a, &na, &smem) != HGT_OK) return false;
-    return !a.compact && (size_t)C * wp * 8 > ((size_t)4 << 20);
+    if (a.compact || C < 2) return false;
+    const size_t bytes = (size_t)C * wp * 8;
+    // cooperative launches run one after the other: worth it for a big matrix, or when there are too few problems to fill
+    // the SMs with one streaming CTA each
+    return bytes > ((size_t)4 << 20) || (n_problems <= 6 && bytes > ((size_t)256 << 10));
 }
 size_t hgt_em_coop_ws_bytes(const hgt_ctx *ctx, int A) { return em_ws_bytes(ctx->sm_count, A); }
 

@@ -25,8 +25,10 @@ struct EmDevProblem {
 
 size_t hgt_em_problem_ws_bytes(int wp);
 size_t hgt_em_args_bytes(int n_problems);
-// true when a problem of this shape is too large for one SM's shared memory and big enough to deserve the whole GPU
-bool hgt_em_wants_coop(const hgt_ctx *ctx, int C, int A, int wp, int A_live_max);
+// true when a problem of this shape is too large for one SM's shared memory and big enough to deserve the whole GPU - or
+// when the launch holds only a handful of problems (n_problems), so that one streaming CTA per problem would leave the
+// GPU idle (a single sample of 10 k single-end reads on a 7 k-allele locus: 15.5 ms on one SM)
+bool hgt_em_wants_coop(const hgt_ctx *ctx, int C, int A, int wp, int A_live_max, int n_problems);
 size_t hgt_em_coop_ws_bytes(const hgt_ctx *ctx, int A);
 // One CTA per problem, all problems of all loci in as few launches as the register variants need.  h_args: host
 // staging (pinned) and d_args: device copy, hgt_em_args_bytes(n_problems) each; h_args must stay untouched until the

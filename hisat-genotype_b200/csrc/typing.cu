@@ -2391,7 +2391,7 @@ static void launch_stage_a(hgt_batch *b, cudaStream_t st, LocusBatch &lb) {
 }
 
 // EM problems of one locus batch on table `table` for the listed local units, appended to `out`.
-static void em_problems(hgt_ctx *ctx, LocusBatch &lb, int table, const std::vector<int> &local_units, const int *c_max,
+static void em_problems(hgt_ctx *ctx, int n_launch, LocusBatch &lb, int table, const std::vector<int> &local_units, const int *c_max,
                         const int *a_live, const double *d_len, int remove_low, DevBuf &prob, DevBuf &inres, DevBuf &fk,
                         DevBuf &is, std::vector<EmDevProblem> *out) {
     const hgt_locus *loc = lb.loc;
@@ -2417,7 +2417,7 @@ static void em_problems(hgt_ctx *ctx, LocusBatch &lb, int table, const std::vect
         p.iters_status = is.as<int32_t>() + (size_t)i * 3;
         p.ws = static_cast<unsigned char *>(lb.d_emws.p) + (size_t)i * wsb;
         p.coop_ws = nullptr;
-        if (hgt_em_wants_coop(ctx, p.C_max, p.A, p.wp, p.A_live_max)) {
+        if (hgt_em_wants_coop(ctx, p.C_max, p.A, p.wp, p.A_live_max, n_launch)) {
             lb.d_coopws.emplace_back();
             if (lb.d_coopws.back().alloc(hgt_em_coop_ws_bytes(ctx, p.A)) == HGT_OK) p.coop_ws = lb.d_coopws.back().p;
         }
@@ -2512,7 +2512,7 @@ static int batch_execute(hgt_batch *b, cudaStream_t st) {
         all.resize(n_units); cmax.resize(n_units); alive.assign(n_units, lb.n_live[table]);
         std::iota(all.begin(), all.end(), 0);
         for (size_t i = 0; i < n_units; i++) cmax[i] = lb.ut_ncls[i * 4 + table];
-        em_problems(ctx, lb, table, all, cmax.data(), alive.data(), nullptr, loc->is_hla ? b->remove_low : 0, lb.d_prob, lb.d_inres,
+        em_problems(ctx, (int)b->units.size(), lb, table, all, cmax.data(), alive.data(), nullptr, loc->is_hla ? b->remove_low : 0, lb.d_prob, lb.d_inres,
                     lb.d_fk, lb.d_is, &probs);
     }
     if (!b->skip_em) {
@@ -2609,7 +2609,7 @@ static int batch_finish(hgt_batch *b, cudaStream_t st) {
             b->timer.end(2);
         }
         HGT_CUDA(cudaMemsetAsync(lb.d_is2.p, 0, n_units * 12, st));
-        em_problems(ctx, lb, 3, lu, cmax.data(), alive.data(), loc->d_allele_len, 1, lb.d_prob2, lb.d_inres2, lb.d_fk2, lb.d_is2,
+        em_problems(ctx, (int)b->units.size(), lb, 3, lu, cmax.data(), alive.data(), loc->d_allele_len, 1, lb.d_prob2, lb.d_inres2, lb.d_fk2, lb.d_is2,
                     &probs);
     }
     if (!probs.empty()) {
