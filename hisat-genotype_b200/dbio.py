@@ -188,3 +188,90 @@ def load_database(prefix):
             raise SystemExit("Error: index files missing (%s)" % path)
         db[ext] = open(path).read()
     return load_database_text(db)
+
+
+# ---- native reader (libhgt hgt_db_*, csrc/dbio.cpp): the same containers from the same files ---------------------------------
+_DB = dict(EXONS=0, VAR_TYPE=1, VAR_POS=2, VAR_IN_INDEX=3, HAP_RANGE=4, GENE=16, BACKBONE=17, VAR_ID=18, VAR_DATA=19, VAR_LINKS=20,
+           ALLELES=21, PARTIAL=22, HAP_ID=23, HAP_VARS=24)
+_TYPES = ["single", "deletion", "insertion"]
+
+
+def load_database_native(prefix):
+    """load_database(prefix) with the files parsed by libhgt (hgt_db_open ...): returns the same dict, plus "haplotypes"
+    (read_haplotypes form) and "index_vars" (read_index_variants form) when those files exist."""
+    import ctypes
+
+    import numpy as np
+
+    from . import _lib
+    L = _lib.lib()
+    L.hgt_db_open.restype = ctypes.c_int
+    L.hgt_db_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
+    L.hgt_db_close.restype = None
+    L.hgt_db_close.argtypes = [ctypes.c_void_p]
+    L.hgt_db_n_genes.restype = ctypes.c_int32
+    L.hgt_db_n_genes.argtypes = [ctypes.c_void_p]
+    L.hgt_db_sizes.restype = ctypes.c_int
+    L.hgt_db_sizes.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p]
+    L.hgt_db_ints.restype = ctypes.c_int
+    L.hgt_db_ints.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64]
+    L.hgt_db_text.restype = ctypes.c_int
+    L.hgt_db_text.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_char_p),
+                              ctypes.POINTER(ctypes.c_size_t)]
+    h = ctypes.c_void_p()
+    rc = L.hgt_db_open(prefix.encode(), ctypes.byref(h))
+    if rc == _lib.HGT_ERR_ARG and "index files missing" in _lib.last_error():
+        raise SystemExit(_lib.last_error())
+    _lib.check(rc)
+
+    def ints(g, what, n):
+        out = np.zeros(max(n, 1), np.int64)
+        _lib.check(L.hgt_db_ints(h, g, _DB[what], out.ctypes.data_as(ctypes.c_void_p), n))
+        return out[:n].tolist()
+
+    def text(g, what, strip=True):
+        p, n = ctypes.c_char_p(), ctypes.c_size_t(0)
+        _lib.check(L.hgt_db_text(h, g, _DB[what], ctypes.byref(p), ctypes.byref(n)))
+        s = ctypes.string_at(p, n.value).decode()
+        if what == "BACKBONE":
+            return s
+        return s.split("\n")[:-1] if s else []
+
+    try:
+        refGenes, refGene_loci, Vars, Var_list, Links, Genes = {}, {}, {}, {}, {}, {}
+        alleles, partial, haplotypes, index_vars = [], set(), {}, {}
+        for g in range(L.hgt_db_n_genes(h)):
+            sz = (ctypes.c_int64 * 8)()
+            _lib.check(L.hgt_db_sizes(h, g, sz))
+            n_seq, n_ex, n_var, n_al, n_pa, n_hap, left, right = list(sz)
+            gene, name, chrom, _strand = text(g, "GENE")
+            ex = ints(g, "EXONS", 3 * n_ex)
+            exons = [[ex[3 * k], ex[3 * k + 1]] for k in range(n_ex)]
+            primary = [[ex[3 * k], ex[3 * k + 1]] for k in range(n_ex) if ex[3 * k + 2]]
+            refGenes[gene] = name
+            refGene_loci[gene] = [name, chrom, left, right, exons, primary]
+            Genes[gene] = {name: text(g, "BACKBONE")}
+            ids, data = text(g, "VAR_ID"), text(g, "VAR_DATA")
+            types, pos, in_idx = ints(g, "VAR_TYPE", n_var), ints(g, "VAR_POS", n_var), ints(g, "VAR_IN_INDEX", n_var)
+            Vars[gene] = {ids[k]: [_TYPES[types[k]], pos[k], data[k]] for k in range(n_var)}
+            Var_list[gene] = [[pos[k], ids[k]] for k in range(n_var)]
+            for k, line in enumerate(text(g, "VAR_LINKS")):
+                if line:
+                    Links[ids[k]] = line.split(" ")
+            alleles += text(g, "ALLELES")
+            partial |= set(text(g, "PARTIAL"))
+            if n_hap:
+                rng, hid, hv = ints(g, "HAP_RANGE", 2 * n_hap), text(g, "HAP_ID"), text(g, "HAP_VARS")
+                haplotypes[gene] = [[hid[k], rng[2 * k], rng[2 * k + 1], [v for v in hv[k].split(",") if v]] for k in range(n_hap)]
+            if any(in_idx):
+                index_vars[gene] = {ids[k] for k in range(n_var) if in_idx[k]}
+    finally:
+        L.hgt_db_close(h)
+    Gene_names, Gene_lengths = build_genes(Genes, Vars, Var_list, Links, alleles)
+    out = dict(refGenes=refGenes, refGene_loci=refGene_loci, Vars=Vars, Var_list=Var_list, Links=Links, Genes=Genes,
+               Gene_names=Gene_names, Gene_lengths=Gene_lengths, partial_alleles=partial)
+    if haplotypes:
+        out["haplotypes"] = haplotypes
+    if index_vars:
+        out["index_vars"] = index_vars
+    return out

@@ -371,6 +371,32 @@ int hgt_walk_table(const hgt_walk *w, int32_t table, int64_t *job_off, int32_t *
                    int64_t *row_off, int32_t *rows);
 void hgt_walk_free(hgt_walk *w);
 
+/* ---- (f)-2: typing database text files, native reader -------------------------------------------------------
+ * Reads what genotyping_locus reads (core:2417-2485 through common:279-309 read_locus, :313-334 read_backbone_alleles,
+ * :339-368 read_variants, :388-403 read_links) - <prefix>_backbone.fa, .locus, .snp, .link, .allele, .partial - and, when
+ * present, the index-side files .index.snp and .haplotype (formats: process.py:1055-1063, 1088-1106, 1215-1220, 1242-1244).
+ * A missing mandatory file gives HGT_ERR_ARG with the reference's message ("index files missing", common:572-575), a
+ * malformed line HGT_ERR_PARSE (the reference would fail an assert or a split).  Genes come in .locus order; the variants
+ * of a gene in Var_list order (by position, file order inside one position).
+ * hgt_db_sizes: out = backbone length, exons, variants, .allele entries, .partial entries, haplotypes, locus left, right.
+ * hgt_db_ints copies one numeric table (at most `cap` values): EXONS = (left, right, primary) triples, VAR_TYPE = 0 single /
+ * 1 deletion / 2 insertion, HAP_RANGE = (left, right) pairs.  hgt_db_text returns one string table as '\n'-terminated
+ * entries (BACKBONE: the bare sequence; GENE: gene, backbone name, chromosome, strand; VAR_LINKS: the allele names of each
+ * variant, blank separated, an empty line for a variant without a .link line; HAP_VARS: comma separated variant ids); the
+ * pointer stays valid until the next hgt_db_text call on the handle. */
+typedef struct hgt_db hgt_db;
+enum {
+    HGT_DB_EXONS = 0, HGT_DB_VAR_TYPE = 1, HGT_DB_VAR_POS = 2, HGT_DB_VAR_IN_INDEX = 3, HGT_DB_HAP_RANGE = 4,
+    HGT_DB_GENE = 16, HGT_DB_BACKBONE = 17, HGT_DB_VAR_ID = 18, HGT_DB_VAR_DATA = 19, HGT_DB_VAR_LINKS = 20,
+    HGT_DB_ALLELES = 21, HGT_DB_PARTIAL = 22, HGT_DB_HAP_ID = 23, HGT_DB_HAP_VARS = 24
+};
+int hgt_db_open(const char *prefix, hgt_db **out);
+void hgt_db_close(hgt_db *db);
+int32_t hgt_db_n_genes(const hgt_db *db);
+int hgt_db_sizes(const hgt_db *db, int32_t gene, int64_t out[8]);
+int hgt_db_ints(const hgt_db *db, int32_t gene, int32_t what, int64_t *out, int64_t cap);
+int hgt_db_text(hgt_db *db, int32_t gene, int32_t what, const char **text, size_t *n_bytes);
+
 #ifdef __cplusplus
 }
 #endif

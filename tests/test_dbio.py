@@ -33,3 +33,47 @@ def test_haplotype_and_index_snp_files(tmp_path):
             assert v in d["Vars"]["A"]
             assert left <= d["Vars"]["A"][v][1] <= right
     assert idx["A"] <= set(d["Vars"]["A"]) and len(idx["A"]) > 0
+
+
+def _write_files(texts, prefix):
+    for ext, text in texts.items():
+        with open(prefix + ext, "w") as f:
+            f.write(text)
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES)
+def test_native_reader_matches_python_on_goldens(name, tmp_path):
+    """hgt_db_* (csrc/dbio.cpp) against the Python readers on the databases of the reference-captured goldens."""
+    from hisatgenotype_b200 import dbio
+    d = golden_db(load_golden(name))
+    prefix = os.path.join(str(tmp_path), "db")
+    _write_files(dbio.write_database_text(d), prefix)
+    py = dbio.load_database(prefix)
+    nat = dbio.load_database_native(prefix)
+    for k in ("refGenes", "refGene_loci", "Vars", "Var_list", "Links", "Genes", "Gene_names", "Gene_lengths", "partial_alleles"):
+        assert nat[k] == py[k], k
+
+
+def test_native_reader_index_files_and_errors(tmp_path):
+    from hisatgenotype_b200 import _lib, dbio, synth
+    loc = synth.make_locus("A", 5, L=900, n_alleles=20, n_groups=4, core_vars=12, pool_private=20, del_frac=0.2)
+    loc2 = synth.make_locus("DQA1", 6, L=700, n_alleles=8, n_groups=2, core_vars=8, pool_private=10, del_frac=0.1)
+    synth.write_database([loc, loc2], "hla", str(tmp_path))
+    prefix = os.path.join(str(tmp_path), "hla")
+    py = dbio.load_database(prefix)
+    nat = dbio.load_database_native(prefix)
+    for k in ("refGenes", "refGene_loci", "Vars", "Var_list", "Links", "Genes", "Gene_names", "Gene_lengths", "partial_alleles"):
+        assert nat[k] == py[k], k
+    assert nat["haplotypes"] == dbio.read_haplotypes(open(prefix + ".haplotype").read())
+    assert nat["index_vars"] == dbio.read_index_variants(open(prefix + ".index.snp").read())
+    # a missing mandatory file: the reference's message and exit (common:572-575)
+    os.remove(prefix + ".link")
+    with pytest.raises(SystemExit) as e:
+        dbio.load_database_native(prefix)
+    assert "index files missing" in str(e.value)
+    # a malformed .snp line is refused
+    open(prefix + ".link", "w").write("")
+    with open(prefix + ".snp", "a") as f:
+        f.write("hv999999\tsingle\tA*BACKBONE\tnot_a_number\tC\n")
+    with pytest.raises(_lib.HgtError):
+        dbio.load_database_native(prefix)
