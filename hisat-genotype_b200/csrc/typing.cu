@@ -1,12 +1,13 @@
 // Stage (a): per-read allele compatibility -> Gene_cmpt / Gene_counts, on the GPU.
 //
 // Replaces the per-read loop of typing() (reference hisatgenotype_typing_core.py:598-1596) and get_mpileup
-// (hisatgenotype_typing_common.py:1059-1184).  Split of work:
-//   host  (walk.hpp)   text intake, filters, CIGAR x MD x Zs walk, error correction, ambiguity expansion, exon
-//                      clipping  ->  per pair and table a list of haplotypes (left, right, sorted variant rows)
-//   GPU   (this file)  pileup histogram + nt_set; haplotype -> allele bitset (add_count, core:626-677);
-//                      per-pair arg-max class (add_stat, core:1171-1236); class de-duplication into
-//                      (bitset, count, first-seen) tables; Gene_counts.
+// (hisatgenotype_typing_common.py:1059-1184).  Everything runs on the GPU once the alignment text has been copied:
+//   record stage (reads.cuh / walk_dev.cuh)  line index, parse, pileup histogram + nt_set, run heads / mate de-dup, CIGAR x
+//                      MD x Zs walk, error correction, ambiguity expansion, exon clipping  ->  per pair and table a list of
+//                      haplotypes (left, right, sorted variant rows)
+//   set stage (this file)  haplotype -> allele bitset (add_count, core:626-677); per-pair arg-max class (add_stat,
+//                      core:1171-1236); class de-duplication into (bitset, count, first-seen) tables; Gene_counts.
+// walk.hpp only holds the host-side description of a locus (hgt_locus_create -> build_walk_tables).
 //
 // HBM layout per locus (built once by hgt_locus_create):
 //   var_pos[V] int32 (Var_list order), delr_{right,row}[D] deletions sorted by right end,
