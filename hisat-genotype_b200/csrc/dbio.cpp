@@ -311,3 +311,57 @@ extern "C" int hgt_db_text(hgt_db *db, int32_t g, int32_t what, const char **tex
     *n_bytes = s.size();
     return HGT_OK;
 }
+
+// Writes the handle's tables back as database files (the formats of process.py:1055-1106, 1215-1220, 1242-1244): variants
+// in Var_list order, one .link line per variant that has alleles, 60-column FASTA, .index.snp / .haplotype only when the
+// handle holds such entries.  hgt_db_open(prefix_out) then gives the same tables.
+extern "C" int hgt_db_write(const hgt_db *db, const char *prefix) {
+    if (!db || !prefix) {
+        hgt_set_error("hgt_db_write: null argument");
+        return HGT_ERR_ARG;
+    }
+    static const char *type_name[3] = {"single", "deletion", "insertion"};
+    std::ostringstream locus, snp, isnp, link, bb, allele, partial, hap;
+    bool any_index = false, any_hap = false;
+    for (const Gene &g : db->genes) {
+        locus << g.name << '\t' << g.chrom << '\t' << g.left << '\t' << g.right << '\t' << (g.length ? g.length : (int64_t)g.seq.size())
+              << '\t';
+        for (size_t k = 0; k + 2 < g.exons.size(); k += 3) {
+            if (k) locus << ',';
+            locus << g.exons[k] << '-' << g.exons[k + 1] << (g.exons[k + 2] ? "p" : "");
+        }
+        locus << '\t' << g.strand << '\n';
+        bb << '>' << g.name << '\n';
+        for (size_t k = 0; k < g.seq.size(); k += 60) bb << g.seq.substr(k, 60) << '\n';
+        for (size_t k = 0; k < g.vars.size(); k++) {
+            const Variant &v = g.vars[k];
+            std::ostringstream line;
+            line << v.id << '\t' << type_name[v.type] << '\t' << g.name << '\t' << v.pos << '\t' << v.data << '\n';
+            snp << line.str();
+            if (v.in_index) {
+                isnp << line.str();
+                any_index = true;
+            }
+            if (!g.links[k].empty()) link << v.id << '\t' << g.links[k] << '\n';
+        }
+        for (const std::string &a : g.alleles) allele << a << '\n';
+        for (const std::string &a : g.partial) partial << a << '\n';
+        for (const Haplotype &h : g.haps) {
+            hap << h.id << '\t' << g.name << '\t' << h.left << '\t' << h.right << '\t' << h.ids << '\n';
+            any_hap = true;
+        }
+    }
+    const std::string p(prefix);
+    const struct { const char *ext; std::string text; bool write; } files[] = {
+        {".locus", locus.str(), true},   {".snp", snp.str(), true},         {".index.snp", isnp.str(), any_index}, {".link", link.str(), true},
+        {"_backbone.fa", bb.str(), true}, {".allele", allele.str(), true}, {".partial", partial.str(), true},     {".haplotype", hap.str(), any_hap}};
+    for (const auto &f : files) {
+        if (!f.write) continue;
+        std::ofstream out(p + f.ext, std::ios::binary);
+        if (!out || !(out << f.text)) {
+            hgt_set_error("hgt_db_write: cannot write %s%s", prefix, f.ext);
+            return HGT_ERR_ARG;
+        }
+    }
+    return HGT_OK;
+}

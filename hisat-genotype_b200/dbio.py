@@ -275,3 +275,24 @@ def load_database_native(prefix):
     if index_vars:
         out["index_vars"] = index_vars
     return out
+
+
+def copy_database_native(prefix_in, prefix_out):
+    """Read the database files with the native reader and write them back with the native writer (hgt_db_open ->
+    hgt_db_write): the canonical form of the same tables (variants in Var_list order, 60-column FASTA)."""
+    import ctypes
+
+    from . import _lib
+    L = _lib.lib()
+    L.hgt_db_open.restype = ctypes.c_int
+    L.hgt_db_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(ctypes.c_void_p)]
+    L.hgt_db_write.restype = ctypes.c_int
+    L.hgt_db_write.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+    L.hgt_db_close.restype = None
+    L.hgt_db_close.argtypes = [ctypes.c_void_p]
+    h = ctypes.c_void_p()
+    _lib.check(L.hgt_db_open(prefix_in.encode(), ctypes.byref(h)))
+    try:
+        _lib.check(L.hgt_db_write(h, prefix_out.encode()))
+    finally:
+        L.hgt_db_close(h)

@@ -396,6 +396,9 @@ int32_t hgt_db_n_genes(const hgt_db *db);
 int hgt_db_sizes(const hgt_db *db, int32_t gene, int64_t out[8]);
 int hgt_db_ints(const hgt_db *db, int32_t gene, int32_t what, int64_t *out, int64_t cap);
 int hgt_db_text(hgt_db *db, int32_t gene, int32_t what, const char **text, size_t *n_bytes);
+/* The writer of the same formats: the handle's tables as <prefix>.locus, .snp, .link, _backbone.fa, .allele, .partial (and
+ * .index.snp / .haplotype when the handle holds such entries); hgt_db_open(prefix) reads the same tables back. */
+int hgt_db_write(const hgt_db *db, const char *prefix);
 
 #ifdef __cplusplus
 }
