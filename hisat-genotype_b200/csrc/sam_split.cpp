@@ -22,11 +22,13 @@ struct hgt_sam_split {
         uint32_t len;       // including the newline (one is added for a last line without)
         uint32_t name_len;
         int32_t pos;
+        uint32_t q_off, q_len;  // QUAL column (11th) inside the line; q_len = 0: absent or kept as it is
     };
     std::vector<std::vector<Rec>> bucket;  // per reference, ordered
     std::vector<size_t> bytes;
     bool last_needs_newline = false;
     uint64_t last_off = 0;
+    bool drop_qual = false;  // write '*' for the QUAL column (the typing path never reads it: 27 % of a 2x100 bp record)
 };
 
 namespace {
@@ -55,6 +57,11 @@ void run_threads(int n_threads, size_t n, F f) {
 
 extern "C" int hgt_sam_split_create(const char *sam_text, size_t n_bytes, int32_t n_refs, const char *const *ref_names,
                                     int32_t n_threads, hgt_sam_split **out) {
+    return hgt_sam_split_create_opts(sam_text, n_bytes, n_refs, ref_names, n_threads, 0, out);
+}
+
+extern "C" int hgt_sam_split_create_opts(const char *sam_text, size_t n_bytes, int32_t n_refs, const char *const *ref_names,
+                                         int32_t n_threads, int32_t flags, hgt_sam_split **out) {
     if (!out || (!sam_text && n_bytes) || n_refs < 1 || !ref_names) {
         hgt_set_error("hgt_sam_split_create: bad argument");
         return HGT_ERR_ARG;
@@ -68,6 +75,8 @@ extern "C" int hgt_sam_split_create(const char *sam_text, size_t n_bytes, int32_
     for (int r = 0; r < n_refs; r++) ref_index[ref_names[r]] = r;
     hgt_sam_split *s = new hgt_sam_split();
     s->text = sam_text;
+    s->drop_qual = (flags & HGT_SPLIT_DROP_QUAL) != 0;
+    const bool drop_qual = s->drop_qual;
     s->bucket.resize((size_t)n_refs);
     s->bytes.assign((size_t)n_refs, 0);
     // pass 1: slices of the text (cut at newlines) -> records per slice and reference
@@ -108,9 +117,21 @@ extern "C" int hgt_sam_split_create(const char *sam_text, size_t n_bytes, int32_
                             pos = pos * 10 + (*c - '0');
                             if (pos > 2000000000) ok = false;
                         }
+                        uint32_t q_off = 0, q_len = 0;
+                        if (ok && drop_qual) {  // columns 5 .. 10 follow POS; QUAL is the 11th
+                            const char *t = t4;
+                            for (int col = 5; col <= 10 && t; col++) t = (const char *)memchr(t + 1, '\t', (size_t)(ln + n - t - 1));
+                            if (t) {
+                                const char *qe = (const char *)memchr(t + 1, '\t', (size_t)(ln + n - t - 1));
+                                if (!qe) qe = ln + n;
+                                q_off = (uint32_t)(t + 1 - ln);
+                                q_len = (uint32_t)(qe - (t + 1));
+                                if (q_len <= 1) q_len = 0;  // already '*' (or empty): nothing to save
+                            }
+                        }
                         if (!ok) bad.store(1);
                         else
-                            part[k][(size_t)it->second].push_back({(uint64_t)p, (uint32_t)(n + 1), (uint32_t)(t1 - ln), (int32_t)pos});
+                            part[k][(size_t)it->second].push_back({(uint64_t)p, (uint32_t)(n + 1), (uint32_t)(t1 - ln), (int32_t)pos, q_off, q_len});
                     }
                 }
             }
@@ -139,7 +160,7 @@ extern "C" int hgt_sam_split_create(const char *sam_text, size_t n_bytes, int32_
             return x.pos < y.pos;
         });
         size_t bytes = 0;
-        for (const auto &rec : b) bytes += rec.len;
+        for (const auto &rec : b) bytes += rec.len - (rec.q_len ? rec.q_len - 1 : 0);
         s->bytes[r] = bytes;
     });
     *out = s;
@@ -162,9 +183,20 @@ extern "C" int hgt_sam_split_write(const hgt_sam_split *s, int32_t ref, char *ds
     }
     char *o = dst;
     for (const auto &rec : s->bucket[(size_t)ref]) {
-        memcpy(o, s->text + rec.off, rec.len - 1);
-        o[rec.len - 1] = '\n';
-        o += rec.len;
+        const char *ln = s->text + rec.off;
+        if (rec.q_len) {  // QUAL column replaced by '*'
+            memcpy(o, ln, rec.q_off);
+            o += rec.q_off;
+            *o++ = '*';
+            const size_t rest = rec.len - 1 - rec.q_off - rec.q_len;
+            memcpy(o, ln + rec.q_off + rec.q_len, rest);
+            o += rest;
+            *o++ = '\n';
+        } else {
+            memcpy(o, ln, rec.len - 1);
+            o[rec.len - 1] = '\n';
+            o += rec.len;
+        }
     }
     return HGT_OK;
 }

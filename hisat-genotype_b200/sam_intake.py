@@ -12,9 +12,10 @@ import numpy as np
 from . import _lib
 
 
-def split_sam(sam_text, ref_names, n_threads=0, pinned=None):
+def split_sam(sam_text, ref_names, n_threads=0, pinned=None, drop_qual=False):
     """sam_text: bytes of SAM (headers allowed, any record order).  ref_names: backbone names (RNAME), e.g. "A*BACKBONE".
-    Returns {ref_name: bytes}, or with pinned=_lib.PinnedText {ref_name: (address, n_bytes)} written into it."""
+    Returns {ref_name: bytes}, or with pinned=_lib.PinnedText {ref_name: (address, n_bytes)} written into it.
+    drop_qual: write '*' for the QUAL column (never read by typing; 27 % fewer bytes to copy to the GPU for 2x100 bp records)."""
     if isinstance(sam_text, str):
         sam_text = sam_text.encode()
     L = _lib.lib()
@@ -22,7 +23,10 @@ def split_sam(sam_text, ref_names, n_threads=0, pinned=None):
     enc = [r.encode() for r in ref_names]
     arr = (ctypes.c_char_p * n)(*enc)
     h = ctypes.c_void_p()
-    rc = L.hgt_sam_split_create(sam_text, len(sam_text), n, arr, int(n_threads), ctypes.byref(h))
+    L.hgt_sam_split_create_opts.restype = ctypes.c_int
+    L.hgt_sam_split_create_opts.argtypes = [ctypes.c_char_p, ctypes.c_size_t, ctypes.c_int32, ctypes.POINTER(ctypes.c_char_p),
+                                            ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(ctypes.c_void_p)]
+    rc = L.hgt_sam_split_create_opts(sam_text, len(sam_text), n, arr, int(n_threads), 1 if drop_qual else 0, ctypes.byref(h))
     if rc == _lib.HGT_ERR_PARSE:
         raise AssertionError(_lib.last_error())
     _lib.check(rc)

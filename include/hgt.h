@@ -353,6 +353,12 @@ int hgt_batch_abundances(const hgt_batch *b, int32_t cap, int32_t *allele, doubl
 typedef struct hgt_sam_split hgt_sam_split;
 int hgt_sam_split_create(const char *sam_text, size_t n_bytes, int32_t n_refs, const char *const *ref_names,
                          int32_t n_threads, hgt_sam_split **out);
+/* The same with options: HGT_SPLIT_DROP_QUAL writes '*' for the QUAL column of every record (legal SAM; the typing path
+ * - the reference's and this one - never reads base qualities, and the column is 27 % of a 2x100 bp record that would
+ * otherwise travel to the GPU). */
+enum { HGT_SPLIT_DROP_QUAL = 1 };
+int hgt_sam_split_create_opts(const char *sam_text, size_t n_bytes, int32_t n_refs, const char *const *ref_names,
+                              int32_t n_threads, int32_t flags, hgt_sam_split **out);
 int hgt_sam_split_sizes(const hgt_sam_split *s, size_t *bytes_per_ref, int64_t *lines_per_ref);
 int hgt_sam_split_write(const hgt_sam_split *s, int32_t ref, char *dst);
 void hgt_sam_split_free(hgt_sam_split *s);

@@ -64,3 +64,43 @@ def test_split_rejects_malformed_and_handles_empty():
         split_sam(b"read1\t99\tX\n", ["X"])
     with pytest.raises(AssertionError):
         split_sam(b"read1\t99\tX\tabc\t60\n", ["X"])
+
+
+@pytest.mark.parametrize("name", GOLDEN_NAMES[:3])
+def test_split_drop_qual(name):
+    """drop_qual: every record keeps its columns except QUAL, which becomes '*'; records without a QUAL column or with '*'
+    already are untouched; and the record stage does not care (same tables from the host emulation of the device code)."""
+    import hgt_oracle as O
+    from helpers import golden_db, pileup_arrays, product_locus, tables_from_jobs, oracle_locus
+    from hisatgenotype_b200.sam_intake import split_sam
+    from hisatgenotype_b200.typing_core import HostWalk, make_params
+    g = load_golden(name)
+    p = g["params"]
+    n_loci = len(p["loci"])
+    caps = g["loci"][:n_loci]
+    text = "\n".join(coordinate_sorted(caps)) + "\n"
+    refs = [c["ref_allele"] for c in caps]
+    out = split_sam(text.encode(), refs, n_threads=2, drop_qual=True)
+    db = golden_db(g)
+    saved = 0
+    for c in caps:
+        got = out[c["ref_allele"]].decode().splitlines()
+        assert len(got) == len(c["sam"])
+        for a, b in zip(got, c["sam"]):
+            ca, cb = a.split("\t"), b.split("\t")
+            assert ca[:10] == cb[:10] and ca[11:] == cb[11:] and ca[10] == "*"
+            saved += len(b) - len(a)
+        # the device code's host emulation on the stripped lines: same haplotype jobs -> same tables as the reference
+        loc = oracle_locus(g, db, c["gene"], c["Gene_names"])
+        counts, nt_sets = O.get_mpileup(got, len(loc.ref_seq), 0, p["discordant"])
+        cnt, mask = pileup_arrays(counts, nt_sets)
+        t = product_locus(g, db, c["gene"], c["Gene_names"], host_only=True)
+        walk = HostWalk(t, got, make_params(p["num_editdist"], p["error_correction"], p["discordant"], p["simulation"]), cnt, mask)
+        res = tables_from_jobs(loc, walk, p["base"] == "hla")
+        assert walk.num_reads == c["num_reads"] and walk.num_pairs == c["num_pairs"]
+        assert res[0][0] == c["Gene_cmpt"] and res[0][1] == c["Gene_counts"]
+        t.close()
+    assert saved > 0
+    # no QUAL column at all / already '*': nothing changes
+    short = b"r1\t0\tX\t5\t60\t4M\t*\t0\t0\tACGT\n" b"r2\t0\tX\t7\t60\t4M\t*\t0\t0\tACGT\t*\tNM:i:0\n"
+    assert split_sam(short, ["X"], drop_qual=True)["X"] == short
